@@ -1,0 +1,110 @@
+/* sdslgpu.h — C ABI of the B200-native rank/select + wavelet-tree + FM-index query engine.
+ *
+ * This is the drop-in boundary for the hot path named in BASELINE.json.  The
+ * reference (xxsds/sdsl-lite 3.0.5) has no FFI of its own — it is a header-only template library
+ * whose composition points are duck-typed concepts — so every entry point below cites the
+ * reference member function(s) it replaces (paths relative to /root/reference/include/sdsl/).
+ * The SDSL-shaped C++ classes on top of this ABI live in sdsl-lite_b200/include/sdsl_b200.hpp;
+ * the binding a maintainer of the reference would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C types only; handles are opaque; no function throws or aborts;
+ *  - every function returns a status: SDSLGPU_OK (0) or a negative SDSLGPU_E* code;
+ *    sdslgpu_last_error() returns a thread-local message for the last failure;
+ *  - batch calls take n inputs and write n outputs in the same order;
+ *  - input/output pointers may be HOST or DEVICE pointers (detected per pointer with
+ *    cudaPointerGetAttributes).  Device pointers must live on the handle's device; the call is
+ *    then asynchronous on `stream`.  Host pointers are staged through pinned buffers in chunks
+ *    (H2D, kernel and D2H overlapped) and the call returns after the results are in `out`;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream);
+ *  - the SDSL preconditions that are undefined behaviour in the reference (rank idx > size,
+ *    select i == 0 or i > #args) are DEFINED here: the result for that query is
+ *    SDSLGPU_NPOS (all ones) and the call still returns SDSLGPU_OK;
+ *  - there is NO CPU fallback: without a CUDA device every create call fails with SDSLGPU_ECUDA.
+ */
+#ifndef SDSLGPU_H
+#define SDSLGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDSLGPU_OK 0
+#define SDSLGPU_EINVAL (-1)   /* bad argument (null pointer, unknown kind/pattern, malformed blob) */
+#define SDSLGPU_ENOMEM (-2)   /* host or device allocation failed */
+#define SDSLGPU_ECUDA (-3)    /* CUDA runtime error (no device, launch failure, ...) */
+#define SDSLGPU_ENOTSUP (-4)  /* operation not supported by this handle kind */
+#define SDSLGPU_NPOS UINT64_MAX
+
+/* handle kinds (sdslgpu_kind) */
+#define SDSLGPU_KIND_BV 1       /* bit_vector + rank_support_v<b> + select_support_mcl<b>           */
+#define SDSLGPU_KIND_RRR63 2    /* rrr_vector<63> + rank_support_rrr + select_support_rrr            */
+#define SDSLGPU_KIND_SD 3       /* sd_vector<> + rank_support_sd + select_support_sd                 */
+#define SDSLGPU_KIND_WT_HUFF 4  /* wt_huff<>                                                         */
+#define SDSLGPU_KIND_WT_INT 5   /* wt_int<>                                                          */
+#define SDSLGPU_KIND_CSA_WT 6   /* csa_wt<wt_huff<>, 32, 64, sa_order_sa_sampling<>, isa_sampling<>> */
+
+/* creation flags */
+#define SDSLGPU_F_DEFAULT 0u
+#define SDSLGPU_F_SDSL_LAYOUT 1u /* additionally keep SDSL's own device layout (plain words + the
+                                    rank_support_v m_basic_block table) and answer rank from it; the
+                                    default is the sector-interleaved B200 layout */
+#define SDSLGPU_F_NO_SELECT 2u   /* skip building the select samples (rank-only handle) */
+
+typedef struct sdslgpu_handle sdslgpu_handle;
+
+/* ---- library ------------------------------------------------------------------------------- */
+const char *sdslgpu_version(void);
+const char *sdslgpu_last_error(void);
+int sdslgpu_device_count(int *count);
+
+/* ---- creation / destruction ---------------------------------------------------------------- */
+
+/* Replaces: bit_vector(words) + rank_support_v<1>/<0> ctor (rank_support_v.hpp:72-122) +
+ * select_support_mcl<1>/<0> ctor (select_support_mcl.hpp:121-128).  `words` holds ceil(nbits/64)
+ * little-endian 64-bit words, bit i = (words[i>>6] >> (i&63)) & 1 (int_vector.hpp:1900-1904); bits
+ * past nbits in the last word are ignored.  All supports are built on the device. */
+int sdslgpu_bv_create(const uint64_t *words, uint64_t nbits, int device, uint32_t flags, sdslgpu_handle **out);
+
+int sdslgpu_free(sdslgpu_handle *h);
+int sdslgpu_kind(const sdslgpu_handle *h, int *kind);
+/* size(): number of bits (bit vectors) / symbols (wavelet trees) / text length + 1 (csa) */
+int sdslgpu_size(const sdslgpu_handle *h, uint64_t *size);
+/* number of b-bits in a bit-vector handle (= rank_b(size)); select domain is 1..arg_count */
+int sdslgpu_arg_count(const sdslgpu_handle *h, int b, uint64_t *count);
+/* bytes of device memory held by the handle */
+int sdslgpu_device_bytes(const sdslgpu_handle *h, uint64_t *bytes);
+
+/* ---- batched queries on bit vectors --------------------------------------------------------- */
+
+/* out[k] = number of b-bits in [0, idx[k]),  0 <= idx[k] <= size.
+ * Replaces rank_support_v<b,1>::rank (rank_support_v.hpp:129-139),
+ *          rank_support_rrr<b,63>::rank (rrr_vector.hpp:503-544),
+ *          rank_support_sd<b>::rank (sd_vector.hpp:553-575).   b in {0,1}. */
+int sdslgpu_rank(const sdslgpu_handle *h, int b, const uint64_t *idx, uint64_t n, uint64_t *out, void *stream);
+
+/* out[k] = position of the i[k]-th b-bit, 1 <= i[k] <= arg_count(b).
+ * Replaces select_support_mcl<b,1>::select (select_support_mcl.hpp:384-439),
+ *          select_support_rrr<b,63>::select (rrr_vector.hpp:639-726),
+ *          select_support_sd<b>::select (sd_vector.hpp:621-664). */
+int sdslgpu_select(const sdslgpu_handle *h, int b, const uint64_t *i, uint64_t n, uint64_t *out, void *stream);
+
+/* out[k] = bit idx[k] (0/1), 0 <= idx[k] < size.  Replaces operator[] of bit_vector
+ * (int_vector.hpp:1900-1904), rrr_vector (rrr_vector.hpp:276-298), sd_vector (sd_vector.hpp:328-349). */
+int sdslgpu_access(const sdslgpu_handle *h, const uint64_t *idx, uint64_t n, uint64_t *out, void *stream);
+
+/* ---- construction parity / interchange ------------------------------------------------------ */
+
+/* Copies the SDSL-format serialisation of one component of a KIND_BV handle into `buf`
+ * (what: 0 = bit_vector, 1 = rank_support_v<1>, 2 = rank_support_v<0>); *nbytes receives the size
+ * needed; buf may be NULL to query it.  The rank tables are built ON THE DEVICE and are byte-identical
+ * to rank_support_v::serialize (rank_support_v.hpp:151-158). */
+int sdslgpu_bv_serialize(const sdslgpu_handle *h, int what, void *buf, uint64_t cap, uint64_t *nbytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDSLGPU_H */

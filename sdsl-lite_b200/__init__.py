@@ -1,0 +1,220 @@
+"""sdsl-lite_b200 — Python host binding of the C-ABI product library (include/sdslgpu.h).
+
+This file is plumbing for tests/ and bench.py: a ctypes wrapper around ``libsdslgpu.so`` whose
+classes mirror the reference's interface for the hot path (``rank(i)``, ``select(i)``,
+``wt.rank(i, c)``, ``count``, ``locate`` — SURVEY.md §8(b)), in batch form.  The product itself is
+the CUDA library; there is NO CPU fallback: if the shared object is missing or no CUDA device is
+present every constructor raises.
+
+Arguments may be numpy arrays (host buffers: the library stages them through the chunked PCIe
+pipeline) or torch CUDA tensors (device buffers: the kernel is launched asynchronously on the given
+stream / torch's current stream).
+
+The directory name contains a hyphen, so import it with ``__graft_entry__.load_package()`` which
+registers it as module ``sdsl_lite_b200``.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsdslgpu.so")
+
+OK, EINVAL, ENOMEM, ECUDA, ENOTSUP = 0, -1, -2, -3, -4
+NPOS = np.uint64(0xFFFFFFFFFFFFFFFF)
+F_DEFAULT, F_SDSL_LAYOUT, F_NO_SELECT = 0, 1, 2
+KIND_BV, KIND_RRR63, KIND_SD, KIND_WT_HUFF, KIND_WT_INT, KIND_CSA_WT = 1, 2, 3, 4, 5, 6
+
+u64p = C.POINTER(C.c_uint64)
+vp = C.c_void_p
+
+# every symbol include/sdslgpu.h declares: (name, restype, argtypes)
+_SIGNATURES = [
+    ("sdslgpu_version", C.c_char_p, []),
+    ("sdslgpu_last_error", C.c_char_p, []),
+    ("sdslgpu_device_count", C.c_int, [C.POINTER(C.c_int)]),
+    ("sdslgpu_bv_create", C.c_int, [vp, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(vp)]),
+    ("sdslgpu_free", C.c_int, [vp]),
+    ("sdslgpu_kind", C.c_int, [vp, C.POINTER(C.c_int)]),
+    ("sdslgpu_size", C.c_int, [vp, u64p]),
+    ("sdslgpu_arg_count", C.c_int, [vp, C.c_int, u64p]),
+    ("sdslgpu_device_bytes", C.c_int, [vp, u64p]),
+    ("sdslgpu_rank", C.c_int, [vp, C.c_int, vp, C.c_uint64, vp, vp]),
+    ("sdslgpu_select", C.c_int, [vp, C.c_int, vp, C.c_uint64, vp, vp]),
+    ("sdslgpu_access", C.c_int, [vp, vp, C.c_uint64, vp, vp]),
+    ("sdslgpu_bv_serialize", C.c_int, [vp, C.c_int, vp, C.c_uint64, u64p]),
+]
+
+_lib = None
+
+
+class SdslGpuError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"sdslgpu status {status}: {msg}")
+        self.status = status
+
+
+def build(verbose=False):
+    """Compile libsdslgpu.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", HERE, "-j8", "all"], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-6000:], r.stderr[-6000:])
+    if r.returncode != 0:
+        raise RuntimeError("building libsdslgpu.so failed")
+
+
+def lib():
+    """Load the product library; fails loudly when it is missing (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, res, args in _SIGNATURES:
+            f = getattr(L, name)  # AttributeError here = the .so does not export a declared symbol
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def declared_symbols():
+    return [s[0] for s in _SIGNATURES]
+
+
+def _check(st):
+    if st != OK:
+        raise SdslGpuError(st, lib().sdslgpu_last_error().decode())
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _in_ptr(x, dtype=np.uint64):
+    """-> (pointer, n, keepalive, on_device)"""
+    if _is_torch(x):
+        import torch
+
+        want = {np.uint64: (torch.int64, torch.uint64), np.uint8: (torch.uint8,)}[dtype]
+        assert x.dtype in want and x.is_contiguous(), "torch inputs must be contiguous int64/uint64 (or uint8)"
+        return x.data_ptr(), x.numel(), x, x.is_cuda
+    a = np.ascontiguousarray(x, dtype=dtype)
+    return a.ctypes.data, a.size, a, False
+
+
+def _out_like(x, n, out=None):
+    """allocate (or validate) the uint64 output next to the input: torch -> torch, numpy -> numpy"""
+    if out is not None:
+        if _is_torch(out):
+            return out.data_ptr(), out, out
+        assert out.dtype == np.uint64 and out.flags["C_CONTIGUOUS"] and out.size >= n
+        return out.ctypes.data, out, out
+    if _is_torch(x):
+        import torch
+
+        o = torch.empty(n, dtype=torch.int64, device=x.device)
+        return o.data_ptr(), o, o
+    o = np.empty(n, dtype=np.uint64)
+    return o.ctypes.data, o, o
+
+
+def _stream_ptr(stream, x):
+    if stream is not None:
+        return int(getattr(stream, "cuda_stream", stream))
+    if _is_torch(x) and x.is_cuda:
+        import torch
+
+        return int(torch.cuda.current_stream(x.device).cuda_stream)
+    return 0
+
+
+class _Handle:
+    def __init__(self):
+        self._h = vp()
+
+    def close(self):
+        if self._h:
+            lib().sdslgpu_free(self._h)
+            self._h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def size(self):
+        v = C.c_uint64()
+        _check(lib().sdslgpu_size(self._h, C.byref(v)))
+        return v.value
+
+    def __len__(self):
+        return self.size
+
+    @property
+    def device_bytes(self):
+        v = C.c_uint64()
+        _check(lib().sdslgpu_device_bytes(self._h, C.byref(v)))
+        return v.value
+
+    # ---- the batched bit-vector concept (rank_support / select_support) ----------
+    def arg_count(self, b=1):
+        v = C.c_uint64()
+        _check(lib().sdslgpu_arg_count(self._h, b, C.byref(v)))
+        return v.value
+
+    def rank(self, idx, b=1, out=None, stream=None):
+        p, n, keep, _ = _in_ptr(idx)
+        po, o, _k = _out_like(idx, n, out)
+        _check(lib().sdslgpu_rank(self._h, b, p, n, po, _stream_ptr(stream, idx)))
+        return o
+
+    def select(self, i, b=1, out=None, stream=None):
+        p, n, keep, _ = _in_ptr(i)
+        po, o, _k = _out_like(i, n, out)
+        _check(lib().sdslgpu_select(self._h, b, p, n, po, _stream_ptr(stream, i)))
+        return o
+
+    def access(self, idx, out=None, stream=None):
+        p, n, keep, _ = _in_ptr(idx)
+        po, o, _k = _out_like(idx, n, out)
+        _check(lib().sdslgpu_access(self._h, p, n, po, _stream_ptr(stream, idx)))
+        return o
+
+
+class BitVector(_Handle):
+    """bit_vector + rank_support_v<b> + select_support_mcl<b> on the device.
+
+    ``words``: ceil(nbits/64) uint64 (numpy, or a torch CUDA int64 tensor already resident in HBM).
+    """
+
+    def __init__(self, words, nbits, device=0, flags=F_DEFAULT):
+        super().__init__()
+        nbits = int(nbits)
+        if _is_torch(words):
+            p, n, keep = words.data_ptr(), words.numel(), words
+        else:
+            keep = np.ascontiguousarray(words, dtype=np.uint64)
+            p, n = keep.ctypes.data, keep.size
+        assert n >= (nbits + 63) // 64, "words too short for nbits"
+        _check(lib().sdslgpu_bv_create(p if n else None, nbits, device, flags, C.byref(self._h)))
+        self.nbits = nbits
+        self.flags = flags
+
+    def serialize(self, what):
+        """SDSL-format bytes (what: 0 bit_vector, 1 rank_support_v<1>, 2 rank_support_v<0>); needs F_SDSL_LAYOUT"""
+        n = C.c_uint64()
+        _check(lib().sdslgpu_bv_serialize(self._h, what, None, 0, C.byref(n)))
+        buf = np.empty(n.value, dtype=np.uint8)
+        _check(lib().sdslgpu_bv_serialize(self._h, what, buf.ctypes.data, n.value, C.byref(n)))
+        return buf.tobytes()

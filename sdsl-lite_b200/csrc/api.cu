@@ -1,0 +1,471 @@
+// api.cu — the extern "C" boundary declared in include/sdslgpu.h: handle lifetime, pointer
+// classification, the chunked host-buffer pipeline, and dispatch to the per-kind device launchers.
+#include <cstdarg>
+#include <new>
+
+#include "internal.h"
+
+namespace sdslgpu
+{
+
+static thread_local char g_err[512] = "";
+
+void set_error(char const * fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, char const * what, char const * file, int line)
+{
+    set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    cudaGetLastError(); // clear the sticky-free error state
+    return e == cudaErrorMemoryAllocation ? SDSLGPU_ENOMEM : SDSLGPU_ECUDA;
+}
+
+int DevicePool::alloc(void ** p, uint64_t n)
+{
+    *p = nullptr;
+    if (n == 0)
+        n = 8;
+    n = (n + 255) & ~255ull;
+    cudaError_t e = cudaMalloc(p, n);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+    ptrs.push_back(*p);
+    sizes_.push_back(n);
+    bytes += n;
+    return SDSLGPU_OK;
+}
+
+void DevicePool::release(void * p)
+{
+    for (size_t k = 0; k < ptrs.size(); ++k)
+        if (ptrs[k] == p)
+        {
+            cudaFree(p);
+            bytes -= sizes_[k];
+            ptrs.erase(ptrs.begin() + k);
+            sizes_.erase(sizes_.begin() + k);
+            return;
+        }
+}
+
+void DevicePool::release_all()
+{
+    for (void * p : ptrs)
+        cudaFree(p);
+    ptrs.clear();
+    sizes_.clear();
+    bytes = 0;
+}
+
+int Staging::ensure()
+{
+    if (ready)
+        return SDSLGPU_OK;
+    for (int k = 0; k < kSlots; ++k)
+    {
+        SG_CUDA(cudaMalloc(reinterpret_cast<void **>(&in[k]), kChunk * kInBytesPerQuery));
+        SG_CUDA(cudaMalloc(reinterpret_cast<void **>(&out[k]), kChunk * kOutBytesPerQuery));
+        SG_CUDA(cudaStreamCreateWithFlags(&stream[k], cudaStreamNonBlocking));
+    }
+    ready = true;
+    return SDSLGPU_OK;
+}
+
+void Staging::destroy()
+{
+    for (int k = 0; k < kSlots; ++k)
+    {
+        if (in[k])
+            cudaFree(in[k]);
+        if (out[k])
+            cudaFree(out[k]);
+        if (stream[k])
+            cudaStreamDestroy(stream[k]);
+        in[k] = out[k] = nullptr;
+        stream[k] = nullptr;
+    }
+    ready = false;
+}
+
+int classify(void const * p, int device, PtrSpace * space)
+{
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess)
+    {
+        cudaGetLastError();
+        *space = PtrSpace::Host; // very old behaviour for unregistered memory
+        return SDSLGPU_OK;
+    }
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged)
+    {
+        if (a.type == cudaMemoryTypeDevice && a.device != device)
+        {
+            set_error("device pointer %p lives on device %d but the handle is on device %d", p, a.device, device);
+            return SDSLGPU_EINVAL;
+        }
+        *space = PtrSpace::Device;
+    }
+    else
+        *space = PtrSpace::Host;
+    return SDSLGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic batch driver: `launch(in_ptrs_on_device, n, out_ptrs_on_device, stream)` for up to 2 input
+// and 2 output columns.  If every pointer is a device pointer the launch is asynchronous on the
+// caller's stream; otherwise host columns are streamed through the handle's staging slots.
+// ------------------------------------------------------------------------------------------------
+struct Column
+{
+    void const * in = nullptr; // user pointer (host or device)
+    void * out = nullptr;
+    uint32_t elem = 8; // bytes per element
+};
+
+template <class Launch>
+static int run_batch(sdslgpu_handle const * hc, Column const * ins, int nin, Column const * outs, int nout, uint64_t n, cudaStream_t user, Launch launch)
+{
+    sdslgpu_handle * h = const_cast<sdslgpu_handle *>(hc);
+    if (n == 0)
+        return SDSLGPU_OK;
+    DeviceGuard g(h->device);
+    if (!g.ok)
+    {
+        set_error("cannot select CUDA device %d", h->device);
+        return SDSLGPU_ECUDA;
+    }
+    bool any_host = false;
+    PtrSpace in_sp[2] = {PtrSpace::Device, PtrSpace::Device}, out_sp[2] = {PtrSpace::Device, PtrSpace::Device};
+    for (int k = 0; k < nin; ++k)
+    {
+        if (!ins[k].in)
+        {
+            set_error("null input pointer");
+            return SDSLGPU_EINVAL;
+        }
+        SG_TRY(classify(ins[k].in, h->device, &in_sp[k]));
+        any_host |= in_sp[k] == PtrSpace::Host;
+    }
+    for (int k = 0; k < nout; ++k)
+    {
+        if (!outs[k].out)
+            continue; // optional output column
+        SG_TRY(classify(outs[k].out, h->device, &out_sp[k]));
+        any_host |= out_sp[k] == PtrSpace::Host;
+    }
+    if (!any_host)
+    {
+        void const * ip[2] = {nin > 0 ? ins[0].in : nullptr, nin > 1 ? ins[1].in : nullptr};
+        void * op[2] = {nout > 0 ? outs[0].out : nullptr, nout > 1 ? outs[1].out : nullptr};
+        return launch(ip, n, op, user);
+    }
+
+    // chunked pipeline over the staging slots
+    std::lock_guard<std::mutex> lock(h->staging.mu);
+    SG_TRY(h->staging.ensure());
+    Staging & st = h->staging;
+    if (user)
+        SG_CUDA(cudaStreamSynchronize(user)); // order after the caller's earlier work
+    uint64_t const chunk = Staging::kChunk;
+    uint64_t nchunks = (n + chunk - 1) / chunk;
+    int status = SDSLGPU_OK;
+    for (uint64_t c = 0; c < nchunks && status == SDSLGPU_OK; ++c)
+    {
+        int slot = (int)(c % Staging::kSlots);
+        cudaStream_t s = st.stream[slot];
+        uint64_t lo = c * chunk, cnt = (n - lo < chunk) ? n - lo : chunk;
+        void const * ip[2] = {nullptr, nullptr};
+        void * op[2] = {nullptr, nullptr};
+        // a slot is reused every kSlots chunks; same-stream ordering makes that safe
+        for (int k = 0; k < nin; ++k)
+        {
+            uint8_t const * src = static_cast<uint8_t const *>(ins[k].in) + lo * ins[k].elem;
+            if (in_sp[k] == PtrSpace::Host)
+            {
+                uint8_t * dst = st.in[slot] + (uint64_t)k * chunk * 8;
+                cudaError_t e = cudaMemcpyAsync(dst, src, cnt * ins[k].elem, cudaMemcpyHostToDevice, s);
+                if (e != cudaSuccess)
+                    status = cuda_fail(e, "H2D chunk", __FILE__, __LINE__);
+                ip[k] = dst;
+            }
+            else
+                ip[k] = src;
+        }
+        for (int k = 0; k < nout; ++k)
+        {
+            if (!outs[k].out)
+                continue;
+            if (out_sp[k] == PtrSpace::Host)
+                op[k] = st.out[slot] + (uint64_t)k * chunk * 8;
+            else
+                op[k] = static_cast<uint8_t *>(outs[k].out) + lo * outs[k].elem;
+        }
+        if (status == SDSLGPU_OK)
+            status = launch(ip, cnt, op, s);
+        for (int k = 0; k < nout && status == SDSLGPU_OK; ++k)
+        {
+            if (!outs[k].out || out_sp[k] != PtrSpace::Host)
+                continue;
+            uint8_t * dst = static_cast<uint8_t *>(outs[k].out) + lo * outs[k].elem;
+            cudaError_t e = cudaMemcpyAsync(dst, op[k], cnt * outs[k].elem, cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess)
+                status = cuda_fail(e, "D2H chunk", __FILE__, __LINE__);
+        }
+    }
+    for (int k = 0; k < Staging::kSlots; ++k)
+    {
+        cudaError_t e = cudaStreamSynchronize(st.stream[k]);
+        if (e != cudaSuccess && status == SDSLGPU_OK)
+            status = cuda_fail(e, "staging sync", __FILE__, __LINE__);
+    }
+    return status;
+}
+
+static int check_handle(sdslgpu_handle const * h)
+{
+    if (!h)
+    {
+        set_error("null handle");
+        return SDSLGPU_EINVAL;
+    }
+    return SDSLGPU_OK;
+}
+
+} // namespace sdslgpu
+
+using namespace sdslgpu;
+
+extern "C"
+{
+
+    const char * sdslgpu_version(void)
+    {
+        return "sdslgpu 0.1 (sm_100a; rank/select/wt/fm batched query engine)";
+    }
+
+    const char * sdslgpu_last_error(void)
+    {
+        return g_err;
+    }
+
+    int sdslgpu_device_count(int * count)
+    {
+        if (!count)
+            return SDSLGPU_EINVAL;
+        *count = 0;
+        SG_CUDA(cudaGetDeviceCount(count));
+        return SDSLGPU_OK;
+    }
+
+    int sdslgpu_bv_create(const uint64_t * words, uint64_t nbits, int device, uint32_t flags, sdslgpu_handle ** out)
+    {
+        if (!out || (!words && nbits))
+        {
+            set_error("sdslgpu_bv_create: null argument");
+            return SDSLGPU_EINVAL;
+        }
+        *out = nullptr;
+        int ndev = 0;
+        SG_CUDA(cudaGetDeviceCount(&ndev));
+        if (device < 0 || device >= ndev)
+        {
+            set_error("sdslgpu_bv_create: device %d out of range (%d devices); there is no CPU fallback", device, ndev);
+            return SDSLGPU_ECUDA;
+        }
+        DeviceGuard g(device);
+        if (!g.ok)
+        {
+            set_error("cannot select CUDA device %d", device);
+            return SDSLGPU_ECUDA;
+        }
+        sdslgpu_handle * h = new (std::nothrow) sdslgpu_handle;
+        if (!h)
+            return SDSLGPU_ENOMEM;
+        h->kind = SDSLGPU_KIND_BV;
+        h->device = device;
+        h->flags = flags;
+        PtrSpace sp = PtrSpace::Host;
+        int st = nbits ? classify(words, device, &sp) : SDSLGPU_OK;
+        if (st == SDSLGPU_OK)
+            st = bv_build(h, words, sp == PtrSpace::Device, nbits, nullptr);
+        if (st != SDSLGPU_OK)
+        {
+            h->pool.release_all();
+            delete h;
+            return st;
+        }
+        *out = h;
+        return SDSLGPU_OK;
+    }
+
+    int sdslgpu_free(sdslgpu_handle * h)
+    {
+        if (!h)
+            return SDSLGPU_OK;
+        DeviceGuard g(h->device);
+        cudaDeviceSynchronize();
+        h->staging.destroy();
+        h->pool.release_all();
+        delete h;
+        return SDSLGPU_OK;
+    }
+
+    int sdslgpu_kind(const sdslgpu_handle * h, int * kind)
+    {
+        SG_TRY(check_handle(h));
+        *kind = h->kind;
+        return SDSLGPU_OK;
+    }
+
+    int sdslgpu_size(const sdslgpu_handle * h, uint64_t * size)
+    {
+        SG_TRY(check_handle(h));
+        switch (h->kind)
+        {
+        case SDSLGPU_KIND_BV:
+            *size = h->bv.nbits;
+            return SDSLGPU_OK;
+        }
+        return SDSLGPU_ENOTSUP;
+    }
+
+    int sdslgpu_arg_count(const sdslgpu_handle * h, int b, uint64_t * count)
+    {
+        SG_TRY(check_handle(h));
+        if (b != 0 && b != 1)
+            return SDSLGPU_EINVAL;
+        switch (h->kind)
+        {
+        case SDSLGPU_KIND_BV:
+            *count = b ? h->bv.ones : h->bv.nbits - h->bv.ones;
+            return SDSLGPU_OK;
+        }
+        return SDSLGPU_ENOTSUP;
+    }
+
+    int sdslgpu_device_bytes(const sdslgpu_handle * h, uint64_t * bytes)
+    {
+        SG_TRY(check_handle(h));
+        *bytes = h->pool.bytes;
+        return SDSLGPU_OK;
+    }
+
+    int sdslgpu_rank(const sdslgpu_handle * h, int b, const uint64_t * idx, uint64_t n, uint64_t * out, void * stream)
+    {
+        SG_TRY(check_handle(h));
+        if (b != 0 && b != 1)
+        {
+            set_error("sdslgpu_rank: pattern must be 0 or 1");
+            return SDSLGPU_EINVAL;
+        }
+        if (n && !out)
+        {
+            set_error("sdslgpu_rank: null output");
+            return SDSLGPU_EINVAL;
+        }
+        Column in{idx, nullptr, 8}, o{nullptr, out, 8};
+        switch (h->kind)
+        {
+        case SDSLGPU_KIND_BV:
+            return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
+                return bv_rank_device(h, b, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
+            });
+        }
+        set_error("sdslgpu_rank: unsupported handle kind %d", h->kind);
+        return SDSLGPU_ENOTSUP;
+    }
+
+    int sdslgpu_select(const sdslgpu_handle * h, int b, const uint64_t * i, uint64_t n, uint64_t * out, void * stream)
+    {
+        SG_TRY(check_handle(h));
+        if (b != 0 && b != 1)
+        {
+            set_error("sdslgpu_select: pattern must be 0 or 1");
+            return SDSLGPU_EINVAL;
+        }
+        if (n && !out)
+        {
+            set_error("sdslgpu_select: null output");
+            return SDSLGPU_EINVAL;
+        }
+        Column in{i, nullptr, 8}, o{nullptr, out, 8};
+        switch (h->kind)
+        {
+        case SDSLGPU_KIND_BV:
+            return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
+                return bv_select_device(h, b, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
+            });
+        }
+        set_error("sdslgpu_select: unsupported handle kind %d", h->kind);
+        return SDSLGPU_ENOTSUP;
+    }
+
+    int sdslgpu_access(const sdslgpu_handle * h, const uint64_t * idx, uint64_t n, uint64_t * out, void * stream)
+    {
+        SG_TRY(check_handle(h));
+        if (n && !out)
+        {
+            set_error("sdslgpu_access: null output");
+            return SDSLGPU_EINVAL;
+        }
+        Column in{idx, nullptr, 8}, o{nullptr, out, 8};
+        switch (h->kind)
+        {
+        case SDSLGPU_KIND_BV:
+            return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
+                return bv_access_device(h, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
+            });
+        }
+        set_error("sdslgpu_access: unsupported handle kind %d", h->kind);
+        return SDSLGPU_ENOTSUP;
+    }
+
+    int sdslgpu_bv_serialize(const sdslgpu_handle * h, int what, void * buf, uint64_t cap, uint64_t * nbytes)
+    {
+        SG_TRY(check_handle(h));
+        if (h->kind != SDSLGPU_KIND_BV || !nbytes)
+            return SDSLGPU_EINVAL;
+        if (!(h->flags & SDSLGPU_F_SDSL_LAYOUT))
+        {
+            set_error("sdslgpu_bv_serialize needs a handle created with SDSLGPU_F_SDSL_LAYOUT");
+            return SDSLGPU_ENOTSUP;
+        }
+        sdslgpu_bv_image const & v = h->bv;
+        uint64_t header, words;
+        uint64_t const * src;
+        if (what == 0)
+        {
+            header = (1ull << 56) | v.nbits; // int_vector.hpp:904-916
+            words = v.nwords;
+            src = v.words;
+        }
+        else if (what == 1 || what == 2)
+        {
+            words = v.table_words;
+            header = (64ull << 56) | (words * 64);
+            src = v.rank_table[what == 1 ? 1 : 0];
+        }
+        else
+            return SDSLGPU_EINVAL;
+        *nbytes = 8 + words * 8;
+        if (!buf)
+            return SDSLGPU_OK;
+        if (cap < *nbytes)
+        {
+            set_error("sdslgpu_bv_serialize: buffer too small");
+            return SDSLGPU_EINVAL;
+        }
+        DeviceGuard g(h->device);
+        std::memcpy(buf, &header, 8);
+        if (words)
+            SG_CUDA(cudaMemcpy(static_cast<uint8_t *>(buf) + 8, src, words * 8, cudaMemcpyDeviceToHost));
+        return SDSLGPU_OK;
+    }
+
+} // extern "C"

@@ -1,0 +1,488 @@
+// bv.cu — plain bit_vector: device builders and batched rank / select / access kernels.
+//
+// Replaces (results bit-exact, layout re-designed for B200 — DESIGN.md §3):
+//   rank_support_v<b,1>  ctor  rank_support_v.hpp:72-122     -> bv_pack_kernel + scan + bv_finish_kernel
+//   rank_support_v<b,1>::rank  rank_support_v.hpp:129-139    -> bv_rank_kernel<B>   (1 sector / query)
+//   select_support_mcl<b,1> ctor select_support_mcl.hpp:207-381 -> bv_samples_kernel<B>
+//   select_support_mcl<b,1>::select  :384-439                -> bv_select_kernel<B>
+//   bit_vector::operator[]     int_vector.hpp:1900-1904      -> bv_access_kernel
+// plus, under SDSLGPU_F_SDSL_LAYOUT, the reference's own table (m_basic_block) built on the device,
+// byte-identical to the reference's, and a rank kernel that reads it exactly as the reference does.
+#include "internal.h"
+#include "scan.cuh"
+
+namespace sdslgpu
+{
+
+// ------------------------------------------------------------------------------------------------
+// build, phase 1: re-chunk the LSB-first bit stream into 224-bit payloads and count each block
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+    bv_pack_kernel(uint32_t const * __restrict__ w32, uint64_t nbits, uint64_t nblocks, bvblock * __restrict__ blocks, uint32_t * __restrict__ blk_ones)
+{
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks)
+        return;
+    uint64_t n32 = (nbits + 31) >> 5; // number of 32-bit words holding valid bits
+    uint32_t d[7];
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+    {
+        uint64_t k = b * 7 + j;
+        uint32_t x = 0;
+        if (k < n32)
+        {
+            x = w32[k];
+            if (k == n32 - 1 && (nbits & 31))
+                x &= (1u << (nbits & 31)) - 1u; // bits past nbits are unspecified in SDSL: ignore them
+        }
+        d[j] = x;
+        c += __popc(x);
+    }
+    // two 128-bit stores = one full sector
+    uint4 * o = reinterpret_cast<uint4 *>(blocks + b);
+    o[0] = make_uint4(0u, d[0], d[1], d[2]);
+    o[1] = make_uint4(d[3], d[4], d[5], d[6]);
+    blk_ones[b] = c;
+}
+
+// build, phase 3: turn absolute prefix counts into (top[superblock], 32-bit in-superblock count)
+__global__ void __launch_bounds__(kThreads)
+    bv_finish_kernel(uint64_t const * __restrict__ abs_ones, uint64_t nblocks, bvblock * __restrict__ blocks, uint64_t * __restrict__ top)
+{
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks)
+        return;
+    uint64_t sb = b >> kSuperShift;
+    uint64_t base = abs_ones[sb << kSuperShift];
+    blocks[b].cnt = (uint32_t)(abs_ones[b] - base);
+    if ((b & ((1ull << kSuperShift) - 1)) == 0)
+        top[sb] = base;
+}
+
+// select samples: samp[j] = block that holds the (j*S+1)-th B-bit.  One thread per block writes the
+// (at most 224/S + 1) samples that fall inside it.
+template <int B>
+__global__ void __launch_bounds__(kThreads) bv_samples_kernel(uint64_t const * __restrict__ abs_ones,
+                                                              uint32_t const * __restrict__ blk_ones,
+                                                              uint64_t nbits,
+                                                              uint64_t nblocks,
+                                                              uint32_t log_s,
+                                                              uint32_t * __restrict__ samp,
+                                                              uint64_t nsamp)
+{
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks)
+        return;
+    uint64_t first = b * kBlockBits;
+    uint64_t valid = (first >= nbits) ? 0 : ((nbits - first < kBlockBits) ? nbits - first : kBlockBits);
+    uint64_t a1 = abs_ones[b], c1 = blk_ones[b];
+    uint64_t a = B ? a1 : first - a1; // B-bits before the block (first <= nbits here whenever valid > 0)
+    uint64_t c = B ? c1 : valid - c1;
+    if (c == 0)
+        return;
+    uint64_t S = 1ull << log_s;
+    for (uint64_t j = (a + S - 1) >> log_s; j < nsamp && (j << log_s) + 1 <= a + c; ++j)
+        samp[j] = (uint32_t)b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// rank: one 32-byte sector per query
+// ------------------------------------------------------------------------------------------------
+template <int B, int ILP>
+__global__ void __launch_bounds__(kThreads) bv_rank_kernel(bvblock const * __restrict__ blocks,
+                                                           uint64_t const * __restrict__ top,
+                                                           uint64_t nbits,
+                                                           uint64_t const * __restrict__ idx,
+                                                           uint64_t n,
+                                                           uint64_t * __restrict__ out)
+{
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x * ILP;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x * ILP + threadIdx.x; base < n; base += stride)
+    {
+        uint64_t i[ILP], blk[ILP];
+        uint32_t cnt[ILP], d[ILP][7];
+        bool ok[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u)
+        {
+            uint64_t q = base + (uint64_t)u * blockDim.x;
+            i[u] = (q < n) ? ld_stream_u64(idx + q) : 0;
+            ok[u] = i[u] <= nbits;
+            blk[u] = ok[u] ? i[u] / kBlockBits : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u)
+            ld_block(blocks + blk[u], cnt[u], d[u]);
+#pragma unroll
+        for (int u = 0; u < ILP; ++u)
+        {
+            uint64_t q = base + (uint64_t)u * blockDim.x;
+            if (q < n)
+            {
+                uint32_t rem = (uint32_t)(i[u] - blk[u] * kBlockBits);
+                uint64_t r = __ldg(top + (blk[u] >> kSuperShift)) + cnt[u] + block_prefix_popc(d[u], rem);
+                if (!B)
+                    r = i[u] - r;
+                st_stream_u64(out + q, ok[u] ? r : SDSLGPU_NPOS);
+            }
+        }
+    }
+}
+
+// rank on the reference's own layout (SDSLGPU_F_SDSL_LAYOUT): 16-byte table pair + 8-byte data word,
+// i.e. the two gathers of rank_support_v.hpp:133-135 issued together.
+template <int B, int ILP>
+__global__ void __launch_bounds__(kThreads) bv_rank_sdsl_kernel(uint64_t const * __restrict__ words,
+                                                                uint64_t const * __restrict__ table,
+                                                                uint64_t nbits,
+                                                                uint64_t const * __restrict__ idx,
+                                                                uint64_t n,
+                                                                uint64_t * __restrict__ out)
+{
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x * ILP;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x * ILP + threadIdx.x; base < n; base += stride)
+    {
+        uint64_t i[ILP], a[ILP], r9[ILP], w[ILP];
+        bool ok[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u)
+        {
+            uint64_t q = base + (uint64_t)u * blockDim.x;
+            i[u] = (q < n) ? ld_stream_u64(idx + q) : 0;
+            ok[u] = i[u] <= nbits;
+            if (!ok[u])
+                i[u] = 0;
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u)
+        {
+            ld_pair(table + ((i[u] >> 8) & ~1ULL), a[u], r9[u]);
+            w[u] = ld_nc_u64(words + (i[u] >> 6)); // the pad word makes i == nbits safe
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u)
+        {
+            uint64_t q = base + (uint64_t)u * blockDim.x;
+            if (q < n)
+            {
+                uint64_t x = B ? w[u] : ~w[u];
+                uint64_t r = a[u] + ((r9[u] >> (63 - 9 * ((i[u] & 0x1FF) >> 6))) & 0x1FF) + __popcll(x & lo_set64((uint32_t)(i[u] & 63)));
+                st_stream_u64(out + q, ok[u] ? r : SDSLGPU_NPOS);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// select
+// ------------------------------------------------------------------------------------------------
+template <int B>
+__device__ __forceinline__ uint64_t abs_before(bvblock const * __restrict__ blocks, uint64_t const * __restrict__ top, uint64_t b)
+{
+    uint64_t a1 = __ldg(top + (b >> kSuperShift)) + __ldg(&blocks[b].cnt);
+    return B ? a1 : b * kBlockBits - a1;
+}
+
+// position of the i-th (1-based) B-bit, given 1 <= i <= #B-bits
+template <int B>
+__device__ __forceinline__ uint64_t bv_select_one(bvblock const * __restrict__ blocks,
+                                                  uint64_t const * __restrict__ top,
+                                                  uint32_t const * __restrict__ samp,
+                                                  uint32_t log_s,
+                                                  uint64_t i)
+{
+    uint64_t j = (i - 1) >> log_s;
+    uint2 s2;
+    // samp[j], samp[j+1]: one 8-byte load when j is even
+    uint64_t lo, hi;
+    if ((j & 1) == 0)
+    {
+        s2 = __ldg(reinterpret_cast<uint2 const *>(samp + j));
+        lo = s2.x;
+        hi = s2.y;
+    }
+    else
+    {
+        lo = __ldg(samp + j);
+        hi = __ldg(samp + j + 1);
+    }
+    // invariant: the answer lies in a block of [lo, hi] and abs_before(lo) < i
+    while (hi - lo > 3)
+    {
+        uint64_t mid = (lo + hi + 1) >> 1;
+        if (abs_before<B>(blocks, top, mid) < i)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    uint32_t cnt, d[7];
+    ld_block(blocks + lo, cnt, d);
+    uint64_t a1 = __ldg(top + (lo >> kSuperShift)) + cnt;
+    uint64_t need = i - (B ? a1 : lo * kBlockBits - a1);
+    uint32_t c = block_popc<B>(d);
+    while (need > c)
+    {
+        need -= c;
+        ++lo;
+        ld_block(blocks + lo, cnt, d);
+        c = block_popc<B>(d);
+    }
+    return lo * kBlockBits + block_select<B>(d, (uint32_t)need);
+}
+
+template <int B>
+__global__ void __launch_bounds__(kThreads) bv_select_kernel(bvblock const * __restrict__ blocks,
+                                                             uint64_t const * __restrict__ top,
+                                                             uint32_t const * __restrict__ samp,
+                                                             uint32_t log_s,
+                                                             uint64_t args,
+                                                             uint64_t const * __restrict__ idx,
+                                                             uint64_t n,
+                                                             uint64_t * __restrict__ out)
+{
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
+    {
+        uint64_t i = ld_stream_u64(idx + q);
+        uint64_t r = SDSLGPU_NPOS;
+        if (i >= 1 && i <= args)
+            r = bv_select_one<B>(blocks, top, samp, log_s, i);
+        st_stream_u64(out + q, r);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+    bv_access_kernel(bvblock const * __restrict__ blocks, uint64_t nbits, uint64_t const * __restrict__ idx, uint64_t n, uint64_t * __restrict__ out)
+{
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
+    {
+        uint64_t i = ld_stream_u64(idx + q);
+        uint64_t r = SDSLGPU_NPOS;
+        if (i < nbits)
+        {
+            uint64_t b = i / kBlockBits;
+            uint32_t rem = (uint32_t)(i - b * kBlockBits);
+            r = (ld_nc_u32(&blocks[b].d[rem >> 5]) >> (rem & 31)) & 1u;
+        }
+        st_stream_u64(out + q, r);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the reference's m_basic_block, built on the device (rank_support_v.hpp:72-122), byte-identical.
+// One thread per 512-bit superblock: 8 word popcounts -> 7 nine-bit prefixes + the superblock total.
+// ------------------------------------------------------------------------------------------------
+template <int B>
+__global__ void __launch_bounds__(kThreads)
+    sdsl_table_rel_kernel(uint64_t const * __restrict__ words, uint64_t nwords, uint64_t nsuper, uint64_t * __restrict__ table, uint32_t * __restrict__ sb_total)
+{
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nsuper)
+        return;
+    uint64_t second = 0, sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+    {
+        uint64_t wi = k * 8 + j;
+        if (j > 0 && wi <= nwords) // the reference also records the prefix just past the last word (:109-113)
+            second |= sum << (63 - 9 * j);
+        if (wi < nwords)
+        {
+            uint64_t x = words[wi];
+            sum += __popcll(B ? x : ~x);
+        }
+    }
+    table[2 * k + 1] = second;
+    sb_total[k] = (uint32_t)sum;
+}
+
+__global__ void __launch_bounds__(kThreads) sdsl_table_abs_kernel(uint64_t const * __restrict__ abs, uint64_t nsuper, uint64_t * __restrict__ table)
+{
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nsuper)
+        table[2 * k] = abs[k];
+}
+
+static inline unsigned grid_for(uint64_t n, int per_thread = 1)
+{
+    uint64_t want = (n + (uint64_t)kThreads * per_thread - 1) / ((uint64_t)kThreads * per_thread);
+    uint64_t cap = (uint64_t)kSmCount * 8; // 8 resident CTAs of 256 threads per SM = 64 warps
+    if (want < 1)
+        want = 1;
+    return (unsigned)(want < cap ? want : cap);
+}
+static inline unsigned blocks_for(uint64_t n)
+{
+    return (unsigned)((n + kThreads - 1) / kThreads);
+}
+
+int bv_build(sdslgpu_handle * h, uint64_t const * words_in, bool on_device, uint64_t nbits, cudaStream_t s)
+{
+    sdslgpu_bv_image & v = h->bv;
+    v.nbits = nbits;
+    v.nwords = (nbits + 63) >> 6;
+    v.nblocks = nbits / kBlockBits + 1;
+    if (v.nblocks >= (1ull << 32))
+    {
+        set_error("bit vector too large: %llu bits (limit 2^32 blocks of 224 bits)", (unsigned long long)nbits);
+        return SDSLGPU_EINVAL;
+    }
+    v.ntop = ((v.nblocks - 1) >> kSuperShift) + 1;
+
+    // raw words on the device (+1 zero pad word, like SDSL's allocation, memory_management.hpp:901-906)
+    uint64_t * words = nullptr;
+    SG_TRY(h->pool.alloc_t(&words, v.nwords + 2));
+    SG_CUDA(cudaMemsetAsync(words + v.nwords, 0, 16, s));
+    if (v.nwords)
+        SG_CUDA(cudaMemcpyAsync(words, words_in, v.nwords * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+
+    uint32_t * blk_ones = nullptr;
+    uint64_t * abs_ones = nullptr;
+    uint64_t * tmp = nullptr;
+    SG_TRY(h->pool.alloc_t(&v.blocks, v.nblocks));
+    SG_TRY(h->pool.alloc_t(&v.top, v.ntop));
+    SG_TRY(h->pool.alloc_t(&blk_ones, v.nblocks));
+    SG_TRY(h->pool.alloc_t(&abs_ones, v.nblocks + 1));
+    SG_TRY(h->pool.alloc_t(&tmp, scan_tmp_words(v.nblocks)));
+
+    bv_pack_kernel<<<blocks_for(v.nblocks), kThreads, 0, s>>>(reinterpret_cast<uint32_t const *>(words), nbits, v.nblocks, v.blocks, blk_ones);
+    SG_CUDA(cudaGetLastError());
+    SG_CUDA(exclusive_scan(blk_ones, v.nblocks, abs_ones, tmp, s));
+    bv_finish_kernel<<<blocks_for(v.nblocks), kThreads, 0, s>>>(abs_ones, v.nblocks, v.blocks, v.top);
+    SG_CUDA(cudaGetLastError());
+    SG_CUDA(cudaMemcpyAsync(&v.ones, abs_ones + v.nblocks, 8, cudaMemcpyDeviceToHost, s));
+    SG_CUDA(cudaStreamSynchronize(s));
+
+    if (!(h->flags & SDSLGPU_F_NO_SELECT))
+    {
+        for (int b = 0; b < 2; ++b)
+        {
+            uint64_t m = b ? v.ones : nbits - v.ones;
+            // sample stride S = 2^log_s: the largest power of two <= 64 with S <= 128 * density, so the
+            // expected distance between samples stays around 128 bits whatever the density
+            uint32_t ls = 6;
+            while (ls > 0 && ((1ull << ls) * nbits > 128ull * m * 1ull) && m > 0)
+                --ls;
+            v.log_s[b] = ls;
+            v.nsamp[b] = m ? ((m - 1) >> ls) + 1 : 0;
+            SG_TRY(h->pool.alloc_t(&v.samp[b], v.nsamp[b] + 2));
+            // sentinel(s): the last block
+            std::vector<uint32_t> tail(2, (uint32_t)(v.nblocks - 1));
+            SG_CUDA(cudaMemcpyAsync(v.samp[b] + v.nsamp[b], tail.data(), 8, cudaMemcpyHostToDevice, s));
+            if (m)
+            {
+                if (b)
+                    bv_samples_kernel<1><<<blocks_for(v.nblocks), kThreads, 0, s>>>(abs_ones, blk_ones, nbits, v.nblocks, ls, v.samp[b], v.nsamp[b]);
+                else
+                    bv_samples_kernel<0><<<blocks_for(v.nblocks), kThreads, 0, s>>>(abs_ones, blk_ones, nbits, v.nblocks, ls, v.samp[b], v.nsamp[b]);
+                SG_CUDA(cudaGetLastError());
+            }
+            SG_CUDA(cudaStreamSynchronize(s)); // `tail` must outlive the copy
+        }
+    }
+    SG_CUDA(cudaStreamSynchronize(s));
+    h->pool.release(blk_ones);
+    h->pool.release(abs_ones);
+    h->pool.release(tmp);
+
+    if (h->flags & SDSLGPU_F_SDSL_LAYOUT)
+    {
+        v.words = words;
+        // keep the caller's bits past nbits exactly as given, like the reference does
+        for (int b = 0; b < 2; ++b)
+            SG_TRY(bv_build_sdsl_rank_table(h, b, s));
+    }
+    else
+    {
+        h->pool.release(words);
+    }
+    return SDSLGPU_OK;
+}
+
+int bv_build_sdsl_rank_table(sdslgpu_handle * h, int b, cudaStream_t s)
+{
+    sdslgpu_bv_image & v = h->bv;
+    // rank_support_v.hpp:79,84: 2 words for an empty vector, else 2 * (((n+63)>>9) + 1)
+    uint64_t nsuper = (v.nbits == 0) ? 1 : ((v.nbits + 63) >> 9) + 1;
+    v.table_words = 2 * nsuper;
+    SG_TRY(h->pool.alloc_t(&v.rank_table[b], v.table_words + 2));
+    uint32_t * sb_total = nullptr;
+    uint64_t * abs = nullptr;
+    uint64_t * tmp = nullptr;
+    SG_TRY(h->pool.alloc_t(&sb_total, nsuper));
+    SG_TRY(h->pool.alloc_t(&abs, nsuper + 1));
+    SG_TRY(h->pool.alloc_t(&tmp, scan_tmp_words(nsuper)));
+    if (b)
+        sdsl_table_rel_kernel<1><<<blocks_for(nsuper), kThreads, 0, s>>>(v.words, v.nwords, nsuper, v.rank_table[b], sb_total);
+    else
+        sdsl_table_rel_kernel<0><<<blocks_for(nsuper), kThreads, 0, s>>>(v.words, v.nwords, nsuper, v.rank_table[b], sb_total);
+    SG_CUDA(cudaGetLastError());
+    SG_CUDA(exclusive_scan(sb_total, nsuper, abs, tmp, s));
+    sdsl_table_abs_kernel<<<blocks_for(nsuper), kThreads, 0, s>>>(abs, nsuper, v.rank_table[b]);
+    SG_CUDA(cudaGetLastError());
+    SG_CUDA(cudaStreamSynchronize(s));
+    h->pool.release(sb_total);
+    h->pool.release(abs);
+    h->pool.release(tmp);
+    return SDSLGPU_OK;
+}
+
+int bv_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)
+{
+    sdslgpu_bv_image const & v = h->bv;
+    if (n == 0)
+        return SDSLGPU_OK;
+    constexpr int ILP = 2;
+    unsigned grid = grid_for(n, ILP);
+    if (h->flags & SDSLGPU_F_SDSL_LAYOUT)
+    {
+        if (b)
+            bv_rank_sdsl_kernel<1, ILP><<<grid, kThreads, 0, s>>>(v.words, v.rank_table[1], v.nbits, idx, n, out);
+        else
+            bv_rank_sdsl_kernel<0, ILP><<<grid, kThreads, 0, s>>>(v.words, v.rank_table[0], v.nbits, idx, n, out);
+    }
+    else
+    {
+        if (b)
+            bv_rank_kernel<1, ILP><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.nbits, idx, n, out);
+        else
+            bv_rank_kernel<0, ILP><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.nbits, idx, n, out);
+    }
+    SG_CUDA(cudaGetLastError());
+    return SDSLGPU_OK;
+}
+
+int bv_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)
+{
+    sdslgpu_bv_image const & v = h->bv;
+    if (n == 0)
+        return SDSLGPU_OK;
+    if (v.samp[b] == nullptr)
+    {
+        set_error("select requested on a handle created with SDSLGPU_F_NO_SELECT");
+        return SDSLGPU_ENOTSUP;
+    }
+    unsigned grid = grid_for(n);
+    uint64_t args = b ? v.ones : v.nbits - v.ones;
+    if (b)
+        bv_select_kernel<1><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.samp[1], v.log_s[1], args, idx, n, out);
+    else
+        bv_select_kernel<0><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.samp[0], v.log_s[0], args, idx, n, out);
+    SG_CUDA(cudaGetLastError());
+    return SDSLGPU_OK;
+}
+
+int bv_access_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)
+{
+    sdslgpu_bv_image const & v = h->bv;
+    if (n == 0)
+        return SDSLGPU_OK;
+    bv_access_kernel<<<grid_for(n), kThreads, 0, s>>>(v.blocks, v.nbits, idx, n, out);
+    SG_CUDA(cudaGetLastError());
+    return SDSLGPU_OK;
+}
+
+} // namespace sdslgpu

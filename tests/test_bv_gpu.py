@@ -1,0 +1,107 @@
+"""GPU parity: batched rank / select / access on plain bit vectors through the C ABI, against the oracle
+(oracle/oracle.c) and, where built, the unmodified reference (oracle/_ref) — SURVEY.md §8 rows a2-a4."""
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _checkers(oracle, orc, w, nbits):
+    out = [("oracle", oracle.bv(w, nbits))]
+    if orc.ref_available():
+        out.append(("reference", orc.Ref().bv(w, nbits)))
+    return out
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["b200_layout", "sdsl_layout"])
+def test_rank_select_catalogue(pkg, oracle, orc, flags):
+    """edge-case catalogue of test/rank_support_test.config / select_support_test.config: every position
+    of the small vectors, 60k random positions of the 1e6-bit ones, both patterns"""
+    for cid, w, nbits in cases.bitvector_catalogue(large=True):
+        with pkg.BitVector(w, nbits, flags=flags) as bv:
+            assert bv.size == nbits
+            idx = cases.rank_queries(nbits, 11, 60000)
+            for name, chk in _checkers(oracle, orc, w, nbits):
+                for b in (1, 0):
+                    assert (bv.rank(idx, b) == chk.rank(idx, b)).all(), (cid, name, "rank", b)
+                    m = bv.arg_count(b)
+                    assert m == int(chk.rank([nbits], b)[0]), (cid, name, "arg_count", b)
+                    q = cases.select_queries(m, 12, 60000)
+                    if len(q):
+                        assert (bv.select(q, b) == chk.select(q, b)).all(), (cid, name, "select", b)
+            if nbits:
+                bits = cases.unpack_bits(w, nbits)
+                pos = idx[idx < nbits]
+                assert (bv.access(pos) == bits[pos.astype(np.int64)]).all(), (cid, "access")
+
+
+def test_sdsl_tables_built_on_device_are_byte_identical(pkg, oracle, orc):
+    """construction parity: m_basic_block built by sdsl_table_*_kernel == rank_support_v::serialize bytes"""
+    for cid, w, nbits in cases.bitvector_catalogue(large=True):
+        with pkg.BitVector(w, nbits, flags=pkg.F_SDSL_LAYOUT) as bv:
+            ob = oracle.bv(w, nbits)
+            rb = orc.Ref().bv(w, nbits, with_select=False) if orc.ref_available() else None
+            for what in (0, 1, 2):
+                got = bv.serialize(what)
+                assert got == ob.serialize(what), (cid, what, "oracle")
+                if rb is not None:
+                    assert got == rb.serialize(what), (cid, what, "reference")
+
+
+def test_out_of_domain_is_defined(pkg):
+    w = cases.random_words(1000, 5)
+    with pkg.BitVector(w, 1000) as bv:
+        r = bv.rank(np.array([1000, 1001, 2**63], dtype=np.uint64))
+        assert r[0] == bv.arg_count(1) and r[1] == pkg.NPOS and r[2] == pkg.NPOS
+        m = bv.arg_count(1)
+        s = bv.select(np.array([0, m, m + 1], dtype=np.uint64))
+        assert s[0] == pkg.NPOS and s[2] == pkg.NPOS and s[1] < 1000
+        assert bv.access(np.array([1000], dtype=np.uint64))[0] == pkg.NPOS
+        assert len(bv.rank(np.zeros(0, np.uint64))) == 0
+
+
+def test_device_buffers_and_streams(pkg, oracle):
+    """device-resident queries (torch tensors) on a non-default stream give the same answers as host buffers"""
+    import torch
+
+    nbits = 3_000_001
+    w = cases.random_words(nbits, 21, dirty_tail=True)
+    idx = cases.rank_queries(nbits, 4, 200000)
+    want = oracle.bv(w, nbits).rank(idx, 1)
+    with pkg.BitVector(torch.from_numpy(w.view(np.int64)).cuda(), nbits) as bv:
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            d_idx = torch.from_numpy(idx.view(np.int64)).cuda()
+            got = bv.rank(d_idx, 1)
+        s.synchronize()
+        assert (got.cpu().numpy().view(np.uint64) == want).all()
+        # host path with more than one staging chunk
+        big = np.tile(idx, 25)  # 5e6 queries > 4 Mi chunk
+        assert (bv.rank(big, 1) == np.tile(want, 25)).all()
+
+
+def test_density_sweep_properties(pkg, oracle):
+    """size-independent properties on 2^27-bit vectors over the density sweep of BASELINE config 3:
+    select(rank(i)+1) >= i, rank(select(k)) == k-1, rank0 + rank1 == idx; spot-checked against the oracle"""
+    nbits = (1 << 27) + 12345
+    for d in (0.01, 0.1, 0.5, 0.9):
+        w = cases.bernoulli_words(nbits, d, int(d * 1000))
+        with pkg.BitVector(w, nbits) as bv:
+            idx = cases.rank_queries(nbits, 8, 500000)
+            r1, r0 = bv.rank(idx, 1), bv.rank(idx, 0)
+            assert (r1 + r0 == idx).all()
+            for b, r in ((1, r1), (0, r0)):
+                m = bv.arg_count(b)
+                k = cases.select_queries(m, 9, 500000)
+                p = bv.select(k, b)
+                assert (bv.rank(p, b) == k - 1).all() and (bv.access(p) == b).all()
+                ok = r < m
+                nxt = bv.select(r[ok] + 1, b)
+                assert (nxt >= idx[ok]).all()
+            o = oracle.bv(w, nbits)
+            sub = idx[:20000]
+            assert (bv.rank(sub, 1) == o.rank(sub, 1)).all()
+            ks = cases.select_queries(bv.arg_count(1), 10, 20000)
+            assert (bv.select(ks, 1) == o.select(ks, 1)).all()
