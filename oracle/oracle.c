@@ -4,7 +4,7 @@
  *         select_support_mcl (a4).
  * Citations are relative to /root/reference/include/sdsl/.
  */
-#include "oracle.h"
+#include "oracle_priv.h"
 
 #include <stdlib.h>
 #include <string.h>
@@ -52,7 +52,7 @@ uint32_t orc_lo(uint64_t x)
     return r;
 }
 
-static uint64_t lo_set(uint32_t k) /* bits.hpp:194-211 */
+uint64_t orc__lo_set(uint32_t k) /* bits.hpp:194-211 */
 {
     return k >= 64 ? ~0ULL : ((1ULL << k) - 1);
 }
@@ -66,24 +66,24 @@ uint64_t orc_read_int(const uint64_t *d, uint64_t bitpos, uint8_t len)
         return 0;
     if (off + len > 64) {
         uint64_t lo = w[0] >> off;
-        uint64_t hi = w[1] & lo_set(off + len - 64);
+        uint64_t hi = w[1] & orc__lo_set(off + len - 64);
         return lo | (hi << (64 - off));
     }
-    return (w[0] >> off) & lo_set(len);
+    return (w[0] >> off) & orc__lo_set(len);
 }
 
-static void write_int(uint64_t *d, uint64_t bitpos, uint64_t x, uint8_t len) /* bits.hpp:748-773 */
+void orc__write_int(uint64_t *d, uint64_t bitpos, uint64_t x, uint8_t len) /* bits.hpp:748-773 */
 {
     uint64_t *w = d + (bitpos >> 6);
     uint32_t off = (uint32_t)(bitpos & 63);
     if (len == 0)
         return;
-    x &= lo_set(len);
+    x &= orc__lo_set(len);
     if (off + len > 64) {
-        w[0] = (w[0] & lo_set(off)) | (x << off);
-        w[1] = (w[1] & ~lo_set(off + len - 64)) | (x >> (64 - off));
+        w[0] = (w[0] & orc__lo_set(off)) | (x << off);
+        w[1] = (w[1] & ~orc__lo_set(off + len - 64)) | (x >> (64 - off));
     } else {
-        uint64_t m = lo_set(len) << off;
+        uint64_t m = orc__lo_set(len) << off;
         w[0] = (w[0] & ~m) | (x << off);
     }
 }
@@ -92,7 +92,7 @@ static void write_int(uint64_t *d, uint64_t bitpos, uint64_t x, uint8_t len) /* 
 /* byte buffer + int_vector                                                                   */
 /* ------------------------------------------------------------------------------------------ */
 
-static void buf_put(orc_buf *b, const void *src, uint64_t n)
+void orc__buf_put(orc_buf *b, const void *src, uint64_t n)
 {
     if (b->n + n > b->cap) {
         uint64_t c = b->cap ? b->cap * 2 : 4096;
@@ -104,9 +104,9 @@ static void buf_put(orc_buf *b, const void *src, uint64_t n)
     memcpy(b->p + b->n, src, n);
     b->n += n;
 }
-static void buf_u64(orc_buf *b, uint64_t x)
+void orc__buf_u64(orc_buf *b, uint64_t x)
 {
-    buf_put(b, &x, 8);
+    orc__buf_put(b, &x, 8);
 }
 void orc_buf_free(orc_buf *b)
 {
@@ -114,7 +114,7 @@ void orc_buf_free(orc_buf *b)
     b->p = NULL;
     b->n = b->cap = 0;
 }
-static uint64_t buf_finish(orc_buf *b, uint8_t *out, uint64_t cap)
+uint64_t orc__buf_finish(orc_buf *b, uint8_t *out, uint64_t cap)
 {
     uint64_t n = b->n;
     if (out != NULL && n <= cap)
@@ -123,7 +123,7 @@ static uint64_t buf_finish(orc_buf *b, uint8_t *out, uint64_t cap)
     return n;
 }
 
-static void iv_init(orc_iv *v, uint64_t size, uint8_t width)
+void orc__iv_init(orc_iv *v, uint64_t size, uint8_t width)
 {
     uint64_t words = ((size * width + 63) >> 6) + 1;
     v->size = size;
@@ -140,30 +140,34 @@ uint64_t orc_iv_get(const orc_iv *v, uint64_t i) /* int_vector.hpp:1865-1869 */
 {
     return orc_read_int(v->data, i * v->width, v->width);
 }
-static void iv_set(orc_iv *v, uint64_t i, uint64_t x)
+void orc__iv_set(orc_iv *v, uint64_t i, uint64_t x)
 {
-    write_int(v->data, i * v->width, x, v->width);
+    orc__write_int(v->data, i * v->width, x, v->width);
 }
 /* int_vector.hpp:904-916,1995-2004: header (width<<56 | bit_size) then ceil(bit_size/64) words */
-static void iv_serialize(orc_buf *b, const orc_iv *v)
+void orc__iv_serialize(orc_buf *b, const orc_iv *v)
 {
     uint64_t bits = v->size * v->width;
-    buf_u64(b, ((uint64_t)v->width << 56) | bits);
+    orc__buf_u64(b, ((uint64_t)v->width << 56) | bits);
     if (bits)
-        buf_put(b, v->data, ((bits + 63) >> 6) * 8);
+        orc__buf_put(b, v->data, ((bits + 63) >> 6) * 8);
 }
 static void empty_iv_serialize(orc_buf *b) /* default int_vector<0>: width 64, size 0 */
 {
-    buf_u64(b, (uint64_t)64 << 56);
+    orc__buf_u64(b, (uint64_t)64 << 56);
 }
 
+void orc__bv_serialize_into(orc_buf *b, const uint64_t *w, uint64_t nbits)
+{
+    orc__buf_u64(b, ((uint64_t)1 << 56) | nbits);
+    if (nbits)
+        orc__buf_put(b, w, ((nbits + 63) >> 6) * 8);
+}
 uint64_t orc_bv_serialize(const uint64_t *w, uint64_t nbits, uint8_t *out, uint64_t cap)
 {
     orc_buf b = {0, 0, 0};
-    buf_u64(&b, ((uint64_t)1 << 56) | nbits);
-    if (nbits)
-        buf_put(&b, w, ((nbits + 63) >> 6) * 8);
-    return buf_finish(&b, out, cap);
+    orc__bv_serialize_into(&b, w, nbits);
+    return orc__buf_finish(&b, out, cap);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -219,7 +223,7 @@ uint64_t orc_rank_v(const uint64_t *w, const uint64_t *B, int b, uint64_t idx)
     uint64_t r = p[0] + ((p[1] >> (63 - 9 * ((idx & 0x1FF) >> 6))) & 0x1FF);
     if (idx & 0x3F) {
         uint64_t x = w[idx >> 6];
-        r += orc_cnt((b ? x : ~x) & lo_set((uint32_t)(idx & 0x3F)));
+        r += orc_cnt((b ? x : ~x) & orc__lo_set((uint32_t)(idx & 0x3F)));
     }
     return r;
 }
@@ -231,13 +235,17 @@ void orc_rank_v_batch(const uint64_t *w, const uint64_t *B, int b, const uint64_
         out[k] = orc_rank_v(w, B, b, idx[k]);
 }
 
+void orc__rank_v_serialize_into(orc_buf *b, const uint64_t *B, uint64_t nbits)
+{
+    uint64_t words = orc_rank_v_table_words(nbits);
+    orc__buf_u64(b, ((uint64_t)64 << 56) | (words * 64));
+    orc__buf_put(b, B, words * 8);
+}
 uint64_t orc_rank_v_serialize(const uint64_t *B, uint64_t nbits, uint8_t *out, uint64_t cap)
 {
     orc_buf b = {0, 0, 0};
-    uint64_t words = orc_rank_v_table_words(nbits);
-    buf_u64(&b, ((uint64_t)64 << 56) | (words * 64));
-    buf_put(&b, B, words * 8);
-    return buf_finish(&b, out, cap);
+    orc__rank_v_serialize_into(&b, B, nbits);
+    return orc__buf_finish(&b, out, cap);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -264,16 +272,16 @@ static void init_slow(orc_selmcl *s, const uint64_t *w)
         if (cnt % SBS == 0 || cnt == s->arg_cnt) {
             uint64_t last = (cnt - 1) % SBS, j;
             uint64_t diff = pos[last] - pos[0];
-            iv_set(&s->superblock, sbc, pos[0]);
+            orc__iv_set(&s->superblock, sbc, pos[0]);
             if (diff > s->logn4) {
                 s->has_long = 1;
-                iv_init(&s->longsb[sbc], SBS, (uint8_t)(orc_hi(pos[last]) + 1));
+                orc__iv_init(&s->longsb[sbc], SBS, (uint8_t)(orc_hi(pos[last]) + 1));
                 for (j = 0; j <= last; ++j)
-                    iv_set(&s->longsb[sbc], j, pos[j]);
+                    orc__iv_set(&s->longsb[sbc], j, pos[j]);
             } else {
-                iv_init(&s->mini[sbc], 64, (uint8_t)(orc_hi(diff) + 1));
+                orc__iv_init(&s->mini[sbc], 64, (uint8_t)(orc_hi(diff) + 1));
                 for (j = 0; j <= last; j += 64)
-                    iv_set(&s->mini[sbc], j / 64, pos[j] - pos[0]);
+                    orc__iv_set(&s->mini[sbc], j / 64, pos[j] - pos[0]);
             }
             ++sbc;
         }
@@ -302,7 +310,7 @@ static void init_fast(orc_selmcl *s, const uint64_t *w)
             last_k64_sum += 64;
             if (last_k64 == SBS + 1) {
                 uint64_t plast = pos[last_k64 - 65], ii, j, k, diff;
-                iv_set(&s->superblock, sbc, pos[0]);
+                orc__iv_set(&s->superblock, sbc, pos[0]);
                 for (ii = pos[last_k64 - 65] + 1, j = last_k64 - 65; ii < s->nbits && j < SBS; ++ii)
                     if (found_arg(w, ii, s->b)) {
                         plast = ii;
@@ -311,14 +319,14 @@ static void init_fast(orc_selmcl *s, const uint64_t *w)
                 diff = plast - pos[0];
                 if (diff > s->logn4) {
                     s->has_long = 1;
-                    iv_init(&s->longsb[sbc], SBS, (uint8_t)(orc_hi(plast) + 1));
+                    orc__iv_init(&s->longsb[sbc], SBS, (uint8_t)(orc_hi(plast) + 1));
                     for (j = pos[0], k = 0; k < SBS && j <= plast; ++j)
                         if (found_arg(w, j, s->b))
-                            iv_set(&s->longsb[sbc], k++, j);
+                            orc__iv_set(&s->longsb[sbc], k++, j);
                 } else {
-                    iv_init(&s->mini[sbc], 64, (uint8_t)(orc_hi(diff) + 1));
+                    orc__iv_init(&s->mini[sbc], 64, (uint8_t)(orc_hi(diff) + 1));
                     for (j = 0; j < SBS; j += 64)
-                        iv_set(&s->mini[sbc], j / 64, pos[j] - pos[0]);
+                        orc__iv_set(&s->mini[sbc], j / 64, pos[j] - pos[0]);
                 }
                 ++sbc;
                 last_k64 = 1;
@@ -329,10 +337,10 @@ static void init_fast(orc_selmcl *s, const uint64_t *w)
     if (last_k64 > 1) {
         uint64_t k = 0;
         s->has_long = 1;
-        iv_init(&s->longsb[sbc], SBS, (uint8_t)(orc_hi(s->nbits - 1) + 1));
+        orc__iv_init(&s->longsb[sbc], SBS, (uint8_t)(orc_hi(s->nbits - 1) + 1));
         for (i = pos[0]; i < s->nbits; ++i)
             if (found_arg(w, i, s->b))
-                iv_set(&s->longsb[sbc], k++, i);
+                orc__iv_set(&s->longsb[sbc], k++, i);
         ++sbc;
     }
     free(pos);
@@ -352,14 +360,14 @@ orc_selmcl *orc_select_mcl_build(const uint64_t *w, uint64_t nbits, int b)
     for (k = 0; k < W; ++k) {
         uint64_t x = w[k];
         if (k == W - 1 && (nbits & 63))
-            x &= lo_set((uint32_t)(nbits & 63));
+            x &= orc__lo_set((uint32_t)(nbits & 63));
         ones += orc_cnt(x);
     }
     s->arg_cnt = b ? ones : nbits - ones;
     if (s->arg_cnt == 0)
         return s;
     s->sb = (s->arg_cnt + SBS - 1) / SBS;
-    iv_init(&s->superblock, s->sb, (uint8_t)s->logn);
+    orc__iv_init(&s->superblock, s->sb, (uint8_t)s->logn);
     s->longsb = (orc_iv *)calloc(s->sb + 1, sizeof(orc_iv));
     s->mini = (orc_iv *)calloc(s->sb + 1, sizeof(orc_iv));
     if (nbits < 100000) /* ctor dispatch, :121-128 */
@@ -403,7 +411,7 @@ uint64_t orc_select_mcl(const orc_selmcl *s, const uint64_t *w, uint64_t i)
     pos += 1;
     wp = pos >> 6;
     wo = (uint32_t)(pos & 63);
-    x = (s->b ? w[wp] : ~w[wp]) & ~lo_set(wo);
+    x = (s->b ? w[wp] : ~w[wp]) & ~orc__lo_set(wo);
     a = orc_cnt(x);
     if (a >= i)
         return (wp << 6) + orc_sel(x, (uint32_t)i);
@@ -426,37 +434,41 @@ void orc_select_mcl_batch(const orc_selmcl *s, const uint64_t *w, const uint64_t
 }
 
 /* select_support_mcl.hpp:474-518 */
-uint64_t orc_select_mcl_serialize(const orc_selmcl *s, uint8_t *out, uint64_t cap)
+void orc__select_mcl_serialize_into(orc_buf *bp, const orc_selmcl *s)
 {
-    orc_buf b = {0, 0, 0};
     uint64_t k;
-    buf_u64(&b, s->arg_cnt);
+    orc__buf_u64(bp, s->arg_cnt);
     if (s->arg_cnt) {
         orc_iv mol;
-        iv_serialize(&b, &s->superblock);
+        orc__iv_serialize(bp, &s->superblock);
         if (s->has_long) {
-            iv_init(&mol, s->sb, 1);
+            orc__iv_init(&mol, s->sb, 1);
             for (k = 0; k < s->sb; ++k)
-                iv_set(&mol, k, s->mini[k].size != 0);
-            iv_serialize(&b, &mol);
+                orc__iv_set(&mol, k, s->mini[k].size != 0);
+            orc__iv_serialize(bp, &mol);
         } else {
-            iv_init(&mol, 0, 1);
-            iv_serialize(&b, &mol);
+            orc__iv_init(&mol, 0, 1);
+            orc__iv_serialize(bp, &mol);
         }
         for (k = 0; k < s->sb; ++k) {
             if (s->has_long && !orc_iv_get(&mol, k)) {
                 if (s->longsb[k].size)
-                    iv_serialize(&b, &s->longsb[k]);
+                    orc__iv_serialize(bp, &s->longsb[k]);
                 else
-                    empty_iv_serialize(&b);
+                    empty_iv_serialize(bp);
             } else {
                 if (s->mini[k].size)
-                    iv_serialize(&b, &s->mini[k]);
+                    orc__iv_serialize(bp, &s->mini[k]);
                 else
-                    empty_iv_serialize(&b);
+                    empty_iv_serialize(bp);
             }
         }
         orc_iv_free(&mol);
     }
-    return buf_finish(&b, out, cap);
+}
+uint64_t orc_select_mcl_serialize(const orc_selmcl *s, uint8_t *out, uint64_t cap)
+{
+    orc_buf b = {0, 0, 0};
+    orc__select_mcl_serialize_into(&b, s);
+    return orc__buf_finish(&b, out, cap);
 }

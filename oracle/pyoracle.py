@@ -96,10 +96,23 @@ class Oracle:
         L.orc_select_mcl_serialize.argtypes = [C.c_void_p, u8p, C.c_uint64]
         L.orc_bv_serialize.restype = C.c_uint64
         L.orc_bv_serialize.argtypes = [u64p, C.c_uint64, u8p, C.c_uint64]
+        L.orc_wt_huff_build.restype = C.c_void_p
+        L.orc_wt_huff_build.argtypes = [u8p, C.c_uint64]
+        L.orc_wt_huff_free.argtypes = [C.c_void_p]
+        for f in (L.orc_wt_huff_rank_batch, L.orc_wt_huff_select_batch):
+            f.restype = None
+            f.argtypes = [C.c_void_p, u64p, u8p, C.c_uint64, u64p]
+        L.orc_wt_huff_access_batch.restype = None
+        L.orc_wt_huff_access_batch.argtypes = [C.c_void_p, u64p, C.c_uint64, u64p, u64p]
+        L.orc_wt_huff_serialize.restype = C.c_uint64
+        L.orc_wt_huff_serialize.argtypes = [C.c_void_p, u8p, C.c_uint64]
 
     # -- plain bit vector ------------------------------------------------------------------
     def bv(self, words, nbits):
         return OracleBV(self, words, nbits)
+
+    def wt_huff(self, text):
+        return OracleWtHuff(self, text)
 
 
 class OracleBV:
@@ -146,6 +159,48 @@ class OracleBV:
         for h in self.sel.values():
             self.L.orc_select_mcl_free(h)
         self.sel = {}
+
+
+def _text(text):
+    return _u8(np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else text)
+
+
+class OracleWtHuff:
+    def __init__(self, o, text):
+        self.L = o.L
+        t = _text(text)
+        self.size = len(t)
+        self.h = self.L.orc_wt_huff_build(_p8(t if len(t) else np.zeros(1, np.uint8)), len(t))
+
+    def rank(self, i, c):
+        i, c = _u64(i), _u8(c)
+        out = np.zeros(len(i), dtype=np.uint64)
+        self.L.orc_wt_huff_rank_batch(self.h, _p64(i), _p8(c), len(i), _p64(out))
+        return out
+
+    def select(self, i, c):
+        i, c = _u64(i), _u8(c)
+        out = np.zeros(len(i), dtype=np.uint64)
+        self.L.orc_wt_huff_select_batch(self.h, _p64(i), _p8(c), len(i), _p64(out))
+        return out
+
+    def inverse_select(self, i):
+        i = _u64(i)
+        sym = np.zeros(len(i), dtype=np.uint64)
+        rnk = np.zeros(len(i), dtype=np.uint64)
+        self.L.orc_wt_huff_access_batch(self.h, _p64(i), len(i), _p64(sym), _p64(rnk))
+        return rnk, sym
+
+    def access(self, i):
+        return self.inverse_select(i)[1]
+
+    def serialize(self):
+        return _blob(self.L.orc_wt_huff_serialize, self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_wt_huff_free(self.h)
+            self.h = None
 
 
 # ------------------------------------------------------------------------------------------------

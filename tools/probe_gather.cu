@@ -88,6 +88,7 @@ void run(const char* name, const uint8_t* base, uint64_t bytes, const uint8_t* b
 
 int main(int argc, char** argv) {
   double lg = argc > 1 ? atof(argv[1]) : 30.2;
+  if (argc > 3) { cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, atoi(argv[3])); printf("pre-set granularity %s: %s\n", argv[3], cudaGetErrorString(e)); }
   uint64_t n = argc > 2 ? (uint64_t)atof(argv[2]) : 100000000ull;
   uint64_t bytes = ((uint64_t)exp2(lg)) & ~255ull;
   uint8_t *base, *base2; uint64_t *idx, *out;
@@ -110,6 +111,25 @@ int main(int argc, char** argv) {
   run<24, 1>("16 B table + 8 B word (SDSL)", base, bytes, base2, idx, n, out, 8);
   run<24, 2>("16 B table + 8 B word (SDSL)", base, bytes, base2, idx, n, out, 8);
   run<24, 4>("16 B table + 8 B word (SDSL)", base, bytes, base2, idx, n, out, 8);
+  // L2 fetch granularity: ncu shows the default path reading FOUR sectors from DRAM per 32-byte gather
+  for (int gran : {32, 64, 128}) {
+    cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    size_t got = 0; cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+    printf("cudaLimitMaxL2FetchGranularity <- %d : %s, reads back %zu\n", gran, cudaGetErrorString(e), got);
+    run<32, 2>("1 x 32 B (sector block)", base, bytes, base2, idx, n, out, 8);
+    run<64, 2>("1 x 64 B", base, bytes, base2, idx, n, out, 8);
+    run<128, 2>("1 x 128 B (line)", base, bytes, base2, idx, n, out, 8);
+    run<128, 4>("1 x 128 B (line)", base, bytes, base2, idx, n, out, 8);
+    run<24, 2>("16 B table + 8 B word (SDSL)", base, bytes, base2, idx, n, out, 8);
+  }
+  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+  printf("footprint sweep at granularity 32\n");
+  for (double g : {0.125, 0.25, 0.5, 1.0, 2.0, 4.0, 8.0}) {
+    uint64_t fb = (uint64_t)(g * 1073741824.0);
+    if (fb > bytes) break;
+    printf("footprint %.3f GiB: ", g);
+    run<32, 2>("1 x 32 B", base, fb, base2, idx, n, out, 8);
+  }
   // L2-resident footprint for contrast
   uint64_t small = 64ull << 20;
   printf("footprint 64 MiB (L2 resident)\n");
