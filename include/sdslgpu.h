@@ -96,6 +96,32 @@ int sdslgpu_select(const sdslgpu_handle *h, int b, const uint64_t *i, uint64_t n
  * (int_vector.hpp:1900-1904), rrr_vector (rrr_vector.hpp:276-298), sd_vector (sd_vector.hpp:328-349). */
 int sdslgpu_access(const sdslgpu_handle *h, const uint64_t *idx, uint64_t n, uint64_t *out, void *stream);
 
+/* ---- wavelet trees ---------------------------------------------------------------------------- */
+
+/* Replaces wt_huff<>(text) = wt_pc<huff_shape,...> ctor (wt_pc.hpp:194-248, wt_huff.hpp:82-115,
+ * wt_helper.hpp:230-327).  `text` is a HOST buffer of n bytes (any byte values).  The Huffman shape is
+ * computed on the host with the reference's tie-breaking, so the concatenated bit vector and node table
+ * equal the reference's; rank/select structures over it are built on the device. */
+int sdslgpu_wt_huff_create(const uint8_t *text, uint64_t n, int device, uint32_t flags, sdslgpu_handle **out);
+
+/* number of distinct symbols (wt.sigma, wt_pc.hpp:177) */
+int sdslgpu_wt_sigma(const sdslgpu_handle *h, uint64_t *sigma);
+
+/* out[k] = occurrences of symbol c[k] in [0, i[k]),  0 <= i[k] <= size.  A symbol that does not occur
+ * gives 0.  `c` points to uint8_t symbols for byte trees (KIND_WT_HUFF, KIND_CSA_WT) and to uint64_t
+ * symbols for KIND_WT_INT.  Replaces wt_pc::rank (wt_pc.hpp:371-399), wt_int::rank (wt_int.hpp:379-409). */
+int sdslgpu_wt_rank(const sdslgpu_handle *h, const uint64_t *i, const void *c, uint64_t n, uint64_t *out, void *stream);
+
+/* out[k] = position of the i[k]-th occurrence of c[k], 1 <= i[k] <= rank(size, c[k]).  A symbol that does
+ * not occur gives size() (as the reference, wt_pc.hpp:447-450); i beyond the occurrences gives
+ * SDSLGPU_NPOS.  Replaces wt_pc::select (wt_pc.hpp:443-474), wt_int::select (wt_int.hpp:456-507). */
+int sdslgpu_wt_select(const sdslgpu_handle *h, const uint64_t *i, const void *c, uint64_t n, uint64_t *out, void *stream);
+
+/* sym_out[k] = wt[i[k]]; if rank_out != NULL also rank_out[k] = rank(i[k], wt[i[k]]) (inverse_select).
+ * Replaces wt_pc::operator[] / inverse_select (wt_pc.hpp:336-357, 411-430), wt_int (wt_int.hpp:340-367,
+ * 418-445). */
+int sdslgpu_wt_access(const sdslgpu_handle *h, const uint64_t *i, uint64_t n, uint64_t *sym_out, uint64_t *rank_out, void *stream);
+
 /* ---- construction parity / interchange ------------------------------------------------------ */
 
 /* Copies the SDSL-format serialisation of one component of a KIND_BV handle into `buf`

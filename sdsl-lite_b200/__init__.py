@@ -45,6 +45,11 @@ _SIGNATURES = [
     ("sdslgpu_select", C.c_int, [vp, C.c_int, vp, C.c_uint64, vp, vp]),
     ("sdslgpu_access", C.c_int, [vp, vp, C.c_uint64, vp, vp]),
     ("sdslgpu_bv_serialize", C.c_int, [vp, C.c_int, vp, C.c_uint64, u64p]),
+    ("sdslgpu_wt_huff_create", C.c_int, [vp, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(vp)]),
+    ("sdslgpu_wt_sigma", C.c_int, [vp, u64p]),
+    ("sdslgpu_wt_rank", C.c_int, [vp, vp, vp, C.c_uint64, vp, vp]),
+    ("sdslgpu_wt_select", C.c_int, [vp, vp, vp, C.c_uint64, vp, vp]),
+    ("sdslgpu_wt_access", C.c_int, [vp, vp, C.c_uint64, vp, vp, vp]),
 ]
 
 _lib = None
@@ -218,3 +223,59 @@ class BitVector(_Handle):
         buf = np.empty(n.value, dtype=np.uint8)
         _check(lib().sdslgpu_bv_serialize(self._h, what, buf.ctypes.data, n.value, C.byref(n)))
         return buf.tobytes()
+
+
+class _WaveletTreeOps:
+    """wt.rank(i, c) / wt.select(i, c) / wt[i] / inverse_select(i) in batch form (SURVEY §8(b) wavelet-tree concept)"""
+
+    _sym_dtype = np.uint8
+
+    @property
+    def sigma(self):
+        v = C.c_uint64()
+        _check(lib().sdslgpu_wt_sigma(self._h, C.byref(v)))
+        return v.value
+
+    def wt_rank(self, i, c, out=None, stream=None):
+        p, n, k1, _ = _in_ptr(i)
+        pc, nc, k2, _ = _in_ptr(c, self._sym_dtype)
+        assert n == nc
+        po, o, _k = _out_like(i, n, out)
+        _check(lib().sdslgpu_wt_rank(self._h, p, pc, n, po, _stream_ptr(stream, i)))
+        return o
+
+    def wt_select(self, i, c, out=None, stream=None):
+        p, n, k1, _ = _in_ptr(i)
+        pc, nc, k2, _ = _in_ptr(c, self._sym_dtype)
+        assert n == nc
+        po, o, _k = _out_like(i, n, out)
+        _check(lib().sdslgpu_wt_select(self._h, p, pc, n, po, _stream_ptr(stream, i)))
+        return o
+
+    def wt_access(self, i, stream=None):
+        p, n, k1, _ = _in_ptr(i)
+        po, o, _k = _out_like(i, n)
+        _check(lib().sdslgpu_wt_access(self._h, p, n, po, None, _stream_ptr(stream, i)))
+        return o
+
+    def inverse_select(self, i, stream=None):
+        """-> (rank(i, wt[i]), wt[i])  (wt_pc.hpp:411-430)"""
+        p, n, k1, _ = _in_ptr(i)
+        ps, sym, _k = _out_like(i, n)
+        pr, rnk, _k2 = _out_like(i, n)
+        _check(lib().sdslgpu_wt_access(self._h, p, n, ps, pr, _stream_ptr(stream, i)))
+        return rnk, sym
+
+
+class WtHuff(_Handle, _WaveletTreeOps):
+    """wt_huff<> over a byte text (host bytes / numpy uint8)."""
+
+    def __init__(self, text, device=0, flags=F_DEFAULT):
+        super().__init__()
+        t = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else np.ascontiguousarray(text, dtype=np.uint8)
+        self._text_keep = t
+        _check(lib().sdslgpu_wt_huff_create(t.ctypes.data if len(t) else None, len(t), device, flags, C.byref(self._h)))
+
+    rank = _WaveletTreeOps.wt_rank
+    select = _WaveletTreeOps.wt_select
+    access = _WaveletTreeOps.wt_access

@@ -237,6 +237,36 @@ static int check_handle(sdslgpu_handle const * h)
     return SDSLGPU_OK;
 }
 
+static bool is_byte_wt(sdslgpu_handle const * h)
+{
+    return h->kind == SDSLGPU_KIND_WT_HUFF || h->kind == SDSLGPU_KIND_CSA_WT;
+}
+
+// validates the device (no CPU fallback) and allocates an empty handle of the given kind
+static int new_handle(int kind, int device, uint32_t flags, sdslgpu_handle ** out)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess)
+    {
+        cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
+        return SDSLGPU_ECUDA;
+    }
+    if (device < 0 || device >= ndev)
+    {
+        set_error("device %d out of range (%d CUDA devices); there is no CPU fallback", device, ndev);
+        return SDSLGPU_ECUDA;
+    }
+    sdslgpu_handle * h = new (std::nothrow) sdslgpu_handle;
+    if (!h)
+        return SDSLGPU_ENOMEM;
+    h->kind = kind;
+    h->device = device;
+    h->flags = flags;
+    *out = h;
+    return SDSLGPU_OK;
+}
+
 } // namespace sdslgpu
 
 using namespace sdslgpu;
@@ -293,7 +323,7 @@ extern "C"
         PtrSpace sp = PtrSpace::Host;
         int st = nbits ? classify(words, device, &sp) : SDSLGPU_OK;
         if (st == SDSLGPU_OK)
-            st = bv_build(h, words, sp == PtrSpace::Device, nbits, nullptr);
+            st = bv_build(h->pool, h->bv, flags, words, sp == PtrSpace::Device, nbits, nullptr);
         if (st != SDSLGPU_OK)
         {
             h->pool.release_all();
@@ -330,6 +360,9 @@ extern "C"
         {
         case SDSLGPU_KIND_BV:
             *size = h->bv.nbits;
+            return SDSLGPU_OK;
+        case SDSLGPU_KIND_WT_HUFF:
+            *size = h->wt.size;
             return SDSLGPU_OK;
         }
         return SDSLGPU_ENOTSUP;
@@ -374,7 +407,7 @@ extern "C"
         {
         case SDSLGPU_KIND_BV:
             return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
-                return bv_rank_device(h, b, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
+                return bv_rank_device(h->bv, h->flags, b, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
             });
         }
         set_error("sdslgpu_rank: unsupported handle kind %d", h->kind);
@@ -399,7 +432,7 @@ extern "C"
         {
         case SDSLGPU_KIND_BV:
             return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
-                return bv_select_device(h, b, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
+                return bv_select_device(h->bv, b, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
             });
         }
         set_error("sdslgpu_select: unsupported handle kind %d", h->kind);
@@ -419,7 +452,7 @@ extern "C"
         {
         case SDSLGPU_KIND_BV:
             return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
-                return bv_access_device(h, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
+                return bv_access_device(h->bv, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
             });
         }
         set_error("sdslgpu_access: unsupported handle kind %d", h->kind);
@@ -436,7 +469,7 @@ extern "C"
             set_error("sdslgpu_bv_serialize needs a handle created with SDSLGPU_F_SDSL_LAYOUT");
             return SDSLGPU_ENOTSUP;
         }
-        sdslgpu_bv_image const & v = h->bv;
+        BvImage const & v = h->bv;
         uint64_t header, words;
         uint64_t const * src;
         if (what == 0)
@@ -466,6 +499,98 @@ extern "C"
         if (words)
             SG_CUDA(cudaMemcpy(static_cast<uint8_t *>(buf) + 8, src, words * 8, cudaMemcpyDeviceToHost));
         return SDSLGPU_OK;
+    }
+
+    // -------------------------------------------------------------------------------- wavelet trees
+    int sdslgpu_wt_huff_create(const uint8_t * text, uint64_t n, int device, uint32_t flags, sdslgpu_handle ** out)
+    {
+        if (!out || (!text && n))
+        {
+            set_error("sdslgpu_wt_huff_create: null argument");
+            return SDSLGPU_EINVAL;
+        }
+        *out = nullptr;
+        sdslgpu_handle * h = nullptr;
+        SG_TRY(new_handle(SDSLGPU_KIND_WT_HUFF, device, flags, &h));
+        DeviceGuard g(device);
+        int st = wt_huff_build_from_text(h, text, n, nullptr);
+        if (st != SDSLGPU_OK)
+        {
+            h->pool.release_all();
+            delete h;
+            return st;
+        }
+        *out = h;
+        return SDSLGPU_OK;
+    }
+
+    int sdslgpu_wt_sigma(const sdslgpu_handle * h, uint64_t * sigma)
+    {
+        SG_TRY(check_handle(h));
+        if (!sigma || !is_byte_wt(h))
+            return SDSLGPU_EINVAL;
+        *sigma = h->wt.sigma;
+        return SDSLGPU_OK;
+    }
+
+    int sdslgpu_wt_rank(const sdslgpu_handle * h, const uint64_t * i, const void * c, uint64_t n, uint64_t * out, void * stream)
+    {
+        SG_TRY(check_handle(h));
+        if (n && (!out || !c))
+        {
+            set_error("sdslgpu_wt_rank: null argument");
+            return SDSLGPU_EINVAL;
+        }
+        if (is_byte_wt(h))
+        {
+            Column in[2] = {{i, nullptr, 8}, {c, nullptr, 1}};
+            Column o{nullptr, out, 8};
+            return run_batch(h, in, 2, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
+                return wt_rank_device(h, static_cast<uint64_t const *>(ip[0]), static_cast<uint8_t const *>(ip[1]), cnt, static_cast<uint64_t *>(op[0]), s);
+            });
+        }
+        set_error("sdslgpu_wt_rank: unsupported handle kind %d", h->kind);
+        return SDSLGPU_ENOTSUP;
+    }
+
+    int sdslgpu_wt_select(const sdslgpu_handle * h, const uint64_t * i, const void * c, uint64_t n, uint64_t * out, void * stream)
+    {
+        SG_TRY(check_handle(h));
+        if (n && (!out || !c))
+        {
+            set_error("sdslgpu_wt_select: null argument");
+            return SDSLGPU_EINVAL;
+        }
+        if (is_byte_wt(h))
+        {
+            Column in[2] = {{i, nullptr, 8}, {c, nullptr, 1}};
+            Column o{nullptr, out, 8};
+            return run_batch(h, in, 2, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
+                return wt_select_device(h, static_cast<uint64_t const *>(ip[0]), static_cast<uint8_t const *>(ip[1]), cnt, static_cast<uint64_t *>(op[0]), s);
+            });
+        }
+        set_error("sdslgpu_wt_select: unsupported handle kind %d", h->kind);
+        return SDSLGPU_ENOTSUP;
+    }
+
+    int sdslgpu_wt_access(const sdslgpu_handle * h, const uint64_t * i, uint64_t n, uint64_t * sym_out, uint64_t * rank_out, void * stream)
+    {
+        SG_TRY(check_handle(h));
+        if (n && !sym_out)
+        {
+            set_error("sdslgpu_wt_access: null output");
+            return SDSLGPU_EINVAL;
+        }
+        if (is_byte_wt(h))
+        {
+            Column in{i, nullptr, 8};
+            Column o[2] = {{nullptr, sym_out, 8}, {nullptr, rank_out, 8}};
+            return run_batch(h, &in, 1, o, 2, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
+                return wt_access_device(h, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), static_cast<uint64_t *>(op[1]), s);
+            });
+        }
+        set_error("sdslgpu_wt_access: unsupported handle kind %d", h->kind);
+        return SDSLGPU_ENOTSUP;
     }
 
 } // extern "C"

@@ -9,6 +9,7 @@
 // plus, under SDSLGPU_F_SDSL_LAYOUT, the reference's own table (m_basic_block) built on the device,
 // byte-identical to the reference's, and a rank kernel that reads it exactly as the reference does.
 #include "internal.h"
+#include "bv_device.cuh"
 #include "scan.cuh"
 
 namespace sdslgpu
@@ -179,68 +180,8 @@ __global__ void __launch_bounds__(kThreads) bv_rank_sdsl_kernel(uint64_t const *
 // select
 // ------------------------------------------------------------------------------------------------
 template <int B>
-__device__ __forceinline__ uint64_t abs_before(bvblock const * __restrict__ blocks, uint64_t const * __restrict__ top, uint64_t b)
-{
-    uint64_t a1 = __ldg(top + (b >> kSuperShift)) + __ldg(&blocks[b].cnt);
-    return B ? a1 : b * kBlockBits - a1;
-}
-
-// position of the i-th (1-based) B-bit, given 1 <= i <= #B-bits
-template <int B>
-__device__ __forceinline__ uint64_t bv_select_one(bvblock const * __restrict__ blocks,
-                                                  uint64_t const * __restrict__ top,
-                                                  uint32_t const * __restrict__ samp,
-                                                  uint32_t log_s,
-                                                  uint64_t i)
-{
-    uint64_t j = (i - 1) >> log_s;
-    uint2 s2;
-    // samp[j], samp[j+1]: one 8-byte load when j is even
-    uint64_t lo, hi;
-    if ((j & 1) == 0)
-    {
-        s2 = __ldg(reinterpret_cast<uint2 const *>(samp + j));
-        lo = s2.x;
-        hi = s2.y;
-    }
-    else
-    {
-        lo = __ldg(samp + j);
-        hi = __ldg(samp + j + 1);
-    }
-    // invariant: the answer lies in a block of [lo, hi] and abs_before(lo) < i
-    while (hi - lo > 3)
-    {
-        uint64_t mid = (lo + hi + 1) >> 1;
-        if (abs_before<B>(blocks, top, mid) < i)
-            lo = mid;
-        else
-            hi = mid - 1;
-    }
-    uint32_t cnt, d[7];
-    ld_block(blocks + lo, cnt, d);
-    uint64_t a1 = __ldg(top + (lo >> kSuperShift)) + cnt;
-    uint64_t need = i - (B ? a1 : lo * kBlockBits - a1);
-    uint32_t c = block_popc<B>(d);
-    while (need > c)
-    {
-        need -= c;
-        ++lo;
-        ld_block(blocks + lo, cnt, d);
-        c = block_popc<B>(d);
-    }
-    return lo * kBlockBits + block_select<B>(d, (uint32_t)need);
-}
-
-template <int B>
-__global__ void __launch_bounds__(kThreads) bv_select_kernel(bvblock const * __restrict__ blocks,
-                                                             uint64_t const * __restrict__ top,
-                                                             uint32_t const * __restrict__ samp,
-                                                             uint32_t log_s,
-                                                             uint64_t args,
-                                                             uint64_t const * __restrict__ idx,
-                                                             uint64_t n,
-                                                             uint64_t * __restrict__ out)
+__global__ void __launch_bounds__(kThreads)
+    bv_select_kernel(BvView const v, uint64_t args, uint64_t const * __restrict__ idx, uint64_t n, uint64_t * __restrict__ out)
 {
     uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
@@ -248,7 +189,7 @@ __global__ void __launch_bounds__(kThreads) bv_select_kernel(bvblock const * __r
         uint64_t i = ld_stream_u64(idx + q);
         uint64_t r = SDSLGPU_NPOS;
         if (i >= 1 && i <= args)
-            r = bv_select_one<B>(blocks, top, samp, log_s, i);
+            r = bv_select<B>(v, i);
         st_stream_u64(out + q, r);
     }
 }
@@ -306,7 +247,7 @@ __global__ void __launch_bounds__(kThreads) sdsl_table_abs_kernel(uint64_t const
         table[2 * k] = abs[k];
 }
 
-static inline unsigned grid_for(uint64_t n, int per_thread = 1)
+unsigned grid_for(uint64_t n, int per_thread)
 {
     uint64_t want = (n + (uint64_t)kThreads * per_thread - 1) / ((uint64_t)kThreads * per_thread);
     uint64_t cap = (uint64_t)kSmCount * 8; // 8 resident CTAs of 256 threads per SM = 64 warps
@@ -314,14 +255,13 @@ static inline unsigned grid_for(uint64_t n, int per_thread = 1)
         want = 1;
     return (unsigned)(want < cap ? want : cap);
 }
-static inline unsigned blocks_for(uint64_t n)
+unsigned blocks_for(uint64_t n)
 {
     return (unsigned)((n + kThreads - 1) / kThreads);
 }
 
-int bv_build(sdslgpu_handle * h, uint64_t const * words_in, bool on_device, uint64_t nbits, cudaStream_t s)
+int bv_build(DevicePool & pool, BvImage & v, uint32_t flags, uint64_t const * words_in, bool on_device, uint64_t nbits, cudaStream_t s)
 {
-    sdslgpu_bv_image & v = h->bv;
     v.nbits = nbits;
     v.nwords = (nbits + 63) >> 6;
     v.nblocks = nbits / kBlockBits + 1;
@@ -334,7 +274,7 @@ int bv_build(sdslgpu_handle * h, uint64_t const * words_in, bool on_device, uint
 
     // raw words on the device (+1 zero pad word, like SDSL's allocation, memory_management.hpp:901-906)
     uint64_t * words = nullptr;
-    SG_TRY(h->pool.alloc_t(&words, v.nwords + 2));
+    SG_TRY(pool.alloc_t(&words, v.nwords + 2));
     SG_CUDA(cudaMemsetAsync(words + v.nwords, 0, 16, s));
     if (v.nwords)
         SG_CUDA(cudaMemcpyAsync(words, words_in, v.nwords * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
@@ -342,11 +282,11 @@ int bv_build(sdslgpu_handle * h, uint64_t const * words_in, bool on_device, uint
     uint32_t * blk_ones = nullptr;
     uint64_t * abs_ones = nullptr;
     uint64_t * tmp = nullptr;
-    SG_TRY(h->pool.alloc_t(&v.blocks, v.nblocks));
-    SG_TRY(h->pool.alloc_t(&v.top, v.ntop));
-    SG_TRY(h->pool.alloc_t(&blk_ones, v.nblocks));
-    SG_TRY(h->pool.alloc_t(&abs_ones, v.nblocks + 1));
-    SG_TRY(h->pool.alloc_t(&tmp, scan_tmp_words(v.nblocks)));
+    SG_TRY(pool.alloc_t(&v.blocks, v.nblocks));
+    SG_TRY(pool.alloc_t(&v.top, v.ntop));
+    SG_TRY(pool.alloc_t(&blk_ones, v.nblocks));
+    SG_TRY(pool.alloc_t(&abs_ones, v.nblocks + 1));
+    SG_TRY(pool.alloc_t(&tmp, scan_tmp_words(v.nblocks)));
 
     bv_pack_kernel<<<blocks_for(v.nblocks), kThreads, 0, s>>>(reinterpret_cast<uint32_t const *>(words), nbits, v.nblocks, v.blocks, blk_ones);
     SG_CUDA(cudaGetLastError());
@@ -356,7 +296,7 @@ int bv_build(sdslgpu_handle * h, uint64_t const * words_in, bool on_device, uint
     SG_CUDA(cudaMemcpyAsync(&v.ones, abs_ones + v.nblocks, 8, cudaMemcpyDeviceToHost, s));
     SG_CUDA(cudaStreamSynchronize(s));
 
-    if (!(h->flags & SDSLGPU_F_NO_SELECT))
+    if (!(flags & SDSLGPU_F_NO_SELECT))
     {
         for (int b = 0; b < 2; ++b)
         {
@@ -368,7 +308,7 @@ int bv_build(sdslgpu_handle * h, uint64_t const * words_in, bool on_device, uint
                 --ls;
             v.log_s[b] = ls;
             v.nsamp[b] = m ? ((m - 1) >> ls) + 1 : 0;
-            SG_TRY(h->pool.alloc_t(&v.samp[b], v.nsamp[b] + 2));
+            SG_TRY(pool.alloc_t(&v.samp[b], v.nsamp[b] + 2));
             // sentinel(s): the last block
             std::vector<uint32_t> tail(2, (uint32_t)(v.nblocks - 1));
             SG_CUDA(cudaMemcpyAsync(v.samp[b] + v.nsamp[b], tail.data(), 8, cudaMemcpyHostToDevice, s));
@@ -384,37 +324,36 @@ int bv_build(sdslgpu_handle * h, uint64_t const * words_in, bool on_device, uint
         }
     }
     SG_CUDA(cudaStreamSynchronize(s));
-    h->pool.release(blk_ones);
-    h->pool.release(abs_ones);
-    h->pool.release(tmp);
+    pool.release(blk_ones);
+    pool.release(abs_ones);
+    pool.release(tmp);
 
-    if (h->flags & SDSLGPU_F_SDSL_LAYOUT)
+    if (flags & SDSLGPU_F_SDSL_LAYOUT)
     {
         v.words = words;
         // keep the caller's bits past nbits exactly as given, like the reference does
         for (int b = 0; b < 2; ++b)
-            SG_TRY(bv_build_sdsl_rank_table(h, b, s));
+            SG_TRY(bv_build_sdsl_rank_table(pool, v, b, s));
     }
     else
     {
-        h->pool.release(words);
+        pool.release(words);
     }
     return SDSLGPU_OK;
 }
 
-int bv_build_sdsl_rank_table(sdslgpu_handle * h, int b, cudaStream_t s)
+int bv_build_sdsl_rank_table(DevicePool & pool, BvImage & v, int b, cudaStream_t s)
 {
-    sdslgpu_bv_image & v = h->bv;
     // rank_support_v.hpp:79,84: 2 words for an empty vector, else 2 * (((n+63)>>9) + 1)
     uint64_t nsuper = (v.nbits == 0) ? 1 : ((v.nbits + 63) >> 9) + 1;
     v.table_words = 2 * nsuper;
-    SG_TRY(h->pool.alloc_t(&v.rank_table[b], v.table_words + 2));
+    SG_TRY(pool.alloc_t(&v.rank_table[b], v.table_words + 2));
     uint32_t * sb_total = nullptr;
     uint64_t * abs = nullptr;
     uint64_t * tmp = nullptr;
-    SG_TRY(h->pool.alloc_t(&sb_total, nsuper));
-    SG_TRY(h->pool.alloc_t(&abs, nsuper + 1));
-    SG_TRY(h->pool.alloc_t(&tmp, scan_tmp_words(nsuper)));
+    SG_TRY(pool.alloc_t(&sb_total, nsuper));
+    SG_TRY(pool.alloc_t(&abs, nsuper + 1));
+    SG_TRY(pool.alloc_t(&tmp, scan_tmp_words(nsuper)));
     if (b)
         sdsl_table_rel_kernel<1><<<blocks_for(nsuper), kThreads, 0, s>>>(v.words, v.nwords, nsuper, v.rank_table[b], sb_total);
     else
@@ -424,20 +363,19 @@ int bv_build_sdsl_rank_table(sdslgpu_handle * h, int b, cudaStream_t s)
     sdsl_table_abs_kernel<<<blocks_for(nsuper), kThreads, 0, s>>>(abs, nsuper, v.rank_table[b]);
     SG_CUDA(cudaGetLastError());
     SG_CUDA(cudaStreamSynchronize(s));
-    h->pool.release(sb_total);
-    h->pool.release(abs);
-    h->pool.release(tmp);
+    pool.release(sb_total);
+    pool.release(abs);
+    pool.release(tmp);
     return SDSLGPU_OK;
 }
 
-int bv_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)
+int bv_rank_device(BvImage const & v, uint32_t flags, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)
 {
-    sdslgpu_bv_image const & v = h->bv;
     if (n == 0)
         return SDSLGPU_OK;
     constexpr int ILP = 2;
     unsigned grid = grid_for(n, ILP);
-    if (h->flags & SDSLGPU_F_SDSL_LAYOUT)
+    if (flags & SDSLGPU_F_SDSL_LAYOUT)
     {
         if (b)
             bv_rank_sdsl_kernel<1, ILP><<<grid, kThreads, 0, s>>>(v.words, v.rank_table[1], v.nbits, idx, n, out);
@@ -455,9 +393,8 @@ int bv_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64
     return SDSLGPU_OK;
 }
 
-int bv_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)
+int bv_select_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)
 {
-    sdslgpu_bv_image const & v = h->bv;
     if (n == 0)
         return SDSLGPU_OK;
     if (v.samp[b] == nullptr)
@@ -468,16 +405,15 @@ int bv_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint
     unsigned grid = grid_for(n);
     uint64_t args = b ? v.ones : v.nbits - v.ones;
     if (b)
-        bv_select_kernel<1><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.samp[1], v.log_s[1], args, idx, n, out);
+        bv_select_kernel<1><<<grid, kThreads, 0, s>>>(bv_view(v), args, idx, n, out);
     else
-        bv_select_kernel<0><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.samp[0], v.log_s[0], args, idx, n, out);
+        bv_select_kernel<0><<<grid, kThreads, 0, s>>>(bv_view(v), args, idx, n, out);
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
 }
 
-int bv_access_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)
+int bv_access_device(BvImage const & v, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)
 {
-    sdslgpu_bv_image const & v = h->bv;
     if (n == 0)
         return SDSLGPU_OK;
     bv_access_kernel<<<grid_for(n), kThreads, 0, s>>>(v.blocks, v.nbits, idx, n, out);

@@ -1,0 +1,111 @@
+// bv_device.cuh — device-side view of a bit-vector image and the per-query primitives every kernel
+// composes: rank1 at a position (one sector gather), bit access, and select by sampled hint + block scan.
+// Used by bv.cu (plain rank/select), wt.cu (wavelet-tree levels), fm.cu (backward search, LF walks),
+// sd.cu (Elias-Fano high part).
+#pragma once
+#include "common.cuh"
+
+namespace sdslgpu
+{
+
+// plain-old-data view passed to kernels by value
+struct BvView
+{
+    bvblock const * blocks;
+    uint64_t const * top;
+    uint32_t const * samp[2];
+    uint32_t log_s[2];
+    uint64_t nbits;
+    uint64_t ones;
+};
+
+// number of 1-bits in [0, pos), 0 <= pos <= nbits: one 32-byte sector gather
+// (device form of rank_support_v<1>::rank, rank_support_v.hpp:129-139)
+__device__ __forceinline__ uint64_t bv_rank1(BvView const & v, uint64_t pos)
+{
+    uint64_t blk = pos / kBlockBits;
+    uint32_t rem = (uint32_t)(pos - blk * kBlockBits);
+    uint32_t cnt, d[7];
+    ld_block(v.blocks + blk, cnt, d);
+    return __ldg(v.top + (blk >> kSuperShift)) + cnt + block_prefix_popc(d, rem);
+}
+
+// rank1(pos) and the bit AT pos from the same sector (pos < nbits): what wt access / LF need per level
+__device__ __forceinline__ uint64_t bv_rank1_and_bit(BvView const & v, uint64_t pos, uint32_t & bit)
+{
+    uint64_t blk = pos / kBlockBits;
+    uint32_t rem = (uint32_t)(pos - blk * kBlockBits);
+    uint32_t cnt, d[7];
+    ld_block(v.blocks + blk, cnt, d);
+    uint32_t w = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 7; ++j)
+        w = (j == (rem >> 5)) ? d[j] : w;
+    bit = (w >> (rem & 31u)) & 1u;
+    return __ldg(v.top + (blk >> kSuperShift)) + cnt + block_prefix_popc(d, rem);
+}
+
+__device__ __forceinline__ uint32_t bv_bit(BvView const & v, uint64_t pos)
+{
+    uint64_t blk = pos / kBlockBits;
+    uint32_t rem = (uint32_t)(pos - blk * kBlockBits);
+    return (ld_nc_u32(&v.blocks[blk].d[rem >> 5]) >> (rem & 31u)) & 1u;
+}
+
+template <int B>
+__device__ __forceinline__ uint64_t abs_before(bvblock const * __restrict__ blocks, uint64_t const * __restrict__ top, uint64_t b)
+{
+    uint64_t a1 = __ldg(top + (b >> kSuperShift)) + __ldg(&blocks[b].cnt);
+    return B ? a1 : b * kBlockBits - a1;
+}
+
+// position of the i-th (1-based) B-bit, given 1 <= i <= #B-bits
+// (device form of select_support_mcl<B>::select, select_support_mcl.hpp:384-439: sampled hint, then a
+//  scan over block counts instead of the reference's word scan)
+template <int B>
+__device__ __forceinline__ uint64_t bv_select(BvView const & v, uint64_t i)
+{
+    bvblock const * __restrict__ blocks = v.blocks;
+    uint64_t const * __restrict__ top = v.top;
+    uint32_t const * __restrict__ samp = v.samp[B];
+    uint32_t const log_s = v.log_s[B];
+    uint64_t j = (i - 1) >> log_s;
+    uint2 s2;
+    // samp[j], samp[j+1]: one 8-byte load when j is even
+    uint64_t lo, hi;
+    if ((j & 1) == 0)
+    {
+        s2 = __ldg(reinterpret_cast<uint2 const *>(samp + j));
+        lo = s2.x;
+        hi = s2.y;
+    }
+    else
+    {
+        lo = __ldg(samp + j);
+        hi = __ldg(samp + j + 1);
+    }
+    // invariant: the answer lies in a block of [lo, hi] and abs_before(lo) < i
+    while (hi - lo > 3)
+    {
+        uint64_t mid = (lo + hi + 1) >> 1;
+        if (abs_before<B>(blocks, top, mid) < i)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    uint32_t cnt, d[7];
+    ld_block(blocks + lo, cnt, d);
+    uint64_t a1 = __ldg(top + (lo >> kSuperShift)) + cnt;
+    uint64_t need = i - (B ? a1 : lo * kBlockBits - a1);
+    uint32_t c = block_popc<B>(d);
+    while (need > c)
+    {
+        need -= c;
+        ++lo;
+        ld_block(blocks + lo, cnt, d);
+        c = block_popc<B>(d);
+    }
+    return lo * kBlockBits + block_select<B>(d, (uint32_t)need);
+}
+
+} // namespace sdslgpu

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/sdslgpu.h"
+#include "bv_device.cuh"
 #include "common.cuh"
 
 namespace sdslgpu
@@ -99,26 +100,69 @@ int classify(void const * p, int device, PtrSpace * space);
 } // namespace sdslgpu
 
 // ------------------------------------------------------------------------------------------------
-// The opaque handle.  `kind` selects which of the per-kind images is populated.
+// Device images.  A BvImage is the building block: wavelet trees and the Elias-Fano high part own one.
 // ------------------------------------------------------------------------------------------------
-struct sdslgpu_bv_image
+namespace sdslgpu
+{
+
+struct BvImage
 {
     uint64_t nbits = 0;
-    uint64_t nblocks = 0;               // nbits/224 + 1 (one past the end so rank(size) stays in range)
-    sdslgpu::bvblock * blocks = nullptr; // sector-interleaved payload + counts
-    uint64_t * top = nullptr;            // absolute 1-count per superblock of 2^24 blocks
+    uint64_t nblocks = 0;      // nbits/224 + 1 (one past the end so rank(size) stays in range)
+    bvblock * blocks = nullptr; // sector-interleaved payload + counts
+    uint64_t * top = nullptr;   // absolute 1-count per superblock of 2^24 blocks
     uint64_t ntop = 0;
     uint64_t ones = 0;
-    // select samples, per pattern b: samp[b][j] = block holding the (j*S+1)-th b-bit; one sentinel
+    // select samples, per pattern b: samp[b][j] = block holding the (j*S+1)-th b-bit; two sentinels
     uint32_t * samp[2] = {nullptr, nullptr};
     uint64_t nsamp[2] = {0, 0};
     uint32_t log_s[2] = {6, 6};
-    // optional SDSL layout (SDSLGPU_F_SDSL_LAYOUT): raw words (+1 pad word) and m_basic_block tables
+    // optional SDSL layout (SDSLGPU_F_SDSL_LAYOUT): raw words (+ pad) and the m_basic_block tables
     uint64_t * words = nullptr;
     uint64_t nwords = 0;
     uint64_t * rank_table[2] = {nullptr, nullptr}; // [b]
     uint64_t table_words = 0;
 };
+
+inline BvView bv_view(BvImage const & v)
+{
+    BvView w;
+    w.blocks = v.blocks;
+    w.top = v.top;
+    w.samp[0] = v.samp[0];
+    w.samp[1] = v.samp[1];
+    w.log_s[0] = v.log_s[0];
+    w.log_s[1] = v.log_s[1];
+    w.nbits = v.nbits;
+    w.ones = v.ones;
+    return w;
+}
+
+// node table + per-symbol paths of a byte wavelet tree (wt_helper.hpp:219-225), as staged into shared
+// memory by every wt / fm kernel.  ~14 KB.
+struct WtTree
+{
+    static constexpr int kMaxNodes = 511;
+    uint64_t bv_pos[kMaxNodes];
+    uint64_t bv_pos_rank[kMaxNodes]; // leaves: the symbol
+    uint16_t child[kMaxNodes][2];    // 0xFFFF = leaf
+    uint16_t parent[kMaxNodes];
+    uint16_t c_to_leaf[256]; // 0xFFFF = symbol absent
+    uint64_t path[256];      // bits 0..55 path from the root (LSB first), bits 56..63 its length
+    uint64_t occ[256];       // occurrences of each symbol (not in the reference's tree; bounds select)
+    uint32_t nnodes;
+    uint32_t pad_;
+};
+
+struct WtHuffImage
+{
+    uint64_t size = 0, sigma = 0;
+    BvImage bv;               // the single concatenated bit vector m_bv (wt_pc.hpp:88-94)
+    WtTree * tree = nullptr;   // device copy
+    WtTree host_tree;          // host copy (kept for serialisation / introspection)
+};
+
+} // namespace sdslgpu
 
 struct sdslgpu_handle
 {
@@ -127,15 +171,24 @@ struct sdslgpu_handle
     uint32_t flags = 0;
     sdslgpu::DevicePool pool;
     sdslgpu::Staging staging;
-    sdslgpu_bv_image bv;
+    sdslgpu::BvImage bv;        // KIND_BV
+    sdslgpu::WtHuffImage wt;    // KIND_WT_HUFF (and the BWT of KIND_CSA_WT)
 };
 
 namespace sdslgpu
 {
 // bv.cu
-int bv_build(sdslgpu_handle * h, uint64_t const * words_host_or_dev, bool words_on_device, uint64_t nbits, cudaStream_t s);
-int bv_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
-int bv_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
-int bv_access_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
-int bv_build_sdsl_rank_table(sdslgpu_handle * h, int b, cudaStream_t s);
+int bv_build(DevicePool & pool, BvImage & v, uint32_t flags, uint64_t const * words_host_or_dev, bool words_on_device, uint64_t nbits, cudaStream_t s);
+int bv_build_sdsl_rank_table(DevicePool & pool, BvImage & v, int b, cudaStream_t s);
+int bv_rank_device(BvImage const & v, uint32_t flags, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
+int bv_select_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
+int bv_access_device(BvImage const & v, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
+// wt.cu
+int wt_huff_upload(sdslgpu_handle * h, uint64_t size, uint64_t sigma, WtTree const & tree, uint64_t const * bv_words, uint64_t bv_bits, cudaStream_t s);
+int wt_huff_build_from_text(sdslgpu_handle * h, uint8_t const * text_host, uint64_t n, cudaStream_t s);
+int wt_rank_device(sdslgpu_handle const * h, uint64_t const * i, uint8_t const * c, uint64_t n, uint64_t * out, cudaStream_t s);
+int wt_select_device(sdslgpu_handle const * h, uint64_t const * i, uint8_t const * c, uint64_t n, uint64_t * out, cudaStream_t s);
+int wt_access_device(sdslgpu_handle const * h, uint64_t const * i, uint64_t n, uint64_t * sym, uint64_t * rnk, cudaStream_t s);
+unsigned grid_for(uint64_t n, int per_thread = 1);
+unsigned blocks_for(uint64_t n);
 } // namespace sdslgpu

@@ -1,0 +1,481 @@
+// wt.cu — wt_huff<> (Huffman-shaped byte wavelet tree): construction and batched queries.
+//
+// Replaces (results bit-exact; the concatenated bit vector m_bv and the node table are built to be
+// byte-identical to the reference's so that SDSL-serialised trees can be ingested as they are):
+//   wt_pc ctor              wt_pc.hpp:194-248 + wt_huff.hpp:82-115 + wt_helper.hpp:230-327 -> wt_huff_build_from_text
+//   wt_pc::rank(i,c)        wt_pc.hpp:371-399   -> wt_rank_kernel      (path_len dependent sector gathers)
+//   wt_pc::operator[] / inverse_select  :336-357 / :411-430 -> wt_access_kernel
+//   wt_pc::select(i,c)      wt_pc.hpp:443-474   -> wt_select_kernel    (bottom-up select0/select1 on m_bv)
+// The node table and the per-symbol paths (≈14 KB) are staged into shared memory once per CTA.
+#include <algorithm>
+#include <atomic>
+#include <queue>
+#include <thread>
+
+#include "internal.h"
+
+namespace sdslgpu
+{
+
+static constexpr uint16_t kUndef = 0xFFFF;
+
+// ------------------------------------------------------------------------------------------------
+// host: Huffman shape + BFS layout (tiny), then the bit planes in parallel over text chunks
+// ------------------------------------------------------------------------------------------------
+namespace
+{
+struct PcNode
+{
+    uint64_t freq, sym, parent, child[2];
+};
+} // namespace
+
+// Fills tree (bv_pos, children, parents, c_to_leaf, path) and returns the number of bits of m_bv.
+// Tie-breaking follows the reference exactly: min-heap ordered by (frequency, node number); the first
+// node popped becomes child 0 (wt_huff.hpp:102-114); nodes are renumbered in BFS order with the two
+// children of a node adjacent (wt_helper.hpp:236-271).
+static uint64_t build_huff_tree(uint64_t const (&C)[256], WtTree & tree, uint64_t & sigma)
+{
+    std::vector<PcNode> t;
+    typedef std::pair<uint64_t, uint64_t> P;
+    std::priority_queue<P, std::vector<P>, std::greater<P>> pq;
+    sigma = 0;
+    for (uint64_t c = 0; c < 256; ++c)
+        if (C[c] > 0)
+        {
+            pq.push(P(C[c], t.size()));
+            t.push_back(PcNode{C[c], c, ~0ull, {~0ull, ~0ull}});
+            ++sigma;
+        }
+    while (pq.size() > 1)
+    {
+        P a = pq.top();
+        pq.pop();
+        P b = pq.top();
+        pq.pop();
+        t[a.second].parent = t.size();
+        t[b.second].parent = t.size();
+        pq.push(P(a.first + b.first, t.size()));
+        t.push_back(PcNode{a.first + b.first, 0, ~0ull, {a.second, b.second}});
+    }
+    std::memset(&tree, 0, sizeof(tree));
+    tree.nnodes = (uint32_t)t.size();
+    // BFS relabel
+    std::vector<uint64_t> src(t.size()); // BFS id -> index in t
+    std::vector<uint64_t> freq(t.size());
+    uint64_t bv_size = 0, node_cnt = 1, head = 0;
+    src[0] = t.size() - 1;
+    tree.parent[0] = kUndef;
+    while (head < node_cnt)
+    {
+        uint64_t idx = head++;
+        PcNode const & p = t[src[idx]];
+        tree.bv_pos[idx] = bv_size;
+        if (p.child[0] != ~0ull)
+        {
+            bv_size += p.freq;
+            for (int k = 0; k < 2; ++k)
+            {
+                src[node_cnt] = p.child[k];
+                tree.parent[node_cnt] = (uint16_t)idx;
+                tree.child[idx][k] = (uint16_t)node_cnt++;
+            }
+        }
+        else
+        {
+            tree.child[idx][0] = tree.child[idx][1] = kUndef;
+            tree.bv_pos_rank[idx] = p.sym; // leaves keep the symbol here (wt_helper.hpp:119-137)
+        }
+    }
+    for (int c = 0; c < 256; ++c)
+        tree.c_to_leaf[c] = kUndef;
+    for (uint64_t v = 0; v < t.size(); ++v)
+        if (tree.child[v][0] == kUndef)
+            tree.c_to_leaf[(uint8_t)tree.bv_pos_rank[v]] = (uint16_t)v;
+    uint64_t prev_c = 0;
+    for (uint64_t c = 0; c < 256; ++c)
+    {
+        if (tree.c_to_leaf[c] != kUndef)
+        {
+            uint16_t v = tree.c_to_leaf[c];
+            uint64_t pw = 0, pl = 0;
+            while (v != 0)
+            {
+                pw <<= 1;
+                if (tree.child[tree.parent[v]][1] == v)
+                    pw |= 1;
+                ++pl;
+                v = tree.parent[v];
+            }
+            tree.path[c] = pw | (pl << 56);
+            prev_c = c;
+        }
+        else
+            tree.path[c] = prev_c; // length 0 (wt_helper.hpp:311-315 stores the previous symbol here)
+    }
+    return bv_size;
+}
+
+// The bit planes: chunk the text over T threads.  Per chunk and node the start offset is the node's
+// bv_pos plus the number of symbols of that node's subtree in earlier chunks, so every thread writes
+// disjoint bit ranges; words shared between two ranges are merged with an atomic OR.
+static void fill_bit_planes(uint8_t const * text, uint64_t n, WtTree const & tree, std::vector<uint64_t> & bv)
+{
+    unsigned T = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+    if (n < (1u << 16))
+        T = 1;
+    uint64_t chunk = (n + T - 1) / T;
+    uint32_t const nn = tree.nnodes;
+    // per chunk: symbols under each node
+    std::vector<std::vector<uint64_t>> cnt(T, std::vector<uint64_t>(nn, 0));
+    auto count_chunk = [&](unsigned t) {
+        uint64_t lo = std::min(n, t * chunk), hi = std::min(n, lo + chunk);
+        uint64_t h[256] = {0};
+        for (uint64_t k = lo; k < hi; ++k)
+            ++h[text[k]];
+        for (int c = 0; c < 256; ++c)
+        {
+            if (!h[c])
+                continue;
+            uint16_t v = tree.c_to_leaf[c];
+            while (v != 0)
+            {
+                v = tree.parent[v];
+                cnt[t][v] += h[c];
+            }
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; ++t)
+            th.emplace_back(count_chunk, t);
+        for (auto & x : th)
+            x.join();
+    }
+    std::vector<std::vector<uint64_t>> start(T, std::vector<uint64_t>(nn, 0));
+    for (uint32_t v = 0; v < nn; ++v)
+    {
+        uint64_t p = tree.bv_pos[v];
+        for (unsigned t = 0; t < T; ++t)
+        {
+            start[t][v] = p;
+            p += cnt[t][v];
+        }
+    }
+    std::atomic<uint64_t> * words = reinterpret_cast<std::atomic<uint64_t> *>(bv.data());
+    auto fill_chunk = [&](unsigned t) {
+        uint64_t lo = std::min(n, t * chunk), hi = std::min(n, lo + chunk);
+        std::vector<uint64_t> pos(start[t]);
+        // per node: the word being assembled
+        std::vector<uint64_t> cur_idx(nn, ~0ull), cur_bits(nn, 0);
+        auto flush = [&](uint32_t v) {
+            if (cur_idx[v] != ~0ull && cur_bits[v])
+                words[cur_idx[v]].fetch_or(cur_bits[v], std::memory_order_relaxed);
+        };
+        for (uint64_t k = lo; k < hi; ++k)
+        {
+            uint64_t p = tree.path[text[k]];
+            uint32_t len = (uint32_t)(p >> 56);
+            uint16_t v = 0;
+            for (uint32_t l = 0; l < len; ++l, p >>= 1)
+            {
+                uint64_t q = pos[v]++;
+                uint64_t wi = q >> 6;
+                if (wi != cur_idx[v])
+                {
+                    flush(v);
+                    cur_idx[v] = wi;
+                    cur_bits[v] = 0;
+                }
+                cur_bits[v] |= (p & 1) << (q & 63);
+                v = tree.child[v][p & 1];
+            }
+        }
+        for (uint32_t v = 0; v < nn; ++v)
+            flush(v);
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < T; ++t)
+        th.emplace_back(fill_chunk, t);
+    for (auto & x : th)
+        x.join();
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_tree(WtTree const * __restrict__ g, WtTree * s)
+{
+    // cooperative 16-byte copy of the ~14 KB table into shared memory
+    uint4 const * src = reinterpret_cast<uint4 const *>(g);
+    uint4 * dst = reinterpret_cast<uint4 *>(s);
+    for (uint32_t k = threadIdx.x; k < sizeof(WtTree) / 16; k += blockDim.x)
+        dst[k] = __ldg(src + k);
+    __syncthreads();
+}
+
+// rank(i, c) for one query against a staged tree (wt_pc.hpp:371-399)
+__device__ __forceinline__ uint64_t wt_rank_one(BvView const & bv, WtTree const * t, uint64_t sigma, uint64_t i, uint32_t c)
+{
+    if (t->c_to_leaf[c] == kUndef)
+        return 0;
+    if (sigma == 1)
+        return i;
+    uint64_t p = t->path[c];
+    uint32_t len = (uint32_t)(p >> 56);
+    uint64_t r = i;
+    uint32_t v = 0;
+    for (uint32_t l = 0; l < len && r; ++l, p >>= 1)
+    {
+        uint64_t o = bv_rank1(bv, t->bv_pos[v] + r) - t->bv_pos_rank[v];
+        r = (p & 1) ? o : r - o;
+        v = t->child[v][p & 1];
+    }
+    return r;
+}
+
+// (rank(i, wt[i]), wt[i]) (wt_pc.hpp:411-430): per level one sector gives both the bit and the rank
+__device__ __forceinline__ uint64_t wt_inverse_select_one(BvView const & bv, WtTree const * t, uint64_t i, uint32_t & sym)
+{
+    uint32_t v = 0;
+    while (t->child[v][0] != kUndef)
+    {
+        uint32_t bit;
+        uint64_t o = bv_rank1_and_bit(bv, t->bv_pos[v] + i, bit) - t->bv_pos_rank[v];
+        i = bit ? o : i - o;
+        v = t->child[v][bit];
+    }
+    sym = (uint32_t)t->bv_pos_rank[v];
+    return i;
+}
+
+__global__ void __launch_bounds__(kThreads) wt_rank_kernel(BvView const bv,
+                                                           WtTree const * __restrict__ tree,
+                                                           uint64_t size,
+                                                           uint64_t sigma,
+                                                           uint64_t const * __restrict__ qi,
+                                                           uint8_t const * __restrict__ qc,
+                                                           uint64_t n,
+                                                           uint64_t * __restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WtTree * t = reinterpret_cast<WtTree *>(smem_raw);
+    stage_tree(tree, t);
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
+    {
+        uint64_t i = ld_stream_u64(qi + q);
+        uint32_t c = qc[q];
+        uint64_t r = SDSLGPU_NPOS;
+        if (i <= size)
+            r = wt_rank_one(bv, t, sigma, i, c);
+        st_stream_u64(out + q, r);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) wt_access_kernel(BvView const bv,
+                                                             WtTree const * __restrict__ tree,
+                                                             uint64_t size,
+                                                             uint64_t const * __restrict__ qi,
+                                                             uint64_t n,
+                                                             uint64_t * __restrict__ sym_out,
+                                                             uint64_t * __restrict__ rank_out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WtTree * t = reinterpret_cast<WtTree *>(smem_raw);
+    stage_tree(tree, t);
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
+    {
+        uint64_t i = ld_stream_u64(qi + q);
+        uint64_t r = SDSLGPU_NPOS, s = SDSLGPU_NPOS;
+        if (i < size)
+        {
+            uint32_t sym;
+            r = wt_inverse_select_one(bv, t, i, sym);
+            s = sym;
+        }
+        st_stream_u64(sym_out + q, s);
+        if (rank_out)
+            st_stream_u64(rank_out + q, r);
+    }
+}
+
+// select(i, c) (wt_pc.hpp:443-474): climb from the leaf; at each parent one select on m_bv
+__global__ void __launch_bounds__(kThreads) wt_select_kernel(BvView const bv,
+                                                             WtTree const * __restrict__ tree,
+                                                             uint64_t size,
+                                                             uint64_t sigma,
+                                                             uint64_t const * __restrict__ qi,
+                                                             uint8_t const * __restrict__ qc,
+                                                             uint64_t n,
+                                                             uint64_t * __restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WtTree * t = reinterpret_cast<WtTree *>(smem_raw);
+    stage_tree(tree, t);
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
+    {
+        uint64_t i = ld_stream_u64(qi + q);
+        uint32_t c = qc[q];
+        uint32_t v = t->c_to_leaf[c];
+        uint64_t r;
+        if (v == kUndef)
+            r = size; // the reference returns size() for an absent symbol (:447-450)
+        else if (i == 0)
+            r = SDSLGPU_NPOS;
+        else if (sigma == 1)
+            r = (i - 1 < size) ? i - 1 : size;
+        else
+        {
+            uint64_t p = t->path[c];
+            uint32_t len = (uint32_t)(p >> 56);
+            uint64_t occ = t->occ[c]; // the reference leaves i > rank(size, c) undefined; here it is NPOS
+            if (i > occ)
+                r = SDSLGPU_NPOS;
+            else
+            {
+                r = i - 1;
+                p <<= (64 - len);
+                for (uint32_t l = 0; l < len; ++l, p <<= 1)
+                {
+                    v = t->parent[v];
+                    if ((p & 0x8000000000000000ULL) == 0)
+                        r = bv_select<0>(bv, t->bv_pos[v] - t->bv_pos_rank[v] + r + 1) - t->bv_pos[v];
+                    else
+                        r = bv_select<1>(bv, t->bv_pos_rank[v] + r + 1) - t->bv_pos[v];
+                }
+            }
+        }
+        st_stream_u64(out + q, r);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host entry points
+// ------------------------------------------------------------------------------------------------
+int wt_huff_upload(sdslgpu_handle * h, uint64_t size, uint64_t sigma, WtTree const & tree, uint64_t const * bv_words, uint64_t bv_bits, cudaStream_t s)
+{
+    WtHuffImage & w = h->wt;
+    w.size = size;
+    w.sigma = sigma;
+    w.host_tree = tree;
+    SG_TRY(bv_build(h->pool, w.bv, h->flags & ~SDSLGPU_F_NO_SELECT, bv_words, false, bv_bits, s));
+    // inner nodes: bv_pos_rank = rank1(m_bv, bv_pos) (wt_helper.hpp:319-327), computed on the device
+    uint32_t nn = tree.nnodes;
+    if (nn)
+    {
+        std::vector<uint64_t> pos(nn), rk(nn);
+        for (uint32_t v = 0; v < nn; ++v)
+            pos[v] = tree.bv_pos[v];
+        uint64_t *d_pos = nullptr, *d_rk = nullptr;
+        SG_TRY(h->pool.alloc_t(&d_pos, nn));
+        SG_TRY(h->pool.alloc_t(&d_rk, nn));
+        SG_CUDA(cudaMemcpyAsync(d_pos, pos.data(), nn * 8, cudaMemcpyHostToDevice, s));
+        SG_TRY(bv_rank_device(w.bv, 0, 1, d_pos, nn, d_rk, s));
+        SG_CUDA(cudaMemcpyAsync(rk.data(), d_rk, nn * 8, cudaMemcpyDeviceToHost, s));
+        SG_CUDA(cudaStreamSynchronize(s));
+        h->pool.release(d_pos);
+        h->pool.release(d_rk);
+        WtTree & ht = w.host_tree;
+        for (uint32_t v = 0; v < nn; ++v)
+            if (ht.child[v][0] != kUndef)
+                ht.bv_pos_rank[v] = rk[v];
+        // occurrences per symbol = size of the leaf's side of its parent's bit range; nodes lie in BFS =
+        // bit-vector order, so node v spans [bv_pos[v], bv_pos[v+1]) and holds rk[v+1] - rk[v] ones
+        for (int c = 0; c < 256; ++c)
+        {
+            uint16_t v = ht.c_to_leaf[c];
+            ht.occ[c] = 0;
+            if (v == kUndef)
+                continue;
+            if (v == 0)
+            {
+                ht.occ[c] = size;
+                continue;
+            }
+            uint16_t par = ht.parent[v];
+            uint64_t span = ht.bv_pos[par + 1] - ht.bv_pos[par], ones = rk[par + 1] - rk[par];
+            ht.occ[c] = (ht.child[par][1] == v) ? ones : span - ones;
+        }
+    }
+    SG_TRY(h->pool.alloc_t(&w.tree, 1));
+    SG_CUDA(cudaMemcpyAsync(w.tree, &w.host_tree, sizeof(WtTree), cudaMemcpyHostToDevice, s));
+    SG_CUDA(cudaStreamSynchronize(s));
+    return SDSLGPU_OK;
+}
+
+int wt_huff_build_from_text(sdslgpu_handle * h, uint8_t const * text, uint64_t n, cudaStream_t s)
+{
+    uint64_t C[256] = {0};
+    {
+        unsigned T = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+        if (n < (1u << 20))
+            T = 1;
+        std::vector<std::vector<uint64_t>> part(T, std::vector<uint64_t>(256, 0));
+        std::vector<std::thread> th;
+        uint64_t chunk = (n + T - 1) / T;
+        for (unsigned t = 0; t < T; ++t)
+            th.emplace_back([&, t] {
+                uint64_t lo = std::min(n, t * chunk), hi = std::min(n, lo + chunk);
+                for (uint64_t k = lo; k < hi; ++k)
+                    ++part[t][text[k]];
+            });
+        for (auto & x : th)
+            x.join();
+        for (unsigned t = 0; t < T; ++t)
+            for (int c = 0; c < 256; ++c)
+                C[c] += part[t][c];
+    }
+    WtTree tree;
+    uint64_t sigma = 0, bits = 0;
+    std::vector<uint64_t> bv(1, 0);
+    if (n)
+    {
+        bits = build_huff_tree(C, tree, sigma);
+        bv.assign(((bits + 63) >> 6) + 1, 0);
+        fill_bit_planes(text, n, tree, bv);
+    }
+    else
+    {
+        std::memset(&tree, 0, sizeof(tree));
+        for (int c = 0; c < 256; ++c)
+            tree.c_to_leaf[c] = kUndef;
+    }
+    return wt_huff_upload(h, n, sigma, tree, bv.data(), bits, s);
+}
+
+static size_t const kTreeSmem = sizeof(WtTree);
+
+int wt_rank_device(sdslgpu_handle const * h, uint64_t const * i, uint8_t const * c, uint64_t n, uint64_t * out, cudaStream_t s)
+{
+    WtHuffImage const & w = h->wt;
+    if (n == 0)
+        return SDSLGPU_OK;
+    wt_rank_kernel<<<grid_for(n), kThreads, kTreeSmem, s>>>(bv_view(w.bv), w.tree, w.size, w.sigma, i, c, n, out);
+    SG_CUDA(cudaGetLastError());
+    return SDSLGPU_OK;
+}
+
+int wt_select_device(sdslgpu_handle const * h, uint64_t const * i, uint8_t const * c, uint64_t n, uint64_t * out, cudaStream_t s)
+{
+    WtHuffImage const & w = h->wt;
+    if (n == 0)
+        return SDSLGPU_OK;
+    wt_select_kernel<<<grid_for(n), kThreads, kTreeSmem, s>>>(bv_view(w.bv), w.tree, w.size, w.sigma, i, c, n, out);
+    SG_CUDA(cudaGetLastError());
+    return SDSLGPU_OK;
+}
+
+int wt_access_device(sdslgpu_handle const * h, uint64_t const * i, uint64_t n, uint64_t * sym, uint64_t * rnk, cudaStream_t s)
+{
+    WtHuffImage const & w = h->wt;
+    if (n == 0)
+        return SDSLGPU_OK;
+    wt_access_kernel<<<grid_for(n), kThreads, kTreeSmem, s>>>(bv_view(w.bv), w.tree, w.size, i, n, sym, rnk);
+    SG_CUDA(cudaGetLastError());
+    return SDSLGPU_OK;
+}
+
+} // namespace sdslgpu
