@@ -107,6 +107,21 @@ class Oracle:
         L.orc_wt_huff_serialize.restype = C.c_uint64
         L.orc_wt_huff_serialize.argtypes = [C.c_void_p, u8p, C.c_uint64]
 
+        L.orc_csa_build.restype = C.c_void_p
+        L.orc_csa_build.argtypes = [u8p, C.c_uint64]
+        L.orc_csa_free.argtypes = [C.c_void_p]
+        L.orc_csa_count_batch.restype = None
+        L.orc_csa_count_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, u64p, u64p]
+        L.orc_csa_locate_batch.restype = None
+        L.orc_csa_locate_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, u64p, u64p]
+        L.orc_csa_sa_batch.restype = None
+        L.orc_csa_sa_batch.argtypes = [C.c_void_p, u64p, C.c_uint64, u64p]
+        L.orc_csa_serialize.restype = C.c_uint64
+        L.orc_csa_serialize.argtypes = [C.c_void_p, u8p, C.c_uint64]
+
+    def csa(self, text):
+        return OracleCsa(self, text)
+
     # -- plain bit vector ------------------------------------------------------------------
     def bv(self, words, nbits):
         return OracleBV(self, words, nbits)
@@ -200,6 +215,44 @@ class OracleWtHuff:
     def __del__(self):
         if getattr(self, "h", None):
             self.L.orc_wt_huff_free(self.h)
+            self.h = None
+
+
+class OracleCsa:
+    def __init__(self, o, text):
+        self.L = o.L
+        t = _text(text)
+        assert not (t == 0).any(), "csa texts must be zero-free (construct.hpp:34-46)"
+        self.size = len(t) + 1
+        self.h = self.L.orc_csa_build(_p8(t if len(t) else np.zeros(1, np.uint8)), len(t))
+
+    def count(self, flat, off, want_l=False):
+        n = len(off) - 1
+        cnt = np.zeros(n, dtype=np.uint64)
+        l = np.zeros(n, dtype=np.uint64) if want_l else None
+        self.L.orc_csa_count_batch(self.h, _p8(flat), _p64(off), n, _p64(cnt), _p64(l) if want_l else None)
+        return (cnt, l) if want_l else cnt
+
+    def locate(self, flat, off):
+        cnt = self.count(flat, off)
+        occ_off = np.zeros(len(cnt) + 1, dtype=np.uint64)
+        occ_off[1:] = np.cumsum(cnt, dtype=np.uint64)
+        occ = np.zeros(max(int(occ_off[-1]), 1), dtype=np.uint64)
+        self.L.orc_csa_locate_batch(self.h, _p8(flat), _p64(off), len(cnt), _p64(occ_off), _p64(occ))
+        return occ_off, occ[: int(occ_off[-1])]
+
+    def sa(self, i):
+        i = _u64(i)
+        out = np.zeros(len(i), dtype=np.uint64)
+        self.L.orc_csa_sa_batch(self.h, _p64(i), len(i), _p64(out))
+        return out
+
+    def serialize(self):
+        return _blob(self.L.orc_csa_serialize, self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_csa_free(self.h)
             self.h = None
 
 
