@@ -122,6 +122,34 @@ int sdslgpu_wt_select(const sdslgpu_handle *h, const uint64_t *i, const void *c,
  * 418-445). */
 int sdslgpu_wt_access(const sdslgpu_handle *h, const uint64_t *i, uint64_t n, uint64_t *sym_out, uint64_t *rank_out, void *stream);
 
+/* ---- FM-index ---------------------------------------------------------------------------------- */
+
+/* Replaces construct(csa_wt<wt_huff<>>, text) (construct.hpp:127-193, csa_wt.hpp:323-355): `text` is a HOST
+ * buffer of n zero-free bytes (a zero byte gives SDSLGPU_EINVAL, as the reference throws, construct.hpp:34-46);
+ * the 0 sentinel is appended, so size() == n + 1.  Suffix array (SA-IS), BWT, byte_alphabet and the SA
+ * samples (every 32nd SA index, csa_sampling_strategy.hpp:98-115) are computed on the host; the wavelet tree
+ * of the BWT gets its rank/select structures on the device.  A CSA handle also answers sdslgpu_wt_* (that is
+ * csa.bwt / csa.wavelet_tree). */
+int sdslgpu_csa_create(const uint8_t *text, uint64_t n, int device, uint32_t flags, sdslgpu_handle **out);
+
+/* Patterns in CSR form: pattern k = pats[pat_off[k] .. pat_off[k+1]).
+ * cnt_out[k] = number of occurrences; if l_out != NULL, l_out[k] = left end of the suffix-array interval
+ * (meaningful when cnt_out[k] > 0).  The empty pattern matches size() times; a pattern longer than size()
+ * or containing a byte that is not in the text matches 0 times.
+ * Replaces sdsl::count / backward_search (suffix_array_algorithm.hpp:166-248, 463-471). */
+int sdslgpu_fm_count(const sdslgpu_handle *h, const uint8_t *pats, const uint64_t *pat_off, uint64_t n,
+                     uint64_t *cnt_out, uint64_t *l_out, void *stream);
+
+/* out[k] = SA[i[k]] (csa[i], csa_wt.hpp:363-381), 0 <= i[k] < size(). */
+int sdslgpu_fm_sa(const sdslgpu_handle *h, const uint64_t *i, uint64_t n, uint64_t *out, void *stream);
+
+/* All occurrences, in SUFFIX-ARRAY order per pattern like sdsl::locate (suffix_array_algorithm.hpp:534-550):
+ * occ_off_out[0..n] receives the exclusive prefix sums of the counts, *total_out their sum; if occ_out != NULL
+ * it must hold occ_cap >= *total_out entries and receives occ_out[occ_off_out[k] + j] = SA[l_k + j].
+ * Call with occ_out == NULL first to size the buffer (or pass a generous occ_cap). */
+int sdslgpu_fm_locate(const sdslgpu_handle *h, const uint8_t *pats, const uint64_t *pat_off, uint64_t n,
+                      uint64_t *occ_off_out, uint64_t *occ_out, uint64_t occ_cap, uint64_t *total_out, void *stream);
+
 /* ---- construction parity / interchange ------------------------------------------------------ */
 
 /* Copies the SDSL-format serialisation of one component of a KIND_BV handle into `buf`

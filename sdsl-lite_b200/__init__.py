@@ -279,3 +279,65 @@ class WtHuff(_Handle, _WaveletTreeOps):
     rank = _WaveletTreeOps.wt_rank
     select = _WaveletTreeOps.wt_select
     access = _WaveletTreeOps.wt_access
+
+
+_SIGNATURES += [
+    ("sdslgpu_csa_create", C.c_int, [vp, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(vp)]),
+    ("sdslgpu_fm_count", C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, vp]),
+    ("sdslgpu_fm_sa", C.c_int, [vp, vp, C.c_uint64, vp, vp]),
+    ("sdslgpu_fm_locate", C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, C.c_uint64, u64p, vp]),
+]
+
+
+def csr_patterns(pats):
+    """list of bytes -> (uint8 concatenation, uint64 offsets[n+1])"""
+    off = np.zeros(len(pats) + 1, dtype=np.uint64)
+    if len(pats):
+        off[1:] = np.cumsum([len(p) for p in pats], dtype=np.uint64)
+    flat = np.frombuffer(b"".join(pats), dtype=np.uint8).copy()
+    if len(flat) == 0:
+        flat = np.zeros(1, np.uint8)
+    return flat, off
+
+
+class CsaWt(_Handle, _WaveletTreeOps):
+    """csa_wt<wt_huff<>> over a zero-free byte text; count / locate / SA access in batch form
+    (sdsl::count, sdsl::locate, csa[i] — suffix_array_algorithm.hpp:463-471, 534-550; csa_wt.hpp:363-381)."""
+
+    def __init__(self, text, device=0, flags=F_DEFAULT):
+        super().__init__()
+        t = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else np.ascontiguousarray(text, dtype=np.uint8)
+        _check(lib().sdslgpu_csa_create(t.ctypes.data if len(t) else None, len(t), device, flags, C.byref(self._h)))
+
+    # csa.bwt.rank(i, c) etc.
+    bwt_rank = _WaveletTreeOps.wt_rank
+
+    def count(self, flat, off, want_l=False, stream=None):
+        """flat: uint8 pattern bytes, off: uint64[n+1] (numpy or torch CUDA tensors)"""
+        pf, nf, k1, _ = _in_ptr(flat, np.uint8)
+        po, no, k2, _ = _in_ptr(off)
+        n = no - 1
+        pc, cnt, _k = _out_like(off, n)
+        pl, l, _k2 = _out_like(off, n) if want_l else (None, None, None)
+        _check(lib().sdslgpu_fm_count(self._h, pf, po, n, pc, pl, _stream_ptr(stream, off)))
+        return (cnt, l) if want_l else cnt
+
+    def sa(self, i, stream=None):
+        p, n, k1, _ = _in_ptr(i)
+        po, o, _k = _out_like(i, n)
+        _check(lib().sdslgpu_fm_sa(self._h, p, n, po, _stream_ptr(stream, i)))
+        return o
+
+    def locate(self, flat, off, stream=None):
+        """-> (occ_off uint64[n+1], occ uint64[total]) with each pattern's occurrences in suffix-array order"""
+        pf, nf, k1, _ = _in_ptr(flat, np.uint8)
+        po, no, k2, _ = _in_ptr(off)
+        n = no - 1
+        poo, occ_off, _k = _out_like(off, n + 1)
+        total = C.c_uint64()
+        sp = _stream_ptr(stream, off)
+        _check(lib().sdslgpu_fm_locate(self._h, pf, po, n, poo, None, 0, C.byref(total), sp))
+        pocc, occ, _k2 = _out_like(off, max(total.value, 1))
+        if total.value:
+            _check(lib().sdslgpu_fm_locate(self._h, pf, po, n, poo, pocc, total.value, C.byref(total), sp))
+        return occ_off, occ[: total.value]

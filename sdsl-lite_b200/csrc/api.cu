@@ -237,6 +237,116 @@ static int check_handle(sdslgpu_handle const * h)
     return SDSLGPU_OK;
 }
 
+// Whole-buffer staging for calls with irregular (CSR) inputs such as pattern sets: host pointers are
+// copied to temporary device buffers up front and host outputs copied back by finish(); device pointers
+// pass through untouched (the call is then asynchronous on the caller's stream apart from the one
+// 8-byte read-back locate needs to size its output).
+struct StagedCall
+{
+    int device;
+    cudaStream_t s;
+    bool any_host = false;
+    std::vector<void *> temps;
+    struct Back
+    {
+        void * host;
+        void * dev;
+        uint64_t bytes;
+    };
+    std::vector<Back> backs;
+    StagedCall(int dev, cudaStream_t st) : device(dev), s(st)
+    {}
+    ~StagedCall()
+    {
+        if (!temps.empty())
+            cudaStreamSynchronize(s);
+        for (void * p : temps)
+            cudaFree(p);
+    }
+    int tmp(uint64_t bytes, void ** p)
+    {
+        cudaError_t e = cudaMalloc(p, bytes ? bytes : 8);
+        if (e != cudaSuccess)
+            return cuda_fail(e, "cudaMalloc (staging)", __FILE__, __LINE__);
+        temps.push_back(*p);
+        return SDSLGPU_OK;
+    }
+    template <class T>
+    int in(T const * p, uint64_t bytes, T const ** dev)
+    {
+        PtrSpace sp = PtrSpace::Device;
+        if (p == nullptr && bytes)
+        {
+            set_error("null input pointer");
+            return SDSLGPU_EINVAL;
+        }
+        if (bytes)
+            SG_TRY(classify(p, device, &sp));
+        if (sp == PtrSpace::Device && bytes)
+        {
+            *dev = p;
+            return SDSLGPU_OK;
+        }
+        void * d = nullptr;
+        SG_TRY(tmp(bytes, &d));
+        if (bytes)
+        {
+            any_host = true;
+            SG_CUDA(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, s));
+        }
+        *dev = static_cast<T const *>(d);
+        return SDSLGPU_OK;
+    }
+    template <class T>
+    int out(T * p, uint64_t bytes, T ** dev)
+    {
+        PtrSpace sp = PtrSpace::Host;
+        SG_TRY(classify(p, device, &sp));
+        if (sp == PtrSpace::Device)
+        {
+            *dev = p;
+            return SDSLGPU_OK;
+        }
+        void * d = nullptr;
+        SG_TRY(tmp(bytes, &d));
+        any_host = true;
+        backs.push_back(Back{p, d, bytes});
+        *dev = static_cast<T *>(d);
+        return SDSLGPU_OK;
+    }
+    template <class T>
+    int scratch(uint64_t bytes, T ** dev)
+    {
+        void * d = nullptr;
+        SG_TRY(tmp(bytes, &d));
+        *dev = static_cast<T *>(d);
+        return SDSLGPU_OK;
+    }
+    int peek_u64(uint64_t const * base, uint64_t index, uint64_t * value)
+    {
+        PtrSpace sp = PtrSpace::Host;
+        SG_TRY(classify(base, device, &sp));
+        if (sp == PtrSpace::Host)
+        {
+            *value = base[index];
+            return SDSLGPU_OK;
+        }
+        SG_CUDA(cudaMemcpyAsync(value, base + index, 8, cudaMemcpyDeviceToHost, s));
+        SG_CUDA(cudaStreamSynchronize(s));
+        return SDSLGPU_OK;
+    }
+    int finish()
+    {
+        for (Back const & b : backs)
+            if (b.bytes)
+                SG_CUDA(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, s));
+        if (any_host || !temps.empty())
+            SG_CUDA(cudaStreamSynchronize(s));
+        backs.clear();
+        return SDSLGPU_OK;
+    }
+};
+
 static bool is_byte_wt(sdslgpu_handle const * h)
 {
     return h->kind == SDSLGPU_KIND_WT_HUFF || h->kind == SDSLGPU_KIND_CSA_WT;
@@ -363,6 +473,9 @@ extern "C"
             return SDSLGPU_OK;
         case SDSLGPU_KIND_WT_HUFF:
             *size = h->wt.size;
+            return SDSLGPU_OK;
+        case SDSLGPU_KIND_CSA_WT:
+            *size = h->csa.n;
             return SDSLGPU_OK;
         }
         return SDSLGPU_ENOTSUP;
@@ -591,6 +704,138 @@ extern "C"
         }
         set_error("sdslgpu_wt_access: unsupported handle kind %d", h->kind);
         return SDSLGPU_ENOTSUP;
+    }
+
+    // -------------------------------------------------------------------------------- FM-index
+    int sdslgpu_csa_create(const uint8_t * text, uint64_t n, int device, uint32_t flags, sdslgpu_handle ** out)
+    {
+        if (!out || (!text && n))
+        {
+            set_error("sdslgpu_csa_create: null argument");
+            return SDSLGPU_EINVAL;
+        }
+        *out = nullptr;
+        sdslgpu_handle * h = nullptr;
+        SG_TRY(new_handle(SDSLGPU_KIND_CSA_WT, device, flags, &h));
+        DeviceGuard g(device);
+        int st = csa_build_from_text(h, text, n, nullptr);
+        if (st != SDSLGPU_OK)
+        {
+            h->pool.release_all();
+            delete h;
+            return st;
+        }
+        *out = h;
+        return SDSLGPU_OK;
+    }
+
+    int sdslgpu_fm_count(const sdslgpu_handle * h, const uint8_t * pats, const uint64_t * pat_off, uint64_t n, uint64_t * cnt_out, uint64_t * l_out, void * stream)
+    {
+        SG_TRY(check_handle(h));
+        if (h->kind != SDSLGPU_KIND_CSA_WT)
+        {
+            set_error("sdslgpu_fm_count: handle is not a CSA");
+            return SDSLGPU_ENOTSUP;
+        }
+        if (n == 0)
+            return SDSLGPU_OK;
+        if (!pat_off || !cnt_out)
+        {
+            set_error("sdslgpu_fm_count: null argument");
+            return SDSLGPU_EINVAL;
+        }
+        DeviceGuard g(h->device);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        StagedCall sc(h->device, s);
+        uint64_t const * d_off = nullptr;
+        uint8_t const * d_pats = nullptr;
+        uint64_t *d_cnt = nullptr, *d_l = nullptr;
+        SG_TRY(sc.in(pat_off, (n + 1) * 8, &d_off));
+        uint64_t total_bytes = 0;
+        SG_TRY(sc.peek_u64(pat_off, n, &total_bytes));
+        SG_TRY(sc.in(pats, total_bytes, &d_pats));
+        SG_TRY(sc.out(cnt_out, n * 8, &d_cnt));
+        if (l_out)
+            SG_TRY(sc.out(l_out, n * 8, &d_l));
+        SG_TRY(fm_count_device(h, d_pats, d_off, n, d_cnt, d_l, s));
+        return sc.finish();
+    }
+
+    int sdslgpu_fm_sa(const sdslgpu_handle * h, const uint64_t * i, uint64_t n, uint64_t * out, void * stream)
+    {
+        SG_TRY(check_handle(h));
+        if (h->kind != SDSLGPU_KIND_CSA_WT)
+        {
+            set_error("sdslgpu_fm_sa: handle is not a CSA");
+            return SDSLGPU_ENOTSUP;
+        }
+        if (n && (!i || !out))
+        {
+            set_error("sdslgpu_fm_sa: null argument");
+            return SDSLGPU_EINVAL;
+        }
+        Column in{i, nullptr, 8}, o{nullptr, out, 8};
+        return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
+            return fm_sa_device(h, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
+        });
+    }
+
+    int sdslgpu_fm_locate(const sdslgpu_handle * h,
+                          const uint8_t * pats,
+                          const uint64_t * pat_off,
+                          uint64_t n,
+                          uint64_t * occ_off_out,
+                          uint64_t * occ_out,
+                          uint64_t occ_cap,
+                          uint64_t * total_out,
+                          void * stream)
+    {
+        SG_TRY(check_handle(h));
+        if (h->kind != SDSLGPU_KIND_CSA_WT)
+        {
+            set_error("sdslgpu_fm_locate: handle is not a CSA");
+            return SDSLGPU_ENOTSUP;
+        }
+        if (!occ_off_out || !total_out || (n && !pat_off))
+        {
+            set_error("sdslgpu_fm_locate: null argument");
+            return SDSLGPU_EINVAL;
+        }
+        DeviceGuard g(h->device);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        StagedCall sc(h->device, s);
+        uint64_t const * d_off = nullptr;
+        uint8_t const * d_pats = nullptr;
+        uint64_t *d_cnt = nullptr, *d_l = nullptr, *d_occ_off = nullptr, *d_tmp = nullptr, *d_occ = nullptr;
+        uint64_t total_bytes = 0, total = 0;
+        if (n)
+        {
+            SG_TRY(sc.in(pat_off, (n + 1) * 8, &d_off));
+            SG_TRY(sc.peek_u64(pat_off, n, &total_bytes));
+            SG_TRY(sc.in(pats, total_bytes, &d_pats));
+        }
+        SG_TRY(sc.scratch((n + 1) * 8, &d_cnt));
+        SG_TRY(sc.scratch((n + 1) * 8, &d_l));
+        SG_TRY(sc.scratch(fm_scan_tmp_words(n) * 8, &d_tmp));
+        SG_TRY(sc.out(occ_off_out, (n + 1) * 8, &d_occ_off));
+        SG_TRY(fm_count_device(h, d_pats, d_off, n, d_cnt, d_l, s));
+        SG_TRY(fm_scan_counts_device(d_cnt, n, d_occ_off, d_tmp, s));
+        SG_CUDA(cudaMemcpyAsync(&total, d_occ_off + n, 8, cudaMemcpyDeviceToHost, s));
+        SG_CUDA(cudaStreamSynchronize(s));
+        *total_out = total;
+        if (occ_out && total)
+        {
+            if (occ_cap < total)
+            {
+                sc.finish();
+                set_error("sdslgpu_fm_locate: occ_out holds %llu entries but %llu occurrences were found", (unsigned long long)occ_cap,
+                          (unsigned long long)total);
+                return SDSLGPU_EINVAL;
+            }
+            SG_TRY(sc.out(occ_out, total * 8, &d_occ));
+            SG_TRY(fm_locate_fill_device(h, d_l, d_occ_off, n, total, d_occ, s));
+        }
+        return sc.finish();
     }
 
 } // extern "C"

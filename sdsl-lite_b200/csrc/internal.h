@@ -162,6 +162,26 @@ struct WtHuffImage
     WtTree host_tree;          // host copy (kept for serialisation / introspection)
 };
 
+// byte_alphabet of a CSA (csa_alphabet_strategy.hpp:136-212), staged in shared memory next to the tree
+struct FmTables
+{
+    uint64_t C[257];
+    uint8_t char2comp[256];
+    uint8_t comp2char[256];
+    uint32_t sigma;
+    uint32_t pad_;
+};
+
+struct CsaImage
+{
+    uint64_t n = 0;              // csa.size() = text length + 1
+    uint32_t sa_dens = 32;       // t_dens (csa_wt.hpp:50)
+    uint64_t * samples = nullptr; // SA[0], SA[dens], ... widened to u64 (csa_sampling_strategy.hpp:98-115)
+    uint64_t nsamples = 0;
+    FmTables * tab = nullptr; // device copy
+    FmTables host_tab;
+};
+
 } // namespace sdslgpu
 
 struct sdslgpu_handle
@@ -173,6 +193,7 @@ struct sdslgpu_handle
     sdslgpu::Staging staging;
     sdslgpu::BvImage bv;        // KIND_BV
     sdslgpu::WtHuffImage wt;    // KIND_WT_HUFF (and the BWT of KIND_CSA_WT)
+    sdslgpu::CsaImage csa;      // KIND_CSA_WT
 };
 
 namespace sdslgpu
@@ -189,6 +210,14 @@ int wt_huff_build_from_text(sdslgpu_handle * h, uint8_t const * text_host, uint6
 int wt_rank_device(sdslgpu_handle const * h, uint64_t const * i, uint8_t const * c, uint64_t n, uint64_t * out, cudaStream_t s);
 int wt_select_device(sdslgpu_handle const * h, uint64_t const * i, uint8_t const * c, uint64_t n, uint64_t * out, cudaStream_t s);
 int wt_access_device(sdslgpu_handle const * h, uint64_t const * i, uint64_t n, uint64_t * sym, uint64_t * rnk, cudaStream_t s);
+// fm.cu
+int csa_build_from_text(sdslgpu_handle * h, uint8_t const * text_host, uint64_t len, cudaStream_t s);
+int csa_upload(sdslgpu_handle * h, uint8_t const * bwt_host, uint64_t const * samples_host, uint64_t nsamples, cudaStream_t s);
+int fm_count_device(sdslgpu_handle const * h, uint8_t const * pats, uint64_t const * off, uint64_t npat, uint64_t * cnt, uint64_t * l, cudaStream_t s);
+int fm_sa_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t cnt, uint64_t * out, cudaStream_t s);
+int fm_scan_counts_device(uint64_t const * cnt, uint64_t npat, uint64_t * occ_off, uint64_t * tmp, cudaStream_t s);
+int fm_locate_fill_device(sdslgpu_handle const * h, uint64_t const * l, uint64_t const * occ_off, uint64_t npat, uint64_t total, uint64_t * occ, cudaStream_t s);
+uint64_t fm_scan_tmp_words(uint64_t npat);
 unsigned grid_for(uint64_t n, int per_thread = 1);
 unsigned blocks_for(uint64_t n);
 } // namespace sdslgpu

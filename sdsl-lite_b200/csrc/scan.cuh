@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(In const *
 }
 
 // in-place exclusive scan of `m` u64 values by ONE CTA; total -> *grand_total
-__global__ void __launch_bounds__(1024) scan_single_cta_kernel(uint64_t * __restrict__ v, uint64_t m, uint64_t * __restrict__ grand_total)
+static __global__ void __launch_bounds__(1024) scan_single_cta_kernel(uint64_t * __restrict__ v, uint64_t m, uint64_t * __restrict__ grand_total)
 {
     uint64_t carry = 0;
     for (uint64_t base = 0; base < m; base += blockDim.x)

@@ -13,11 +13,12 @@
 #include <thread>
 
 #include "internal.h"
+#include "wt_device.cuh"
 
 namespace sdslgpu
 {
 
-static constexpr uint16_t kUndef = 0xFFFF;
+static constexpr uint16_t kUndef = kWtUndef;
 
 // ------------------------------------------------------------------------------------------------
 // host: Huffman shape + BFS layout (tiny), then the bit planes in parallel over text chunks
@@ -204,51 +205,6 @@ static void fill_bit_planes(uint8_t const * text, uint64_t n, WtTree const & tre
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_tree(WtTree const * __restrict__ g, WtTree * s)
-{
-    // cooperative 16-byte copy of the ~14 KB table into shared memory
-    uint4 const * src = reinterpret_cast<uint4 const *>(g);
-    uint4 * dst = reinterpret_cast<uint4 *>(s);
-    for (uint32_t k = threadIdx.x; k < sizeof(WtTree) / 16; k += blockDim.x)
-        dst[k] = __ldg(src + k);
-    __syncthreads();
-}
-
-// rank(i, c) for one query against a staged tree (wt_pc.hpp:371-399)
-__device__ __forceinline__ uint64_t wt_rank_one(BvView const & bv, WtTree const * t, uint64_t sigma, uint64_t i, uint32_t c)
-{
-    if (t->c_to_leaf[c] == kUndef)
-        return 0;
-    if (sigma == 1)
-        return i;
-    uint64_t p = t->path[c];
-    uint32_t len = (uint32_t)(p >> 56);
-    uint64_t r = i;
-    uint32_t v = 0;
-    for (uint32_t l = 0; l < len && r; ++l, p >>= 1)
-    {
-        uint64_t o = bv_rank1(bv, t->bv_pos[v] + r) - t->bv_pos_rank[v];
-        r = (p & 1) ? o : r - o;
-        v = t->child[v][p & 1];
-    }
-    return r;
-}
-
-// (rank(i, wt[i]), wt[i]) (wt_pc.hpp:411-430): per level one sector gives both the bit and the rank
-__device__ __forceinline__ uint64_t wt_inverse_select_one(BvView const & bv, WtTree const * t, uint64_t i, uint32_t & sym)
-{
-    uint32_t v = 0;
-    while (t->child[v][0] != kUndef)
-    {
-        uint32_t bit;
-        uint64_t o = bv_rank1_and_bit(bv, t->bv_pos[v] + i, bit) - t->bv_pos_rank[v];
-        i = bit ? o : i - o;
-        v = t->child[v][bit];
-    }
-    sym = (uint32_t)t->bv_pos_rank[v];
-    return i;
-}
-
 __global__ void __launch_bounds__(kThreads) wt_rank_kernel(BvView const bv,
                                                            WtTree const * __restrict__ tree,
                                                            uint64_t size,

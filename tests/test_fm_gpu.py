@@ -1,0 +1,91 @@
+"""GPU parity: csa_wt<wt_huff<>> count / locate / SA access / bwt.rank through the C ABI (SURVEY.md §8 rows
+a9, a10) against the oracle, the unmodified reference, and a brute-force scan (count/locate are unpinned by
+the reference's own tests)."""
+import numpy as np
+import pytest
+
+import texts
+
+pytestmark = pytest.mark.gpu
+
+
+def _patterns(t, rng, k, maxlen=24):
+    n = len(t)
+    pats = []
+    for _ in range(k):
+        m = int(rng.integers(1, maxlen + 1))
+        if n and rng.random() < 0.7:
+            s = int(rng.integers(0, max(1, n - m + 1)))
+            pats.append(t[s : s + m])
+        else:
+            pats.append(rng.integers(1, 256, m, dtype=np.uint8).tobytes())
+    return pats + [b"", t, t[:4], t + b"x"]
+
+
+def test_fm_catalogue(pkg, oracle, orc):
+    rng = np.random.default_rng(21)
+    for name, t in texts.text_catalogue(zero_free=True, large=True):
+        with pkg.CsaWt(t) as csa:
+            assert csa.size == len(t) + 1, name
+            pats = _patterns(t, rng, 1500)
+            flat, off = pkg.csr_patterns(pats)
+            cnt, l = csa.count(flat, off, want_l=True)
+            small = [p for p, c in zip(pats, cnt) if c <= 5000]
+            sflat, soff = pkg.csr_patterns(small)
+            occ_off, occ = csa.locate(sflat, soff)
+            i = rng.integers(0, len(t) + 1, 4000, dtype=np.uint64)
+            sa = csa.sa(i)
+            qi, qc = texts.wt_queries(t + b"\0", rng, 4000)
+            br = csa.bwt_rank(qi, qc)
+            checkers = [("oracle", oracle.csa(t))]
+            if orc.ref_available():
+                checkers.append(("reference", orc.Ref().csa(t)))
+            for cname, chk in checkers:
+                c2, l2 = chk.count(flat, off, want_l=True)
+                assert (cnt == c2).all(), (name, cname, "count")
+                assert (l[cnt > 0] == l2[cnt > 0]).all(), (name, cname, "interval")
+                o2 = chk.locate(sflat, soff)
+                assert (occ_off == o2[0]).all() and (occ == o2[1]).all(), (name, cname, "locate order")
+                assert (sa == chk.sa(i)).all(), (name, cname, "SA access")
+                if cname == "reference":
+                    assert (br == chk.bwt_rank(qi, qc)).all(), (name, "bwt.rank")
+            # brute force on a few patterns
+            for k in rng.integers(0, len(small), 25):
+                p = small[int(k)]
+                if not p or len(t) > 200000:
+                    continue
+                want, s = [], t.find(p)
+                while s >= 0:
+                    want.append(s)
+                    s = t.find(p, s + 1)
+                assert sorted(occ[int(occ_off[k]) : int(occ_off[k + 1])].tolist()) == want, (name, p)
+
+
+def test_fm_rejects_zero_byte(pkg):
+    with pytest.raises(pkg.SdslGpuError):
+        pkg.CsaWt(b"abc\0def")
+
+
+def test_fm_device_buffers(pkg, oracle):
+    import torch
+
+    rng = np.random.default_rng(2)
+    t = rng.integers(1, 256, 2_000_000, dtype=np.uint8).tobytes()
+    pats = [t[s : s + 20] for s in rng.integers(0, len(t) - 20, 50000)]
+    flat, off = pkg.csr_patterns(pats)
+    with pkg.CsaWt(t) as csa:
+        d_flat, d_off = torch.from_numpy(flat).cuda(), torch.from_numpy(off.view(np.int64)).cuda()
+        cnt = csa.count(d_flat, d_off)
+        torch.cuda.synchronize()
+        host = csa.count(flat, off)
+        assert (cnt.cpu().numpy().view(np.uint64) == host).all() and (host >= 1).all()
+        occ_off, occ = csa.locate(d_flat, d_off)
+        torch.cuda.synchronize()
+        occ_off, occ = occ_off.cpu().numpy().view(np.uint64), occ.cpu().numpy().view(np.uint64)
+        # every reported position really is an occurrence; patterns sampled at s are found at s
+        arr = np.frombuffer(t, dtype=np.uint8)
+        for k in rng.integers(0, len(pats), 300):
+            for p in occ[int(occ_off[k]) : int(occ_off[k + 1])]:
+                assert t[int(p) : int(p) + 20] == pats[int(k)]
+        chk = oracle.csa(t)
+        assert (host == chk.count(flat, off)).all()
