@@ -119,8 +119,29 @@ class Oracle:
         L.orc_csa_serialize.restype = C.c_uint64
         L.orc_csa_serialize.argtypes = [C.c_void_p, u8p, C.c_uint64]
 
+        for kind in ("rrr", "sd"):
+            getattr(L, f"orc_{kind}_build").restype = C.c_void_p
+            getattr(L, f"orc_{kind}_build").argtypes = [u64p, C.c_uint64]
+            getattr(L, f"orc_{kind}_free").argtypes = [C.c_void_p]
+            for op in ("rank", "select"):
+                f = getattr(L, f"orc_{kind}_{op}_batch")
+                f.restype = None
+                f.argtypes = [C.c_void_p, C.c_int, u64p, C.c_uint64, u64p]
+            f = getattr(L, f"orc_{kind}_access_batch")
+            f.restype = None
+            f.argtypes = [C.c_void_p, u64p, C.c_uint64, u64p]
+            f = getattr(L, f"orc_{kind}_serialize")
+            f.restype = C.c_uint64
+            f.argtypes = [C.c_void_p, u8p, C.c_uint64]
+
     def csa(self, text):
         return OracleCsa(self, text)
+
+    def rrr(self, words, nbits):
+        return OracleCompressed(self, "rrr", words, nbits)
+
+    def sd(self, words, nbits):
+        return OracleCompressed(self, "sd", words, nbits)
 
     # -- plain bit vector ------------------------------------------------------------------
     def bv(self, words, nbits):
@@ -215,6 +236,42 @@ class OracleWtHuff:
     def __del__(self):
         if getattr(self, "h", None):
             self.L.orc_wt_huff_free(self.h)
+            self.h = None
+
+
+class OracleCompressed:
+    """rrr_vector<63> / sd_vector<> restatement"""
+
+    def __init__(self, o, kind, words, nbits):
+        self.L, self.kind = o.L, kind
+        self.nbits = int(nbits)
+        self.w = _padded_words(words, nbits)
+        self.h = getattr(self.L, f"orc_{kind}_build")(_p64(self.w), self.nbits)
+
+    def _q(self, op, x, b):
+        x = _u64(x)
+        out = np.zeros(len(x), dtype=np.uint64)
+        getattr(self.L, f"orc_{self.kind}_{op}_batch")(self.h, b, _p64(x), len(x), _p64(out))
+        return out
+
+    def rank(self, idx, b=1):
+        return self._q("rank", idx, b)
+
+    def select(self, i, b=1):
+        return self._q("select", i, b)
+
+    def access(self, idx):
+        idx = _u64(idx)
+        out = np.zeros(len(idx), dtype=np.uint64)
+        getattr(self.L, f"orc_{self.kind}_access_batch")(self.h, _p64(idx), len(idx), _p64(out))
+        return out
+
+    def serialize(self):
+        return _blob(getattr(self.L, f"orc_{self.kind}_serialize"), self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            getattr(self.L, f"orc_{self.kind}_free")(self.h)
             self.h = None
 
 

@@ -140,9 +140,9 @@ inline BvView bv_view(BvImage const & v)
 
 // node table + per-symbol paths of a byte wavelet tree (wt_helper.hpp:219-225), as staged into shared
 // memory by every wt / fm kernel.  ~14 KB.
-struct WtTree
+struct alignas(16) WtTree
 {
-    static constexpr int kMaxNodes = 511;
+    static constexpr int kMaxNodes = 512; // 2*256-1 nodes + one sentinel slot (keeps every array 16-byte aligned)
     uint64_t bv_pos[kMaxNodes];
     uint64_t bv_pos_rank[kMaxNodes]; // leaves: the symbol
     uint16_t child[kMaxNodes][2];    // 0xFFFF = leaf
@@ -163,7 +163,7 @@ struct WtHuffImage
 };
 
 // byte_alphabet of a CSA (csa_alphabet_strategy.hpp:136-212), staged in shared memory next to the tree
-struct FmTables
+struct alignas(16) FmTables
 {
     uint64_t C[257];
     uint8_t char2comp[256];
@@ -221,3 +221,5 @@ uint64_t fm_scan_tmp_words(uint64_t npat);
 unsigned grid_for(uint64_t n, int per_thread = 1);
 unsigned blocks_for(uint64_t n);
 } // namespace sdslgpu
+
+static_assert(sizeof(sdslgpu::WtTree) % 16 == 0 && sizeof(sdslgpu::FmTables) % 16 == 0, "tables are staged with 16-byte copies");
