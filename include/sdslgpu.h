@@ -69,6 +69,16 @@ int sdslgpu_device_count(int *count);
  * past nbits in the last word are ignored.  All supports are built on the device. */
 int sdslgpu_bv_create(const uint64_t *words, uint64_t nbits, int device, uint32_t flags, sdslgpu_handle **out);
 
+/* Replaces rrr_vector<63>(bit_vector) (rrr_vector.hpp:158-270): classes, enumerative offsets (bin_to_nr,
+ * rrr_helper.hpp:346-366), per-superblock samples and invert bits are computed ON THE DEVICE and are
+ * bit-identical to the reference's (sdslgpu_serialize returns the reference's byte format). */
+int sdslgpu_rrr63_create(const uint64_t *words, uint64_t nbits, int device, uint32_t flags, sdslgpu_handle **out);
+
+/* Replaces sd_vector<>(bit_vector) (sd_vector.hpp:218-257): low / high parts are scattered on the device
+ * (bit-identical to m_low / m_high); select_support_mcl<1>/<0> over `high` (sd_vector.hpp:162-163) are
+ * served by the engine's own rank blocks + select samples. */
+int sdslgpu_sd_create(const uint64_t *words, uint64_t nbits, int device, uint32_t flags, sdslgpu_handle **out);
+
 int sdslgpu_free(sdslgpu_handle *h);
 int sdslgpu_kind(const sdslgpu_handle *h, int *kind);
 /* size(): number of bits (bit vectors) / symbols (wavelet trees) / text length + 1 (csa) */
@@ -157,6 +167,14 @@ int sdslgpu_fm_locate(const sdslgpu_handle *h, const uint8_t *pats, const uint64
  * needed; buf may be NULL to query it.  The rank tables are built ON THE DEVICE and are byte-identical
  * to rank_support_v::serialize (rank_support_v.hpp:151-158). */
 int sdslgpu_bv_serialize(const sdslgpu_handle *h, int what, void *buf, uint64_t cap, uint64_t *nbytes);
+
+/* Same protocol for the other kinds (what = 0):
+ *   KIND_BV     -> as sdslgpu_bv_serialize (what 0..2)
+ *   KIND_RRR63  -> the complete rrr_vector<63>::serialize bytes (rrr_vector.hpp:366-378)
+ *   KIND_SD     -> size, wl, m_low, m_high as sd_vector::serialize writes them (sd_vector.hpp:426-433; the two
+ *                  select supports that follow in the reference's file are not part of this engine's image);
+ *                  needs SDSLGPU_F_SDSL_LAYOUT. */
+int sdslgpu_serialize(const sdslgpu_handle *h, int what, void *buf, uint64_t cap, uint64_t *nbytes);
 
 #ifdef __cplusplus
 }

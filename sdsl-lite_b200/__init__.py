@@ -341,3 +341,45 @@ class CsaWt(_Handle, _WaveletTreeOps):
         if total.value:
             _check(lib().sdslgpu_fm_locate(self._h, pf, po, n, poo, pocc, total.value, C.byref(total), sp))
         return occ_off, occ[: total.value]
+
+
+_SIGNATURES += [
+    ("sdslgpu_rrr63_create", C.c_int, [vp, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(vp)]),
+    ("sdslgpu_sd_create", C.c_int, [vp, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(vp)]),
+    ("sdslgpu_serialize", C.c_int, [vp, C.c_int, vp, C.c_uint64, u64p]),
+]
+
+
+class _CompressedBitVector(_Handle):
+    _create = None
+
+    def __init__(self, words, nbits, device=0, flags=F_DEFAULT):
+        super().__init__()
+        nbits = int(nbits)
+        if _is_torch(words):
+            p, n, keep = words.data_ptr(), words.numel(), words
+        else:
+            keep = np.ascontiguousarray(words, dtype=np.uint64)
+            p, n = keep.ctypes.data, keep.size
+        assert n >= (nbits + 63) // 64, "words too short for nbits"
+        _check(getattr(lib(), self._create)(p if n else None, nbits, device, flags, C.byref(self._h)))
+        self.nbits = nbits
+
+    def serialize(self, what=0):
+        n = C.c_uint64()
+        _check(lib().sdslgpu_serialize(self._h, what, None, 0, C.byref(n)))
+        buf = np.empty(max(n.value, 1), dtype=np.uint8)
+        _check(lib().sdslgpu_serialize(self._h, what, buf.ctypes.data, n.value, C.byref(n)))
+        return buf[: n.value].tobytes()
+
+
+class RrrVector(_CompressedBitVector):
+    """rrr_vector<63> + rank_support_rrr + select_support_rrr, encoded on the device"""
+
+    _create = "sdslgpu_rrr63_create"
+
+
+class SdVector(_CompressedBitVector):
+    """sd_vector<> + rank_support_sd + select_support_sd, built on the device"""
+
+    _create = "sdslgpu_sd_create"

@@ -477,6 +477,12 @@ extern "C"
         case SDSLGPU_KIND_CSA_WT:
             *size = h->csa.n;
             return SDSLGPU_OK;
+        case SDSLGPU_KIND_RRR63:
+            *size = h->rrr.size;
+            return SDSLGPU_OK;
+        case SDSLGPU_KIND_SD:
+            *size = h->sd.size;
+            return SDSLGPU_OK;
         }
         return SDSLGPU_ENOTSUP;
     }
@@ -490,6 +496,12 @@ extern "C"
         {
         case SDSLGPU_KIND_BV:
             *count = b ? h->bv.ones : h->bv.nbits - h->bv.ones;
+            return SDSLGPU_OK;
+        case SDSLGPU_KIND_RRR63:
+            *count = b ? h->rrr.ones : h->rrr.size - h->rrr.ones;
+            return SDSLGPU_OK;
+        case SDSLGPU_KIND_SD:
+            *count = b ? h->sd.m : h->sd.size - h->sd.m;
             return SDSLGPU_OK;
         }
         return SDSLGPU_ENOTSUP;
@@ -521,6 +533,13 @@ extern "C"
         case SDSLGPU_KIND_BV:
             return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
                 return bv_rank_device(h->bv, h->flags, b, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
+            });        case SDSLGPU_KIND_RRR63:
+            return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
+                return rrr_rank_device(h, b, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
+            });
+        case SDSLGPU_KIND_SD:
+            return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
+                return sd_rank_device(h, b, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
             });
         }
         set_error("sdslgpu_rank: unsupported handle kind %d", h->kind);
@@ -546,6 +565,13 @@ extern "C"
         case SDSLGPU_KIND_BV:
             return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
                 return bv_select_device(h->bv, b, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
+            });        case SDSLGPU_KIND_RRR63:
+            return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
+                return rrr_select_device(h, b, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
+            });
+        case SDSLGPU_KIND_SD:
+            return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
+                return sd_select_device(h, b, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
             });
         }
         set_error("sdslgpu_select: unsupported handle kind %d", h->kind);
@@ -566,6 +592,13 @@ extern "C"
         case SDSLGPU_KIND_BV:
             return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
                 return bv_access_device(h->bv, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
+            });        case SDSLGPU_KIND_RRR63:
+            return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
+                return rrr_access_device(h, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
+            });
+        case SDSLGPU_KIND_SD:
+            return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
+                return sd_access_device(h, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
             });
         }
         set_error("sdslgpu_access: unsupported handle kind %d", h->kind);
@@ -611,6 +644,73 @@ extern "C"
         std::memcpy(buf, &header, 8);
         if (words)
             SG_CUDA(cudaMemcpy(static_cast<uint8_t *>(buf) + 8, src, words * 8, cudaMemcpyDeviceToHost));
+        return SDSLGPU_OK;
+    }
+
+    // -------------------------------------------------------------------------------- compressed bit vectors
+    static int create_compressed(int kind, const uint64_t * words, uint64_t nbits, int device, uint32_t flags, sdslgpu_handle ** out)
+    {
+        if (!out || (!words && nbits))
+        {
+            set_error("create: null argument");
+            return SDSLGPU_EINVAL;
+        }
+        *out = nullptr;
+        sdslgpu_handle * h = nullptr;
+        SG_TRY(new_handle(kind, device, flags, &h));
+        DeviceGuard g(device);
+        PtrSpace sp = PtrSpace::Host;
+        int st = nbits ? classify(words, device, &sp) : SDSLGPU_OK;
+        if (st == SDSLGPU_OK)
+            st = (kind == SDSLGPU_KIND_RRR63) ? rrr_build(h, words, sp == PtrSpace::Device, nbits, nullptr)
+                                              : sd_build(h, words, sp == PtrSpace::Device, nbits, nullptr);
+        if (st != SDSLGPU_OK)
+        {
+            h->pool.release_all();
+            delete h;
+            return st;
+        }
+        *out = h;
+        return SDSLGPU_OK;
+    }
+
+    int sdslgpu_rrr63_create(const uint64_t * words, uint64_t nbits, int device, uint32_t flags, sdslgpu_handle ** out)
+    {
+        return create_compressed(SDSLGPU_KIND_RRR63, words, nbits, device, flags, out);
+    }
+
+    int sdslgpu_sd_create(const uint64_t * words, uint64_t nbits, int device, uint32_t flags, sdslgpu_handle ** out)
+    {
+        return create_compressed(SDSLGPU_KIND_SD, words, nbits, device, flags, out);
+    }
+
+    int sdslgpu_serialize(const sdslgpu_handle * h, int what, void * buf, uint64_t cap, uint64_t * nbytes)
+    {
+        SG_TRY(check_handle(h));
+        if (!nbytes)
+            return SDSLGPU_EINVAL;
+        if (h->kind == SDSLGPU_KIND_BV)
+            return sdslgpu_bv_serialize(h, what, buf, cap, nbytes);
+        DeviceGuard g(h->device);
+        std::vector<uint8_t> blob;
+        if (h->kind == SDSLGPU_KIND_RRR63 && what == 0)
+            SG_TRY(rrr_serialize(h, blob));
+        else if (h->kind == SDSLGPU_KIND_SD && what == 0)
+            SG_TRY(sd_serialize_low_high(h, blob));
+        else
+        {
+            set_error("sdslgpu_serialize: unsupported (kind %d, what %d)", h->kind, what);
+            return SDSLGPU_ENOTSUP;
+        }
+        *nbytes = blob.size();
+        if (!buf)
+            return SDSLGPU_OK;
+        if (cap < blob.size())
+        {
+            set_error("sdslgpu_serialize: buffer too small");
+            return SDSLGPU_EINVAL;
+        }
+        std::memcpy(buf, blob.data(), blob.size());
         return SDSLGPU_OK;
     }
 

@@ -172,6 +172,25 @@ struct alignas(16) FmTables
     uint32_t pad_;
 };
 
+// rrr_vector<63, int_vector<>, 32> (rrr_vector.hpp:101-109)
+struct RrrImage
+{
+    uint64_t size = 0, nblocks = 0, nsuper = 0, ones = 0, btnr_bits = 0;
+    uint64_t * bt = nullptr;      // m_bt: packed 6-bit classes, 3 words per superblock
+    uint64_t * btnr = nullptr;    // m_btnr
+    uint64_t * records = nullptr; // per superblock {m_rank, m_btnrp | m_invert << 63}, plus a closing record
+    void * tables = nullptr;      // RrrTables (binomials + code lengths), device copy
+};
+
+// sd_vector<> (sd_vector.hpp:155-163)
+struct SdImage
+{
+    uint64_t size = 0, m = 0, high_bits = 0, low_words = 0;
+    uint32_t wl = 0;
+    uint64_t * low = nullptr; // m_low, packed wl-bit entries
+    BvImage high;             // m_high with rank blocks + select<1>/<0> samples
+};
+
 struct CsaImage
 {
     uint64_t n = 0;              // csa.size() = text length + 1
@@ -194,6 +213,8 @@ struct sdslgpu_handle
     sdslgpu::BvImage bv;        // KIND_BV
     sdslgpu::WtHuffImage wt;    // KIND_WT_HUFF (and the BWT of KIND_CSA_WT)
     sdslgpu::CsaImage csa;      // KIND_CSA_WT
+    sdslgpu::RrrImage rrr;      // KIND_RRR63
+    sdslgpu::SdImage sd;        // KIND_SD
 };
 
 namespace sdslgpu
@@ -210,6 +231,18 @@ int wt_huff_build_from_text(sdslgpu_handle * h, uint8_t const * text_host, uint6
 int wt_rank_device(sdslgpu_handle const * h, uint64_t const * i, uint8_t const * c, uint64_t n, uint64_t * out, cudaStream_t s);
 int wt_select_device(sdslgpu_handle const * h, uint64_t const * i, uint8_t const * c, uint64_t n, uint64_t * out, cudaStream_t s);
 int wt_access_device(sdslgpu_handle const * h, uint64_t const * i, uint64_t n, uint64_t * sym, uint64_t * rnk, cudaStream_t s);
+// rrr.cu
+int rrr_build(sdslgpu_handle * h, uint64_t const * words_host_or_dev, bool on_device, uint64_t nbits, cudaStream_t s);
+int rrr_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
+int rrr_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
+int rrr_access_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
+int rrr_serialize(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
+// sd.cu
+int sd_build(sdslgpu_handle * h, uint64_t const * words_host_or_dev, bool on_device, uint64_t nbits, cudaStream_t s);
+int sd_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
+int sd_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
+int sd_access_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
+int sd_serialize_low_high(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
 // fm.cu
 int csa_build_from_text(sdslgpu_handle * h, uint8_t const * text_host, uint64_t len, cudaStream_t s);
 int csa_upload(sdslgpu_handle * h, uint8_t const * bwt_host, uint64_t const * samples_host, uint64_t nsamples, cudaStream_t s);

@@ -1,0 +1,80 @@
+"""GPU parity: rrr_vector<63> and sd_vector<> rank / select / access through the C ABI (SURVEY.md §8 rows a5,
+a6), against the oracle and the unmodified reference; plus construction parity: the device encoders reproduce
+the reference's serialised bytes."""
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+KINDS = {"rrr": "RrrVector", "sd": "SdVector"}
+
+
+def _checkers(oracle, orc, kind, w, nbits):
+    out = [("oracle", getattr(oracle, kind)(w, nbits))]
+    if orc.ref_available():
+        out.append(("reference", getattr(orc.Ref(), kind)(w, nbits)))
+    return out
+
+
+def _vectors():
+    for cid, w, nbits in cases.bitvector_catalogue(large=True):
+        yield cid, w, nbits
+    for d in (0.01, 0.05, 0.25, 0.5, 0.9):
+        nbits = (1 << 21) + 63 * 32 * 5
+        yield f"density {d}", cases.bernoulli_words(nbits, d, int(d * 100)), nbits
+    for nbits in (63, 63 * 32, 63 * 32 * 3, 63 * 31, 63 * 33, 2016 * 2 + 1):
+        yield f"edge {nbits}", cases.random_words(nbits, nbits), nbits
+        yield f"edge90 {nbits}", cases.bernoulli_words(nbits, 0.9, nbits), nbits
+
+
+@pytest.mark.parametrize("kind", ["rrr", "sd"])
+def test_compressed_catalogue(pkg, oracle, orc, kind):
+    for cid, w, nbits in _vectors():
+        if kind == "sd" and nbits == 0:
+            continue
+        with getattr(pkg, KINDS[kind])(w, nbits, flags=pkg.F_SDSL_LAYOUT) as v:
+            assert v.size == nbits
+            idx = cases.rank_queries(nbits, 11, 40000)
+            got_rank = {b: v.rank(idx, b) for b in (0, 1)}
+            sel_q = {b: cases.select_queries(v.arg_count(b), 12, 2000 if (kind == "sd" and b == 0) else 40000) for b in (0, 1)}
+            got_sel = {b: v.select(sel_q[b], b) for b in (0, 1)}
+            pos = idx[idx < nbits]
+            got_acc = v.access(pos)
+            blob = v.serialize()
+            for name, chk in _checkers(oracle, orc, kind, w, nbits):
+                for b in (0, 1):
+                    assert (got_rank[b] == chk.rank(idx, b)).all(), (kind, cid, name, "rank", b)
+                    assert v.arg_count(b) == int(chk.rank([nbits], b)[0]), (kind, cid, name, "arg_count")
+                    if len(sel_q[b]):
+                        assert (got_sel[b] == chk.select(sel_q[b], b)).all(), (kind, cid, name, "select", b)
+                if len(pos):
+                    assert (got_acc == chk.access(pos)).all(), (kind, cid, name, "access")
+                ref_blob = chk.serialize()
+                if kind == "rrr":
+                    assert blob == ref_blob, (kind, cid, name, "serialised bytes")
+                else:  # size, wl, low, high = a prefix of sd_vector::serialize
+                    assert ref_blob[: len(blob)] == blob, (kind, cid, name, "serialised low/high")
+            if kind == "rrr":  # beyond the last b-bit the reference answers size() in-band
+                for b in (0, 1):
+                    assert v.select(np.array([v.arg_count(b) + 1], np.uint64), b)[0] == nbits
+
+
+@pytest.mark.parametrize("kind", ["rrr", "sd"])
+def test_compressed_density_sweep_properties(pkg, oracle, kind):
+    """BASELINE config 3 shape at 2^26 bits: density sweep, size-independent properties + oracle spot checks"""
+    nbits = (1 << 26) + 4321
+    for d in (0.01, 0.1, 0.5):
+        w = cases.bernoulli_words(nbits, d, 7 + int(d * 1000))
+        with getattr(pkg, KINDS[kind])(w, nbits) as v, pkg.BitVector(w, nbits) as plain:
+            idx = cases.rank_queries(nbits, 8, 300000)
+            r1 = v.rank(idx, 1)
+            assert (r1 == plain.rank(idx, 1)).all() and (v.rank(idx, 0) + r1 == idx).all()
+            k = cases.select_queries(v.arg_count(1), 9, 300000)
+            p = v.select(k, 1)
+            assert (p == plain.select(k, 1)).all() and (v.access(p) == 1).all()
+            k0 = cases.select_queries(v.arg_count(0), 10, 300000 if kind == "rrr" else 3000)
+            assert (v.select(k0, 0) == plain.select(k0, 0)).all()
+            o = getattr(oracle, kind)(w, nbits)
+            assert (v.rank(idx[:5000], 1) == o.rank(idx[:5000], 1)).all()
