@@ -114,6 +114,10 @@ int sdslgpu_access(const sdslgpu_handle *h, const uint64_t *idx, uint64_t n, uin
  * equal the reference's; rank/select structures over it are built on the device. */
 int sdslgpu_wt_huff_create(const uint8_t *text, uint64_t n, int device, uint32_t flags, sdslgpu_handle **out);
 
+/* Replaces wt_int<>(seq) (wt_int.hpp:160-260): `seq` is a HOST array of n integers; the level bit vector
+ * m_tree (max_level = hi(max)+1 levels of n bits) is laid out exactly like the reference's. */
+int sdslgpu_wt_int_create(const uint64_t *seq, uint64_t n, int device, uint32_t flags, sdslgpu_handle **out);
+
 /* number of distinct symbols (wt.sigma, wt_pc.hpp:177) */
 int sdslgpu_wt_sigma(const sdslgpu_handle *h, uint64_t *sigma);
 

@@ -291,3 +291,199 @@ uint64_t orc_wt_huff_serialize(const orc_wt_huff *w, uint8_t *out, uint64_t cap)
     orc__wt_huff_serialize_into(&b, w);
     return orc__buf_finish(&b, out, cap);
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* a8: wt_int<> = wt_int<bit_vector, rank_support_v<1>, select_support_mcl<1>, <0>>            */
+/* ------------------------------------------------------------------------------------------ */
+
+/* wt_int.hpp:160-260: level k holds, for the sequence stably sorted by its top k bits, bit (max_level-k-1) */
+orc_wt_int *orc_wt_int_build(const uint64_t *seq, uint64_t n)
+{
+    orc_wt_int *w = (orc_wt_int *)calloc(1, sizeof(*w));
+    uint64_t max_elem = 1, i, *cur, *nxt, bits;
+    uint32_t k;
+    w->size = n;
+    if (n == 0)
+        return w;
+    for (i = 0; i < n; ++i)
+        if (seq[i] > max_elem)
+            max_elem = seq[i];
+    w->max_level = orc_hi(max_elem) + 1;
+    bits = n * w->max_level;
+    w->tree_bits = bits;
+    w->tree = (uint64_t *)calloc(((bits + 63) >> 6) + 2, 8);
+    cur = (uint64_t *)malloc(8 * n);
+    nxt = (uint64_t *)malloc(8 * n);
+    memcpy(cur, seq, 8 * n);
+    for (k = 0; k < w->max_level; ++k) {
+        uint32_t shift = w->max_level - k - 1;
+        uint64_t start = 0;
+        while (start < n) {
+            uint64_t node = (shift + 1 >= 64) ? 0 : (cur[start] >> (shift + 1)), end = start, c0 = 0, c1 = 0, z;
+            while (end < n && ((shift + 1 >= 64) ? 0 : (cur[end] >> (shift + 1))) == node)
+                ++end;
+            for (i = start; i < end; ++i)
+                c0 += !((cur[i] >> shift) & 1);
+            z = 0;
+            for (i = start; i < end; ++i) {
+                uint64_t pos = (uint64_t)k * n + i;
+                if ((cur[i] >> shift) & 1) {
+                    w->tree[pos >> 6] |= 1ULL << (pos & 63);
+                    nxt[start + c0 + c1++] = cur[i];
+                } else
+                    nxt[start + z++] = cur[i];
+            }
+            if (k + 1 == w->max_level)
+                w->sigma += (c0 > 0) + (c1 > 0);
+            start = end;
+        }
+        {
+            uint64_t *t = cur;
+            cur = nxt;
+            nxt = t;
+        }
+    }
+    free(cur);
+    free(nxt);
+    w->rank_table = (uint64_t *)calloc(orc_rank_v_table_words(bits), 8);
+    orc_rank_v_build(w->tree, bits, 1, w->rank_table);
+    w->sel1 = orc_select_mcl_build(w->tree, bits, 1);
+    w->sel0 = orc_select_mcl_build(w->tree, bits, 0);
+    return w;
+}
+
+void orc_wt_int_free(orc_wt_int *w)
+{
+    if (!w)
+        return;
+    free(w->tree);
+    free(w->rank_table);
+    orc_select_mcl_free(w->sel1);
+    orc_select_mcl_free(w->sel0);
+    free(w);
+}
+
+static uint64_t ti_rank(const orc_wt_int *w, uint64_t i)
+{
+    return orc_rank_v(w->tree, w->rank_table, 1, i);
+}
+
+/* wt_int.hpp:379-409 */
+uint64_t orc_wt_int_rank(const orc_wt_int *w, uint64_t i, uint64_t c)
+{
+    uint64_t offset = 0, mask, node_size = w->size;
+    uint32_t k;
+    if (w->size == 0 || (w->max_level < 64 && (1ULL << w->max_level) <= c))
+        return 0;
+    mask = 1ULL << (w->max_level - 1);
+    for (k = 0; k < w->max_level && i; ++k) {
+        uint64_t o0 = ti_rank(w, offset), oi = ti_rank(w, offset + i) - o0, oe = ti_rank(w, offset + node_size) - o0;
+        if (c & mask) {
+            offset += node_size - oe;
+            node_size = oe;
+            i = oi;
+        } else {
+            node_size -= oe;
+            i -= oi;
+        }
+        offset += w->size;
+        mask >>= 1;
+    }
+    return i;
+}
+
+/* wt_int.hpp:418-445 (and operator[] :340-367) */
+uint64_t orc_wt_int_inverse_select(const orc_wt_int *w, uint64_t i, uint64_t *sym)
+{
+    uint64_t c = 0, node_size = w->size, offset = 0;
+    uint32_t k;
+    for (k = 0; k < w->max_level; ++k) {
+        uint64_t o0 = ti_rank(w, offset), oi = ti_rank(w, offset + i) - o0, oe = ti_rank(w, offset + node_size) - o0;
+        uint64_t pos = offset + i;
+        c <<= 1;
+        if ((w->tree[pos >> 6] >> (pos & 63)) & 1) {
+            offset += node_size - oe;
+            node_size = oe;
+            i = oi;
+            c |= 1;
+        } else {
+            node_size -= oe;
+            i -= oi;
+        }
+        offset += w->size;
+    }
+    *sym = c;
+    return i;
+}
+
+/* wt_int.hpp:456-507; returns size when c does not occur i times (the reference throws there) */
+uint64_t orc_wt_int_select(const orc_wt_int *w, uint64_t i, uint64_t c)
+{
+    uint64_t offset = 0, mask, node_size = w->size, path_off[65], path_rank_off[65];
+    uint32_t k;
+    if (w->size == 0 || (w->max_level < 64 && (1ULL << w->max_level) <= c))
+        return w->size;
+    mask = 1ULL << (w->max_level - 1);
+    path_off[0] = path_rank_off[0] = 0;
+    for (k = 0; k < w->max_level && node_size; ++k) {
+        uint64_t o0 = ti_rank(w, offset), oe = ti_rank(w, offset + node_size) - o0;
+        path_rank_off[k] = o0;
+        if (c & mask) {
+            offset += node_size - oe;
+            node_size = oe;
+        } else
+            node_size -= oe;
+        offset += w->size;
+        path_off[k + 1] = offset;
+        mask >>= 1;
+    }
+    if (node_size == 0 || node_size < i)
+        return w->size;
+    mask = 1;
+    for (k = w->max_level; k > 0; --k) {
+        uint64_t o0 = path_rank_off[k - 1];
+        offset = path_off[k - 1];
+        if (c & mask)
+            i = orc_select_mcl(w->sel1, w->tree, o0 + i) - offset + 1;
+        else
+            i = orc_select_mcl(w->sel0, w->tree, offset - o0 + i) - offset + 1;
+        mask <<= 1;
+    }
+    return i - 1;
+}
+
+void orc_wt_int_rank_batch(const orc_wt_int *w, const uint64_t *i, const uint64_t *c, uint64_t n, uint64_t *out)
+{
+    uint64_t k;
+    for (k = 0; k < n; ++k)
+        out[k] = orc_wt_int_rank(w, i[k], c[k]);
+}
+void orc_wt_int_select_batch(const orc_wt_int *w, const uint64_t *i, const uint64_t *c, uint64_t n, uint64_t *out)
+{
+    uint64_t k;
+    for (k = 0; k < n; ++k)
+        out[k] = orc_wt_int_select(w, i[k], c[k]);
+}
+void orc_wt_int_access_batch(const orc_wt_int *w, const uint64_t *i, uint64_t n, uint64_t *sym, uint64_t *rnk)
+{
+    uint64_t k, r;
+    for (k = 0; k < n; ++k) {
+        r = orc_wt_int_inverse_select(w, i[k], &sym[k]);
+        if (rnk)
+            rnk[k] = r;
+    }
+}
+
+/* wt_int.hpp:792-805 */
+uint64_t orc_wt_int_serialize(const orc_wt_int *w, uint8_t *out, uint64_t cap)
+{
+    orc_buf b = {0, 0, 0};
+    orc__buf_u64(&b, w->size);
+    orc__buf_u64(&b, w->sigma);
+    orc__bv_serialize_into(&b, w->tree, w->tree_bits);
+    orc__rank_v_serialize_into(&b, w->rank_table, w->tree_bits);
+    orc__select_mcl_serialize_into(&b, w->sel1);
+    orc__select_mcl_serialize_into(&b, w->sel0);
+    orc__buf_put(&b, &w->max_level, 4);
+    return orc__buf_finish(&b, out, cap);
+}

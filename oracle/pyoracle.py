@@ -134,8 +134,22 @@ class Oracle:
             f.restype = C.c_uint64
             f.argtypes = [C.c_void_p, u8p, C.c_uint64]
 
+        L.orc_wt_int_build.restype = C.c_void_p
+        L.orc_wt_int_build.argtypes = [u64p, C.c_uint64]
+        L.orc_wt_int_free.argtypes = [C.c_void_p]
+        for f in (L.orc_wt_int_rank_batch, L.orc_wt_int_select_batch):
+            f.restype = None
+            f.argtypes = [C.c_void_p, u64p, u64p, C.c_uint64, u64p]
+        L.orc_wt_int_access_batch.restype = None
+        L.orc_wt_int_access_batch.argtypes = [C.c_void_p, u64p, C.c_uint64, u64p, u64p]
+        L.orc_wt_int_serialize.restype = C.c_uint64
+        L.orc_wt_int_serialize.argtypes = [C.c_void_p, u8p, C.c_uint64]
+
     def csa(self, text):
         return OracleCsa(self, text)
+
+    def wt_int(self, seq):
+        return OracleWtInt(self, seq)
 
     def rrr(self, words, nbits):
         return OracleCompressed(self, "rrr", words, nbits)
@@ -236,6 +250,44 @@ class OracleWtHuff:
     def __del__(self):
         if getattr(self, "h", None):
             self.L.orc_wt_huff_free(self.h)
+            self.h = None
+
+
+class OracleWtInt:
+    def __init__(self, o, seq):
+        self.L = o.L
+        s = _u64(seq)
+        self.size = len(s)
+        self.h = self.L.orc_wt_int_build(_p64(s if len(s) else np.zeros(1, np.uint64)), len(s))
+
+    def rank(self, i, c):
+        i, c = _u64(i), _u64(c)
+        out = np.zeros(len(i), dtype=np.uint64)
+        self.L.orc_wt_int_rank_batch(self.h, _p64(i), _p64(c), len(i), _p64(out))
+        return out
+
+    def select(self, i, c):
+        i, c = _u64(i), _u64(c)
+        out = np.zeros(len(i), dtype=np.uint64)
+        self.L.orc_wt_int_select_batch(self.h, _p64(i), _p64(c), len(i), _p64(out))
+        return out
+
+    def inverse_select(self, i):
+        i = _u64(i)
+        sym = np.zeros(len(i), dtype=np.uint64)
+        rnk = np.zeros(len(i), dtype=np.uint64)
+        self.L.orc_wt_int_access_batch(self.h, _p64(i), len(i), _p64(sym), _p64(rnk))
+        return rnk, sym
+
+    def access(self, i):
+        return self.inverse_select(i)[1]
+
+    def serialize(self):
+        return _blob(self.L.orc_wt_int_serialize, self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_wt_int_free(self.h)
             self.h = None
 
 

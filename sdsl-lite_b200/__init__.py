@@ -383,3 +383,23 @@ class SdVector(_CompressedBitVector):
     """sd_vector<> + rank_support_sd + select_support_sd, built on the device"""
 
     _create = "sdslgpu_sd_create"
+
+
+_SIGNATURES += [
+    ("sdslgpu_wt_int_create", C.c_int, [vp, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(vp)]),
+]
+
+
+class WtInt(_Handle, _WaveletTreeOps):
+    """wt_int<> over a sequence of unsigned integers (host numpy uint64)"""
+
+    _sym_dtype = np.uint64
+
+    def __init__(self, seq, device=0, flags=F_DEFAULT):
+        super().__init__()
+        s = np.ascontiguousarray(seq, dtype=np.uint64)
+        _check(lib().sdslgpu_wt_int_create(s.ctypes.data if len(s) else None, len(s), device, flags, C.byref(self._h)))
+
+    rank = _WaveletTreeOps.wt_rank
+    select = _WaveletTreeOps.wt_select
+    access = _WaveletTreeOps.wt_access

@@ -477,6 +477,9 @@ extern "C"
         case SDSLGPU_KIND_CSA_WT:
             *size = h->csa.n;
             return SDSLGPU_OK;
+        case SDSLGPU_KIND_WT_INT:
+            *size = h->wti.size;
+            return SDSLGPU_OK;
         case SDSLGPU_KIND_RRR63:
             *size = h->rrr.size;
             return SDSLGPU_OK;
@@ -533,7 +536,8 @@ extern "C"
         case SDSLGPU_KIND_BV:
             return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
                 return bv_rank_device(h->bv, h->flags, b, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
-            });        case SDSLGPU_KIND_RRR63:
+            });
+        case SDSLGPU_KIND_RRR63:
             return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
                 return rrr_rank_device(h, b, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
             });
@@ -565,7 +569,8 @@ extern "C"
         case SDSLGPU_KIND_BV:
             return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
                 return bv_select_device(h->bv, b, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
-            });        case SDSLGPU_KIND_RRR63:
+            });
+        case SDSLGPU_KIND_RRR63:
             return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
                 return rrr_select_device(h, b, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
             });
@@ -592,7 +597,8 @@ extern "C"
         case SDSLGPU_KIND_BV:
             return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
                 return bv_access_device(h->bv, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
-            });        case SDSLGPU_KIND_RRR63:
+            });
+        case SDSLGPU_KIND_RRR63:
             return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
                 return rrr_access_device(h, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
             });
@@ -737,12 +743,34 @@ extern "C"
         return SDSLGPU_OK;
     }
 
+    int sdslgpu_wt_int_create(const uint64_t * seq, uint64_t n, int device, uint32_t flags, sdslgpu_handle ** out)
+    {
+        if (!out || (!seq && n))
+        {
+            set_error("sdslgpu_wt_int_create: null argument");
+            return SDSLGPU_EINVAL;
+        }
+        *out = nullptr;
+        sdslgpu_handle * h = nullptr;
+        SG_TRY(new_handle(SDSLGPU_KIND_WT_INT, device, flags, &h));
+        DeviceGuard g(device);
+        int st = wt_int_build(h, seq, n, nullptr);
+        if (st != SDSLGPU_OK)
+        {
+            h->pool.release_all();
+            delete h;
+            return st;
+        }
+        *out = h;
+        return SDSLGPU_OK;
+    }
+
     int sdslgpu_wt_sigma(const sdslgpu_handle * h, uint64_t * sigma)
     {
         SG_TRY(check_handle(h));
-        if (!sigma || !is_byte_wt(h))
+        if (!sigma || !(is_byte_wt(h) || h->kind == SDSLGPU_KIND_WT_INT))
             return SDSLGPU_EINVAL;
-        *sigma = h->wt.sigma;
+        *sigma = h->kind == SDSLGPU_KIND_WT_INT ? h->wti.sigma : h->wt.sigma;
         return SDSLGPU_OK;
     }
 
@@ -760,6 +788,14 @@ extern "C"
             Column o{nullptr, out, 8};
             return run_batch(h, in, 2, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
                 return wt_rank_device(h, static_cast<uint64_t const *>(ip[0]), static_cast<uint8_t const *>(ip[1]), cnt, static_cast<uint64_t *>(op[0]), s);
+            });
+        }
+        if (h->kind == SDSLGPU_KIND_WT_INT)
+        {
+            Column in[2] = {{i, nullptr, 8}, {c, nullptr, 8}};
+            Column o{nullptr, out, 8};
+            return run_batch(h, in, 2, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
+                return wt_int_rank_device(h, static_cast<uint64_t const *>(ip[0]), static_cast<uint64_t const *>(ip[1]), cnt, static_cast<uint64_t *>(op[0]), s);
             });
         }
         set_error("sdslgpu_wt_rank: unsupported handle kind %d", h->kind);
@@ -782,6 +818,14 @@ extern "C"
                 return wt_select_device(h, static_cast<uint64_t const *>(ip[0]), static_cast<uint8_t const *>(ip[1]), cnt, static_cast<uint64_t *>(op[0]), s);
             });
         }
+        if (h->kind == SDSLGPU_KIND_WT_INT)
+        {
+            Column in[2] = {{i, nullptr, 8}, {c, nullptr, 8}};
+            Column o{nullptr, out, 8};
+            return run_batch(h, in, 2, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
+                return wt_int_select_device(h, static_cast<uint64_t const *>(ip[0]), static_cast<uint64_t const *>(ip[1]), cnt, static_cast<uint64_t *>(op[0]), s);
+            });
+        }
         set_error("sdslgpu_wt_select: unsupported handle kind %d", h->kind);
         return SDSLGPU_ENOTSUP;
     }
@@ -800,6 +844,14 @@ extern "C"
             Column o[2] = {{nullptr, sym_out, 8}, {nullptr, rank_out, 8}};
             return run_batch(h, &in, 1, o, 2, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
                 return wt_access_device(h, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), static_cast<uint64_t *>(op[1]), s);
+            });
+        }
+        if (h->kind == SDSLGPU_KIND_WT_INT)
+        {
+            Column in{i, nullptr, 8};
+            Column o[2] = {{nullptr, sym_out, 8}, {nullptr, rank_out, 8}};
+            return run_batch(h, &in, 1, o, 2, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
+                return wt_int_access_device(h, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), static_cast<uint64_t *>(op[1]), s);
             });
         }
         set_error("sdslgpu_wt_access: unsupported handle kind %d", h->kind);

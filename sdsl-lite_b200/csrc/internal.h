@@ -162,6 +162,14 @@ struct WtHuffImage
     WtTree host_tree;          // host copy (kept for serialisation / introspection)
 };
 
+// wt_int<> (wt_int.hpp:85-91): max_level levels of `size` bits each, concatenated
+struct WtIntImage
+{
+    uint64_t size = 0, sigma = 0;
+    uint32_t max_level = 0;
+    BvImage tree;
+};
+
 // byte_alphabet of a CSA (csa_alphabet_strategy.hpp:136-212), staged in shared memory next to the tree
 struct alignas(16) FmTables
 {
@@ -213,6 +221,7 @@ struct sdslgpu_handle
     sdslgpu::BvImage bv;        // KIND_BV
     sdslgpu::WtHuffImage wt;    // KIND_WT_HUFF (and the BWT of KIND_CSA_WT)
     sdslgpu::CsaImage csa;      // KIND_CSA_WT
+    sdslgpu::WtIntImage wti;    // KIND_WT_INT
     sdslgpu::RrrImage rrr;      // KIND_RRR63
     sdslgpu::SdImage sd;        // KIND_SD
 };
@@ -231,6 +240,11 @@ int wt_huff_build_from_text(sdslgpu_handle * h, uint8_t const * text_host, uint6
 int wt_rank_device(sdslgpu_handle const * h, uint64_t const * i, uint8_t const * c, uint64_t n, uint64_t * out, cudaStream_t s);
 int wt_select_device(sdslgpu_handle const * h, uint64_t const * i, uint8_t const * c, uint64_t n, uint64_t * out, cudaStream_t s);
 int wt_access_device(sdslgpu_handle const * h, uint64_t const * i, uint64_t n, uint64_t * sym, uint64_t * rnk, cudaStream_t s);
+// wt_int.cu
+int wt_int_build(sdslgpu_handle * h, uint64_t const * seq_host, uint64_t n, cudaStream_t s);
+int wt_int_rank_device(sdslgpu_handle const * h, uint64_t const * i, uint64_t const * c, uint64_t n, uint64_t * out, cudaStream_t s);
+int wt_int_select_device(sdslgpu_handle const * h, uint64_t const * i, uint64_t const * c, uint64_t n, uint64_t * out, cudaStream_t s);
+int wt_int_access_device(sdslgpu_handle const * h, uint64_t const * i, uint64_t n, uint64_t * sym, uint64_t * rnk, cudaStream_t s);
 // rrr.cu
 int rrr_build(sdslgpu_handle * h, uint64_t const * words_host_or_dev, bool on_device, uint64_t nbits, cudaStream_t s);
 int rrr_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
