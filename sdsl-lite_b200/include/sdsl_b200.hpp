@@ -1,0 +1,520 @@
+// sdsl_b200.hpp — SDSL-shaped C++ classes over the C ABI (include/sdslgpu.h).
+//
+// Header-only host-side mirror of the reference's interface for the hot path: the same
+// names, argument meaning and in-band results as xxsds/sdsl-lite, so that a call site written against
+//     sdsl::bit_vector / rank_support_v<b> / select_support_mcl<b> / rrr_vector<63> / sd_vector<> /
+//     wt_huff<> / wt_int<> / csa_wt<wt_huff<>> / sdsl::count / sdsl::locate
+// compiles against namespace sdsl_b200 unchanged, and gains batch overloads (pointer + count, or
+// std::vector) that are the fast path: one call = one kernel launch over the whole batch.
+// Scalar calls (rank(i), wt.rank(i,c), count(csa, b, e)) are batches of one and cost a launch each: they
+// exist for drop-in compatibility and tests, not for speed.
+//
+// Ownership mirrors the reference: supports hold a NON-OWNING pointer to their vector and are re-pointed
+// with set_vector (rank_support.hpp:33, util.hpp:414-432).  Errors from the C ABI become std::runtime_error
+// (the reference throws std::logic_error / std::runtime_error from constructors too).
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/sdslgpu.h"
+
+namespace sdsl_b200
+{
+
+typedef uint64_t size_type;
+
+inline void check(int status, char const * what)
+{
+    if (status != SDSLGPU_OK)
+        throw std::runtime_error(std::string(what) + ": " + sdslgpu_last_error());
+}
+
+namespace detail
+{
+struct handle_deleter
+{
+    void operator()(sdslgpu_handle * h) const
+    {
+        sdslgpu_free(h);
+    }
+};
+typedef std::shared_ptr<sdslgpu_handle> handle_ptr;
+inline handle_ptr adopt(sdslgpu_handle * h)
+{
+    return handle_ptr(h, handle_deleter());
+}
+inline int & default_device()
+{
+    static int d = 0;
+    return d;
+}
+} // namespace detail
+
+//! Device used by constructors that do not name one (there is no CPU fallback).
+inline void set_device(int d)
+{
+    detail::default_device() = d;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// bit_vector = int_vector<1> (int_vector.hpp:210-257): host words + a lazily built device image that
+// carries rank_support_v<0/1> and select_support_mcl<0/1>.
+// ------------------------------------------------------------------------------------------------------
+class bit_vector
+{
+public:
+    typedef sdsl_b200::size_type size_type;
+    bit_vector() = default;
+    explicit bit_vector(size_type n, bool value = false) : m_size(n), m_words((n + 63) / 64 + 1, value ? ~0ull : 0ull)
+    {
+        trim();
+    }
+    bit_vector(uint64_t const * words, size_type n) : m_size(n), m_words(words, words + (n + 63) / 64)
+    {
+        m_words.push_back(0);
+    }
+    size_type size() const
+    {
+        return m_size;
+    }
+    size_type bit_size() const
+    {
+        return m_size;
+    }
+    bool empty() const
+    {
+        return m_size == 0;
+    }
+    uint64_t const * data() const
+    {
+        return m_words.data();
+    }
+    uint64_t * data()
+    {
+        m_image.reset(); // the caller may write: the device image is rebuilt on next use
+        return m_words.data();
+    }
+    bool operator[](size_type i) const // int_vector.hpp:1900-1904
+    {
+        return (m_words[i >> 6] >> (i & 63)) & 1;
+    }
+    void set(size_type i, bool v)
+    {
+        m_image.reset();
+        if (v)
+            m_words[i >> 6] |= 1ull << (i & 63);
+        else
+            m_words[i >> 6] &= ~(1ull << (i & 63));
+    }
+    //! the device image (built on first use)
+    sdslgpu_handle const * image() const
+    {
+        if (!m_image)
+        {
+            sdslgpu_handle * h = nullptr;
+            check(sdslgpu_bv_create(m_words.data(), m_size, detail::default_device(), SDSLGPU_F_DEFAULT, &h), "bit_vector");
+            m_image = detail::adopt(h);
+        }
+        return m_image.get();
+    }
+
+private:
+    void trim()
+    {
+        if (m_size & 63)
+            m_words[m_size >> 6] &= (1ull << (m_size & 63)) - 1;
+        m_words.back() = 0;
+        if ((m_size & 63) == 0 && !m_words.empty())
+            m_words[(m_size + 63) / 64] = 0;
+    }
+    size_type m_size = 0;
+    std::vector<uint64_t> m_words;
+    mutable detail::handle_ptr m_image;
+};
+
+namespace detail
+{
+// shared implementation of the rank / select support concept (rank_support.hpp:30-75, select_support.hpp:32-78)
+template <class t_vec>
+class support_base
+{
+public:
+    typedef sdsl_b200::size_type size_type;
+    typedef t_vec bit_vector_type;
+    explicit support_base(t_vec const * v = nullptr) : m_v(v)
+    {}
+    void set_vector(t_vec const * v = nullptr)
+    {
+        m_v = v;
+    }
+    size_type size() const
+    {
+        return m_v ? m_v->size() : 0;
+    }
+
+protected:
+    sdslgpu_handle const * image() const
+    {
+        if (!m_v)
+            throw std::runtime_error("support used without a vector (set_vector)");
+        return m_v->image();
+    }
+    t_vec const * m_v;
+};
+} // namespace detail
+
+//! rank_support_v<t_b,1> concept (rank_support_v.hpp:47-192) for any bit-vector type of this header.
+template <uint8_t t_b, class t_vec>
+class rank_support : public detail::support_base<t_vec>
+{
+    using base = detail::support_base<t_vec>;
+
+public:
+    using typename base::size_type;
+    enum
+    {
+        bit_pat = t_b,
+        bit_pat_len = 1
+    };
+    using base::base;
+    size_type rank(size_type i) const
+    {
+        size_type r;
+        rank(&i, 1, &r);
+        return r;
+    }
+    size_type operator()(size_type i) const
+    {
+        return rank(i);
+    }
+    //! batch: out[k] = rank(idx[k]); pointers may be host or device memory
+    void rank(uint64_t const * idx, size_type n, uint64_t * out, void * stream = nullptr) const
+    {
+        check(sdslgpu_rank(this->image(), t_b, idx, n, out, stream), "rank");
+    }
+    std::vector<uint64_t> rank(std::vector<uint64_t> const & idx) const
+    {
+        std::vector<uint64_t> out(idx.size());
+        rank(idx.data(), idx.size(), out.data());
+        return out;
+    }
+};
+
+template <uint8_t t_b, class t_vec>
+class select_support : public detail::support_base<t_vec>
+{
+    using base = detail::support_base<t_vec>;
+
+public:
+    using typename base::size_type;
+    enum
+    {
+        bit_pat = t_b,
+        bit_pat_len = 1
+    };
+    using base::base;
+    size_type select(size_type i) const
+    {
+        size_type r;
+        select(&i, 1, &r);
+        return r;
+    }
+    size_type operator()(size_type i) const
+    {
+        return select(i);
+    }
+    void select(uint64_t const * i, size_type n, uint64_t * out, void * stream = nullptr) const
+    {
+        check(sdslgpu_select(this->image(), t_b, i, n, out, stream), "select");
+    }
+    std::vector<uint64_t> select(std::vector<uint64_t> const & i) const
+    {
+        std::vector<uint64_t> out(i.size());
+        select(i.data(), i.size(), out.data());
+        return out;
+    }
+};
+
+template <uint8_t t_b = 1, uint8_t t_pat_len = 1>
+using rank_support_v = rank_support<t_b, bit_vector>;
+template <uint8_t t_b = 1, uint8_t t_pat_len = 1>
+using select_support_mcl = select_support<t_b, bit_vector>;
+
+// ------------------------------------------------------------------------------------------------------
+// compressed bit vectors (rrr_vector.hpp:67-109, sd_vector.hpp:131-163)
+// ------------------------------------------------------------------------------------------------------
+namespace detail
+{
+template <int KIND>
+class compressed_vector
+{
+public:
+    typedef sdsl_b200::size_type size_type;
+    typedef rank_support<1, compressed_vector> rank_1_type;
+    typedef rank_support<0, compressed_vector> rank_0_type;
+    typedef select_support<1, compressed_vector> select_1_type;
+    typedef select_support<0, compressed_vector> select_0_type;
+    compressed_vector() = default;
+    explicit compressed_vector(bit_vector const & bv) : m_size(bv.size())
+    {
+        sdslgpu_handle * h = nullptr;
+        if (KIND == SDSLGPU_KIND_RRR63)
+            check(sdslgpu_rrr63_create(bv.data(), bv.size(), default_device(), SDSLGPU_F_DEFAULT, &h), "rrr_vector");
+        else
+            check(sdslgpu_sd_create(bv.data(), bv.size(), default_device(), SDSLGPU_F_DEFAULT, &h), "sd_vector");
+        m_image = adopt(h);
+    }
+    size_type size() const
+    {
+        return m_size;
+    }
+    bool operator[](size_type i) const
+    {
+        uint64_t r;
+        check(sdslgpu_access(image(), &i, 1, &r, nullptr), "operator[]");
+        return r != 0;
+    }
+    sdslgpu_handle const * image() const
+    {
+        if (!m_image)
+            throw std::runtime_error("empty compressed vector");
+        return m_image.get();
+    }
+
+private:
+    size_type m_size = 0;
+    handle_ptr m_image;
+};
+} // namespace detail
+
+template <uint16_t t_bs = 63>
+using rrr_vector = detail::compressed_vector<SDSLGPU_KIND_RRR63>; // only t_bs = 63 is on the hot path
+template <int dummy = 0>
+using sd_vector = detail::compressed_vector<SDSLGPU_KIND_SD>;
+
+// ------------------------------------------------------------------------------------------------------
+// wavelet trees (wt_pc.hpp:61-78, 314-474; wt_int.hpp:57-61, 340-507)
+// ------------------------------------------------------------------------------------------------------
+namespace detail
+{
+template <class t_sym>
+class wavelet_tree_base
+{
+public:
+    typedef sdsl_b200::size_type size_type;
+    typedef t_sym value_type;
+    size_type size() const
+    {
+        return m_size;
+    }
+    bool empty() const
+    {
+        return m_size == 0;
+    }
+    size_type sigma = 0;
+    value_type operator[](size_type i) const
+    {
+        uint64_t s;
+        check(sdslgpu_wt_access(image(), &i, 1, &s, nullptr, nullptr), "wt[i]");
+        return (value_type)s;
+    }
+    size_type rank(size_type i, value_type c) const
+    {
+        size_type r;
+        rank(&i, &c, 1, &r);
+        return r;
+    }
+    size_type select(size_type i, value_type c) const
+    {
+        size_type r;
+        select(&i, &c, 1, &r);
+        return r;
+    }
+    std::pair<size_type, value_type> inverse_select(size_type i) const
+    {
+        uint64_t s, r;
+        check(sdslgpu_wt_access(image(), &i, 1, &s, &r, nullptr), "inverse_select");
+        return std::make_pair((size_type)r, (value_type)s);
+    }
+    // batch forms
+    void rank(uint64_t const * i, value_type const * c, size_type n, uint64_t * out, void * stream = nullptr) const
+    {
+        check(sdslgpu_wt_rank(image(), i, c, n, out, stream), "wt.rank");
+    }
+    void select(uint64_t const * i, value_type const * c, size_type n, uint64_t * out, void * stream = nullptr) const
+    {
+        check(sdslgpu_wt_select(image(), i, c, n, out, stream), "wt.select");
+    }
+    void access(uint64_t const * i, size_type n, uint64_t * sym_out, uint64_t * rank_out = nullptr, void * stream = nullptr) const
+    {
+        check(sdslgpu_wt_access(image(), i, n, sym_out, rank_out, stream), "wt.access");
+    }
+    sdslgpu_handle const * image() const
+    {
+        if (!m_image)
+            throw std::runtime_error("empty wavelet tree");
+        return m_image.get();
+    }
+
+protected:
+    void adopt_image(sdslgpu_handle * h)
+    {
+        m_image = adopt(h);
+        check(sdslgpu_size(h, &m_size), "size");
+        uint64_t s = 0;
+        check(sdslgpu_wt_sigma(h, &s), "sigma");
+        sigma = s;
+    }
+    size_type m_size = 0;
+    handle_ptr m_image;
+};
+} // namespace detail
+
+class wt_huff : public detail::wavelet_tree_base<uint8_t>
+{
+public:
+    wt_huff() = default;
+    //! wt_pc(t_it begin, t_it end) (wt_pc.hpp:194): any contiguous range of bytes
+    wt_huff(uint8_t const * begin, uint8_t const * end)
+    {
+        sdslgpu_handle * h = nullptr;
+        check(sdslgpu_wt_huff_create(begin, (uint64_t)(end - begin), detail::default_device(), SDSLGPU_F_DEFAULT, &h), "wt_huff");
+        adopt_image(h);
+    }
+    explicit wt_huff(std::string const & text) : wt_huff(reinterpret_cast<uint8_t const *>(text.data()), reinterpret_cast<uint8_t const *>(text.data()) + text.size())
+    {}
+};
+
+class wt_int : public detail::wavelet_tree_base<uint64_t>
+{
+public:
+    wt_int() = default;
+    wt_int(uint64_t const * begin, uint64_t const * end)
+    {
+        sdslgpu_handle * h = nullptr;
+        check(sdslgpu_wt_int_create(begin, (uint64_t)(end - begin), detail::default_device(), SDSLGPU_F_DEFAULT, &h), "wt_int");
+        adopt_image(h);
+    }
+    explicit wt_int(std::vector<uint64_t> const & seq) : wt_int(seq.data(), seq.data() + seq.size())
+    {}
+};
+
+// ------------------------------------------------------------------------------------------------------
+// csa_wt<wt_huff<>> and the search algorithms (csa_wt.hpp:49-130; suffix_array_algorithm.hpp:166-248,463-570)
+// ------------------------------------------------------------------------------------------------------
+class csa_wt
+{
+public:
+    typedef sdsl_b200::size_type size_type;
+    typedef uint8_t char_type;
+    typedef std::string string_type;
+    csa_wt() = default;
+    //! construct(csa, text, 1) / construct_im(csa, text, 1): the text must not contain a 0 byte (construct.hpp:34-46)
+    explicit csa_wt(std::string const & text)
+    {
+        sdslgpu_handle * h = nullptr;
+        check(sdslgpu_csa_create(reinterpret_cast<uint8_t const *>(text.data()), text.size(), detail::default_device(), SDSLGPU_F_DEFAULT, &h), "csa_wt");
+        m_image = detail::adopt(h);
+        check(sdslgpu_size(h, &m_size), "size");
+    }
+    size_type size() const
+    {
+        return m_size;
+    }
+    //! csa[i]: the i-th suffix array entry (csa_wt.hpp:363-381)
+    size_type operator[](size_type i) const
+    {
+        uint64_t r;
+        check(sdslgpu_fm_sa(image(), &i, 1, &r, nullptr), "csa[i]");
+        return r;
+    }
+    //! csa.bwt.rank(i, c) (suffix_array_helper.hpp:461-464)
+    size_type rank_bwt(size_type i, char_type c) const
+    {
+        uint64_t r;
+        check(sdslgpu_wt_rank(image(), &i, &c, 1, &r, nullptr), "rank_bwt");
+        return r;
+    }
+    sdslgpu_handle const * image() const
+    {
+        if (!m_image)
+            throw std::runtime_error("empty csa");
+        return m_image.get();
+    }
+
+private:
+    size_type m_size = 0;
+    detail::handle_ptr m_image;
+};
+
+//! sdsl::count(csa, begin, end) (suffix_array_algorithm.hpp:463-471)
+template <class t_pat_iter>
+size_type count(csa_wt const & csa, t_pat_iter begin, t_pat_iter end)
+{
+    std::string p(begin, end);
+    uint64_t off[2] = {0, p.size()}, cnt = 0;
+    check(sdslgpu_fm_count(csa.image(), reinterpret_cast<uint8_t const *>(p.data()), off, 1, &cnt, nullptr, nullptr), "count");
+    return cnt;
+}
+inline size_type count(csa_wt const & csa, std::string const & pat)
+{
+    return count(csa, pat.begin(), pat.end());
+}
+
+//! sdsl::locate(csa, begin, end): all occurrences, in suffix-array order (suffix_array_algorithm.hpp:534-550)
+template <class t_pat_iter>
+std::vector<uint64_t> locate(csa_wt const & csa, t_pat_iter begin, t_pat_iter end)
+{
+    std::string p(begin, end);
+    uint64_t off[2] = {0, p.size()}, occ_off[2], total = 0;
+    uint8_t const * bytes = reinterpret_cast<uint8_t const *>(p.data());
+    check(sdslgpu_fm_locate(csa.image(), bytes, off, 1, occ_off, nullptr, 0, &total, nullptr), "locate");
+    std::vector<uint64_t> occ(total);
+    if (total)
+        check(sdslgpu_fm_locate(csa.image(), bytes, off, 1, occ_off, occ.data(), total, &total, nullptr), "locate");
+    return occ;
+}
+inline std::vector<uint64_t> locate(csa_wt const & csa, std::string const & pat)
+{
+    return locate(csa, pat.begin(), pat.end());
+}
+
+//! batch count: one launch for the whole pattern set
+inline std::vector<uint64_t> count(csa_wt const & csa, std::vector<std::string> const & pats)
+{
+    std::string flat;
+    std::vector<uint64_t> off(pats.size() + 1, 0), cnt(pats.size());
+    for (size_t k = 0; k < pats.size(); ++k)
+    {
+        flat += pats[k];
+        off[k + 1] = flat.size();
+    }
+    if (!pats.empty())
+        check(sdslgpu_fm_count(csa.image(), reinterpret_cast<uint8_t const *>(flat.data()), off.data(), pats.size(), cnt.data(), nullptr, nullptr), "count");
+    return cnt;
+}
+
+//! batch locate: occurrences of pattern k are occ[occ_off[k] .. occ_off[k+1]) in suffix-array order
+inline void locate(csa_wt const & csa, std::vector<std::string> const & pats, std::vector<uint64_t> & occ_off, std::vector<uint64_t> & occ)
+{
+    std::string flat;
+    std::vector<uint64_t> off(pats.size() + 1, 0);
+    for (size_t k = 0; k < pats.size(); ++k)
+    {
+        flat += pats[k];
+        off[k + 1] = flat.size();
+    }
+    occ_off.assign(pats.size() + 1, 0);
+    uint64_t total = 0;
+    uint8_t const * bytes = reinterpret_cast<uint8_t const *>(flat.data());
+    check(sdslgpu_fm_locate(csa.image(), bytes, off.data(), pats.size(), occ_off.data(), nullptr, 0, &total, nullptr), "locate");
+    occ.assign(total, 0);
+    if (total)
+        check(sdslgpu_fm_locate(csa.image(), bytes, off.data(), pats.size(), occ_off.data(), occ.data(), total, &total, nullptr), "locate");
+}
+
+} // namespace sdsl_b200

@@ -1,0 +1,138 @@
+// tests/cpp/shim_test.cpp — the SDSL-shaped C++ classes (sdsl-lite_b200/include/sdsl_b200.hpp) exercised the way
+// the reference's own typed tests exercise sdsl:: (test/rank_support_test.cpp:109-126, select_support_test.cpp:85-104,
+// wt_byte_test.cpp:134-203, csa_byte_test.cpp:84-110): every result is compared with a naive scan.
+// Built by tests/test_cpp_shim.py:  g++ -std=c++17 shim_test.cpp -L<pkg> -lsdslgpu ; needs a GPU to run.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <string>
+
+#include "../../sdsl-lite_b200/include/sdsl_b200.hpp"
+
+using namespace sdsl_b200;
+
+#define EXPECT(cond)                                                                                                   \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if (!(cond))                                                                                                   \
+        {                                                                                                              \
+            std::printf("FAILED %s:%d  %s\n", __FILE__, __LINE__, #cond);                                             \
+            std::exit(1);                                                                                              \
+        }                                                                                                              \
+    } while (0)
+
+template <class t_vec, class t_rank1, class t_rank0, class t_sel1, class t_sel0>
+void check_bitvector(bit_vector const & plain, t_vec const & v)
+{
+    t_rank1 r1(&v);
+    t_rank0 r0(&v);
+    t_sel1 s1(&v);
+    t_sel0 s0(&v);
+    std::vector<uint64_t> idx(plain.size() + 1);
+    for (uint64_t j = 0; j <= plain.size(); ++j)
+        idx[j] = j;
+    auto got1 = r1.rank(idx), got0 = r0.rank(idx); // batch overloads
+    uint64_t ones = 0;
+    std::vector<uint64_t> pos1, pos0;
+    for (uint64_t j = 0; j < plain.size(); ++j)
+    {
+        EXPECT(got1[j] == ones && got0[j] == j - ones);
+        (plain[j] ? pos1 : pos0).push_back(j);
+        ones += plain[j];
+    }
+    EXPECT(got1[plain.size()] == ones);
+    EXPECT(r1.rank(plain.size() / 2) == got1[plain.size() / 2] && r1(plain.size()) == ones); // scalar drop-in calls
+    std::vector<uint64_t> k1(pos1.size()), k0(pos0.size());
+    for (size_t k = 0; k < k1.size(); ++k)
+        k1[k] = k + 1;
+    for (size_t k = 0; k < k0.size(); ++k)
+        k0[k] = k + 1;
+    EXPECT(s1.select(k1) == pos1);
+    EXPECT(s0.select(k0) == pos0);
+    if (!pos1.empty())
+        EXPECT(s1.select(1) == pos1[0] && s1(pos1.size()) == pos1.back());
+}
+
+int main(int argc, char ** argv)
+{
+    if (argc > 1)
+        set_device(std::atoi(argv[1]));
+    std::mt19937_64 rng(4711);
+    // ---- bit vectors
+    for (uint64_t n : {1ull, 63ull, 64ull, 1000ull, 100000ull})
+        for (double d : {0.5, 0.03})
+        {
+            bit_vector bv(n);
+            for (uint64_t j = 0; j < n; ++j)
+                if ((rng() % 10000) < d * 10000)
+                    bv.set(j, true);
+            check_bitvector<bit_vector, rank_support_v<1>, rank_support_v<0>, select_support_mcl<1>, select_support_mcl<0>>(bv, bv);
+            rrr_vector<63> rrr(bv);
+            check_bitvector<rrr_vector<63>, rrr_vector<63>::rank_1_type, rrr_vector<63>::rank_0_type, rrr_vector<63>::select_1_type,
+                            rrr_vector<63>::select_0_type>(bv, rrr);
+            sd_vector<> sd(bv);
+            check_bitvector<sd_vector<>, sd_vector<>::rank_1_type, sd_vector<>::rank_0_type, sd_vector<>::select_1_type,
+                            sd_vector<>::select_0_type>(bv, sd);
+            EXPECT(rrr[n / 2] == bv[n / 2] && sd[n / 2] == bv[n / 2]);
+        }
+    // ---- wt_huff
+    std::string text;
+    for (int j = 0; j < 20000; ++j)
+        text += (char)("abracadabra_$%&XYZ"[rng() % 18]);
+    wt_huff wt(text);
+    EXPECT(wt.size() == text.size() && wt.sigma == 14);
+    {
+        std::vector<uint64_t> cnt(256, 0);
+        for (uint64_t j = 0; j < text.size(); ++j)
+        {
+            uint8_t c = (uint8_t)text[j];
+            if (j % 37 == 0)
+            {
+                EXPECT(wt.rank(j, c) == cnt[c]);                       // wt_byte_test.cpp:134-168
+                EXPECT(wt[j] == c);                                    // :106-131
+                auto rc = wt.inverse_select(j);                        // :187-203
+                EXPECT(rc.first == cnt[c] && rc.second == c);
+                EXPECT(wt.select(cnt[c] + 1, c) == j);                 // :171-184
+            }
+            ++cnt[c];
+        }
+        EXPECT(wt.rank(text.size(), 'q') == 0 && wt.select(1, 'q') == text.size()); // absent symbol
+    }
+    // ---- wt_int
+    std::vector<uint64_t> seq(5000);
+    for (auto & x : seq)
+        x = rng() % 1000;
+    wt_int wi(seq);
+    EXPECT(wi.size() == seq.size());
+    for (uint64_t j = 0; j < seq.size(); j += 97)
+    {
+        uint64_t c = seq[j], r = std::count(seq.begin(), seq.begin() + j, c);
+        EXPECT(wi.rank(j, c) == r && wi[j] == c && wi.select(r + 1, c) == j);
+    }
+    // ---- csa_wt + count / locate (examples/fm-index.cpp:64-69)
+    std::string t2 = "abracadabra abracadabra simsalabim abracadabra";
+    csa_wt csa(t2);
+    EXPECT(csa.size() == t2.size() + 1);
+    EXPECT(count(csa, std::string("abra")) == 6);
+    EXPECT(count(csa, std::string("")) == t2.size() + 1 && count(csa, std::string("xyz")) == 0);
+    auto occ = locate(csa, std::string("abracadabra"));
+    std::sort(occ.begin(), occ.end());
+    EXPECT((occ == std::vector<uint64_t>{0, 12, 35}));
+    std::vector<uint64_t> sa(t2.size() + 1);
+    for (uint64_t j = 0; j <= t2.size(); ++j)
+        sa[j] = csa[j];
+    std::vector<uint64_t> sorted(sa);
+    std::sort(sorted.begin(), sorted.end());
+    for (uint64_t j = 0; j <= t2.size(); ++j)
+        EXPECT(sorted[j] == j); // SA is a permutation
+    for (uint64_t j = 1; j <= t2.size(); ++j)
+        EXPECT(t2.compare(sa[j - 1], std::string::npos, t2, sa[j], std::string::npos) < 0); // and sorted (csa_byte_test.cpp:162-175)
+    auto cnts = count(csa, std::vector<std::string>{"a", "abra", "sim", "zzz"});
+    EXPECT((cnts == std::vector<uint64_t>{(uint64_t)std::count(t2.begin(), t2.end(), 'a'), 6, 1, 0}));
+    std::vector<uint64_t> occ_off, occs;
+    locate(csa, std::vector<std::string>{"sim", "cad"}, occ_off, occs);
+    EXPECT(occ_off.size() == 3 && occ_off[2] == 4 && occs[0] == 24);
+    std::printf("shim_test ok\n");
+    return 0;
+}
