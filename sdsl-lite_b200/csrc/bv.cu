@@ -8,6 +8,8 @@
 //   bit_vector::operator[]     int_vector.hpp:1900-1904      -> bv_access_kernel
 // plus, under SDSLGPU_F_SDSL_LAYOUT, the reference's own table (m_basic_block) built on the device,
 // byte-identical to the reference's, and a rank kernel that reads it exactly as the reference does.
+#include <cstdlib>
+
 #include "internal.h"
 #include "bv_device.cuh"
 #include "scan.cuh"
@@ -301,11 +303,17 @@ int bv_build(DevicePool & pool, BvImage & v, uint32_t flags, uint64_t const * wo
         for (int b = 0; b < 2; ++b)
         {
             uint64_t m = b ? v.ones : nbits - v.ones;
-            // sample stride S = 2^log_s: the largest power of two <= 64 with S <= 128 * density, so the
-            // expected distance between samples stays around 128 bits whatever the density
+            // sample stride S = 2^log_s.  Small vectors: the largest power of two <= 64 with S <= 128 * density
+            // (samples ~128 bits apart, the hinted block is almost always the right one).  Large vectors: S grows
+            // (up to 4096) until the u32 sample table is <= 32 MB, so the table stays resident in the 126 MB L2 and
+            // a query pays ONE DRAM line (the sector block found by interpolating between two samples) instead of two.
             uint32_t ls = 6;
             while (ls > 0 && ((1ull << ls) * nbits > 128ull * m * 1ull) && m > 0)
                 --ls;
+            while (ls < 12 && 4ull * (m >> ls) > (32ull << 20))
+                ++ls;
+            if (char const * e = std::getenv("SDSLGPU_SELECT_LOG_S")) // tuning knob for experiments
+                ls = (uint32_t)std::atoi(e) > 16 ? 16u : (uint32_t)std::atoi(e);
             v.log_s[b] = ls;
             v.nsamp[b] = m ? ((m - 1) >> ls) + 1 : 0;
             SG_TRY(pool.alloc_t(&v.samp[b], v.nsamp[b] + 2));

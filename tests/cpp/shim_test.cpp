@@ -81,7 +81,11 @@ int main(int argc, char ** argv)
     for (int j = 0; j < 20000; ++j)
         text += (char)("abracadabra_$%&XYZ"[rng() % 18]);
     wt_huff wt(text);
-    EXPECT(wt.size() == text.size() && wt.sigma == 14);
+    {
+        std::string u(text);
+        std::sort(u.begin(), u.end());
+        EXPECT(wt.size() == text.size() && wt.sigma == (uint64_t)(std::unique(u.begin(), u.end()) - u.begin()));
+    }
     {
         std::vector<uint64_t> cnt(256, 0);
         for (uint64_t j = 0; j < text.size(); ++j)
