@@ -172,6 +172,18 @@ int sdslgpu_fm_locate(const sdslgpu_handle *h, const uint8_t *pats, const uint64
  * to rank_support_v::serialize (rank_support_v.hpp:151-158). */
 int sdslgpu_bv_serialize(const sdslgpu_handle *h, int what, void *buf, uint64_t cap, uint64_t *nbytes);
 
+/* Ingest of the reference's own serialised bytes (store_to_file / serialize(), io.hpp:877-896) for
+ * kind = SDSLGPU_KIND_BV        bit_vector                          (int_vector.hpp:1995-2004)
+ *        SDSLGPU_KIND_RRR63     rrr_vector<63>                      (rrr_vector.hpp:366-378; taken as is, no re-encoding)
+ *        SDSLGPU_KIND_SD        sd_vector<>                         (sd_vector.hpp:426-438)
+ *        SDSLGPU_KIND_WT_HUFF   wt_huff<>                           (wt_pc.hpp:713-726, wt_helper.hpp:362-375)
+ *        SDSLGPU_KIND_WT_INT    wt_int<>                            (wt_int.hpp:792-805)
+ *        SDSLGPU_KIND_CSA_WT    csa_wt<wt_huff<>, t_dens, ...>      (csa_wt.hpp:389-402); param = t_dens (0 -> 32)
+ * The rank/select supports stored inside a blob are skipped; this engine builds its own on the device.
+ * `blob` is a HOST buffer.  A truncated or inconsistent blob gives SDSLGPU_EINVAL. */
+int sdslgpu_load_sdsl(const void *blob, uint64_t nbytes, int kind, int device, uint32_t flags, uint32_t param,
+                      sdslgpu_handle **out);
+
 /* Same protocol for the other kinds (what = 0):
  *   KIND_BV     -> as sdslgpu_bv_serialize (what 0..2)
  *   KIND_RRR63  -> the complete rrr_vector<63>::serialize bytes (rrr_vector.hpp:366-378)

@@ -390,6 +390,23 @@ _SIGNATURES += [
 ]
 
 
+_SIGNATURES += [
+    ("sdslgpu_load_sdsl", C.c_int, [vp, C.c_uint64, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
+]
+
+
+def load_sdsl(blob, kind, device=0, flags=F_DEFAULT, param=0):
+    """Ingest bytes written by the reference's serialize()/store_to_file -> a handle object of the right class."""
+    cls = {KIND_BV: BitVector, KIND_RRR63: RrrVector, KIND_SD: SdVector, KIND_WT_HUFF: WtHuff, KIND_WT_INT: WtInt, KIND_CSA_WT: CsaWt}[kind]
+    obj = cls.__new__(cls)
+    _Handle.__init__(obj)
+    buf = np.frombuffer(blob, dtype=np.uint8)
+    _check(lib().sdslgpu_load_sdsl(buf.ctypes.data, len(buf), kind, device, flags, param, C.byref(obj._h)))
+    obj.flags = flags
+    obj.nbits = obj.size
+    return obj
+
+
 class WtInt(_Handle, _WaveletTreeOps):
     """wt_int<> over a sequence of unsigned integers (host numpy uint64)"""
 

@@ -690,6 +690,33 @@ extern "C"
         return create_compressed(SDSLGPU_KIND_SD, words, nbits, device, flags, out);
     }
 
+    int sdslgpu_load_sdsl(const void * blob, uint64_t nbytes, int kind, int device, uint32_t flags, uint32_t param, sdslgpu_handle ** out)
+    {
+        if (!out || !blob)
+        {
+            set_error("sdslgpu_load_sdsl: null argument");
+            return SDSLGPU_EINVAL;
+        }
+        *out = nullptr;
+        if (kind < SDSLGPU_KIND_BV || kind > SDSLGPU_KIND_CSA_WT)
+        {
+            set_error("sdslgpu_load_sdsl: unknown kind %d", kind);
+            return SDSLGPU_EINVAL;
+        }
+        sdslgpu_handle * h = nullptr;
+        SG_TRY(new_handle(kind, device, flags, &h));
+        DeviceGuard g(device);
+        int st = load_sdsl_blob(h, static_cast<uint8_t const *>(blob), nbytes, param, nullptr);
+        if (st != SDSLGPU_OK)
+        {
+            h->pool.release_all();
+            delete h;
+            return st;
+        }
+        *out = h;
+        return SDSLGPU_OK;
+    }
+
     int sdslgpu_serialize(const sdslgpu_handle * h, int what, void * buf, uint64_t cap, uint64_t * nbytes)
     {
         SG_TRY(check_handle(h));

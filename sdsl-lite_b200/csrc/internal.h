@@ -251,6 +251,9 @@ int rrr_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint6
 int rrr_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 int rrr_access_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 int rrr_serialize(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
+int rrr_upload_tables(sdslgpu_handle * h, cudaStream_t s);
+// sdsl_format.cu
+int load_sdsl_blob(sdslgpu_handle * h, uint8_t const * blob, uint64_t nbytes, uint32_t sa_dens, cudaStream_t s);
 // sd.cu
 int sd_build(sdslgpu_handle * h, uint64_t const * words_host_or_dev, bool on_device, uint64_t nbits, cudaStream_t s);
 int sd_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
