@@ -174,7 +174,9 @@ int load_rrr(sdslgpu_handle * h, Reader & r, cudaStream_t s)
         rec[2 * g + 1] = btnrp.get(g) | (inv.get(g) ? (1ull << 63) : 0);
     }
     rec[2 * im.nsuper] = im.ones;
-    rec[2 * im.nsuper + 1] = btnr.bits;
+    // the blob does not store the exact number of offset bits (m_btnr is padded to >= 64 bits); only its top bit
+    // matters (it fixes the width of m_btnrp when serialising back), and m_btnrp's width preserves that
+    rec[2 * im.nsuper + 1] = btnrp.width ? (1ull << (btnrp.width - 1)) : 0;
     SG_TRY(rrr_upload_tables(h, s));
     uint64_t btw = 3 * im.nsuper + 2, nrw = ((btnr.bits + 63) >> 6) + 2;
     std::vector<uint64_t> btp(btw, 0), nrp(nrw, 0);
