@@ -1,0 +1,101 @@
+"""Golden vectors produced by the UNMODIFIED reference (tests/golden/make_golden.py -> golden_v1.npz): queries,
+answers and SHA-256 digests of its serialised structures.  The oracle is checked on CPU; the CUDA path on GPU.
+This is the parity pin that survives on a machine where oracle/_ref was never built."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import texts
+from test_oracle_wt_int import sequences
+
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz"))
+
+
+def sha(b):
+    return np.frombuffer(hashlib.sha256(b).digest(), dtype=np.uint8)
+
+
+def _bitvectors():
+    for cid, w, nbits in cases.bitvector_catalogue(large=True):
+        if nbits <= 1_000_000:
+            yield cid, w, nbits
+
+
+def _check_bitvector(obj, key):
+    idx = GOLD[key + "|idx"]
+    for b in (0, 1):
+        assert (obj.rank(idx, b) == GOLD[key + f"|rank{b}"]).all(), (key, "rank", b)
+        q = GOLD[key + f"|sel{b}_q"]
+        if len(q):
+            assert (obj.select(q, b) == GOLD[key + f"|sel{b}"]).all(), (key, "select", b)
+
+
+def test_oracle_against_golden(oracle, orc):
+    for cid, w, nbits in _bitvectors():
+        for kind in ("bv", "rrr", "sd"):
+            if kind == "sd" and nbits == 0:
+                continue
+            obj = getattr(oracle, kind)(w, nbits)
+            key = f"{kind}|{cid}"
+            _check_bitvector(obj, key)
+            blobs = [obj.serialize(k) for k in range(5)] if kind == "bv" else [obj.serialize()]
+            assert (np.concatenate([sha(x) for x in blobs]) == GOLD[key + "|sha"]).all(), (key, "serialised bytes")
+    for name, t in texts.text_catalogue(large=False):
+        wt, key = oracle.wt_huff(t), f"wt_huff|{name}"
+        assert (wt.rank(GOLD[key + "|i"], GOLD[key + "|c"]) == GOLD[key + "|rank"]).all(), key
+        r, s = wt.inverse_select(GOLD[key + "|j"])
+        assert (r == GOLD[key + "|inv_rank"]).all() and (s == GOLD[key + "|inv_sym"]).all(), key
+        assert (wt.select(r + np.uint64(1), s.astype(np.uint8)) == GOLD[key + "|sel"]).all(), key
+        assert (sha(wt.serialize()) == GOLD[key + "|sha"]).all(), key
+    for name, seq in sequences():
+        wt, key = oracle.wt_int(seq), f"wt_int|{name}"
+        assert (wt.rank(GOLD[key + "|i"], GOLD[key + "|c"]) == GOLD[key + "|rank"]).all(), key
+        r, s = wt.inverse_select(GOLD[key + "|j"])
+        assert (r == GOLD[key + "|inv_rank"]).all() and (s == GOLD[key + "|inv_sym"]).all(), key
+        assert (sha(wt.serialize()) == GOLD[key + "|sha"]).all(), key
+    for name, t in texts.text_catalogue(zero_free=True, large=False):
+        csa, key = oracle.csa(t), f"csa|{name}"
+        flat, off = GOLD[key + "|flat"], GOLD[key + "|off"]
+        cnt, l = csa.count(flat, off, want_l=True)
+        assert (cnt == GOLD[key + "|cnt"]).all() and (l[cnt > 0] == GOLD[key + "|l"][cnt > 0]).all(), key
+        occ_off, occ = csa.locate(flat, off)
+        assert (occ_off == GOLD[key + "|occ_off"]).all() and (occ == GOLD[key + "|occ"]).all(), key
+        assert (csa.sa(GOLD[key + "|sa_i"]) == GOLD[key + "|sa"]).all(), key
+        assert (sha(csa.serialize()) == GOLD[key + "|sha"]).all(), key
+
+
+@pytest.mark.gpu
+def test_gpu_against_golden(pkg):
+    for cid, w, nbits in _bitvectors():
+        for kind, cls in (("bv", pkg.BitVector), ("rrr", pkg.RrrVector), ("sd", pkg.SdVector)):
+            if kind == "sd" and nbits == 0:
+                continue
+            with cls(w, nbits) as obj:
+                _check_bitvector(obj, f"{kind}|{cid}")
+                if kind == "rrr":  # the device encoder reproduces the reference's bytes
+                    assert (sha(obj.serialize()) == GOLD[f"rrr|{cid}|sha"]).all(), cid
+    for name, t in texts.text_catalogue(large=False):
+        key = f"wt_huff|{name}"
+        with pkg.WtHuff(t) as wt:
+            assert (wt.rank(GOLD[key + "|i"], GOLD[key + "|c"]) == GOLD[key + "|rank"]).all(), key
+            r, s = wt.inverse_select(GOLD[key + "|j"])
+            assert (r == GOLD[key + "|inv_rank"]).all() and (s == GOLD[key + "|inv_sym"]).all(), key
+            assert (wt.select(r + np.uint64(1), s.astype(np.uint8)) == GOLD[key + "|sel"]).all(), key
+    for name, seq in sequences():
+        key = f"wt_int|{name}"
+        with pkg.WtInt(seq) as wt:
+            assert (wt.rank(GOLD[key + "|i"], GOLD[key + "|c"]) == GOLD[key + "|rank"]).all(), key
+            r, s = wt.inverse_select(GOLD[key + "|j"])
+            assert (r == GOLD[key + "|inv_rank"]).all() and (s == GOLD[key + "|inv_sym"]).all(), key
+    for name, t in texts.text_catalogue(zero_free=True, large=False):
+        key = f"csa|{name}"
+        with pkg.CsaWt(t) as csa:
+            flat, off = GOLD[key + "|flat"], GOLD[key + "|off"]
+            cnt, l = csa.count(flat, off, want_l=True)
+            assert (cnt == GOLD[key + "|cnt"]).all() and (l[cnt > 0] == GOLD[key + "|l"][cnt > 0]).all(), key
+            occ_off, occ = csa.locate(flat, off)
+            assert (occ_off == GOLD[key + "|occ_off"]).all() and (occ == GOLD[key + "|occ"]).all(), key
+            assert (csa.sa(GOLD[key + "|sa_i"]) == GOLD[key + "|sa"]).all(), key
