@@ -336,10 +336,15 @@ class CsaWt(_Handle, _WaveletTreeOps):
         poo, occ_off, _k = _out_like(off, n + 1)
         total = C.c_uint64()
         sp = _stream_ptr(stream, off)
-        _check(lib().sdslgpu_fm_locate(self._h, pf, po, n, poo, None, 0, C.byref(total), sp))
-        pocc, occ, _k2 = _out_like(off, max(total.value, 1))
-        if total.value:
-            _check(lib().sdslgpu_fm_locate(self._h, pf, po, n, poo, pocc, total.value, C.byref(total), sp))
+        # one pass when the guessed capacity suffices (one backward search per pattern); otherwise the call
+        # reports the exact total and a second pass fills a buffer of that size
+        cap = max(2 * n, 1 << 16)
+        pocc, occ, _k2 = _out_like(off, cap)
+        st = lib().sdslgpu_fm_locate(self._h, pf, po, n, poo, pocc, cap, C.byref(total), sp)
+        if st == EINVAL and total.value > cap:
+            pocc, occ, _k2 = _out_like(off, total.value)
+            st = lib().sdslgpu_fm_locate(self._h, pf, po, n, poo, pocc, total.value, C.byref(total), sp)
+        _check(st)
         return occ_off, occ[: total.value]
 
 

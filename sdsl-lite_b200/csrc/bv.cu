@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kThreads) bv_rank_kernel(bvblock const * __res
         }
 #pragma unroll
         for (int u = 0; u < ILP; ++u)
-            ld_block(blocks + blk[u], cnt[u], d[u]);
+            ld_block_half_line(blocks + blk[u], cnt[u], d[u]);
 #pragma unroll
         for (int u = 0; u < ILP; ++u)
         {

@@ -26,7 +26,7 @@ __device__ __forceinline__ uint64_t bv_rank1(BvView const & v, uint64_t pos)
     uint64_t blk = pos / kBlockBits;
     uint32_t rem = (uint32_t)(pos - blk * kBlockBits);
     uint32_t cnt, d[7];
-    ld_block(v.blocks + blk, cnt, d);
+    ld_block_half_line(v.blocks + blk, cnt, d);
     return __ldg(v.top + (blk >> kSuperShift)) + cnt + block_prefix_popc(d, rem);
 }
 

@@ -36,6 +36,16 @@ __device__ __forceinline__ void ld_block(bvblock const * p, uint32_t & cnt, uint
                  : "l"(p));
 }
 
+// same gather, but tells the L2 to fill only the 64-byte half line on a miss (SASS: LDG...LTC64B.256).  A B200 L2
+// miss otherwise fills the whole 128-byte line (ncu: 4 DRAM sectors per 32-byte gather, profiles/r01_probe_fetch*);
+// for single-block lookups (rank, one wavelet-tree level) the other 96 bytes are never used.
+__device__ __forceinline__ void ld_block_half_line(bvblock const * p, uint32_t & cnt, uint32_t (&d)[7])
+{
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(cnt), "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6])
+                 : "l"(p));
+}
+
 // 128-bit read-only gather (SDSL-layout rank table pair: absolute count + 7x9-bit relative counts)
 __device__ __forceinline__ void ld_pair(uint64_t const * p, uint64_t & a, uint64_t & b)
 {

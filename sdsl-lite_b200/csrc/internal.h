@@ -188,6 +188,7 @@ struct RrrImage
     uint64_t * btnr = nullptr;    // m_btnr
     uint64_t * records = nullptr; // per superblock {m_rank, m_btnrp | m_invert << 63}, plus a closing record
     void * tables = nullptr;      // RrrTables (binomials + code lengths), device copy
+    uint32_t * hint[2] = {nullptr, nullptr}; // select hints: superblock of every 8192nd b-bit
 };
 
 // sd_vector<> (sd_vector.hpp:155-163)
@@ -252,6 +253,7 @@ int rrr_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uin
 int rrr_access_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 int rrr_serialize(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
 int rrr_upload_tables(sdslgpu_handle * h, cudaStream_t s);
+int rrr_build_hints(sdslgpu_handle * h, cudaStream_t s);
 // sdsl_format.cu
 int load_sdsl_blob(sdslgpu_handle * h, uint8_t const * blob, uint64_t nbytes, uint32_t sa_dens, cudaStream_t s);
 // sd.cu

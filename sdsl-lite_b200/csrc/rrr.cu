@@ -97,7 +97,10 @@ struct RrrView
     uint64_t const * btnr;    // packed offsets
     uint64_t const * records; // 2 words per superblock: ones before it, (bit offset into btnr) | invert << 63
     RrrTables const * tables;
+    uint32_t const * hint[2]; // hint[b][j] = superblock holding the (j * 2^kHintShift + 1)-th b-bit (+ sentinels)
 };
+
+static constexpr uint32_t kHintShift = 13;
 
 __device__ __forceinline__ uint32_t rrr_class(uint64_t const * __restrict__ bt, uint64_t j)
 {
@@ -230,7 +233,8 @@ __global__ void __launch_bounds__(kThreads) rrr_select_kernel(RrrView const v, u
         else
         {
             // superblock g with count_before(g) < i <= count_before(g + 1)   (:643-655)
-            uint64_t begin = 0, end = v.nsuper;
+            uint64_t hj = (i - 1) >> kHintShift;
+            uint64_t begin = __ldg(v.hint[B] + hj), end = (uint64_t)__ldg(v.hint[B] + hj + 1) + 1;
             while (end - begin > 1)
             {
                 uint64_t mid = (begin + end) >> 1;
@@ -386,6 +390,46 @@ __global__ void __launch_bounds__(kThreads) rrr_encode_kernel(uint64_t const * _
         atomicOr(btnr + (p >> 6) + 1, (unsigned long long)(nr >> (64 - o)));
 }
 
+// select hints: one thread per superblock writes the hints whose sampled b-bit falls inside it
+template <int B>
+__global__ void __launch_bounds__(kThreads) rrr_hint_kernel(uint64_t const * __restrict__ records, uint64_t nsuper, uint32_t * __restrict__ hint, uint64_t nhint)
+{
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nsuper)
+        return;
+    uint64_t r0 = records[2 * g], r1 = records[2 * g + 2];
+    uint64_t a = B ? r0 : g * kBs * kK - r0, e = B ? r1 : (g + 1) * kBs * kK - r1; // b-bits before / through g
+    if (e <= a)
+        return;
+    for (uint64_t j = (a + (1ull << kHintShift) - 1) >> kHintShift; j < nhint && (j << kHintShift) + 1 <= e; ++j)
+        hint[j] = (uint32_t)g;
+}
+
+int rrr_build_hints(sdslgpu_handle * h, cudaStream_t s)
+{
+    RrrImage & r = h->rrr;
+    for (int b = 0; b < 2; ++b)
+    {
+        // zeros are counted over whole 2016-bit superblocks (the zero-extended tail included), like select0 does
+        uint64_t args = b ? r.ones : r.nsuper * kBs * kK - r.ones;
+        uint64_t nhint = args ? ((args - 1) >> kHintShift) + 1 : 0;
+        SG_TRY(h->pool.alloc_t(&r.hint[b], nhint + 2));
+        std::vector<uint32_t> fill(nhint + 2, (uint32_t)(r.nsuper ? r.nsuper - 1 : 0));
+        SG_CUDA(cudaMemcpyAsync(r.hint[b], fill.data(), (nhint + 2) * 4, cudaMemcpyHostToDevice, s));
+        SG_CUDA(cudaStreamSynchronize(s));
+        if (nhint)
+        {
+            if (b)
+                rrr_hint_kernel<1><<<blocks_for(r.nsuper), kThreads, 0, s>>>(r.records, r.nsuper, r.hint[b], nhint);
+            else
+                rrr_hint_kernel<0><<<blocks_for(r.nsuper), kThreads, 0, s>>>(r.records, r.nsuper, r.hint[b], nhint);
+            SG_CUDA(cudaGetLastError());
+        }
+    }
+    SG_CUDA(cudaStreamSynchronize(s));
+    return SDSLGPU_OK;
+}
+
 static RrrView rrr_view(RrrImage const & r)
 {
     RrrView v;
@@ -397,6 +441,8 @@ static RrrView rrr_view(RrrImage const & r)
     v.btnr = r.btnr;
     v.records = r.records;
     v.tables = reinterpret_cast<RrrTables const *>(r.tables);
+    v.hint[0] = r.hint[0];
+    v.hint[1] = r.hint[1];
     return v;
 }
 
@@ -458,7 +504,7 @@ int rrr_build(sdslgpu_handle * h, uint64_t const * words_in, bool on_device, uin
     h->pool.release(ones_before);
     h->pool.release(bits_before);
     h->pool.release(tmp);
-    return SDSLGPU_OK;
+    return rrr_build_hints(h, s);
 }
 
 int rrr_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)

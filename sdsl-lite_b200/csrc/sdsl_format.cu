@@ -189,7 +189,7 @@ int load_rrr(sdslgpu_handle * h, Reader & r, cudaStream_t s)
     SG_CUDA(cudaMemcpyAsync(im.btnr, nrp.data(), nrw * 8, cudaMemcpyHostToDevice, s));
     SG_CUDA(cudaMemcpyAsync(im.records, rec.data(), rec.size() * 8, cudaMemcpyHostToDevice, s));
     SG_CUDA(cudaStreamSynchronize(s));
-    return SDSLGPU_OK;
+    return rrr_build_hints(h, s);
 }
 
 int load_sd(sdslgpu_handle * h, Reader & r, cudaStream_t s)
