@@ -315,6 +315,9 @@ int bv_build(DevicePool & pool, BvImage & v, uint32_t flags, uint64_t const * wo
             if (char const * e = std::getenv("SDSLGPU_SELECT_LOG_S")) // tuning knob for experiments
                 ls = (uint32_t)std::atoi(e) > 16 ? 16u : (uint32_t)std::atoi(e);
             v.log_s[b] = ls;
+            v.interp[b] = ls > 6;
+            if (char const * e = std::getenv("SDSLGPU_SELECT_INTERP"))
+                v.interp[b] = std::atoi(e) != 0;
             v.nsamp[b] = m ? ((m - 1) >> ls) + 1 : 0;
             SG_TRY(pool.alloc_t(&v.samp[b], v.nsamp[b] + 2));
             // sentinel(s): the last block

@@ -17,6 +17,7 @@ struct BvView
     uint32_t log_s[2];
     uint64_t nbits;
     uint64_t ones;
+    uint32_t interp[2]; // 1: start the block search at the interpolated position between two samples
 };
 
 // number of 1-bits in [0, pos), 0 <= pos <= nbits: one 32-byte sector gather
@@ -90,7 +91,7 @@ __device__ __forceinline__ uint64_t bv_select(BvView const & v, uint64_t i)
     // ~90 % of the time on random data; any miss is repaired by walking / bisecting on the block counts, so
     // the result never depends on the guess.
     uint32_t cnt, d[7];
-    uint64_t g = lo + (((hi - lo) * ((i - 1) & ((1ull << log_s) - 1)) + (1ull << log_s >> 1)) >> log_s);
+    uint64_t g = v.interp[B] ? lo + (((hi - lo) * ((i - 1) & ((1ull << log_s) - 1)) + (1ull << log_s >> 1)) >> log_s) : lo;
     ld_block(blocks + g, cnt, d);
     uint64_t a1 = __ldg(top + (g >> kSuperShift)) + cnt;
     uint64_t before = B ? a1 : g * kBlockBits - a1;

@@ -117,6 +117,7 @@ struct BvImage
     uint32_t * samp[2] = {nullptr, nullptr};
     uint64_t nsamp[2] = {0, 0};
     uint32_t log_s[2] = {6, 6};
+    uint32_t interp[2] = {0, 0}; // interpolate between samples (set when the stride exceeds 64)
     // optional SDSL layout (SDSLGPU_F_SDSL_LAYOUT): raw words (+ pad) and the m_basic_block tables
     uint64_t * words = nullptr;
     uint64_t nwords = 0;
@@ -133,6 +134,8 @@ inline BvView bv_view(BvImage const & v)
     w.samp[1] = v.samp[1];
     w.log_s[0] = v.log_s[0];
     w.log_s[1] = v.log_s[1];
+    w.interp[0] = v.interp[0];
+    w.interp[1] = v.interp[1];
     w.nbits = v.nbits;
     w.ones = v.ones;
     return w;

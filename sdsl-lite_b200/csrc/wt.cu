@@ -8,6 +8,7 @@
 //   wt_pc::select(i,c)      wt_pc.hpp:443-474   -> wt_select_kernel    (bottom-up select0/select1 on m_bv)
 // The node table and the per-symbol paths (≈14 KB) are staged into shared memory once per CTA.
 #include <algorithm>
+#include <cstdlib>
 #include <atomic>
 #include <queue>
 #include <thread>
@@ -404,13 +405,90 @@ int wt_huff_build_from_text(sdslgpu_handle * h, uint8_t const * text, uint64_t n
 
 static size_t const kTreeSmem = sizeof(WtTree);
 
+// ------------------------------------------------------------------------------------------------
+// level-synchronous rank: ALL queries advance one tree level per launch.  The bits of one depth of the tree are
+// a contiguous slice of m_bv (nodes are laid out in BFS order) — 1/8 of the index for a byte alphabet — so each
+// pass gathers from a slice that stays resident in the 126 MB L2 (160 G gathers/s measured) instead of
+// from DRAM at random (37 G/s).  Per-query state between passes (running rank: 48 bits, current node: 9 bits)
+// lives in the output array itself.
+// ------------------------------------------------------------------------------------------------
+static constexpr uint64_t kStateMask = (1ull << 48) - 1;
+
+__global__ void __launch_bounds__(kThreads) wt_rank_level_kernel(BvView const bv,
+                                                                 WtTree const * __restrict__ tree,
+                                                                 uint64_t size,
+                                                                 uint32_t level,
+                                                                 uint32_t last_level,
+                                                                 uint64_t const * __restrict__ qi,
+                                                                 uint8_t const * __restrict__ qc,
+                                                                 uint64_t n,
+                                                                 uint64_t * __restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WtTree * t = reinterpret_cast<WtTree *>(smem_raw);
+    stage_tree(tree, t);
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
+    {
+        uint32_t c = qc[q];
+        uint64_t r;
+        uint32_t v = 0;
+        if (level == 0)
+        {
+            r = qi[q];
+            if (r > size)
+            {
+                out[q] = SDSLGPU_NPOS;
+                continue;
+            }
+            if (t->c_to_leaf[c] == kUndef)
+                r = 0;
+        }
+        else
+        {
+            uint64_t st = out[q];
+            if (st == SDSLGPU_NPOS)
+                continue;
+            r = st & kStateMask;
+            v = (uint32_t)(st >> 48);
+        }
+        uint64_t p = t->path[c];
+        uint32_t len = (uint32_t)(p >> 56);
+        if (level < len && r != 0)
+        {
+            uint32_t bit = (uint32_t)(p >> level) & 1u;
+            uint64_t o = bv_rank1(bv, t->bv_pos[v] + r) - t->bv_pos_rank[v];
+            r = bit ? o : r - o;
+            v = t->child[v][bit];
+        }
+        out[q] = (level == last_level) ? r : (r | ((uint64_t)v << 48));
+    }
+}
+
 int wt_rank_device(sdslgpu_handle const * h, uint64_t const * i, uint8_t const * c, uint64_t n, uint64_t * out, cudaStream_t s)
 {
     WtHuffImage const & w = h->wt;
     if (n == 0)
         return SDSLGPU_OK;
-    wt_rank_kernel<<<grid_for(n), kThreads, kTreeSmem, s>>>(bv_view(w.bv), w.tree, w.size, w.sigma, i, c, n, out);
-    SG_CUDA(cudaGetLastError());
+    // depth of the tree = number of passes of the level-synchronous form
+    uint32_t depth = 0;
+    for (int k = 0; k < 256; ++k)
+        if (w.host_tree.c_to_leaf[k] != kUndef)
+            depth = std::max(depth, (uint32_t)(w.host_tree.path[k] >> 56));
+    bool level_sync = n >= (1u << 16) && depth >= 2 && depth <= 24 && w.sigma > 1 && w.bv.nbits < (1ull << 47);
+    if (char const * e = std::getenv("SDSLGPU_WT_LEVEL_SYNC")) // tuning knob for experiments
+        level_sync = std::atoi(e) != 0 && depth >= 1 && w.sigma > 1;
+    if (!level_sync)
+    {
+        wt_rank_kernel<<<grid_for(n), kThreads, kTreeSmem, s>>>(bv_view(w.bv), w.tree, w.size, w.sigma, i, c, n, out);
+        SG_CUDA(cudaGetLastError());
+        return SDSLGPU_OK;
+    }
+    for (uint32_t l = 0; l < depth; ++l)
+    {
+        wt_rank_level_kernel<<<grid_for(n), kThreads, kTreeSmem, s>>>(bv_view(w.bv), w.tree, w.size, l, depth - 1, i, c, n, out);
+        SG_CUDA(cudaGetLastError());
+    }
     return SDSLGPU_OK;
 }
 
