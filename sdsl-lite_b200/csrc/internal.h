@@ -187,9 +187,8 @@ struct alignas(16) FmTables
 struct RrrImage
 {
     uint64_t size = 0, nblocks = 0, nsuper = 0, ones = 0, btnr_bits = 0;
-    uint64_t * bt = nullptr;      // m_bt: packed 6-bit classes, 3 words per superblock
     uint64_t * btnr = nullptr;    // m_btnr
-    uint64_t * records = nullptr; // per superblock {m_rank, m_btnrp | m_invert << 63}, plus a closing record
+    uint64_t * records = nullptr; // 64-byte record per superblock (rank, btnrp|invert, 32 classes, quarter sums) + closing record
     void * tables = nullptr;      // RrrTables (binomials + code lengths), device copy
     uint32_t * hint[2] = {nullptr, nullptr}; // select hints: superblock of every 8192nd b-bit
 };
@@ -257,6 +256,8 @@ int rrr_access_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t n
 int rrr_serialize(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
 int rrr_upload_tables(sdslgpu_handle * h, cudaStream_t s);
 int rrr_build_hints(sdslgpu_handle * h, cudaStream_t s);
+int rrr_records_from_sdsl(sdslgpu_handle * h, uint64_t const * bt_words, uint64_t nblocks, std::vector<uint64_t> const & rank,
+                          std::vector<uint64_t> const & btnrp, std::vector<uint8_t> const & invert, uint64_t total_bits_hint, cudaStream_t s);
 // sdsl_format.cu
 int load_sdsl_blob(sdslgpu_handle * h, uint8_t const * blob, uint64_t nbytes, uint32_t sa_dens, cudaStream_t s);
 // sd.cu

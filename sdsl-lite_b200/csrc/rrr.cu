@@ -1,15 +1,23 @@
 // rrr.cu — rrr_vector<63, int_vector<>, 32>: device-side encoder and batched rank / select / access.
 //
-// Replaces (results bit-exact; m_bt and m_btnr are bit-identical to the reference's, so SDSL-serialised
-// vectors can be ingested as they are):
+// Replaces (results bit-exact; the encoding is bit-identical to the reference's, so SDSL-serialised
+// vectors are ingested without re-encoding and the device image serialises back to the same bytes):
 //   rrr_vector ctor            rrr_vector.hpp:158-270 + rrr_helper.hpp:346-366 (bin_to_nr) -> rrr_classify /
 //                                                                  rrr_superblock / rrr_encode kernels + scans
 //   rank_support_rrr::rank     rrr_vector.hpp:503-544  -> rrr_rank_kernel
 //   select_support_rrr::select rrr_vector.hpp:639-726  -> rrr_select_kernel<B>
 //   rrr_vector::operator[]     rrr_vector.hpp:276-298  -> rrr_access_kernel
-// Device layout: the 6-bit classes (m_bt) and the offsets (m_btnr) stay packed exactly as in the reference;
-// the three per-superblock arrays (m_rank, m_btnrp, m_invert) are fused into one 16-byte record so a query
-// reads them with a single 128-bit load.  C(n,k) for n,k <= 63 (32 KB) and the code lengths live in shared memory.
+//
+// Device layout.  The reference keeps five arrays (m_bt, m_btnr, m_btnrp, m_rank, m_invert) and a query
+// touches four of them at unrelated addresses.  A B200 pays per cache line touched, so all
+// per-superblock metadata is fused into ONE 64-byte record (half a line, two LDG.256):
+//     w0      ones before the superblock                         (m_rank[g])
+//     w1      bit offset into the offset stream | invert << 63   (m_btnrp[g], m_invert[g])
+//     w2..w4  the 32 six-bit classes exactly as stored in m_bt   (192 bits)
+//     w5      prefix sums after 8 / 16 / 24 blocks: ones (10+10+11 bits) and offset bits (10+10+11 bits)
+//     w6      ones in the superblock, w7 offset bits of the superblock
+// so rank = record + one read of the offset stream (m_btnr, unchanged), and the class scan is at most 7 steps.
+// C(n,k) for n,k <= 63 (32 KB) and the code lengths live in shared memory.
 #include "internal.h"
 #include "scan.cuh"
 
@@ -19,6 +27,8 @@ namespace sdslgpu
 static constexpr uint32_t kBs = 63; // t_bs
 static constexpr uint32_t kK = 32;  // t_k
 static constexpr uint64_t kInvBit = 1ull << 63;
+static constexpr uint32_t kRecWords = 8;
+static constexpr uint32_t kHintShift = 13;
 
 struct RrrTables
 {
@@ -90,44 +100,63 @@ __device__ __forceinline__ uint64_t rrr_decode(RrrTables const * t, uint32_t k, 
 struct RrrView
 {
     uint64_t size;
-    uint64_t nblocks;  // m_bt.size()
-    uint64_t nsuper;   // m_btnrp.size(); records has nsuper + 1 entries (the last holds the total)
+    uint64_t nblocks; // m_bt.size()
+    uint64_t nsuper;  // m_btnrp.size(); `records` has nsuper + 1 entries (the last holds the totals)
     uint64_t ones;
-    uint64_t const * bt;      // packed 6-bit stored classes
-    uint64_t const * btnr;    // packed offsets
-    uint64_t const * records; // 2 words per superblock: ones before it, (bit offset into btnr) | invert << 63
+    uint64_t const * btnr;    // packed offsets (m_btnr)
+    uint64_t const * records; // 8 words per superblock, see the file header
     RrrTables const * tables;
     uint32_t const * hint[2]; // hint[b][j] = superblock holding the (j * 2^kHintShift + 1)-th b-bit (+ sentinels)
 };
 
-static constexpr uint32_t kHintShift = 13;
-
-__device__ __forceinline__ uint32_t rrr_class(uint64_t const * __restrict__ bt, uint64_t j)
+struct RrrRecord
 {
-    return (uint32_t)read_int(bt, j * 6, 6);
+    uint64_t w[kRecWords];
+};
+
+__device__ __forceinline__ void ld_record(uint64_t const * __restrict__ records, uint64_t g, RrrRecord & r)
+{
+    uint64_t const * p = records + g * kRecWords;
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.w[0]), "=l"(r.w[1]), "=l"(r.w[2]), "=l"(r.w[3]) : "l"(p));
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.w[4]), "=l"(r.w[5]), "=l"(r.w[6]), "=l"(r.w[7]) : "l"(p + 4));
 }
 
-// classes of superblock g up to (not including) block `blk`: ones and btnr bits consumed
-__device__ __forceinline__ void rrr_scan_classes(RrrView const & v, RrrTables const * t, uint64_t g, uint32_t nblk, bool inv, uint64_t & ones, uint64_t & p)
+// stored class of block j (0..31) of a record
+__host__ __device__ __forceinline__ uint32_t rec_class(uint64_t w2, uint64_t w3, uint64_t w4, uint32_t j)
 {
-    // 32 classes = 192 bits = exactly three words
-    uint64_t const * w = v.bt + g * 3;
-    uint64_t w0 = __ldg(w), w1 = nblk > 10 ? __ldg(w + 1) : 0, w2 = nblk > 21 ? __ldg(w + 2) : 0;
-    for (uint32_t j = 0; j < nblk; ++j)
+    uint32_t bit = j * 6;
+    if (bit < 60)
+        return (uint32_t)(w2 >> bit) & 63u;
+    if (bit == 60)
+        return (uint32_t)((w2 >> 60) | (w3 << 4)) & 63u;
+    if (bit < 124)
+        return (uint32_t)(w3 >> (bit - 64)) & 63u;
+    if (bit == 126)
+        return (uint32_t)((w3 >> 62) | (w4 << 2)) & 63u;
+    return (uint32_t)(w4 >> (bit - 128)) & 63u;
+}
+
+// prefix sums over whole quarters (8 blocks each): q in 0..3
+__host__ __device__ __forceinline__ uint32_t rec_qones(uint64_t w5, uint32_t q)
+{
+    return q == 0 ? 0u : q == 1 ? (uint32_t)(w5 & 1023) : q == 2 ? (uint32_t)((w5 >> 10) & 1023) : (uint32_t)((w5 >> 20) & 2047);
+}
+__host__ __device__ __forceinline__ uint32_t rec_qbits(uint64_t w5, uint32_t q)
+{
+    return q == 0 ? 0u : q == 1 ? (uint32_t)((w5 >> 31) & 1023) : q == 2 ? (uint32_t)((w5 >> 41) & 1023) : (uint32_t)((w5 >> 51) & 2047);
+}
+
+// ones and offset bits of the first nblk (0..31) blocks of a superblock
+__device__ __forceinline__ void rec_prefix(RrrRecord const & r, RrrTables const * t, uint32_t nblk, bool inv, uint64_t & ones, uint64_t & p)
+{
+    uint32_t q = nblk >> 3;
+    ones += rec_qones(r.w[5], q);
+    p += rec_qbits(r.w[5], q);
+    for (uint32_t j = q << 3; j < nblk; ++j)
     {
-        uint32_t bit = j * 6, c;
-        if (bit < 60)
-            c = (uint32_t)(w0 >> bit) & 63u;
-        else if (bit == 60)
-            c = (uint32_t)((w0 >> 60) | (w1 << 4)) & 63u;
-        else if (bit < 124)
-            c = (uint32_t)(w1 >> (bit - 64)) & 63u;
-        else if (bit == 126)
-            c = (uint32_t)((w1 >> 62) | (w2 << 2)) & 63u;
-        else
-            c = (uint32_t)(w2 >> (bit - 128)) & 63u;
+        uint32_t c = rec_class(r.w[2], r.w[3], r.w[4], j);
         ones += inv ? kBs - c : c;
-        p += t->space[c];
+        p += t->space[c]; // space is symmetric: stored or real class give the same width (rrr_vector.hpp:528-541)
     }
 }
 
@@ -138,20 +167,20 @@ __device__ __forceinline__ uint64_t rrr_rank1_one(RrrView const & v, RrrTables c
 {
     uint64_t blk = i / kBs, g = blk / kK;
     uint32_t off = (uint32_t)(i - blk * kBs);
-    uint64_t r0, pw, r1;
-    ld_pair(v.records + 2 * g, r0, pw);
-    r1 = __ldg(v.records + 2 * g + 2);
-    uint64_t d = r1 - r0;
+    RrrRecord r;
+    ld_record(v.records, g, r);
+    uint64_t d = r.w[6];
     if (d == 0)
-        return r0; // uniform superblocks (rrr_vector.hpp:514-523); same result as the general path
+        return r.w[0]; // uniform superblocks (rrr_vector.hpp:514-523); same result as the general path
     if (d == (uint64_t)kBs * kK)
-        return r0 + i - g * kK * kBs;
-    bool inv = (pw & kInvBit) != 0;
-    uint64_t p = pw & ~kInvBit, ones = r0;
-    rrr_scan_classes(v, t, g, (uint32_t)(blk - g * kK), inv, ones, p);
+        return r.w[0] + i - g * kK * kBs;
+    bool inv = (r.w[1] & kInvBit) != 0;
+    uint64_t p = r.w[1] & ~kInvBit, ones = r.w[0];
+    uint32_t nblk = (uint32_t)(blk - g * kK);
+    rec_prefix(r, t, nblk, inv, ones, p);
     if (off == 0)
         return ones;
-    uint32_t k = rrr_class(v.bt, blk);
+    uint32_t k = rec_class(r.w[2], r.w[3], r.w[4], nblk);
     if (inv)
         k = kBs - k;
     uint32_t sp = t->space[k];
@@ -189,28 +218,28 @@ __global__ void __launch_bounds__(kThreads) rrr_access_kernel(RrrView const v, u
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
     {
         uint64_t i = ld_stream_u64(idx + q);
-        uint64_t r = SDSLGPU_NPOS;
+        uint64_t res = SDSLGPU_NPOS;
         if (i < v.size)
         {
             uint64_t blk = i / kBs, g = blk / kK;
-            uint32_t off = (uint32_t)(i - blk * kBs);
-            uint64_t r0, pw;
-            ld_pair(v.records + 2 * g, r0, pw);
-            bool inv = (pw & kInvBit) != 0;
-            uint32_t k = rrr_class(v.bt, blk);
+            uint32_t off = (uint32_t)(i - blk * kBs), nblk = (uint32_t)(blk - g * kK);
+            RrrRecord r;
+            ld_record(v.records, g, r);
+            bool inv = (r.w[1] & kInvBit) != 0;
+            uint32_t k = rec_class(r.w[2], r.w[3], r.w[4], nblk);
             if (inv)
                 k = kBs - k;
             if (k == 0 || k == kBs)
-                r = k != 0; // rrr_vector.hpp:283-288
+                res = k != 0; // rrr_vector.hpp:283-288
             else
             {
-                uint64_t p = pw & ~kInvBit, ones = 0;
-                rrr_scan_classes(v, t, g, (uint32_t)(blk - g * kK), inv, ones, p);
+                uint64_t p = r.w[1] & ~kInvBit, ones = 0;
+                rec_prefix(r, t, nblk, inv, ones, p);
                 uint64_t bin = rrr_decode(t, k, read_int(v.btnr, p, t->space[k]), off + 1);
-                r = (bin >> off) & 1;
+                res = (bin >> off) & 1;
             }
         }
-        st_stream_u64(out + q, r);
+        st_stream_u64(out + q, res);
     }
 }
 
@@ -225,42 +254,55 @@ __global__ void __launch_bounds__(kThreads) rrr_select_kernel(RrrView const v, u
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
     {
         uint64_t i = ld_stream_u64(idx + q);
-        uint64_t r;
+        uint64_t res;
         if (i == 0)
-            r = SDSLGPU_NPOS;
+            res = SDSLGPU_NPOS;
         else if (i > args)
-            r = v.size; // the reference's in-band answer (rrr_vector.hpp:641-642, 686-689)
+            res = v.size; // the reference's in-band answer (rrr_vector.hpp:641-642, 686-689)
         else
         {
-            // superblock g with count_before(g) < i <= count_before(g + 1)   (:643-655)
+            // superblock g with count_before(g) < i <= count_before(g + 1)   (:643-655), bracketed by the hints
             uint64_t hj = (i - 1) >> kHintShift;
             uint64_t begin = __ldg(v.hint[B] + hj), end = (uint64_t)__ldg(v.hint[B] + hj + 1) + 1;
             while (end - begin > 1)
             {
                 uint64_t mid = (begin + end) >> 1;
-                uint64_t rk = __ldg(v.records + 2 * mid);
+                uint64_t rk = __ldg(v.records + mid * kRecWords);
                 uint64_t c = B ? rk : mid * kBs * kK - rk;
                 if (c >= i)
                     end = mid;
                 else
                     begin = mid;
             }
-            uint64_t r0, pw;
-            ld_pair(v.records + 2 * begin, r0, pw);
-            uint64_t r1 = __ldg(v.records + 2 * begin + 2);
-            uint64_t cnt = B ? r0 : begin * kBs * kK - r0;
-            uint64_t d = r1 - r0;
+            RrrRecord r;
+            ld_record(v.records, begin, r);
+            uint64_t cnt = B ? r.w[0] : begin * kBs * kK - r.w[0];
+            uint64_t d = r.w[6];
             if (B ? (d == (uint64_t)kBs * kK) : (d == 0))
-                r = begin * kK * kBs + (i - cnt - 1); // all-ones / all-zeros superblock (:658-663, :703-706)
+                res = begin * kK * kBs + (i - cnt - 1); // all-ones / all-zeros superblock (:658-663, :703-706)
             else
             {
-                bool inv = (pw & kInvBit) != 0;
-                uint64_t p = pw & ~kInvBit;
-                uint64_t blk = begin * kK;
-                uint32_t k = 0, sp = 0;
-                for (;; ++blk)
+                bool inv = (r.w[1] & kInvBit) != 0;
+                uint64_t p = r.w[1] & ~kInvBit;
+                // skip whole quarters, then scan at most 8 classes
+                uint32_t quarter = 0;
+#pragma unroll
+                for (uint32_t qq = 1; qq < 4; ++qq)
                 {
-                    k = rrr_class(v.bt, blk);
+                    uint32_t o = rec_qones(r.w[5], qq);
+                    uint64_t c = B ? o : qq * 8 * kBs - o;
+                    if (cnt + c < i)
+                        quarter = qq;
+                }
+                {
+                    uint32_t o = rec_qones(r.w[5], quarter);
+                    cnt += B ? o : quarter * 8 * kBs - o;
+                    p += rec_qbits(r.w[5], quarter);
+                }
+                uint32_t j = quarter << 3, k = 0, sp = 0;
+                for (;; ++j)
+                {
+                    k = rec_class(r.w[2], r.w[3], r.w[4], j);
                     if (inv)
                         k = kBs - k;
                     sp = t->space[k];
@@ -272,10 +314,10 @@ __global__ void __launch_bounds__(kThreads) rrr_select_kernel(RrrView const v, u
                 }
                 uint64_t bin = rrr_decode(t, k, sp ? read_int(v.btnr, p, sp) : 0, kBs);
                 uint64_t x = B ? bin : (~bin & ((1ull << kBs) - 1));
-                r = blk * kBs + sel64(x, (uint32_t)(i - cnt));
+                res = (begin * kK + j) * kBs + sel64(x, (uint32_t)(i - cnt));
             }
         }
-        st_stream_u64(out + q, r);
+        st_stream_u64(out + q, res);
     }
 }
 
@@ -307,49 +349,82 @@ __global__ void __launch_bounds__(kThreads) rrr_classify_kernel(uint64_t const *
     blk_sp[b] = (b * kBs < nbits) ? tables->space[k] : 0; // the dummy block stores nothing
 }
 
-// per superblock: the invert decision, the fused record and the three words of stored classes
+// fills one 64-byte record from the REAL classes of its blocks (host and device share this)
+__host__ __device__ inline void rrr_make_record(uint32_t const * k_real, uint32_t nblk_here, bool complete, uint8_t const * space, uint64_t ones_before,
+                                                uint64_t bits_before, uint64_t * rec)
+{
+    bool inv = false;
+    if (complete)
+    { // only complete superblocks can be inverted (rrr_vector.hpp:203-228)
+        uint32_t gt = 0;
+        for (uint32_t j = 0; j < kK; ++j)
+            gt += k_real[j] > kBs / 2;
+        inv = gt > kK / 2;
+    }
+    uint64_t w[3] = {0, 0, 0};
+    uint32_t ones = 0, bits = 0, qo[4] = {0, 0, 0, 0}, qb[4] = {0, 0, 0, 0};
+    for (uint32_t j = 0; j < kK; ++j)
+    {
+        if ((j & 7) == 0)
+        {
+            qo[j >> 3] = ones;
+            qb[j >> 3] = bits;
+        }
+        if (j >= nblk_here)
+            continue;
+        uint64_t c = inv ? kBs - k_real[j] : k_real[j];
+        uint32_t bit = j * 6;
+        w[bit >> 6] |= c << (bit & 63);
+        if ((bit & 63) > 58)
+            w[(bit >> 6) + 1] |= c >> (64 - (bit & 63));
+        ones += k_real[j];
+        bits += space[k_real[j]];
+    }
+    rec[0] = ones_before;
+    rec[1] = bits_before | (inv ? kInvBit : 0);
+    rec[2] = w[0];
+    rec[3] = w[1];
+    rec[4] = w[2];
+    rec[5] = (uint64_t)qo[1] | ((uint64_t)qo[2] << 10) | ((uint64_t)qo[3] << 20) | ((uint64_t)qb[1] << 31) | ((uint64_t)qb[2] << 41) | ((uint64_t)qb[3] << 51);
+    rec[6] = ones;
+    rec[7] = bits;
+}
+
 __global__ void __launch_bounds__(kThreads) rrr_superblock_kernel(uint32_t const * __restrict__ blk_k,
+                                                                  uint32_t const * __restrict__ blk_sp,
                                                                   uint64_t const * __restrict__ ones_before,
                                                                   uint64_t const * __restrict__ bits_before,
+                                                                  uint64_t nbits,
                                                                   uint64_t nblocks,
                                                                   uint64_t nsuper,
-                                                                  uint64_t * __restrict__ bt,
+                                                                  RrrTables const * __restrict__ tables,
                                                                   uint64_t * __restrict__ records)
 {
     uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g > nsuper)
         return;
+    uint64_t * rec = records + g * kRecWords;
     if (g == nsuper)
-    { // closing record: total number of ones (m_rank's extra element, :261-262)
-        records[2 * g] = ones_before[nblocks];
-        records[2 * g + 1] = bits_before[nblocks];
+    { // closing record: totals (m_rank's extra element, rrr_vector.hpp:261-262)
+        rec[0] = ones_before[nblocks];
+        rec[1] = bits_before[nblocks];
+        for (uint32_t k = 2; k < kRecWords; ++k)
+            rec[k] = 0;
         return;
     }
     uint64_t first = g * kK;
-    bool inv = false;
-    if (first + kK <= nblocks)
-    { // only complete superblocks can be inverted (:203-228)
-        uint32_t gt = 0;
-        for (uint32_t j = 0; j < kK; ++j)
-            gt += blk_k[first + j] > kBs / 2;
-        inv = gt > kK / 2;
-    }
-    uint64_t w[3] = {0, 0, 0};
-    for (uint32_t j = 0; j < kK && first + j < nblocks; ++j)
+    uint32_t k_real[kK];
+    uint32_t here = 0;
+    for (uint32_t j = 0; j < kK; ++j)
     {
-        uint64_t c = blk_k[first + j];
-        if (inv)
-            c = kBs - c;
-        uint32_t bit = j * 6;
-        w[bit >> 6] |= c << (bit & 63);
-        if ((bit & 63) > 58)
-            w[(bit >> 6) + 1] |= c >> (64 - (bit & 63));
+        k_real[j] = (first + j < nblocks) ? blk_k[first + j] : 0;
+        // blocks that start at or past nbits (the dummy block) carry a class but no offset bits
+        here += (first + j < nblocks);
     }
-    bt[3 * g] = w[0];
-    bt[3 * g + 1] = w[1];
-    bt[3 * g + 2] = w[2];
-    records[2 * g] = ones_before[first];
-    records[2 * g + 1] = bits_before[first] | (inv ? kInvBit : 0);
+    // the dummy block must not contribute offset bits: its real class is 0 => space[0] == 0 already
+    (void)blk_sp;
+    (void)nbits;
+    rrr_make_record(k_real, here, first + kK <= nblocks, tables->space, ones_before[first], bits_before[first], rec);
 }
 
 // per block: offset within its class (bin_to_nr, rrr_helper.hpp:346-366) OR-ed into the packed stream
@@ -397,7 +472,7 @@ __global__ void __launch_bounds__(kThreads) rrr_hint_kernel(uint64_t const * __r
     uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nsuper)
         return;
-    uint64_t r0 = records[2 * g], r1 = records[2 * g + 2];
+    uint64_t r0 = records[g * kRecWords], r1 = records[(g + 1) * kRecWords];
     uint64_t a = B ? r0 : g * kBs * kK - r0, e = B ? r1 : (g + 1) * kBs * kK - r1; // b-bits before / through g
     if (e <= a)
         return;
@@ -437,7 +512,6 @@ static RrrView rrr_view(RrrImage const & r)
     v.nblocks = r.nblocks;
     v.nsuper = r.nsuper;
     v.ones = r.ones;
-    v.bt = r.bt;
     v.btnr = r.btnr;
     v.records = r.records;
     v.tables = reinterpret_cast<RrrTables const *>(r.tables);
@@ -487,12 +561,10 @@ int rrr_build(sdslgpu_handle * h, uint64_t const * words_in, bool on_device, uin
     r.ones = totals[0];
     r.btnr_bits = totals[1] > 64 ? totals[1] : 64; // m_btnr has at least 64 bits (:182)
     uint64_t btnr_words = ((r.btnr_bits + 63) >> 6) + 2;
-    SG_TRY(h->pool.alloc_t(&r.bt, 3 * r.nsuper + 2));
     SG_TRY(h->pool.alloc_t(&r.btnr, btnr_words));
-    SG_TRY(h->pool.alloc_t(&r.records, 2 * (r.nsuper + 1) + 2));
+    SG_TRY(h->pool.alloc_t(&r.records, kRecWords * (r.nsuper + 1)));
     SG_CUDA(cudaMemsetAsync(r.btnr, 0, btnr_words * 8, s));
-    SG_CUDA(cudaMemsetAsync(r.bt + 3 * r.nsuper, 0, 16, s));
-    rrr_superblock_kernel<<<blocks_for(r.nsuper + 1), kThreads, 0, s>>>(blk_k, ones_before, bits_before, r.nblocks, r.nsuper, r.bt, r.records);
+    rrr_superblock_kernel<<<blocks_for(r.nsuper + 1), kThreads, 0, s>>>(blk_k, blk_sp, ones_before, bits_before, nbits, r.nblocks, r.nsuper, tables, r.records);
     SG_CUDA(cudaGetLastError());
     rrr_encode_kernel<<<blocks_for(r.nblocks), kThreads, sizeof(RrrTables), s>>>(words, nbits, r.nblocks, tables, bits_before,
                                                                                   reinterpret_cast<unsigned long long *>(r.btnr));
@@ -505,6 +577,53 @@ int rrr_build(sdslgpu_handle * h, uint64_t const * words_in, bool on_device, uin
     h->pool.release(bits_before);
     h->pool.release(tmp);
     return rrr_build_hints(h, s);
+}
+
+// records from the reference's own arrays (ingest of a serialised rrr_vector): stored classes + samples
+int rrr_records_from_sdsl(sdslgpu_handle * h,
+                          uint64_t const * bt_words /* packed 6-bit stored classes */,
+                          uint64_t nblocks,
+                          std::vector<uint64_t> const & rank,
+                          std::vector<uint64_t> const & btnrp,
+                          std::vector<uint8_t> const & invert,
+                          uint64_t total_bits_hint,
+                          cudaStream_t s)
+{
+    RrrImage & r = h->rrr;
+    RrrTables const & t = host_tables();
+    std::vector<uint64_t> rec(kRecWords * (r.nsuper + 1), 0);
+    for (uint64_t g = 0; g < r.nsuper; ++g)
+    {
+        uint32_t k_real[kK];
+        uint32_t here = 0;
+        for (uint32_t j = 0; j < kK; ++j)
+        {
+            uint64_t b = g * kK + j;
+            uint32_t c = 0;
+            if (b < nblocks)
+            {
+                uint64_t pos = b * 6;
+                uint64_t lo = bt_words[pos >> 6] >> (pos & 63);
+                if ((pos & 63) > 58)
+                    lo |= bt_words[(pos >> 6) + 1] << (64 - (pos & 63));
+                c = (uint32_t)(lo & 63);
+                if (invert[g])
+                    c = kBs - c;
+                ++here;
+            }
+            k_real[j] = c;
+        }
+        uint64_t * out = rec.data() + g * kRecWords;
+        rrr_make_record(k_real, here, g * kK + kK <= nblocks, t.space, rank[g], btnrp[g], out);
+        // keep the reference's invert bit verbatim (it equals the recomputed one for every complete superblock)
+        out[1] = btnrp[g] | (invert[g] ? kInvBit : 0);
+    }
+    rec[kRecWords * r.nsuper] = r.ones;
+    rec[kRecWords * r.nsuper + 1] = total_bits_hint;
+    SG_TRY(h->pool.alloc_t(&r.records, rec.size()));
+    SG_CUDA(cudaMemcpyAsync(r.records, rec.data(), rec.size() * 8, cudaMemcpyHostToDevice, s));
+    SG_CUDA(cudaStreamSynchronize(s));
+    return SDSLGPU_OK;
 }
 
 int rrr_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)
@@ -542,8 +661,7 @@ int rrr_access_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t n
 int rrr_serialize(sdslgpu_handle const * h, std::vector<uint8_t> & blob)
 {
     RrrImage const & r = h->rrr;
-    std::vector<uint64_t> bt(3 * r.nsuper + 1), btnr((r.btnr_bits + 63) >> 6), rec(2 * (r.nsuper + 1));
-    SG_CUDA(cudaMemcpy(bt.data(), r.bt, 3 * r.nsuper * 8, cudaMemcpyDeviceToHost));
+    std::vector<uint64_t> btnr((r.btnr_bits + 63) >> 6), rec(kRecWords * (r.nsuper + 1));
     SG_CUDA(cudaMemcpy(btnr.data(), r.btnr, btnr.size() * 8, cudaMemcpyDeviceToHost));
     SG_CUDA(cudaMemcpy(rec.data(), r.records, rec.size() * 8, cudaMemcpyDeviceToHost));
     auto put64 = [&](uint64_t x) {
@@ -571,31 +689,31 @@ int rrr_serialize(sdslgpu_handle const * h, std::vector<uint8_t> & blob)
             put64(w[k]);
     };
     put64(r.size);
-    // m_bt: nblocks x 6 bits — the device keeps exactly these words
+    // m_bt: nblocks x 6 bits = the class words of the records, 3 per superblock
     {
-        uint64_t bits = r.nblocks * 6;
+        uint64_t bits = r.nblocks * 6, nw = (bits + 63) >> 6;
         put64((6ull << 56) | bits);
-        for (uint64_t k = 0; k < ((bits + 63) >> 6); ++k)
-            put64(bt[k]);
+        for (uint64_t k = 0; k < nw; ++k)
+            put64(rec[(k / 3) * kRecWords + 2 + (k % 3)]);
     }
     put64((1ull << 56) | r.btnr_bits);
     for (uint64_t k = 0; k < btnr.size(); ++k)
         put64(btnr[k]);
-    uint64_t total_bits = rec[2 * r.nsuper + 1];
+    uint64_t total_bits = rec[kRecWords * r.nsuper + 1];
     std::vector<uint64_t> p(r.nsuper), rk, inv(r.nsuper);
     for (uint64_t g = 0; g < r.nsuper; ++g)
     {
-        p[g] = rec[2 * g + 1] & ~kInvBit;
-        inv[g] = (rec[2 * g + 1] & kInvBit) ? 1 : 0;
-        rk.push_back(rec[2 * g]);
+        p[g] = rec[g * kRecWords + 1] & ~kInvBit;
+        inv[g] = (rec[g * kRecWords + 1] & kInvBit) ? 1 : 0;
+        rk.push_back(rec[g * kRecWords]);
     }
     // a trailing superblock that only holds the dummy block keeps btnrp == 0 in the reference (:240-258)
     if (r.nsuper && (r.nsuper - 1) * kK * kBs >= r.size && r.size > 0)
         p[r.nsuper - 1] = 0;
     if (r.size % (kK * kBs))
-        rk.push_back(rec[2 * r.nsuper]);
+        rk.push_back(rec[kRecWords * r.nsuper]);
     else if (!rk.empty())
-        rk.back() = rec[2 * r.nsuper]; // m_rank[last] = total (:261-262)
+        rk.back() = rec[kRecWords * r.nsuper]; // m_rank[last] = total (:261-262)
     put_iv(p.data(), p.size(), hi(total_bits) + 1);
     put_iv(rk.data(), rk.size(), hi(r.ones) + 1);
     put_iv(inv.data(), inv.size(), 1);

@@ -166,28 +166,25 @@ int load_rrr(sdslgpu_handle * h, Reader & r, cudaStream_t s)
         return malformed("rrr_vector<63> (inconsistent sizes; only t_bs = 63, t_k = 32 is supported)");
     im.ones = rank.get(rank.size() - 1);
     im.btnr_bits = btnr.bits;
-    // fused per-superblock records; the closing record carries the total
-    std::vector<uint64_t> rec(2 * (im.nsuper + 1) + 2, 0);
+    SG_TRY(rrr_upload_tables(h, s));
+    std::vector<uint64_t> rk(im.nsuper), bp(im.nsuper);
+    std::vector<uint8_t> iv(im.nsuper);
     for (uint64_t g = 0; g < im.nsuper; ++g)
     {
-        rec[2 * g] = rank.get(g);
-        rec[2 * g + 1] = btnrp.get(g) | (inv.get(g) ? (1ull << 63) : 0);
+        rk[g] = rank.get(g);
+        bp[g] = btnrp.get(g);
+        iv[g] = (uint8_t)inv.get(g);
     }
-    rec[2 * im.nsuper] = im.ones;
     // the blob does not store the exact number of offset bits (m_btnr is padded to >= 64 bits); only its top bit
     // matters (it fixes the width of m_btnrp when serialising back), and m_btnrp's width preserves that
-    rec[2 * im.nsuper + 1] = btnrp.width ? (1ull << (btnrp.width - 1)) : 0;
-    SG_TRY(rrr_upload_tables(h, s));
-    uint64_t btw = 3 * im.nsuper + 2, nrw = ((btnr.bits + 63) >> 6) + 2;
-    std::vector<uint64_t> btp(btw, 0), nrp(nrw, 0);
-    std::memcpy(btp.data(), bt.words.data(), std::min<uint64_t>(bt.words.size(), btw) * 8);
+    uint64_t total_bits_hint = btnrp.width ? (1ull << (btnrp.width - 1)) : 0;
+    bt.words.resize(bt.words.size() + 2, 0);
+    SG_TRY(rrr_records_from_sdsl(h, bt.words.data(), im.nblocks, rk, bp, iv, total_bits_hint, s));
+    uint64_t nrw = ((btnr.bits + 63) >> 6) + 2;
+    std::vector<uint64_t> nrp(nrw, 0);
     std::memcpy(nrp.data(), btnr.words.data(), std::min<uint64_t>(btnr.words.size(), nrw) * 8);
-    SG_TRY(h->pool.alloc_t(&im.bt, btw));
     SG_TRY(h->pool.alloc_t(&im.btnr, nrw));
-    SG_TRY(h->pool.alloc_t(&im.records, rec.size()));
-    SG_CUDA(cudaMemcpyAsync(im.bt, btp.data(), btw * 8, cudaMemcpyHostToDevice, s));
     SG_CUDA(cudaMemcpyAsync(im.btnr, nrp.data(), nrw * 8, cudaMemcpyHostToDevice, s));
-    SG_CUDA(cudaMemcpyAsync(im.records, rec.data(), rec.size() * 8, cudaMemcpyHostToDevice, s));
     SG_CUDA(cudaStreamSynchronize(s));
     return rrr_build_hints(h, s);
 }
