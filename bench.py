@@ -278,12 +278,18 @@ def main():
                             "rank_qps": sample / (t1 - t0), "select_qps": sample / (t2 - t1)}
 
     if rank == 0:
-        def roof(bytes_per_q, ms):
+        traffic = {}
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp) and nbits == 1 << 33 and nq == int(1e8):  # measured for exactly this launch shape
+            tj = json.load(open(tp))
+            traffic = {k: v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in tj.items() if isinstance(v, dict)}
+
+        def roof(bytes_per_q, ms, kernel=None):
             a = nq * bytes_per_q / (ms * 1e-3) / 1e9
-            return {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": None,
+            return {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": traffic.get(kernel),
                     "peak_source": peak_src, "algorithmic_bytes_per_query": bytes_per_q, "kernel_ms": ms}
-        r_rank = dict(roof(RANK_BYTES, rank_ms), kernel="bv_rank_kernel<1,2>", qps=nq / (rank_ms * 1e-3))
-        r_sel = dict(roof(SELECT_BYTES, sel_ms), kernel="bv_select_kernel<1>", qps=nq / (sel_ms * 1e-3))
+        r_rank = dict(roof(RANK_BYTES, rank_ms, "bv_rank_kernel"), kernel="bv_rank_kernel<1,2>", qps=nq / (rank_ms * 1e-3))
+        r_sel = dict(roof(SELECT_BYTES, sel_ms, "bv_select_kernel"), kernel="bv_select_kernel<1>", qps=nq / (sel_ms * 1e-3))
         dominant = r_sel if sel_ms >= rank_ms else r_rank
         line = {
             "metric": "rank/select queries/s on 1 GiB bit_vector", "value": value, "unit": "queries/s",

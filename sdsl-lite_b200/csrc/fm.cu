@@ -11,6 +11,7 @@
 // root-to-leaf path, so their sector gathers are issued together.  Node table, paths, C[] and char2comp[]
 // (~19 KB) are staged in shared memory once per CTA.
 #include <algorithm>
+#include <cstdlib>
 #include <thread>
 
 #include "internal.h"
@@ -212,28 +213,42 @@ int csa_build_from_text(sdslgpu_handle * h, uint8_t const * text, uint64_t len, 
     CsaImage & c = h->csa;
     c.n = n;
     c.sa_dens = 32;
-    std::vector<uint8_t> t(n), bwt(n);
-    std::memcpy(t.data(), text, len);
-    t[len] = 0;
-    std::vector<uint64_t> samples((n + c.sa_dens - 1) / c.sa_dens);
-    if (n < (1ull << 31))
+    std::vector<uint8_t> bwt;
+    std::vector<uint64_t> samples;
+    // suffix array + BWT + samples: on the device (prefix doubling, gpu_sa.cu) unless SDSLGPU_HOST_SA=1 or the
+    // text does not fit 32-bit suffix indices / device memory, in which case the host SA-IS builder runs
+    int st = SDSLGPU_ENOTSUP;
+    char const * force_host = std::getenv("SDSLGPU_HOST_SA");
+    if (!(force_host && std::atoi(force_host) != 0))
+        st = gpu_suffix_array_bwt(text, len, c.sa_dens, bwt, samples, nullptr, s);
+    if (st == SDSLGPU_ENOTSUP)
     {
-        std::vector<int32_t> sa(n);
-        sais<uint8_t, int32_t>(t.data(), sa.data(), (int32_t)n, 255);
-        for (uint64_t i = 0; i < n; ++i)
-            bwt[i] = sa[i] ? t[sa[i] - 1] : t[n - 1];
-        for (uint64_t i = 0; i < n; i += c.sa_dens)
-            samples[i / c.sa_dens] = (uint64_t)sa[i];
+        std::vector<uint8_t> t(n);
+        bwt.assign(n, 0);
+        std::memcpy(t.data(), text, len);
+        t[len] = 0;
+        samples.assign((n + c.sa_dens - 1) / c.sa_dens, 0);
+        if (n < (1ull << 31))
+        {
+            std::vector<int32_t> sa(n);
+            sais<uint8_t, int32_t>(t.data(), sa.data(), (int32_t)n, 255);
+            for (uint64_t i = 0; i < n; ++i)
+                bwt[i] = sa[i] ? t[sa[i] - 1] : t[n - 1];
+            for (uint64_t i = 0; i < n; i += c.sa_dens)
+                samples[i / c.sa_dens] = (uint64_t)sa[i];
+        }
+        else
+        {
+            std::vector<int64_t> sa(n);
+            sais<uint8_t, int64_t>(t.data(), sa.data(), (int64_t)n, 255);
+            for (uint64_t i = 0; i < n; ++i)
+                bwt[i] = sa[i] ? t[sa[i] - 1] : t[n - 1];
+            for (uint64_t i = 0; i < n; i += c.sa_dens)
+                samples[i / c.sa_dens] = (uint64_t)sa[i];
+        }
     }
-    else
-    {
-        std::vector<int64_t> sa(n);
-        sais<uint8_t, int64_t>(t.data(), sa.data(), (int64_t)n, 255);
-        for (uint64_t i = 0; i < n; ++i)
-            bwt[i] = sa[i] ? t[sa[i] - 1] : t[n - 1];
-        for (uint64_t i = 0; i < n; i += c.sa_dens)
-            samples[i / c.sa_dens] = (uint64_t)sa[i];
-    }
+    else if (st != SDSLGPU_OK)
+        return st;
     // byte_alphabet (csa_alphabet_strategy.hpp:175-212)
     FmTables & tab = c.host_tab;
     std::memset(&tab, 0, sizeof(tab));

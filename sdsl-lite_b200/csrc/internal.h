@@ -266,6 +266,9 @@ int sd_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64
 int sd_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 int sd_access_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 int sd_serialize_low_high(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
+// gpu_sa.cu
+int gpu_suffix_array_bwt(uint8_t const * text_host, uint64_t len, uint32_t dens, std::vector<uint8_t> & bwt, std::vector<uint64_t> & samples, uint32_t * rounds_out,
+                         cudaStream_t s);
 // fm.cu
 int csa_build_from_text(sdslgpu_handle * h, uint8_t const * text_host, uint64_t len, cudaStream_t s);
 int csa_upload(sdslgpu_handle * h, uint8_t const * bwt_host, uint64_t const * samples_host, uint64_t nsamples, cudaStream_t s);

@@ -89,3 +89,19 @@ def test_fm_device_buffers(pkg, oracle):
                 assert t[int(p) : int(p) + 20] == pats[int(k)]
         chk = oracle.csa(t)
         assert (host == chk.count(flat, off)).all()
+
+
+def test_gpu_suffix_array_matches_host_sais(pkg, monkeypatch):
+    """construction: the device prefix-doubling suffix sorter and the host SA-IS builder give the same index
+    (same counts, same locate order, same SA values) on random, repetitive and natural-language-like texts"""
+    rng = np.random.default_rng(31)
+    for name, t in texts.text_catalogue(zero_free=True, large=True):
+        pats = _patterns(t, rng, 300)
+        flat, off = pkg.csr_patterns(pats)
+        i = rng.integers(0, len(t) + 1, 3000, dtype=np.uint64)
+        monkeypatch.setenv("SDSLGPU_HOST_SA", "1")
+        with pkg.CsaWt(t) as a:
+            want = (a.count(flat, off), a.sa(i))
+        monkeypatch.delenv("SDSLGPU_HOST_SA")
+        with pkg.CsaWt(t) as b:
+            assert (b.count(flat, off) == want[0]).all() and (b.sa(i) == want[1]).all(), name
