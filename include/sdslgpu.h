@@ -164,6 +164,13 @@ int sdslgpu_fm_sa(const sdslgpu_handle *h, const uint64_t *i, uint64_t n, uint64
 int sdslgpu_fm_locate(const sdslgpu_handle *h, const uint8_t *pats, const uint64_t *pat_off, uint64_t n,
                       uint64_t *occ_off_out, uint64_t *occ_out, uint64_t occ_cap, uint64_t *total_out, void *stream);
 
+/* out[out_off[k] + j] = text[begin[k] + j] for j = 0 .. end[k] - begin[k]  (end INCLUSIVE, end[k] < size(); the
+ * sentinel at position size()-1 reads as 0).  out_off holds n+1 offsets chosen by the caller (normally the
+ * exclusive prefix sums of end-begin+1).  Replaces sdsl::extract(csa, begin, end) (suffix_array_algorithm.hpp:590-610)
+ * with csa.isa (suffix_array_helper.hpp:519-537) behind it. */
+int sdslgpu_fm_extract(const sdslgpu_handle *h, const uint64_t *begin, const uint64_t *end, uint64_t n,
+                       const uint64_t *out_off, uint8_t *out, void *stream);
+
 /* ---- construction parity / interchange ------------------------------------------------------ */
 
 /* Copies the SDSL-format serialisation of one component of a KIND_BV handle into `buf`

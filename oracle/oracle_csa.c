@@ -211,6 +211,40 @@ void orc_csa_sa_batch(const orc_csa *c, const uint64_t *i, uint64_t n, uint64_t 
         out[k] = orc_csa_sa(c, i[k]);
 }
 
+/* ISA[i] from the samples (suffix_array_helper.hpp:519-537, csa_sampling_strategy.hpp:795-800 sample_qeq) */
+uint64_t orc_csa_isa(const orc_csa *c, uint64_t i)
+{
+    uint64_t ci = (i / ISA_DENS + 1) % c->isa_sample.size, pos = ci * ISA_DENS, r = orc_iv_get(&c->isa_sample, ci), steps;
+    steps = pos < i ? pos + c->n - i : pos - i;
+    while (steps--) {
+        uint64_t sym, j = orc_wt_huff_inverse_select(c->wt, r, &sym);
+        r = c->C[c->char2comp[sym]] + j;
+    }
+    return r;
+}
+
+/* extract(csa, begin, end) for the LF-based CSA (suffix_array_algorithm.hpp:590-610): text[begin..end] inclusive */
+void orc_csa_extract(const orc_csa *c, uint64_t begin, uint64_t end, uint8_t *out)
+{
+    uint64_t steps = end - begin + 1, order = orc_csa_isa(c, end), k;
+    /* first_row_symbol(order): the symbol whose C-bucket contains `order` (suffix_array_helper.hpp) */
+    for (k = 0; k + 1 < c->sigma && c->C[k + 1] <= order; ++k)
+        ;
+    out[--steps] = c->comp2char[k];
+    while (steps != 0) {
+        uint64_t sym, j = orc_wt_huff_inverse_select(c->wt, order, &sym);
+        order = c->C[c->char2comp[sym]] + j;
+        out[--steps] = (uint8_t)sym;
+    }
+}
+
+void orc_csa_extract_batch(const orc_csa *c, const uint64_t *begin, const uint64_t *end, uint64_t n, const uint64_t *out_off, uint8_t *out)
+{
+    uint64_t k;
+    for (k = 0; k < n; ++k)
+        orc_csa_extract(c, begin[k], end[k], out + out_off[k]);
+}
+
 /* csa_wt.hpp:389-402 + csa_alphabet_strategy.hpp:258-268 */
 uint64_t orc_csa_serialize(const orc_csa *c, uint8_t *out, uint64_t cap)
 {

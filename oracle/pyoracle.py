@@ -118,6 +118,8 @@ class Oracle:
         L.orc_csa_sa_batch.argtypes = [C.c_void_p, u64p, C.c_uint64, u64p]
         L.orc_csa_serialize.restype = C.c_uint64
         L.orc_csa_serialize.argtypes = [C.c_void_p, u8p, C.c_uint64]
+        L.orc_csa_extract_batch.restype = None
+        L.orc_csa_extract_batch.argtypes = [C.c_void_p, u64p, u64p, C.c_uint64, u64p, u8p]
 
         for kind in ("rrr", "sd"):
             getattr(L, f"orc_{kind}_build").restype = C.c_void_p
@@ -358,6 +360,15 @@ class OracleCsa:
 
     def serialize(self):
         return _blob(self.L.orc_csa_serialize, self.h)
+
+    def extract(self, begin, end):
+        """text[begin[k] .. end[k]] (inclusive) for every k -> (offsets uint64[n+1], bytes)"""
+        begin, end = _u64(begin), _u64(end)
+        off = np.zeros(len(begin) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(end - begin + np.uint64(1), dtype=np.uint64)
+        out = np.zeros(max(int(off[-1]), 1), dtype=np.uint8)
+        self.L.orc_csa_extract_batch(self.h, _p64(begin), _p64(end), len(begin), _p64(off), _p8(out))
+        return off, out[: int(off[-1])]
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -286,6 +286,7 @@ _SIGNATURES += [
     ("sdslgpu_fm_count", C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, vp]),
     ("sdslgpu_fm_sa", C.c_int, [vp, vp, C.c_uint64, vp, vp]),
     ("sdslgpu_fm_locate", C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, C.c_uint64, u64p, vp]),
+    ("sdslgpu_fm_extract", C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, vp]),
 ]
 
 
@@ -327,6 +328,16 @@ class CsaWt(_Handle, _WaveletTreeOps):
         po, o, _k = _out_like(i, n)
         _check(lib().sdslgpu_fm_sa(self._h, p, n, po, _stream_ptr(stream, i)))
         return o
+
+    def extract(self, begin, end, stream=None):
+        """text[begin[k] .. end[k]] (inclusive) for every k -> (offsets uint64[n+1], uint8 bytes); host arrays"""
+        b = np.ascontiguousarray(begin, dtype=np.uint64)
+        e = np.ascontiguousarray(end, dtype=np.uint64)
+        off = np.zeros(len(b) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(e - b + np.uint64(1), dtype=np.uint64)
+        out = np.zeros(max(int(off[-1]), 1), dtype=np.uint8)
+        _check(lib().sdslgpu_fm_extract(self._h, b.ctypes.data, e.ctypes.data, len(b), off.ctypes.data, out.ctypes.data, _stream_ptr(stream, b)))
+        return off, out[: int(off[-1])]
 
     def locate(self, flat, off, stream=None):
         """-> (occ_off uint64[n+1], occ uint64[total]) with each pattern's occurrences in suffix-array order"""

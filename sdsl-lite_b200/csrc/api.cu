@@ -959,6 +959,36 @@ extern "C"
         });
     }
 
+    int sdslgpu_fm_extract(const sdslgpu_handle * h, const uint64_t * begin, const uint64_t * end, uint64_t n, const uint64_t * out_off, uint8_t * out, void * stream)
+    {
+        SG_TRY(check_handle(h));
+        if (h->kind != SDSLGPU_KIND_CSA_WT)
+        {
+            set_error("sdslgpu_fm_extract: handle is not a CSA");
+            return SDSLGPU_ENOTSUP;
+        }
+        if (n == 0)
+            return SDSLGPU_OK;
+        if (!begin || !end || !out_off || !out)
+        {
+            set_error("sdslgpu_fm_extract: null argument");
+            return SDSLGPU_EINVAL;
+        }
+        DeviceGuard g(h->device);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        StagedCall sc(h->device, s);
+        uint64_t const *d_b = nullptr, *d_e = nullptr, *d_off = nullptr;
+        uint8_t * d_out = nullptr;
+        uint64_t total = 0;
+        SG_TRY(sc.in(begin, n * 8, &d_b));
+        SG_TRY(sc.in(end, n * 8, &d_e));
+        SG_TRY(sc.in(out_off, (n + 1) * 8, &d_off));
+        SG_TRY(sc.peek_u64(out_off, n, &total));
+        SG_TRY(sc.out(out, total, &d_out));
+        SG_TRY(fm_extract_device(h, d_b, d_e, d_off, n, d_out, s));
+        return sc.finish();
+    }
+
     int sdslgpu_fm_locate(const sdslgpu_handle * h,
                           const uint8_t * pats,
                           const uint64_t * pat_off,

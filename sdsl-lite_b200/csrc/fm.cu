@@ -197,6 +197,64 @@ __global__ void __launch_bounds__(kThreads) fm_locate_fill_kernel(BvView const b
     }
 }
 
+// extract(csa, begin, end) (suffix_array_algorithm.hpp:590-610): text[begin..end] by walking LF backwards from
+// ISA[end]; ISA[end] itself is reached from the next ISA sample (suffix_array_helper.hpp:519-537).  One thread
+// per requested range; the chain is sequential, the batch is the parallelism.
+__global__ void __launch_bounds__(kThreads) fm_extract_kernel(BvView const bv,
+                                                              WtTree const * __restrict__ tree,
+                                                              FmTables const * __restrict__ tab,
+                                                              uint64_t const * __restrict__ isa_samples,
+                                                              uint64_t nisa,
+                                                              uint32_t isa_dens,
+                                                              uint64_t n,
+                                                              uint64_t const * __restrict__ begin,
+                                                              uint64_t const * __restrict__ end,
+                                                              uint64_t const * __restrict__ out_off,
+                                                              uint64_t cnt,
+                                                              uint8_t * __restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FmSmem * sm = reinterpret_cast<FmSmem *>(smem_raw);
+    stage_fm(tree, tab, sm);
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += stride)
+    {
+        uint64_t b = begin[q], e = end[q];
+        if (e >= n || b > e)
+            continue; // out of domain: the caller sized the output from (begin, end); nothing is written
+        uint8_t * dst = out + out_off[q];
+        // ISA[e]: rightmost... the next sample at or after e, then LF back (sample_qeq, csa_sampling_strategy.hpp:795-800)
+        uint64_t ci = (e / isa_dens + 1) % nisa, pos = ci * isa_dens;
+        uint64_t order = __ldg(isa_samples + ci);
+        uint64_t back = pos < e ? pos + n - e : pos - e;
+        while (back--)
+        {
+            uint32_t sym;
+            uint64_t j = wt_inverse_select_one(bv, &sm->tree, order, sym);
+            order = sm->tab.C[sm->tab.char2comp[sym]] + j;
+        }
+        uint64_t steps = e - b + 1;
+        // first_row_symbol(order): the symbol whose C-bucket holds `order`
+        uint32_t lo = 0, hi = sm->tab.sigma;
+        while (hi - lo > 1)
+        {
+            uint32_t mid = (lo + hi) >> 1;
+            if (sm->tab.C[mid] <= order)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        dst[--steps] = sm->tab.comp2char[lo];
+        while (steps != 0)
+        {
+            uint32_t sym;
+            uint64_t j = wt_inverse_select_one(bv, &sm->tree, order, sym);
+            order = sm->tab.C[sm->tab.char2comp[sym]] + j;
+            dst[--steps] = (uint8_t)sym;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host: construction
 // ------------------------------------------------------------------------------------------------
@@ -214,13 +272,14 @@ int csa_build_from_text(sdslgpu_handle * h, uint8_t const * text, uint64_t len, 
     c.n = n;
     c.sa_dens = 32;
     std::vector<uint8_t> bwt;
-    std::vector<uint64_t> samples;
+    std::vector<uint64_t> samples, isa;
+    c.isa_dens = 64;
     // suffix array + BWT + samples: on the device (prefix doubling, gpu_sa.cu) unless SDSLGPU_HOST_SA=1 or the
     // text does not fit 32-bit suffix indices / device memory, in which case the host SA-IS builder runs
     int st = SDSLGPU_ENOTSUP;
     char const * force_host = std::getenv("SDSLGPU_HOST_SA");
     if (!(force_host && std::atoi(force_host) != 0))
-        st = gpu_suffix_array_bwt(text, len, c.sa_dens, bwt, samples, nullptr, s);
+        st = gpu_suffix_array_bwt(text, len, c.sa_dens, c.isa_dens, bwt, samples, isa, nullptr, s);
     if (st == SDSLGPU_ENOTSUP)
     {
         std::vector<uint8_t> t(n);
@@ -228,6 +287,7 @@ int csa_build_from_text(sdslgpu_handle * h, uint8_t const * text, uint64_t len, 
         std::memcpy(t.data(), text, len);
         t[len] = 0;
         samples.assign((n + c.sa_dens - 1) / c.sa_dens, 0);
+        isa.assign((n - 1) / c.isa_dens + 1, 0);
         if (n < (1ull << 31))
         {
             std::vector<int32_t> sa(n);
@@ -236,6 +296,9 @@ int csa_build_from_text(sdslgpu_handle * h, uint8_t const * text, uint64_t len, 
                 bwt[i] = sa[i] ? t[sa[i] - 1] : t[n - 1];
             for (uint64_t i = 0; i < n; i += c.sa_dens)
                 samples[i / c.sa_dens] = (uint64_t)sa[i];
+            for (uint64_t i = 0; i < n; ++i)
+                if ((uint64_t)sa[i] % c.isa_dens == 0)
+                    isa[(uint64_t)sa[i] / c.isa_dens] = i;
         }
         else
         {
@@ -245,6 +308,9 @@ int csa_build_from_text(sdslgpu_handle * h, uint8_t const * text, uint64_t len, 
                 bwt[i] = sa[i] ? t[sa[i] - 1] : t[n - 1];
             for (uint64_t i = 0; i < n; i += c.sa_dens)
                 samples[i / c.sa_dens] = (uint64_t)sa[i];
+            for (uint64_t i = 0; i < n; ++i)
+                if ((uint64_t)sa[i] % c.isa_dens == 0)
+                    isa[(uint64_t)sa[i] / c.isa_dens] = i;
         }
     }
     else if (st != SDSLGPU_OK)
@@ -267,14 +333,25 @@ int csa_build_from_text(sdslgpu_handle * h, uint8_t const * text, uint64_t len, 
     for (uint32_t k = 1; k <= sigma; ++k)
         tab.C[k] += tab.C[k - 1];
     tab.sigma = sigma;
-    return csa_upload(h, bwt.data(), samples.data(), samples.size(), s);
+    return csa_upload(h, bwt.data(), samples.data(), samples.size(), isa.data(), isa.size(), s);
 }
 
 // uploads the CSA parts; the wavelet tree of the BWT is built by the wt_huff path
-int csa_upload(sdslgpu_handle * h, uint8_t const * bwt, uint64_t const * samples, uint64_t nsamples, cudaStream_t s)
+int csa_upload_isa(sdslgpu_handle * h, uint64_t const * isa, uint64_t nisa, cudaStream_t s)
+{
+    CsaImage & c = h->csa;
+    c.nisa = nisa;
+    SG_TRY(h->pool.alloc_t(&c.isa_samples, nisa + 1));
+    SG_CUDA(cudaMemcpyAsync(c.isa_samples, isa, nisa * 8, cudaMemcpyHostToDevice, s));
+    SG_CUDA(cudaStreamSynchronize(s));
+    return SDSLGPU_OK;
+}
+
+int csa_upload(sdslgpu_handle * h, uint8_t const * bwt, uint64_t const * samples, uint64_t nsamples, uint64_t const * isa, uint64_t nisa, cudaStream_t s)
 {
     CsaImage & c = h->csa;
     SG_TRY(wt_huff_build_from_text(h, bwt, c.n, s));
+    SG_TRY(csa_upload_isa(h, isa, nisa, s));
     c.nsamples = nsamples;
     SG_TRY(h->pool.alloc_t(&c.samples, nsamples + 1));
     SG_CUDA(cudaMemcpyAsync(c.samples, samples, nsamples * 8, cudaMemcpyHostToDevice, s));
@@ -303,6 +380,16 @@ int fm_sa_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t cnt, u
     if (cnt == 0)
         return SDSLGPU_OK;
     fm_sa_kernel<<<grid_for(cnt), kThreads, kFmSmem, s>>>(bv_view(h->wt.bv), h->wt.tree, h->csa.tab, h->csa.samples, h->csa.sa_dens, h->csa.n, idx, cnt, out);
+    SG_CUDA(cudaGetLastError());
+    return SDSLGPU_OK;
+}
+
+int fm_extract_device(sdslgpu_handle const * h, uint64_t const * begin, uint64_t const * end, uint64_t const * out_off, uint64_t n, uint8_t * out, cudaStream_t s)
+{
+    if (n == 0)
+        return SDSLGPU_OK;
+    fm_extract_kernel<<<grid_for(n), kThreads, kFmSmem, s>>>(bv_view(h->wt.bv), h->wt.tree, h->csa.tab, h->csa.isa_samples, h->csa.nisa, h->csa.isa_dens, h->csa.n, begin, end,
+                                                              out_off, n, out);
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
 }

@@ -58,7 +58,14 @@ __global__ void __launch_bounds__(kThreads) sa_next_keys_kernel(uint32_t const *
 }
 
 __global__ void __launch_bounds__(kThreads)
-    sa_bwt_kernel(uint8_t const * __restrict__ t, uint32_t const * __restrict__ sa, uint64_t n, uint32_t dens, uint8_t * __restrict__ bwt, uint64_t * __restrict__ samples)
+    sa_bwt_kernel(uint8_t const * __restrict__ t,
+                  uint32_t const * __restrict__ sa,
+                  uint64_t n,
+                  uint32_t dens,
+                  uint32_t isa_dens,
+                  uint8_t * __restrict__ bwt,
+                  uint64_t * __restrict__ samples,
+                  uint64_t * __restrict__ isa_samples)
 {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n)
@@ -67,6 +74,8 @@ __global__ void __launch_bounds__(kThreads)
     bwt[j] = p ? t[p - 1] : t[n - 1]; // construct_bwt.hpp:53-60
     if (j % dens == 0)
         samples[j / dens] = p; // csa_sampling_strategy.hpp:98-115
+    if (p % isa_dens == 0)
+        isa_samples[p / isa_dens] = j; // csa_sampling_strategy.hpp:758-779
 }
 
 namespace
@@ -94,20 +103,28 @@ struct Buf
 // text_host: len zero-free bytes.  Outputs (host): bwt[len+1], samples[ceil((len+1)/dens)].
 // Returns SDSLGPU_ENOTSUP when the text is too long for 32-bit suffix indices or the device lacks memory, so the
 // caller can fall back to the host SA-IS builder.
-int gpu_suffix_array_bwt(uint8_t const * text_host, uint64_t len, uint32_t dens, std::vector<uint8_t> & bwt, std::vector<uint64_t> & samples, uint32_t * rounds_out, cudaStream_t s)
+int gpu_suffix_array_bwt(uint8_t const * text_host,
+                         uint64_t len,
+                         uint32_t dens,
+                         uint32_t isa_dens,
+                         std::vector<uint8_t> & bwt,
+                         std::vector<uint64_t> & samples,
+                         std::vector<uint64_t> & isa_samples,
+                         uint32_t * rounds_out,
+                         cudaStream_t s)
 {
     uint64_t n = len + 1;
     if (n >= (1ull << 32) - 1)
         return SDSLGPU_ENOTSUP;
     Buf t, k0, k1, v0, v1, rk, fl, hb, tmp, cubtmp, dbwt, dsamp;
-    uint64_t nsamp = (n + dens - 1) / dens;
+    uint64_t nsamp = (n + dens - 1) / dens, nisa = (n - 1) / isa_dens + 1;
     size_t cub_bytes = 0;
     cub::DoubleBuffer<uint64_t> dk(nullptr, nullptr);
     cub::DoubleBuffer<uint32_t> dv(nullptr, nullptr);
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, dk, dv, n, 0, 64, s);
     if (t.alloc(n + 16) != cudaSuccess || k0.alloc(n * 8) != cudaSuccess || k1.alloc(n * 8) != cudaSuccess || v0.alloc(n * 4) != cudaSuccess ||
         v1.alloc(n * 4) != cudaSuccess || rk.alloc(n * 4) != cudaSuccess || fl.alloc(n * 4) != cudaSuccess || hb.alloc((n + 1) * 8) != cudaSuccess ||
-        tmp.alloc(scan_tmp_words(n) * 8) != cudaSuccess || cubtmp.alloc(cub_bytes) != cudaSuccess)
+        tmp.alloc(scan_tmp_words(n) * 8) != cudaSuccess || cubtmp.alloc(cub_bytes) != cudaSuccess || dsamp.alloc(nisa * 8) != cudaSuccess)
     {
         cudaGetLastError();
         return SDSLGPU_ENOTSUP;
@@ -147,10 +164,12 @@ int gpu_suffix_array_bwt(uint8_t const * text_host, uint64_t len, uint32_t dens,
     // BWT + samples; the key buffers are free again: reuse one for the BWT bytes and the scan output for the samples
     uint8_t * d_bwt = reinterpret_cast<uint8_t *>(dk.Alternate());
     uint64_t * d_samp = hb.as<uint64_t>();
-    sa_bwt_kernel<<<blocks_for(n), kThreads, 0, s>>>(t.as<uint8_t>(), dv.Current(), n, dens, d_bwt, d_samp);
+    sa_bwt_kernel<<<blocks_for(n), kThreads, 0, s>>>(t.as<uint8_t>(), dv.Current(), n, dens, isa_dens, d_bwt, d_samp, dsamp.as<uint64_t>());
     SG_CUDA(cudaGetLastError());
     bwt.resize(n);
     samples.resize(nsamp);
+    isa_samples.resize(nisa);
+    SG_CUDA(cudaMemcpyAsync(isa_samples.data(), dsamp.p, nisa * 8, cudaMemcpyDeviceToHost, s));
     SG_CUDA(cudaMemcpyAsync(bwt.data(), d_bwt, n, cudaMemcpyDeviceToHost, s));
     SG_CUDA(cudaMemcpyAsync(samples.data(), d_samp, nsamp * 8, cudaMemcpyDeviceToHost, s));
     SG_CUDA(cudaStreamSynchronize(s));

@@ -208,6 +208,9 @@ struct CsaImage
     uint32_t sa_dens = 32;       // t_dens (csa_wt.hpp:50)
     uint64_t * samples = nullptr; // SA[0], SA[dens], ... widened to u64 (csa_sampling_strategy.hpp:98-115)
     uint64_t nsamples = 0;
+    uint32_t isa_dens = 64;           // t_inv_dens (csa_wt.hpp:51)
+    uint64_t * isa_samples = nullptr; // ISA[0], ISA[64], ... widened to u64 (csa_sampling_strategy.hpp:758-779)
+    uint64_t nisa = 0;
     FmTables * tab = nullptr; // device copy
     FmTables host_tab;
 };
@@ -267,11 +270,13 @@ int sd_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint
 int sd_access_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 int sd_serialize_low_high(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
 // gpu_sa.cu
-int gpu_suffix_array_bwt(uint8_t const * text_host, uint64_t len, uint32_t dens, std::vector<uint8_t> & bwt, std::vector<uint64_t> & samples, uint32_t * rounds_out,
-                         cudaStream_t s);
+int gpu_suffix_array_bwt(uint8_t const * text_host, uint64_t len, uint32_t dens, uint32_t isa_dens, std::vector<uint8_t> & bwt, std::vector<uint64_t> & samples,
+                         std::vector<uint64_t> & isa_samples, uint32_t * rounds_out, cudaStream_t s);
 // fm.cu
 int csa_build_from_text(sdslgpu_handle * h, uint8_t const * text_host, uint64_t len, cudaStream_t s);
-int csa_upload(sdslgpu_handle * h, uint8_t const * bwt_host, uint64_t const * samples_host, uint64_t nsamples, cudaStream_t s);
+int csa_upload(sdslgpu_handle * h, uint8_t const * bwt_host, uint64_t const * samples_host, uint64_t nsamples, uint64_t const * isa_host, uint64_t nisa, cudaStream_t s);
+int csa_upload_isa(sdslgpu_handle * h, uint64_t const * isa_host, uint64_t nisa, cudaStream_t s);
+int fm_extract_device(sdslgpu_handle const * h, uint64_t const * begin, uint64_t const * end, uint64_t const * out_off, uint64_t n, uint8_t * out, cudaStream_t s);
 int fm_count_device(sdslgpu_handle const * h, uint8_t const * pats, uint64_t const * off, uint64_t npat, uint64_t * cnt, uint64_t * l, cudaStream_t s);
 int fm_sa_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t cnt, uint64_t * out, cudaStream_t s);
 int fm_scan_counts_device(uint64_t const * cnt, uint64_t npat, uint64_t * occ_off, uint64_t * tmp, cudaStream_t s);

@@ -292,7 +292,19 @@ int load_csa(sdslgpu_handle * h, Reader & r, uint32_t sa_dens, cudaStream_t s)
     SG_TRY(h->pool.alloc_t(&c.tab, 1));
     SG_CUDA(cudaMemcpyAsync(c.tab, &c.host_tab, sizeof(FmTables), cudaMemcpyHostToDevice, s));
     SG_CUDA(cudaStreamSynchronize(s));
-    return SDSLGPU_OK;
+    // ISA samples (t_inv_dens is not stored: inferred from the sample count, csa_sampling_strategy.hpp:762-763)
+    std::vector<uint64_t> isav(isa.size() + 1, 0);
+    for (uint64_t k = 0; k < isa.size(); ++k)
+        isav[k] = isa.get(k);
+    c.isa_dens = 64;
+    if (isa.size() && isa.size() != (c.n - 1) / 64 + 1)
+    {
+        uint32_t d = 1;
+        while (d < (1u << 20) && (c.n - 1) / d + 1 != isa.size())
+            d <<= 1;
+        c.isa_dens = d;
+    }
+    return csa_upload_isa(h, isav.data(), isa.size(), s);
 }
 
 } // namespace

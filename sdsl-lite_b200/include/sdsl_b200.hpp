@@ -483,6 +483,15 @@ inline std::vector<uint64_t> locate(csa_wt const & csa, std::string const & pat)
     return locate(csa, pat.begin(), pat.end());
 }
 
+//! sdsl::extract(csa, begin, end): text[begin..end], end inclusive (suffix_array_algorithm.hpp:645-665)
+inline std::string extract(csa_wt const & csa, size_type begin, size_type end)
+{
+    std::string out(end - begin + 1, '\0');
+    uint64_t off[2] = {0, end - begin + 1};
+    check(sdslgpu_fm_extract(csa.image(), &begin, &end, 1, off, reinterpret_cast<uint8_t *>(&out[0]), nullptr), "extract");
+    return out;
+}
+
 //! batch count: one launch for the whole pattern set
 inline std::vector<uint64_t> count(csa_wt const & csa, std::vector<std::string> const & pats)
 {

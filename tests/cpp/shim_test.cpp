@@ -132,6 +132,7 @@ int main(int argc, char ** argv)
         EXPECT(sorted[j] == j); // SA is a permutation
     for (uint64_t j = 1; j <= t2.size(); ++j)
         EXPECT(t2.compare(sa[j - 1], std::string::npos, t2, sa[j], std::string::npos) < 0); // and sorted (csa_byte_test.cpp:162-175)
+    EXPECT(extract(csa, 12, 22) == "abracadabra" && extract(csa, 0, t2.size() - 1) == t2); // examples/fm-index.cpp:83
     auto cnts = count(csa, std::vector<std::string>{"a", "abra", "sim", "zzz"});
     EXPECT((cnts == std::vector<uint64_t>{(uint64_t)std::count(t2.begin(), t2.end(), 'a'), 6, 1, 0}));
     std::vector<uint64_t> occ_off, occs;

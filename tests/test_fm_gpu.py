@@ -105,3 +105,31 @@ def test_gpu_suffix_array_matches_host_sais(pkg, monkeypatch):
         monkeypatch.delenv("SDSLGPU_HOST_SA")
         with pkg.CsaWt(t) as b:
             assert (b.count(flat, off) == want[0]).all() and (b.sa(i) == want[1]).all(), name
+
+
+def test_extract(pkg, oracle, orc):
+    """sdsl::extract (suffix_array_algorithm.hpp:590-610) == the text itself, == the oracle / reference"""
+    rng = np.random.default_rng(41)
+    for name, t in texts.text_catalogue(zero_free=True, large=True):
+        n = len(t) + 1
+        full = t + b"\0"
+        b = rng.integers(0, n, 3000, dtype=np.uint64)
+        e = np.minimum(b + rng.integers(0, 100, 3000, dtype=np.uint64), np.uint64(n - 1))
+        b[0], e[0] = 0, min(n - 1, 5000)
+        with pkg.CsaWt(t) as csa:
+            off, out = csa.extract(b, e)
+            assert off[-1] == int((e - b + 1).sum())
+            for k in range(0, len(b), 7):
+                assert out[int(off[k]) : int(off[k + 1])].tobytes() == full[int(b[k]) : int(e[k]) + 1], (name, k)
+            if len(t) <= 200000:
+                o_off, o_out = oracle.csa(t).extract(b, e)
+                assert (o_off == off).all() and (o_out == out).all(), (name, "oracle")
+                if orc.ref_available():
+                    rc = orc.Ref().csa(t)
+                    for k in range(0, 40):
+                        assert rc.extract(int(b[k]), int(e[k])) == out[int(off[k]) : int(off[k + 1])].tobytes(), (name, "reference")
+            # an index ingested from the reference's serialised bytes extracts the same text
+            if len(t) <= 200000 and orc.ref_available():
+                with pkg.load_sdsl(orc.Ref().csa(t).serialize(), pkg.KIND_CSA_WT) as loaded:
+                    l_off, l_out = loaded.extract(b, e)
+                    assert (l_out == out).all(), (name, "loaded blob")
