@@ -105,3 +105,43 @@ def test_density_sweep_properties(pkg, oracle):
             assert (bv.rank(sub, 1) == o.rank(sub, 1)).all()
             ks = cases.select_queries(bv.arg_count(1), 10, 20000)
             assert (bv.select(ks, 1) == o.select(ks, 1)).all()
+
+
+@pytest.mark.parametrize("log_s", ["0", "3", "8", "10", "12"])
+def test_select_sparse_samples_and_interpolation(pkg, oracle, monkeypatch, log_s):
+    """the select paths large vectors use (sample stride > 64, interpolated first probe, bisect / walk-left /
+    walk-right repairs) forced onto the small catalogue — clustered and skewed vectors included — and compared
+    exhaustively with the oracle"""
+    monkeypatch.setenv("SDSLGPU_SELECT_LOG_S", log_s)
+    monkeypatch.setenv("SDSLGPU_SELECT_INTERP", "1")
+    for cid, w, nbits in cases.bitvector_catalogue(large=True):
+        o = oracle.bv(w, nbits)
+        with pkg.BitVector(w, nbits) as bv:
+            for b in (1, 0):
+                q = cases.select_queries(bv.arg_count(b), 13, 60000)
+                if len(q):
+                    assert (bv.select(q, b) == o.select(q, b)).all(), (cid, b, log_s)
+
+
+def test_select_clustered_large(pkg):
+    """2^31 bits, strongly clustered (long empty stretches, dense bursts): automatic stride + interpolation;
+    checked through rank(select(k)) == k-1 and bit(select(k)) == b for 2e6 queries per pattern"""
+    import torch
+
+    nbits = 1 << 31
+    nw = nbits // 64
+    g = torch.Generator(device="cuda").manual_seed(3)
+    words = torch.zeros(nw, dtype=torch.int64, device="cuda")
+    # bursts: 1/16 of the 64-Kbit regions are 90 % dense, the rest nearly empty
+    region = torch.rand(nw // 1024, device="cuda", generator=g) < (1 / 16)
+    dense = region.repeat_interleave(1024)
+    r = torch.randint(-(2**63), 2**63 - 1, (nw,), dtype=torch.int64, device="cuda", generator=g)
+    r2 = torch.randint(-(2**63), 2**63 - 1, (nw,), dtype=torch.int64, device="cuda", generator=g)
+    r3 = torch.randint(-(2**63), 2**63 - 1, (nw,), dtype=torch.int64, device="cuda", generator=g)
+    words = torch.where(dense, r | r2 | r3, r & r2 & r3 & torch.roll(r, 1) & torch.roll(r2, 1) & torch.roll(r3, 2))
+    with pkg.BitVector(words, nbits) as bv:
+        for b in (1, 0):
+            m = bv.arg_count(b)
+            k = torch.from_numpy(cases.select_queries(m, 17, 2_000_000).view(np.int64)).cuda()
+            p = bv.select(k, b)
+            assert bool((bv.rank(p, b) == k - 1).all()) and bool((bv.access(p) == b).all()), b

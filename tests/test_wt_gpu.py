@@ -68,3 +68,21 @@ def test_wt_huff_large_properties(pkg):
         # rank is monotone in i and increases by exactly [t[i] == c]
         c = sym.astype(np.uint8)
         assert (wt.rank(j + np.uint64(1), c) == rnk + np.uint64(1)).all()
+
+
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_wt_rank_level_synchronous_equals_per_query(pkg, oracle, monkeypatch, mode):
+    """both rank strategies (per-query kernel / one launch per tree depth) forced onto every text of the catalogue,
+    skewed Huffman shapes included, and compared with the oracle"""
+    monkeypatch.setenv("SDSLGPU_WT_LEVEL_SYNC", mode)
+    rng = np.random.default_rng(78)
+    for name, t in texts.text_catalogue(large=True):
+        with pkg.WtHuff(t) as wt:
+            i, c = texts.wt_queries(t, rng, min(80000, 20 * len(t) + 16))
+            want = oracle.wt_huff(t).rank(i, c)
+            i = i.copy()
+            i[1] = len(t) + 5  # out of domain stays NPOS through all passes
+            got = wt.rank(i, c)
+            assert got[1] == pkg.NPOS
+            got[1] = want[1]
+            assert (got == want).all(), (name, mode)
