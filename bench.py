@@ -166,6 +166,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = ge.load_package()
     nbits = 1 << args.nbits_log2
