@@ -53,6 +53,8 @@ extern "C" {
                                     rank_support_v m_basic_block table) and answer rank from it; the
                                     default is the sector-interleaved B200 layout */
 #define SDSLGPU_F_NO_SELECT 2u   /* skip building the select samples (rank-only handle) */
+#define SDSLGPU_F_RRR_BV 4u      /* wavelet trees / CSA: store the tree's bit vector as rrr_vector<63>, i.e.
+                                    wt_huff<rrr_vector<63>> and csa_wt<wt_huff<rrr_vector<63>>> (H0-compressed) */
 
 typedef struct sdslgpu_handle sdslgpu_handle;
 

@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(HERE, "libsdslgpu.so")
 
 OK, EINVAL, ENOMEM, ECUDA, ENOTSUP = 0, -1, -2, -3, -4
 NPOS = np.uint64(0xFFFFFFFFFFFFFFFF)
-F_DEFAULT, F_SDSL_LAYOUT, F_NO_SELECT = 0, 1, 2
+F_DEFAULT, F_SDSL_LAYOUT, F_NO_SELECT, F_RRR_BV = 0, 1, 2, 4
 KIND_BV, KIND_RRR63, KIND_SD, KIND_WT_HUFF, KIND_WT_INT, KIND_CSA_WT = 1, 2, 3, 4, 5, 6
 
 u64p = C.POINTER(C.c_uint64)

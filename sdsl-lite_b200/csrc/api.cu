@@ -258,16 +258,15 @@ struct StagedCall
     {}
     ~StagedCall()
     {
-        if (!temps.empty())
-            cudaStreamSynchronize(s);
+        // stream-ordered frees: no device-wide synchronisation, the pool recycles the blocks for the next call
         for (void * p : temps)
-            cudaFree(p);
+            cudaFreeAsync(p, s);
     }
     int tmp(uint64_t bytes, void ** p)
     {
-        cudaError_t e = cudaMalloc(p, bytes ? bytes : 8);
+        cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 8, s);
         if (e != cudaSuccess)
-            return cuda_fail(e, "cudaMalloc (staging)", __FILE__, __LINE__);
+            return cuda_fail(e, "cudaMallocAsync (staging)", __FILE__, __LINE__);
         temps.push_back(*p);
         return SDSLGPU_OK;
     }
@@ -366,6 +365,17 @@ static int new_handle(int kind, int device, uint32_t flags, sdslgpu_handle ** ou
     {
         set_error("device %d out of range (%d CUDA devices); there is no CPU fallback", device, ndev);
         return SDSLGPU_ECUDA;
+    }
+    {
+        // keep freed staging blocks cached in the device's stream-ordered pool instead of returning them to the
+        // driver at every synchronisation (the default release threshold is 0)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+        {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
     }
     sdslgpu_handle * h = new (std::nothrow) sdslgpu_handle;
     if (!h)

@@ -44,7 +44,8 @@ __device__ __forceinline__ void stage_fm(WtTree const * __restrict__ gt, FmTable
 }
 
 // (rank(a, c), rank(b, c)) on the BWT's wavelet tree: both chains descend the same path (wt_pc.hpp:371-399)
-__device__ __forceinline__ void wt_rank_pair(BvView const & bv, WtTree const * t, uint64_t sigma, uint32_t c, uint64_t & a, uint64_t & b)
+template <class Bits>
+__device__ __forceinline__ void wt_rank_pair(Bits const & bits, WtTree const * t, uint64_t sigma, uint32_t c, uint64_t & a, uint64_t & b)
 {
     if (t->c_to_leaf[c] == kUndef)
     {
@@ -59,15 +60,16 @@ __device__ __forceinline__ void wt_rank_pair(BvView const & bv, WtTree const * t
     for (uint32_t l = 0; l < len && (a | b); ++l, p >>= 1)
     {
         uint64_t base = t->bv_pos[v], br = t->bv_pos_rank[v];
-        uint64_t oa = bv_rank1(bv, base + a) - br;
-        uint64_t ob = bv_rank1(bv, base + b) - br;
+        uint64_t oa = bits.rank1(base + a) - br;
+        uint64_t ob = bits.rank1(base + b) - br;
         a = (p & 1) ? oa : a - oa;
         b = (p & 1) ? ob : b - ob;
         v = t->child[v][p & 1];
     }
 }
 
-__global__ void __launch_bounds__(kThreads) fm_count_kernel(BvView const bv,
+template <class Bits>
+__global__ void __launch_bounds__(kThreads) fm_count_kernel(Bits bits,
                                                             WtTree const * __restrict__ tree,
                                                             FmTables const * __restrict__ tab,
                                                             uint64_t n,     // csa.size() = text length + 1
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(kThreads) fm_count_kernel(BvView const bv,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FmSmem * sm = reinterpret_cast<FmSmem *>(smem_raw);
     stage_fm(tree, tab, sm);
+    bits.attach(smem_raw + sizeof(FmSmem));
     uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < npat; q += stride)
     {
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(kThreads) fm_count_kernel(BvView const bv,
                 else
                 {
                     uint64_t ra = l, rb = r + 1;
-                    wt_rank_pair(bv, &sm->tree, sigma, c, ra, rb);
+                    wt_rank_pair(bits, &sm->tree, sigma, c, ra, rb);
                     l = cb + ra;
                     r = cb + rb - 1;
                 }
@@ -128,13 +131,14 @@ __global__ void __launch_bounds__(kThreads) fm_count_kernel(BvView const bv,
 }
 
 // SA[i] by LF-walking to the next sampled index (csa_wt.hpp:363-381)
-__device__ __forceinline__ uint64_t fm_sa_one(BvView const & bv, FmSmem const * sm, uint64_t const * __restrict__ samples, uint32_t dens, uint64_t n, uint64_t i)
+template <class Bits>
+__device__ __forceinline__ uint64_t fm_sa_one(Bits const & bits, FmSmem const * sm, uint64_t const * __restrict__ samples, uint32_t dens, uint64_t n, uint64_t i)
 {
     uint64_t steps = 0;
     while (i % dens != 0)
     {
         uint32_t sym;
-        uint64_t j = wt_inverse_select_one(bv, &sm->tree, i, sym);
+        uint64_t j = wt_inverse_select_one(bits, &sm->tree, i, sym);
         i = sm->tab.C[sm->tab.char2comp[sym]] + j; // LF (suffix_array_helper.hpp:352-359)
         ++steps;
     }
@@ -142,7 +146,8 @@ __device__ __forceinline__ uint64_t fm_sa_one(BvView const & bv, FmSmem const * 
     return v < n ? v : v - n;
 }
 
-__global__ void __launch_bounds__(kThreads) fm_sa_kernel(BvView const bv,
+template <class Bits>
+__global__ void __launch_bounds__(kThreads) fm_sa_kernel(Bits bits,
                                                          WtTree const * __restrict__ tree,
                                                          FmTables const * __restrict__ tab,
                                                          uint64_t const * __restrict__ samples,
@@ -155,16 +160,18 @@ __global__ void __launch_bounds__(kThreads) fm_sa_kernel(BvView const bv,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FmSmem * sm = reinterpret_cast<FmSmem *>(smem_raw);
     stage_fm(tree, tab, sm);
+    bits.attach(smem_raw + sizeof(FmSmem));
     uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += stride)
     {
         uint64_t i = idx[q];
-        out[q] = (i < n) ? fm_sa_one(bv, sm, samples, dens, n, i) : SDSLGPU_NPOS;
+        out[q] = (i < n) ? fm_sa_one(bits, sm, samples, dens, n, i) : SDSLGPU_NPOS;
     }
 }
 
 // locate, phase 3: one thread per reported occurrence; occ[occ_off[k] + j] = SA[l[k] + j]  (SA order)
-__global__ void __launch_bounds__(kThreads) fm_locate_fill_kernel(BvView const bv,
+template <class Bits>
+__global__ void __launch_bounds__(kThreads) fm_locate_fill_kernel(Bits bits,
                                                                   WtTree const * __restrict__ tree,
                                                                   FmTables const * __restrict__ tab,
                                                                   uint64_t const * __restrict__ samples,
@@ -179,6 +186,7 @@ __global__ void __launch_bounds__(kThreads) fm_locate_fill_kernel(BvView const b
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FmSmem * sm = reinterpret_cast<FmSmem *>(smem_raw);
     stage_fm(tree, tab, sm);
+    bits.attach(smem_raw + sizeof(FmSmem));
     uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += stride)
     {
@@ -193,14 +201,15 @@ __global__ void __launch_bounds__(kThreads) fm_locate_fill_kernel(BvView const b
                 hi = mid - 1;
         }
         uint64_t j = o - __ldg(occ_off + lo);
-        occ[o] = fm_sa_one(bv, sm, samples, dens, n, __ldg(l + lo) + j);
+        occ[o] = fm_sa_one(bits, sm, samples, dens, n, __ldg(l + lo) + j);
     }
 }
 
 // extract(csa, begin, end) (suffix_array_algorithm.hpp:590-610): text[begin..end] by walking LF backwards from
 // ISA[end]; ISA[end] itself is reached from the next ISA sample (suffix_array_helper.hpp:519-537).  One thread
 // per requested range; the chain is sequential, the batch is the parallelism.
-__global__ void __launch_bounds__(kThreads) fm_extract_kernel(BvView const bv,
+template <class Bits>
+__global__ void __launch_bounds__(kThreads) fm_extract_kernel(Bits bits,
                                                               WtTree const * __restrict__ tree,
                                                               FmTables const * __restrict__ tab,
                                                               uint64_t const * __restrict__ isa_samples,
@@ -216,6 +225,7 @@ __global__ void __launch_bounds__(kThreads) fm_extract_kernel(BvView const bv,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FmSmem * sm = reinterpret_cast<FmSmem *>(smem_raw);
     stage_fm(tree, tab, sm);
+    bits.attach(smem_raw + sizeof(FmSmem));
     uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += stride)
     {
@@ -230,7 +240,7 @@ __global__ void __launch_bounds__(kThreads) fm_extract_kernel(BvView const bv,
         while (back--)
         {
             uint32_t sym;
-            uint64_t j = wt_inverse_select_one(bv, &sm->tree, order, sym);
+            uint64_t j = wt_inverse_select_one(bits, &sm->tree, order, sym);
             order = sm->tab.C[sm->tab.char2comp[sym]] + j;
         }
         uint64_t steps = e - b + 1;
@@ -248,7 +258,7 @@ __global__ void __launch_bounds__(kThreads) fm_extract_kernel(BvView const bv,
         while (steps != 0)
         {
             uint32_t sym;
-            uint64_t j = wt_inverse_select_one(bv, &sm->tree, order, sym);
+            uint64_t j = wt_inverse_select_one(bits, &sm->tree, order, sym);
             order = sm->tab.C[sm->tab.char2comp[sym]] + j;
             dst[--steps] = (uint8_t)sym;
         }
@@ -370,7 +380,7 @@ int fm_count_device(sdslgpu_handle const * h, uint8_t const * pats, uint64_t con
 {
     if (npat == 0)
         return SDSLGPU_OK;
-    fm_count_kernel<<<grid_for(npat), kThreads, kFmSmem, s>>>(bv_view(h->wt.bv), h->wt.tree, h->csa.tab, h->csa.n, h->wt.sigma, pats, off, npat, cnt, l);
+    SG_LAUNCH_BITS(fm_count_kernel, h->wt, grid_for(npat), kFmSmem, s, h->wt.tree, h->csa.tab, h->csa.n, h->wt.sigma, pats, off, npat, cnt, l);
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
 }
@@ -379,7 +389,7 @@ int fm_sa_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t cnt, u
 {
     if (cnt == 0)
         return SDSLGPU_OK;
-    fm_sa_kernel<<<grid_for(cnt), kThreads, kFmSmem, s>>>(bv_view(h->wt.bv), h->wt.tree, h->csa.tab, h->csa.samples, h->csa.sa_dens, h->csa.n, idx, cnt, out);
+    SG_LAUNCH_BITS(fm_sa_kernel, h->wt, grid_for(cnt), kFmSmem, s, h->wt.tree, h->csa.tab, h->csa.samples, h->csa.sa_dens, h->csa.n, idx, cnt, out);
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
 }
@@ -388,7 +398,7 @@ int fm_extract_device(sdslgpu_handle const * h, uint64_t const * begin, uint64_t
 {
     if (n == 0)
         return SDSLGPU_OK;
-    fm_extract_kernel<<<grid_for(n), kThreads, kFmSmem, s>>>(bv_view(h->wt.bv), h->wt.tree, h->csa.tab, h->csa.isa_samples, h->csa.nisa, h->csa.isa_dens, h->csa.n, begin, end,
+    SG_LAUNCH_BITS(fm_extract_kernel, h->wt, grid_for(n), kFmSmem, s, h->wt.tree, h->csa.tab, h->csa.isa_samples, h->csa.nisa, h->csa.isa_dens, h->csa.n, begin, end,
                                                               out_off, n, out);
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
@@ -405,7 +415,7 @@ int fm_locate_fill_device(sdslgpu_handle const * h, uint64_t const * l, uint64_t
 {
     if (total == 0 || npat == 0)
         return SDSLGPU_OK;
-    fm_locate_fill_kernel<<<grid_for(total), kThreads, kFmSmem, s>>>(bv_view(h->wt.bv), h->wt.tree, h->csa.tab, h->csa.samples, h->csa.sa_dens, h->csa.n, l, occ_off, npat,
+    SG_LAUNCH_BITS(fm_locate_fill_kernel, h->wt, grid_for(total), kFmSmem, s, h->wt.tree, h->csa.tab, h->csa.samples, h->csa.sa_dens, h->csa.n, l, occ_off, npat,
                                                                       total, occ);
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;

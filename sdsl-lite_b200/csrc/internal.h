@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/sdslgpu.h"
+#include "bits_access.cuh"
 #include "bv_device.cuh"
 #include "common.cuh"
 
@@ -157,10 +158,22 @@ struct alignas(16) WtTree
     uint32_t pad_;
 };
 
+// rrr_vector<63, int_vector<>, 32> (rrr_vector.hpp:101-109)
+struct RrrImage
+{
+    uint64_t size = 0, nblocks = 0, nsuper = 0, ones = 0, btnr_bits = 0;
+    uint64_t * btnr = nullptr;    // m_btnr
+    uint64_t * records = nullptr; // 64-byte record per superblock (rank, btnrp|invert, 32 classes, quarter sums) + closing record
+    void * tables = nullptr;      // RrrTables (binomials + code lengths), device copy
+    uint32_t * hint[2] = {nullptr, nullptr}; // select hints: superblock of every 8192nd b-bit
+};
+
 struct WtHuffImage
 {
     uint64_t size = 0, sigma = 0;
-    BvImage bv;               // the single concatenated bit vector m_bv (wt_pc.hpp:88-94)
+    BvImage bv;               // the single concatenated bit vector m_bv (wt_pc.hpp:88-94) as sector blocks ...
+    RrrImage rrr;             // ... or H0-compressed (wt_huff<rrr_vector<63>>) when use_rrr
+    bool use_rrr = false;
     WtTree * tree = nullptr;   // device copy
     WtTree host_tree;          // host copy (kept for serialisation / introspection)
 };
@@ -181,16 +194,6 @@ struct alignas(16) FmTables
     uint8_t comp2char[256];
     uint32_t sigma;
     uint32_t pad_;
-};
-
-// rrr_vector<63, int_vector<>, 32> (rrr_vector.hpp:101-109)
-struct RrrImage
-{
-    uint64_t size = 0, nblocks = 0, nsuper = 0, ones = 0, btnr_bits = 0;
-    uint64_t * btnr = nullptr;    // m_btnr
-    uint64_t * records = nullptr; // 64-byte record per superblock (rank, btnrp|invert, 32 classes, quarter sums) + closing record
-    void * tables = nullptr;      // RrrTables (binomials + code lengths), device copy
-    uint32_t * hint[2] = {nullptr, nullptr}; // select hints: superblock of every 8192nd b-bit
 };
 
 // sd_vector<> (sd_vector.hpp:155-163)
@@ -234,6 +237,47 @@ struct sdslgpu_handle
 
 namespace sdslgpu
 {
+inline RrrView rrr_view(RrrImage const & r)
+{
+    RrrView v;
+    v.size = r.size;
+    v.nblocks = r.nblocks;
+    v.nsuper = r.nsuper;
+    v.ones = r.ones;
+    v.btnr = r.btnr;
+    v.records = r.records;
+    v.tables = reinterpret_cast<RrrTables const *>(r.tables);
+    v.hint[0] = r.hint[0];
+    v.hint[1] = r.hint[1];
+    return v;
+}
+inline PlainBits plain_bits(WtHuffImage const & w)
+{
+    PlainBits b;
+    b.v = bv_view(w.bv);
+    return b;
+}
+inline RrrBits rrr_bits(WtHuffImage const & w)
+{
+    RrrBits b;
+    b.v = rrr_view(w.rrr);
+    b.t = nullptr;
+    return b;
+}
+// launches KERNEL<PlainBits> or KERNEL<RrrBits> (with the binomial tables appended to the dynamic shared memory)
+#define SG_LAUNCH_BITS(KERNEL, W, GRID, BASE_SMEM, STREAM, ...)                                                        \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if ((W).use_rrr)                                                                                               \
+        {                                                                                                              \
+            auto kfn__ = KERNEL<RrrBits>;                                                                              \
+            cudaFuncSetAttribute(kfn__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((BASE_SMEM) + RrrBits::kSmem)); \
+            kfn__<<<(GRID), kThreads, (BASE_SMEM) + RrrBits::kSmem, (STREAM)>>>(rrr_bits(W), __VA_ARGS__);             \
+        }                                                                                                              \
+        else                                                                                                           \
+            KERNEL<PlainBits><<<(GRID), kThreads, (BASE_SMEM), (STREAM)>>>(plain_bits(W), __VA_ARGS__);                \
+    } while (0)
+
 // bv.cu
 int bv_build(DevicePool & pool, BvImage & v, uint32_t flags, uint64_t const * words_host_or_dev, bool words_on_device, uint64_t nbits, cudaStream_t s);
 int bv_build_sdsl_rank_table(DevicePool & pool, BvImage & v, int b, cudaStream_t s);
@@ -257,9 +301,11 @@ int rrr_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint6
 int rrr_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 int rrr_access_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 int rrr_serialize(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
-int rrr_upload_tables(sdslgpu_handle * h, cudaStream_t s);
-int rrr_build_hints(sdslgpu_handle * h, cudaStream_t s);
-int rrr_records_from_sdsl(sdslgpu_handle * h, uint64_t const * bt_words, uint64_t nblocks, std::vector<uint64_t> const & rank,
+int rrr_upload_tables(DevicePool & pool, RrrImage & r, cudaStream_t s);
+int rrr_build_hints(DevicePool & pool, RrrImage & r, cudaStream_t s);
+int rrr_build_image(DevicePool & pool, RrrImage & r, uint64_t const * words_host_or_dev, bool on_device, uint64_t nbits, cudaStream_t s);
+int rrr_rank_image(RrrImage const & r, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
+int rrr_records_from_sdsl(DevicePool & pool, RrrImage & r, uint64_t const * bt_words, uint64_t nblocks, std::vector<uint64_t> const & rank,
                           std::vector<uint64_t> const & btnrp, std::vector<uint8_t> const & invert, uint64_t total_bits_hint, cudaStream_t s);
 // sdsl_format.cu
 int load_sdsl_blob(sdslgpu_handle * h, uint8_t const * blob, uint64_t nbytes, uint32_t sa_dens, cudaStream_t s);

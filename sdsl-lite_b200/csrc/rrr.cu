@@ -19,22 +19,11 @@
 // so rank = record + one read of the offset stream (m_btnr, unchanged), and the class scan is at most 7 steps.
 // C(n,k) for n,k <= 63 (32 KB) and the code lengths live in shared memory.
 #include "internal.h"
+#include "rrr_device.cuh"
 #include "scan.cuh"
 
 namespace sdslgpu
 {
-
-static constexpr uint32_t kBs = 63; // t_bs
-static constexpr uint32_t kK = 32;  // t_k
-static constexpr uint64_t kInvBit = 1ull << 63;
-static constexpr uint32_t kRecWords = 8;
-static constexpr uint32_t kHintShift = 13;
-
-struct RrrTables
-{
-    uint64_t binom[64][64]; // binom[n][k] = C(n, k), 0 for k > n   (rrr_helper.hpp:193-237)
-    uint8_t space[64];      // bits of an offset of class k: 0 if C(63,k) == 1 else hi(C(63,k)) + 1 (:286-293)
-};
 
 static RrrTables const & host_tables()
 {
@@ -64,129 +53,6 @@ static RrrTables const & host_tables()
         ready = true;
     }
     return t;
-}
-
-__device__ __forceinline__ void stage_rrr(RrrTables const * __restrict__ g, RrrTables * s)
-{
-    uint4 const * src = reinterpret_cast<uint4 const *>(g);
-    uint4 * dst = reinterpret_cast<uint4 *>(s);
-    for (uint32_t k = threadIdx.x; k < sizeof(RrrTables) / 16; k += blockDim.x)
-        dst[k] = __ldg(src + k);
-    __syncthreads();
-}
-
-// the block with k ones and offset nr, decoded up to `upto` positions (inverse of bin_to_nr, rrr_helper.hpp:346-366;
-// what decode_bit / decode_popcount / decode_select of rrr_helper.hpp:369-649 all compute from)
-__device__ __forceinline__ uint64_t rrr_decode(RrrTables const * t, uint32_t k, uint64_t nr, uint32_t upto)
-{
-    if (k == 0)
-        return 0;
-    if (k == kBs)
-        return (1ull << kBs) - 1;
-    uint64_t bin = 0;
-    for (uint32_t p = 0; p < upto && k; ++p)
-    {
-        uint64_t c = t->binom[kBs - 1 - p][k];
-        if (nr >= c)
-        {
-            nr -= c;
-            bin |= 1ull << p;
-            --k;
-        }
-    }
-    return bin;
-}
-
-struct RrrView
-{
-    uint64_t size;
-    uint64_t nblocks; // m_bt.size()
-    uint64_t nsuper;  // m_btnrp.size(); `records` has nsuper + 1 entries (the last holds the totals)
-    uint64_t ones;
-    uint64_t const * btnr;    // packed offsets (m_btnr)
-    uint64_t const * records; // 8 words per superblock, see the file header
-    RrrTables const * tables;
-    uint32_t const * hint[2]; // hint[b][j] = superblock holding the (j * 2^kHintShift + 1)-th b-bit (+ sentinels)
-};
-
-struct RrrRecord
-{
-    uint64_t w[kRecWords];
-};
-
-__device__ __forceinline__ void ld_record(uint64_t const * __restrict__ records, uint64_t g, RrrRecord & r)
-{
-    uint64_t const * p = records + g * kRecWords;
-    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.w[0]), "=l"(r.w[1]), "=l"(r.w[2]), "=l"(r.w[3]) : "l"(p));
-    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.w[4]), "=l"(r.w[5]), "=l"(r.w[6]), "=l"(r.w[7]) : "l"(p + 4));
-}
-
-// stored class of block j (0..31) of a record
-__host__ __device__ __forceinline__ uint32_t rec_class(uint64_t w2, uint64_t w3, uint64_t w4, uint32_t j)
-{
-    uint32_t bit = j * 6;
-    if (bit < 60)
-        return (uint32_t)(w2 >> bit) & 63u;
-    if (bit == 60)
-        return (uint32_t)((w2 >> 60) | (w3 << 4)) & 63u;
-    if (bit < 124)
-        return (uint32_t)(w3 >> (bit - 64)) & 63u;
-    if (bit == 126)
-        return (uint32_t)((w3 >> 62) | (w4 << 2)) & 63u;
-    return (uint32_t)(w4 >> (bit - 128)) & 63u;
-}
-
-// prefix sums over whole quarters (8 blocks each): q in 0..3
-__host__ __device__ __forceinline__ uint32_t rec_qones(uint64_t w5, uint32_t q)
-{
-    return q == 0 ? 0u : q == 1 ? (uint32_t)(w5 & 1023) : q == 2 ? (uint32_t)((w5 >> 10) & 1023) : (uint32_t)((w5 >> 20) & 2047);
-}
-__host__ __device__ __forceinline__ uint32_t rec_qbits(uint64_t w5, uint32_t q)
-{
-    return q == 0 ? 0u : q == 1 ? (uint32_t)((w5 >> 31) & 1023) : q == 2 ? (uint32_t)((w5 >> 41) & 1023) : (uint32_t)((w5 >> 51) & 2047);
-}
-
-// ones and offset bits of the first nblk (0..31) blocks of a superblock
-__device__ __forceinline__ void rec_prefix(RrrRecord const & r, RrrTables const * t, uint32_t nblk, bool inv, uint64_t & ones, uint64_t & p)
-{
-    uint32_t q = nblk >> 3;
-    ones += rec_qones(r.w[5], q);
-    p += rec_qbits(r.w[5], q);
-    for (uint32_t j = q << 3; j < nblk; ++j)
-    {
-        uint32_t c = rec_class(r.w[2], r.w[3], r.w[4], j);
-        ones += inv ? kBs - c : c;
-        p += t->space[c]; // space is symmetric: stored or real class give the same width (rrr_vector.hpp:528-541)
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// queries
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t rrr_rank1_one(RrrView const & v, RrrTables const * t, uint64_t i)
-{
-    uint64_t blk = i / kBs, g = blk / kK;
-    uint32_t off = (uint32_t)(i - blk * kBs);
-    RrrRecord r;
-    ld_record(v.records, g, r);
-    uint64_t d = r.w[6];
-    if (d == 0)
-        return r.w[0]; // uniform superblocks (rrr_vector.hpp:514-523); same result as the general path
-    if (d == (uint64_t)kBs * kK)
-        return r.w[0] + i - g * kK * kBs;
-    bool inv = (r.w[1] & kInvBit) != 0;
-    uint64_t p = r.w[1] & ~kInvBit, ones = r.w[0];
-    uint32_t nblk = (uint32_t)(blk - g * kK);
-    rec_prefix(r, t, nblk, inv, ones, p);
-    if (off == 0)
-        return ones;
-    uint32_t k = rec_class(r.w[2], r.w[3], r.w[4], nblk);
-    if (inv)
-        k = kBs - k;
-    uint32_t sp = t->space[k];
-    uint64_t nr = sp ? read_int(v.btnr, p, sp) : 0;
-    uint64_t bin = rrr_decode(t, k, nr, off);
-    return ones + __popcll(bin & ((1ull << off) - 1));
 }
 
 __global__ void __launch_bounds__(kThreads) rrr_rank_kernel(RrrView const v, int b, uint64_t const * __restrict__ idx, uint64_t n, uint64_t * __restrict__ out)
@@ -260,63 +126,7 @@ __global__ void __launch_bounds__(kThreads) rrr_select_kernel(RrrView const v, u
         else if (i > args)
             res = v.size; // the reference's in-band answer (rrr_vector.hpp:641-642, 686-689)
         else
-        {
-            // superblock g with count_before(g) < i <= count_before(g + 1)   (:643-655), bracketed by the hints
-            uint64_t hj = (i - 1) >> kHintShift;
-            uint64_t begin = __ldg(v.hint[B] + hj), end = (uint64_t)__ldg(v.hint[B] + hj + 1) + 1;
-            while (end - begin > 1)
-            {
-                uint64_t mid = (begin + end) >> 1;
-                uint64_t rk = __ldg(v.records + mid * kRecWords);
-                uint64_t c = B ? rk : mid * kBs * kK - rk;
-                if (c >= i)
-                    end = mid;
-                else
-                    begin = mid;
-            }
-            RrrRecord r;
-            ld_record(v.records, begin, r);
-            uint64_t cnt = B ? r.w[0] : begin * kBs * kK - r.w[0];
-            uint64_t d = r.w[6];
-            if (B ? (d == (uint64_t)kBs * kK) : (d == 0))
-                res = begin * kK * kBs + (i - cnt - 1); // all-ones / all-zeros superblock (:658-663, :703-706)
-            else
-            {
-                bool inv = (r.w[1] & kInvBit) != 0;
-                uint64_t p = r.w[1] & ~kInvBit;
-                // skip whole quarters, then scan at most 8 classes
-                uint32_t quarter = 0;
-#pragma unroll
-                for (uint32_t qq = 1; qq < 4; ++qq)
-                {
-                    uint32_t o = rec_qones(r.w[5], qq);
-                    uint64_t c = B ? o : qq * 8 * kBs - o;
-                    if (cnt + c < i)
-                        quarter = qq;
-                }
-                {
-                    uint32_t o = rec_qones(r.w[5], quarter);
-                    cnt += B ? o : quarter * 8 * kBs - o;
-                    p += rec_qbits(r.w[5], quarter);
-                }
-                uint32_t j = quarter << 3, k = 0, sp = 0;
-                for (;; ++j)
-                {
-                    k = rec_class(r.w[2], r.w[3], r.w[4], j);
-                    if (inv)
-                        k = kBs - k;
-                    sp = t->space[k];
-                    uint32_t c = B ? k : kBs - k;
-                    if (cnt + c >= i)
-                        break;
-                    cnt += c;
-                    p += sp;
-                }
-                uint64_t bin = rrr_decode(t, k, sp ? read_int(v.btnr, p, sp) : 0, kBs);
-                uint64_t x = B ? bin : (~bin & ((1ull << kBs) - 1));
-                res = (begin * kK + j) * kBs + sel64(x, (uint32_t)(i - cnt));
-            }
-        }
+            res = rrr_select_one<B>(v, t, i);
         st_stream_u64(out + q, res);
     }
 }
@@ -480,15 +290,14 @@ __global__ void __launch_bounds__(kThreads) rrr_hint_kernel(uint64_t const * __r
         hint[j] = (uint32_t)g;
 }
 
-int rrr_build_hints(sdslgpu_handle * h, cudaStream_t s)
+int rrr_build_hints(DevicePool & pool, RrrImage & r, cudaStream_t s)
 {
-    RrrImage & r = h->rrr;
     for (int b = 0; b < 2; ++b)
     {
         // zeros are counted over whole 2016-bit superblocks (the zero-extended tail included), like select0 does
         uint64_t args = b ? r.ones : r.nsuper * kBs * kK - r.ones;
         uint64_t nhint = args ? ((args - 1) >> kHintShift) + 1 : 0;
-        SG_TRY(h->pool.alloc_t(&r.hint[b], nhint + 2));
+        SG_TRY(pool.alloc_t(&r.hint[b], nhint + 2));
         std::vector<uint32_t> fill(nhint + 2, (uint32_t)(r.nsuper ? r.nsuper - 1 : 0));
         SG_CUDA(cudaMemcpyAsync(r.hint[b], fill.data(), (nhint + 2) * 4, cudaMemcpyHostToDevice, s));
         SG_CUDA(cudaStreamSynchronize(s));
@@ -505,50 +314,34 @@ int rrr_build_hints(sdslgpu_handle * h, cudaStream_t s)
     return SDSLGPU_OK;
 }
 
-static RrrView rrr_view(RrrImage const & r)
-{
-    RrrView v;
-    v.size = r.size;
-    v.nblocks = r.nblocks;
-    v.nsuper = r.nsuper;
-    v.ones = r.ones;
-    v.btnr = r.btnr;
-    v.records = r.records;
-    v.tables = reinterpret_cast<RrrTables const *>(r.tables);
-    v.hint[0] = r.hint[0];
-    v.hint[1] = r.hint[1];
-    return v;
-}
-
-int rrr_upload_tables(sdslgpu_handle * h, cudaStream_t s)
+int rrr_upload_tables(DevicePool & pool, RrrImage & r, cudaStream_t s)
 {
     RrrTables * d = nullptr;
-    SG_TRY(h->pool.alloc_t(&d, 1));
+    SG_TRY(pool.alloc_t(&d, 1));
     SG_CUDA(cudaMemcpyAsync(d, &host_tables(), sizeof(RrrTables), cudaMemcpyHostToDevice, s));
-    h->rrr.tables = d;
+    r.tables = d;
     return SDSLGPU_OK;
 }
 
-int rrr_build(sdslgpu_handle * h, uint64_t const * words_in, bool on_device, uint64_t nbits, cudaStream_t s)
+int rrr_build_image(DevicePool & pool, RrrImage & r, uint64_t const * words_in, bool on_device, uint64_t nbits, cudaStream_t s)
 {
-    RrrImage & r = h->rrr;
     r.size = nbits;
     r.nblocks = (nbits + kBs) / kBs;
     r.nsuper = (r.nblocks + kK - 1) / kK;
     uint64_t nwords = (nbits + 63) >> 6;
-    SG_TRY(rrr_upload_tables(h, s));
+    SG_TRY(rrr_upload_tables(pool, r, s));
     uint64_t * words = nullptr;
-    SG_TRY(h->pool.alloc_t(&words, nwords + 2));
+    SG_TRY(pool.alloc_t(&words, nwords + 2));
     SG_CUDA(cudaMemsetAsync(words + nwords, 0, 16, s));
     if (nwords)
         SG_CUDA(cudaMemcpyAsync(words, words_in, nwords * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
     uint32_t *blk_k = nullptr, *blk_sp = nullptr;
     uint64_t *ones_before = nullptr, *bits_before = nullptr, *tmp = nullptr;
-    SG_TRY(h->pool.alloc_t(&blk_k, r.nblocks));
-    SG_TRY(h->pool.alloc_t(&blk_sp, r.nblocks));
-    SG_TRY(h->pool.alloc_t(&ones_before, r.nblocks + 1));
-    SG_TRY(h->pool.alloc_t(&bits_before, r.nblocks + 1));
-    SG_TRY(h->pool.alloc_t(&tmp, scan_tmp_words(r.nblocks)));
+    SG_TRY(pool.alloc_t(&blk_k, r.nblocks));
+    SG_TRY(pool.alloc_t(&blk_sp, r.nblocks));
+    SG_TRY(pool.alloc_t(&ones_before, r.nblocks + 1));
+    SG_TRY(pool.alloc_t(&bits_before, r.nblocks + 1));
+    SG_TRY(pool.alloc_t(&tmp, scan_tmp_words(r.nblocks)));
     RrrTables const * tables = reinterpret_cast<RrrTables const *>(r.tables);
     rrr_classify_kernel<<<blocks_for(r.nblocks), kThreads, 0, s>>>(words, nbits, r.nblocks, tables, blk_k, blk_sp);
     SG_CUDA(cudaGetLastError());
@@ -561,8 +354,8 @@ int rrr_build(sdslgpu_handle * h, uint64_t const * words_in, bool on_device, uin
     r.ones = totals[0];
     r.btnr_bits = totals[1] > 64 ? totals[1] : 64; // m_btnr has at least 64 bits (:182)
     uint64_t btnr_words = ((r.btnr_bits + 63) >> 6) + 2;
-    SG_TRY(h->pool.alloc_t(&r.btnr, btnr_words));
-    SG_TRY(h->pool.alloc_t(&r.records, kRecWords * (r.nsuper + 1)));
+    SG_TRY(pool.alloc_t(&r.btnr, btnr_words));
+    SG_TRY(pool.alloc_t(&r.records, kRecWords * (r.nsuper + 1)));
     SG_CUDA(cudaMemsetAsync(r.btnr, 0, btnr_words * 8, s));
     rrr_superblock_kernel<<<blocks_for(r.nsuper + 1), kThreads, 0, s>>>(blk_k, blk_sp, ones_before, bits_before, nbits, r.nblocks, r.nsuper, tables, r.records);
     SG_CUDA(cudaGetLastError());
@@ -570,17 +363,22 @@ int rrr_build(sdslgpu_handle * h, uint64_t const * words_in, bool on_device, uin
                                                                                   reinterpret_cast<unsigned long long *>(r.btnr));
     SG_CUDA(cudaGetLastError());
     SG_CUDA(cudaStreamSynchronize(s));
-    h->pool.release(words);
-    h->pool.release(blk_k);
-    h->pool.release(blk_sp);
-    h->pool.release(ones_before);
-    h->pool.release(bits_before);
-    h->pool.release(tmp);
-    return rrr_build_hints(h, s);
+    pool.release(words);
+    pool.release(blk_k);
+    pool.release(blk_sp);
+    pool.release(ones_before);
+    pool.release(bits_before);
+    pool.release(tmp);
+    return rrr_build_hints(pool, r, s);
+}
+
+int rrr_build(sdslgpu_handle * h, uint64_t const * words_in, bool on_device, uint64_t nbits, cudaStream_t s)
+{
+    return rrr_build_image(h->pool, h->rrr, words_in, on_device, nbits, s);
 }
 
 // records from the reference's own arrays (ingest of a serialised rrr_vector): stored classes + samples
-int rrr_records_from_sdsl(sdslgpu_handle * h,
+int rrr_records_from_sdsl(DevicePool & pool, RrrImage & r,
                           uint64_t const * bt_words /* packed 6-bit stored classes */,
                           uint64_t nblocks,
                           std::vector<uint64_t> const & rank,
@@ -589,7 +387,6 @@ int rrr_records_from_sdsl(sdslgpu_handle * h,
                           uint64_t total_bits_hint,
                           cudaStream_t s)
 {
-    RrrImage & r = h->rrr;
     RrrTables const & t = host_tables();
     std::vector<uint64_t> rec(kRecWords * (r.nsuper + 1), 0);
     for (uint64_t g = 0; g < r.nsuper; ++g)
@@ -620,19 +417,24 @@ int rrr_records_from_sdsl(sdslgpu_handle * h,
     }
     rec[kRecWords * r.nsuper] = r.ones;
     rec[kRecWords * r.nsuper + 1] = total_bits_hint;
-    SG_TRY(h->pool.alloc_t(&r.records, rec.size()));
+    SG_TRY(pool.alloc_t(&r.records, rec.size()));
     SG_CUDA(cudaMemcpyAsync(r.records, rec.data(), rec.size() * 8, cudaMemcpyHostToDevice, s));
     SG_CUDA(cudaStreamSynchronize(s));
     return SDSLGPU_OK;
 }
 
-int rrr_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)
+int rrr_rank_image(RrrImage const & r, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)
 {
     if (n == 0)
         return SDSLGPU_OK;
-    rrr_rank_kernel<<<grid_for(n), kThreads, sizeof(RrrTables), s>>>(rrr_view(h->rrr), b, idx, n, out);
+    rrr_rank_kernel<<<grid_for(n), kThreads, sizeof(RrrTables), s>>>(rrr_view(r), b, idx, n, out);
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
+}
+
+int rrr_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)
+{
+    return rrr_rank_image(h->rrr, b, idx, n, out, s);
 }
 
 int rrr_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)

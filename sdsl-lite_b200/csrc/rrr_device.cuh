@@ -1,0 +1,223 @@
+// rrr_device.cuh — device-side view of an rrr_vector<63> image and its per-query primitives (rank, bit, select),
+// shared by rrr.cu (plain rank/select/access batches) and the wavelet-tree / FM-index kernels when the tree's
+// bit vector is stored H0-compressed (wt_huff<rrr_vector<63>>).  Layout: see rrr.cu.
+#pragma once
+#include "common.cuh"
+
+namespace sdslgpu
+{
+
+static constexpr uint32_t kBs = 63; // t_bs
+static constexpr uint32_t kK = 32;  // t_k
+static constexpr uint64_t kInvBit = 1ull << 63;
+static constexpr uint32_t kRecWords = 8;
+static constexpr uint32_t kHintShift = 13;
+
+struct RrrTables
+{
+    uint64_t binom[64][64]; // binom[n][k] = C(n, k), 0 for k > n   (rrr_helper.hpp:193-237)
+    uint8_t space[64];      // bits of an offset of class k: 0 if C(63,k) == 1 else hi(C(63,k)) + 1 (:286-293)
+};
+
+__device__ __forceinline__ void stage_rrr(RrrTables const * __restrict__ g, RrrTables * s)
+{
+    uint4 const * src = reinterpret_cast<uint4 const *>(g);
+    uint4 * dst = reinterpret_cast<uint4 *>(s);
+    for (uint32_t k = threadIdx.x; k < sizeof(RrrTables) / 16; k += blockDim.x)
+        dst[k] = __ldg(src + k);
+    __syncthreads();
+}
+
+// the block with k ones and offset nr, decoded up to `upto` positions (inverse of bin_to_nr, rrr_helper.hpp:346-366;
+// what decode_bit / decode_popcount / decode_select of rrr_helper.hpp:369-649 all compute from)
+__device__ __forceinline__ uint64_t rrr_decode(RrrTables const * t, uint32_t k, uint64_t nr, uint32_t upto)
+{
+    if (k == 0)
+        return 0;
+    if (k == kBs)
+        return (1ull << kBs) - 1;
+    uint64_t bin = 0;
+    for (uint32_t p = 0; p < upto && k; ++p)
+    {
+        uint64_t c = t->binom[kBs - 1 - p][k];
+        if (nr >= c)
+        {
+            nr -= c;
+            bin |= 1ull << p;
+            --k;
+        }
+    }
+    return bin;
+}
+
+struct RrrView
+{
+    uint64_t size;
+    uint64_t nblocks; // m_bt.size()
+    uint64_t nsuper;  // m_btnrp.size(); `records` has nsuper + 1 entries (the last holds the totals)
+    uint64_t ones;
+    uint64_t const * btnr;    // packed offsets (m_btnr)
+    uint64_t const * records; // 8 words per superblock, see the file header
+    RrrTables const * tables;
+    uint32_t const * hint[2]; // hint[b][j] = superblock holding the (j * 2^kHintShift + 1)-th b-bit (+ sentinels)
+};
+
+struct RrrRecord
+{
+    uint64_t w[kRecWords];
+};
+
+__device__ __forceinline__ void ld_record(uint64_t const * __restrict__ records, uint64_t g, RrrRecord & r)
+{
+    uint64_t const * p = records + g * kRecWords;
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.w[0]), "=l"(r.w[1]), "=l"(r.w[2]), "=l"(r.w[3]) : "l"(p));
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.w[4]), "=l"(r.w[5]), "=l"(r.w[6]), "=l"(r.w[7]) : "l"(p + 4));
+}
+
+// stored class of block j (0..31) of a record
+__host__ __device__ __forceinline__ uint32_t rec_class(uint64_t w2, uint64_t w3, uint64_t w4, uint32_t j)
+{
+    uint32_t bit = j * 6;
+    if (bit < 60)
+        return (uint32_t)(w2 >> bit) & 63u;
+    if (bit == 60)
+        return (uint32_t)((w2 >> 60) | (w3 << 4)) & 63u;
+    if (bit < 124)
+        return (uint32_t)(w3 >> (bit - 64)) & 63u;
+    if (bit == 126)
+        return (uint32_t)((w3 >> 62) | (w4 << 2)) & 63u;
+    return (uint32_t)(w4 >> (bit - 128)) & 63u;
+}
+
+// prefix sums over whole quarters (8 blocks each): q in 0..3
+__host__ __device__ __forceinline__ uint32_t rec_qones(uint64_t w5, uint32_t q)
+{
+    return q == 0 ? 0u : q == 1 ? (uint32_t)(w5 & 1023) : q == 2 ? (uint32_t)((w5 >> 10) & 1023) : (uint32_t)((w5 >> 20) & 2047);
+}
+__host__ __device__ __forceinline__ uint32_t rec_qbits(uint64_t w5, uint32_t q)
+{
+    return q == 0 ? 0u : q == 1 ? (uint32_t)((w5 >> 31) & 1023) : q == 2 ? (uint32_t)((w5 >> 41) & 1023) : (uint32_t)((w5 >> 51) & 2047);
+}
+
+// ones and offset bits of the first nblk (0..31) blocks of a superblock
+__device__ __forceinline__ void rec_prefix(RrrRecord const & r, RrrTables const * t, uint32_t nblk, bool inv, uint64_t & ones, uint64_t & p)
+{
+    uint32_t q = nblk >> 3;
+    ones += rec_qones(r.w[5], q);
+    p += rec_qbits(r.w[5], q);
+    for (uint32_t j = q << 3; j < nblk; ++j)
+    {
+        uint32_t c = rec_class(r.w[2], r.w[3], r.w[4], j);
+        ones += inv ? kBs - c : c;
+        p += t->space[c]; // space is symmetric: stored or real class give the same width (rrr_vector.hpp:528-541)
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// queries
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t rrr_rank1_one(RrrView const & v, RrrTables const * t, uint64_t i)
+{
+    uint64_t blk = i / kBs, g = blk / kK;
+    uint32_t off = (uint32_t)(i - blk * kBs);
+    RrrRecord r;
+    ld_record(v.records, g, r);
+    uint64_t d = r.w[6];
+    if (d == 0)
+        return r.w[0]; // uniform superblocks (rrr_vector.hpp:514-523); same result as the general path
+    if (d == (uint64_t)kBs * kK)
+        return r.w[0] + i - g * kK * kBs;
+    bool inv = (r.w[1] & kInvBit) != 0;
+    uint64_t p = r.w[1] & ~kInvBit, ones = r.w[0];
+    uint32_t nblk = (uint32_t)(blk - g * kK);
+    rec_prefix(r, t, nblk, inv, ones, p);
+    if (off == 0)
+        return ones;
+    uint32_t k = rec_class(r.w[2], r.w[3], r.w[4], nblk);
+    if (inv)
+        k = kBs - k;
+    uint32_t sp = t->space[k];
+    uint64_t nr = sp ? read_int(v.btnr, p, sp) : 0;
+    uint64_t bin = rrr_decode(t, k, nr, off);
+    return ones + __popcll(bin & ((1ull << off) - 1));
+}
+
+// rank1(pos) and the bit at pos (pos < size) from one record + one offset read
+__device__ __forceinline__ uint64_t rrr_rank1_and_bit(RrrView const & v, RrrTables const * t, uint64_t i, uint32_t & bit)
+{
+    uint64_t blk = i / kBs, g = blk / kK;
+    uint32_t off = (uint32_t)(i - blk * kBs);
+    RrrRecord r;
+    ld_record(v.records, g, r);
+    bool inv = (r.w[1] & kInvBit) != 0;
+    uint64_t p = r.w[1] & ~kInvBit, ones = r.w[0];
+    uint32_t nblk = (uint32_t)(blk - g * kK);
+    rec_prefix(r, t, nblk, inv, ones, p);
+    uint32_t k = rec_class(r.w[2], r.w[3], r.w[4], nblk);
+    if (inv)
+        k = kBs - k;
+    uint32_t sp = t->space[k];
+    uint64_t bin = rrr_decode(t, k, sp ? read_int(v.btnr, p, sp) : 0, off + 1);
+    bit = (uint32_t)(bin >> off) & 1u;
+    return ones + __popcll(bin & ((1ull << off) - 1));
+}
+
+// position of the i-th (1-based) B-bit, 1 <= i <= #B-bits (rrr_vector.hpp:639-726)
+template <int B>
+__device__ __forceinline__ uint64_t rrr_select_one(RrrView const & v, RrrTables const * t, uint64_t i)
+{
+    // superblock g with count_before(g) < i <= count_before(g + 1)   (:643-655), bracketed by the hints
+    uint64_t hj = (i - 1) >> kHintShift;
+    uint64_t begin = __ldg(v.hint[B] + hj), end = (uint64_t)__ldg(v.hint[B] + hj + 1) + 1;
+    while (end - begin > 1)
+    {
+        uint64_t mid = (begin + end) >> 1;
+        uint64_t rk = __ldg(v.records + mid * kRecWords);
+        uint64_t c = B ? rk : mid * kBs * kK - rk;
+        if (c >= i)
+            end = mid;
+        else
+            begin = mid;
+    }
+    RrrRecord r;
+    ld_record(v.records, begin, r);
+    uint64_t cnt = B ? r.w[0] : begin * kBs * kK - r.w[0];
+    uint64_t d = r.w[6];
+    if (B ? (d == (uint64_t)kBs * kK) : (d == 0))
+        return begin * kK * kBs + (i - cnt - 1); // all-ones / all-zeros superblock (:658-663, :703-706)
+    bool inv = (r.w[1] & kInvBit) != 0;
+    uint64_t p = r.w[1] & ~kInvBit;
+    // skip whole quarters, then scan at most 8 classes
+    uint32_t quarter = 0;
+#pragma unroll
+    for (uint32_t qq = 1; qq < 4; ++qq)
+    {
+        uint32_t o = rec_qones(r.w[5], qq);
+        uint64_t c = B ? o : qq * 8 * kBs - o;
+        if (cnt + c < i)
+            quarter = qq;
+    }
+    {
+        uint32_t o = rec_qones(r.w[5], quarter);
+        cnt += B ? o : quarter * 8 * kBs - o;
+        p += rec_qbits(r.w[5], quarter);
+    }
+    uint32_t j = quarter << 3, k = 0, sp = 0;
+    for (;; ++j)
+    {
+        k = rec_class(r.w[2], r.w[3], r.w[4], j);
+        if (inv)
+            k = kBs - k;
+        sp = t->space[k];
+        uint32_t c = B ? k : kBs - k;
+        if (cnt + c >= i)
+            break;
+        cnt += c;
+        p += sp;
+    }
+    uint64_t bin = rrr_decode(t, k, sp ? read_int(v.btnr, p, sp) : 0, kBs);
+    uint64_t x = B ? bin : (~bin & ((1ull << kBs) - 1));
+    return (begin * kK + j) * kBs + sel64(x, (uint32_t)(i - cnt));
+}
+
+} // namespace sdslgpu

@@ -166,7 +166,7 @@ int load_rrr(sdslgpu_handle * h, Reader & r, cudaStream_t s)
         return malformed("rrr_vector<63> (inconsistent sizes; only t_bs = 63, t_k = 32 is supported)");
     im.ones = rank.get(rank.size() - 1);
     im.btnr_bits = btnr.bits;
-    SG_TRY(rrr_upload_tables(h, s));
+    SG_TRY(rrr_upload_tables(h->pool, im, s));
     std::vector<uint64_t> rk(im.nsuper), bp(im.nsuper);
     std::vector<uint8_t> iv(im.nsuper);
     for (uint64_t g = 0; g < im.nsuper; ++g)
@@ -179,14 +179,14 @@ int load_rrr(sdslgpu_handle * h, Reader & r, cudaStream_t s)
     // matters (it fixes the width of m_btnrp when serialising back), and m_btnrp's width preserves that
     uint64_t total_bits_hint = btnrp.width ? (1ull << (btnrp.width - 1)) : 0;
     bt.words.resize(bt.words.size() + 2, 0);
-    SG_TRY(rrr_records_from_sdsl(h, bt.words.data(), im.nblocks, rk, bp, iv, total_bits_hint, s));
+    SG_TRY(rrr_records_from_sdsl(h->pool, im, bt.words.data(), im.nblocks, rk, bp, iv, total_bits_hint, s));
     uint64_t nrw = ((btnr.bits + 63) >> 6) + 2;
     std::vector<uint64_t> nrp(nrw, 0);
     std::memcpy(nrp.data(), btnr.words.data(), std::min<uint64_t>(btnr.words.size(), nrw) * 8);
     SG_TRY(h->pool.alloc_t(&im.btnr, nrw));
     SG_CUDA(cudaMemcpyAsync(im.btnr, nrp.data(), nrw * 8, cudaMemcpyHostToDevice, s));
     SG_CUDA(cudaStreamSynchronize(s));
-    return rrr_build_hints(h, s);
+    return rrr_build_hints(h->pool, im, s);
 }
 
 int load_sd(sdslgpu_handle * h, Reader & r, cudaStream_t s)

@@ -206,7 +206,8 @@ static void fill_bit_planes(uint8_t const * text, uint64_t n, WtTree const & tre
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) wt_rank_kernel(BvView const bv,
+template <class Bits>
+__global__ void __launch_bounds__(kThreads) wt_rank_kernel(Bits bits,
                                                            WtTree const * __restrict__ tree,
                                                            uint64_t size,
                                                            uint64_t sigma,
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(kThreads) wt_rank_kernel(BvView const bv,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WtTree * t = reinterpret_cast<WtTree *>(smem_raw);
     stage_tree(tree, t);
+    bits.attach(smem_raw + sizeof(WtTree));
     uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
     {
@@ -225,12 +227,13 @@ __global__ void __launch_bounds__(kThreads) wt_rank_kernel(BvView const bv,
         uint32_t c = qc[q];
         uint64_t r = SDSLGPU_NPOS;
         if (i <= size)
-            r = wt_rank_one(bv, t, sigma, i, c);
+            r = wt_rank_one(bits, t, sigma, i, c);
         st_stream_u64(out + q, r);
     }
 }
 
-__global__ void __launch_bounds__(kThreads) wt_access_kernel(BvView const bv,
+template <class Bits>
+__global__ void __launch_bounds__(kThreads) wt_access_kernel(Bits bits,
                                                              WtTree const * __restrict__ tree,
                                                              uint64_t size,
                                                              uint64_t const * __restrict__ qi,
@@ -241,6 +244,7 @@ __global__ void __launch_bounds__(kThreads) wt_access_kernel(BvView const bv,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WtTree * t = reinterpret_cast<WtTree *>(smem_raw);
     stage_tree(tree, t);
+    bits.attach(smem_raw + sizeof(WtTree));
     uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
     {
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(kThreads) wt_access_kernel(BvView const bv,
         if (i < size)
         {
             uint32_t sym;
-            r = wt_inverse_select_one(bv, t, i, sym);
+            r = wt_inverse_select_one(bits, t, i, sym);
             s = sym;
         }
         st_stream_u64(sym_out + q, s);
@@ -259,7 +263,8 @@ __global__ void __launch_bounds__(kThreads) wt_access_kernel(BvView const bv,
 }
 
 // select(i, c) (wt_pc.hpp:443-474): climb from the leaf; at each parent one select on m_bv
-__global__ void __launch_bounds__(kThreads) wt_select_kernel(BvView const bv,
+template <class Bits>
+__global__ void __launch_bounds__(kThreads) wt_select_kernel(Bits bits,
                                                              WtTree const * __restrict__ tree,
                                                              uint64_t size,
                                                              uint64_t sigma,
@@ -271,6 +276,7 @@ __global__ void __launch_bounds__(kThreads) wt_select_kernel(BvView const bv,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WtTree * t = reinterpret_cast<WtTree *>(smem_raw);
     stage_tree(tree, t);
+    bits.attach(smem_raw + sizeof(WtTree));
     uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
     {
@@ -299,9 +305,9 @@ __global__ void __launch_bounds__(kThreads) wt_select_kernel(BvView const bv,
                 {
                     v = t->parent[v];
                     if ((p & 0x8000000000000000ULL) == 0)
-                        r = bv_select<0>(bv, t->bv_pos[v] - t->bv_pos_rank[v] + r + 1) - t->bv_pos[v];
+                        r = bits.template select<0>(t->bv_pos[v] - t->bv_pos_rank[v] + r + 1) - t->bv_pos[v];
                     else
-                        r = bv_select<1>(bv, t->bv_pos_rank[v] + r + 1) - t->bv_pos[v];
+                        r = bits.template select<1>(t->bv_pos_rank[v] + r + 1) - t->bv_pos[v];
                 }
             }
         }
@@ -318,7 +324,11 @@ int wt_huff_upload(sdslgpu_handle * h, uint64_t size, uint64_t sigma, WtTree con
     w.size = size;
     w.sigma = sigma;
     w.host_tree = tree;
-    SG_TRY(bv_build(h->pool, w.bv, h->flags & ~SDSLGPU_F_NO_SELECT, bv_words, false, bv_bits, s));
+    w.use_rrr = (h->flags & SDSLGPU_F_RRR_BV) != 0;
+    if (w.use_rrr)
+        SG_TRY(rrr_build_image(h->pool, w.rrr, bv_words, false, bv_bits, s));
+    else
+        SG_TRY(bv_build(h->pool, w.bv, h->flags & ~SDSLGPU_F_NO_SELECT, bv_words, false, bv_bits, s));
     // inner nodes: bv_pos_rank = rank1(m_bv, bv_pos) (wt_helper.hpp:319-327), computed on the device
     uint32_t nn = tree.nnodes;
     if (nn)
@@ -330,7 +340,10 @@ int wt_huff_upload(sdslgpu_handle * h, uint64_t size, uint64_t sigma, WtTree con
         SG_TRY(h->pool.alloc_t(&d_pos, nn));
         SG_TRY(h->pool.alloc_t(&d_rk, nn));
         SG_CUDA(cudaMemcpyAsync(d_pos, pos.data(), nn * 8, cudaMemcpyHostToDevice, s));
-        SG_TRY(bv_rank_device(w.bv, 0, 1, d_pos, nn, d_rk, s));
+        if (w.use_rrr)
+            SG_TRY(rrr_rank_image(w.rrr, 1, d_pos, nn, d_rk, s));
+        else
+            SG_TRY(bv_rank_device(w.bv, 0, 1, d_pos, nn, d_rk, s));
         SG_CUDA(cudaMemcpyAsync(rk.data(), d_rk, nn * 8, cudaMemcpyDeviceToHost, s));
         SG_CUDA(cudaStreamSynchronize(s));
         h->pool.release(d_pos);
@@ -414,7 +427,8 @@ static size_t const kTreeSmem = sizeof(WtTree);
 // ------------------------------------------------------------------------------------------------
 static constexpr uint64_t kStateMask = (1ull << 48) - 1;
 
-__global__ void __launch_bounds__(kThreads) wt_rank_level_kernel(BvView const bv,
+template <class Bits>
+__global__ void __launch_bounds__(kThreads) wt_rank_level_kernel(Bits bits,
                                                                  WtTree const * __restrict__ tree,
                                                                  uint64_t size,
                                                                  uint32_t level,
@@ -427,6 +441,7 @@ __global__ void __launch_bounds__(kThreads) wt_rank_level_kernel(BvView const bv
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WtTree * t = reinterpret_cast<WtTree *>(smem_raw);
     stage_tree(tree, t);
+    bits.attach(smem_raw + sizeof(WtTree));
     uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
     {
@@ -457,7 +472,7 @@ __global__ void __launch_bounds__(kThreads) wt_rank_level_kernel(BvView const bv
         if (level < len && r != 0)
         {
             uint32_t bit = (uint32_t)(p >> level) & 1u;
-            uint64_t o = bv_rank1(bv, t->bv_pos[v] + r) - t->bv_pos_rank[v];
+            uint64_t o = bits.rank1(t->bv_pos[v] + r) - t->bv_pos_rank[v];
             r = bit ? o : r - o;
             v = t->child[v][bit];
         }
@@ -475,18 +490,18 @@ int wt_rank_device(sdslgpu_handle const * h, uint64_t const * i, uint8_t const *
     for (int k = 0; k < 256; ++k)
         if (w.host_tree.c_to_leaf[k] != kUndef)
             depth = std::max(depth, (uint32_t)(w.host_tree.path[k] >> 56));
-    bool level_sync = n >= (1u << 16) && depth >= 2 && depth <= 24 && w.sigma > 1 && w.bv.nbits < (1ull << 47);
+    bool level_sync = n >= (1u << 16) && depth >= 2 && depth <= 24 && w.sigma > 1 && (w.use_rrr ? w.rrr.size : w.bv.nbits) < (1ull << 47);
     if (char const * e = std::getenv("SDSLGPU_WT_LEVEL_SYNC")) // tuning knob for experiments
         level_sync = std::atoi(e) != 0 && depth >= 1 && w.sigma > 1;
     if (!level_sync)
     {
-        wt_rank_kernel<<<grid_for(n), kThreads, kTreeSmem, s>>>(bv_view(w.bv), w.tree, w.size, w.sigma, i, c, n, out);
+        SG_LAUNCH_BITS(wt_rank_kernel, w, grid_for(n), kTreeSmem, s, w.tree, w.size, w.sigma, i, c, n, out);
         SG_CUDA(cudaGetLastError());
         return SDSLGPU_OK;
     }
     for (uint32_t l = 0; l < depth; ++l)
     {
-        wt_rank_level_kernel<<<grid_for(n), kThreads, kTreeSmem, s>>>(bv_view(w.bv), w.tree, w.size, l, depth - 1, i, c, n, out);
+        SG_LAUNCH_BITS(wt_rank_level_kernel, w, grid_for(n), kTreeSmem, s, w.tree, w.size, l, depth - 1, i, c, n, out);
         SG_CUDA(cudaGetLastError());
     }
     return SDSLGPU_OK;
@@ -497,7 +512,7 @@ int wt_select_device(sdslgpu_handle const * h, uint64_t const * i, uint8_t const
     WtHuffImage const & w = h->wt;
     if (n == 0)
         return SDSLGPU_OK;
-    wt_select_kernel<<<grid_for(n), kThreads, kTreeSmem, s>>>(bv_view(w.bv), w.tree, w.size, w.sigma, i, c, n, out);
+    SG_LAUNCH_BITS(wt_select_kernel, w, grid_for(n), kTreeSmem, s, w.tree, w.size, w.sigma, i, c, n, out);
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
 }
@@ -507,7 +522,7 @@ int wt_access_device(sdslgpu_handle const * h, uint64_t const * i, uint64_t n, u
     WtHuffImage const & w = h->wt;
     if (n == 0)
         return SDSLGPU_OK;
-    wt_access_kernel<<<grid_for(n), kThreads, kTreeSmem, s>>>(bv_view(w.bv), w.tree, w.size, i, n, sym, rnk);
+    SG_LAUNCH_BITS(wt_access_kernel, w, grid_for(n), kTreeSmem, s, w.tree, w.size, i, n, sym, rnk);
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
 }

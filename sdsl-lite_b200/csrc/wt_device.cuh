@@ -1,7 +1,7 @@
 // wt_device.cuh — per-query wavelet-tree primitives over a tree staged in shared memory, shared by wt.cu
 // (wt_huff queries) and fm.cu (backward search, LF walks).
 #pragma once
-#include "bv_device.cuh"
+#include "bits_access.cuh"
 #include "internal.h"
 
 namespace sdslgpu
@@ -20,7 +20,8 @@ __device__ __forceinline__ void stage_tree(WtTree const * __restrict__ g, WtTree
 }
 
 // rank(i, c) for one query (wt_pc.hpp:371-399): path_len dependent sector gathers on the concatenated m_bv
-__device__ __forceinline__ uint64_t wt_rank_one(BvView const & bv, WtTree const * t, uint64_t sigma, uint64_t i, uint32_t c)
+template <class Bits>
+__device__ __forceinline__ uint64_t wt_rank_one(Bits const & bits, WtTree const * t, uint64_t sigma, uint64_t i, uint32_t c)
 {
     if (t->c_to_leaf[c] == kWtUndef)
         return 0;
@@ -32,7 +33,7 @@ __device__ __forceinline__ uint64_t wt_rank_one(BvView const & bv, WtTree const 
     uint32_t v = 0;
     for (uint32_t l = 0; l < len && r; ++l, p >>= 1)
     {
-        uint64_t o = bv_rank1(bv, t->bv_pos[v] + r) - t->bv_pos_rank[v];
+        uint64_t o = bits.rank1(t->bv_pos[v] + r) - t->bv_pos_rank[v];
         r = (p & 1) ? o : r - o;
         v = t->child[v][p & 1];
     }
@@ -40,13 +41,14 @@ __device__ __forceinline__ uint64_t wt_rank_one(BvView const & bv, WtTree const 
 }
 
 // (rank(i, wt[i]), wt[i]) (wt_pc.hpp:411-430): per level ONE sector yields both the bit and the rank
-__device__ __forceinline__ uint64_t wt_inverse_select_one(BvView const & bv, WtTree const * t, uint64_t i, uint32_t & sym)
+template <class Bits>
+__device__ __forceinline__ uint64_t wt_inverse_select_one(Bits const & bits, WtTree const * t, uint64_t i, uint32_t & sym)
 {
     uint32_t v = 0;
     while (t->child[v][0] != kWtUndef)
     {
         uint32_t bit;
-        uint64_t o = bv_rank1_and_bit(bv, t->bv_pos[v] + i, bit) - t->bv_pos_rank[v];
+        uint64_t o = bits.rank1_and_bit(t->bv_pos[v] + i, bit) - t->bv_pos_rank[v];
         i = bit ? o : i - o;
         v = t->child[v][bit];
     }
