@@ -459,6 +459,21 @@ class Ref:
         L.ref_csa_extract.restype = None
         L.ref_csa_extract.argtypes = [vp, C.c_uint64, C.c_uint64, u8p]
         L.ref_version.restype = C.c_char_p
+        if hasattr(L, "ref_wt_huff_rrr_create"):
+            L.ref_wt_huff_rrr_create.restype = vp
+            L.ref_wt_huff_rrr_create.argtypes = [u8p, C.c_uint64]
+            L.ref_wt_huff_rrr_free.argtypes = [vp]
+            L.ref_wt_huff_rrr_rank.restype = None
+            L.ref_wt_huff_rrr_rank.argtypes = [vp, u64p, u8p, C.c_uint64, u64p, C.c_int]
+            L.ref_wt_huff_rrr_serialize.restype = C.c_uint64
+            L.ref_wt_huff_rrr_serialize.argtypes = [vp, u8p, C.c_uint64]
+            L.ref_csa_rrr_create.restype = vp
+            L.ref_csa_rrr_create.argtypes = [u8p, C.c_uint64]
+            L.ref_csa_rrr_free.argtypes = [vp]
+            L.ref_csa_rrr_serialize.restype = C.c_uint64
+            L.ref_csa_rrr_serialize.argtypes = [vp, u8p, C.c_uint64]
+            L.ref_csa_rrr_count.restype = None
+            L.ref_csa_rrr_count.argtypes = [vp, u8p, u64p, C.c_uint64, u64p, C.c_int]
 
     def bv(self, words, nbits, with_select=True):
         return RefBV(self, words, nbits, with_select)
@@ -477,6 +492,33 @@ class Ref:
 
     def csa(self, text=None, blob=None):
         return RefCsa(self, text, blob)
+
+    def wt_huff_rrr_blob(self, text):
+        """serialised wt_huff<rrr_vector<63>> of `text` and its rank answers for (i, c) -> (blob, rank_fn)"""
+        t = _text(text)
+        h = self.L.ref_wt_huff_rrr_create(_p8(t if len(t) else np.zeros(1, np.uint8)), len(t))
+        blob = _blob(self.L.ref_wt_huff_rrr_serialize, h)
+
+        def rank(i, c):
+            i, c = _u64(i), _u8(c)
+            out = np.zeros(len(i), dtype=np.uint64)
+            self.L.ref_wt_huff_rrr_rank(h, _p64(i), _p8(c), len(i), _p64(out), 1)
+            return out
+
+        return blob, rank
+
+    def csa_rrr_blob(self, text):
+        """serialised csa_wt<wt_huff<rrr_vector<63>>> of `text` and its count() -> (blob, count_fn)"""
+        t = _text(text)
+        h = self.L.ref_csa_rrr_create(_p8(t if len(t) else np.zeros(1, np.uint8)), len(t))
+        blob = _blob(self.L.ref_csa_rrr_serialize, h)
+
+        def count(flat, off):
+            out = np.zeros(len(off) - 1, dtype=np.uint64)
+            self.L.ref_csa_rrr_count(h, _p8(flat), _p64(off), len(off) - 1, _p64(out), 1)
+            return out
+
+        return blob, count
 
 
 class RefBV:

@@ -523,6 +523,73 @@ extern "C"
         std::memcpy(out, s.data(), s.size());
     }
 
+    // ---------------------------------------------------------------- wt_huff<rrr_vector<63>> and the CSA over it
+    // (the reference's FM_HUFF_RRR63 benchmark index, benchmark/indexing_count/index.config:10)
+    struct ref_wt_huff_rrr
+    {
+        wt_huff<rrr_vector<63>> wt;
+    };
+    struct ref_csa_rrr
+    {
+        csa_wt<wt_huff<rrr_vector<63>>> csa;
+    };
+    void * ref_wt_huff_rrr_create(uint8_t const * text, uint64_t n)
+    {
+        auto * h = new ref_wt_huff_rrr;
+        int_vector<8> t(n);
+        if (n)
+            std::memcpy(t.data(), text, n);
+        construct_im(h->wt, t, 0);
+        return h;
+    }
+    void ref_wt_huff_rrr_free(void * p)
+    {
+        delete static_cast<ref_wt_huff_rrr *>(p);
+    }
+    void ref_wt_huff_rrr_rank(void * p, uint64_t const * i, uint8_t const * c, uint64_t n, uint64_t * out, int threads)
+    {
+        auto * h = static_cast<ref_wt_huff_rrr *>(p);
+        parallel_for(n, threads, [=](uint64_t lo, uint64_t hi) {
+            for (uint64_t k = lo; k < hi; ++k)
+                out[k] = h->wt.rank(i[k], c[k]);
+        });
+    }
+    uint64_t ref_wt_huff_rrr_serialize(void * p, uint8_t * buf, uint64_t cap)
+    {
+        return serialize_to(static_cast<ref_wt_huff_rrr *>(p)->wt, buf, cap);
+    }
+    void * ref_csa_rrr_create(uint8_t const * text, uint64_t n)
+    {
+        auto * h = new ref_csa_rrr;
+        std::string s(reinterpret_cast<char const *>(text), n);
+        try
+        {
+            construct_im(h->csa, s, 1);
+        }
+        catch (...)
+        {
+            delete h;
+            return nullptr;
+        }
+        return h;
+    }
+    void ref_csa_rrr_free(void * p)
+    {
+        delete static_cast<ref_csa_rrr *>(p);
+    }
+    uint64_t ref_csa_rrr_serialize(void * p, uint8_t * buf, uint64_t cap)
+    {
+        return serialize_to(static_cast<ref_csa_rrr *>(p)->csa, buf, cap);
+    }
+    void ref_csa_rrr_count(void * p, uint8_t const * pats, uint64_t const * off, uint64_t n, uint64_t * cnt_out, int threads)
+    {
+        auto * h = static_cast<ref_csa_rrr *>(p);
+        parallel_for(n, threads, [=](uint64_t lo, uint64_t hi) {
+            for (uint64_t k = lo; k < hi; ++k)
+                cnt_out[k] = count(h->csa, pats + off[k], pats + off[k + 1]);
+        });
+    }
+
     char const * ref_version()
     {
         return "sdsl-lite 3.0.5 (reference headers, unmodified) via oracle/ref_driver.cpp";

@@ -153,9 +153,8 @@ int load_bv(sdslgpu_handle * h, Reader & r, cudaStream_t s)
     return bv_build(h->pool, h->bv, h->flags, bv.words.data(), false, bv.bits, s);
 }
 
-int load_rrr(sdslgpu_handle * h, Reader & r, cudaStream_t s)
+int load_rrr_image(DevicePool & pool, RrrImage & im, Reader & r, cudaStream_t s)
 {
-    RrrImage & im = h->rrr;
     im.size = r.u64();
     IntVec bt, btnr, btnrp, rank, inv;
     if (!read_iv(r, bt) || !read_iv(r, btnr) || !read_iv(r, btnrp) || !read_iv(r, rank) || !read_iv(r, inv) || bt.width != 6 || btnr.width != 1)
@@ -166,7 +165,7 @@ int load_rrr(sdslgpu_handle * h, Reader & r, cudaStream_t s)
         return malformed("rrr_vector<63> (inconsistent sizes; only t_bs = 63, t_k = 32 is supported)");
     im.ones = rank.get(rank.size() - 1);
     im.btnr_bits = btnr.bits;
-    SG_TRY(rrr_upload_tables(h->pool, im, s));
+    SG_TRY(rrr_upload_tables(pool, im, s));
     std::vector<uint64_t> rk(im.nsuper), bp(im.nsuper);
     std::vector<uint8_t> iv(im.nsuper);
     for (uint64_t g = 0; g < im.nsuper; ++g)
@@ -179,14 +178,19 @@ int load_rrr(sdslgpu_handle * h, Reader & r, cudaStream_t s)
     // matters (it fixes the width of m_btnrp when serialising back), and m_btnrp's width preserves that
     uint64_t total_bits_hint = btnrp.width ? (1ull << (btnrp.width - 1)) : 0;
     bt.words.resize(bt.words.size() + 2, 0);
-    SG_TRY(rrr_records_from_sdsl(h->pool, im, bt.words.data(), im.nblocks, rk, bp, iv, total_bits_hint, s));
+    SG_TRY(rrr_records_from_sdsl(pool, im, bt.words.data(), im.nblocks, rk, bp, iv, total_bits_hint, s));
     uint64_t nrw = ((btnr.bits + 63) >> 6) + 2;
     std::vector<uint64_t> nrp(nrw, 0);
     std::memcpy(nrp.data(), btnr.words.data(), std::min<uint64_t>(btnr.words.size(), nrw) * 8);
-    SG_TRY(h->pool.alloc_t(&im.btnr, nrw));
+    SG_TRY(pool.alloc_t(&im.btnr, nrw));
     SG_CUDA(cudaMemcpyAsync(im.btnr, nrp.data(), nrw * 8, cudaMemcpyHostToDevice, s));
     SG_CUDA(cudaStreamSynchronize(s));
-    return rrr_build_hints(h->pool, im, s);
+    return rrr_build_hints(pool, im, s);
+}
+
+int load_rrr(sdslgpu_handle * h, Reader & r, cudaStream_t s)
+{
+    return load_rrr_image(h->pool, h->rrr, r, s);
 }
 
 int load_sd(sdslgpu_handle * h, Reader & r, cudaStream_t s)
@@ -213,7 +217,13 @@ int load_wt_huff(sdslgpu_handle * h, Reader & r, cudaStream_t s)
 {
     uint64_t size = r.u64(), sigma = r.u64();
     IntVec bv;
-    if (!read_iv(r, bv) || bv.width != 1 || !skip_iv(r) || !skip_select_mcl(r) || !skip_select_mcl(r))
+    bool const over_rrr = (h->flags & SDSLGPU_F_RRR_BV) != 0;
+    if (over_rrr)
+    { // wt_huff<rrr_vector<63>>: the rrr_vector, then its rank/select supports which serialise to nothing
+        h->wt.use_rrr = true;
+        SG_TRY(load_rrr_image(h->pool, h->wt.rrr, r, s));
+    }
+    else if (!read_iv(r, bv) || bv.width != 1 || !skip_iv(r) || !skip_select_mcl(r) || !skip_select_mcl(r))
         return malformed("wt_huff");
     uint64_t nn = r.u64();
     if (!r.ok || nn > 511 || !r.need(nn * 22 + 512 + 2048))
@@ -238,6 +248,8 @@ int load_wt_huff(sdslgpu_handle * h, Reader & r, cudaStream_t s)
     if (size == 0)
         for (int c = 0; c < 256; ++c)
             tree.c_to_leaf[c] = 0xFFFF; // an empty reference tree serialises uninitialised tables
+    if (over_rrr)
+        return wt_huff_finish(h, size, sigma, tree, s);
     return wt_huff_upload(h, size, sigma, tree, bv.words.data(), bv.bits, s);
 }
 

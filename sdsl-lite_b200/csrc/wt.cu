@@ -321,14 +321,21 @@ __global__ void __launch_bounds__(kThreads) wt_select_kernel(Bits bits,
 int wt_huff_upload(sdslgpu_handle * h, uint64_t size, uint64_t sigma, WtTree const & tree, uint64_t const * bv_words, uint64_t bv_bits, cudaStream_t s)
 {
     WtHuffImage & w = h->wt;
-    w.size = size;
-    w.sigma = sigma;
-    w.host_tree = tree;
     w.use_rrr = (h->flags & SDSLGPU_F_RRR_BV) != 0;
     if (w.use_rrr)
         SG_TRY(rrr_build_image(h->pool, w.rrr, bv_words, false, bv_bits, s));
     else
         SG_TRY(bv_build(h->pool, w.bv, h->flags & ~SDSLGPU_F_NO_SELECT, bv_words, false, bv_bits, s));
+    return wt_huff_finish(h, size, sigma, tree, s);
+}
+
+// the bit vector image (plain or rrr) is in place: node ranks, symbol counts, device copy of the tree
+int wt_huff_finish(sdslgpu_handle * h, uint64_t size, uint64_t sigma, WtTree const & tree, cudaStream_t s)
+{
+    WtHuffImage & w = h->wt;
+    w.size = size;
+    w.sigma = sigma;
+    w.host_tree = tree;
     // inner nodes: bv_pos_rank = rank1(m_bv, bv_pos) (wt_helper.hpp:319-327), computed on the device
     uint32_t nn = tree.nnodes;
     if (nn)

@@ -48,3 +48,31 @@ def test_csa_over_rrr(pkg, oracle):
             eq = np.minimum(bq + rng.integers(0, 50, 500, dtype=np.uint64), np.uint64(len(t)))
             assert (csa.extract(bq, eq)[1] == plain.extract(bq, eq)[1]).all(), (name, "extract")
             assert csa.device_bytes <= plain.device_bytes or len(t) < 100000, (name, "compressed image is not larger")
+
+
+def test_load_reference_blobs_over_rrr(pkg, orc):
+    """ingest of wt_huff<rrr_vector<63>> / csa_wt<wt_huff<rrr_vector<63>>> as serialised by the reference"""
+    if not orc.ref_available() or not hasattr(orc.Ref().L, "ref_wt_huff_rrr_create"):
+        pytest.skip("reference library without the rrr-backed types")
+    ref = orc.Ref()
+    rng = np.random.default_rng(93)
+    for name, t in texts.text_catalogue(large=False):
+        blob, ref_rank = ref.wt_huff_rrr_blob(t)
+        with pkg.load_sdsl(blob, pkg.KIND_WT_HUFF, flags=pkg.F_RRR_BV) as wt:
+            i, c = texts.wt_queries(t, rng, 5000)
+            assert wt.size == len(t) and (wt.rank(i, c) == ref_rank(i, c)).all(), (name, "wt rank")
+            j = rng.integers(0, len(t), 3000, dtype=np.uint64)
+            r, s = wt.inverse_select(j)
+            assert (s == np.frombuffer(t, np.uint8)[j.astype(np.int64)]).all(), (name, "access")
+            assert (wt.select(r + np.uint64(1), s.astype(np.uint8)) == j).all(), (name, "select")
+    for name, t in texts.text_catalogue(zero_free=True, large=False):
+        blob, ref_count = ref.csa_rrr_blob(t)
+        pats = [t[s : s + int(rng.integers(1, 12))] for s in rng.integers(0, max(1, len(t) - 12), 300)] + [b"", b"\x01\x02zz"]
+        flat, off = pkg.csr_patterns(pats)
+        with pkg.load_sdsl(blob, pkg.KIND_CSA_WT, flags=pkg.F_RRR_BV) as csa:
+            assert csa.size == len(t) + 1 and (csa.count(flat, off) == ref_count(flat, off)).all(), (name, "count")
+            bq = rng.integers(0, len(t), 200, dtype=np.uint64)
+            eq = np.minimum(bq + rng.integers(0, 30, 200, dtype=np.uint64), np.uint64(len(t) - 1))
+            o, out = csa.extract(bq, eq)
+            for k in range(0, 200, 9):
+                assert out[int(o[k]) : int(o[k + 1])].tobytes() == t[int(bq[k]) : int(eq[k]) + 1], (name, "extract")
