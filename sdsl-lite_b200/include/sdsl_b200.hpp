@@ -243,6 +243,10 @@ template <uint8_t t_b = 1, uint8_t t_pat_len = 1>
 using rank_support_v = rank_support<t_b, bit_vector>;
 template <uint8_t t_b = 1, uint8_t t_pat_len = 1>
 using select_support_mcl = select_support<t_b, bit_vector>;
+//! rank_support_v5 (rank_support_v5.hpp:131-149) answers exactly what rank_support_v answers; on the device both
+//! map onto the same sector blocks, so the alias keeps call sites that name the 6.25 %-overhead variant compiling.
+template <uint8_t t_b = 1, uint8_t t_pat_len = 1>
+using rank_support_v5 = rank_support<t_b, bit_vector>;
 
 // ------------------------------------------------------------------------------------------------------
 // compressed bit vectors (rrr_vector.hpp:67-109, sd_vector.hpp:131-163)

@@ -259,6 +259,15 @@ def run_c5(args):
         par = bool((oo[: nl + 1] == w[0]).all() and (oc[: int(w[0][-1])] == w[1]).all())
         cpu = {"qps": nl / t, "cores": CORES, "sample": nl}
     record(cfg, "locate() (two passes: size, then fill)", npat, ms, best, 7324 + 2992 * tot / npat, par, cpu, {"occurrences": tot, "unit": "patterns/s"})
+    if args.rrr_variant:
+        csa.close()
+        torch.cuda.empty_cache()
+        t0 = time.perf_counter()
+        csa = pkg.CsaWt(text, flags=pkg.F_RRR_BV)
+        b2 = time.perf_counter() - t0
+        ms, best = time_gpu(lambda: csa.count(d_flat, d_off), args.reps)
+        par = bool((host(csa.count(d_flat, d_off)) == cnt).all())
+        record(cfg, "count() on csa_wt<wt_huff<rrr_vector<63>>>", npat, ms, best, 7324, par, None, {"index_bytes": csa.device_bytes, "build_s": b2, "unit": "patterns/s"})
     # uniformly random 20-mers: almost all absent -> early exit
     rflat = qr.integers(1, 256, npat * plen, dtype=np.uint8)
     d_rflat = dev(rflat)
@@ -281,6 +290,7 @@ def main():
     ap.add_argument("--queries-c4", type=float, default=1e7)
     ap.add_argument("--csa-log2", type=int, default=28)
     ap.add_argument("--csa-ref", type=int, default=1)
+    ap.add_argument("--rrr-variant", type=int, default=1)
     ap.add_argument("--patterns", type=float, default=1e6)
     ap.add_argument("--cpu-sample", type=float, default=2e7)
     ap.add_argument("--reps", type=int, default=5)
