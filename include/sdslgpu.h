@@ -56,6 +56,12 @@ extern "C" {
 #define SDSLGPU_F_RRR_BV 4u      /* wavelet trees / CSA: store the tree's bit vector as rrr_vector<63>, i.e.
                                     wt_huff<rrr_vector<63>> and csa_wt<wt_huff<rrr_vector<63>>> (H0-compressed) */
 
+#define SDSLGPU_F_COMPACT 8u     /* CSA: keep the wavelet tree of the BWT as the only occurrence structure
+                                    (1.14 bytes/symbol; a backward-search step is one sector gather per Huffman
+                                    level).  By default a CSA additionally holds 32 one-hot sector-block bitmaps
+                                    and the BWT (5.6 bytes/symbol) so that a step is 2 gathers and
+                                    an LF step 3; results are identical.  Implied by SDSLGPU_F_RRR_BV. */
+
 typedef struct sdslgpu_handle sdslgpu_handle;
 
 /* ---- library ------------------------------------------------------------------------------- */
@@ -142,10 +148,18 @@ int sdslgpu_wt_access(const sdslgpu_handle *h, const uint64_t *i, uint64_t n, ui
 
 /* Replaces construct(csa_wt<wt_huff<>>, text) (construct.hpp:127-193, csa_wt.hpp:323-355): `text` is a HOST
  * buffer of n zero-free bytes (a zero byte gives SDSLGPU_EINVAL, as the reference throws, construct.hpp:34-46);
- * the 0 sentinel is appended, so size() == n + 1.  Suffix array (SA-IS), BWT, byte_alphabet and the SA
- * samples (every 32nd SA index, csa_sampling_strategy.hpp:98-115) are computed on the host; the wavelet tree
- * of the BWT gets its rank/select structures on the device.  A CSA handle also answers sdslgpu_wt_* (that is
- * csa.bwt / csa.wavelet_tree). */
+ * the 0 sentinel is appended, so size() == n + 1.  Suffix array, BWT and the SA / ISA samples are computed on the
+ * device (prefix doubling; the host SA-IS builder takes over when the text does not fit 32-bit suffix indices or
+ * SDSLGPU_HOST_SA=1); the wavelet tree of the BWT gets its rank/select structures on the device.  With
+ * SDSLGPU_F_RRR_BV the tree's bit vector is rrr_vector<63>.  A CSA handle also answers sdslgpu_wt_* (that is
+ * csa.bwt / csa.wavelet_tree).
+ * sdslgpu_csa_create_ex takes the reference's two template parameters (csa_wt.hpp:50-51): sa_dens = t_dens, every
+ * sa_dens-th suffix-array entry is kept (csa_sampling_strategy.hpp:98-115), isa_dens = t_inv_dens; 0 means the
+ * defaults 32 / 64, which is what sdslgpu_csa_create uses.  Densities change speed and memory, never a result:
+ * locate walks on average (sa_dens - 1) / 2 LF steps per occurrence, so with HBM to spare a small sa_dens
+ * (4 ... 8) is the B200-side choice. */
+int sdslgpu_csa_create_ex(const uint8_t *text, uint64_t n, int device, uint32_t flags, uint32_t sa_dens, uint32_t isa_dens,
+                          sdslgpu_handle **out);
 int sdslgpu_csa_create(const uint8_t *text, uint64_t n, int device, uint32_t flags, sdslgpu_handle **out);
 
 /* Patterns in CSR form: pattern k = pats[pat_off[k] .. pat_off[k+1]).

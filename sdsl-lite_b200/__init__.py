@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(HERE, "libsdslgpu.so")
 
 OK, EINVAL, ENOMEM, ECUDA, ENOTSUP = 0, -1, -2, -3, -4
 NPOS = np.uint64(0xFFFFFFFFFFFFFFFF)
-F_DEFAULT, F_SDSL_LAYOUT, F_NO_SELECT, F_RRR_BV = 0, 1, 2, 4
+F_DEFAULT, F_SDSL_LAYOUT, F_NO_SELECT, F_RRR_BV, F_COMPACT = 0, 1, 2, 4, 8
 KIND_BV, KIND_RRR63, KIND_SD, KIND_WT_HUFF, KIND_WT_INT, KIND_CSA_WT = 1, 2, 3, 4, 5, 6
 
 u64p = C.POINTER(C.c_uint64)
@@ -283,6 +283,7 @@ class WtHuff(_Handle, _WaveletTreeOps):
 
 _SIGNATURES += [
     ("sdslgpu_csa_create", C.c_int, [vp, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(vp)]),
+    ("sdslgpu_csa_create_ex", C.c_int, [vp, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
     ("sdslgpu_fm_count", C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, vp]),
     ("sdslgpu_fm_sa", C.c_int, [vp, vp, C.c_uint64, vp, vp]),
     ("sdslgpu_fm_locate", C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, C.c_uint64, u64p, vp]),
@@ -305,10 +306,11 @@ class CsaWt(_Handle, _WaveletTreeOps):
     """csa_wt<wt_huff<>> over a zero-free byte text; count / locate / SA access in batch form
     (sdsl::count, sdsl::locate, csa[i] — suffix_array_algorithm.hpp:463-471, 534-550; csa_wt.hpp:363-381)."""
 
-    def __init__(self, text, device=0, flags=F_DEFAULT):
+    def __init__(self, text, device=0, flags=F_DEFAULT, sa_dens=0, isa_dens=0):
+        """sa_dens / isa_dens are csa_wt's t_dens / t_inv_dens (csa_wt.hpp:50-51); 0 = the defaults 32 / 64"""
         super().__init__()
         t = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else np.ascontiguousarray(text, dtype=np.uint8)
-        _check(lib().sdslgpu_csa_create(t.ctypes.data if len(t) else None, len(t), device, flags, C.byref(self._h)))
+        _check(lib().sdslgpu_csa_create_ex(t.ctypes.data if len(t) else None, len(t), device, flags, sa_dens, isa_dens, C.byref(self._h)))
 
     # csa.bwt.rank(i, c) etc.
     bwt_rank = _WaveletTreeOps.wt_rank

@@ -896,7 +896,7 @@ extern "C"
     }
 
     // -------------------------------------------------------------------------------- FM-index
-    int sdslgpu_csa_create(const uint8_t * text, uint64_t n, int device, uint32_t flags, sdslgpu_handle ** out)
+    int sdslgpu_csa_create_ex(const uint8_t * text, uint64_t n, int device, uint32_t flags, uint32_t sa_dens, uint32_t isa_dens, sdslgpu_handle ** out)
     {
         if (!out || (!text && n))
         {
@@ -907,7 +907,7 @@ extern "C"
         sdslgpu_handle * h = nullptr;
         SG_TRY(new_handle(SDSLGPU_KIND_CSA_WT, device, flags, &h));
         DeviceGuard g(device);
-        int st = csa_build_from_text(h, text, n, nullptr);
+        int st = csa_build_from_text(h, text, n, sa_dens, isa_dens, nullptr);
         if (st != SDSLGPU_OK)
         {
             h->pool.release_all();
@@ -916,6 +916,11 @@ extern "C"
         }
         *out = h;
         return SDSLGPU_OK;
+    }
+
+    int sdslgpu_csa_create(const uint8_t * text, uint64_t n, int device, uint32_t flags, sdslgpu_handle ** out)
+    {
+        return sdslgpu_csa_create_ex(text, n, device, flags, 0, 0, out);
     }
 
     int sdslgpu_fm_count(const sdslgpu_handle * h, const uint8_t * pats, const uint64_t * pat_off, uint64_t n, uint64_t * cnt_out, uint64_t * l_out, void * stream)

@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kThreads) fm_extract_kernel(Bits bits,
 // ------------------------------------------------------------------------------------------------
 // host: construction
 // ------------------------------------------------------------------------------------------------
-int csa_build_from_text(sdslgpu_handle * h, uint8_t const * text, uint64_t len, cudaStream_t s)
+int csa_build_from_text(sdslgpu_handle * h, uint8_t const * text, uint64_t len, uint32_t sa_dens, uint32_t isa_dens, cudaStream_t s)
 {
     for (uint64_t k = 0; k < len; ++k)
         if (text[k] == 0)
@@ -280,10 +280,10 @@ int csa_build_from_text(sdslgpu_handle * h, uint8_t const * text, uint64_t len, 
     uint64_t n = len + 1;
     CsaImage & c = h->csa;
     c.n = n;
-    c.sa_dens = 32;
+    c.sa_dens = sa_dens ? sa_dens : 32;
     std::vector<uint8_t> bwt;
     std::vector<uint64_t> samples, isa;
-    c.isa_dens = 64;
+    c.isa_dens = isa_dens ? isa_dens : 64;
     // suffix array + BWT + samples: on the device (prefix doubling, gpu_sa.cu) unless SDSLGPU_HOST_SA=1 or the
     // text does not fit 32-bit suffix indices / device memory, in which case the host SA-IS builder runs
     int st = SDSLGPU_ENOTSUP;
@@ -368,6 +368,9 @@ int csa_upload(sdslgpu_handle * h, uint8_t const * bwt, uint64_t const * samples
     SG_TRY(h->pool.alloc_t(&c.tab, 1));
     SG_CUDA(cudaMemcpyAsync(c.tab, &c.host_tab, sizeof(FmTables), cudaMemcpyHostToDevice, s));
     SG_CUDA(cudaStreamSynchronize(s));
+    // the one-hot occurrence bitmaps the searches run on (occ16_device.cuh), unless the caller asked for a compact index
+    if (!(h->flags & (SDSLGPU_F_COMPACT | SDSLGPU_F_RRR_BV)))
+        SG_TRY(occ16_build(h, bwt, s));
     return SDSLGPU_OK;
 }
 
@@ -378,6 +381,8 @@ static size_t const kFmSmem = sizeof(FmSmem);
 
 int fm_count_device(sdslgpu_handle const * h, uint8_t const * pats, uint64_t const * off, uint64_t npat, uint64_t * cnt, uint64_t * l, cudaStream_t s)
 {
+    if (h->csa.occ.levels)
+        return fm16_count_device(h, pats, off, npat, cnt, l, s);
     if (npat == 0)
         return SDSLGPU_OK;
     SG_LAUNCH_BITS(fm_count_kernel, h->wt, grid_for(npat), kFmSmem, s, h->wt.tree, h->csa.tab, h->csa.n, h->wt.sigma, pats, off, npat, cnt, l);
@@ -387,6 +392,8 @@ int fm_count_device(sdslgpu_handle const * h, uint8_t const * pats, uint64_t con
 
 int fm_sa_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t cnt, uint64_t * out, cudaStream_t s)
 {
+    if (h->csa.occ.levels)
+        return fm16_sa_device(h, idx, cnt, out, s);
     if (cnt == 0)
         return SDSLGPU_OK;
     SG_LAUNCH_BITS(fm_sa_kernel, h->wt, grid_for(cnt), kFmSmem, s, h->wt.tree, h->csa.tab, h->csa.samples, h->csa.sa_dens, h->csa.n, idx, cnt, out);
@@ -396,6 +403,8 @@ int fm_sa_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t cnt, u
 
 int fm_extract_device(sdslgpu_handle const * h, uint64_t const * begin, uint64_t const * end, uint64_t const * out_off, uint64_t n, uint8_t * out, cudaStream_t s)
 {
+    if (h->csa.occ.levels)
+        return fm16_extract_device(h, begin, end, out_off, n, out, s);
     if (n == 0)
         return SDSLGPU_OK;
     SG_LAUNCH_BITS(fm_extract_kernel, h->wt, grid_for(n), kFmSmem, s, h->wt.tree, h->csa.tab, h->csa.isa_samples, h->csa.nisa, h->csa.isa_dens, h->csa.n, begin, end,
@@ -413,6 +422,8 @@ int fm_scan_counts_device(uint64_t const * cnt, uint64_t npat, uint64_t * occ_of
 
 int fm_locate_fill_device(sdslgpu_handle const * h, uint64_t const * l, uint64_t const * occ_off, uint64_t npat, uint64_t total, uint64_t * occ, cudaStream_t s)
 {
+    if (h->csa.occ.levels)
+        return fm16_locate_fill_device(h, l, occ_off, npat, total, occ, s);
     if (total == 0 || npat == 0)
         return SDSLGPU_OK;
     SG_LAUNCH_BITS(fm_locate_fill_kernel, h->wt, grid_for(total), kFmSmem, s, h->wt.tree, h->csa.tab, h->csa.samples, h->csa.sa_dens, h->csa.n, l, occ_off, npat,

@@ -205,8 +205,31 @@ struct SdImage
     BvImage high;             // m_high with rank blocks + select<1>/<0> samples
 };
 
+// one-hot occurrence bitmaps of the BWT (occ16_device.cuh), staged in shared memory by the fm16 kernels
+struct alignas(16) Occ16Tab
+{
+    bvblock const * blocks[2][16];
+    uint64_t const * top[2][16];
+    uint64_t CH[16];       // level-1 start of the subsequence of each high nibble
+    uint64_t D[256];       // per comp symbol: C[cc] - rank1(B1[lo], CH[h])  (wrapping)
+    uint8_t const * bwtc;  // the BWT in comp codes
+    uint32_t levels;       // 1 (sigma <= 16) or 2
+    uint32_t pad_;
+};
+static_assert(sizeof(Occ16Tab) % 16 == 0, "staged with 16-byte copies");
+
+struct Occ16Image
+{
+    uint32_t levels = 0; // 0: not built (SDSLGPU_F_COMPACT / rrr-backed / ingest without it)
+    BvImage bm[2][16];
+    uint8_t * bwtc = nullptr;
+    Occ16Tab * tab = nullptr; // device copy
+    Occ16Tab host_tab;
+};
+
 struct CsaImage
 {
+    Occ16Image occ;
     uint64_t n = 0;              // csa.size() = text length + 1
     uint32_t sa_dens = 32;       // t_dens (csa_wt.hpp:50)
     uint64_t * samples = nullptr; // SA[0], SA[dens], ... widened to u64 (csa_sampling_strategy.hpp:98-115)
@@ -320,7 +343,7 @@ int sd_serialize_low_high(sdslgpu_handle const * h, std::vector<uint8_t> & blob)
 int gpu_suffix_array_bwt(uint8_t const * text_host, uint64_t len, uint32_t dens, uint32_t isa_dens, std::vector<uint8_t> & bwt, std::vector<uint64_t> & samples,
                          std::vector<uint64_t> & isa_samples, uint32_t * rounds_out, cudaStream_t s);
 // fm.cu
-int csa_build_from_text(sdslgpu_handle * h, uint8_t const * text_host, uint64_t len, cudaStream_t s);
+int csa_build_from_text(sdslgpu_handle * h, uint8_t const * text_host, uint64_t len, uint32_t sa_dens, uint32_t isa_dens, cudaStream_t s);
 int csa_upload(sdslgpu_handle * h, uint8_t const * bwt_host, uint64_t const * samples_host, uint64_t nsamples, uint64_t const * isa_host, uint64_t nisa, cudaStream_t s);
 int csa_upload_isa(sdslgpu_handle * h, uint64_t const * isa_host, uint64_t nisa, cudaStream_t s);
 int fm_extract_device(sdslgpu_handle const * h, uint64_t const * begin, uint64_t const * end, uint64_t const * out_off, uint64_t n, uint8_t * out, cudaStream_t s);
@@ -329,6 +352,13 @@ int fm_sa_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t cnt, u
 int fm_scan_counts_device(uint64_t const * cnt, uint64_t npat, uint64_t * occ_off, uint64_t * tmp, cudaStream_t s);
 int fm_locate_fill_device(sdslgpu_handle const * h, uint64_t const * l, uint64_t const * occ_off, uint64_t npat, uint64_t total, uint64_t * occ, cudaStream_t s);
 uint64_t fm_scan_tmp_words(uint64_t npat);
+// fm16.cu: the same four searches over the one-hot occurrence structure
+int occ16_build(sdslgpu_handle * h, uint8_t const * bwt_host, cudaStream_t s);
+int occ16_build_from_wt(sdslgpu_handle * h, cudaStream_t s);
+int fm16_count_device(sdslgpu_handle const * h, uint8_t const * pats, uint64_t const * off, uint64_t npat, uint64_t * cnt, uint64_t * l, cudaStream_t s);
+int fm16_sa_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t cnt, uint64_t * out, cudaStream_t s);
+int fm16_locate_fill_device(sdslgpu_handle const * h, uint64_t const * l, uint64_t const * occ_off, uint64_t npat, uint64_t total, uint64_t * occ, cudaStream_t s);
+int fm16_extract_device(sdslgpu_handle const * h, uint64_t const * begin, uint64_t const * end, uint64_t const * out_off, uint64_t n, uint8_t * out, cudaStream_t s);
 unsigned grid_for(uint64_t n, int per_thread = 1);
 unsigned blocks_for(uint64_t n);
 } // namespace sdslgpu

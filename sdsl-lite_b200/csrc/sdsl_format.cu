@@ -316,7 +316,11 @@ int load_csa(sdslgpu_handle * h, Reader & r, uint32_t sa_dens, cudaStream_t s)
             d <<= 1;
         c.isa_dens = d;
     }
-    return csa_upload_isa(h, isav.data(), isa.size(), s);
+    SG_TRY(csa_upload_isa(h, isav.data(), isa.size(), s));
+    // the searches' one-hot occurrence bitmaps, decoded from the ingested tree (fm16.cu) unless a compact index was asked for
+    if (!(h->flags & SDSLGPU_F_COMPACT) && !h->wt.use_rrr)
+        SG_TRY(occ16_build_from_wt(h, s));
+    return SDSLGPU_OK;
 }
 
 } // namespace

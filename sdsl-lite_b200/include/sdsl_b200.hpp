@@ -418,10 +418,12 @@ public:
     typedef std::string string_type;
     csa_wt() = default;
     //! construct(csa, text, 1) / construct_im(csa, text, 1): the text must not contain a 0 byte (construct.hpp:34-46)
-    explicit csa_wt(std::string const & text)
+    //! t_dens / t_inv_dens (csa_wt.hpp:50-51) are run-time arguments here; 0 = the reference's defaults 32 / 64
+    explicit csa_wt(std::string const & text, uint32_t t_dens = 0, uint32_t t_inv_dens = 0)
     {
         sdslgpu_handle * h = nullptr;
-        check(sdslgpu_csa_create(reinterpret_cast<uint8_t const *>(text.data()), text.size(), detail::default_device(), SDSLGPU_F_DEFAULT, &h), "csa_wt");
+        check(sdslgpu_csa_create_ex(reinterpret_cast<uint8_t const *>(text.data()), text.size(), detail::default_device(), SDSLGPU_F_DEFAULT, t_dens, t_inv_dens, &h),
+              "csa_wt");
         m_image = detail::adopt(h);
         check(sdslgpu_size(h, &m_size), "size");
     }

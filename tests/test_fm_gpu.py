@@ -22,10 +22,16 @@ def _patterns(t, rng, k, maxlen=24):
     return pats + [b"", t, t[:4], t + b"x"]
 
 
-def test_fm_catalogue(pkg, oracle, orc):
+# the searches run on the one-hot occurrence bitmaps by default and on the wavelet tree alone with F_COMPACT
+VARIANTS = [("occ16", 0), ("compact", 8)]
+
+
+@pytest.mark.parametrize("variant,flags", VARIANTS)
+def test_fm_catalogue(pkg, oracle, orc, variant, flags):
     rng = np.random.default_rng(21)
+    assert pkg.F_COMPACT == 8
     for name, t in texts.text_catalogue(zero_free=True, large=True):
-        with pkg.CsaWt(t) as csa:
+        with pkg.CsaWt(t, flags=flags) as csa:
             assert csa.size == len(t) + 1, name
             pats = _patterns(t, rng, 1500)
             flat, off = pkg.csr_patterns(pats)
@@ -107,7 +113,8 @@ def test_gpu_suffix_array_matches_host_sais(pkg, monkeypatch):
             assert (b.count(flat, off) == want[0]).all() and (b.sa(i) == want[1]).all(), name
 
 
-def test_extract(pkg, oracle, orc):
+@pytest.mark.parametrize("variant,flags", VARIANTS)
+def test_extract(pkg, oracle, orc, variant, flags):
     """sdsl::extract (suffix_array_algorithm.hpp:590-610) == the text itself, == the oracle / reference"""
     rng = np.random.default_rng(41)
     for name, t in texts.text_catalogue(zero_free=True, large=True):
@@ -116,7 +123,7 @@ def test_extract(pkg, oracle, orc):
         b = rng.integers(0, n, 3000, dtype=np.uint64)
         e = np.minimum(b + rng.integers(0, 100, 3000, dtype=np.uint64), np.uint64(n - 1))
         b[0], e[0] = 0, min(n - 1, 5000)
-        with pkg.CsaWt(t) as csa:
+        with pkg.CsaWt(t, flags=flags) as csa:
             off, out = csa.extract(b, e)
             assert off[-1] == int((e - b + 1).sum())
             for k in range(0, len(b), 7):
@@ -130,6 +137,54 @@ def test_extract(pkg, oracle, orc):
                         assert rc.extract(int(b[k]), int(e[k])) == out[int(off[k]) : int(off[k + 1])].tobytes(), (name, "reference")
             # an index ingested from the reference's serialised bytes extracts the same text
             if len(t) <= 200000 and orc.ref_available():
-                with pkg.load_sdsl(orc.Ref().csa(t).serialize(), pkg.KIND_CSA_WT) as loaded:
+                with pkg.load_sdsl(orc.Ref().csa(t).serialize(), pkg.KIND_CSA_WT, flags=flags) as loaded:
                     l_off, l_out = loaded.extract(b, e)
                     assert (l_out == out).all(), (name, "loaded blob")
+
+
+@pytest.mark.parametrize("sa_dens,isa_dens", [(1, 1), (3, 5), (8, 16), (64, 128)])
+def test_sampling_densities_do_not_change_results(pkg, oracle, sa_dens, isa_dens):
+    """t_dens / t_inv_dens (csa_wt.hpp:50-51) trade memory for LF steps; count / locate / csa[i] / extract stay
+    those of the default-density oracle"""
+    rng = np.random.default_rng(43)
+    for name, t in texts.text_catalogue(zero_free=True):
+        n = len(t) + 1
+        pats = _patterns(t, rng, 200)
+        flat, off = pkg.csr_patterns(pats)
+        i = rng.integers(0, n, 2000, dtype=np.uint64)
+        b = rng.integers(0, n, 500, dtype=np.uint64)
+        e = np.minimum(b + rng.integers(0, 60, 500, dtype=np.uint64), np.uint64(n - 1))
+        chk = oracle.csa(t)
+        with pkg.CsaWt(t, sa_dens=sa_dens, isa_dens=isa_dens, flags=pkg.F_COMPACT if sa_dens == 3 else 0) as csa:
+            assert (csa.count(flat, off) == chk.count(flat, off)).all(), name
+            a, w = csa.locate(flat, off), chk.locate(flat, off)
+            assert (a[0] == w[0]).all() and (a[1] == w[1]).all(), name
+            assert (csa.sa(i) == chk.sa(i)).all(), name
+            got, want = csa.extract(b, e), chk.extract(b, e)
+            assert (got[0] == want[0]).all() and (got[1] == want[1]).all(), name
+
+
+@pytest.mark.parametrize("distinct", [1, 15, 16, 17, 32, 33, 255])
+def test_occ16_alphabet_edges(pkg, oracle, distinct):
+    """the occurrence bitmaps switch from one level to two at sigma = 17 (text symbols + the sentinel): both sides of
+    the switch, a level-0 bitmap with a single symbol, and the full byte alphabet"""
+    rng = np.random.default_rng(100 + distinct)
+    t = (rng.integers(0, distinct, 40000, dtype=np.uint8) + 1).astype(np.uint8).tobytes()
+    n = len(t) + 1
+    pats = _patterns(t, rng, 400, maxlen=6)
+    flat, off = pkg.csr_patterns(pats)
+    i = rng.integers(0, n, 3000, dtype=np.uint64)
+    b = rng.integers(0, n, 300, dtype=np.uint64)
+    e = np.minimum(b + rng.integers(0, 50, 300, dtype=np.uint64), np.uint64(n - 1))
+    chk = oracle.csa(t)
+    want = (chk.count(flat, off, want_l=True), chk.sa(i), chk.extract(b, e))
+    for flags in (0, pkg.F_COMPACT):
+        with pkg.CsaWt(t, flags=flags) as csa:
+            cnt, l = csa.count(flat, off, want_l=True)
+            assert (cnt == want[0][0]).all() and (l[cnt > 0] == want[0][1][cnt > 0]).all(), (distinct, flags)
+            assert (csa.sa(i) == want[1]).all(), (distinct, flags)
+            got = csa.extract(b, e)
+            assert (got[0] == want[2][0]).all() and (got[1] == want[2][1]).all(), (distinct, flags)
+    # the default index pays for its speed in device memory; the compact one is the wavelet tree alone
+    with pkg.CsaWt(t) as a, pkg.CsaWt(t, flags=pkg.F_COMPACT) as c:
+        assert a.device_bytes > c.device_bytes

@@ -136,6 +136,15 @@ def run_c2(args):
                 record(f"C2 2^{args.nbits_log2}-bit random bit_vector", f"select_{b}", nq, ms, best, 48, par, cpu)
             ms, best = time_gpu(lambda: bv.access(d_idx, out=d_out), args.reps)
             record(f"C2 2^{args.nbits_log2}-bit random bit_vector", "access", nq, ms, best, 24, None)
+            # the same batch in ascending order: neighbouring queries share sectors, the kernel is unchanged
+            d_sorted = torch.sort(d_idx.view(torch.int64)).values
+            d_chk = torch.empty_like(d_out)
+            bv.rank(d_idx, 1, out=d_chk)
+            want_sorted = torch.sort(d_chk).values  # rank is monotone in i
+            ms, best = time_gpu(lambda: bv.rank(d_sorted, 1, out=d_out), args.reps)
+            record(f"C2 2^{args.nbits_log2}-bit random bit_vector", "rank_1, queries sorted ascending", nq, ms, best, 40,
+                   bool(torch.equal(d_out, want_sorted)), None)
+            del d_sorted, d_chk, want_sorted
         bv.close()
         del d_idx, d_out
     torch.cuda.empty_cache()
@@ -247,7 +256,7 @@ def run_c5(args):
     if ref:
         t, w = time_cpu(lambda: ref.count(flat[: ns * plen], off[: ns + 1], threads=CORES))
         par, cpu = par and bool((cnt[:ns] == w).all()), {"qps": ns / t, "cores": CORES, "sample": ns, "build_s": ref_build}
-    record(cfg, "count()", npat, ms, best, 7324, par, cpu, {"index_bytes": csa.device_bytes, "build_s": build_s, "unit": "patterns/s"})
+    record(cfg, "count()", npat, ms, best, 19 * 2 * 32, par, cpu, {"index_bytes": csa.device_bytes, "build_s": build_s, "unit": "patterns/s"})
     ms, best = time_gpu(lambda: csa.locate(d_flat, d_off), args.reps)
     occ_off, occ = csa.locate(d_flat, d_off)
     tot = int(occ.numel())
@@ -258,7 +267,39 @@ def run_c5(args):
         oo, oc = host(occ_off), host(occ)
         par = bool((oo[: nl + 1] == w[0]).all() and (oc[: int(w[0][-1])] == w[1]).all())
         cpu = {"qps": nl / t, "cores": CORES, "sample": nl}
-    record(cfg, "locate() (two passes: size, then fill)", npat, ms, best, 7324 + 2992 * tot / npat, par, cpu, {"occurrences": tot, "unit": "patterns/s"})
+    record(cfg, "locate()", npat, ms, best, 19 * 2 * 32 + 15.5 * 96 * tot / npat, par, cpu, {"occurrences": tot, "unit": "patterns/s"})
+    # uniformly random 20-mers: almost all absent -> the search stops after ~4 symbols
+    rflat = qr.integers(1, 256, npat * plen, dtype=np.uint8)
+    d_rflat = dev(rflat)
+    ms, best = time_gpu(lambda: csa.count(d_rflat, d_off), args.reps)
+    record(cfg, "count() of random 20-mers (absent)", npat, ms, best, 4 * 2 * 32, None, None, {"unit": "patterns/s"})
+    del d_rflat
+    # the same index with the wavelet tree as its only occurrence structure (SDSLGPU_F_COMPACT)
+    csa.close()
+    torch.cuda.empty_cache()
+    t0 = time.perf_counter()
+    csa = pkg.CsaWt(text, flags=pkg.F_COMPACT)
+    b2 = time.perf_counter() - t0
+    ms, best = time_gpu(lambda: csa.count(d_flat, d_off), args.reps)
+    par = bool((host(csa.count(d_flat, d_off)) == cnt).all())
+    record(cfg, "count() [F_COMPACT: wt_huff only]", npat, ms, best, 7324, par, None, {"index_bytes": csa.device_bytes, "build_s": b2, "unit": "patterns/s"})
+    ms, best = time_gpu(lambda: csa.locate(d_flat, d_off), args.reps)
+    o2, c2 = csa.locate(d_flat, d_off)
+    par = bool(torch.equal(o2, occ_off) and torch.equal(c2, occ))
+    record(cfg, "locate() [F_COMPACT: wt_huff only]", npat, ms, best, 7324 + 2992 * tot / npat, par, None, {"occurrences": tot, "unit": "patterns/s"})
+    del o2, c2
+    if args.dense_sa:
+        csa.close()
+        torch.cuda.empty_cache()
+        t0 = time.perf_counter()
+        csa = pkg.CsaWt(text, sa_dens=args.dense_sa, isa_dens=args.dense_sa)
+        b2 = time.perf_counter() - t0
+        ms, best = time_gpu(lambda: csa.locate(d_flat, d_off), args.reps)
+        o2, c2 = csa.locate(d_flat, d_off)
+        par = bool(torch.equal(o2, occ_off) and torch.equal(c2, occ))
+        record(cfg, f"locate() with t_dens = {args.dense_sa}", npat, ms, best, 19 * 2 * 32 + 96 * (args.dense_sa - 1) / 2 * tot / npat, par, None,
+               {"occurrences": tot, "index_bytes": csa.device_bytes, "build_s": b2, "unit": "patterns/s"})
+        del o2, c2
     if args.rrr_variant:
         csa.close()
         torch.cuda.empty_cache()
@@ -268,11 +309,6 @@ def run_c5(args):
         ms, best = time_gpu(lambda: csa.count(d_flat, d_off), args.reps)
         par = bool((host(csa.count(d_flat, d_off)) == cnt).all())
         record(cfg, "count() on csa_wt<wt_huff<rrr_vector<63>>>", npat, ms, best, 7324, par, None, {"index_bytes": csa.device_bytes, "build_s": b2, "unit": "patterns/s"})
-    # uniformly random 20-mers: almost all absent -> early exit
-    rflat = qr.integers(1, 256, npat * plen, dtype=np.uint8)
-    d_rflat = dev(rflat)
-    ms, best = time_gpu(lambda: csa.count(d_rflat, d_off), args.reps)
-    record(cfg, "count() of random 20-mers (absent)", npat, ms, best, 7324, None, None, {"unit": "patterns/s"})
     csa.close()
     torch.cuda.empty_cache()
 
@@ -291,6 +327,7 @@ def main():
     ap.add_argument("--csa-log2", type=int, default=28)
     ap.add_argument("--csa-ref", type=int, default=1)
     ap.add_argument("--rrr-variant", type=int, default=1)
+    ap.add_argument("--dense-sa", type=int, default=4, help="also time locate() on an index with this t_dens (0 = skip)")
     ap.add_argument("--patterns", type=float, default=1e6)
     ap.add_argument("--cpu-sample", type=float, default=2e7)
     ap.add_argument("--reps", type=int, default=5)
