@@ -62,6 +62,17 @@ extern "C" {
                                     and the BWT (5.6 bytes/symbol) so that a step is 2 gathers and
                                     an LF step 3; results are identical.  Implied by SDSLGPU_F_RRR_BV. */
 
+/* bit patterns of sdslgpu_rank / sdslgpu_select / sdslgpu_arg_count on KIND_BV handles: the reference's
+ * <t_b, t_pat_len> template arguments (rank_support_v.hpp:46, select_support_mcl.hpp:54).  An occurrence of a
+ * two-bit pattern "xy" is counted / reported at the position of y, its second bit (x = the bit before it), as
+ * in the reference (select_support.hpp:233-238). */
+#define SDSLGPU_PAT_0 0
+#define SDSLGPU_PAT_1 1
+#define SDSLGPU_PAT_10 2 /* <10,2>: a 1 followed by a 0 */
+#define SDSLGPU_PAT_01 3 /* <01,2> */
+#define SDSLGPU_PAT_00 4 /* <00,2> */
+#define SDSLGPU_PAT_11 5 /* <11,2> */
+
 typedef struct sdslgpu_handle sdslgpu_handle;
 
 /* ---- library ------------------------------------------------------------------------------- */
@@ -91,7 +102,7 @@ int sdslgpu_free(sdslgpu_handle *h);
 int sdslgpu_kind(const sdslgpu_handle *h, int *kind);
 /* size(): number of bits (bit vectors) / symbols (wavelet trees) / text length + 1 (csa) */
 int sdslgpu_size(const sdslgpu_handle *h, uint64_t *size);
-/* number of b-bits in a bit-vector handle (= rank_b(size)); select domain is 1..arg_count */
+/* number of b-bits (occurrences of pattern b) in a bit-vector handle (= rank_b(size)); select domain is 1..arg_count */
 int sdslgpu_arg_count(const sdslgpu_handle *h, int b, uint64_t *count);
 /* bytes of device memory held by the handle */
 int sdslgpu_device_bytes(const sdslgpu_handle *h, uint64_t *bytes);
@@ -101,13 +112,17 @@ int sdslgpu_device_bytes(const sdslgpu_handle *h, uint64_t *bytes);
 /* out[k] = number of b-bits in [0, idx[k]),  0 <= idx[k] <= size.
  * Replaces rank_support_v<b,1>::rank (rank_support_v.hpp:129-139),
  *          rank_support_rrr<b,63>::rank (rrr_vector.hpp:503-544),
- *          rank_support_sd<b>::rank (sd_vector.hpp:553-575).   b in {0,1}. */
+ *          rank_support_sd<b>::rank (sd_vector.hpp:553-575).   b in {0,1}.
+ * On KIND_BV handles b may also be SDSLGPU_PAT_10 / _01 / _00 / _11: rank_support_v<10|01|00|11, 2>::rank
+ * (rank_support.hpp:161-284).  The first such call builds that pattern's indicator vector on the device
+ * (+ 1.14 bits/bit for rank, + samples for select) and later calls reuse it. */
 int sdslgpu_rank(const sdslgpu_handle *h, int b, const uint64_t *idx, uint64_t n, uint64_t *out, void *stream);
 
 /* out[k] = position of the i[k]-th b-bit, 1 <= i[k] <= arg_count(b).
  * Replaces select_support_mcl<b,1>::select (select_support_mcl.hpp:384-439),
  *          select_support_rrr<b,63>::select (rrr_vector.hpp:639-726),
- *          select_support_sd<b>::select (sd_vector.hpp:621-664). */
+ *          select_support_sd<b>::select (sd_vector.hpp:621-664);
+ *          on KIND_BV also select_support_mcl<10|01|00|11, 2>::select (select_support.hpp:204-405). */
 int sdslgpu_select(const sdslgpu_handle *h, int b, const uint64_t *i, uint64_t n, uint64_t *out, void *stream);
 
 /* out[k] = bit idx[k] (0/1), 0 <= idx[k] < size.  Replaces operator[] of bit_vector

@@ -174,9 +174,31 @@ uint64_t orc_bv_serialize(const uint64_t *w, uint64_t nbits, uint8_t *out, uint6
 /* a3: rank_support_v<b,1>                                                                    */
 /* ------------------------------------------------------------------------------------------ */
 
-static uint32_t args(uint64_t w, int b) /* rank_support.hpp:112-115 / :138-141 */
+/* The word of `pattern ends here` indicator bits every trait function of the reference is a popcount / select of:
+ *   pattern codes b: 0, 1 (one bit, rank_support.hpp:105-158, select_support.hpp:120-201) and the two-bit patterns
+ *   2 = "10", 3 = "01", 4 = "00", 5 = "11" (rank_support.hpp:161-284, select_support.hpp:204-405; bits.hpp:565-583).
+ * carry = msb of the previous word, or init_carry() for word 0 (rank_support.hpp:184-187,214-217,247-250,280-283;
+ * select_support.hpp:239-242,276-279,339-342,398-401): "01" and "00" start with 1, so bit 0 never ends a pattern. */
+static uint64_t pat_map(const uint64_t *w, uint64_t k, int b)
 {
-    return orc_cnt(b ? w : ~w);
+    uint64_t x = w[k], c;
+    if (b < 2)
+        return b ? x : ~x;
+    c = k ? (w[k - 1] >> 63) : (uint64_t)(b == 3 || b == 4);
+    switch (b) {
+    case 2:
+        return ((x << 1) | c) & ~x; /* map10 */
+    case 3:
+        return (x ^ ((x << 1) | c)) & x; /* map01 */
+    case 4:
+        return ~(x | ((x << 1) | c));
+    default:
+        return x & ((x << 1) | c);
+    }
+}
+static uint32_t args(const uint64_t *w, uint64_t k, int b) /* args_in_the_word */
+{
+    return orc_cnt(pat_map(w, k, b));
 }
 
 uint64_t orc_rank_v_table_words(uint64_t nbits) /* rank_support_v.hpp:79,84 */
@@ -193,7 +215,7 @@ void orc_rank_v_build(const uint64_t *w, uint64_t nbits, int b, uint64_t *B)
     B[0] = B[1] = 0;
     if (nbits == 0)
         return;
-    sum = args(w[0], b);
+    sum = args(w, 0, b);
     for (i = 1; i < W; ++i) {
         if ((i & 7) == 0) {
             j += 2;
@@ -203,7 +225,7 @@ void orc_rank_v_build(const uint64_t *w, uint64_t nbits, int b, uint64_t *B)
         } else {
             second |= sum << (63 - 9 * (i & 7));
         }
-        sum += args(w[i], b);
+        sum += args(w, i, b);
     }
     if (i & 7) {
         second |= sum << (63 - 9 * (i & 7));
@@ -221,10 +243,8 @@ uint64_t orc_rank_v(const uint64_t *w, const uint64_t *B, int b, uint64_t idx)
 {
     const uint64_t *p = B + ((idx >> 8) & ~1ULL);
     uint64_t r = p[0] + ((p[1] >> (63 - 9 * ((idx & 0x1FF) >> 6))) & 0x1FF);
-    if (idx & 0x3F) {
-        uint64_t x = w[idx >> 6];
-        r += orc_cnt((b ? x : ~x) & orc__lo_set((uint32_t)(idx & 0x3F)));
-    }
+    if (idx & 0x3F)
+        r += orc_cnt(pat_map(w, idx >> 6, b) & orc__lo_set((uint32_t)(idx & 0x3F)));
     return r;
 }
 
@@ -252,9 +272,15 @@ uint64_t orc_rank_v_serialize(const uint64_t *B, uint64_t nbits, uint8_t *out, u
 /* a4: select_support_mcl<b,1>                                                                */
 /* ------------------------------------------------------------------------------------------ */
 
-static int found_arg(const uint64_t *w, uint64_t i, int b) /* select_support.hpp:149-152,191-194 */
+static int found_arg(const uint64_t *w, uint64_t i, int b) /* select_support.hpp:149-152,191-194,233-238,270-275,334-337,392-397 */
 {
-    return (int)((w[i >> 6] >> (i & 63)) & 1) == b;
+    int cur = (int)((w[i >> 6] >> (i & 63)) & 1), prev;
+    if (b < 2)
+        return cur == b;
+    if (i == 0)
+        return 0;
+    prev = (int)((w[(i - 1) >> 6] >> ((i - 1) & 63)) & 1);
+    return prev == (b == 2 || b == 5) && cur == (b == 3 || b == 5);
 }
 
 #define SBS 4096u
@@ -364,13 +390,16 @@ orc_selmcl *orc_select_mcl_build(const uint64_t *w, uint64_t nbits, int b)
         ones += orc_cnt(x);
     }
     s->arg_cnt = b ? ones : nbits - ones;
+    if (b >= 2) /* cnt_onezero_bits / cnt_zeroone_bits (util.hpp:689-726), arg_cnt of "00"/"11" (select_support.hpp:286-301,350-365) */
+        for (s->arg_cnt = 0, k = 0; k < nbits; ++k)
+            s->arg_cnt += (uint64_t)found_arg(w, k, b);
     if (s->arg_cnt == 0)
         return s;
     s->sb = (s->arg_cnt + SBS - 1) / SBS;
     orc__iv_init(&s->superblock, s->sb, (uint8_t)s->logn);
     s->longsb = (orc_iv *)calloc(s->sb + 1, sizeof(orc_iv));
     s->mini = (orc_iv *)calloc(s->sb + 1, sizeof(orc_iv));
-    if (nbits < 100000) /* ctor dispatch, :121-128 */
+    if (b >= 2 || nbits < 100000) /* ctor dispatch, :121-128: two-bit patterns always take init_slow */
         init_slow(s, w);
     else
         init_fast(s, w);
@@ -411,14 +440,14 @@ uint64_t orc_select_mcl(const orc_selmcl *s, const uint64_t *w, uint64_t i)
     pos += 1;
     wp = pos >> 6;
     wo = (uint32_t)(pos & 63);
-    x = (s->b ? w[wp] : ~w[wp]) & ~orc__lo_set(wo);
+    x = pat_map(w, wp, s->b) & ~orc__lo_set(wo); /* args_in_the_first_word with init_carry(data, word_pos) */
     a = orc_cnt(x);
     if (a >= i)
         return (wp << 6) + orc_sel(x, (uint32_t)i);
     sum = a;
     for (;;) {
         ++wp;
-        x = s->b ? w[wp] : ~w[wp];
+        x = pat_map(w, wp, s->b); /* args_in_the_word with get_carry of the previous word */
         a = orc_cnt(x);
         if (sum + a >= i)
             return (wp << 6) + orc_sel(x, (uint32_t)(i - sum));

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -77,7 +78,29 @@ struct ref_bv
     select_support_mcl<1> s1;
     select_support_mcl<0> s0;
     bool has_select = false;
+    // two-bit patterns, built on first use: codes 2 = "10", 3 = "01", 4 = "00", 5 = "11"
+    // (rank_support_test.cpp:44-47, select_support_test.cpp:39-42 instantiate exactly these)
+    std::unique_ptr<rank_support_v<10, 2>> r10;
+    std::unique_ptr<rank_support_v<01, 2>> r01;
+    std::unique_ptr<rank_support_v<00, 2>> r00;
+    std::unique_ptr<rank_support_v<11, 2>> r11;
+    std::unique_ptr<select_support_mcl<10, 2>> s10;
+    std::unique_ptr<select_support_mcl<01, 2>> s01;
+    std::unique_ptr<select_support_mcl<00, 2>> s00;
+    std::unique_ptr<select_support_mcl<11, 2>> s11;
 };
+
+template <class S, class F>
+void run_pat(std::unique_ptr<S> & sup, bit_vector const * bv, uint64_t n, int threads, F f)
+{
+    if (!sup)
+        sup = std::make_unique<S>(bv);
+    S const * p = sup.get();
+    parallel_for(n, threads, [=](uint64_t lo, uint64_t hi) {
+        for (uint64_t k = lo; k < hi; ++k)
+            f(p, k);
+    });
+}
 
 struct ref_rrr
 {
@@ -137,7 +160,18 @@ extern "C"
     void ref_bv_rank(void * p, int pattern, uint64_t const * idx, uint64_t n, uint64_t * out, int threads)
     {
         auto * h = static_cast<ref_bv *>(p);
-        if (pattern)
+        auto rk = [=](auto const * s, uint64_t k) {
+            out[k] = s->rank(idx[k]);
+        };
+        if (pattern == 2)
+            run_pat(h->r10, &h->bv, n, threads, rk);
+        else if (pattern == 3)
+            run_pat(h->r01, &h->bv, n, threads, rk);
+        else if (pattern == 4)
+            run_pat(h->r00, &h->bv, n, threads, rk);
+        else if (pattern == 5)
+            run_pat(h->r11, &h->bv, n, threads, rk);
+        else if (pattern)
             parallel_for(n, threads, [=](uint64_t lo, uint64_t hi) {
                 for (uint64_t k = lo; k < hi; ++k)
                     out[k] = h->r1.rank(idx[k]);
@@ -151,7 +185,18 @@ extern "C"
     void ref_bv_select(void * p, int pattern, uint64_t const * idx, uint64_t n, uint64_t * out, int threads)
     {
         auto * h = static_cast<ref_bv *>(p);
-        if (pattern)
+        auto sl = [=](auto const * s, uint64_t k) {
+            out[k] = s->select(idx[k]);
+        };
+        if (pattern == 2)
+            run_pat(h->s10, &h->bv, n, threads, sl);
+        else if (pattern == 3)
+            run_pat(h->s01, &h->bv, n, threads, sl);
+        else if (pattern == 4)
+            run_pat(h->s00, &h->bv, n, threads, sl);
+        else if (pattern == 5)
+            run_pat(h->s11, &h->bv, n, threads, sl);
+        else if (pattern)
             parallel_for(n, threads, [=](uint64_t lo, uint64_t hi) {
                 for (uint64_t k = lo; k < hi; ++k)
                     out[k] = h->s1.select(idx[k]);

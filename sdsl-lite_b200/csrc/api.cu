@@ -391,6 +391,38 @@ static int new_handle(int kind, int device, uint32_t flags, sdslgpu_handle ** ou
 
 using namespace sdslgpu;
 
+// pattern codes: 0 / 1 everywhere; the two-bit patterns only on plain bit vectors
+static int check_pattern(sdslgpu_handle const * h, int b, char const * who)
+{
+    if (b == 0 || b == 1)
+        return SDSLGPU_OK;
+    if (b >= SDSLGPU_PAT_10 && b <= SDSLGPU_PAT_11 && h->kind == SDSLGPU_KIND_BV)
+        return SDSLGPU_OK;
+    set_error("%s: pattern %d is not supported by this handle (0 / 1; SDSLGPU_PAT_10..11 on bit_vector handles)", who, b);
+    return SDSLGPU_EINVAL;
+}
+
+// the indicator-vector image of a two-bit pattern, built on first use (the handle is logically const)
+static int pattern_image(sdslgpu_handle const * ch, int b, BvImage const ** out)
+{
+    sdslgpu_handle * h = const_cast<sdslgpu_handle *>(ch);
+    std::lock_guard<std::mutex> lock(h->pat_mu);
+    int k = b - SDSLGPU_PAT_10;
+    if (!h->pat_ready[k])
+    {
+        if (h->flags & SDSLGPU_F_NO_SELECT)
+        {
+            set_error("two-bit patterns need a handle created without SDSLGPU_F_NO_SELECT");
+            return SDSLGPU_EINVAL;
+        }
+        DeviceGuard g(h->device);
+        SG_TRY(bv_build_pattern(h->pool, h->bv, b, h->pat[k], nullptr));
+        h->pat_ready[k] = true;
+    }
+    *out = &h->pat[k];
+    return SDSLGPU_OK;
+}
+
 extern "C"
 {
 
@@ -503,11 +535,17 @@ extern "C"
     int sdslgpu_arg_count(const sdslgpu_handle * h, int b, uint64_t * count)
     {
         SG_TRY(check_handle(h));
-        if (b != 0 && b != 1)
-            return SDSLGPU_EINVAL;
+        SG_TRY(check_pattern(h, b, "sdslgpu_arg_count"));
         switch (h->kind)
         {
         case SDSLGPU_KIND_BV:
+            if (b >= 2)
+            {
+                BvImage const * img = nullptr;
+                SG_TRY(pattern_image(h, b, &img));
+                *count = img->ones;
+                return SDSLGPU_OK;
+            }
             *count = b ? h->bv.ones : h->bv.nbits - h->bv.ones;
             return SDSLGPU_OK;
         case SDSLGPU_KIND_RRR63:
@@ -530,11 +568,7 @@ extern "C"
     int sdslgpu_rank(const sdslgpu_handle * h, int b, const uint64_t * idx, uint64_t n, uint64_t * out, void * stream)
     {
         SG_TRY(check_handle(h));
-        if (b != 0 && b != 1)
-        {
-            set_error("sdslgpu_rank: pattern must be 0 or 1");
-            return SDSLGPU_EINVAL;
-        }
+        SG_TRY(check_pattern(h, b, "sdslgpu_rank"));
         if (n && !out)
         {
             set_error("sdslgpu_rank: null output");
@@ -544,6 +578,14 @@ extern "C"
         switch (h->kind)
         {
         case SDSLGPU_KIND_BV:
+            if (b >= 2)
+            { // rank_support_v<pattern, 2>: one-bit rank over the pattern's indicator vector
+                BvImage const * img = nullptr;
+                SG_TRY(pattern_image(h, b, &img));
+                return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
+                    return bv_rank_device(*img, SDSLGPU_F_DEFAULT, 1, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
+                });
+            }
             return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
                 return bv_rank_device(h->bv, h->flags, b, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
             });
@@ -563,11 +605,7 @@ extern "C"
     int sdslgpu_select(const sdslgpu_handle * h, int b, const uint64_t * i, uint64_t n, uint64_t * out, void * stream)
     {
         SG_TRY(check_handle(h));
-        if (b != 0 && b != 1)
-        {
-            set_error("sdslgpu_select: pattern must be 0 or 1");
-            return SDSLGPU_EINVAL;
-        }
+        SG_TRY(check_pattern(h, b, "sdslgpu_select"));
         if (n && !out)
         {
             set_error("sdslgpu_select: null output");
@@ -577,6 +615,14 @@ extern "C"
         switch (h->kind)
         {
         case SDSLGPU_KIND_BV:
+            if (b >= 2)
+            {
+                BvImage const * img = nullptr;
+                SG_TRY(pattern_image(h, b, &img));
+                return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
+                    return bv_select_device(*img, 1, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
+                });
+            }
             return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
                 return bv_select_device(h->bv, b, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
             });

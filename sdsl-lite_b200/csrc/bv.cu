@@ -353,6 +353,66 @@ int bv_build(DevicePool & pool, BvImage & v, uint32_t flags, uint64_t const * wo
     return SDSLGPU_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// two-bit patterns: rank_support_v<10|01|00|11, 2> / select_support_mcl<..., 2> (rank_support.hpp:161-284,
+// select_support.hpp:204-405).  Every trait function of the reference is a popcount / select over the word of
+// "the pattern ENDS at this bit" indicators (bits.hpp:565-583 map10 / map01, and the 00 / 11 analogues), with the
+// carry = msb of the previous word and init_carry() for word 0.  So the supports of pattern p over v ARE the
+// one-bit supports over that indicator vector: build it once from the sector blocks and reuse every kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bv_chunk32(bvblock const * __restrict__ blocks, uint64_t c)
+{
+    // 224 = 7 * 32: an aligned 32-bit chunk of the original vector never straddles a block
+    return ld_nc_u32(&blocks[c / 7].d[c % 7]);
+}
+
+__global__ void bv_pattern_words_kernel(bvblock const * __restrict__ blocks, uint64_t nbits, int pat, uint64_t * __restrict__ words, uint64_t nwords)
+{
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nwords; k += stride)
+    {
+        uint64_t nchunks = (nbits + 31) / 32;
+        uint64_t lo = bv_chunk32(blocks, 2 * k), hi = (2 * k + 1 < nchunks) ? bv_chunk32(blocks, 2 * k + 1) : 0u;
+        uint64_t x = lo | (hi << 32);
+        uint64_t c = k ? (uint64_t)(bv_chunk32(blocks, 2 * k - 1) >> 31) : (uint64_t)(pat == SDSLGPU_PAT_01 || pat == SDSLGPU_PAT_00);
+        uint64_t y = (x << 1) | c, m;
+        switch (pat)
+        {
+        case SDSLGPU_PAT_10:
+            m = y & ~x;
+            break;
+        case SDSLGPU_PAT_01:
+            m = (x ^ y) & x;
+            break;
+        case SDSLGPU_PAT_00:
+            m = ~(x | y);
+            break;
+        default:
+            m = x & y;
+            break;
+        }
+        uint64_t base = k * 64;
+        if (base + 64 > nbits) // occurrences end inside the vector (util.hpp:689-726, select_support.hpp:286-301)
+            m &= (nbits > base) ? lo_set64((uint32_t)(nbits - base)) : 0ull;
+        words[k] = m;
+    }
+}
+
+int bv_build_pattern(DevicePool & pool, BvImage const & src, int pat, BvImage & dst, cudaStream_t s)
+{
+    uint64_t nwords = (src.nbits + 63) >> 6;
+    uint64_t * words = nullptr;
+    SG_TRY(pool.alloc_t(&words, nwords + 2));
+    if (nwords)
+    {
+        bv_pattern_words_kernel<<<blocks_for(nwords), kThreads, 0, s>>>(src.blocks, src.nbits, pat, words, nwords);
+        SG_CUDA(cudaGetLastError());
+    }
+    int st = bv_build(pool, dst, SDSLGPU_F_DEFAULT, words, true, src.nbits, s);
+    pool.release(words);
+    return st;
+}
+
 int bv_build_sdsl_rank_table(DevicePool & pool, BvImage & v, int b, cudaStream_t s)
 {
     // rank_support_v.hpp:79,84: 2 words for an empty vector, else 2 * (((n+63)>>9) + 1)

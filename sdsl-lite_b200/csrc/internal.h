@@ -251,6 +251,10 @@ struct sdslgpu_handle
     sdslgpu::DevicePool pool;
     sdslgpu::Staging staging;
     sdslgpu::BvImage bv;        // KIND_BV
+    // KIND_BV: indicator vectors of the two-bit patterns 10 / 01 / 00 / 11, built on first use (bv.cu)
+    sdslgpu::BvImage pat[4];
+    bool pat_ready[4] = {false, false, false, false};
+    std::mutex pat_mu;
     sdslgpu::WtHuffImage wt;    // KIND_WT_HUFF (and the BWT of KIND_CSA_WT)
     sdslgpu::CsaImage csa;      // KIND_CSA_WT
     sdslgpu::WtIntImage wti;    // KIND_WT_INT
@@ -304,6 +308,7 @@ inline RrrBits rrr_bits(WtHuffImage const & w)
 // bv.cu
 int bv_build(DevicePool & pool, BvImage & v, uint32_t flags, uint64_t const * words_host_or_dev, bool words_on_device, uint64_t nbits, cudaStream_t s);
 int bv_build_sdsl_rank_table(DevicePool & pool, BvImage & v, int b, cudaStream_t s);
+int bv_build_pattern(DevicePool & pool, BvImage const & src, int pat, BvImage & dst, cudaStream_t s);
 int bv_rank_device(BvImage const & v, uint32_t flags, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 int bv_select_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 int bv_access_device(BvImage const & v, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);

@@ -165,10 +165,18 @@ protected:
     }
     t_vec const * m_v;
 };
+
+//! <t_b, t_pat_len> of the reference (rank_support.hpp:105-284: 0, 1, and 10 / 01 / 00 / 11 with length 2; note that
+//! the literals 01 and 00 are the integers 1 and 0) -> the C ABI's pattern code
+constexpr int pattern_code(uint8_t t_b, uint8_t t_pat_len)
+{
+    return t_pat_len == 1 ? (t_b ? SDSLGPU_PAT_1 : SDSLGPU_PAT_0)
+                          : (t_b == 10 ? SDSLGPU_PAT_10 : t_b == 1 ? SDSLGPU_PAT_01 : t_b == 0 ? SDSLGPU_PAT_00 : SDSLGPU_PAT_11);
+}
 } // namespace detail
 
 //! rank_support_v<t_b,1> concept (rank_support_v.hpp:47-192) for any bit-vector type of this header.
-template <uint8_t t_b, class t_vec>
+template <uint8_t t_b, class t_vec, uint8_t t_pat_len = 1>
 class rank_support : public detail::support_base<t_vec>
 {
     using base = detail::support_base<t_vec>;
@@ -178,7 +186,7 @@ public:
     enum
     {
         bit_pat = t_b,
-        bit_pat_len = 1
+        bit_pat_len = t_pat_len
     };
     using base::base;
     size_type rank(size_type i) const
@@ -194,7 +202,7 @@ public:
     //! batch: out[k] = rank(idx[k]); pointers may be host or device memory
     void rank(uint64_t const * idx, size_type n, uint64_t * out, void * stream = nullptr) const
     {
-        check(sdslgpu_rank(this->image(), t_b, idx, n, out, stream), "rank");
+        check(sdslgpu_rank(this->image(), detail::pattern_code(t_b, t_pat_len), idx, n, out, stream), "rank");
     }
     std::vector<uint64_t> rank(std::vector<uint64_t> const & idx) const
     {
@@ -204,7 +212,7 @@ public:
     }
 };
 
-template <uint8_t t_b, class t_vec>
+template <uint8_t t_b, class t_vec, uint8_t t_pat_len = 1>
 class select_support : public detail::support_base<t_vec>
 {
     using base = detail::support_base<t_vec>;
@@ -214,7 +222,7 @@ public:
     enum
     {
         bit_pat = t_b,
-        bit_pat_len = 1
+        bit_pat_len = t_pat_len
     };
     using base::base;
     size_type select(size_type i) const
@@ -229,7 +237,7 @@ public:
     }
     void select(uint64_t const * i, size_type n, uint64_t * out, void * stream = nullptr) const
     {
-        check(sdslgpu_select(this->image(), t_b, i, n, out, stream), "select");
+        check(sdslgpu_select(this->image(), detail::pattern_code(t_b, t_pat_len), i, n, out, stream), "select");
     }
     std::vector<uint64_t> select(std::vector<uint64_t> const & i) const
     {
@@ -240,13 +248,13 @@ public:
 };
 
 template <uint8_t t_b = 1, uint8_t t_pat_len = 1>
-using rank_support_v = rank_support<t_b, bit_vector>;
+using rank_support_v = rank_support<t_b, bit_vector, t_pat_len>;
 template <uint8_t t_b = 1, uint8_t t_pat_len = 1>
-using select_support_mcl = select_support<t_b, bit_vector>;
+using select_support_mcl = select_support<t_b, bit_vector, t_pat_len>;
 //! rank_support_v5 (rank_support_v5.hpp:131-149) answers exactly what rank_support_v answers; on the device both
 //! map onto the same sector blocks, so the alias keeps call sites that name the 6.25 %-overhead variant compiling.
 template <uint8_t t_b = 1, uint8_t t_pat_len = 1>
-using rank_support_v5 = rank_support<t_b, bit_vector>;
+using rank_support_v5 = rank_support<t_b, bit_vector, t_pat_len>;
 
 // ------------------------------------------------------------------------------------------------------
 // compressed bit vectors (rrr_vector.hpp:67-109, sd_vector.hpp:131-163)

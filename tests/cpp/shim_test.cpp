@@ -54,6 +54,30 @@ void check_bitvector(bit_vector const & plain, t_vec const & v)
         EXPECT(s1.select(1) == pos1[0] && s1(pos1.size()) == pos1.back());
 }
 
+// rank_support_v<pat, 2> / select_support_mcl<pat, 2> the way rank_support_test.cpp:44-47 and
+// select_support_test.cpp:39-42 instantiate them; an occurrence sits at the position of its second bit
+template <uint8_t t_b>
+void check_pattern(bit_vector const & bv, bool prev, bool cur)
+{
+    rank_support_v<t_b, 2> rs(&bv);
+    select_support_mcl<t_b, 2> ss(&bv);
+    std::vector<uint64_t> idx(bv.size() + 1), pos;
+    for (uint64_t j = 0; j <= bv.size(); ++j)
+        idx[j] = j;
+    auto got = rs.rank(idx);
+    for (uint64_t j = 0; j < bv.size(); ++j)
+    {
+        EXPECT(got[j] == pos.size());
+        if (j > 0 && bv[j - 1] == prev && bv[j] == cur)
+            pos.push_back(j);
+    }
+    EXPECT(got[bv.size()] == pos.size());
+    std::vector<uint64_t> k(pos.size());
+    for (size_t q = 0; q < k.size(); ++q)
+        k[q] = q + 1;
+    EXPECT(ss.select(k) == pos);
+}
+
 int main(int argc, char ** argv)
 {
     if (argc > 1)
@@ -68,6 +92,10 @@ int main(int argc, char ** argv)
                 if ((rng() % 10000) < d * 10000)
                     bv.set(j, true);
             check_bitvector<bit_vector, rank_support_v<1>, rank_support_v<0>, select_support_mcl<1>, select_support_mcl<0>>(bv, bv);
+            check_pattern<10>(bv, true, false);
+            check_pattern<01>(bv, false, true);
+            check_pattern<00>(bv, false, false);
+            check_pattern<11>(bv, true, true);
             rrr_vector<63> rrr(bv);
             check_bitvector<rrr_vector<63>, rrr_vector<63>::rank_1_type, rrr_vector<63>::rank_0_type, rrr_vector<63>::select_1_type,
                             rrr_vector<63>::select_0_type>(bv, rrr);

@@ -145,3 +145,48 @@ def test_select_clustered_large(pkg):
             k = torch.from_numpy(cases.select_queries(m, 17, 2_000_000).view(np.int64)).cuda()
             p = bv.select(k, b)
             assert bool((bv.rank(p, b) == k - 1).all()) and bool((bv.access(p) == b).all()), b
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["b200_layout", "sdsl_layout"])
+def test_two_bit_patterns(pkg, oracle, orc, flags):
+    """rank_support_v<10|01|00|11, 2> / select_support_mcl<..., 2> (rank_support_test.cpp:44-47,
+    select_support_test.cpp:39-42) over the catalogue: oracle, reference, and dirty tail bits past size()"""
+    assert (pkg.PAT_10, pkg.PAT_01, pkg.PAT_00, pkg.PAT_11) == (2, 3, 4, 5)
+    for cid, w, nbits in cases.bitvector_catalogue(large=True):
+        with pkg.BitVector(w, nbits, flags=flags) as bv:
+            idx = cases.rank_queries(nbits, 13, 40000)
+            for name, chk in _checkers(oracle, orc, w, nbits):
+                for b in (2, 3, 4, 5):
+                    assert (bv.rank(idx, b) == chk.rank(idx, b)).all(), (cid, name, "rank", b)
+                    m = bv.arg_count(b)
+                    assert m == int(chk.rank([nbits], b)[0]), (cid, name, "arg_count", b)
+                    q = cases.select_queries(m, 14, 40000)
+                    if len(q):
+                        assert (bv.select(q, b) == chk.select(q, b)).all(), (cid, name, "select", b)
+                    # out of domain: defined here, UB in the reference
+                    assert bv.rank(np.array([nbits + 1], np.uint64), b)[0] == pkg.NPOS
+                    assert (bv.select(np.array([0, m + 1], np.uint64), b) == pkg.NPOS).all()
+    # a compressed vector has no two-bit supports in the reference either
+    w, nbits = cases.random_words(5000, 3), 5000
+    with pkg.RrrVector(w, nbits) as r:
+        with pytest.raises(pkg.SdslGpuError):
+            r.rank(np.array([1], np.uint64), 2)
+
+
+def test_two_bit_patterns_large_properties(pkg):
+    """2^30-bit vector: select(rank(i)+1) >= i, rank(select(k)+1) == k, and the four pattern counts add up to n-1"""
+    import torch
+
+    nbits = 1 << 30
+    g = torch.Generator(device="cuda").manual_seed(5)
+    words = torch.randint(-(2**63), 2**63 - 1, (nbits // 64,), dtype=torch.int64, device="cuda", generator=g)
+    with pkg.BitVector(words, nbits) as bv:
+        total = 0
+        k = torch.randint(1, 1 << 27, (2_000_000,), dtype=torch.int64, device="cuda", generator=g)
+        for b in (2, 3, 4, 5):
+            m = bv.arg_count(b)
+            total += m
+            assert abs(m - nbits / 4) < 1e6
+            pos = bv.select(k, b)
+            assert bool((bv.rank(pos + 1, b) == k).all()) and bool((bv.rank(pos, b) == k - 1).all())
+        assert total == nbits - 1

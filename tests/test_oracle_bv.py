@@ -56,3 +56,37 @@ def test_rank_select_vs_naive(oracle):
             pos = np.nonzero(hit)[0].astype(np.uint64)
             if len(pos):
                 assert (ob.select(np.arange(1, len(pos) + 1, dtype=np.uint64), b) == pos).all(), cid
+
+
+# two-bit patterns: code -> (previous bit, current bit); the position of an occurrence is that of its SECOND bit
+PATTERNS = {2: (1, 0), 3: (0, 1), 4: (0, 0), 5: (1, 1)}
+
+
+def pattern_hits(bits, code):
+    prev, cur = PATTERNS[code]
+    hit = np.zeros(len(bits), dtype=bool)
+    if len(bits) > 1:
+        hit[1:] = (bits[:-1] == prev) & (bits[1:] == cur)
+    return hit
+
+
+def test_two_bit_patterns_vs_naive_and_reference(oracle, ref):
+    """rank_support_v<10|01|00|11, 2> and select_support_mcl<..., 2> (rank_support.hpp:161-284,
+    select_support.hpp:204-405): the restatement against the definition the reference's tests use
+    (rank_support_test.cpp:109-126, select_support_test.cpp:85-104) and against the reference itself"""
+    for cid, w, nbits in cases.bitvector_catalogue(large=False):
+        bits = cases.unpack_bits(w, nbits).astype(np.int64)
+        ob, rb = oracle.bv(w, nbits), ref.bv(w, nbits)
+        every = np.arange(nbits + 1, dtype=np.uint64) if nbits <= 20000 else cases.rank_queries(nbits, 5, 20000)
+        for code in PATTERNS:
+            hit = pattern_hits(bits, code)
+            pref = np.concatenate([[0], np.cumsum(hit)]).astype(np.uint64)
+            got = ob.rank(every, code)
+            assert (got == pref[every.astype(np.int64)]).all(), (cid, code, "rank vs naive")
+            assert (got == rb.rank(every, code)).all(), (cid, code, "rank vs reference")
+            pos = np.nonzero(hit)[0].astype(np.uint64)
+            if len(pos):
+                k = np.arange(1, len(pos) + 1, dtype=np.uint64) if len(pos) <= 20000 else cases.select_queries(len(pos), 6, 20000)
+                got = ob.select(k, code)
+                assert (got == pos[k.astype(np.int64) - 1]).all(), (cid, code, "select vs naive")
+                assert (got == rb.select(k, code)).all(), (cid, code, "select vs reference")
