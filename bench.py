@@ -149,6 +149,8 @@ def main():
     ap.add_argument("--ref-sample", type=float, default=2e7, help="queries per step for the CPU arms")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--order", default="auto", choices=["auto", "direct", "binned"],
+                    help="sdslgpu_set_batch_order: auto picks the binned pipeline for this workload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -175,6 +177,10 @@ def main():
 
     words, idx, qr = make_workload(nbits, nq, rank)
     bv = pkg.BitVector(words, nbits, device=local)
+    bv.set_batch_order({"auto": pkg.ORDER_AUTO, "direct": pkg.ORDER_DIRECT, "binned": pkg.ORDER_BINNED}[args.order])
+    # what AUTO resolves to (include/sdslgpu.h): binned iff index >= 192 MB, n >= 2^21 and n >= index_bytes / 64
+    index_bytes = (nbits // 224 + 1) * 32
+    binned = args.order == "binned" or (args.order == "auto" and index_bytes >= 192 << 20 and nq >= 1 << 21 and nq >= index_bytes // 64)
     m = bv.arg_count(1)
     sel = qr.integers(1, m + 1, nq, dtype=np.uint64)
 
@@ -284,13 +290,19 @@ def main():
         if os.path.exists(tp) and nbits == 1 << 33 and nq == int(1e8):  # measured for exactly this launch shape
             tj = json.load(open(tp))
             traffic = {k: v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in tj.items() if isinstance(v, dict)}
+        k_rank, k_sel = ("bv_rank_kernel", "bv_select_kernel")
+        n_rank, n_sel = "bv_rank_kernel<1,2>", "bv_select_kernel<1>"
+        if binned:  # one op = three launches; the roofline entry is for the whole op (all three inside the event pair)
+            k_rank, k_sel = "binned_rank_pipeline", "binned_select_pipeline"
+            n_rank = "bin_tile_sort_kernel<1> + bin_apply_kernel<BvRankOp<1>> + bin_unsort_kernel"
+            n_sel = "bin_tile_sort_kernel<1> + bin_apply_kernel<BvSelectOp<1>> + bin_unsort_kernel"
 
         def roof(bytes_per_q, ms, kernel=None):
             a = nq * bytes_per_q / (ms * 1e-3) / 1e9
             return {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": traffic.get(kernel),
                     "peak_source": peak_src, "algorithmic_bytes_per_query": bytes_per_q, "kernel_ms": ms}
-        r_rank = dict(roof(RANK_BYTES, rank_ms, "bv_rank_kernel"), kernel="bv_rank_kernel<1,2>", qps=nq / (rank_ms * 1e-3))
-        r_sel = dict(roof(SELECT_BYTES, sel_ms, "bv_select_kernel"), kernel="bv_select_kernel<1>", qps=nq / (sel_ms * 1e-3))
+        r_rank = dict(roof(RANK_BYTES, rank_ms, k_rank), kernel=n_rank, launches=3 if binned else 1, qps=nq / (rank_ms * 1e-3))
+        r_sel = dict(roof(SELECT_BYTES, sel_ms, k_sel), kernel=n_sel, launches=3 if binned else 1, qps=nq / (sel_ms * 1e-3))
         dominant = r_sel if sel_ms >= rank_ms else r_rank
         line = {
             "metric": "rank/select queries/s on 1 GiB bit_vector", "value": value, "unit": "queries/s",
@@ -301,7 +313,8 @@ def main():
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": 2 * nq * 8, "d2h_bytes_per_step": 2 * nq * 8,
                     "ms_per_step": e2e_s * 1e3, "path": "sdslgpu_rank/sdslgpu_select with pinned host buffers (chunked H2D/kernel/D2H)"},
-            "gpu_launches": 2 * args.steps, "clocks": clocks, "parity": parity,
+            "gpu_launches": (6 if binned else 2) * args.steps, "batch_order": "binned" if binned else "direct",
+            "clocks": clocks, "parity": parity,
             "index_device_bytes": bv.device_bytes,
         }
         print(json.dumps(line), flush=True)

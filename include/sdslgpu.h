@@ -125,6 +125,20 @@ int sdslgpu_rank(const sdslgpu_handle *h, int b, const uint64_t *idx, uint64_t n
  *          on KIND_BV also select_support_mcl<10|01|00|11, 2>::select (select_support.hpp:204-405). */
 int sdslgpu_select(const sdslgpu_handle *h, int b, const uint64_t *i, uint64_t n, uint64_t *out, void *stream);
 
+/* Order of work inside one sdslgpu_rank / sdslgpu_select call on a KIND_BV handle; never changes a result.
+ *   SDSLGPU_ORDER_DIRECT  one thread per query in the caller's order: one random DRAM gather per query
+ *   SDSLGPU_ORDER_BINNED  the batch is counting-sorted tile by tile into ~24 MB chunks of the index, answered chunk
+ *                         by chunk (L2-resident gathers) and un-sorted again; needs ~14 bytes of stream-ordered
+ *                         scratch per query (cudaMallocAsync on the call's stream)
+ *   SDSLGPU_ORDER_AUTO    (default) BINNED when the index is larger than the L2 (>= 192 MB) and the batch is dense
+ *                         enough for queries to share cache lines (>= 2^21 queries and >= 1 query per 64 bytes of
+ *                         index), else DIRECT
+ * The reference has no counterpart (its queries are scalar calls, rank_support_v.hpp:129-139). */
+#define SDSLGPU_ORDER_AUTO 0
+#define SDSLGPU_ORDER_DIRECT 1
+#define SDSLGPU_ORDER_BINNED 2
+int sdslgpu_set_batch_order(sdslgpu_handle *h, int order);
+
 /* out[k] = bit idx[k] (0/1), 0 <= idx[k] < size.  Replaces operator[] of bit_vector
  * (int_vector.hpp:1900-1904), rrr_vector (rrr_vector.hpp:276-298), sd_vector (sd_vector.hpp:328-349). */
 int sdslgpu_access(const sdslgpu_handle *h, const uint64_t *idx, uint64_t n, uint64_t *out, void *stream);

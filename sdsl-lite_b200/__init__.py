@@ -27,6 +27,7 @@ NPOS = np.uint64(0xFFFFFFFFFFFFFFFF)
 F_DEFAULT, F_SDSL_LAYOUT, F_NO_SELECT, F_RRR_BV, F_COMPACT = 0, 1, 2, 4, 8
 KIND_BV, KIND_RRR63, KIND_SD, KIND_WT_HUFF, KIND_WT_INT, KIND_CSA_WT = 1, 2, 3, 4, 5, 6
 PAT_0, PAT_1, PAT_10, PAT_01, PAT_00, PAT_11 = 0, 1, 2, 3, 4, 5  # <t_b, t_pat_len> of rank_support_v / select_support_mcl
+ORDER_AUTO, ORDER_DIRECT, ORDER_BINNED = 0, 1, 2  # sdslgpu_set_batch_order
 
 u64p = C.POINTER(C.c_uint64)
 vp = C.c_void_p
@@ -45,6 +46,7 @@ _SIGNATURES = [
     ("sdslgpu_rank", C.c_int, [vp, C.c_int, vp, C.c_uint64, vp, vp]),
     ("sdslgpu_select", C.c_int, [vp, C.c_int, vp, C.c_uint64, vp, vp]),
     ("sdslgpu_access", C.c_int, [vp, vp, C.c_uint64, vp, vp]),
+    ("sdslgpu_set_batch_order", C.c_int, [vp, C.c_int]),
     ("sdslgpu_bv_serialize", C.c_int, [vp, C.c_int, vp, C.c_uint64, u64p]),
     ("sdslgpu_wt_huff_create", C.c_int, [vp, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(vp)]),
     ("sdslgpu_wt_sigma", C.c_int, [vp, u64p]),
@@ -216,6 +218,10 @@ class BitVector(_Handle):
         _check(lib().sdslgpu_bv_create(p if n else None, nbits, device, flags, C.byref(self._h)))
         self.nbits = nbits
         self.flags = flags
+
+    def set_batch_order(self, order):
+        """ORDER_AUTO / ORDER_DIRECT / ORDER_BINNED: how large rank / select batches are executed (never changes a result)"""
+        _check(lib().sdslgpu_set_batch_order(self._h, int(order)))
 
     def serialize(self, what):
         """SDSL-format bytes (what: 0 bit_vector, 1 rank_support_v<1>, 2 rank_support_v<0>); needs F_SDSL_LAYOUT"""

@@ -351,6 +351,19 @@ static bool is_byte_wt(sdslgpu_handle const * h)
     return h->kind == SDSLGPU_KIND_WT_HUFF || h->kind == SDSLGPU_KIND_CSA_WT;
 }
 
+// keep freed scratch / staging blocks cached in the device's stream-ordered pool instead of returning them to the
+// driver at every synchronisation (the default release threshold is 0: a 1 GB scratch would be re-mapped per call)
+static void keep_stream_pool_cached(int device)
+{
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+    {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+}
+
 // validates the device (no CPU fallback) and allocates an empty handle of the given kind
 static int new_handle(int kind, int device, uint32_t flags, sdslgpu_handle ** out)
 {
@@ -366,17 +379,7 @@ static int new_handle(int kind, int device, uint32_t flags, sdslgpu_handle ** ou
         set_error("device %d out of range (%d CUDA devices); there is no CPU fallback", device, ndev);
         return SDSLGPU_ECUDA;
     }
-    {
-        // keep freed staging blocks cached in the device's stream-ordered pool instead of returning them to the
-        // driver at every synchronisation (the default release threshold is 0)
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
-        {
-            uint64_t keep = UINT64_MAX;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        cudaGetLastError();
-    }
+    keep_stream_pool_cached(device);
     sdslgpu_handle * h = new (std::nothrow) sdslgpu_handle;
     if (!h)
         return SDSLGPU_ENOMEM;
@@ -466,6 +469,7 @@ extern "C"
             set_error("cannot select CUDA device %d", device);
             return SDSLGPU_ECUDA;
         }
+        keep_stream_pool_cached(device);
         sdslgpu_handle * h = new (std::nothrow) sdslgpu_handle;
         if (!h)
             return SDSLGPU_ENOMEM;
@@ -562,6 +566,26 @@ extern "C"
     {
         SG_TRY(check_handle(h));
         *bytes = h->pool.bytes;
+        return SDSLGPU_OK;
+    }
+
+    int sdslgpu_set_batch_order(sdslgpu_handle * h, int order)
+    {
+        SG_TRY(check_handle(h));
+        if (h->kind != SDSLGPU_KIND_BV)
+        {
+            set_error("sdslgpu_set_batch_order: only bit_vector handles have a binned batch path");
+            return SDSLGPU_ENOTSUP;
+        }
+        if (order != SDSLGPU_ORDER_AUTO && order != SDSLGPU_ORDER_DIRECT && order != SDSLGPU_ORDER_BINNED)
+        {
+            set_error("sdslgpu_set_batch_order: unknown order %d", order);
+            return SDSLGPU_EINVAL;
+        }
+        std::lock_guard<std::mutex> lock(h->pat_mu);
+        h->bv.order = order;
+        for (int k = 0; k < 4; ++k)
+            h->pat[k].order = order;
         return SDSLGPU_OK;
     }
 

@@ -1,0 +1,359 @@
+// binned.cu — the op-independent parts of the locality-ordered batch pipeline (binned.cuh): tile counting sort,
+// un-sort, plan / scratch, and the plain bit vector's rank / select ops on top of it
+// (rank_support_v.hpp:129-139, select_support_mcl.hpp:384-439 — same results, different order of work).
+#include <cstdlib>
+
+#include "binned.cuh"
+#include "bv_device.cuh"
+
+namespace sdslgpu
+{
+
+static constexpr int kPer = kTile / kTileThreads;
+
+// ------------------------------------------------------------------------------------------------
+// 1. tile-local counting sort by bin
+//    key = q - sub (sub = 0 for rank, 1 for select); valid iff key <= maxkey.
+//    Persistent CTAs (two per SM); the 64 KB of keys of a CTA's NEXT tile are fetched by one TMA bulk copy
+//    (cp.async.bulk + mbarrier) while the current tile is scanned, scattered and written out, so DRAM reads never
+//    pause for the barrier phases.  kTma = false: plain loads (key array not 16-byte aligned).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(void const * p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, void const * src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do
+    {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+template <bool kTma>
+__global__ void __launch_bounds__(kTileThreads, 2) bin_tile_sort_kernel(uint64_t const * __restrict__ q,
+                                                                        uint64_t n,
+                                                                        uint64_t sub,
+                                                                        uint64_t maxkey,
+                                                                        uint32_t shift,
+                                                                        uint32_t nb,
+                                                                        uint64_t ntiles,
+                                                                        uint32_t * __restrict__ recs,
+                                                                        uint16_t * __restrict__ lp,
+                                                                        uint16_t * __restrict__ loff)
+{
+    extern __shared__ __align__(128) uint8_t sort_smem[];
+    uint32_t * srec = reinterpret_cast<uint32_t *>(sort_smem);                    // kTile * 4 bytes
+    uint64_t * skey = reinterpret_cast<uint64_t *>(sort_smem + kTile * 4);        // kTile * 8 bytes (kTma only)
+    // counts, then exclusive offsets; entry nb+1 = queries in the tile.  Two copies used alternately, so that zeroing
+    // the next tile's counters never races with a slow thread still reading this tile's offsets
+    __shared__ uint32_t cnt2[2][kMaxBins + 2];
+    __shared__ __align__(8) uint64_t bar_mem;
+    uint32_t const tid = threadIdx.x;
+    uint32_t const bar = smem_u32(&bar_mem), skey_addr = smem_u32(skey);
+    uint64_t const mask = (1ull << shift) - 1ull; // shift <= 32
+    uint32_t parity = 0;
+    if (kTma)
+    {
+        if (tid == 0)
+        {
+            mbar_init(bar, 1);
+            if ((uint64_t)(blockIdx.x + 1) * kTile <= n) // a full first tile: fetch it
+                tma_load_1d(skey_addr, q + (uint64_t)blockIdx.x * kTile, kTile * 8, bar);
+        }
+    }
+    uint32_t flip = 0;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, flip ^= 1u)
+    {
+        uint32_t * const cnt = cnt2[flip];
+        uint64_t const base = tile * kTile;
+        bool const full = kTma && base + kTile <= n; // partial last tile: plain loads
+        for (uint32_t k = tid; k < nb + 2; k += kTileThreads)
+            cnt[k] = 0;
+        __syncthreads(); // counters zeroed (and mbarrier initialised); previous tile's srec fully written out
+        if (full)
+        {
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        }
+        uint32_t binr[kPer], rec[kPer]; // bin << 16 | rank of the query among the tile's queries of that bin
+#pragma unroll
+        for (int u = 0; u < kPer; ++u)
+        {
+            uint32_t j = (uint32_t)u * kTileThreads + tid;
+            uint64_t p = base + j;
+            binr[u] = 0xFFFFFFFFu;
+            rec[u] = 0;
+            if (p < n)
+            {
+                uint64_t key = (full ? skey[j] : ld_stream_u64(q + p)) - sub;
+                uint32_t b = (key <= maxkey) ? (uint32_t)(key >> shift) : nb;
+                rec[u] = (uint32_t)(key & mask);
+                binr[u] = (b << 16) | atomicAdd(&cnt[b], 1u);
+            }
+        }
+        __syncthreads(); // counts complete; every key has been read out of skey
+        if (kTma && tid == 0)
+        {
+            uint64_t next = tile + gridDim.x;
+            if (next < ntiles && (next + 1) * kTile <= n)
+                tma_load_1d(skey_addr, q + next * kTile, kTile * 8, bar);
+        }
+        if (tid < 32)
+        { // exclusive scan of the nb+1 counters; entry nb+1 receives the total
+            uint32_t carry = 0;
+            for (uint32_t c0 = 0; c0 < nb + 2; c0 += 32)
+            {
+                uint32_t k = c0 + tid;
+                uint32_t v = (k <= nb) ? cnt[k] : 0u, x = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1)
+                {
+                    uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+                    if ((int)tid >= d)
+                        x += y;
+                }
+                if (k < nb + 2)
+                    cnt[k] = carry + x - v;
+                carry += __shfl_sync(0xFFFFFFFFu, x, 31);
+            }
+        }
+        __syncthreads();
+        for (uint32_t k = tid; k < nb + 2; k += kTileThreads)
+            loff[tile * (nb + 2) + k] = (uint16_t)cnt[k];
+#pragma unroll
+        for (int u = 0; u < kPer; ++u)
+        {
+            if (binr[u] != 0xFFFFFFFFu)
+            {
+                uint32_t l = cnt[binr[u] >> 16] + (binr[u] & 0xFFFFu);
+                srec[l] = rec[u];
+                lp[base + (uint64_t)u * kTileThreads + tid] = (uint16_t)l;
+            }
+        }
+        __syncthreads();
+        uint32_t const total = cnt[nb]; // valid queries only: the out-of-domain slots are never read
+        for (uint32_t k = tid; k < total; k += kTileThreads)
+            recs[base + k] = srec[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3. back to the caller's order
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTileThreads, 2) bin_unsort_kernel(uint64_t const * __restrict__ res,
+                                                                     uint16_t const * __restrict__ lp,
+                                                                     uint16_t const * __restrict__ loff,
+                                                                     uint32_t nb,
+                                                                     uint64_t n,
+                                                                     uint64_t * __restrict__ out)
+{
+    extern __shared__ __align__(16) uint8_t unsort_smem[];
+    uint64_t * sres = reinterpret_cast<uint64_t *>(unsort_smem);
+    uint32_t const tid = threadIdx.x;
+    uint64_t const tile = blockIdx.x, first = tile * kTile;
+    uint32_t const nvalid = loff[tile * (nb + 2) + nb]; // slots >= nvalid hold the out-of-domain queries
+    uint32_t l[kPer];
+#pragma unroll
+    for (int u = 0; u < kPer; ++u)
+    {
+        uint64_t p = first + (uint64_t)u * kTileThreads + tid;
+        l[u] = (p < n) ? ld_stream_u16(lp + p) : 0xFFFFu;
+    }
+    for (uint32_t k = tid; k < nvalid; k += kTileThreads)
+        sres[k] = ld_stream_u64(res + first + k);
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kPer; ++u)
+    {
+        uint64_t p = first + (uint64_t)u * kTileThreads + tid;
+        if (p < n)
+            st_stream_u64(out + p, l[u] < nvalid ? sres[l[u]] : SDSLGPU_NPOS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static uint64_t chunk_target_bytes()
+{
+    if (char const * e = std::getenv("SDSLGPU_BIN_CHUNK_BYTES")) // test / tuning knob
+    {
+        long long v = std::atoll(e);
+        if (v > 0)
+            return (uint64_t)v;
+    }
+    return 24ull << 20;
+}
+
+// bins are equal ranges of the key space sized so that one bin's share of the index is ~24 MB
+bool bin_make_plan(uint64_t index_bytes, uint64_t maxkey, uint64_t n, BinPlan & p)
+{
+    uint64_t target = chunk_target_bytes();
+    uint64_t want = (index_bytes + target - 1) / target;
+    if (want < 1)
+        want = 1;
+    if (want > kMaxBins)
+        want = kMaxBins;
+    uint32_t s = 0;
+    while (s < 63 && (maxkey >> s) + 1 > want)
+        ++s;
+    if (s > 32)
+        return false;
+    p.shift = s;
+    p.nb = (uint32_t)((maxkey >> s) + 1);
+    p.ntiles = (n + kTile - 1) / kTile;
+    return p.ntiles < (1ull << 31);
+}
+
+bool bin_wanted(int order, uint64_t index_bytes, uint64_t n)
+{
+    if (order == SDSLGPU_ORDER_BINNED)
+        return true;
+    if (order == SDSLGPU_ORDER_DIRECT)
+        return false;
+    // auto: only when the index cannot live in L2 and the batch is dense enough that the queries of a bin share
+    // cache lines (>= 2 queries per 128-byte line of the index on average); a sparser batch misses in DRAM anyway
+    return index_bytes >= (192ull << 20) && n >= (1ull << 21) && n >= index_bytes / 64;
+}
+
+static constexpr uint64_t kTicketBytes = kTicketLanes * kTicketStride * 8;
+
+static uint64_t up256(uint64_t x)
+{
+    return (x + 255) & ~255ull;
+}
+
+int bin_scratch_alloc(BinScratch & w, BinPlan const & p, cudaStream_t s)
+{
+    uint64_t slots = p.ntiles * kTile;
+    uint64_t b_recs = up256(slots * 4), b_lp = up256(slots * 2), b_loff = up256(p.ntiles * (p.nb + 2) * 2), b_res = up256(slots * 8);
+    w.s = s;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&w.mem), kTicketBytes + b_recs + b_lp + b_loff + b_res, s);
+    if (e != cudaSuccess)
+    {
+        w.mem = nullptr;
+        return cuda_fail(e, "cudaMallocAsync (binned batch scratch)", __FILE__, __LINE__);
+    }
+    uint8_t * m = w.mem;
+    w.ticket = reinterpret_cast<unsigned long long *>(m);
+    m += kTicketBytes;
+    w.res = reinterpret_cast<uint64_t *>(m);
+    m += b_res;
+    w.recs = reinterpret_cast<uint32_t *>(m);
+    m += b_recs;
+    w.lp = reinterpret_cast<uint16_t *>(m);
+    m += b_lp;
+    w.loff = reinterpret_cast<uint16_t *>(m);
+    SG_CUDA(cudaMemsetAsync(w.ticket, 0, kTicketBytes, s));
+    return SDSLGPU_OK;
+}
+
+int bin_launch_tile_sort(BinPlan const & p, BinScratch const & w, uint64_t const * q, uint64_t n, uint64_t sub, uint64_t maxkey, cudaStream_t s)
+{
+    // persistent CTAs, two per SM (96 KB of shared memory each with the TMA key buffer)
+    unsigned grid = (unsigned)(p.ntiles < 2ull * kSmCount ? p.ntiles : 2ull * kSmCount);
+    if ((reinterpret_cast<uintptr_t>(q) & 15u) == 0)
+    {
+        int smem = kTile * 4 + kTile * 8;
+        SG_CUDA(cudaFuncSetAttribute(bin_tile_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        bin_tile_sort_kernel<true><<<grid, kTileThreads, smem, s>>>(q, n, sub, maxkey, p.shift, p.nb, p.ntiles, w.recs, w.lp, w.loff);
+    }
+    else
+        bin_tile_sort_kernel<false><<<grid, kTileThreads, kTile * 4, s>>>(q, n, sub, maxkey, p.shift, p.nb, p.ntiles, w.recs, w.lp, w.loff);
+    SG_CUDA(cudaGetLastError());
+    return SDSLGPU_OK;
+}
+
+int bin_launch_unsort(BinPlan const & p, BinScratch const & w, uint64_t n, uint64_t * out, cudaStream_t s)
+{
+    // 64 KB of dynamic shared memory for the result tile (attribute is per device / context: set on every call)
+    SG_CUDA(cudaFuncSetAttribute(bin_unsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTile * 8)));
+    bin_unsort_kernel<<<(unsigned)p.ntiles, kTileThreads, kTile * 8, s>>>(w.res, w.lp, w.loff, p.nb, n, out);
+    SG_CUDA(cudaGetLastError());
+    return SDSLGPU_OK;
+}
+
+unsigned bin_apply_grid(BinPlan const & p)
+{
+    uint64_t runs = (uint64_t)p.nb * p.ntiles;
+    uint64_t want = (runs + kThreads / 32 - 1) / (kThreads / 32), cap = (uint64_t)kSmCount * 8;
+    return (unsigned)(want < cap ? (want ? want : 1) : cap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// plain bit vector ops
+// ------------------------------------------------------------------------------------------------
+template <int B>
+struct BvRankOp
+{
+    static constexpr int kIlp = 2;
+    static constexpr uint32_t kSmem = 0;
+    BvView v;
+    __device__ __forceinline__ void stage(uint8_t *) const
+    {}
+    __device__ __forceinline__ uint64_t operator()(uint64_t pos) const
+    {
+        uint64_t blk = pos / kBlockBits;
+        uint32_t rem = (uint32_t)(pos - blk * kBlockBits);
+        uint32_t cnt, d[7];
+        ld_block(v.blocks + blk, cnt, d); // whole-line fill: the neighbours are wanted by other queries of the bin
+        uint64_t r = __ldg(v.top + (blk >> kSuperShift)) + cnt + block_prefix_popc(d, rem);
+        return B ? r : pos - r;
+    }
+};
+
+template <int B>
+struct BvSelectOp
+{
+    static constexpr int kIlp = 1;
+    static constexpr uint32_t kSmem = 0;
+    BvView v;
+    __device__ __forceinline__ void stage(uint8_t *) const
+    {}
+    __device__ __forceinline__ uint64_t operator()(uint64_t key) const
+    {
+        return bv_select<B>(v, key + 1);
+    }
+};
+
+bool bv_binned_wanted(BvImage const & v, uint64_t n)
+{
+    return bin_wanted(v.order, v.nblocks * sizeof(bvblock), n);
+}
+
+int bv_rank_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done)
+{
+    uint64_t bytes = v.nblocks * sizeof(bvblock);
+    if (b)
+        return bin_run(BvRankOp<1>{bv_view(v)}, bytes, 0, v.nbits, idx, n, out, s, done);
+    return bin_run(BvRankOp<0>{bv_view(v)}, bytes, 0, v.nbits, idx, n, out, s, done);
+}
+
+int bv_select_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done)
+{
+    *done = false;
+    uint64_t args = b ? v.ones : v.nbits - v.ones, bytes = v.nblocks * sizeof(bvblock);
+    if (args == 0)
+        return SDSLGPU_OK; // every query is out of domain: the direct kernel answers NPOS
+    if (b)
+        return bin_run(BvSelectOp<1>{bv_view(v)}, bytes, 1, args - 1, idx, n, out, s, done);
+    return bin_run(BvSelectOp<0>{bv_view(v)}, bytes, 1, args - 1, idx, n, out, s, done);
+}
+
+} // namespace sdslgpu

@@ -1,0 +1,150 @@
+// binned.cuh — locality-ordered execution of very large query batches whose answer lives near `key` in the index
+// (rank: key = position; select: key = i - 1, the i-th one sits at a position that grows with i).
+//
+// Same results as the one-thread-per-query kernels, different order of work.  A B200 serves ~38-44 G random DRAM
+// gathers/s whatever their width but several times that from the 126 MB L2.  For batches of tens of
+// millions of queries over an index larger than L2 the batch is therefore re-ordered so that all queries in flight
+// touch one L2-sized chunk of the index:
+//
+//   1. bin_tile_sort_kernel   one CTA per tile of 8192 queries: counting sort of the tile by bin = key >> shift
+//                             (a bin = a contiguous ~24 MB chunk of the index).  Writes, per tile, the 32-bit in-bin
+//                             offsets in bin order (`recs`), every query's slot (`lp`, u16) and the tile's bin
+//                             boundaries (`loff`, u16).  Streaming: 8 B read + 6 B written per query.
+//   2. bin_apply_kernel<Op>   warps take (bin, tile) runs from a global ticket counter in BIN-MAJOR order, so at any
+//                             moment the whole GPU gathers from one or two chunks: L2 hits after the first touch, and
+//                             the index is read from DRAM once per batch.  Results go to the runs' own slots.
+//   3. bin_unsort_kernel      one CTA per tile: the tile's results (contiguous) -> shared memory -> caller's order.
+//
+// No global sort, no scan across tiles; deterministic results.  ~22 B per query of extra coalesced streams next to
+// the 16 B of query + result every path moves.  (Storing rank results as u32 differences to the bin's first rank
+// halves two of those streams but the un-sort then needs the bin of every slot; measured, it gains nothing:
+// profiles/r01d_binned_v4_relative_*.)
+#pragma once
+#include "internal.h"
+
+namespace sdslgpu
+{
+
+static constexpr int kTile = 8192;        // queries per tile (slots fit u16)
+static constexpr int kTileThreads = 1024; // CTA size of the sort / un-sort kernels
+static constexpr uint32_t kMaxBins = 254; // valid bins; bin index nb collects the out-of-domain queries
+static constexpr uint32_t kTicketLanes = 32;  // independent ticket counters (128 bytes apart), run w belongs to counter w % 32
+static constexpr uint32_t kTicketStride = 16; // in u64 units
+
+struct BinPlan
+{
+    uint32_t shift = 0, nb = 0;
+    uint64_t ntiles = 0;
+};
+
+// scratch of one call, carved from a single stream-ordered allocation
+struct BinScratch
+{
+    uint8_t * mem = nullptr;
+    cudaStream_t s = nullptr;
+    uint32_t * recs = nullptr;
+    uint16_t * lp = nullptr;
+    uint16_t * loff = nullptr;
+    uint64_t * res = nullptr;
+    unsigned long long * ticket = nullptr;
+    ~BinScratch()
+    {
+        if (mem)
+            cudaFreeAsync(mem, s);
+    }
+};
+
+// binned.cu
+bool bin_make_plan(uint64_t index_bytes, uint64_t maxkey, uint64_t n, BinPlan & p);
+bool bin_wanted(int order, uint64_t index_bytes, uint64_t n);
+int bin_scratch_alloc(BinScratch & w, BinPlan const & p, cudaStream_t s);
+int bin_launch_tile_sort(BinPlan const & p, BinScratch const & w, uint64_t const * q, uint64_t n, uint64_t sub, uint64_t maxkey, cudaStream_t s);
+int bin_launch_unsort(BinPlan const & p, BinScratch const & w, uint64_t n, uint64_t * out, cudaStream_t s);
+unsigned bin_apply_grid(BinPlan const & p);
+
+// Op: plain-old-data functor with
+//   static constexpr int kIlp          independent gathers per lane and trip (1 or 2)
+//   static constexpr uint32_t kSmem    bytes of dynamic shared memory its tables need (0: none)
+//   __device__ void stage(uint8_t *)   copy tables into shared memory (called by every thread; must __syncthreads if kSmem)
+//   __device__ uint64_t operator()(uint64_t key) const
+template <class Op>
+__global__ void __launch_bounds__(kThreads) bin_apply_kernel(Op op,
+                                                             uint32_t const * __restrict__ recs,
+                                                             uint16_t const * __restrict__ loff,
+                                                             uint32_t shift,
+                                                             uint32_t nb,
+                                                             uint64_t ntiles,
+                                                             unsigned long long * __restrict__ ticket,
+                                                             uint64_t * __restrict__ res)
+{
+    extern __shared__ __align__(16) uint8_t bin_smem[];
+    op.stage(bin_smem);
+    uint32_t const lane = threadIdx.x & 31u;
+    uint64_t const runs = (uint64_t)nb * ntiles;
+    // Runs are handed out by ticket counters in increasing order, so the runs in flight are always one contiguous
+    // window of the bin-major sequence (about one run per resident warp: less than one bin) whatever the residency
+    // or the speed of individual warps.  32 counters, each owning the runs w = 32 k + c, keep the atomics off one address.
+    uint32_t const c = (blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) % kTicketLanes;
+    for (;;)
+    {
+        unsigned long long w0 = 0;
+        if (lane == 0)
+            w0 = atomicAdd(ticket + c * kTicketStride, 1ull);
+        w0 = __shfl_sync(0xFFFFFFFFu, w0, 0) * kTicketLanes + c;
+        if (w0 >= runs)
+            break;
+        {
+            uint64_t const w = w0;
+            uint32_t const b = (uint32_t)(w / ntiles);
+            uint64_t const t = w - (uint64_t)b * ntiles;
+            uint16_t const * o = loff + t * (nb + 2) + b;
+            uint32_t const o0 = __ldg(o), o1 = __ldg(o + 1);
+            uint64_t const hi = (uint64_t)b << shift;
+            uint32_t const * r_in = recs + t * kTile;
+            uint64_t * r_out = res + t * kTile;
+            if (Op::kIlp == 2)
+            {
+                for (uint32_t k = o0 + lane; k < o1; k += 64)
+                {
+                    uint32_t k2 = k + 32;
+                    bool two = k2 < o1;
+                    uint64_t p1 = hi + ld_stream_u32(r_in + k);
+                    uint64_t p2 = two ? hi + ld_stream_u32(r_in + k2) : p1;
+                    uint64_t a1 = op(p1);
+                    uint64_t a2 = op(p2);
+                    st_stream_u64(r_out + k, a1);
+                    if (two)
+                        st_stream_u64(r_out + k2, a2);
+                }
+            }
+            else
+            {
+                for (uint32_t k = o0 + lane; k < o1; k += 32)
+                    st_stream_u64(r_out + k, op(hi + ld_stream_u32(r_in + k)));
+            }
+        }
+    }
+}
+
+// the whole pipeline.  key = q - sub, in domain iff key <= maxkey; out-of-domain queries get SDSLGPU_NPOS.
+// *done = false (and nothing launched) when the plan does not fit (shift > 32, tile count overflow).
+template <class Op>
+int bin_run(Op const & op, uint64_t index_bytes, uint64_t sub, uint64_t maxkey, uint64_t const * q, uint64_t n, uint64_t * out, cudaStream_t s, bool * done)
+{
+    *done = false;
+    BinPlan p;
+    if (n == 0 || !bin_make_plan(index_bytes, maxkey, n, p))
+        return SDSLGPU_OK;
+    BinScratch w;
+    SG_TRY(bin_scratch_alloc(w, p, s));
+    SG_TRY(bin_launch_tile_sort(p, w, q, n, sub, maxkey, s));
+    if (Op::kSmem > 48 * 1024)
+        SG_CUDA(cudaFuncSetAttribute(bin_apply_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Op::kSmem));
+    bin_apply_kernel<Op><<<bin_apply_grid(p), kThreads, Op::kSmem, s>>>(op, w.recs, w.loff, p.shift, p.nb, p.ntiles, w.ticket, w.res);
+    SG_CUDA(cudaGetLastError());
+    SG_TRY(bin_launch_unsort(p, w, n, out, s));
+    *done = true;
+    return SDSLGPU_OK;
+}
+
+} // namespace sdslgpu

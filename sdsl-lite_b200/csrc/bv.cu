@@ -444,6 +444,13 @@ int bv_rank_device(BvImage const & v, uint32_t flags, int b, uint64_t const * id
 {
     if (n == 0)
         return SDSLGPU_OK;
+    if (!(flags & SDSLGPU_F_SDSL_LAYOUT) && bv_binned_wanted(v, n))
+    {
+        bool done = false;
+        SG_TRY(bv_rank_binned_device(v, b, idx, n, out, s, &done));
+        if (done)
+            return SDSLGPU_OK;
+    }
     constexpr int ILP = 2;
     unsigned grid = grid_for(n, ILP);
     if (flags & SDSLGPU_F_SDSL_LAYOUT)
@@ -472,6 +479,13 @@ int bv_select_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n,
     {
         set_error("select requested on a handle created with SDSLGPU_F_NO_SELECT");
         return SDSLGPU_ENOTSUP;
+    }
+    if (bv_binned_wanted(v, n))
+    {
+        bool done = false;
+        SG_TRY(bv_select_binned_device(v, b, idx, n, out, s, &done));
+        if (done)
+            return SDSLGPU_OK;
     }
     unsigned grid = grid_for(n);
     uint64_t args = b ? v.ones : v.nbits - v.ones;

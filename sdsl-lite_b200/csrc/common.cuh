@@ -76,6 +76,32 @@ __device__ __forceinline__ void st_stream_u64(uint64_t * p, uint64_t v)
     asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(v));
 }
 
+__device__ __forceinline__ uint32_t ld_stream_u32(uint32_t const * p)
+{
+    uint32_t v;
+    asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_stream_u16(uint16_t const * p)
+{
+    uint16_t v;
+    asm volatile("ld.global.cs.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream_u32(uint32_t * p, uint32_t v)
+{
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v));
+}
+
+__device__ __forceinline__ void st_stream(uint32_t * p, uint32_t v)
+{
+    st_stream_u32(p, v);
+}
+__device__ __forceinline__ void st_stream(uint64_t * p, uint64_t v)
+{
+    st_stream_u64(p, v);
+}
+
 // lo_set[k] for 0 <= k <= 63 (bits.hpp:194-211); k == 64 is never needed on the device paths
 __device__ __forceinline__ uint64_t lo_set64(uint32_t k)
 {

@@ -114,6 +114,7 @@ struct BvImage
     uint64_t * top = nullptr;   // absolute 1-count per superblock of 2^24 blocks
     uint64_t ntop = 0;
     uint64_t ones = 0;
+    int order = SDSLGPU_ORDER_AUTO; // sdslgpu_set_batch_order: direct / binned execution of large batches (binned.cu)
     // select samples, per pattern b: samp[b][j] = block holding the (j*S+1)-th b-bit; two sentinels
     uint32_t * samp[2] = {nullptr, nullptr};
     uint64_t nsamp[2] = {0, 0};
@@ -312,6 +313,10 @@ int bv_build_pattern(DevicePool & pool, BvImage const & src, int pat, BvImage & 
 int bv_rank_device(BvImage const & v, uint32_t flags, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 int bv_select_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 int bv_access_device(BvImage const & v, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
+// binned.cu: locality-ordered execution of large batches; *done = false means "not applicable, use the direct kernel"
+bool bv_binned_wanted(BvImage const & v, uint64_t n);
+int bv_rank_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done);
+int bv_select_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done);
 // wt.cu
 int wt_huff_upload(sdslgpu_handle * h, uint64_t size, uint64_t sigma, WtTree const & tree, uint64_t const * bv_words, uint64_t bv_bits, cudaStream_t s);
 int wt_huff_finish(sdslgpu_handle * h, uint64_t size, uint64_t sigma, WtTree const & tree, cudaStream_t s);

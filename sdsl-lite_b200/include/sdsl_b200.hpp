@@ -121,6 +121,11 @@ public:
         }
         return m_image.get();
     }
+    //! how large batches are executed: SDSLGPU_ORDER_AUTO (default) / _DIRECT / _BINNED; never changes a result
+    void batch_order(int order) const
+    {
+        check(sdslgpu_set_batch_order(const_cast<sdslgpu_handle *>(image()), order), "bit_vector::batch_order");
+    }
 
 private:
     void trim()

@@ -190,3 +190,77 @@ def test_two_bit_patterns_large_properties(pkg):
             pos = bv.select(k, b)
             assert bool((bv.rank(pos + 1, b) == k).all()) and bool((bv.rank(pos, b) == k - 1).all())
         assert total == nbits - 1
+
+
+@pytest.mark.parametrize("chunk_bytes", ["64", "4096", "1048576"])
+def test_binned_order_matches_direct_and_oracle(pkg, oracle, monkeypatch, chunk_bytes):
+    """ORDER_BINNED (binned.cu: tile counting sort -> bin-major gathers -> un-sort) forced onto the catalogue with
+    tiny bins (many bins, empty bins, bins of one block): same answers as the oracle for both patterns, for batches
+    shorter than a tile, of exactly one tile, ragged, and with out-of-domain queries mixed in"""
+    monkeypatch.setenv("SDSLGPU_BIN_CHUNK_BYTES", chunk_bytes)
+    for cid, w, nbits in cases.bitvector_catalogue(large=True):
+        o = oracle.bv(w, nbits)
+        with pkg.BitVector(w, nbits) as bv:
+            bv.set_batch_order(pkg.ORDER_BINNED)
+            for nq in (1, 777, 8192, 8193, 50001):
+                idx = cases.rank_queries(nbits, 31 + nq, nq)
+                bad = np.arange(len(idx)) % 97 == 5
+                idx_bad = idx.copy()
+                idx_bad[bad] = np.uint64(nbits + 1) + (idx[bad] << np.uint64(20))
+                for b in (1, 0):
+                    want = o.rank(idx, b)
+                    assert (bv.rank(idx, b) == want).all(), (cid, "rank", b, nq)
+                    want_bad = want.copy()
+                    want_bad[bad] = pkg.NPOS
+                    assert (bv.rank(idx_bad, b) == want_bad).all(), (cid, "rank+ood", b, nq)
+                    m = bv.arg_count(b)
+                    q = cases.select_queries(m, 32 + nq, nq)
+                    if len(q):
+                        wsel = o.select(q, b)
+                        assert (bv.select(q, b) == wsel).all(), (cid, "select", b, nq)
+                        qb = q.copy()
+                        badq = np.arange(len(q)) % 89 == 3
+                        qb[badq] = np.where(np.arange(len(q))[badq] % 2 == 0, 0, m + 1).astype(np.uint64)
+                        wb = wsel.copy()
+                        wb[badq] = pkg.NPOS
+                        assert (bv.select(qb, b) == wb).all(), (cid, "select+ood", b, nq)
+                    else:
+                        assert (bv.select(np.array([0, 1, 5], np.uint64), b) == pkg.NPOS).all()
+            # two-bit patterns ride on the same launchers
+            idx = cases.rank_queries(nbits, 5, 20000)
+            assert (bv.rank(idx, pkg.PAT_10) == o.rank(idx, pkg.PAT_10)).all(), (cid, "rank10")
+
+
+def test_binned_order_large_device_batches(pkg):
+    """2^31-bit vector (index > L2), 6e6 device-resident queries: AUTO picks the binned path; BINNED == DIRECT bit
+    for bit on uniform and on fully skewed batches (every query in one bin), both patterns, on a side stream"""
+    import torch
+
+    nbits = (1 << 31) + 4321
+    g = torch.Generator(device="cuda").manual_seed(9)
+    words = torch.randint(-(2**63), 2**63 - 1, ((nbits + 63) // 64,), dtype=torch.int64, device="cuda", generator=g)
+    nq = 6_000_000 + 17
+    with pkg.BitVector(words, nbits) as bv:
+        uni = torch.randint(0, nbits + 1, (nq,), dtype=torch.int64, device="cuda", generator=g)
+        skew = torch.randint(12345, 12345 + 5000, (nq,), dtype=torch.int64, device="cuda", generator=g)
+        mixed = uni.clone()
+        mixed[::3] = nbits + 7  # out of domain
+        st = torch.cuda.Stream()
+        for b in (1, 0):
+            m = bv.arg_count(b)
+            sel = torch.randint(1, m + 1, (nq,), dtype=torch.int64, device="cuda", generator=g)
+            sel_skew = torch.randint(m - 3000, m + 1, (nq,), dtype=torch.int64, device="cuda", generator=g)
+            res = {}
+            for order in (pkg.ORDER_DIRECT, pkg.ORDER_BINNED, pkg.ORDER_AUTO):
+                bv.set_batch_order(order)
+                torch.cuda.synchronize()
+                with torch.cuda.stream(st):
+                    res[order] = [bv.rank(x, b) for x in (uni, skew, mixed)] + [bv.select(x, b) for x in (sel, sel_skew)]
+                st.synchronize()
+            for k in range(5):
+                assert bool((res[pkg.ORDER_DIRECT][k] == res[pkg.ORDER_BINNED][k]).all()), (b, k, "binned")
+                assert bool((res[pkg.ORDER_DIRECT][k] == res[pkg.ORDER_AUTO][k]).all()), (b, k, "auto")
+            assert bool((res[pkg.ORDER_BINNED][2][::3] == -1).all())
+            p = res[pkg.ORDER_BINNED][3]
+            bv.set_batch_order(pkg.ORDER_DIRECT)
+            assert bool((bv.rank(p, b) == sel - 1).all())
