@@ -181,6 +181,11 @@ class _Handle:
         _check(lib().sdslgpu_arg_count(self._h, b, C.byref(v)))
         return v.value
 
+    def set_batch_order(self, order):
+        """ORDER_AUTO / ORDER_DIRECT / ORDER_BINNED: how large rank / select batches on bit-vector handles (plain, rrr,
+        sd) are executed; never changes a result"""
+        _check(lib().sdslgpu_set_batch_order(self._h, int(order)))
+
     def rank(self, idx, b=1, out=None, stream=None):
         p, n, keep, _ = _in_ptr(idx)
         po, o, _k = _out_like(idx, n, out)
@@ -218,10 +223,6 @@ class BitVector(_Handle):
         _check(lib().sdslgpu_bv_create(p if n else None, nbits, device, flags, C.byref(self._h)))
         self.nbits = nbits
         self.flags = flags
-
-    def set_batch_order(self, order):
-        """ORDER_AUTO / ORDER_DIRECT / ORDER_BINNED: how large rank / select batches are executed (never changes a result)"""
-        _check(lib().sdslgpu_set_batch_order(self._h, int(order)))
 
     def serialize(self, what):
         """SDSL-format bytes (what: 0 bit_vector, 1 rank_support_v<1>, 2 rank_support_v<0>); needs F_SDSL_LAYOUT"""

@@ -572,9 +572,9 @@ extern "C"
     int sdslgpu_set_batch_order(sdslgpu_handle * h, int order)
     {
         SG_TRY(check_handle(h));
-        if (h->kind != SDSLGPU_KIND_BV)
+        if (h->kind != SDSLGPU_KIND_BV && h->kind != SDSLGPU_KIND_SD && h->kind != SDSLGPU_KIND_RRR63)
         {
-            set_error("sdslgpu_set_batch_order: only bit_vector handles have a binned batch path");
+            set_error("sdslgpu_set_batch_order: only bit-vector handles (plain, sd, rrr) have a binned batch path");
             return SDSLGPU_ENOTSUP;
         }
         if (order != SDSLGPU_ORDER_AUTO && order != SDSLGPU_ORDER_DIRECT && order != SDSLGPU_ORDER_BINNED)
@@ -583,6 +583,7 @@ extern "C"
             return SDSLGPU_EINVAL;
         }
         std::lock_guard<std::mutex> lock(h->pat_mu);
+        h->order = order;
         h->bv.order = order;
         for (int k = 0; k < 4; ++k)
             h->pat[k].order = order;

@@ -45,6 +45,50 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     } while (!ok);
 }
 
+// key j of the tile: from the TMA buffer (complete tiles) or straight from global memory
+template <bool kFull>
+__device__ __forceinline__ bool tile_key(uint64_t const * __restrict__ src, uint32_t limit, uint32_t j, uint64_t sub, uint64_t & key)
+{
+    if (!kFull && j >= limit)
+        return false;
+    key = (kFull ? src[j] : ld_stream_u64(src + j)) - sub;
+    return true;
+}
+
+// pass A: histogram of the tile over the bins (bin nb = out of domain)
+template <bool kFull>
+__device__ __forceinline__ void tile_count(uint64_t const * __restrict__ src, uint32_t limit, uint64_t sub, uint64_t maxkey, uint32_t shift, uint32_t nb,
+                                           uint32_t * __restrict__ cnt, uint32_t tid)
+{
+#pragma unroll
+    for (int u = 0; u < kPer; ++u)
+    {
+        uint64_t key;
+        if (tile_key<kFull>(src, limit, (uint32_t)u * kTileThreads + tid, sub, key))
+            atomicAdd(&cnt[(key <= maxkey) ? (uint32_t)(key >> shift) : nb], 1u);
+    }
+}
+
+// pass B: every key takes the next free slot of its bin (cur[] starts at the bins' exclusive offsets): in-bin offsets
+// to shared memory in slot order, slots to `lp`.  Keeping nothing in registers between the passes (the keys are
+// re-read from shared memory) is what lets two 1024-thread CTAs share an SM without spills.
+template <bool kFull>
+__device__ __forceinline__ void tile_scatter(uint64_t const * __restrict__ src, uint32_t limit, uint64_t sub, uint64_t maxkey, uint32_t shift, uint32_t mask32,
+                                             uint32_t nb, uint32_t * __restrict__ cur, uint32_t * __restrict__ srec, uint16_t * __restrict__ lp_t, uint32_t tid)
+{
+#pragma unroll
+    for (int u = 0; u < kPer; ++u)
+    {
+        uint64_t key;
+        if (tile_key<kFull>(src, limit, (uint32_t)u * kTileThreads + tid, sub, key))
+        {
+            uint32_t l = atomicAdd(&cur[(key <= maxkey) ? (uint32_t)(key >> shift) : nb], 1u);
+            srec[l] = (uint32_t)key & mask32;
+            lp_t[u * kTileThreads] = (uint16_t)l;
+        }
+    }
+}
+
 template <bool kTma>
 __global__ void __launch_bounds__(kTileThreads, 2) bin_tile_sort_kernel(uint64_t const * __restrict__ q,
                                                                         uint64_t n,
@@ -58,15 +102,16 @@ __global__ void __launch_bounds__(kTileThreads, 2) bin_tile_sort_kernel(uint64_t
                                                                         uint16_t * __restrict__ loff)
 {
     extern __shared__ __align__(128) uint8_t sort_smem[];
-    uint32_t * srec = reinterpret_cast<uint32_t *>(sort_smem);                    // kTile * 4 bytes
-    uint64_t * skey = reinterpret_cast<uint64_t *>(sort_smem + kTile * 4);        // kTile * 8 bytes (kTma only)
-    // counts, then exclusive offsets; entry nb+1 = queries in the tile.  Two copies used alternately, so that zeroing
-    // the next tile's counters never races with a slow thread still reading this tile's offsets
+    uint32_t * srec = reinterpret_cast<uint32_t *>(sort_smem);             // kTile * 4 bytes
+    uint64_t * skey = reinterpret_cast<uint64_t *>(sort_smem + kTile * 4); // kTile * 8 bytes (kTma only)
+    // cnt: counts, then exclusive offsets (entry nb+1 = queries in the tile); two copies used alternately, so that
+    // zeroing the next tile's counters never races with a slow thread still reading this tile's.  cur: slot cursors.
     __shared__ uint32_t cnt2[2][kMaxBins + 2];
+    __shared__ uint32_t cur[kMaxBins + 2];
     __shared__ __align__(8) uint64_t bar_mem;
     uint32_t const tid = threadIdx.x;
     uint32_t const bar = smem_u32(&bar_mem), skey_addr = smem_u32(skey);
-    uint64_t const mask = (1ull << shift) - 1ull; // shift <= 32
+    uint32_t const mask32 = shift >= 32 ? 0xFFFFFFFFu : (1u << shift) - 1u; // shift <= 32
     uint32_t parity = 0;
     if (kTma)
     {
@@ -83,6 +128,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) bin_tile_sort_kernel(uint64_t
         uint32_t * const cnt = cnt2[flip];
         uint64_t const base = tile * kTile;
         bool const full = kTma && base + kTile <= n; // partial last tile: plain loads
+        uint32_t const limit = (n - base < (uint64_t)kTile) ? (uint32_t)(n - base) : (uint32_t)kTile;
         for (uint32_t k = tid; k < nb + 2; k += kTileThreads)
             cnt[k] = 0;
         __syncthreads(); // counters zeroed (and mbarrier initialised); previous tile's srec fully written out
@@ -90,30 +136,11 @@ __global__ void __launch_bounds__(kTileThreads, 2) bin_tile_sort_kernel(uint64_t
         {
             mbar_wait(bar, parity);
             parity ^= 1u;
+            tile_count<true>(skey, limit, sub, maxkey, shift, nb, cnt, tid);
         }
-        uint32_t binr[kPer], rec[kPer]; // bin << 16 | rank of the query among the tile's queries of that bin
-#pragma unroll
-        for (int u = 0; u < kPer; ++u)
-        {
-            uint32_t j = (uint32_t)u * kTileThreads + tid;
-            uint64_t p = base + j;
-            binr[u] = 0xFFFFFFFFu;
-            rec[u] = 0;
-            if (p < n)
-            {
-                uint64_t key = (full ? skey[j] : ld_stream_u64(q + p)) - sub;
-                uint32_t b = (key <= maxkey) ? (uint32_t)(key >> shift) : nb;
-                rec[u] = (uint32_t)(key & mask);
-                binr[u] = (b << 16) | atomicAdd(&cnt[b], 1u);
-            }
-        }
-        __syncthreads(); // counts complete; every key has been read out of skey
-        if (kTma && tid == 0)
-        {
-            uint64_t next = tile + gridDim.x;
-            if (next < ntiles && (next + 1) * kTile <= n)
-                tma_load_1d(skey_addr, q + next * kTile, kTile * 8, bar);
-        }
+        else
+            tile_count<false>(q + base, limit, sub, maxkey, shift, nb, cnt, tid);
+        __syncthreads();
         if (tid < 32)
         { // exclusive scan of the nb+1 counters; entry nb+1 receives the total
             uint32_t carry = 0;
@@ -129,27 +156,40 @@ __global__ void __launch_bounds__(kTileThreads, 2) bin_tile_sort_kernel(uint64_t
                         x += y;
                 }
                 if (k < nb + 2)
+                {
                     cnt[k] = carry + x - v;
+                    cur[k] = carry + x - v;
+                }
                 carry += __shfl_sync(0xFFFFFFFFu, x, 31);
             }
         }
         __syncthreads();
         for (uint32_t k = tid; k < nb + 2; k += kTileThreads)
             loff[tile * (nb + 2) + k] = (uint16_t)cnt[k];
-#pragma unroll
-        for (int u = 0; u < kPer; ++u)
+        if (full)
+            tile_scatter<true>(skey, limit, sub, maxkey, shift, mask32, nb, cur, srec, lp + base + tid, tid);
+        else
+            tile_scatter<false>(q + base, limit, sub, maxkey, shift, mask32, nb, cur, srec, lp + base + tid, tid);
+        __syncthreads(); // srec complete; every key has been read out of skey for the last time
+        if (kTma && tid == 0)
         {
-            if (binr[u] != 0xFFFFFFFFu)
-            {
-                uint32_t l = cnt[binr[u] >> 16] + (binr[u] & 0xFFFFu);
-                srec[l] = rec[u];
-                lp[base + (uint64_t)u * kTileThreads + tid] = (uint16_t)l;
-            }
+            uint64_t next = tile + gridDim.x;
+            if (next < ntiles && (next + 1) * kTile <= n)
+                tma_load_1d(skey_addr, q + next * kTile, kTile * 8, bar);
         }
-        __syncthreads();
         uint32_t const total = cnt[nb]; // valid queries only: the out-of-domain slots are never read
-        for (uint32_t k = tid; k < total; k += kTileThreads)
-            recs[base + k] = srec[k];
+        uint32_t * const recs_t = recs + base + tid;
+        if (total == kTile)
+        {
+#pragma unroll
+            for (int u = 0; u < kPer; ++u)
+                recs_t[u * kTileThreads] = srec[u * kTileThreads + tid];
+        }
+        else
+        {
+            for (uint32_t k = tid; k < total; k += kTileThreads)
+                recs_t[k - tid] = srec[k];
+        }
     }
 }
 
@@ -302,7 +342,14 @@ unsigned bin_apply_grid(BinPlan const & p)
 template <int B>
 struct BvRankOp
 {
-    static constexpr int kIlp = 2;
+    // measured (profiles/r01d_binned_variants.txt): 1 gather per lane x 8 CTAs/SM beats 2 x 6, 3 x 5 and 4 x 4 —
+    // the L2 gather rate, not latency, is the limit, and more resident warps keep it fed
+#ifndef BIN_RANK_ILP
+#define BIN_RANK_ILP 1
+#define BIN_RANK_CTAS 8
+#endif
+    static constexpr int kIlp = BIN_RANK_ILP;
+    static constexpr int kMinCtas = BIN_RANK_CTAS;
     static constexpr uint32_t kSmem = 0;
     BvView v;
     __device__ __forceinline__ void stage(uint8_t *) const
@@ -321,7 +368,12 @@ struct BvRankOp
 template <int B>
 struct BvSelectOp
 {
-    static constexpr int kIlp = 1;
+#ifndef BIN_SEL_ILP
+#define BIN_SEL_ILP 1
+#define BIN_SEL_CTAS 8
+#endif
+    static constexpr int kIlp = BIN_SEL_ILP;
+    static constexpr int kMinCtas = BIN_SEL_CTAS;
     static constexpr uint32_t kSmem = 0;
     BvView v;
     __device__ __forceinline__ void stage(uint8_t *) const

@@ -63,12 +63,13 @@ int bin_launch_unsort(BinPlan const & p, BinScratch const & w, uint64_t n, uint6
 unsigned bin_apply_grid(BinPlan const & p);
 
 // Op: plain-old-data functor with
-//   static constexpr int kIlp          independent gathers per lane and trip (1 or 2)
+//   static constexpr int kIlp          independent gathers per lane and trip
+//   static constexpr int kMinCtas      resident CTAs per SM the kernel is compiled for (register budget)
 //   static constexpr uint32_t kSmem    bytes of dynamic shared memory its tables need (0: none)
 //   __device__ void stage(uint8_t *)   copy tables into shared memory (called by every thread; must __syncthreads if kSmem)
 //   __device__ uint64_t operator()(uint64_t key) const
 template <class Op>
-__global__ void __launch_bounds__(kThreads) bin_apply_kernel(Op op,
+__global__ void __launch_bounds__(kThreads, Op::kMinCtas) bin_apply_kernel(Op op,
                                                              uint32_t const * __restrict__ recs,
                                                              uint16_t const * __restrict__ loff,
                                                              uint32_t shift,
@@ -102,25 +103,20 @@ __global__ void __launch_bounds__(kThreads) bin_apply_kernel(Op op,
             uint64_t const hi = (uint64_t)b << shift;
             uint32_t const * r_in = recs + t * kTile;
             uint64_t * r_out = res + t * kTile;
-            if (Op::kIlp == 2)
-            {
-                for (uint32_t k = o0 + lane; k < o1; k += 64)
-                {
-                    uint32_t k2 = k + 32;
-                    bool two = k2 < o1;
-                    uint64_t p1 = hi + ld_stream_u32(r_in + k);
-                    uint64_t p2 = two ? hi + ld_stream_u32(r_in + k2) : p1;
-                    uint64_t a1 = op(p1);
-                    uint64_t a2 = op(p2);
-                    st_stream_u64(r_out + k, a1);
-                    if (two)
-                        st_stream_u64(r_out + k2, a2);
-                }
-            }
-            else
-            {
-                for (uint32_t k = o0 + lane; k < o1; k += 32)
-                    st_stream_u64(r_out + k, op(hi + ld_stream_u32(r_in + k)));
+            constexpr int I = Op::kIlp;
+            for (uint32_t k = o0 + lane; k < o1; k += 32 * I)
+            { // I independent gathers per lane and trip
+                uint64_t key[I], a[I];
+#pragma unroll
+                for (int u = 0; u < I; ++u)
+                    key[u] = hi + ld_stream_u32(r_in + ((k + 32 * u < o1) ? k + 32 * u : k));
+#pragma unroll
+                for (int u = 0; u < I; ++u)
+                    a[u] = op(key[u]);
+#pragma unroll
+                for (int u = 0; u < I; ++u)
+                    if (k + 32 * u < o1)
+                        st_stream_u64(r_out + k + 32 * u, a[u]);
             }
         }
     }

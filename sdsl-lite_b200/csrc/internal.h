@@ -249,6 +249,7 @@ struct sdslgpu_handle
     int kind = 0;
     int device = 0;
     uint32_t flags = 0;
+    int order = SDSLGPU_ORDER_AUTO; // sdslgpu_set_batch_order (bit vectors keep their own copy in BvImage::order)
     sdslgpu::DevicePool pool;
     sdslgpu::Staging staging;
     sdslgpu::BvImage bv;        // KIND_BV
@@ -338,7 +339,7 @@ int rrr_serialize(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
 int rrr_upload_tables(DevicePool & pool, RrrImage & r, cudaStream_t s);
 int rrr_build_hints(DevicePool & pool, RrrImage & r, cudaStream_t s);
 int rrr_build_image(DevicePool & pool, RrrImage & r, uint64_t const * words_host_or_dev, bool on_device, uint64_t nbits, cudaStream_t s);
-int rrr_rank_image(RrrImage const & r, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
+int rrr_rank_image(RrrImage const & r, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, int order = SDSLGPU_ORDER_DIRECT);
 int rrr_records_from_sdsl(DevicePool & pool, RrrImage & r, uint64_t const * bt_words, uint64_t nblocks, std::vector<uint64_t> const & rank,
                           std::vector<uint64_t> const & btnrp, std::vector<uint8_t> const & invert, uint64_t total_bits_hint, cudaStream_t s);
 // sdsl_format.cu

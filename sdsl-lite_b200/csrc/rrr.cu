@@ -18,6 +18,7 @@
 //     w6      ones in the superblock, w7 offset bits of the superblock
 // so rank = record + one read of the offset stream (m_btnr, unchanged), and the class scan is at most 7 steps.
 // C(n,k) for n,k <= 63 (32 KB) and the code lengths live in shared memory.
+#include "binned.cuh"
 #include "internal.h"
 #include "rrr_device.cuh"
 #include "scan.cuh"
@@ -423,10 +424,41 @@ int rrr_records_from_sdsl(DevicePool & pool, RrrImage & r,
     return SDSLGPU_OK;
 }
 
-int rrr_rank_image(RrrImage const & r, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)
+// op of the locality-ordered batch pipeline (binned.cuh): rank(i) reads the 64-byte record of superblock i / 2016
+// and the offset bits right behind btnrp — both grow with i
+struct RrrRankOp
+{
+    static constexpr int kIlp = 1;
+    static constexpr int kMinCtas = 6;
+    static constexpr uint32_t kSmem = sizeof(RrrTables);
+    RrrView v;
+    int b;
+    RrrTables const * t;
+    __device__ __forceinline__ void stage(uint8_t * smem)
+    {
+        RrrTables * st = reinterpret_cast<RrrTables *>(smem);
+        stage_rrr(v.tables, st);
+        t = st;
+    }
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const
+    {
+        uint64_t r = rrr_rank1_one(v, t, i);
+        return b ? r : i - r;
+    }
+};
+
+int rrr_rank_image(RrrImage const & r, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, int order)
 {
     if (n == 0)
         return SDSLGPU_OK;
+    uint64_t index_bytes = (r.nsuper + 1) * 64 + ((r.btnr_bits + 63) >> 6) * 8;
+    if (bin_wanted(order, index_bytes, n))
+    {
+        bool done = false;
+        SG_TRY(bin_run(RrrRankOp{rrr_view(r), b, nullptr}, index_bytes, 0, r.size, idx, n, out, s, &done));
+        if (done)
+            return SDSLGPU_OK;
+    }
     rrr_rank_kernel<<<grid_for(n), kThreads, sizeof(RrrTables), s>>>(rrr_view(r), b, idx, n, out);
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
@@ -434,7 +466,7 @@ int rrr_rank_image(RrrImage const & r, int b, uint64_t const * idx, uint64_t n, 
 
 int rrr_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)
 {
-    return rrr_rank_image(h->rrr, b, idx, n, out, s);
+    return rrr_rank_image(h->rrr, b, idx, n, out, s, h->order);
 }
 
 int rrr_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)

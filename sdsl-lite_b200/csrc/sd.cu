@@ -9,6 +9,7 @@
 // `high` (m ones, 2^logm zeros: always about half dense) gets the same one-sector rank blocks and select
 // samples as a plain bit vector; select_support_mcl<1>/<0> of the reference (sd_vector.hpp:162-163) are
 // therefore served by bv_select<1>/<0>.
+#include "binned.cuh"
 #include "internal.h"
 #include "scan.cuh"
 
@@ -266,10 +267,53 @@ int sd_build(sdslgpu_handle * h, uint64_t const * words_in, bool on_device, uint
     return SDSLGPU_OK;
 }
 
+// ops of the locality-ordered batch pipeline (binned.cuh): rank(i) looks at bucket i >> wl of `high` and the low
+// parts next to it, select_1(i) at low[i-1] and the i-th one of `high` — both positions grow with the key
+struct SdRankOp
+{
+    static constexpr int kIlp = 1;
+    static constexpr int kMinCtas = 6;
+    static constexpr uint32_t kSmem = 0;
+    SdView v;
+    int b;
+    __device__ __forceinline__ void stage(uint8_t *) const
+    {}
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const
+    {
+        uint64_t r = sd_rank1_one(v, i);
+        return b ? r : i - r;
+    }
+};
+struct SdSelect1Op
+{
+    static constexpr int kIlp = 1;
+    static constexpr int kMinCtas = 6;
+    static constexpr uint32_t kSmem = 0;
+    SdView v;
+    __device__ __forceinline__ void stage(uint8_t *) const
+    {}
+    __device__ __forceinline__ uint64_t operator()(uint64_t key) const
+    {
+        return sd_select1_one(v, key + 1);
+    }
+};
+
+static uint64_t sd_index_bytes(SdImage const & d)
+{
+    return d.high.nblocks * sizeof(bvblock) + d.low_words * 8;
+}
+
 int sd_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)
 {
     if (n == 0)
         return SDSLGPU_OK;
+    if (bin_wanted(h->order, sd_index_bytes(h->sd), n))
+    {
+        bool done = false;
+        SG_TRY(bin_run(SdRankOp{sd_view(h->sd), b}, sd_index_bytes(h->sd), 0, h->sd.size, idx, n, out, s, &done));
+        if (done)
+            return SDSLGPU_OK;
+    }
     sd_rank_kernel<<<grid_for(n), kThreads, 0, s>>>(sd_view(h->sd), b, idx, n, out);
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
@@ -279,6 +323,13 @@ int sd_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint
 {
     if (n == 0)
         return SDSLGPU_OK;
+    if (b && h->sd.m && bin_wanted(h->order, sd_index_bytes(h->sd), n)) // select_0 is a binary search over select_1: no locality
+    {
+        bool done = false;
+        SG_TRY(bin_run(SdSelect1Op{sd_view(h->sd)}, sd_index_bytes(h->sd), 1, h->sd.m - 1, idx, n, out, s, &done));
+        if (done)
+            return SDSLGPU_OK;
+    }
     if (b)
         sd_select_kernel<1><<<grid_for(n), kThreads, 0, s>>>(sd_view(h->sd), idx, n, out);
     else

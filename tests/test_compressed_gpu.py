@@ -78,3 +78,40 @@ def test_compressed_density_sweep_properties(pkg, oracle, kind):
             assert (v.select(k0, 0) == plain.select(k0, 0)).all()
             o = getattr(oracle, kind)(w, nbits)
             assert (v.rank(idx[:5000], 1) == o.rank(idx[:5000], 1)).all()
+
+
+@pytest.mark.parametrize("kind", ["rrr", "sd"])
+@pytest.mark.parametrize("chunk_bytes", ["256", "65536"])
+def test_compressed_binned_order(pkg, oracle, monkeypatch, kind, chunk_bytes):
+    """ORDER_BINNED (binned.cuh pipeline with the sd / rrr ops) forced onto the catalogue with tiny bins: rank (both
+    patterns) and select_1 agree with the oracle, out-of-domain queries included; the operations without a binned
+    form (sd select_0, rrr select) still answer through the direct kernels"""
+    monkeypatch.setenv("SDSLGPU_BIN_CHUNK_BYTES", chunk_bytes)
+    for cid, w, nbits in _vectors():
+        if kind == "sd" and nbits == 0:
+            continue
+        o = getattr(oracle, kind)(w, nbits)
+        with getattr(pkg, KINDS[kind])(w, nbits) as v:
+            v.set_batch_order(pkg.ORDER_BINNED)
+            for nq in (5, 8192, 20011):
+                idx = cases.rank_queries(nbits, 3 + nq, nq)
+                bad = np.arange(len(idx)) % 53 == 7
+                idx_bad = idx.copy()
+                idx_bad[bad] = np.uint64(nbits + 1 + nq)
+                for b in (1, 0):
+                    want = o.rank(idx, b)
+                    assert (v.rank(idx, b) == want).all(), (kind, cid, "rank", b, nq)
+                    want[bad] = pkg.NPOS
+                    assert (v.rank(idx_bad, b) == want).all(), (kind, cid, "rank+ood", b, nq)
+                m = v.arg_count(1)
+                q = cases.select_queries(m, 4 + nq, nq)
+                if len(q):
+                    assert (v.select(q, 1) == o.select(q, 1)).all(), (kind, cid, "select1", nq)
+                    if kind == "sd":
+                        qb = q.copy()
+                        qb[::5] = 0
+                        got = v.select(qb, 1)
+                        assert (got[::5] == pkg.NPOS).all() and (got[1::5] == o.select(q[1::5], 1)).all()
+            q0 = cases.select_queries(v.arg_count(0), 6, 500)
+            if len(q0):
+                assert (v.select(q0, 0) == o.select(q0, 0)).all(), (kind, cid, "select0")
