@@ -46,25 +46,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 }
 
 // key j of the tile: from the TMA buffer (complete tiles) or straight from global memory
+// (clamp: keys beyond maxkey — but not a wrapped-around 0 - sub — count as maxkey: for ops whose answer is the same
+//  for every query past the end, like select_support_rrr's in-band size())
 template <bool kFull>
-__device__ __forceinline__ bool tile_key(uint64_t const * __restrict__ src, uint32_t limit, uint32_t j, uint64_t sub, uint64_t & key)
+__device__ __forceinline__ bool tile_key(uint64_t const * __restrict__ src, uint32_t limit, uint32_t j, uint64_t sub, uint64_t maxkey, uint32_t clamp, uint64_t & key)
 {
     if (!kFull && j >= limit)
         return false;
     key = (kFull ? src[j] : ld_stream_u64(src + j)) - sub;
+    if (clamp && key > maxkey && key != ~0ull)
+        key = maxkey;
     return true;
 }
 
 // pass A: histogram of the tile over the bins (bin nb = out of domain)
 template <bool kFull>
-__device__ __forceinline__ void tile_count(uint64_t const * __restrict__ src, uint32_t limit, uint64_t sub, uint64_t maxkey, uint32_t shift, uint32_t nb,
-                                           uint32_t * __restrict__ cnt, uint32_t tid)
+__device__ __forceinline__ void tile_count(uint64_t const * __restrict__ src, uint32_t limit, uint64_t sub, uint64_t maxkey, uint32_t clamp, uint32_t shift,
+                                           uint32_t nb, uint32_t * __restrict__ cnt, uint32_t tid)
 {
 #pragma unroll
     for (int u = 0; u < kPer; ++u)
     {
         uint64_t key;
-        if (tile_key<kFull>(src, limit, (uint32_t)u * kTileThreads + tid, sub, key))
+        if (tile_key<kFull>(src, limit, (uint32_t)u * kTileThreads + tid, sub, maxkey, clamp, key))
             atomicAdd(&cnt[(key <= maxkey) ? (uint32_t)(key >> shift) : nb], 1u);
     }
 }
@@ -73,14 +77,14 @@ __device__ __forceinline__ void tile_count(uint64_t const * __restrict__ src, ui
 // to shared memory in slot order, slots to `lp`.  Keeping nothing in registers between the passes (the keys are
 // re-read from shared memory) is what lets two 1024-thread CTAs share an SM without spills.
 template <bool kFull>
-__device__ __forceinline__ void tile_scatter(uint64_t const * __restrict__ src, uint32_t limit, uint64_t sub, uint64_t maxkey, uint32_t shift, uint32_t mask32,
-                                             uint32_t nb, uint32_t * __restrict__ cur, uint32_t * __restrict__ srec, uint16_t * __restrict__ lp_t, uint32_t tid)
+__device__ __forceinline__ void tile_scatter(uint64_t const * __restrict__ src, uint32_t limit, uint64_t sub, uint64_t maxkey, uint32_t clamp, uint32_t shift,
+                                             uint32_t mask32, uint32_t nb, uint32_t * __restrict__ cur, uint32_t * __restrict__ srec, uint16_t * __restrict__ lp_t, uint32_t tid)
 {
 #pragma unroll
     for (int u = 0; u < kPer; ++u)
     {
         uint64_t key;
-        if (tile_key<kFull>(src, limit, (uint32_t)u * kTileThreads + tid, sub, key))
+        if (tile_key<kFull>(src, limit, (uint32_t)u * kTileThreads + tid, sub, maxkey, clamp, key))
         {
             uint32_t l = atomicAdd(&cur[(key <= maxkey) ? (uint32_t)(key >> shift) : nb], 1u);
             srec[l] = (uint32_t)key & mask32;
@@ -94,6 +98,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) bin_tile_sort_kernel(uint64_t
                                                                         uint64_t n,
                                                                         uint64_t sub,
                                                                         uint64_t maxkey,
+                                                                        uint32_t clamp,
                                                                         uint32_t shift,
                                                                         uint32_t nb,
                                                                         uint64_t ntiles,
@@ -136,10 +141,10 @@ __global__ void __launch_bounds__(kTileThreads, 2) bin_tile_sort_kernel(uint64_t
         {
             mbar_wait(bar, parity);
             parity ^= 1u;
-            tile_count<true>(skey, limit, sub, maxkey, shift, nb, cnt, tid);
+            tile_count<true>(skey, limit, sub, maxkey, clamp, shift, nb, cnt, tid);
         }
         else
-            tile_count<false>(q + base, limit, sub, maxkey, shift, nb, cnt, tid);
+            tile_count<false>(q + base, limit, sub, maxkey, clamp, shift, nb, cnt, tid);
         __syncthreads();
         if (tid < 32)
         { // exclusive scan of the nb+1 counters; entry nb+1 receives the total
@@ -167,9 +172,9 @@ __global__ void __launch_bounds__(kTileThreads, 2) bin_tile_sort_kernel(uint64_t
         for (uint32_t k = tid; k < nb + 2; k += kTileThreads)
             loff[tile * (nb + 2) + k] = (uint16_t)cnt[k];
         if (full)
-            tile_scatter<true>(skey, limit, sub, maxkey, shift, mask32, nb, cur, srec, lp + base + tid, tid);
+            tile_scatter<true>(skey, limit, sub, maxkey, clamp, shift, mask32, nb, cur, srec, lp + base + tid, tid);
         else
-            tile_scatter<false>(q + base, limit, sub, maxkey, shift, mask32, nb, cur, srec, lp + base + tid, tid);
+            tile_scatter<false>(q + base, limit, sub, maxkey, clamp, shift, mask32, nb, cur, srec, lp + base + tid, tid);
         __syncthreads(); // srec complete; every key has been read out of skey for the last time
         if (kTma && tid == 0)
         {
@@ -304,7 +309,7 @@ int bin_scratch_alloc(BinScratch & w, BinPlan const & p, cudaStream_t s)
     return SDSLGPU_OK;
 }
 
-int bin_launch_tile_sort(BinPlan const & p, BinScratch const & w, uint64_t const * q, uint64_t n, uint64_t sub, uint64_t maxkey, cudaStream_t s)
+int bin_launch_tile_sort(BinPlan const & p, BinScratch const & w, uint64_t const * q, uint64_t n, uint64_t sub, uint64_t maxkey, bool clamp, cudaStream_t s)
 {
     // persistent CTAs, two per SM (96 KB of shared memory each with the TMA key buffer)
     unsigned grid = (unsigned)(p.ntiles < 2ull * kSmCount ? p.ntiles : 2ull * kSmCount);
@@ -312,10 +317,10 @@ int bin_launch_tile_sort(BinPlan const & p, BinScratch const & w, uint64_t const
     {
         int smem = kTile * 4 + kTile * 8;
         SG_CUDA(cudaFuncSetAttribute(bin_tile_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        bin_tile_sort_kernel<true><<<grid, kTileThreads, smem, s>>>(q, n, sub, maxkey, p.shift, p.nb, p.ntiles, w.recs, w.lp, w.loff);
+        bin_tile_sort_kernel<true><<<grid, kTileThreads, smem, s>>>(q, n, sub, maxkey, clamp ? 1u : 0u, p.shift, p.nb, p.ntiles, w.recs, w.lp, w.loff);
     }
     else
-        bin_tile_sort_kernel<false><<<grid, kTileThreads, kTile * 4, s>>>(q, n, sub, maxkey, p.shift, p.nb, p.ntiles, w.recs, w.lp, w.loff);
+        bin_tile_sort_kernel<false><<<grid, kTileThreads, kTile * 4, s>>>(q, n, sub, maxkey, clamp ? 1u : 0u, p.shift, p.nb, p.ntiles, w.recs, w.lp, w.loff);
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
 }

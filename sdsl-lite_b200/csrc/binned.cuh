@@ -58,7 +58,7 @@ struct BinScratch
 bool bin_make_plan(uint64_t index_bytes, uint64_t maxkey, uint64_t n, BinPlan & p);
 bool bin_wanted(int order, uint64_t index_bytes, uint64_t n);
 int bin_scratch_alloc(BinScratch & w, BinPlan const & p, cudaStream_t s);
-int bin_launch_tile_sort(BinPlan const & p, BinScratch const & w, uint64_t const * q, uint64_t n, uint64_t sub, uint64_t maxkey, cudaStream_t s);
+int bin_launch_tile_sort(BinPlan const & p, BinScratch const & w, uint64_t const * q, uint64_t n, uint64_t sub, uint64_t maxkey, bool clamp, cudaStream_t s);
 int bin_launch_unsort(BinPlan const & p, BinScratch const & w, uint64_t n, uint64_t * out, cudaStream_t s);
 unsigned bin_apply_grid(BinPlan const & p);
 
@@ -122,10 +122,12 @@ __global__ void __launch_bounds__(kThreads, Op::kMinCtas) bin_apply_kernel(Op op
     }
 }
 
-// the whole pipeline.  key = q - sub, in domain iff key <= maxkey; out-of-domain queries get SDSLGPU_NPOS.
+// the whole pipeline.  key = q - sub, in domain iff key <= maxkey; out-of-domain queries get SDSLGPU_NPOS
+// (clamp_high: keys past maxkey are answered as maxkey, only a wrapped-around 0 - sub is out of domain).
 // *done = false (and nothing launched) when the plan does not fit (shift > 32, tile count overflow).
 template <class Op>
-int bin_run(Op const & op, uint64_t index_bytes, uint64_t sub, uint64_t maxkey, uint64_t const * q, uint64_t n, uint64_t * out, cudaStream_t s, bool * done)
+int bin_run(Op const & op, uint64_t index_bytes, uint64_t sub, uint64_t maxkey, uint64_t const * q, uint64_t n, uint64_t * out, cudaStream_t s, bool * done,
+            bool clamp_high = false)
 {
     *done = false;
     BinPlan p;
@@ -133,7 +135,7 @@ int bin_run(Op const & op, uint64_t index_bytes, uint64_t sub, uint64_t maxkey, 
         return SDSLGPU_OK;
     BinScratch w;
     SG_TRY(bin_scratch_alloc(w, p, s));
-    SG_TRY(bin_launch_tile_sort(p, w, q, n, sub, maxkey, s));
+    SG_TRY(bin_launch_tile_sort(p, w, q, n, sub, maxkey, clamp_high, s));
     if (Op::kSmem > 48 * 1024)
         SG_CUDA(cudaFuncSetAttribute(bin_apply_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Op::kSmem));
     bin_apply_kernel<Op><<<bin_apply_grid(p), kThreads, Op::kSmem, s>>>(op, w.recs, w.loff, p.shift, p.nb, p.ntiles, w.ticket, w.res);

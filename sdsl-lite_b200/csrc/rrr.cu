@@ -447,11 +447,39 @@ struct RrrRankOp
     }
 };
 
+// select(i): hint -> bisection over the superblock records -> class scan -> decode, all next to the i-th b-bit.
+// key = i - 1; key == #b-bits stands for every i past the end (the reference's in-band size(), rrr_vector.hpp:641-642)
+template <int B>
+struct RrrSelectOp
+{
+    static constexpr int kIlp = 1;
+    static constexpr int kMinCtas = 6;
+    static constexpr uint32_t kSmem = sizeof(RrrTables);
+    RrrView v;
+    uint64_t args;
+    RrrTables const * t;
+    __device__ __forceinline__ void stage(uint8_t * smem)
+    {
+        RrrTables * st = reinterpret_cast<RrrTables *>(smem);
+        stage_rrr(v.tables, st);
+        t = st;
+    }
+    __device__ __forceinline__ uint64_t operator()(uint64_t key) const
+    {
+        return key >= args ? v.size : rrr_select_one<B>(v, t, key + 1);
+    }
+};
+
+static uint64_t rrr_index_bytes(RrrImage const & r)
+{
+    return (r.nsuper + 1) * 64 + ((r.btnr_bits + 63) >> 6) * 8;
+}
+
 int rrr_rank_image(RrrImage const & r, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, int order)
 {
     if (n == 0)
         return SDSLGPU_OK;
-    uint64_t index_bytes = (r.nsuper + 1) * 64 + ((r.btnr_bits + 63) >> 6) * 8;
+    uint64_t index_bytes = rrr_index_bytes(r);
     if (bin_wanted(order, index_bytes, n))
     {
         bool done = false;
@@ -473,6 +501,18 @@ int rrr_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uin
 {
     if (n == 0)
         return SDSLGPU_OK;
+    if (bin_wanted(h->order, rrr_index_bytes(h->rrr), n))
+    {
+        RrrImage const & r = h->rrr;
+        uint64_t args = b ? r.ones : r.size - r.ones;
+        bool done = false;
+        if (b)
+            SG_TRY(bin_run(RrrSelectOp<1>{rrr_view(r), args, nullptr}, rrr_index_bytes(r), 1, args, idx, n, out, s, &done, true));
+        else
+            SG_TRY(bin_run(RrrSelectOp<0>{rrr_view(r), args, nullptr}, rrr_index_bytes(r), 1, args, idx, n, out, s, &done, true));
+        if (done)
+            return SDSLGPU_OK;
+    }
     if (b)
         rrr_select_kernel<1><<<grid_for(n), kThreads, sizeof(RrrTables), s>>>(rrr_view(h->rrr), idx, n, out);
     else

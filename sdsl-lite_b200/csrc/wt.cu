@@ -487,20 +487,163 @@ __global__ void __launch_bounds__(kThreads) wt_rank_level_kernel(Bits bits,
     }
 }
 
+// level-synchronous operator[] / inverse_select (wt_pc.hpp:336-357, 411-430): every query descends one depth per
+// launch; state (position inside the node: 48 bits, node: 16 bits) lives in `state` (= rank_out, or sym_out when the
+// caller wants symbols only).  Queries that reach their leaf early (short Huffman codes) just wait.
+template <class Bits>
+__global__ void __launch_bounds__(kThreads) wt_access_level_kernel(Bits bits,
+                                                                   WtTree const * __restrict__ tree,
+                                                                   uint64_t size,
+                                                                   uint32_t level,
+                                                                   uint32_t last_level,
+                                                                   uint64_t const * __restrict__ qi,
+                                                                   uint64_t n,
+                                                                   uint64_t * __restrict__ state,
+                                                                   uint64_t * __restrict__ sym_out,
+                                                                   uint64_t * __restrict__ rank_out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WtTree * t = reinterpret_cast<WtTree *>(smem_raw);
+    stage_tree(tree, t);
+    bits.attach(smem_raw + sizeof(WtTree));
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
+    {
+        uint64_t i;
+        uint32_t v = 0;
+        if (level == 0)
+        {
+            i = qi[q];
+            if (i >= size)
+            {
+                sym_out[q] = SDSLGPU_NPOS;
+                if (rank_out)
+                    rank_out[q] = SDSLGPU_NPOS;
+                continue;
+            }
+        }
+        else
+        {
+            uint64_t st = state[q];
+            if (st == SDSLGPU_NPOS)
+                continue;
+            i = st & kStateMask;
+            v = (uint32_t)(st >> 48);
+        }
+        if (t->child[v][0] != kUndef)
+        {
+            uint32_t bit;
+            uint64_t o = bits.rank1_and_bit(t->bv_pos[v] + i, bit) - t->bv_pos_rank[v];
+            i = bit ? o : i - o;
+            v = t->child[v][bit];
+        }
+        if (level == last_level)
+        { // every path has ended by now
+            sym_out[q] = t->bv_pos_rank[v];
+            if (rank_out)
+                rank_out[q] = i;
+        }
+        else
+            state[q] = i | ((uint64_t)v << 48);
+    }
+}
+
+// level-synchronous select(i, c) (wt_pc.hpp:443-474): the climb from the leaf, one ABSOLUTE tree depth per launch
+// (deepest first), so that all selects of a launch fall into the bit range of one depth.  A symbol whose code has
+// `len` bits takes its first step in the launch for depth len-1.
+template <class Bits>
+__global__ void __launch_bounds__(kThreads) wt_select_level_kernel(Bits bits,
+                                                                   WtTree const * __restrict__ tree,
+                                                                   uint64_t size,
+                                                                   uint32_t level,
+                                                                   uint32_t top_level,
+                                                                   uint64_t const * __restrict__ qi,
+                                                                   uint8_t const * __restrict__ qc,
+                                                                   uint64_t n,
+                                                                   uint64_t * __restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WtTree * t = reinterpret_cast<WtTree *>(smem_raw);
+    stage_tree(tree, t);
+    bits.attach(smem_raw + sizeof(WtTree));
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
+    {
+        uint32_t c = qc[q];
+        uint64_t p = t->path[c];
+        uint32_t len = (uint32_t)(p >> 56);
+        uint32_t leaf = t->c_to_leaf[c];
+        if (level == top_level)
+        { // first launch: settle the answers that need no climbing and the out-of-domain ones
+            uint64_t i = qi[q];
+            if (leaf == kUndef)
+            {
+                out[q] = size; // the reference returns size() for an absent symbol (wt_pc.hpp:447-450)
+                continue;
+            }
+            if (i == 0 || i > t->occ[c])
+            {
+                out[q] = SDSLGPU_NPOS;
+                continue;
+            }
+            if (len <= level)
+            { // starts in a later launch (shorter code): park the state
+                out[q] = (i - 1) | ((uint64_t)leaf << 48);
+                continue;
+            }
+        }
+        uint64_t r;
+        uint32_t v;
+        if (level == top_level)
+        { // the deepest codes take their first step in the first launch
+            r = qi[q] - 1;
+            v = leaf;
+        }
+        else
+        {
+            if (leaf == kUndef || len <= level)
+                continue; // settled (absent symbol), or not started yet
+            uint64_t st = out[q];
+            if (st == SDSLGPU_NPOS)
+                continue; // out of domain, settled in the first launch
+            r = st & kStateMask;
+            v = (uint32_t)(st >> 48);
+        }
+        uint32_t bit = (uint32_t)(p >> level) & 1u; // path bit taken at depth `level` (LSB first from the root)
+        v = t->parent[v];
+        if (bit == 0)
+            r = bits.template select<0>(t->bv_pos[v] - t->bv_pos_rank[v] + r + 1) - t->bv_pos[v];
+        else
+            r = bits.template select<1>(t->bv_pos_rank[v] + r + 1) - t->bv_pos[v];
+        out[q] = (level == 0) ? r : (r | ((uint64_t)v << 48));
+    }
+}
+
+static uint32_t wt_depth(WtHuffImage const & w)
+{
+    uint32_t depth = 0;
+    for (int k = 0; k < 256; ++k)
+        if (w.host_tree.c_to_leaf[k] != kUndef)
+            depth = std::max(depth, (uint32_t)(w.host_tree.path[k] >> 56));
+    return depth;
+}
+
+// one launch per tree depth pays when the batch is large and a depth's share of m_bv can stay in the L2
+static bool wt_level_sync(WtHuffImage const & w, uint64_t n, uint32_t depth)
+{
+    bool level_sync = n >= (1u << 16) && depth >= 2 && depth <= 24 && w.sigma > 1 && (w.use_rrr ? w.rrr.size : w.bv.nbits) < (1ull << 47);
+    if (char const * e = std::getenv("SDSLGPU_WT_LEVEL_SYNC")) // tuning knob for experiments
+        level_sync = std::atoi(e) != 0 && depth >= 1 && w.sigma > 1;
+    return level_sync;
+}
+
 int wt_rank_device(sdslgpu_handle const * h, uint64_t const * i, uint8_t const * c, uint64_t n, uint64_t * out, cudaStream_t s)
 {
     WtHuffImage const & w = h->wt;
     if (n == 0)
         return SDSLGPU_OK;
-    // depth of the tree = number of passes of the level-synchronous form
-    uint32_t depth = 0;
-    for (int k = 0; k < 256; ++k)
-        if (w.host_tree.c_to_leaf[k] != kUndef)
-            depth = std::max(depth, (uint32_t)(w.host_tree.path[k] >> 56));
-    bool level_sync = n >= (1u << 16) && depth >= 2 && depth <= 24 && w.sigma > 1 && (w.use_rrr ? w.rrr.size : w.bv.nbits) < (1ull << 47);
-    if (char const * e = std::getenv("SDSLGPU_WT_LEVEL_SYNC")) // tuning knob for experiments
-        level_sync = std::atoi(e) != 0 && depth >= 1 && w.sigma > 1;
-    if (!level_sync)
+    uint32_t depth = wt_depth(w); // = number of passes of the level-synchronous form
+    if (!wt_level_sync(w, n, depth))
     {
         SG_LAUNCH_BITS(wt_rank_kernel, w, grid_for(n), kTreeSmem, s, w.tree, w.size, w.sigma, i, c, n, out);
         SG_CUDA(cudaGetLastError());
@@ -519,6 +662,16 @@ int wt_select_device(sdslgpu_handle const * h, uint64_t const * i, uint8_t const
     WtHuffImage const & w = h->wt;
     if (n == 0)
         return SDSLGPU_OK;
+    uint32_t depth = wt_depth(w);
+    if (wt_level_sync(w, n, depth))
+    {
+        for (uint32_t l = depth; l-- > 0;)
+        {
+            SG_LAUNCH_BITS(wt_select_level_kernel, w, grid_for(n), kTreeSmem, s, w.tree, w.size, l, depth - 1, i, c, n, out);
+            SG_CUDA(cudaGetLastError());
+        }
+        return SDSLGPU_OK;
+    }
     SG_LAUNCH_BITS(wt_select_kernel, w, grid_for(n), kTreeSmem, s, w.tree, w.size, w.sigma, i, c, n, out);
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
@@ -529,6 +682,17 @@ int wt_access_device(sdslgpu_handle const * h, uint64_t const * i, uint64_t n, u
     WtHuffImage const & w = h->wt;
     if (n == 0)
         return SDSLGPU_OK;
+    uint32_t depth = wt_depth(w);
+    if (wt_level_sync(w, n, depth))
+    {
+        uint64_t * state = rnk ? rnk : sym;
+        for (uint32_t l = 0; l < depth; ++l)
+        {
+            SG_LAUNCH_BITS(wt_access_level_kernel, w, grid_for(n), kTreeSmem, s, w.tree, w.size, l, depth - 1, i, n, state, sym, rnk);
+            SG_CUDA(cudaGetLastError());
+        }
+        return SDSLGPU_OK;
+    }
     SG_LAUNCH_BITS(wt_access_kernel, w, grid_for(n), kTreeSmem, s, w.tree, w.size, i, n, sym, rnk);
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;

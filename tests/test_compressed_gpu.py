@@ -84,8 +84,8 @@ def test_compressed_density_sweep_properties(pkg, oracle, kind):
 @pytest.mark.parametrize("chunk_bytes", ["256", "65536"])
 def test_compressed_binned_order(pkg, oracle, monkeypatch, kind, chunk_bytes):
     """ORDER_BINNED (binned.cuh pipeline with the sd / rrr ops) forced onto the catalogue with tiny bins: rank (both
-    patterns) and select_1 agree with the oracle, out-of-domain queries included; the operations without a binned
-    form (sd select_0, rrr select) still answer through the direct kernels"""
+    patterns), select_1 and rrr select_0 agree with the oracle, out-of-domain queries included (rrr: the reference's
+    in-band size() past the last b-bit); sd select_0 has no binned form and still answers through the direct kernel"""
     monkeypatch.setenv("SDSLGPU_BIN_CHUNK_BYTES", chunk_bytes)
     for cid, w, nbits in _vectors():
         if kind == "sd" and nbits == 0:
@@ -107,11 +107,14 @@ def test_compressed_binned_order(pkg, oracle, monkeypatch, kind, chunk_bytes):
                 q = cases.select_queries(m, 4 + nq, nq)
                 if len(q):
                     assert (v.select(q, 1) == o.select(q, 1)).all(), (kind, cid, "select1", nq)
-                    if kind == "sd":
-                        qb = q.copy()
-                        qb[::5] = 0
-                        got = v.select(qb, 1)
-                        assert (got[::5] == pkg.NPOS).all() and (got[1::5] == o.select(q[1::5], 1)).all()
-            q0 = cases.select_queries(v.arg_count(0), 6, 500)
+                    qb = q.copy()
+                    qb[::5] = 0
+                    qb[2::5] = np.uint64(m + 1 + nq)
+                    got = v.select(qb, 1)
+                    assert (got[::5] == pkg.NPOS).all() and (got[1::5] == o.select(q[1::5], 1)).all(), (kind, cid, "select1 mixed", nq)
+                    assert (got[2::5] == (nbits if kind == "rrr" else pkg.NPOS)).all(), (kind, cid, "select1 past the end", nq)
+            q0 = cases.select_queries(v.arg_count(0), 6, 500 if kind == "sd" else 20000)
             if len(q0):
                 assert (v.select(q0, 0) == o.select(q0, 0)).all(), (kind, cid, "select0")
+            if kind == "rrr":
+                assert (v.select(np.array([0, v.arg_count(0) + 1, 2**63], np.uint64), 0) == np.array([pkg.NPOS, nbits, nbits], np.uint64)).all()

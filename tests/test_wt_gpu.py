@@ -15,7 +15,12 @@ def _checkers(oracle, orc, t):
     return out
 
 
-def test_wt_huff_catalogue(pkg, oracle, orc):
+@pytest.mark.parametrize("level_sync", [None, "0", "1"], ids=["auto", "per_query", "level_sync"])
+def test_wt_huff_catalogue(pkg, oracle, orc, monkeypatch, level_sync):
+    """every operation under both execution strategies (one thread per query / one launch per tree depth for rank,
+    operator[], inverse_select and select), forced onto every text of the catalogue, skewed Huffman shapes included"""
+    if level_sync is not None:
+        monkeypatch.setenv("SDSLGPU_WT_LEVEL_SYNC", level_sync)
     rng = np.random.default_rng(77)
     for name, t in texts.text_catalogue(large=True):
         n = len(t)
@@ -27,6 +32,14 @@ def test_wt_huff_catalogue(pkg, oracle, orc):
             got_rank = wt.rank(i, c)
             got_rnk, got_sym = wt.inverse_select(j)
             assert (wt.access(j) == arr[j.astype(np.int64)]).all(), (name, "access vs text")
+            if n:  # out of domain stays NPOS through all passes
+                jb = j.copy()
+                jb[::7] = n + 3
+                ab = wt.access(jb)
+                rb, sb = wt.inverse_select(jb)
+                assert (ab[::7] == pkg.NPOS).all() and (rb[::7] == pkg.NPOS).all() and (sb[::7] == pkg.NPOS).all(), (name, "access ood")
+                keep = np.arange(len(j)) % 7 != 0
+                assert (ab[keep] == arr[j[keep].astype(np.int64)]).all() and (rb[keep] == got_rnk[keep]).all(), (name, "access mixed")
             # rank(size, c) for all 256 symbols == histogram (test/wt_byte_test.cpp:160-167)
             allc = np.arange(256, dtype=np.uint8)
             tot = wt.rank(np.full(256, n, dtype=np.uint64), allc)

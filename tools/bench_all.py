@@ -113,27 +113,35 @@ def run_c2(args):
     for layout, flags in (("b200", 0), ("sdsl", pkg.F_SDSL_LAYOUT)):
         bv = pkg.BitVector(words, nbits, flags=flags)
         d_idx, d_out = dev(idx), torch.empty(nq, dtype=torch.int64, device="cuda")
+        orders = (("binned", pkg.ORDER_BINNED), ("direct", pkg.ORDER_DIRECT)) if layout == "b200" else (("direct", pkg.ORDER_DIRECT),)
         for b in (1, 0):
-            ms, best = time_gpu(lambda: bv.rank(d_idx, b, out=d_out), args.reps)
             par, cpu = None, None
-            if ref:
-                t, want = time_cpu(lambda: ref.rank(idx[:ns], b, threads=CORES))
-                par = bool((host(d_out[:ns]) == want).all())
-                cpu = {"qps": ns / t, "cores": CORES, "sample": ns}
-            record(f"C2 2^{args.nbits_log2}-bit random bit_vector", f"rank_{b} [{layout} layout]", nq, ms, best, 40, par, cpu,
-                   {"index_bytes": bv.device_bytes})
+            for oname, order in orders:
+                bv.set_batch_order(order)
+                ms, best = time_gpu(lambda: bv.rank(d_idx, b, out=d_out), args.reps)
+                if ref:
+                    if cpu is None:
+                        t, want = time_cpu(lambda: ref.rank(idx[:ns], b, threads=CORES))
+                        cpu = {"qps": ns / t, "cores": CORES, "sample": ns}
+                    par = bool((host(d_out[:ns]) == want).all())
+                record(f"C2 2^{args.nbits_log2}-bit random bit_vector", f"rank_{b} [{layout} layout, {oname} order]", nq, ms, best, 40, par, cpu,
+                       {"index_bytes": bv.device_bytes, "batch_order": oname})
         if layout == "b200":
             for b in (1, 0):
                 m = bv.arg_count(b)
                 sel = qr.integers(1, m + 1, nq, dtype=np.uint64)
                 d_sel = dev(sel)
-                ms, best = time_gpu(lambda: bv.select(d_sel, b, out=d_out), args.reps)
                 par, cpu = None, None
-                if ref:
-                    t, want = time_cpu(lambda: ref.select(sel[:ns], b, threads=CORES))
-                    par = bool((host(d_out[:ns]) == want).all())
-                    cpu = {"qps": ns / t, "cores": CORES, "sample": ns}
-                record(f"C2 2^{args.nbits_log2}-bit random bit_vector", f"select_{b}", nq, ms, best, 48, par, cpu)
+                for oname, order in orders:
+                    bv.set_batch_order(order)
+                    ms, best = time_gpu(lambda: bv.select(d_sel, b, out=d_out), args.reps)
+                    if ref:
+                        if cpu is None:
+                            t, want = time_cpu(lambda: ref.select(sel[:ns], b, threads=CORES))
+                            cpu = {"qps": ns / t, "cores": CORES, "sample": ns}
+                        par = bool((host(d_out[:ns]) == want).all())
+                    record(f"C2 2^{args.nbits_log2}-bit random bit_vector", f"select_{b} [{oname} order]", nq, ms, best, 48, par, cpu, {"batch_order": oname})
+            bv.set_batch_order(pkg.ORDER_DIRECT)
             ms, best = time_gpu(lambda: bv.access(d_idx, out=d_out), args.reps)
             record(f"C2 2^{args.nbits_log2}-bit random bit_vector", "access", nq, ms, best, 24, None)
             # the same batch in ascending order: neighbouring queries share sectors, the kernel is unchanged
@@ -175,16 +183,21 @@ def run_c3(args):
                 tb, ref = time_cpu(lambda: (REF.rrr if kind.startswith("rrr") else REF.sd)(words_h, nbits))
             for op, q, dq, want, nbytes in (("rank_1", idx, d_idx, want_rank, rank_bytes), ("select_1", sel, d_sel, want_sel, sel_bytes)):
                 fn = (lambda: v.rank(dq, 1, out=d_out)) if op == "rank_1" else (lambda: v.select(dq, 1, out=d_out))
-                ms, best = time_gpu(fn, args.reps)
-                par = bool((d_out == want).all().item())  # vs the plain-vector kernels (themselves reference-checked in C2)
-                cpu = None
-                if ref is not None:
-                    f = (lambda: ref.rank(q[:ns], 1, threads=CORES)) if op == "rank_1" else (lambda: ref.select(q[:ns], 1, threads=CORES))
-                    t, w = time_cpu(f)
-                    par = par and bool((host(d_out[:ns]) == w).all())
-                    cpu = {"qps": ns / t, "cores": CORES, "sample": ns, "build_s": tb}
-                record(f"C3 2^{args.nbits_log2} bits, density {d:g}", f"{kind} {op}", nq, ms, best, nbytes, par, cpu,
-                       {"index_bytes": v.device_bytes, "gpu_build_s": build_s, "bits_per_bit": 8.0 * v.device_bytes / nbits})
+                cpu, w = None, None
+                for oname, order in (("auto", pkg.ORDER_AUTO), ("direct", pkg.ORDER_DIRECT)):
+                    if oname == "direct" and kind.startswith("rrr") and op == "select_1":
+                        continue  # rrr select has no binned form: auto == direct
+                    v.set_batch_order(order)
+                    ms, best = time_gpu(fn, args.reps)
+                    par = bool((d_out == want).all().item())  # vs the plain-vector kernels (themselves reference-checked in C2)
+                    if ref is not None:
+                        if cpu is None:
+                            f = (lambda: ref.rank(q[:ns], 1, threads=CORES)) if op == "rank_1" else (lambda: ref.select(q[:ns], 1, threads=CORES))
+                            t, w = time_cpu(f)
+                            cpu = {"qps": ns / t, "cores": CORES, "sample": ns, "build_s": tb}
+                        par = par and bool((host(d_out[:ns]) == w).all())
+                    record(f"C3 2^{args.nbits_log2} bits, density {d:g}", f"{kind} {op} [{oname} order]", nq, ms, best, nbytes, par, cpu,
+                           {"index_bytes": v.device_bytes, "gpu_build_s": build_s, "bits_per_bit": 8.0 * v.device_bytes / nbits, "batch_order": oname})
             v.close()
             del ref
         plain.close()
@@ -319,7 +332,7 @@ def main():
     ap.add_argument("--configs", default="C2,C3,C4,C5")
     ap.add_argument("--nbits-log2", type=int, default=33)
     ap.add_argument("--queries", type=float, default=1e8)
-    ap.add_argument("--queries-c3", type=float, default=2e7)
+    ap.add_argument("--queries-c3", type=float, default=1e8)
     ap.add_argument("--densities", default="0.01,0.05,0.1,0.25,0.5")
     ap.add_argument("--cpu-densities", default="0.1")
     ap.add_argument("--text-log2", type=int, default=28)
