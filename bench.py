@@ -73,8 +73,9 @@ class ClockSampler:
             for k, nm in enumerate(names):
                 if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(float(rows[0][2])) if rows else None,
-                "reasons": sorted(reasons), "samples": len(rows)}
+        pw = [float(r[3]) for r in rows if len(r) > 3 and r[3].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None, "sm_max_mhz": int(float(rows[0][2])) if rows else None,
+                "reasons": sorted(reasons), "samples": len(rows), "power_w_max": max(pw) if pw else None}
 
 
 def make_workload(nbits, nq, rank_seed):
@@ -127,7 +128,7 @@ def run_reference(args, rank, world):
                          "rank_qps": sample * args.steps / tr, "select_qps": sample * args.steps / ts},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, nbits):
@@ -138,7 +139,29 @@ def workload_config(args, nbits):
             "l2": "no flush needed: per step 1.6 GB of queries/results stream through and the 1.14 GiB index is gathered uniformly at random (L2 = 126 MB)"}
 
 
+_REAL_STDOUT = None
+
+
+def own_stdout():
+    """stdout carries exactly ONE JSON line: everything else any library prints there (NCCL's version banner, ...)
+    is sent to stderr by pointing fd 1 at fd 2 for the whole run; emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    own_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -168,7 +191,6 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = ge.load_package()
     nbits = 1 << args.nbits_log2
@@ -213,10 +235,9 @@ def main():
         step()
     barrier()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
+    sampler = ClockSampler(local)  # every rank watches its own GPU
+    sampler.start()
+    time.sleep(0.25)
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     barrier()
@@ -227,11 +248,16 @@ def main():
     t_end.record()
     barrier()
     w1 = time.perf_counter()
-    clocks = sampler.stop(w0, w1) if rank == 0 else None
+    clocks = sampler.stop(w0, w1)
     total_ms = t_start.elapsed_time(t_end)
     rank_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
     sel_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    per_rank = None
     if world > 1:
+        mine = torch.tensor([total_ms / args.steps, rank_ms, sel_ms, float(clocks.get("sm_mhz") or 0)], device="cuda", dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"ms_per_step": a[0].item(), "rank_ms": a[1].item(), "select_ms": a[2].item(), "sm_mhz": int(a[3].item())} for a in allr]
         t = torch.tensor([total_ms, rank_ms, sel_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, rank_ms, sel_ms = t.tolist()
@@ -274,7 +300,7 @@ def main():
         parity = {"checked_queries": 2 * ns, "against": kind, "bit_exact": ok}
         if not ok:
             raise SystemExit("bench.py: GPU results differ from the reference — refusing to report a number")
-        if not args.no_cpu_baseline and world >= 1:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is reported at N = 1 only
             sample = int(min(nq, args.ref_sample))
             kw = {"threads": cores} if kind == "reference" else {}
             chk.rank(idx[: sample // 10], 1, **kw)
@@ -314,10 +340,10 @@ def main():
             "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": 2 * nq * 8, "d2h_bytes_per_step": 2 * nq * 8,
                     "ms_per_step": e2e_s * 1e3, "path": "sdslgpu_rank/sdslgpu_select with pinned host buffers (chunked H2D/kernel/D2H)"},
             "gpu_launches": (6 if binned else 2) * args.steps, "batch_order": "binned" if binned else "direct",
-            "clocks": clocks, "parity": parity,
+            "clocks": clocks, "per_rank": per_rank, "parity": parity,
             "index_device_bytes": bv.device_bytes,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     bv.close()
     if world > 1:
         dist.destroy_process_group()

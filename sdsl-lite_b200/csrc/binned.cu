@@ -389,108 +389,6 @@ struct BvSelectOp
     }
 };
 
-// ------------------------------------------------------------------------------------------------
-// 2'. select over the runs with the bin's coarse hint table in shared memory.
-// All warps of a CTA work in the same bin (a CTA takes 8 consecutive runs per ticket), so the samples of that bin —
-// every 2^cs-th b-bit's block, a strided subset of the handle's sample table, at most 8193 entries = 32 KB — are
-// staged once per bin and a query costs ~1.5 block gathers instead of a sample gather plus ~1.2 block gathers.
-// ------------------------------------------------------------------------------------------------
-static constexpr uint32_t kCoarseMax = 8192; // spans per bin in the shared-memory table
-
-template <int B>
-__global__ void __launch_bounds__(kThreads, 6) bin_select_coarse_kernel(BvView const v,
-                                                                         uint64_t nsamp,
-                                                                         uint32_t const * __restrict__ recs,
-                                                                         uint16_t const * __restrict__ loff,
-                                                                         uint32_t shift,
-                                                                         uint32_t cs,
-                                                                         uint32_t nb,
-                                                                         uint64_t ntiles,
-                                                                         unsigned long long * __restrict__ ticket,
-                                                                         uint64_t * __restrict__ res)
-{
-    __shared__ uint32_t tbl[kCoarseMax + 1];
-    __shared__ unsigned long long s_w0;
-    uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint64_t const runs = (uint64_t)nb * ntiles;
-    uint32_t const * __restrict__ samp = v.samp[B];
-    uint32_t const log_s = v.log_s[B];
-    uint32_t const spans = 1u << (shift - cs); // per bin
-    uint32_t const c = blockIdx.x % kTicketLanes;
-    uint32_t cur_bin = 0xFFFFFFFFu;
-    for (;;)
-    {
-        __syncthreads(); // every warp is done with its previous run (and with tbl)
-        if (threadIdx.x == 0)
-            s_w0 = atomicAdd(ticket + c * kTicketStride, 1ull);
-        __syncthreads();
-        // ticket k of counter c = the 8 runs [8 * (32 k + c), +8): still handed out in increasing order
-        uint64_t const w0 = (s_w0 * kTicketLanes + c) * (kThreads / 32);
-        if (w0 >= runs)
-            break;
-        uint32_t const b0 = (uint32_t)(w0 / ntiles);
-        if (b0 != cur_bin)
-        {
-            uint64_t const first = (uint64_t)b0 << shift; // rank - 1 of the bin's first b-bit
-            for (uint32_t k = threadIdx.x; k <= spans; k += kThreads)
-            {
-                uint64_t j = (first + ((uint64_t)k << cs)) >> log_s;
-                tbl[k] = __ldg(samp + (j < nsamp ? j : nsamp)); // samp[nsamp] = sentinel: the last block
-            }
-            cur_bin = b0;
-            __syncthreads();
-        }
-        uint64_t const w = w0 + warp;
-        if (w >= runs)
-            continue;
-        uint32_t const b = (uint32_t)(w / ntiles);
-        uint64_t const t = w - (uint64_t)b * ntiles;
-        uint16_t const * o = loff + t * (nb + 2) + b;
-        uint32_t const o0 = __ldg(o), o1 = __ldg(o + 1);
-        uint64_t const hi1 = ((uint64_t)b << shift) + 1;
-        uint32_t const * r_in = recs + t * kTile;
-        uint64_t * r_out = res + t * kTile;
-        for (uint32_t k = o0 + lane; k < o1; k += 32)
-        {
-            uint32_t rec = ld_stream_u32(r_in + k);
-            uint64_t i = hi1 + rec, ans;
-            if (b == cur_bin)
-            {
-                uint32_t sp = rec >> cs;
-                ans = bv_select_coarse<B>(v, i, tbl[sp], tbl[sp + 1], rec & ((1u << cs) - 1u), cs);
-            }
-            else
-                ans = bv_select<B>(v, i); // the few runs of a ticket that already belong to the next bin
-            st_stream_u64(r_out + k, ans);
-        }
-    }
-}
-
-template <int B>
-static int bv_select_binned_coarse(BvImage const & v, uint64_t args, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done)
-{
-    *done = false;
-    BinPlan p;
-    if (!bin_make_plan(v.nblocks * sizeof(bvblock), args - 1, n, p))
-        return SDSLGPU_OK;
-    uint32_t const log_s = v.log_s[B];
-    if (p.shift < log_s || p.shift > 31)
-        return SDSLGPU_OK; // bins smaller than one sample span (tiny vectors) or in-bin offsets of 32 bits: generic kernel
-    uint32_t cs = p.shift > 13 ? p.shift - 13 : 0; // at most 8192 spans per bin
-    if (cs < log_s)
-        cs = log_s; // never finer than the handle's own samples
-    BinScratch w;
-    SG_TRY(bin_scratch_alloc(w, p, s));
-    SG_TRY(bin_launch_tile_sort(p, w, idx, n, 1, args - 1, false, s));
-    uint64_t tickets = ((uint64_t)p.nb * p.ntiles + kThreads / 32 - 1) / (kThreads / 32), cap = (uint64_t)kSmCount * 6;
-    unsigned grid = (unsigned)(tickets < cap ? (tickets ? tickets : 1) : cap);
-    bin_select_coarse_kernel<B><<<grid, kThreads, 0, s>>>(bv_view(v), v.nsamp[B], w.recs, w.loff, p.shift, cs, p.nb, p.ntiles, w.ticket, w.res);
-    SG_CUDA(cudaGetLastError());
-    SG_TRY(bin_launch_unsort(p, w, n, out, s));
-    *done = true;
-    return SDSLGPU_OK;
-}
-
 bool bv_binned_wanted(BvImage const & v, uint64_t n)
 {
     return bin_wanted(v.order, v.nblocks * sizeof(bvblock), n);
@@ -510,16 +408,6 @@ int bv_select_binned_device(BvImage const & v, int b, uint64_t const * idx, uint
     uint64_t args = b ? v.ones : v.nbits - v.ones, bytes = v.nblocks * sizeof(bvblock);
     if (args == 0)
         return SDSLGPU_OK; // every query is out of domain: the direct kernel answers NPOS
-    char const * e = std::getenv("SDSLGPU_BIN_SELECT_COARSE"); // tuning knob: 0 = generic kernel with the sample gather
-    if (n && !(e && std::atoi(e) == 0))
-    {
-        if (b)
-            SG_TRY(bv_select_binned_coarse<1>(v, args, idx, n, out, s, done));
-        else
-            SG_TRY(bv_select_binned_coarse<0>(v, args, idx, n, out, s, done));
-        if (*done)
-            return SDSLGPU_OK;
-    }
     if (b)
         return bin_run(BvSelectOp<1>{bv_view(v)}, bytes, 1, args - 1, idx, n, out, s, done);
     return bin_run(BvSelectOp<0>{bv_view(v)}, bytes, 1, args - 1, idx, n, out, s, done);

@@ -149,49 +149,4 @@ __device__ __forceinline__ uint64_t bv_select(BvView const & v, uint64_t i)
     return g * kBlockBits + block_select<B>(d, (uint32_t)need);
 }
 
-// select with a COARSE hint: lo / hi = blocks holding the first one of two consecutive spans of 2^log_span b-bits
-// around the i-th, r = (i - 1) mod 2^log_span.  Used by the binned select kernel, whose hint table lives in shared
-// memory: no sample gather, and on near-uniform data the interpolated block or its neighbour holds the answer.
-// Up to three probes, each moved by the count deficit at the span's average density; every hit is verified
-// (before < i <= before + ones in the block), anything else falls back to the exact path, so the result never
-// depends on how good the hint is.
-template <int B>
-__device__ __forceinline__ uint64_t bv_select_coarse(BvView const & v, uint64_t i, uint64_t lo, uint64_t hi, uint32_t r, uint32_t log_span)
-{
-    bvblock const * __restrict__ blocks = v.blocks;
-    uint64_t const * __restrict__ top = v.top;
-    // blocks per b-bit over the span, 16.16 fixed point (hi - lo < 2^32, log_span <= 32)
-    uint64_t const bpo = (((hi - lo + 1) << 16) >> log_span);
-    uint64_t g = lo + (((hi - lo) * r + ((1ull << log_span) >> 1)) >> log_span);
-#pragma unroll 1
-    for (int probe = 0; probe < 3 && lo <= hi; ++probe)
-    {
-        uint32_t cnt, d[7];
-        ld_block(blocks + g, cnt, d);
-        uint64_t a1 = __ldg(top + (g >> kSuperShift)) + cnt;
-        uint64_t before = B ? a1 : g * kBlockBits - a1;
-        uint32_t c = block_popc<B>(d);
-        // (the zero padding of the last block inflates c for B = 0, harmlessly: i <= #zeros, and the real zeros come first)
-        if (before < i && i <= before + c)
-            return g * kBlockBits + block_select<B>(d, (uint32_t)(i - before));
-        if (before >= i)
-        { // overshoot: the answer is in [lo, g - 1]
-            if (g == lo)
-                break;
-            hi = g - 1;
-            uint64_t back = 1 + (((before - i + 1) * bpo) >> 16);
-            g = (g - lo > back) ? g - back : lo;
-        }
-        else
-        { // undershoot: the answer is in [g + 1, hi]
-            if (g == hi)
-                break;
-            lo = g + 1;
-            uint64_t fwd = 1 + (((i - before - c) * bpo) >> 16);
-            g = (hi - g > fwd) ? g + fwd : hi;
-        }
-    }
-    return bv_select<B>(v, i);
-}
-
 } // namespace sdslgpu
