@@ -305,12 +305,14 @@ int bv_build(DevicePool & pool, BvImage & v, uint32_t flags, uint64_t const * wo
             uint64_t m = b ? v.ones : nbits - v.ones;
             // sample stride S = 2^log_s.  Small vectors: the largest power of two <= 64 with S <= 128 * density
             // (samples ~128 bits apart, the hinted block is almost always the right one).  Large vectors: S grows
-            // (up to 4096) until the u32 sample table is <= 32 MB, so the table stays resident in the 126 MB L2 and
+            // (up to 4096) until the u32 sample table is <= 48 MB, so the table stays resident in the 126 MB L2 and
             // a query pays ONE DRAM line (the sector block found by interpolating between two samples) instead of two.
+            // (48 MB, not 32: a 2^33-bit vector of density 1/2 has 2^32 +- 50 K ones — a 32 MB limit put S = 512 and
+            // S = 1024 on either side of that coin flip, and S = 1024 costs 12 % in both batch orders.)
             uint32_t ls = 6;
             while (ls > 0 && ((1ull << ls) * nbits > 128ull * m * 1ull) && m > 0)
                 --ls;
-            while (ls < 12 && 4ull * (m >> ls) > (32ull << 20))
+            while (ls < 12 && 4ull * (m >> ls) > (48ull << 20))
                 ++ls;
             if (char const * e = std::getenv("SDSLGPU_SELECT_LOG_S")) // tuning knob for experiments
                 ls = (uint32_t)std::atoi(e) > 16 ? 16u : (uint32_t)std::atoi(e);
