@@ -186,6 +186,16 @@ class _Handle:
         sd) are executed; never changes a result"""
         _check(lib().sdslgpu_set_batch_order(self._h, int(order)))
 
+    def serialize(self, what=0):
+        """the reference's serialize() / store_to_file bytes (sdslgpu_serialize): bit vectors what = 0 bit_vector,
+        1 / 2 rank_support_v<1> / <0> (need F_SDSL_LAYOUT), 3 / 4 select_support_mcl<1> / <0>; sd_vector what = 1 the
+        complete blob; rrr_vector, wavelet trees and csa_wt what = 0 the complete blob"""
+        n = C.c_uint64()
+        _check(lib().sdslgpu_serialize(self._h, what, None, 0, C.byref(n)))
+        buf = np.empty(max(n.value, 1), dtype=np.uint8)
+        _check(lib().sdslgpu_serialize(self._h, what, buf.ctypes.data, n.value, C.byref(n)))
+        return buf[: n.value].tobytes()
+
     def rank(self, idx, b=1, out=None, stream=None):
         p, n, keep, _ = _in_ptr(idx)
         po, o, _k = _out_like(idx, n, out)
@@ -224,13 +234,6 @@ class BitVector(_Handle):
         self.nbits = nbits
         self.flags = flags
 
-    def serialize(self, what):
-        """SDSL-format bytes (what: 0 bit_vector, 1 rank_support_v<1>, 2 rank_support_v<0>); needs F_SDSL_LAYOUT"""
-        n = C.c_uint64()
-        _check(lib().sdslgpu_bv_serialize(self._h, what, None, 0, C.byref(n)))
-        buf = np.empty(n.value, dtype=np.uint8)
-        _check(lib().sdslgpu_bv_serialize(self._h, what, buf.ctypes.data, n.value, C.byref(n)))
-        return buf.tobytes()
 
 
 class _WaveletTreeOps:
@@ -390,14 +393,6 @@ class _CompressedBitVector(_Handle):
         assert n >= (nbits + 63) // 64, "words too short for nbits"
         _check(getattr(lib(), self._create)(p if n else None, nbits, device, flags, C.byref(self._h)))
         self.nbits = nbits
-
-    def serialize(self, what=0):
-        n = C.c_uint64()
-        _check(lib().sdslgpu_serialize(self._h, what, None, 0, C.byref(n)))
-        buf = np.empty(max(n.value, 1), dtype=np.uint8)
-        _check(lib().sdslgpu_serialize(self._h, what, buf.ctypes.data, n.value, C.byref(n)))
-        return buf[: n.value].tobytes()
-
 
 class RrrVector(_CompressedBitVector):
     """rrr_vector<63> + rank_support_rrr + select_support_rrr, encoded on the device"""

@@ -803,14 +803,24 @@ extern "C"
         SG_TRY(check_handle(h));
         if (!nbytes)
             return SDSLGPU_EINVAL;
-        if (h->kind == SDSLGPU_KIND_BV)
+        if (h->kind == SDSLGPU_KIND_BV && what >= 0 && what <= 2)
             return sdslgpu_bv_serialize(h, what, buf, cap, nbytes);
         DeviceGuard g(h->device);
         std::vector<uint8_t> blob;
-        if (h->kind == SDSLGPU_KIND_RRR63 && what == 0)
+        if (h->kind == SDSLGPU_KIND_BV && (what == 3 || what == 4))
+            SG_TRY(egress_select_mcl(h->bv, what == 3 ? 1 : 0, blob));
+        else if (h->kind == SDSLGPU_KIND_RRR63 && what == 0)
             SG_TRY(rrr_serialize(h, blob));
         else if (h->kind == SDSLGPU_KIND_SD && what == 0)
             SG_TRY(sd_serialize_low_high(h, blob));
+        else if (h->kind == SDSLGPU_KIND_SD && what == 1)
+            SG_TRY(egress_sd(h, blob));
+        else if (h->kind == SDSLGPU_KIND_WT_HUFF && what == 0)
+            SG_TRY(egress_wt_huff(h, blob));
+        else if (h->kind == SDSLGPU_KIND_WT_INT && what == 0)
+            SG_TRY(egress_wt_int(h, blob));
+        else if (h->kind == SDSLGPU_KIND_CSA_WT && what == 0)
+            SG_TRY(egress_csa(h, blob));
         else
         {
             set_error("sdslgpu_serialize: unsupported (kind %d, what %d)", h->kind, what);

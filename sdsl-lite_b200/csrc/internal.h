@@ -325,6 +325,10 @@ int wt_huff_build_from_text(sdslgpu_handle * h, uint8_t const * text_host, uint6
 int wt_rank_device(sdslgpu_handle const * h, uint64_t const * i, uint8_t const * c, uint64_t n, uint64_t * out, cudaStream_t s);
 int wt_select_device(sdslgpu_handle const * h, uint64_t const * i, uint8_t const * c, uint64_t n, uint64_t * out, cudaStream_t s);
 int wt_access_device(sdslgpu_handle const * h, uint64_t const * i, uint64_t n, uint64_t * sym, uint64_t * rnk, cudaStream_t s);
+// wt_build.cu: bit planes on the device; SDSLGPU_ENOTSUP = not enough device memory for the scratch (use the host fill)
+int wt_histogram_device(uint8_t const * d_text, uint64_t n, uint64_t (&C)[256], cudaStream_t s);
+int wt_huff_planes_device(uint8_t const * d_text, uint64_t n, WtTree const & tree, uint64_t bits, uint64_t * d_words, cudaStream_t s);
+int wt_int_planes_device(uint64_t * d_seq, uint64_t n, uint32_t * max_level_out, uint64_t * sigma_out, uint64_t ** d_words_out, cudaStream_t s);
 // wt_int.cu
 int wt_int_build(sdslgpu_handle * h, uint64_t const * seq_host, uint64_t n, cudaStream_t s);
 int wt_int_rank_device(sdslgpu_handle const * h, uint64_t const * i, uint64_t const * c, uint64_t n, uint64_t * out, cudaStream_t s);
@@ -336,6 +340,7 @@ int rrr_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint6
 int rrr_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 int rrr_access_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 int rrr_serialize(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
+int rrr_serialize_image(RrrImage const & r, std::vector<uint8_t> & blob); // appends rrr_vector<63>::serialize bytes
 int rrr_upload_tables(DevicePool & pool, RrrImage & r, cudaStream_t s);
 int rrr_build_hints(DevicePool & pool, RrrImage & r, cudaStream_t s);
 int rrr_build_image(DevicePool & pool, RrrImage & r, uint64_t const * words_host_or_dev, bool on_device, uint64_t nbits, cudaStream_t s);
@@ -350,6 +355,12 @@ int sd_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64
 int sd_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 int sd_access_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 int sd_serialize_low_high(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
+// sdsl_egress.cu: complete reference-format blobs (what the reference's serialize() / store_to_file writes)
+int egress_select_mcl(BvImage const & v, int b, std::vector<uint8_t> & blob);
+int egress_sd(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
+int egress_wt_huff(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
+int egress_wt_int(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
+int egress_csa(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
 // gpu_sa.cu
 int gpu_suffix_array_bwt(uint8_t const * text_host, uint64_t len, uint32_t dens, uint32_t isa_dens, std::vector<uint8_t> & bwt, std::vector<uint64_t> & samples,
                          std::vector<uint64_t> & isa_samples, uint32_t * rounds_out, cudaStream_t s);

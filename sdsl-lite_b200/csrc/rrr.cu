@@ -534,7 +534,11 @@ int rrr_access_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t n
 // reproduces the reference's m_bt / m_btnr / m_btnrp / m_rank / m_invert bit for bit
 int rrr_serialize(sdslgpu_handle const * h, std::vector<uint8_t> & blob)
 {
-    RrrImage const & r = h->rrr;
+    return rrr_serialize_image(h->rrr, blob);
+}
+
+int rrr_serialize_image(RrrImage const & r, std::vector<uint8_t> & blob)
+{
     std::vector<uint64_t> btnr((r.btnr_bits + 63) >> 6), rec(kRecWords * (r.nsuper + 1));
     SG_CUDA(cudaMemcpy(btnr.data(), r.btnr, btnr.size() * 8, cudaMemcpyDeviceToHost));
     SG_CUDA(cudaMemcpy(rec.data(), r.records, rec.size() * 8, cudaMemcpyDeviceToHost));

@@ -383,8 +383,66 @@ int wt_huff_finish(sdslgpu_handle * h, uint64_t size, uint64_t sigma, WtTree con
     return SDSLGPU_OK;
 }
 
+// Device path of the constructor: text -> HBM, symbol counts, (host: Huffman shape), bit planes (wt_build.cu), rank
+// blocks + select samples (bv.cu) without the bits ever visiting the host.  *done = false: not enough device memory
+// for the sort scratch (6 bytes per symbol) or SDSLGPU_HOST_WT=1 — the caller takes the host fill below.
+static int wt_huff_build_on_device(sdslgpu_handle * h, uint8_t const * text, uint64_t n, cudaStream_t s, bool * done)
+{
+    *done = false;
+    char const * force_host = std::getenv("SDSLGPU_HOST_WT");
+    if (n == 0 || (force_host && std::atoi(force_host) != 0))
+        return SDSLGPU_OK;
+    uint8_t * d_text = nullptr;
+    if (cudaMalloc(reinterpret_cast<void **>(&d_text), n) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return SDSLGPU_OK;
+    }
+    struct Free
+    {
+        void * p;
+        ~Free()
+        {
+            cudaFree(p);
+        }
+    } free_text{d_text};
+    SG_CUDA(cudaMemcpyAsync(d_text, text, n, cudaMemcpyHostToDevice, s));
+    uint64_t C[256];
+    int st = wt_histogram_device(d_text, n, C, s);
+    if (st == SDSLGPU_ENOTSUP)
+        return SDSLGPU_OK;
+    SG_TRY(st);
+    WtTree tree;
+    uint64_t sigma = 0;
+    uint64_t bits = build_huff_tree(C, tree, sigma);
+    uint64_t * d_words = nullptr;
+    if (cudaMalloc(reinterpret_cast<void **>(&d_words), (((bits + 63) >> 6) + 2) * 8) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return SDSLGPU_OK;
+    }
+    Free free_words{d_words};
+    st = wt_huff_planes_device(d_text, n, tree, bits, d_words, s);
+    if (st == SDSLGPU_ENOTSUP)
+        return SDSLGPU_OK;
+    SG_TRY(st);
+    WtHuffImage & w = h->wt;
+    w.use_rrr = (h->flags & SDSLGPU_F_RRR_BV) != 0;
+    if (w.use_rrr)
+        SG_TRY(rrr_build_image(h->pool, w.rrr, d_words, true, bits, s));
+    else
+        SG_TRY(bv_build(h->pool, w.bv, h->flags & ~SDSLGPU_F_NO_SELECT, d_words, true, bits, s));
+    SG_TRY(wt_huff_finish(h, n, sigma, tree, s));
+    *done = true;
+    return SDSLGPU_OK;
+}
+
 int wt_huff_build_from_text(sdslgpu_handle * h, uint8_t const * text, uint64_t n, cudaStream_t s)
 {
+    bool done = false;
+    SG_TRY(wt_huff_build_on_device(h, text, n, s, &done));
+    if (done)
+        return SDSLGPU_OK;
     uint64_t C[256] = {0};
     {
         unsigned T = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));

@@ -10,6 +10,8 @@
 // and issued together.
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace sdslgpu
@@ -164,8 +166,54 @@ __global__ void __launch_bounds__(kThreads)
 // ------------------------------------------------------------------------------------------------
 // host builder: level k = the sequence stably sorted by its top k bits, bit (max_level - k - 1) of each element
 // ------------------------------------------------------------------------------------------------
+// Device path (wt_build.cu): sequence -> HBM, one stable radix pass per level, rank blocks + select samples from the
+// device-resident level bits.  *done = false: no device memory for the scratch or SDSLGPU_HOST_WT=1 (host fill below).
+static int wt_int_build_on_device(sdslgpu_handle * h, uint64_t const * seq, uint64_t n, cudaStream_t s, bool * done)
+{
+    *done = false;
+    char const * force_host = std::getenv("SDSLGPU_HOST_WT");
+    if (n == 0 || (force_host && std::atoi(force_host) != 0))
+        return SDSLGPU_OK;
+    struct Free
+    {
+        void * p;
+        ~Free()
+        {
+            if (p)
+                cudaFree(p);
+        }
+    };
+    uint64_t * d_seq = nullptr;
+    if (cudaMalloc(reinterpret_cast<void **>(&d_seq), n * 8) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return SDSLGPU_OK;
+    }
+    Free free_seq{d_seq};
+    SG_CUDA(cudaMemcpyAsync(d_seq, seq, n * 8, cudaMemcpyHostToDevice, s));
+    WtIntImage & w = h->wti;
+    uint64_t * d_words = nullptr;
+    uint32_t levels = 0;
+    uint64_t sigma = 0;
+    int st = wt_int_planes_device(d_seq, n, &levels, &sigma, &d_words, s);
+    if (st == SDSLGPU_ENOTSUP)
+        return SDSLGPU_OK;
+    SG_TRY(st);
+    Free free_words{d_words};
+    w.size = n;
+    w.sigma = sigma;
+    w.max_level = levels;
+    SG_TRY(bv_build(h->pool, w.tree, h->flags & ~SDSLGPU_F_NO_SELECT, d_words, true, n * levels, s));
+    *done = true;
+    return SDSLGPU_OK;
+}
+
 int wt_int_build(sdslgpu_handle * h, uint64_t const * seq, uint64_t n, cudaStream_t s)
 {
+    bool done = false;
+    SG_TRY(wt_int_build_on_device(h, seq, n, s, &done));
+    if (done)
+        return SDSLGPU_OK;
     WtIntImage & w = h->wti;
     w.size = n;
     w.sigma = 0;
