@@ -146,13 +146,17 @@ int sdslgpu_access(const sdslgpu_handle *h, const uint64_t *idx, uint64_t n, uin
 /* ---- wavelet trees ---------------------------------------------------------------------------- */
 
 /* Replaces wt_huff<>(text) = wt_pc<huff_shape,...> ctor (wt_pc.hpp:194-248, wt_huff.hpp:82-115,
- * wt_helper.hpp:230-327).  `text` is a HOST buffer of n bytes (any byte values).  The Huffman shape is
- * computed on the host with the reference's tie-breaking, so the concatenated bit vector and node table
- * equal the reference's; rank/select structures over it are built on the device. */
+ * wt_helper.hpp:230-327).  `text` is a HOST buffer of n bytes (any byte values).  The Huffman shape
+ * (<= 511 nodes) is computed on the host with the reference's tie-breaking; the concatenated bit vector m_bv is
+ * built on the device — one stable radix pass per tree depth over the device-resident text (wt_build.cu) — and is
+ * bit-identical to the reference's, as are the node table and the serialised tree (sdslgpu_serialize); rank / select
+ * structures over it are built on the device.  (SDSLGPU_HOST_WT=1, or no device memory for the 6 bytes/symbol of
+ * sort scratch: the multi-threaded host fill produces the same bits.) */
 int sdslgpu_wt_huff_create(const uint8_t *text, uint64_t n, int device, uint32_t flags, sdslgpu_handle **out);
 
 /* Replaces wt_int<>(seq) (wt_int.hpp:160-260): `seq` is a HOST array of n integers; the level bit vector
- * m_tree (max_level = hi(max)+1 levels of n bits) is laid out exactly like the reference's. */
+ * m_tree (max_level = hi(max)+1 levels of n bits) is laid out exactly like the reference's; like wt_huff it is built
+ * on the device (level k = the sequence stably radix-sorted by its top k bits). */
 int sdslgpu_wt_int_create(const uint64_t *seq, uint64_t n, int device, uint32_t flags, sdslgpu_handle **out);
 
 /* number of distinct symbols (wt.sigma, wt_pc.hpp:177) */
@@ -236,12 +240,24 @@ int sdslgpu_bv_serialize(const sdslgpu_handle *h, int what, void *buf, uint64_t 
 int sdslgpu_load_sdsl(const void *blob, uint64_t nbytes, int kind, int device, uint32_t flags, uint32_t param,
                       sdslgpu_handle **out);
 
-/* Same protocol for the other kinds (what = 0):
- *   KIND_BV     -> as sdslgpu_bv_serialize (what 0..2)
- *   KIND_RRR63  -> the complete rrr_vector<63>::serialize bytes (rrr_vector.hpp:366-378)
- *   KIND_SD     -> size, wl, m_low, m_high as sd_vector::serialize writes them (sd_vector.hpp:426-433; the two
- *                  select supports that follow in the reference's file are not part of this engine's image);
- *                  needs SDSLGPU_F_SDSL_LAYOUT. */
+/* Egress: the bytes the reference's serialize() / store_to_file (io.hpp:877-896) writes for the same input, so that
+ * an index built here can be stored and loaded by the reference (and by sdslgpu_load_sdsl).  Same buffer protocol as
+ * sdslgpu_bv_serialize.
+ *   KIND_BV      what 0..2 as sdslgpu_bv_serialize; what 3 / 4 = select_support_mcl<1> / <0>::serialize
+ *                (select_support_mcl.hpp:474-518) with the contents of init_slow / init_fast (:207-381): the argument
+ *                positions they store come from the batched select kernel, the host only packs them
+ *   KIND_RRR63   what 0 = the complete rrr_vector<63>::serialize bytes (rrr_vector.hpp:366-378)
+ *   KIND_SD      what 0 = size, wl, m_low, m_high (sd_vector.hpp:426-433; needs SDSLGPU_F_SDSL_LAYOUT);
+ *                what 1 = the complete sd_vector<>::serialize bytes incl. the two select supports over m_high (:434-435)
+ *   KIND_WT_HUFF what 0 = wt_pc::serialize (wt_pc.hpp:713-726): size, sigma, m_bv, rank_support_v<1>,
+ *                select_support_mcl<1>, <0>, byte_tree (wt_helper.hpp:362-375); with SDSLGPU_F_RRR_BV the
+ *                wt_huff<rrr_vector<63>> form (the rrr supports serialise to nothing, rrr_vector.hpp:580-585)
+ *   KIND_WT_INT  what 0 = wt_int::serialize (wt_int.hpp:792-805)
+ *   KIND_CSA_WT  what 0 = csa_wt::serialize (csa_wt.hpp:389-402): wavelet tree, SA samples, ISA samples (both
+ *                int_vector<0> of width hi(size)+1, csa_sampling_strategy.hpp:103,762), byte_alphabet
+ *                (csa_alphabet_strategy.hpp:258-268)
+ * Byte-identical to the reference for every non-empty input (tests/test_egress_gpu.py; an EMPTY wt_huff of the
+ * reference serialises uninitialised tables, here they are written as "no symbol"). */
 int sdslgpu_serialize(const sdslgpu_handle *h, int what, void *buf, uint64_t cap, uint64_t *nbytes);
 
 #ifdef __cplusplus

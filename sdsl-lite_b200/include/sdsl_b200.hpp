@@ -14,7 +14,12 @@
 // (the reference throws std::logic_error / std::runtime_error from constructors too).
 #pragma once
 #include <cstdint>
+#include <fstream>
+#include <istream>
+#include <iterator>
 #include <memory>
+#include <ostream>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -51,6 +56,29 @@ inline int & default_device()
 {
     static int d = 0;
     return d;
+}
+// the reference's serialize() bytes of a device image (sdslgpu_serialize) / a device image from such bytes
+inline std::vector<uint8_t> image_blob(sdslgpu_handle const * h, int what)
+{
+    uint64_t n = 0;
+    check(sdslgpu_serialize(h, what, nullptr, 0, &n), "serialize");
+    std::vector<uint8_t> blob(n ? n : 1);
+    check(sdslgpu_serialize(h, what, blob.data(), n, &n), "serialize");
+    blob.resize(n);
+    return blob;
+}
+inline size_type write_blob(sdslgpu_handle const * h, int what, std::ostream & out)
+{
+    std::vector<uint8_t> blob = image_blob(h, what);
+    out.write(reinterpret_cast<char const *>(blob.data()), (std::streamsize)blob.size());
+    return blob.size();
+}
+inline handle_ptr load_blob(std::istream & in, int kind, uint32_t flags, uint32_t param)
+{
+    std::vector<char> blob((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>()); // the rest of the stream
+    sdslgpu_handle * h = nullptr;
+    check(sdslgpu_load_sdsl(blob.data(), blob.size(), kind, default_device(), flags, param, &h), "load");
+    return adopt(h);
 }
 } // namespace detail
 
@@ -295,6 +323,17 @@ public:
         check(sdslgpu_access(image(), &i, 1, &r, nullptr), "operator[]");
         return r != 0;
     }
+    //! serialize (rrr_vector.hpp:366-378, sd_vector.hpp:426-438): the reference's bytes, supports included
+    size_type serialize(std::ostream & out) const
+    {
+        return detail::write_blob(image(), KIND == SDSLGPU_KIND_SD ? 1 : 0, out);
+    }
+    //! load: reads the REST of the stream (one structure per stream / file, as store_to_file writes it)
+    void load(std::istream & in)
+    {
+        m_image = detail::load_blob(in, KIND, SDSLGPU_F_DEFAULT, 0);
+        check(sdslgpu_size(m_image.get(), &m_size), "size");
+    }
     sdslgpu_handle const * image() const
     {
         if (!m_image)
@@ -370,6 +409,12 @@ public:
     {
         check(sdslgpu_wt_access(image(), i, n, sym_out, rank_out, stream), "wt.access");
     }
+    //! serialize (wt_pc.hpp:713-726, wt_int.hpp:792-805): byte-identical to the reference's, so that the reference
+    //! can load an index built here (and `load` below takes what the reference stored)
+    size_type serialize(std::ostream & out) const
+    {
+        return detail::write_blob(image(), 0, out);
+    }
     sdslgpu_handle const * image() const
     {
         if (!m_image)
@@ -380,10 +425,14 @@ public:
 protected:
     void adopt_image(sdslgpu_handle * h)
     {
-        m_image = adopt(h);
-        check(sdslgpu_size(h, &m_size), "size");
+        adopt_ptr(adopt(h));
+    }
+    void adopt_ptr(handle_ptr p)
+    {
+        m_image = p;
+        check(sdslgpu_size(p.get(), &m_size), "size");
         uint64_t s = 0;
-        check(sdslgpu_wt_sigma(h, &s), "sigma");
+        check(sdslgpu_wt_sigma(p.get(), &s), "sigma");
         sigma = s;
     }
     size_type m_size = 0;
@@ -404,6 +453,11 @@ public:
     }
     explicit wt_huff(std::string const & text) : wt_huff(reinterpret_cast<uint8_t const *>(text.data()), reinterpret_cast<uint8_t const *>(text.data()) + text.size())
     {}
+    //! load (wt_pc.hpp:729-741): reads the rest of the stream
+    void load(std::istream & in)
+    {
+        adopt_ptr(detail::load_blob(in, SDSLGPU_KIND_WT_HUFF, SDSLGPU_F_DEFAULT, 0));
+    }
 };
 
 class wt_int : public detail::wavelet_tree_base<uint64_t>
@@ -418,6 +472,11 @@ public:
     }
     explicit wt_int(std::vector<uint64_t> const & seq) : wt_int(seq.data(), seq.data() + seq.size())
     {}
+    //! load (wt_int.hpp:808-821): reads the rest of the stream
+    void load(std::istream & in)
+    {
+        adopt_ptr(detail::load_blob(in, SDSLGPU_KIND_WT_INT, SDSLGPU_F_DEFAULT, 0));
+    }
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -457,6 +516,18 @@ public:
         uint64_t r;
         check(sdslgpu_wt_rank(image(), &i, &c, 1, &r, nullptr), "rank_bwt");
         return r;
+    }
+    //! serialize (csa_wt.hpp:389-402): wavelet tree, SA samples, ISA samples, alphabet — the reference's bytes
+    size_type serialize(std::ostream & out) const
+    {
+        return detail::write_blob(image(), 0, out);
+    }
+    //! load (csa_wt.hpp:410-416): reads the rest of the stream; t_dens is a template argument in the reference and is
+    //! not stored in the file, so an index sampled at another density needs it named here (0 = 32)
+    void load(std::istream & in, uint32_t t_dens = 0)
+    {
+        m_image = detail::load_blob(in, SDSLGPU_KIND_CSA_WT, SDSLGPU_F_DEFAULT, t_dens);
+        check(sdslgpu_size(m_image.get(), &m_size), "size");
     }
     sdslgpu_handle const * image() const
     {
@@ -543,6 +614,37 @@ inline void locate(csa_wt const & csa, std::vector<std::string> const & pats, st
     occ.assign(total, 0);
     if (total)
         check(sdslgpu_fm_locate(csa.image(), bytes, off.data(), pats.size(), occ_off.data(), occ.data(), total, &total, nullptr), "locate");
+}
+
+//! sdsl::store_to_file(v, file) (io.hpp:877-896): true on success
+template <class T>
+bool store_to_file(T const & v, std::string const & file)
+{
+    std::ofstream out(file, std::ios::binary | std::ios::trunc | std::ios::out);
+    if (!out)
+        return false;
+    v.serialize(out);
+    out.close();
+    return (bool)out;
+}
+
+//! sdsl::load_from_file(v, file) (io.hpp:992-1011): true on success
+template <class T>
+bool load_from_file(T & v, std::string const & file)
+{
+    std::ifstream in(file, std::ios::binary | std::ios::in);
+    if (!in)
+        return false;
+    v.load(in);
+    return true;
+}
+
+//! sdsl::size_in_bytes(v) (io.hpp:778-786): length of the serialised form
+template <class T>
+size_type size_in_bytes(T const & v)
+{
+    std::ostringstream os;
+    return v.serialize(os);
 }
 
 } // namespace sdsl_b200

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <random>
+#include <sstream>
 #include <string>
 
 #include "../../sdsl-lite_b200/include/sdsl_b200.hpp"
@@ -166,6 +167,38 @@ int main(int argc, char ** argv)
     std::vector<uint64_t> occ_off, occs;
     locate(csa, std::vector<std::string>{"sim", "cad"}, occ_off, occs);
     EXPECT(occ_off.size() == 3 && occ_off[2] == 4 && occs[0] == 24);
+    // ---- serialize / load / store_to_file / load_from_file (io.hpp:877-896, 992-1011): round trips through the
+    //      reference's byte format
+    {
+        std::stringstream ss;
+        uint64_t written = wt.serialize(ss);
+        EXPECT(written == ss.str().size() && written == size_in_bytes(wt));
+        wt_huff wt2;
+        wt2.load(ss);
+        EXPECT(wt2.size() == wt.size() && wt2.sigma == wt.sigma);
+        for (uint64_t j = 0; j < text.size(); j += 131)
+            EXPECT(wt2[j] == wt[j] && wt2.rank(j, (uint8_t)text[j]) == wt.rank(j, (uint8_t)text[j]));
+        std::string file = "/tmp/sdsl_b200_shim_test.csa";
+        EXPECT(store_to_file(csa, file));
+        csa_wt csa2;
+        EXPECT(load_from_file(csa2, file) && csa2.size() == csa.size());
+        EXPECT(count(csa2, std::string("abra")) == 6 && extract(csa2, 12, 22) == "abracadabra");
+        EXPECT(!load_from_file(csa2, "/nonexistent/dir/x.csa"));
+        std::remove(file.c_str());
+        std::stringstream s2, s3;
+        wi.serialize(s2);
+        wt_int wi2;
+        wi2.load(s2);
+        EXPECT(wi2.size() == wi.size() && wi2[5] == wi[5]);
+        bit_vector bv(5000);
+        for (uint64_t j = 0; j < 5000; j += 7)
+            bv.set(j, true);
+        sd_vector<> sd(bv), sd2;
+        sd.serialize(s3);
+        sd2.load(s3);
+        sd_vector<>::rank_1_type r1(&sd), r2(&sd2);
+        EXPECT(sd2.size() == 5000 && r1.rank(4321) == r2.rank(4321));
+    }
     std::printf("shim_test ok\n");
     return 0;
 }
