@@ -806,8 +806,15 @@ extern "C"
         if (h->kind == SDSLGPU_KIND_BV && what >= 0 && what <= 2)
             return sdslgpu_bv_serialize(h, what, buf, cap, nbytes);
         DeviceGuard g(h->device);
+        sdslgpu_handle * hm = const_cast<sdslgpu_handle *>(h);
+        std::lock_guard<std::mutex> lock(hm->ser_mu);
         std::vector<uint8_t> blob;
-        if (h->kind == SDSLGPU_KIND_BV && (what == 3 || what == 4))
+        if (hm->ser_what == what && buf)
+        { // the size query before this call already built it
+            blob.swap(hm->ser_blob);
+            hm->ser_what = -1;
+        }
+        else if (h->kind == SDSLGPU_KIND_BV && (what == 3 || what == 4))
             SG_TRY(egress_select_mcl(h->bv, what == 3 ? 1 : 0, blob));
         else if (h->kind == SDSLGPU_KIND_RRR63 && what == 0)
             SG_TRY(rrr_serialize(h, blob));
@@ -828,7 +835,11 @@ extern "C"
         }
         *nbytes = blob.size();
         if (!buf)
+        {
+            hm->ser_blob.swap(blob);
+            hm->ser_what = what;
             return SDSLGPU_OK;
+        }
         if (cap < blob.size())
         {
             set_error("sdslgpu_serialize: buffer too small");

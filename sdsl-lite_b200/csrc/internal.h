@@ -262,6 +262,10 @@ struct sdslgpu_handle
     sdslgpu::WtIntImage wti;    // KIND_WT_INT
     sdslgpu::RrrImage rrr;      // KIND_RRR63
     sdslgpu::SdImage sd;        // KIND_SD
+    // sdslgpu_serialize: the blob computed by a size query (buf == NULL) is kept for the call that fetches it
+    std::mutex ser_mu;
+    std::vector<uint8_t> ser_blob;
+    int ser_what = -1;
 };
 
 namespace sdslgpu
