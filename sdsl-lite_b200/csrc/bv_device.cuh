@@ -60,14 +60,85 @@ __device__ __forceinline__ uint64_t abs_before(bvblock const * __restrict__ bloc
     return B ? a1 : b * kBlockBits - a1;
 }
 
+// position of the i-th (1-based) B-bit, given that it lies in a block of [lo, hi] and fewer than i B-bits precede
+// block lo.  r / 2^log_span = how far i lies between the two bracketing hints in B-bit count; with `interp` the
+// search starts at the interpolated block — for the sparse hint tables that stay on chip (spans up to 2^14 B-bits)
+// this lands in the right sector block 75-90 % of the time on random data; any miss is repaired by walking /
+// bisecting on the block counts, so the result never depends on the guess.
+template <int B>
+__device__ __forceinline__ uint64_t bv_select_between(BvView const & v, uint64_t i, uint64_t lo, uint64_t hi, uint64_t r, uint32_t log_span, bool interp)
+{
+    bvblock const * __restrict__ blocks = v.blocks;
+    uint64_t const * __restrict__ top = v.top;
+    uint32_t cnt, d[7];
+    uint64_t g = interp ? lo + (((hi - lo) * r + (1ull << log_span >> 1)) >> log_span) : lo;
+    ld_block(blocks + g, cnt, d);
+    uint64_t a1 = __ldg(top + (g >> kSuperShift)) + cnt;
+    uint64_t before = B ? a1 : g * kBlockBits - a1;
+    uint32_t steps = 0;
+    if (before >= i)
+    { // overshoot: the answer is in [lo, g-1].  Walk left; after three near misses with a long way to go (clustered
+      // data, wide hint spans) bisect on the block counts, then finish the walk
+        for (;;)
+        {
+            --g;
+            if (++steps == 4 && g - lo > 3)
+            {
+                uint64_t h = g; // before(h + 1) >= i, before(lo) < i
+                while (h - lo > 3)
+                {
+                    uint64_t mid = (lo + h + 1) >> 1;
+                    if (abs_before<B>(blocks, top, mid) < i)
+                        lo = mid;
+                    else
+                        h = mid - 1;
+                }
+                g = h;
+            }
+            ld_block(blocks + g, cnt, d);
+            a1 = __ldg(top + (g >> kSuperShift)) + cnt;
+            before = B ? a1 : g * kBlockBits - a1;
+            if (before < i)
+                break; // the first block from the right whose prefix count drops below i holds the answer
+        }
+    }
+    uint64_t need = i - before;
+    uint32_t c = block_popc<B>(d);
+    while (need > c)
+    { // undershoot: walk right, same escape to a bisection
+        need -= c;
+        ++g;
+        if (++steps == 4 && hi - g > 8)
+        {
+            uint64_t l = g, h = hi; // before(l) < i
+            while (h - l > 3)
+            {
+                uint64_t mid = (l + h + 1) >> 1;
+                if (abs_before<B>(blocks, top, mid) < i)
+                    l = mid;
+                else
+                    h = mid - 1;
+            }
+            g = l;
+            ld_block(blocks + g, cnt, d);
+            a1 = __ldg(top + (g >> kSuperShift)) + cnt;
+            before = B ? a1 : g * kBlockBits - a1;
+            need = i - before;
+        }
+        else
+            ld_block(blocks + g, cnt, d);
+        c = block_popc<B>(d);
+    }
+    return g * kBlockBits + block_select<B>(d, (uint32_t)need);
+}
+
+
 // position of the i-th (1-based) B-bit, given 1 <= i <= #B-bits
 // (device form of select_support_mcl<B>::select, select_support_mcl.hpp:384-439: sampled hint, then a
 //  scan over block counts instead of the reference's word scan)
 template <int B>
 __device__ __forceinline__ uint64_t bv_select(BvView const & v, uint64_t i)
 {
-    bvblock const * __restrict__ blocks = v.blocks;
-    uint64_t const * __restrict__ top = v.top;
     uint32_t const * __restrict__ samp = v.samp[B];
     uint32_t const log_s = v.log_s[B];
     uint64_t j = (i - 1) >> log_s;
@@ -85,68 +156,7 @@ __device__ __forceinline__ uint64_t bv_select(BvView const & v, uint64_t i)
         lo = __ldg(samp + j);
         hi = __ldg(samp + j + 1);
     }
-    // invariant: the answer lies in a block of [lo, hi] and abs_before(lo) < i.
-    // Interpolate: the (r+1)-th of the S b-bits between the two samples sits about r/S of the way from lo to hi.
-    // For the sparse sample tables that stay L2-resident (S up to 4096) this lands in the right sector block
-    // ~90 % of the time on random data; any miss is repaired by walking / bisecting on the block counts, so
-    // the result never depends on the guess.
-    uint32_t cnt, d[7];
-    uint64_t g = v.interp[B] ? lo + (((hi - lo) * ((i - 1) & ((1ull << log_s) - 1)) + (1ull << log_s >> 1)) >> log_s) : lo;
-    ld_block(blocks + g, cnt, d);
-    uint64_t a1 = __ldg(top + (g >> kSuperShift)) + cnt;
-    uint64_t before = B ? a1 : g * kBlockBits - a1;
-    if (before >= i)
-    { // overshoot: the answer is in [lo, g-1]
-        hi = g - 1;
-        while (hi - lo > 3)
-        {
-            uint64_t mid = (lo + hi + 1) >> 1;
-            if (abs_before<B>(blocks, top, mid) < i)
-                lo = mid;
-            else
-                hi = mid - 1;
-        }
-        // walk left from hi: the first block whose prefix count drops below i holds the answer
-        g = hi;
-        for (;;)
-        {
-            ld_block(blocks + g, cnt, d);
-            a1 = __ldg(top + (g >> kSuperShift)) + cnt;
-            before = B ? a1 : g * kBlockBits - a1;
-            if (before < i)
-                break;
-            --g;
-        }
-    }
-    else if (hi - g > 8)
-    { // far undershoot (clustered data): bisect on the counts first
-        lo = g;
-        while (hi - lo > 3)
-        {
-            uint64_t mid = (lo + hi + 1) >> 1;
-            if (abs_before<B>(blocks, top, mid) < i)
-                lo = mid;
-            else
-                hi = mid - 1;
-        }
-        if (lo != g)
-        {
-            g = lo;
-            ld_block(blocks + g, cnt, d);
-            a1 = __ldg(top + (g >> kSuperShift)) + cnt;
-            before = B ? a1 : g * kBlockBits - a1;
-        }
-    }
-    uint64_t need = i - before;
-    uint32_t c = block_popc<B>(d);
-    while (need > c)
-    { // walk right
-        need -= c;
-        ++g;
-        ld_block(blocks + g, cnt, d);
-        c = block_popc<B>(d);
-    }
-    return g * kBlockBits + block_select<B>(d, (uint32_t)need);
+    return bv_select_between<B>(v, i, lo, hi, (i - 1) & ((1ull << log_s) - 1), log_s, v.interp[B] != 0);
 }
 
 } // namespace sdslgpu
