@@ -803,8 +803,8 @@ extern "C"
         SG_TRY(check_handle(h));
         if (!nbytes)
             return SDSLGPU_EINVAL;
-        if (h->kind == SDSLGPU_KIND_BV && what >= 0 && what <= 2)
-            return sdslgpu_bv_serialize(h, what, buf, cap, nbytes);
+        if (h->kind == SDSLGPU_KIND_BV && what >= 0 && what <= 2 && (h->flags & SDSLGPU_F_SDSL_LAYOUT))
+            return sdslgpu_bv_serialize(h, what, buf, cap, nbytes); // resident words / tables
         DeviceGuard g(h->device);
         sdslgpu_handle * hm = const_cast<sdslgpu_handle *>(h);
         std::lock_guard<std::mutex> lock(hm->ser_mu);
@@ -814,6 +814,8 @@ extern "C"
             blob.swap(hm->ser_blob);
             hm->ser_what = -1;
         }
+        else if (h->kind == SDSLGPU_KIND_BV && what >= 0 && what <= 2)
+            SG_TRY(egress_bv_part(h->bv, what, blob)); // unpacked from the sector blocks, table rebuilt on the device
         else if (h->kind == SDSLGPU_KIND_BV && (what == 3 || what == 4))
             SG_TRY(egress_select_mcl(h->bv, what == 3 ? 1 : 0, blob));
         else if (h->kind == SDSLGPU_KIND_RRR63 && what == 0)

@@ -360,6 +360,7 @@ int sd_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint
 int sd_access_device(sdslgpu_handle const * h, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 int sd_serialize_low_high(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
 // sdsl_egress.cu: complete reference-format blobs (what the reference's serialize() / store_to_file writes)
+int egress_bv_part(BvImage const & v, int what, std::vector<uint8_t> & blob);
 int egress_select_mcl(BvImage const & v, int b, std::vector<uint8_t> & blob);
 int egress_sd(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
 int egress_wt_huff(sdslgpu_handle const * h, std::vector<uint8_t> & blob);

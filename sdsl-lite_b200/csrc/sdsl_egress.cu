@@ -74,27 +74,36 @@ int unpack_words(BvImage const & v, DBuf & words)
     return SDSLGPU_OK;
 }
 
-// bit_vector, then rank_support_v<1> over it (rank_support_v.hpp:151-158)
-int write_bv_and_rank(BvImage const & v, pack::Sink & out)
+} // namespace
+
+// what 0 = bit_vector, 1 = rank_support_v<1>, 2 = rank_support_v<0> of an image that keeps the sector blocks only
+// (handles created with SDSLGPU_F_SDSL_LAYOUT serve these from their resident words / tables, api.cu)
+int egress_bv_part(BvImage const & v, int what, std::vector<uint8_t> & blob)
 {
+    pack::Sink out{blob};
     uint64_t nwords = (v.nbits + 63) >> 6;
     DBuf words;
     SG_TRY(unpack_words(v, words));
-    std::vector<uint64_t> host(nwords + 1, 0);
-    if (nwords)
-        SG_CUDA(cudaMemcpy(host.data(), words.p, nwords * 8, cudaMemcpyDeviceToHost));
-    out.int_vector(1, v.nbits, host.data());
-    // the reference's table from the same words, on the device
+    std::vector<uint64_t> host;
+    if (what == 0)
+    {
+        host.assign(nwords + 1, 0);
+        if (nwords)
+            SG_CUDA(cudaMemcpy(host.data(), words.p, nwords * 8, cudaMemcpyDeviceToHost));
+        out.int_vector(1, v.nbits, host.data());
+        return SDSLGPU_OK;
+    }
+    int const b = what == 1 ? 1 : 0;
     DevicePool scratch;
     BvImage tmp;
     tmp.nbits = v.nbits;
     tmp.nwords = nwords;
     tmp.words = words.as<uint64_t>();
-    int st = bv_build_sdsl_rank_table(scratch, tmp, 1, nullptr);
+    int st = bv_build_sdsl_rank_table(scratch, tmp, b, nullptr);
     if (st == SDSLGPU_OK)
     {
         host.assign(tmp.table_words + 1, 0);
-        cudaError_t e = cudaMemcpy(host.data(), tmp.rank_table[1], tmp.table_words * 8, cudaMemcpyDeviceToHost);
+        cudaError_t e = cudaMemcpy(host.data(), tmp.rank_table[b], tmp.table_words * 8, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess)
             st = cuda_fail(e, "D2H (rank table)", __FILE__, __LINE__);
         else
@@ -103,8 +112,6 @@ int write_bv_and_rank(BvImage const & v, pack::Sink & out)
     scratch.release_all();
     return st;
 }
-
-} // namespace
 
 // select_support_mcl<b,1>::serialize over the image's bit vector
 int egress_select_mcl(BvImage const & v, int b, std::vector<uint8_t> & blob)
@@ -169,7 +176,8 @@ int egress_wt_huff(sdslgpu_handle const * h, std::vector<uint8_t> & blob)
         SG_TRY(rrr_serialize_image(w.rrr, blob)); // rank_support_rrr / select_support_rrr serialise to nothing (rrr_vector.hpp:580-585)
     else
     {
-        SG_TRY(write_bv_and_rank(w.bv, out));
+        SG_TRY(egress_bv_part(w.bv, 0, blob));
+        SG_TRY(egress_bv_part(w.bv, 1, blob)); // rank_support_v<1> (rank_support_v.hpp:151-158)
         SG_TRY(egress_select_mcl(w.bv, 1, blob));
         SG_TRY(egress_select_mcl(w.bv, 0, blob));
     }
@@ -183,7 +191,8 @@ int egress_wt_int(sdslgpu_handle const * h, std::vector<uint8_t> & blob)
     pack::Sink out{blob};
     out.u64(w.size);
     out.u64(w.sigma);
-    SG_TRY(write_bv_and_rank(w.tree, out));
+    SG_TRY(egress_bv_part(w.tree, 0, blob));
+    SG_TRY(egress_bv_part(w.tree, 1, blob));
     SG_TRY(egress_select_mcl(w.tree, 1, blob));
     SG_TRY(egress_select_mcl(w.tree, 0, blob));
     out.u32(w.max_level);

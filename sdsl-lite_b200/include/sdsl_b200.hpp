@@ -22,6 +22,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -72,6 +73,22 @@ inline size_type write_blob(sdslgpu_handle const * h, int what, std::ostream & o
     std::vector<uint8_t> blob = image_blob(h, what);
     out.write(reinterpret_cast<char const *>(blob.data()), (std::streamsize)blob.size());
     return blob.size();
+}
+inline uint64_t read_u64(std::istream & in)
+{
+    uint64_t x = 0;
+    in.read(reinterpret_cast<char *>(&x), 8);
+    if (!in)
+        throw std::runtime_error("load: truncated stream");
+    return x;
+}
+// skips one serialised int_vector<w> (int_vector.hpp:884-916): header (width << 56 | bit_size), ceil(bit_size/64) words
+inline void skip_int_vector(std::istream & in)
+{
+    uint64_t bits = read_u64(in) & ((1ull << 56) - 1);
+    in.ignore((std::streamsize)(((bits + 63) >> 6) * 8));
+    if (!in)
+        throw std::runtime_error("load: truncated stream");
 }
 inline handle_ptr load_blob(std::istream & in, int kind, uint32_t flags, uint32_t param)
 {
@@ -149,6 +166,40 @@ public:
         }
         return m_image.get();
     }
+    //! int_vector<1>::serialize (int_vector.hpp:1995-2004): header (1 << 56 | size), then the words
+    size_type serialize(std::ostream & out) const
+    {
+        uint64_t header = (1ull << 56) | m_size, nw = (m_size + 63) >> 6;
+        out.write(reinterpret_cast<char const *>(&header), 8);
+        out.write(reinterpret_cast<char const *>(m_words.data()), (std::streamsize)(nw * 8));
+        return 8 + nw * 8;
+    }
+    //! int_vector<1>::load (int_vector.hpp:2006-2022): consumes exactly one serialised bit_vector
+    void load(std::istream & in)
+    {
+        uint64_t header = detail::read_u64(in);
+        if ((header >> 56) != 1)
+            throw std::runtime_error("bit_vector::load: not an int_vector<1>");
+        m_size = header & ((1ull << 56) - 1);
+        m_words.assign(((m_size + 63) >> 6) + 1, 0);
+        in.read(reinterpret_cast<char *>(m_words.data()), (std::streamsize)(((m_size + 63) >> 6) * 8));
+        if (!in)
+            throw std::runtime_error("bit_vector::load: truncated stream");
+        m_image.reset();
+    }
+    bool operator==(bit_vector const & o) const
+    {
+        if (m_size != o.m_size)
+            return false;
+        for (size_type w = 0; w < (m_size >> 6); ++w)
+            if (m_words[w] != o.m_words[w])
+                return false;
+        return (m_size & 63) == 0 || ((m_words[m_size >> 6] ^ o.m_words[m_size >> 6]) & ((1ull << (m_size & 63)) - 1)) == 0;
+    }
+    bool operator!=(bit_vector const & o) const
+    {
+        return !(*this == o);
+    }
     //! how large batches are executed: SDSLGPU_ORDER_AUTO (default) / _DIRECT / _BINNED; never changes a result
     void batch_order(int order) const
     {
@@ -187,6 +238,15 @@ public:
     size_type size() const
     {
         return m_v ? m_v->size() : 0;
+    }
+    //! supports are views of their vector's device image: two supports are equal when they answer for the same vector
+    bool operator==(support_base const & o) const noexcept
+    {
+        return m_v == o.m_v;
+    }
+    bool operator!=(support_base const & o) const noexcept
+    {
+        return m_v != o.m_v;
     }
 
 protected:
@@ -243,6 +303,23 @@ public:
         rank(idx.data(), idx.size(), out.data());
         return out;
     }
+    //! serialize: over a plain bit_vector the reference's m_basic_block, byte for byte (rank_support_v.hpp:151-158);
+    //! the supports of rrr_vector / sd_vector serialise to nothing, as in the reference (rrr_vector.hpp:580-585)
+    size_type serialize(std::ostream & out) const
+    {
+        if (!std::is_same<t_vec, bit_vector>::value)
+            return 0;
+        if (t_pat_len != 1)
+            throw std::runtime_error("rank_support::serialize: only the one-bit patterns have a serialised form here");
+        return detail::write_blob(this->image(), t_b ? 1 : 2, out);
+    }
+    //! load(in, v) (rank_support_v.hpp:160-165): the stored table is skipped — the device image of *v answers
+    void load(std::istream & in, t_vec const * v = nullptr)
+    {
+        this->set_vector(v);
+        if (std::is_same<t_vec, bit_vector>::value)
+            detail::skip_int_vector(in);
+    }
 };
 
 template <uint8_t t_b, class t_vec, uint8_t t_pat_len = 1>
@@ -277,6 +354,29 @@ public:
         std::vector<uint64_t> out(i.size());
         select(i.data(), i.size(), out.data());
         return out;
+    }
+    //! serialize: over a plain bit_vector the reference's select_support_mcl bytes (select_support_mcl.hpp:474-518)
+    size_type serialize(std::ostream & out) const
+    {
+        if (!std::is_same<t_vec, bit_vector>::value)
+            return 0;
+        if (t_pat_len != 1)
+            throw std::runtime_error("select_support::serialize: only the one-bit patterns have a serialised form here");
+        return detail::write_blob(this->image(), t_b ? 3 : 4, out);
+    }
+    //! load(in, v) (select_support_mcl.hpp:521-555): the stored samples are skipped — the device image of *v answers
+    void load(std::istream & in, t_vec const * v = nullptr)
+    {
+        this->set_vector(v);
+        if (!std::is_same<t_vec, bit_vector>::value)
+            return;
+        uint64_t arg_cnt = detail::read_u64(in);
+        if (arg_cnt == 0)
+            return;
+        detail::skip_int_vector(in); // m_superblock
+        detail::skip_int_vector(in); // mini_or_long
+        for (uint64_t sb = (arg_cnt + 4095) >> 12; sb > 0; --sb)
+            detail::skip_int_vector(in); // one mini or long block per superblock
     }
 };
 

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <random>
 #include <sstream>
 #include <string>
@@ -81,6 +82,26 @@ void check_pattern(bit_vector const & bv, bool prev, bool cur)
 
 int main(int argc, char ** argv)
 {
+    if (argc > 1 && std::string(argv[1]) == "--host-only")
+    { // the parts of the shim that never touch the device: bit_vector storage and its serialised form
+        bit_vector bv(130);
+        bv.set(0, true);
+        bv.set(64, true);
+        bv.set(129, true);
+        std::stringstream ss;
+        EXPECT(bv.serialize(ss) == 8 + 3 * 8);
+        std::string bytes = ss.str();
+        uint64_t header;
+        std::memcpy(&header, bytes.data(), 8);
+        EXPECT(header == ((1ull << 56) | 130)); // int_vector.hpp:904-916
+        bit_vector back;
+        back.load(ss);
+        EXPECT(back == bv && back.size() == 130 && back[64] && !back[65]);
+        back.set(1, true);
+        EXPECT(back != bv);
+        std::printf("shim_test host-only ok\n");
+        return 0;
+    }
     if (argc > 1)
         set_device(std::atoi(argv[1]));
     std::mt19937_64 rng(4711);
@@ -198,6 +219,45 @@ int main(int argc, char ** argv)
         sd2.load(s3);
         sd_vector<>::rank_1_type r1(&sd), r2(&sd2);
         EXPECT(sd2.size() == 5000 && r1.rank(4321) == r2.rank(4321));
+    }
+    // ---- the support concept's serialize / load (rank_support.hpp:57-74, select_support.hpp:62-77): a vector and its
+    //      supports written to one stream and read back in the same order, like util::init_support users do
+    {
+        bit_vector bv(70001);
+        for (uint64_t j = 0; j < bv.size(); j += 3 + (j % 11))
+            bv.set(j, true);
+        rank_support_v<1> r1(&bv);
+        rank_support_v<0> r0(&bv);
+        select_support_mcl<1> s1(&bv);
+        select_support_mcl<0> s0(&bv);
+        std::stringstream ss;
+        uint64_t total = bv.serialize(ss) + r1.serialize(ss) + r0.serialize(ss) + s1.serialize(ss) + s0.serialize(ss);
+        EXPECT(total == ss.str().size());
+        ss.write("tail", 4);
+        bit_vector bv2;
+        rank_support_v<1> q1;
+        rank_support_v<0> q0;
+        select_support_mcl<1> t1;
+        select_support_mcl<0> t0;
+        bv2.load(ss);
+        q1.load(ss, &bv2);
+        q0.load(ss, &bv2);
+        t1.load(ss, &bv2);
+        t0.load(ss, &bv2);
+        char tail[5] = {0};
+        ss.read(tail, 4);
+        EXPECT(std::string(tail) == "tail"); // every load consumed exactly its own bytes
+        EXPECT(bv2 == bv && q1 != r1 && q1 == rank_support_v<1>(&bv2));
+        for (uint64_t j = 0; j <= bv.size(); j += 997)
+            EXPECT(q1.rank(j) == r1.rank(j) && q0.rank(j) == r0.rank(j));
+        uint64_t ones = r1.rank(bv.size());
+        for (uint64_t k = 1; k <= ones; k += 1013)
+            EXPECT(t1.select(k) == s1.select(k));
+        EXPECT(t0.select(5) == s0.select(5));
+        rrr_vector<63> rrr(bv);
+        rrr_vector<63>::rank_1_type rr(&rrr);
+        std::stringstream none;
+        EXPECT(rr.serialize(none) == 0 && none.str().empty());
     }
     std::printf("shim_test ok\n");
     return 0;

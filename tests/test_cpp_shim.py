@@ -25,6 +25,13 @@ def test_shim_compiles_and_links(pkg):
     assert os.path.exists(BIN)
 
 
+def test_shim_host_only_parts(pkg):
+    """bit_vector storage and its serialised form need no device"""
+    _build(pkg)
+    r = subprocess.run([BIN, "--host-only"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "host-only ok" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
 @pytest.mark.gpu
 def test_shim_matches_naive_on_gpu(pkg):
     _build(pkg)

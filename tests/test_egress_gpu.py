@@ -28,7 +28,10 @@ def test_select_supports_and_sd_vector(pkg, oracle, orc):
     for cid, w, nbits in cases.bitvector_catalogue(large=True):
         w = _clean(w, nbits)
         chk = mk.bv(w, nbits)
-        with pkg.BitVector(w, nbits) as v:
+        with pkg.BitVector(w, nbits) as v:  # default layout: sector blocks only, nothing of the reference's form resident
+            assert v.serialize(0) == chk.serialize(0), (cid, "bit_vector")
+            assert v.serialize(1) == chk.serialize(1), (cid, "rank_support_v<1>")
+            assert v.serialize(2) == chk.serialize(2), (cid, "rank_support_v<0>")
             assert v.serialize(3) == chk.serialize(3), (cid, "select_support_mcl<1>")
             assert v.serialize(4) == chk.serialize(4), (cid, "select_support_mcl<0>")
         if nbits and nbits <= 2_000_000:
