@@ -56,6 +56,10 @@ extern "C" {
 #define SDSLGPU_F_RRR_BV 4u      /* wavelet trees / CSA: store the tree's bit vector as rrr_vector<63>, i.e.
                                     wt_huff<rrr_vector<63>> and csa_wt<wt_huff<rrr_vector<63>>> (H0-compressed) */
 
+#define SDSLGPU_F_V5_SCAN 16u    /* sdslgpu_load_sdsl of a wavelet tree / CSA: the blob is the reference's
+                                    wt_huff<bit_vector, rank_support_v5<>, select_support_scan<>, select_support_scan<0>>
+                                    form (its own count benchmark's FM_HUFF index, benchmark/indexing_count/
+                                    index.config:8): a rank_support_v5 table and no select data follow m_bv */
 #define SDSLGPU_F_COMPACT 8u     /* CSA: keep the wavelet tree of the BWT as the only occurrence structure
                                     (1.14 bytes/symbol; a backward-search step is one sector gather per Huffman
                                     level).  By default a CSA additionally holds 32 one-hot sector-block bitmaps
@@ -243,7 +247,9 @@ int sdslgpu_load_sdsl(const void *blob, uint64_t nbytes, int kind, int device, u
 /* Egress: the bytes the reference's serialize() / store_to_file (io.hpp:877-896) writes for the same input, so that
  * an index built here can be stored and loaded by the reference (and by sdslgpu_load_sdsl).  Same buffer protocol as
  * sdslgpu_bv_serialize.
- *   KIND_BV      what 0..2 as sdslgpu_bv_serialize; what 3 / 4 = select_support_mcl<1> / <0>::serialize
+ *   KIND_BV      what 0 / 1 / 2 = bit_vector / rank_support_v<1> / <0> (any handle; with SDSLGPU_F_SDSL_LAYOUT from the
+ *                resident copies); what 5 / 6 = rank_support_v5<1> / <0> (rank_support_v5.hpp:66-158);
+ *                what 3 / 4 = select_support_mcl<1> / <0>::serialize
  *                (select_support_mcl.hpp:474-518) with the contents of init_slow / init_fast (:207-381): the argument
  *                positions they store come from the batched select kernel, the host only packs them
  *   KIND_RRR63   what 0 = the complete rrr_vector<63>::serialize bytes (rrr_vector.hpp:366-378)
@@ -252,6 +258,9 @@ int sdslgpu_load_sdsl(const void *blob, uint64_t nbytes, int kind, int device, u
  *   KIND_WT_HUFF what 0 = wt_pc::serialize (wt_pc.hpp:713-726): size, sigma, m_bv, rank_support_v<1>,
  *                select_support_mcl<1>, <0>, byte_tree (wt_helper.hpp:362-375); with SDSLGPU_F_RRR_BV the
  *                wt_huff<rrr_vector<63>> form (the rrr supports serialise to nothing, rrr_vector.hpp:580-585)
+ *                what 1 (KIND_WT_HUFF and KIND_CSA_WT) = the same tree as wt_huff<bit_vector, rank_support_v5<>,
+ *                select_support_scan<>, select_support_scan<0>>: with a CSA created at sa_dens = isa_dens = 2^20 this
+ *                is the reference's count-benchmark index FM_HUFF (benchmark/indexing_count/index.config:8)
  *   KIND_WT_INT  what 0 = wt_int::serialize (wt_int.hpp:792-805)
  *   KIND_CSA_WT  what 0 = csa_wt::serialize (csa_wt.hpp:389-402): wavelet tree, SA samples, ISA samples (both
  *                int_vector<0> of width hi(size)+1, csa_sampling_strategy.hpp:103,762), byte_alphabet

@@ -269,6 +269,71 @@ uint64_t orc_rank_v_serialize(const uint64_t *B, uint64_t nbits, uint8_t *out, u
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* f-3: rank_support_v5<b,1> — the 6.25 %-overhead table the reference's own count benchmark    */
+/* uses (benchmark/indexing_count/index.config:8): 2048-bit superblocks, per superblock the       */
+/* absolute count and five 12-bit prefix counts, one per 6 words                                  */
+/* ------------------------------------------------------------------------------------------ */
+uint64_t orc_rank_v5_table_words(uint64_t nbits) /* rank_support_v5.hpp:73-79 */
+{
+    if (nbits == 0)
+        return 2;
+    return (((nbits + 63) >> 11) + 1) << 1;
+}
+
+/* rank_support_v5.hpp:66-122 */
+void orc_rank_v5_build(const uint64_t *w, uint64_t nbits, int b, uint64_t *B)
+{
+    uint64_t W = (nbits + 63) >> 6, i, j = 0, sum, second = 0, cw = 1;
+    B[0] = B[1] = 0;
+    if (nbits == 0)
+        return;
+    sum = args(w, 0, b);
+    for (i = 1; i < W; ++i, ++cw) {
+        if (cw == 32) {
+            j += 2;
+            B[j - 1] = second;
+            B[j] = B[j - 2] + sum;
+            second = sum = cw = 0;
+        } else if (cw % 6 == 0) {
+            second |= sum << (60 - 12 * (cw / 6));
+        }
+        sum += args(w, i, b);
+    }
+    if (cw % 6 == 0)
+        second |= sum << (60 - 12 * (cw / 6));
+    if (cw == 32) {
+        j += 2;
+        B[j - 1] = second;
+        B[j] = B[j - 2] + sum;
+        B[j + 1] = 0;
+    } else {
+        B[j + 1] = second;
+    }
+}
+
+/* rank_support_v5.hpp:131-149 */
+uint64_t orc_rank_v5(const uint64_t *w, const uint64_t *B, int b, uint64_t idx)
+{
+    const uint64_t *p = B + ((idx >> 10) & ~1ull);
+    uint64_t r = p[0] + ((p[1] >> (60 - 12 * ((idx & 0x7FF) / 384))) & 0x7FF);
+    uint64_t word = idx >> 6, todo = (word & 31) % 6, k;
+    if (idx & 63)
+        r += orc_cnt(pat_map(w, word, b) & orc__lo_set((uint32_t)(idx & 63)));
+    for (k = 1; k <= todo; ++k)
+        r += args(w, word - k, b);
+    return r;
+}
+
+uint64_t orc_rank_v5_serialize(const uint64_t *B, uint64_t nbits, uint8_t *out, uint64_t cap) /* :151-158 */
+{
+    orc_buf b = {0, 0, 0};
+    uint64_t words = orc_rank_v5_table_words(nbits);
+    orc__buf_u64(&b, ((uint64_t)64 << 56) | (words * 64));
+    orc__buf_put(&b, B, words * 8);
+    return orc__buf_finish(&b, out, cap);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* a4: select_support_mcl<b,1>                                                                */
 /* ------------------------------------------------------------------------------------------ */
 

@@ -86,6 +86,14 @@ class Oracle:
         L.orc_rank_v_batch.argtypes = [u64p, u64p, C.c_int, u64p, C.c_uint64, u64p]
         L.orc_rank_v_serialize.restype = C.c_uint64
         L.orc_rank_v_serialize.argtypes = [u64p, C.c_uint64, u8p, C.c_uint64]
+        L.orc_rank_v5_table_words.restype = C.c_uint64
+        L.orc_rank_v5_table_words.argtypes = [C.c_uint64]
+        L.orc_rank_v5_build.restype = None
+        L.orc_rank_v5_build.argtypes = [u64p, C.c_uint64, C.c_int, u64p]
+        L.orc_rank_v5.restype = C.c_uint64
+        L.orc_rank_v5.argtypes = [u64p, u64p, C.c_int, C.c_uint64]
+        L.orc_rank_v5_serialize.restype = C.c_uint64
+        L.orc_rank_v5_serialize.argtypes = [u64p, C.c_uint64, u8p, C.c_uint64]
         L.orc_select_mcl_build.restype = C.c_void_p
         L.orc_select_mcl_build.argtypes = [u64p, C.c_uint64, C.c_int]
         L.orc_select_mcl_free.restype = None
@@ -199,10 +207,23 @@ class OracleBV:
         self.L.orc_select_mcl_batch(self._sel(b), _p64(self.w), _p64(i), len(i), _p64(out))
         return out
 
+    def rank_v5_table(self, b):
+        t = np.zeros(int(self.L.orc_rank_v5_table_words(self.nbits)), dtype=np.uint64)
+        self.L.orc_rank_v5_build(_p64(self.w), self.nbits, b, _p64(t))
+        return t
+
+    def rank_v5(self, idx, b=1):
+        """rank_support_v5<b>::rank, one query at a time (small inputs only)"""
+        t = self.rank_v5_table(b)
+        return np.array([self.L.orc_rank_v5(_p64(self.w), _p64(t), b, int(i)) for i in idx], dtype=np.uint64)
+
     def serialize(self, what):
-        """what: 0 bit_vector, 1 rank_support_v<1>, 2 rank_support_v<0>, 3 select_support_mcl<1>, 4 <0>"""
+        """what: 0 bit_vector, 1 rank_support_v<1>, 2 rank_support_v<0>, 3 select_support_mcl<1>, 4 <0>,
+        5 rank_support_v5<1>, 6 rank_support_v5<0>"""
         if what == 0:
             return _blob(self.L.orc_bv_serialize, _p64(self.w), self.nbits)
+        if what in (5, 6):
+            return _blob(self.L.orc_rank_v5_serialize, _p64(self.rank_v5_table(1 if what == 5 else 0)), self.nbits)
         if what in (1, 2):
             return _blob(self.L.orc_rank_v_serialize, _p64(self.rank_table(1 if what == 1 else 0)), self.nbits)
         return _blob(self.L.orc_select_mcl_serialize, self._sel(1 if what == 3 else 0))
@@ -474,6 +495,44 @@ class Ref:
             L.ref_csa_rrr_serialize.argtypes = [vp, u8p, C.c_uint64]
             L.ref_csa_rrr_count.restype = None
             L.ref_csa_rrr_count.argtypes = [vp, u8p, u64p, C.c_uint64, u64p, C.c_int]
+
+        if hasattr(L, "ref_fm_huff_create"):
+            for name in ("ref_wt_huff_v5_create", "ref_fm_huff_create", "ref_fm_huff_load"):
+                getattr(L, name).restype = vp
+                getattr(L, name).argtypes = [u8p, C.c_uint64]
+            L.ref_wt_huff_v5_free.argtypes = [vp]
+            L.ref_fm_huff_free.argtypes = [vp]
+            for name in ("ref_wt_huff_v5_serialize", "ref_fm_huff_serialize"):
+                getattr(L, name).restype = C.c_uint64
+                getattr(L, name).argtypes = [vp, u8p, C.c_uint64]
+            L.ref_fm_huff_count.restype = None
+            L.ref_fm_huff_count.argtypes = [vp, u8p, u64p, C.c_uint64, u64p, C.c_int]
+
+    def wt_huff_v5_blob(self, text):
+        """serialised wt_huff<bit_vector, rank_support_v5<>, select_support_scan<>, select_support_scan<0>> of `text`"""
+        t = _text(text)
+        h = self.L.ref_wt_huff_v5_create(_p8(t if len(t) else np.zeros(1, np.uint8)), len(t))
+        blob = _blob(self.L.ref_wt_huff_v5_serialize, h)
+        self.L.ref_wt_huff_v5_free(h)
+        return blob
+
+    def fm_huff(self, text=None, blob=None):
+        """the reference's count-benchmark index FM_HUFF (benchmark/indexing_count/index.config:8), built from `text`
+        or loaded from `blob` -> (serialised bytes, count_fn)"""
+        if blob is not None:
+            b = np.frombuffer(blob, dtype=np.uint8)
+            h = self.L.ref_fm_huff_load(_p8(b), len(b))
+        else:
+            t = _text(text)
+            h = self.L.ref_fm_huff_create(_p8(t), len(t))
+        out_blob = _blob(self.L.ref_fm_huff_serialize, h)
+
+        def count(flat, off):
+            out = np.zeros(len(off) - 1, dtype=np.uint64)
+            self.L.ref_fm_huff_count(h, _p8(flat), _p64(off), len(off) - 1, _p64(out), 1)
+            return out
+
+        return out_blob, count
 
     def bv(self, words, nbits, with_select=True):
         return RefBV(self, words, nbits, with_select)

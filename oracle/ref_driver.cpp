@@ -207,12 +207,17 @@ extern "C"
                     out[k] = h->s0.select(idx[k]);
             });
     }
-    // what: 0 = bit_vector, 1 = rank_support_v<1>, 2 = rank_support_v<0>, 3 = select_support_mcl<1>, 4 = <0>
+    // what: 0 = bit_vector, 1 = rank_support_v<1>, 2 = rank_support_v<0>, 3 = select_support_mcl<1>, 4 = <0>,
+    //       5 = rank_support_v5<1>, 6 = rank_support_v5<0>
     uint64_t ref_bv_serialize(void * p, int what, uint8_t * buf, uint64_t cap)
     {
         auto * h = static_cast<ref_bv *>(p);
         switch (what)
         {
+        case 5:
+            return serialize_to(rank_support_v5<1>(&h->bv), buf, cap);
+        case 6:
+            return serialize_to(rank_support_v5<0>(&h->bv), buf, cap);
         case 0:
             return serialize_to(h->bv, buf, cap);
         case 1:
@@ -632,6 +637,68 @@ extern "C"
         parallel_for(n, threads, [=](uint64_t lo, uint64_t hi) {
             for (uint64_t k = lo; k < hi; ++k)
                 cnt_out[k] = count(h->csa, pats + off[k], pats + off[k + 1]);
+        });
+    }
+
+    // ---------------------------------------------------------------- the reference's own count-benchmark index
+    // FM_HUFF of benchmark/indexing_count/index.config:8 — rank_support_v5 + select_support_scan inside the tree,
+    // one SA / ISA sample per 2^20 entries
+    typedef wt_huff<bit_vector, rank_support_v5<>, select_support_scan<>, select_support_scan<0>> wt_huff_v5;
+    typedef csa_wt<wt_huff_v5, 1 << 20, 1 << 20> fm_huff;
+    void * ref_wt_huff_v5_create(uint8_t const * text, uint64_t n)
+    {
+        auto * h = new wt_huff_v5;
+        int_vector<8> t(n);
+        if (n)
+            std::memcpy(t.data(), text, n);
+        construct_im(*h, t, 0);
+        return h;
+    }
+    void ref_wt_huff_v5_free(void * p)
+    {
+        delete static_cast<wt_huff_v5 *>(p);
+    }
+    uint64_t ref_wt_huff_v5_serialize(void * p, uint8_t * buf, uint64_t cap)
+    {
+        return serialize_to(*static_cast<wt_huff_v5 *>(p), buf, cap);
+    }
+    void * ref_fm_huff_create(uint8_t const * text, uint64_t n)
+    {
+        auto * h = new fm_huff;
+        std::string s(reinterpret_cast<char const *>(text), n);
+        try
+        {
+            construct_im(*h, s, 1);
+        }
+        catch (...)
+        {
+            delete h;
+            return nullptr;
+        }
+        return h;
+    }
+    void * ref_fm_huff_load(uint8_t const * blob, uint64_t nbytes)
+    {
+        auto * h = new fm_huff;
+        std::istringstream is(std::string(reinterpret_cast<char const *>(blob), nbytes), std::ios::binary);
+        std::istream & in = is;
+        h->load(in);
+        return h;
+    }
+    void ref_fm_huff_free(void * p)
+    {
+        delete static_cast<fm_huff *>(p);
+    }
+    uint64_t ref_fm_huff_serialize(void * p, uint8_t * buf, uint64_t cap)
+    {
+        return serialize_to(*static_cast<fm_huff *>(p), buf, cap);
+    }
+    void ref_fm_huff_count(void * p, uint8_t const * pats, uint64_t const * off, uint64_t n, uint64_t * cnt_out, int threads)
+    {
+        auto * h = static_cast<fm_huff *>(p);
+        parallel_for(n, threads, [=](uint64_t lo, uint64_t hi) {
+            for (uint64_t k = lo; k < hi; ++k)
+                cnt_out[k] = count(*h, pats + off[k], pats + off[k + 1]);
         });
     }
 

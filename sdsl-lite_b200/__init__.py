@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(HERE, "libsdslgpu.so")
 
 OK, EINVAL, ENOMEM, ECUDA, ENOTSUP = 0, -1, -2, -3, -4
 NPOS = np.uint64(0xFFFFFFFFFFFFFFFF)
-F_DEFAULT, F_SDSL_LAYOUT, F_NO_SELECT, F_RRR_BV, F_COMPACT = 0, 1, 2, 4, 8
+F_DEFAULT, F_SDSL_LAYOUT, F_NO_SELECT, F_RRR_BV, F_COMPACT, F_V5_SCAN = 0, 1, 2, 4, 8, 16
 KIND_BV, KIND_RRR63, KIND_SD, KIND_WT_HUFF, KIND_WT_INT, KIND_CSA_WT = 1, 2, 3, 4, 5, 6
 PAT_0, PAT_1, PAT_10, PAT_01, PAT_00, PAT_11 = 0, 1, 2, 3, 4, 5  # <t_b, t_pat_len> of rank_support_v / select_support_mcl
 ORDER_AUTO, ORDER_DIRECT, ORDER_BINNED = 0, 1, 2  # sdslgpu_set_batch_order

@@ -814,7 +814,7 @@ extern "C"
             blob.swap(hm->ser_blob);
             hm->ser_what = -1;
         }
-        else if (h->kind == SDSLGPU_KIND_BV && what >= 0 && what <= 2)
+        else if (h->kind == SDSLGPU_KIND_BV && ((what >= 0 && what <= 2) || what == 5 || what == 6))
             SG_TRY(egress_bv_part(h->bv, what, blob)); // unpacked from the sector blocks, table rebuilt on the device
         else if (h->kind == SDSLGPU_KIND_BV && (what == 3 || what == 4))
             SG_TRY(egress_select_mcl(h->bv, what == 3 ? 1 : 0, blob));
@@ -824,12 +824,12 @@ extern "C"
             SG_TRY(sd_serialize_low_high(h, blob));
         else if (h->kind == SDSLGPU_KIND_SD && what == 1)
             SG_TRY(egress_sd(h, blob));
-        else if (h->kind == SDSLGPU_KIND_WT_HUFF && what == 0)
-            SG_TRY(egress_wt_huff(h, blob));
+        else if (h->kind == SDSLGPU_KIND_WT_HUFF && (what == 0 || what == 1))
+            SG_TRY(egress_wt_huff(h, blob, what == 1));
         else if (h->kind == SDSLGPU_KIND_WT_INT && what == 0)
             SG_TRY(egress_wt_int(h, blob));
-        else if (h->kind == SDSLGPU_KIND_CSA_WT && what == 0)
-            SG_TRY(egress_csa(h, blob));
+        else if (h->kind == SDSLGPU_KIND_CSA_WT && (what == 0 || what == 1))
+            SG_TRY(egress_csa(h, blob, what == 1));
         else
         {
             set_error("sdslgpu_serialize: unsupported (kind %d, what %d)", h->kind, what);

@@ -242,6 +242,32 @@ __global__ void __launch_bounds__(kThreads)
     sb_total[k] = (uint32_t)sum;
 }
 
+// rank_support_v5's table (rank_support_v5.hpp:66-122): 2048-bit superblocks; the second word of a pair packs the
+// prefix counts after 6, 12, 18, 24 and 30 words of the superblock into 12-bit fields at bits 48, 36, 24, 12, 0
+// (the prefix just past the last word is recorded too when it falls on a multiple of 6 words).
+template <int B>
+__global__ void __launch_bounds__(kThreads)
+    sdsl_table5_rel_kernel(uint64_t const * __restrict__ words, uint64_t nwords, uint64_t nsuper, uint64_t * __restrict__ table, uint32_t * __restrict__ sb_total)
+{
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nsuper)
+        return;
+    uint64_t second = 0, sum = 0;
+    for (int j = 0; j < 32; ++j)
+    {
+        uint64_t wi = k * 32 + j;
+        if (j > 0 && j % 6 == 0 && wi <= nwords)
+            second |= sum << (60 - 12 * (j / 6));
+        if (wi < nwords)
+        {
+            uint64_t x = words[wi];
+            sum += __popcll(B ? x : ~x);
+        }
+    }
+    table[2 * k + 1] = second;
+    sb_total[k] = (uint32_t)sum;
+}
+
 __global__ void __launch_bounds__(kThreads) sdsl_table_abs_kernel(uint64_t const * __restrict__ abs, uint64_t nsuper, uint64_t * __restrict__ table)
 {
     uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -415,10 +441,10 @@ int bv_build_pattern(DevicePool & pool, BvImage const & src, int pat, BvImage & 
     return st;
 }
 
-int bv_build_sdsl_rank_table(DevicePool & pool, BvImage & v, int b, cudaStream_t s)
+int bv_build_sdsl_rank_table(DevicePool & pool, BvImage & v, int b, cudaStream_t s, bool v5)
 {
-    // rank_support_v.hpp:79,84: 2 words for an empty vector, else 2 * (((n+63)>>9) + 1)
-    uint64_t nsuper = (v.nbits == 0) ? 1 : ((v.nbits + 63) >> 9) + 1;
+    // rank_support_v.hpp:79,84: 2 words for an empty vector, else 2 * (((n+63)>>9) + 1); v5: >> 11 (rank_support_v5.hpp:73-79)
+    uint64_t nsuper = (v.nbits == 0) ? 1 : ((v.nbits + 63) >> (v5 ? 11 : 9)) + 1;
     v.table_words = 2 * nsuper;
     SG_TRY(pool.alloc_t(&v.rank_table[b], v.table_words + 2));
     uint32_t * sb_total = nullptr;
@@ -427,7 +453,11 @@ int bv_build_sdsl_rank_table(DevicePool & pool, BvImage & v, int b, cudaStream_t
     SG_TRY(pool.alloc_t(&sb_total, nsuper));
     SG_TRY(pool.alloc_t(&abs, nsuper + 1));
     SG_TRY(pool.alloc_t(&tmp, scan_tmp_words(nsuper)));
-    if (b)
+    if (v5 && b)
+        sdsl_table5_rel_kernel<1><<<blocks_for(nsuper), kThreads, 0, s>>>(v.words, v.nwords, nsuper, v.rank_table[b], sb_total);
+    else if (v5)
+        sdsl_table5_rel_kernel<0><<<blocks_for(nsuper), kThreads, 0, s>>>(v.words, v.nwords, nsuper, v.rank_table[b], sb_total);
+    else if (b)
         sdsl_table_rel_kernel<1><<<blocks_for(nsuper), kThreads, 0, s>>>(v.words, v.nwords, nsuper, v.rank_table[b], sb_total);
     else
         sdsl_table_rel_kernel<0><<<blocks_for(nsuper), kThreads, 0, s>>>(v.words, v.nwords, nsuper, v.rank_table[b], sb_total);

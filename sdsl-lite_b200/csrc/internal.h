@@ -313,7 +313,7 @@ inline RrrBits rrr_bits(WtHuffImage const & w)
 
 // bv.cu
 int bv_build(DevicePool & pool, BvImage & v, uint32_t flags, uint64_t const * words_host_or_dev, bool words_on_device, uint64_t nbits, cudaStream_t s);
-int bv_build_sdsl_rank_table(DevicePool & pool, BvImage & v, int b, cudaStream_t s);
+int bv_build_sdsl_rank_table(DevicePool & pool, BvImage & v, int b, cudaStream_t s, bool v5 = false);
 int bv_build_pattern(DevicePool & pool, BvImage const & src, int pat, BvImage & dst, cudaStream_t s);
 int bv_rank_device(BvImage const & v, uint32_t flags, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 int bv_select_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
@@ -363,9 +363,9 @@ int sd_serialize_low_high(sdslgpu_handle const * h, std::vector<uint8_t> & blob)
 int egress_bv_part(BvImage const & v, int what, std::vector<uint8_t> & blob);
 int egress_select_mcl(BvImage const & v, int b, std::vector<uint8_t> & blob);
 int egress_sd(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
-int egress_wt_huff(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
+int egress_wt_huff(sdslgpu_handle const * h, std::vector<uint8_t> & blob, bool v5_scan = false);
 int egress_wt_int(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
-int egress_csa(sdslgpu_handle const * h, std::vector<uint8_t> & blob);
+int egress_csa(sdslgpu_handle const * h, std::vector<uint8_t> & blob, bool v5_scan = false);
 // gpu_sa.cu
 int gpu_suffix_array_bwt(uint8_t const * text_host, uint64_t len, uint32_t dens, uint32_t isa_dens, std::vector<uint8_t> & bwt, std::vector<uint64_t> & samples,
                          std::vector<uint64_t> & isa_samples, uint32_t * rounds_out, cudaStream_t s);

@@ -76,8 +76,9 @@ int unpack_words(BvImage const & v, DBuf & words)
 
 } // namespace
 
-// what 0 = bit_vector, 1 = rank_support_v<1>, 2 = rank_support_v<0> of an image that keeps the sector blocks only
-// (handles created with SDSLGPU_F_SDSL_LAYOUT serve these from their resident words / tables, api.cu)
+// what 0 = bit_vector, 1 = rank_support_v<1>, 2 = rank_support_v<0>, 5 = rank_support_v5<1>, 6 = rank_support_v5<0>
+// of an image that keeps the sector blocks only (handles created with SDSLGPU_F_SDSL_LAYOUT serve 0..2 from their
+// resident words / tables, api.cu)
 int egress_bv_part(BvImage const & v, int what, std::vector<uint8_t> & blob)
 {
     pack::Sink out{blob};
@@ -93,13 +94,13 @@ int egress_bv_part(BvImage const & v, int what, std::vector<uint8_t> & blob)
         out.int_vector(1, v.nbits, host.data());
         return SDSLGPU_OK;
     }
-    int const b = what == 1 ? 1 : 0;
+    int const b = (what == 1 || what == 5) ? 1 : 0;
     DevicePool scratch;
     BvImage tmp;
     tmp.nbits = v.nbits;
     tmp.nwords = nwords;
     tmp.words = words.as<uint64_t>();
-    int st = bv_build_sdsl_rank_table(scratch, tmp, b, nullptr);
+    int st = bv_build_sdsl_rank_table(scratch, tmp, b, nullptr, what >= 5);
     if (st == SDSLGPU_OK)
     {
         host.assign(tmp.table_words + 1, 0);
@@ -166,7 +167,10 @@ int egress_sd(sdslgpu_handle const * h, std::vector<uint8_t> & blob)
     return egress_select_mcl(d.high, 0, blob);
 }
 
-int egress_wt_huff(sdslgpu_handle const * h, std::vector<uint8_t> & blob)
+// v5_scan: the wt_huff<bit_vector, rank_support_v5<>, select_support_scan<>, select_support_scan<0>> form of the
+// reference's count-benchmark index (benchmark/indexing_count/index.config:8): the rank slot holds rank_support_v5's
+// table and the two scanning select supports serialise to nothing (select_support_scan.hpp:63-66)
+int egress_wt_huff(sdslgpu_handle const * h, std::vector<uint8_t> & blob, bool v5_scan)
 {
     WtHuffImage const & w = h->wt;
     pack::Sink out{blob};
@@ -177,9 +181,12 @@ int egress_wt_huff(sdslgpu_handle const * h, std::vector<uint8_t> & blob)
     else
     {
         SG_TRY(egress_bv_part(w.bv, 0, blob));
-        SG_TRY(egress_bv_part(w.bv, 1, blob)); // rank_support_v<1> (rank_support_v.hpp:151-158)
-        SG_TRY(egress_select_mcl(w.bv, 1, blob));
-        SG_TRY(egress_select_mcl(w.bv, 0, blob));
+        SG_TRY(egress_bv_part(w.bv, v5_scan ? 5 : 1, blob)); // rank_support_v<1> (rank_support_v.hpp:151-158) / rank_support_v5<1>
+        if (!v5_scan)
+        {
+            SG_TRY(egress_select_mcl(w.bv, 1, blob));
+            SG_TRY(egress_select_mcl(w.bv, 0, blob));
+        }
     }
     pack::write_byte_tree(w.host_tree, out);
     return SDSLGPU_OK;
@@ -199,10 +206,10 @@ int egress_wt_int(sdslgpu_handle const * h, std::vector<uint8_t> & blob)
     return SDSLGPU_OK;
 }
 
-int egress_csa(sdslgpu_handle const * h, std::vector<uint8_t> & blob)
+int egress_csa(sdslgpu_handle const * h, std::vector<uint8_t> & blob, bool v5_scan)
 {
     CsaImage const & c = h->csa;
-    SG_TRY(egress_wt_huff(h, blob));
+    SG_TRY(egress_wt_huff(h, blob, v5_scan));
     pack::Sink out{blob};
     uint32_t const width = pack::hi(c.n) + 1; // csa_sampling_strategy.hpp:103, 762
     std::vector<uint64_t> host;

@@ -223,8 +223,10 @@ int load_wt_huff(sdslgpu_handle * h, Reader & r, cudaStream_t s)
         h->wt.use_rrr = true;
         SG_TRY(load_rrr_image(h->pool, h->wt.rrr, r, s));
     }
-    else if (!read_iv(r, bv) || bv.width != 1 || !skip_iv(r) || !skip_select_mcl(r) || !skip_select_mcl(r))
+    else if (!read_iv(r, bv) || bv.width != 1 || !skip_iv(r))
         return malformed("wt_huff");
+    else if (!(h->flags & SDSLGPU_F_V5_SCAN) && (!skip_select_mcl(r) || !skip_select_mcl(r)))
+        return malformed("wt_huff (select supports)"); // with rank_support_v5 + select_support_scan nothing follows the table
     uint64_t nn = r.u64();
     if (!r.ok || nn > 511 || !r.need(nn * 22 + 512 + 2048))
         return malformed("wt_huff (byte_tree)");

@@ -385,9 +385,20 @@ using rank_support_v = rank_support<t_b, bit_vector, t_pat_len>;
 template <uint8_t t_b = 1, uint8_t t_pat_len = 1>
 using select_support_mcl = select_support<t_b, bit_vector, t_pat_len>;
 //! rank_support_v5 (rank_support_v5.hpp:131-149) answers exactly what rank_support_v answers; on the device both
-//! map onto the same sector blocks, so the alias keeps call sites that name the 6.25 %-overhead variant compiling.
+//! map onto the same sector blocks.  Only the serialised form differs: the 6.25 %-overhead table of 2048-bit
+//! superblocks (rank_support_v5.hpp:66-122), rebuilt on the device, byte for byte.
 template <uint8_t t_b = 1, uint8_t t_pat_len = 1>
-using rank_support_v5 = rank_support<t_b, bit_vector, t_pat_len>;
+class rank_support_v5 : public rank_support<t_b, bit_vector, t_pat_len>
+{
+public:
+    using rank_support<t_b, bit_vector, t_pat_len>::rank_support;
+    size_type serialize(std::ostream & out) const
+    {
+        if (t_pat_len != 1)
+            throw std::runtime_error("rank_support_v5::serialize: only the one-bit patterns have a serialised form here");
+        return detail::write_blob(this->image(), t_b ? 5 : 6, out);
+    }
+};
 
 // ------------------------------------------------------------------------------------------------------
 // compressed bit vectors (rrr_vector.hpp:67-109, sd_vector.hpp:131-163)

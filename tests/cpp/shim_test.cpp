@@ -80,6 +80,13 @@ void check_pattern(bit_vector const & bv, bool prev, bool cur)
     EXPECT(ss.select(k) == pos);
 }
 
+static std::ostream & none_sink()
+{
+    static std::stringstream s;
+    s.str("");
+    return s;
+}
+
 int main(int argc, char ** argv)
 {
     if (argc > 1 && std::string(argv[1]) == "--host-only")
@@ -254,6 +261,12 @@ int main(int argc, char ** argv)
         for (uint64_t k = 1; k <= ones; k += 1013)
             EXPECT(t1.select(k) == s1.select(k));
         EXPECT(t0.select(5) == s0.select(5));
+        rank_support_v5<1> r5(&bv), q5;
+        std::stringstream s5;
+        uint64_t n5 = r5.serialize(s5);
+        EXPECT(n5 == 8 + 8 * 2 * (((bv.size() + 63) >> 11) + 1) && n5 < r1.serialize(none_sink())); // rank_support_v5.hpp:73-79: a quarter of the table
+        q5.load(s5, &bv2);
+        EXPECT(q5.rank(31337) == r1.rank(31337) && r5(70001) == ones);
         rrr_vector<63> rrr(bv);
         rrr_vector<63>::rank_1_type rr(&rrr);
         std::stringstream none;

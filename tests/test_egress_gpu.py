@@ -34,6 +34,8 @@ def test_select_supports_and_sd_vector(pkg, oracle, orc):
             assert v.serialize(2) == chk.serialize(2), (cid, "rank_support_v<0>")
             assert v.serialize(3) == chk.serialize(3), (cid, "select_support_mcl<1>")
             assert v.serialize(4) == chk.serialize(4), (cid, "select_support_mcl<0>")
+            assert v.serialize(5) == chk.serialize(5), (cid, "rank_support_v5<1>")
+            assert v.serialize(6) == chk.serialize(6), (cid, "rank_support_v5<0>")
         if nbits and nbits <= 2_000_000:
             with pkg.SdVector(w, nbits) as v:
                 assert v.serialize(1) == mk.sd(w, nbits).serialize(), (cid, "sd_vector")
@@ -132,3 +134,35 @@ def test_device_and_host_builders_agree(pkg, oracle, orc, monkeypatch):
         with pkg.WtInt(seq) as b:
             assert x == b.serialize() and sa == b.sigma, name
     monkeypatch.delenv("SDSLGPU_HOST_WT", raising=False)
+
+
+def test_reference_count_benchmark_index_both_ways(pkg, orc):
+    """FM_HUFF of the reference's own count benchmark (benchmark/indexing_count/index.config:8):
+    csa_wt<wt_huff<bit_vector, rank_support_v5<>, select_support_scan<>, select_support_scan<0>>, 1<<20, 1<<20>.
+    Built here -> the reference's bytes, loadable and countable by the reference; built by the reference -> ingested
+    here (SDSLGPU_F_V5_SCAN) with the same counts"""
+    if not orc.ref_available():
+        pytest.skip("needs oracle/_ref/libsdslref.so (the unmodified reference)")
+    R = orc.Ref()
+    rng = np.random.default_rng(31)
+    dens = 1 << 20
+    for name, t in texts.text_catalogue(zero_free=True, large=True):
+        ref_blob, ref_count = R.fm_huff(text=t)
+        pats = [t[s : s + int(rng.integers(1, 10))] for s in rng.integers(0, max(1, len(t) - 10), 300)] + [b"", b"\x01\x02zz"]
+        flat, off = pkg.csr_patterns(pats)
+        want = ref_count(flat, off)
+        with pkg.CsaWt(t, sa_dens=dens, isa_dens=dens) as csa:
+            blob = csa.serialize(1)
+            assert blob == ref_blob, name
+            assert (csa.count(flat, off) == want).all(), name
+        _, loaded_count = R.fm_huff(blob=blob)
+        assert (loaded_count(flat, off) == want).all(), (name, "reference on our blob")
+        with pkg.load_sdsl(ref_blob, pkg.KIND_CSA_WT, flags=pkg.F_V5_SCAN, param=dens) as back:
+            assert (back.count(flat, off) == want).all(), (name, "ingest")
+            if len(t) < 10_000:  # one SA sample per 2^20 entries: every occurrence walks back to SA[0]
+                a = back.locate(flat[: int(off[10])], off[:11])
+                with pkg.CsaWt(t) as plain:
+                    b = plain.locate(flat[: int(off[10])], off[:11])
+                assert (a[0] == b[0]).all() and (a[1] == b[1]).all(), (name, "locate after ingest")
+        with pkg.WtHuff(t) as wt:
+            assert wt.serialize(1) == R.wt_huff_v5_blob(t), (name, "wt_huff over rank_support_v5")

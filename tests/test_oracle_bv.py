@@ -90,3 +90,21 @@ def test_two_bit_patterns_vs_naive_and_reference(oracle, ref):
                 got = ob.select(k, code)
                 assert (got == pos[k.astype(np.int64) - 1]).all(), (cid, code, "select vs naive")
                 assert (got == rb.select(k, code)).all(), (cid, code, "select vs reference")
+
+
+def test_rank_support_v5_vs_reference(oracle, ref):
+    """rank_support_v5<b> (rank_support_v5.hpp:66-158; the table inside the reference's count-benchmark index,
+    benchmark/indexing_count/index.config:8): serialised table byte-exact vs the unmodified reference, and its rank
+    equal to rank_support_v's on every position of the small vectors / a sample of the large ones"""
+    checked = 0
+    for cid, w, nbits in cases.bitvector_catalogue(large=True):
+        if nbits > 2_000_000:
+            continue
+        ob, rb = oracle.bv(w, nbits), ref.bv(w, nbits, with_select=False)
+        for what in (5, 6):
+            assert ob.serialize(what) == rb.serialize(what), (cid, what)
+        idx = cases.rank_queries(nbits, 3, 3000 if nbits > 3000 else nbits + 1)
+        for b in (0, 1):
+            assert (ob.rank_v5(idx, b) == rb.rank(idx, b)).all(), (cid, "rank_v5", b)
+        checked += 1
+    assert checked > 30
