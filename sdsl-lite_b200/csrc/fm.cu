@@ -12,6 +12,7 @@
 // (~19 KB) are staged in shared memory once per CTA.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <thread>
 
 #include "internal.h"
@@ -270,13 +271,12 @@ __global__ void __launch_bounds__(kThreads) fm_extract_kernel(Bits bits,
 // ------------------------------------------------------------------------------------------------
 int csa_build_from_text(sdslgpu_handle * h, uint8_t const * text, uint64_t len, uint32_t sa_dens, uint32_t isa_dens, cudaStream_t s)
 {
-    for (uint64_t k = 0; k < len; ++k)
-        if (text[k] == 0)
-        {
-            set_error("csa: the text contains a zero byte at position %llu (the reference rejects it too, construct.hpp:34-46)",
-                      (unsigned long long)k);
-            return SDSLGPU_EINVAL;
-        }
+    if (void const * z = len ? std::memchr(text, 0, len) : nullptr)
+    {
+        set_error("csa: the text contains a zero byte at position %llu (the reference rejects it too, construct.hpp:34-46)",
+                  (unsigned long long)(static_cast<uint8_t const *>(z) - text));
+        return SDSLGPU_EINVAL;
+    }
     uint64_t n = len + 1;
     CsaImage & c = h->csa;
     c.n = n;
@@ -329,8 +329,26 @@ int csa_build_from_text(sdslgpu_handle * h, uint8_t const * text, uint64_t len, 
     FmTables & tab = c.host_tab;
     std::memset(&tab, 0, sizeof(tab));
     uint64_t cnt[256] = {0};
-    for (uint64_t i = 0; i < n; ++i)
-        ++cnt[bwt[i]];
+    {
+        unsigned T = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+        if (n < (1u << 20))
+            T = 1;
+        std::vector<std::vector<uint64_t>> part(T, std::vector<uint64_t>(256, 0));
+        std::vector<std::thread> th;
+        uint64_t chunk = (n + T - 1) / T;
+        for (unsigned t = 0; t < T; ++t)
+            th.emplace_back([&, t] {
+                uint64_t lo = std::min(n, t * chunk), hi = std::min(n, lo + chunk);
+                uint64_t * c = part[t].data();
+                for (uint64_t k = lo; k < hi; ++k)
+                    ++c[bwt[k]];
+            });
+        for (auto & x : th)
+            x.join();
+        for (unsigned t = 0; t < T; ++t)
+            for (int ch = 0; ch < 256; ++ch)
+                cnt[ch] += part[t][ch];
+    }
     uint32_t sigma = 0;
     for (int ch = 0; ch < 256; ++ch)
         if (cnt[ch])
