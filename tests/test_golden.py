@@ -12,6 +12,8 @@ import texts
 from test_oracle_wt_int import sequences
 
 GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz"))
+# make_golden_v2.py: rank_support_v5 tables and the reference's count-benchmark index FM_HUFF
+GOLD2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v2.npz"))
 
 
 def sha(b):
@@ -65,6 +67,42 @@ def test_oracle_against_golden(oracle, orc):
         assert (occ_off == GOLD[key + "|occ_off"]).all() and (occ == GOLD[key + "|occ"]).all(), key
         assert (csa.sa(GOLD[key + "|sa_i"]) == GOLD[key + "|sa"]).all(), key
         assert (sha(csa.serialize()) == GOLD[key + "|sha"]).all(), key
+
+
+def _clean_tail(w, nbits):
+    return nbits % 64 == 0 or int(w[-1]) >> (nbits % 64) == 0
+
+
+def test_oracle_rank_v5_against_golden(oracle):
+    for cid, w, nbits in _bitvectors():
+        ob = oracle.bv(w, nbits)
+        assert (np.concatenate([sha(ob.serialize(5)), sha(ob.serialize(6))]) == GOLD2[f"v5|{cid}|sha"]).all(), cid
+
+
+@pytest.mark.gpu
+def test_gpu_egress_against_golden(pkg):
+    """sdslgpu_serialize against the digests of the reference's own files: wavelet trees, csa_wt, rank_support_v5
+    tables, and the count-benchmark index FM_HUFF (built here at densities 2^20, counted, serialised as what = 1)"""
+    for cid, w, nbits in _bitvectors():
+        if not _clean_tail(w, nbits):
+            continue  # the library drops the unspecified bits past size(); the reference's table counts them
+        with pkg.BitVector(w, nbits) as bv:
+            assert (np.concatenate([sha(bv.serialize(5)), sha(bv.serialize(6))]) == GOLD2[f"v5|{cid}|sha"]).all(), cid
+    for name, t in texts.text_catalogue(large=False):
+        with pkg.WtHuff(t) as wt:
+            assert (sha(wt.serialize()) == GOLD[f"wt_huff|{name}|sha"]).all(), name
+    for name, seq in sequences():
+        with pkg.WtInt(seq) as wt:
+            assert (sha(wt.serialize()) == GOLD[f"wt_int|{name}|sha"]).all(), name
+    for name, t in texts.text_catalogue(zero_free=True, large=False):
+        with pkg.CsaWt(t) as csa:
+            assert (sha(csa.serialize()) == GOLD[f"csa|{name}|sha"]).all(), name
+        key = f"fm_huff|{name}"
+        with pkg.CsaWt(t, sa_dens=1 << 20, isa_dens=1 << 20) as fm:
+            assert (fm.count(GOLD2[key + "|flat"], GOLD2[key + "|off"]) == GOLD2[key + "|cnt"]).all(), key
+            assert (sha(fm.serialize(1)) == GOLD2[key + "|sha"]).all(), key
+        with pkg.WtHuff(t) as wt:
+            assert (sha(wt.serialize(1)) == GOLD2[key + "|wt_sha"]).all(), key
 
 
 @pytest.mark.gpu
