@@ -635,9 +635,11 @@ public:
     }
     //! load (csa_wt.hpp:410-416): reads the rest of the stream; t_dens is a template argument in the reference and is
     //! not stored in the file, so an index sampled at another density needs it named here (0 = 32)
-    void load(std::istream & in, uint32_t t_dens = 0)
+    //! flags: SDSLGPU_F_V5_SCAN for the reference's wt_huff<bit_vector, rank_support_v5<>, select_support_scan<>, ...>
+    //! form (its count benchmark's FM_HUFF), SDSLGPU_F_RRR_BV for wt_huff<rrr_vector<63>>, SDSLGPU_F_COMPACT
+    void load(std::istream & in, uint32_t t_dens = 0, uint32_t flags = SDSLGPU_F_DEFAULT)
     {
-        m_image = detail::load_blob(in, SDSLGPU_KIND_CSA_WT, SDSLGPU_F_DEFAULT, t_dens);
+        m_image = detail::load_blob(in, SDSLGPU_KIND_CSA_WT, flags, t_dens);
         check(sdslgpu_size(m_image.get(), &m_size), "size");
     }
     sdslgpu_handle const * image() const
