@@ -80,3 +80,31 @@ def test_select_mcl_blob_edges(packer, ref):
         rb = ref.bv(w, nbits)
         for b in (1, 0):
             assert packer(w, nbits, b) == rb.serialize(3 if b else 4), (cid, b)
+
+
+def test_select_mcl_blob_random_shapes(packer, ref):
+    """seeded random shapes: sizes on both sides of the 100000-bit switch, densities from 1e-4 to 0.999, clustered runs
+    (long superblocks next to mini ones), so that every combination of block kinds and widths shows up"""
+    rng = np.random.default_rng(2026)
+    kinds = set()
+    for trial in range(48):
+        n = int(rng.choice([rng.integers(1, 5000), rng.integers(60000, 100000), rng.integers(100000, 140000), rng.integers(400000, 1500000)]))
+        d = float(rng.choice([1e-4, 1e-3, 0.01, 0.2, 0.5, 0.9, 0.999]))
+        bits = (rng.random(n) < d).astype(np.uint8)
+        if trial % 3 == 0:  # clusters: stretches of one value
+            for _ in range(int(rng.integers(1, 6))):
+                a = int(rng.integers(0, n))
+                b = min(n, a + int(rng.integers(1, max(2, n // 3))))
+                bits[a:b] = rng.integers(0, 2)
+        w = cases.pack_bits(bits)
+        rb = ref.bv(w, n)
+        for b in (1, 0):
+            blob = packer(w, n, b)
+            assert blob == rb.serialize(3 if b else 4), (trial, n, d, b)
+            m = int(np.frombuffer(blob[:8], np.uint64)[0])
+            if m:  # which block kinds did this shape exercise? (mini_or_long is empty when no long block exists)
+                sb_bits = int(np.frombuffer(blob[8:16], np.uint64)[0]) & ((1 << 56) - 1)
+                pos = 16 + ((sb_bits + 63) // 64) * 8
+                mol_bits = int(np.frombuffer(blob[pos : pos + 8], np.uint64)[0]) & ((1 << 56) - 1)
+                kinds.add(("fast" if n >= 100000 else "slow", "mixed" if mol_bits else "mini-only"))
+    assert len(kinds) == 4, kinds
