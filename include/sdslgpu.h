@@ -226,10 +226,11 @@ int sdslgpu_fm_extract(const sdslgpu_handle *h, const uint64_t *begin, const uin
 
 /* ---- construction parity / interchange ------------------------------------------------------ */
 
-/* Copies the SDSL-format serialisation of one component of a KIND_BV handle into `buf`
+/* Copies the SDSL-format serialisation of one component of a KIND_BV handle created with SDSLGPU_F_SDSL_LAYOUT
+ * into `buf`, from the words / tables that handle keeps resident, caller's bits past size() included
  * (what: 0 = bit_vector, 1 = rank_support_v<1>, 2 = rank_support_v<0>); *nbytes receives the size
  * needed; buf may be NULL to query it.  The rank tables are built ON THE DEVICE and are byte-identical
- * to rank_support_v::serialize (rank_support_v.hpp:151-158). */
+ * to rank_support_v::serialize (rank_support_v.hpp:151-158).  (Handles of the default layout: sdslgpu_serialize.) */
 int sdslgpu_bv_serialize(const sdslgpu_handle *h, int what, void *buf, uint64_t cap, uint64_t *nbytes);
 
 /* Ingest of the reference's own serialised bytes (store_to_file / serialize(), io.hpp:877-896) for
