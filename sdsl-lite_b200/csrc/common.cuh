@@ -5,7 +5,34 @@
 // structures are built on.
 #pragma once
 #include <cstdint>
+#ifdef SDSLGPU_HOST_EMU
+// tests only (tests/cpp/device_on_host.cpp): the per-query device functions of this header and of bv_device.cuh
+// compiled as plain C++, so that their logic is checked against the oracle on a box without a GPU.  The product
+// library never defines SDSLGPU_HOST_EMU.
+#include <cstring>
+#define __device__
+#define __forceinline__ inline
+#define __align__(n) alignas(n)
+struct uint2
+{
+    uint32_t x, y;
+};
+static inline int __popc(uint32_t x)
+{
+    return __builtin_popcount(x);
+}
+static inline int __popcll(uint64_t x)
+{
+    return __builtin_popcountll(x);
+}
+template <class T>
+static inline T __ldg(T const * p)
+{
+    return *p;
+}
+#else
 #include <cuda_runtime.h>
+#endif
 
 namespace sdslgpu
 {
@@ -28,6 +55,25 @@ struct __align__(32) bvblock
 static constexpr uint32_t kBlockBits = 224;
 static constexpr uint32_t kSuperShift = 24; // blocks per superblock = 1 << 24
 
+#ifdef SDSLGPU_HOST_EMU
+inline void ld_block(bvblock const * p, uint32_t & cnt, uint32_t (&d)[7])
+{
+    cnt = p->cnt;
+    std::memcpy(d, p->d, sizeof(d));
+}
+inline void ld_block_half_line(bvblock const * p, uint32_t & cnt, uint32_t (&d)[7])
+{
+    ld_block(p, cnt, d);
+}
+inline uint32_t ld_nc_u32(uint32_t const * p)
+{
+    return *p;
+}
+inline uint64_t ld_nc_u64(uint64_t const * p)
+{
+    return *p;
+}
+#else
 // 256-bit (one sector) read-only gather: a single LDG.E.256 on sm_100a.
 __device__ __forceinline__ void ld_block(bvblock const * p, uint32_t & cnt, uint32_t (&d)[7])
 {
@@ -101,6 +147,7 @@ __device__ __forceinline__ void st_stream(uint64_t * p, uint64_t v)
 {
     st_stream_u64(p, v);
 }
+#endif // SDSLGPU_HOST_EMU
 
 // lo_set[k] for 0 <= k <= 63 (bits.hpp:194-211); k == 64 is never needed on the device paths
 __device__ __forceinline__ uint64_t lo_set64(uint32_t k)

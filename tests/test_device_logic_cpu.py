@@ -1,0 +1,99 @@
+"""CPU: the per-query DEVICE functions themselves — sdsl-lite_b200/csrc/bv_device.cuh (bv_rank1, bv_rank1_and_bit,
+bv_bit, bv_select<B>: sampled hint, interpolated first probe, walk, bisection) and the word-level helpers of
+common.cuh — compiled as plain C++ (SDSLGPU_HOST_EMU, tests/cpp/device_on_host.cpp) and checked against the oracle:
+the same source the kernels run, every sample stride from 1 to 4096, interpolation on and off, random / sparse /
+clustered data.  The GPU tests check the kernels; this checks their logic where no GPU is."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "sdsl-lite_b200", "build", "libdevhost.so")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    src = os.path.join(ROOT, "tests", "cpp", "device_on_host.cpp")
+    deps = [src] + [os.path.join(ROOT, "sdsl-lite_b200", "csrc", f) for f in ("bv_device.cuh", "common.cuh")]
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
+        r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Wno-unknown-pragmas", "-DSDSLGPU_HOST_EMU", "-shared", "-fPIC", src, "-o", SO],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+    L = ctypes.CDLL(SO)
+    vp, u64, u32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32
+    L.emu_rank1.argtypes = [vp, u64, vp, u64, vp, vp]
+    L.emu_select.argtypes = [vp, u64, ctypes.c_int, u32, u32, vp, u64, vp]
+    L.emu_sel64.argtypes = [u64, u32]
+    L.emu_sel64.restype = u32
+    return L
+
+
+def _words(w):
+    return np.ascontiguousarray(np.concatenate([np.asarray(w, np.uint64), np.zeros(2, np.uint64)]))
+
+
+def _shapes():
+    for cid, w, nbits in cases.bitvector_catalogue(large=True):
+        if nbits <= 1_100_000:
+            yield cid, w, nbits
+    rng = np.random.default_rng(77)
+    n = 700_000
+    b = np.zeros(n, np.uint8)
+    b[-5000:] = 1  # every one at the very end: the interpolated guess is far too low, bisection territory
+    yield "ones_at_end", cases.pack_bits(b), n
+    b = np.zeros(n, np.uint8)
+    b[:3000] = 1
+    b[350_000:353_000] = 1
+    b[-1] = 1  # two clusters and a straggler: both over- and undershoots over long hint ranges
+    yield "clusters", cases.pack_bits(b), n
+    b = (rng.random(n) < 0.5).astype(np.uint8)
+    b[100_000:600_000] = 0  # a desert inside random data (and an oasis for the zeros)
+    yield "desert", cases.pack_bits(b), n
+
+
+def test_word_select(emu):
+    rng = np.random.default_rng(5)
+    for x in list(rng.integers(1, 2**64, 400, dtype=np.uint64)) + [np.uint64(1), np.uint64(1 << 63), np.uint64(2**64 - 1)]:
+        x = int(x)
+        pos = [i for i in range(64) if (x >> i) & 1]
+        for k, p in enumerate(pos, 1):  # test/bits_test.cpp:150-177
+            assert emu.emu_sel64(x, k) == p
+
+
+def test_device_rank_and_bit_logic(emu, oracle):
+    for cid, w, nbits in _shapes():
+        ww = _words(w)
+        idx = cases.rank_queries(nbits, 9, 20000)
+        out = np.zeros(len(idx), np.uint64)
+        bit = np.full(len(idx), 7, np.uint64)
+        emu.emu_rank1(ww.ctypes.data, nbits, idx.ctypes.data, len(idx), out.ctypes.data, bit.ctypes.data)
+        assert (out == oracle.bv(w, nbits).rank(idx, 1)).all(), cid
+        inside = idx < nbits
+        if inside.any():
+            bits = cases.unpack_bits(w, nbits)
+            assert (bit[inside] == bits[idx[inside].astype(np.int64)]).all(), (cid, "bit / rank_and_bit")
+
+
+@pytest.mark.parametrize("interp", [0, 1])
+@pytest.mark.parametrize("log_s", [0, 3, 6, 9, 12])
+def test_device_select_logic(emu, oracle, log_s, interp):
+    checked = 0
+    for cid, w, nbits in _shapes():
+        ww = _words(w)
+        ob = oracle.bv(w, nbits)
+        for b in (1, 0):
+            m = int(ob.rank([nbits], b)[0])
+            q = cases.select_queries(m, 11 + log_s, 6000)
+            if not len(q):
+                continue
+            out = np.zeros(len(q), np.uint64)
+            emu.emu_select(ww.ctypes.data, nbits, b, log_s, interp, q.ctypes.data, len(q), out.ctypes.data)
+            assert (out == ob.select(q, b)).all(), (cid, b, log_s, interp)
+            checked += len(q)
+    assert checked > 100000
