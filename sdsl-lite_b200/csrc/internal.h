@@ -13,6 +13,7 @@
 #include "bits_access.cuh"
 #include "bv_device.cuh"
 #include "common.cuh"
+#include "wt_tree.h"
 
 namespace sdslgpu
 {
@@ -142,22 +143,6 @@ inline BvView bv_view(BvImage const & v)
     w.ones = v.ones;
     return w;
 }
-
-// node table + per-symbol paths of a byte wavelet tree (wt_helper.hpp:219-225), as staged into shared
-// memory by every wt / fm kernel.  ~14 KB.
-struct alignas(16) WtTree
-{
-    static constexpr int kMaxNodes = 512; // 2*256-1 nodes + one sentinel slot (keeps every array 16-byte aligned)
-    uint64_t bv_pos[kMaxNodes];
-    uint64_t bv_pos_rank[kMaxNodes]; // leaves: the symbol
-    uint16_t child[kMaxNodes][2];    // 0xFFFF = leaf
-    uint16_t parent[kMaxNodes];
-    uint16_t c_to_leaf[256]; // 0xFFFF = symbol absent
-    uint64_t path[256];      // bits 0..55 path from the root (LSB first), bits 56..63 its length
-    uint64_t occ[256];       // occurrences of each symbol (not in the reference's tree; bounds select)
-    uint32_t nnodes;
-    uint32_t pad_;
-};
 
 // rrr_vector<63, int_vector<>, 32> (rrr_vector.hpp:101-109)
 struct RrrImage

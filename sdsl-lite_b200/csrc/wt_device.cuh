@@ -7,8 +7,6 @@
 namespace sdslgpu
 {
 
-static constexpr uint16_t kWtUndef = 0xFFFF;
-
 // cooperative 16-byte copy of the node table + paths (~16 KB) into shared memory, once per CTA
 __device__ __forceinline__ void stage_tree(WtTree const * __restrict__ g, WtTree * s)
 {
