@@ -11,6 +11,7 @@
 // library never defines SDSLGPU_HOST_EMU.
 #include <cstring>
 #define __device__
+#define __host__
 #define __forceinline__ inline
 #define __align__(n) alignas(n)
 struct uint2

@@ -26,36 +26,6 @@
 namespace sdslgpu
 {
 
-static RrrTables const & host_tables()
-{
-    static RrrTables t;
-    static bool ready = false;
-    if (!ready)
-    {
-        std::memset(&t, 0, sizeof(t));
-        uint64_t full[65][65];
-        std::memset(full, 0, sizeof(full));
-        for (int n = 0; n <= 64; ++n)
-            full[n][0] = 1;
-        for (int n = 1; n <= 64; ++n)
-            for (int k = 1; k <= n; ++k)
-                full[n][k] = full[n - 1][k - 1] + full[n - 1][k];
-        for (int n = 0; n < 64; ++n)
-            for (int k = 0; k < 64; ++k)
-                t.binom[n][k] = full[n][k];
-        for (int k = 0; k < 64; ++k)
-        {
-            uint64_t c = full[63][k];
-            uint8_t hi = 0;
-            for (uint64_t x = c; x >>= 1;)
-                ++hi;
-            t.space[k] = (c == 1) ? 0 : (uint8_t)(hi + 1);
-        }
-        ready = true;
-    }
-    return t;
-}
-
 __global__ void __launch_bounds__(kThreads) rrr_rank_kernel(RrrView const v, int b, uint64_t const * __restrict__ idx, uint64_t n, uint64_t * __restrict__ out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -158,47 +128,6 @@ __global__ void __launch_bounds__(kThreads) rrr_classify_kernel(uint64_t const *
     uint32_t k = __popcll(rrr_block_bits(words, nbits, b));
     blk_k[b] = k;
     blk_sp[b] = (b * kBs < nbits) ? tables->space[k] : 0; // the dummy block stores nothing
-}
-
-// fills one 64-byte record from the REAL classes of its blocks (host and device share this)
-__host__ __device__ inline void rrr_make_record(uint32_t const * k_real, uint32_t nblk_here, bool complete, uint8_t const * space, uint64_t ones_before,
-                                                uint64_t bits_before, uint64_t * rec)
-{
-    bool inv = false;
-    if (complete)
-    { // only complete superblocks can be inverted (rrr_vector.hpp:203-228)
-        uint32_t gt = 0;
-        for (uint32_t j = 0; j < kK; ++j)
-            gt += k_real[j] > kBs / 2;
-        inv = gt > kK / 2;
-    }
-    uint64_t w[3] = {0, 0, 0};
-    uint32_t ones = 0, bits = 0, qo[4] = {0, 0, 0, 0}, qb[4] = {0, 0, 0, 0};
-    for (uint32_t j = 0; j < kK; ++j)
-    {
-        if ((j & 7) == 0)
-        {
-            qo[j >> 3] = ones;
-            qb[j >> 3] = bits;
-        }
-        if (j >= nblk_here)
-            continue;
-        uint64_t c = inv ? kBs - k_real[j] : k_real[j];
-        uint32_t bit = j * 6;
-        w[bit >> 6] |= c << (bit & 63);
-        if ((bit & 63) > 58)
-            w[(bit >> 6) + 1] |= c >> (64 - (bit & 63));
-        ones += k_real[j];
-        bits += space[k_real[j]];
-    }
-    rec[0] = ones_before;
-    rec[1] = bits_before | (inv ? kInvBit : 0);
-    rec[2] = w[0];
-    rec[3] = w[1];
-    rec[4] = w[2];
-    rec[5] = (uint64_t)qo[1] | ((uint64_t)qo[2] << 10) | ((uint64_t)qo[3] << 20) | ((uint64_t)qb[1] << 31) | ((uint64_t)qb[2] << 41) | ((uint64_t)qb[3] << 51);
-    rec[6] = ones;
-    rec[7] = bits;
 }
 
 __global__ void __launch_bounds__(kThreads) rrr_superblock_kernel(uint32_t const * __restrict__ blk_k,
@@ -388,36 +317,8 @@ int rrr_records_from_sdsl(DevicePool & pool, RrrImage & r,
                           uint64_t total_bits_hint,
                           cudaStream_t s)
 {
-    RrrTables const & t = host_tables();
-    std::vector<uint64_t> rec(kRecWords * (r.nsuper + 1), 0);
-    for (uint64_t g = 0; g < r.nsuper; ++g)
-    {
-        uint32_t k_real[kK];
-        uint32_t here = 0;
-        for (uint32_t j = 0; j < kK; ++j)
-        {
-            uint64_t b = g * kK + j;
-            uint32_t c = 0;
-            if (b < nblocks)
-            {
-                uint64_t pos = b * 6;
-                uint64_t lo = bt_words[pos >> 6] >> (pos & 63);
-                if ((pos & 63) > 58)
-                    lo |= bt_words[(pos >> 6) + 1] << (64 - (pos & 63));
-                c = (uint32_t)(lo & 63);
-                if (invert[g])
-                    c = kBs - c;
-                ++here;
-            }
-            k_real[j] = c;
-        }
-        uint64_t * out = rec.data() + g * kRecWords;
-        rrr_make_record(k_real, here, g * kK + kK <= nblocks, t.space, rank[g], btnrp[g], out);
-        // keep the reference's invert bit verbatim (it equals the recomputed one for every complete superblock)
-        out[1] = btnrp[g] | (invert[g] ? kInvBit : 0);
-    }
-    rec[kRecWords * r.nsuper] = r.ones;
-    rec[kRecWords * r.nsuper + 1] = total_bits_hint;
+    std::vector<uint64_t> rec;
+    rrr_records_host(bt_words, nblocks, r.nsuper, r.ones, rank, btnrp, invert, total_bits_hint, rec);
     SG_TRY(pool.alloc_t(&r.records, rec.size()));
     SG_CUDA(cudaMemcpyAsync(r.records, rec.data(), rec.size() * 8, cudaMemcpyHostToDevice, s));
     SG_CUDA(cudaStreamSynchronize(s));

@@ -2,6 +2,9 @@
 // shared by rrr.cu (plain rank/select/access batches) and the wavelet-tree / FM-index kernels when the tree's
 // bit vector is stored H0-compressed (wt_huff<rrr_vector<63>>).  Layout: see rrr.cu.
 #pragma once
+#include <cstring>
+#include <vector>
+
 #include "common.cuh"
 
 namespace sdslgpu
@@ -19,6 +22,7 @@ struct RrrTables
     uint8_t space[64];      // bits of an offset of class k: 0 if C(63,k) == 1 else hi(C(63,k)) + 1 (:286-293)
 };
 
+#ifndef SDSLGPU_HOST_EMU
 __device__ __forceinline__ void stage_rrr(RrrTables const * __restrict__ g, RrrTables * s)
 {
     uint4 const * src = reinterpret_cast<uint4 const *>(g);
@@ -27,6 +31,7 @@ __device__ __forceinline__ void stage_rrr(RrrTables const * __restrict__ g, RrrT
         dst[k] = __ldg(src + k);
     __syncthreads();
 }
+#endif
 
 // the block with k ones and offset nr, decoded up to `upto` positions (inverse of bin_to_nr, rrr_helper.hpp:346-366;
 // what decode_bit / decode_popcount / decode_select of rrr_helper.hpp:369-649 all compute from)
@@ -67,12 +72,19 @@ struct RrrRecord
     uint64_t w[kRecWords];
 };
 
+#ifdef SDSLGPU_HOST_EMU
+inline void ld_record(uint64_t const * records, uint64_t g, RrrRecord & r)
+{
+    std::memcpy(r.w, records + g * kRecWords, sizeof(r.w));
+}
+#else
 __device__ __forceinline__ void ld_record(uint64_t const * __restrict__ records, uint64_t g, RrrRecord & r)
 {
     uint64_t const * p = records + g * kRecWords;
     asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.w[0]), "=l"(r.w[1]), "=l"(r.w[2]), "=l"(r.w[3]) : "l"(p));
     asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.w[4]), "=l"(r.w[5]), "=l"(r.w[6]), "=l"(r.w[7]) : "l"(p + 4));
 }
+#endif
 
 // stored class of block j (0..31) of a record
 __host__ __device__ __forceinline__ uint32_t rec_class(uint64_t w2, uint64_t w3, uint64_t w4, uint32_t j)
@@ -218,6 +230,119 @@ __device__ __forceinline__ uint64_t rrr_select_one(RrrView const & v, RrrTables 
     uint64_t bin = rrr_decode(t, k, sp ? read_int(v.btnr, p, sp) : 0, kBs);
     uint64_t x = B ? bin : (~bin & ((1ull << kBs) - 1));
     return (begin * kK + j) * kBs + sel64(x, (uint32_t)(i - cnt));
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side shared by rrr.cu and the CPU tests
+// ------------------------------------------------------------------------------------------------
+// C(n,k) for n,k <= 63 and the code lengths, computed once on the host (uploaded by rrr.cu, used by the CPU tests)
+inline RrrTables const & host_tables()
+{
+    static RrrTables t;
+    static bool ready = false;
+    if (!ready)
+    {
+        std::memset(&t, 0, sizeof(t));
+        uint64_t full[65][65];
+        std::memset(full, 0, sizeof(full));
+        for (int n = 0; n <= 64; ++n)
+            full[n][0] = 1;
+        for (int n = 1; n <= 64; ++n)
+            for (int k = 1; k <= n; ++k)
+                full[n][k] = full[n - 1][k - 1] + full[n - 1][k];
+        for (int n = 0; n < 64; ++n)
+            for (int k = 0; k < 64; ++k)
+                t.binom[n][k] = full[n][k];
+        for (int k = 0; k < 64; ++k)
+        {
+            uint64_t c = full[63][k];
+            uint8_t hi = 0;
+            for (uint64_t x = c; x >>= 1;)
+                ++hi;
+            t.space[k] = (c == 1) ? 0 : (uint8_t)(hi + 1);
+        }
+        ready = true;
+    }
+    return t;
+}
+
+// fills one 64-byte record from the REAL classes of its blocks (host and device share this)
+__host__ __device__ inline void rrr_make_record(uint32_t const * k_real, uint32_t nblk_here, bool complete, uint8_t const * space, uint64_t ones_before,
+                                                uint64_t bits_before, uint64_t * rec)
+{
+    bool inv = false;
+    if (complete)
+    { // only complete superblocks can be inverted (rrr_vector.hpp:203-228)
+        uint32_t gt = 0;
+        for (uint32_t j = 0; j < kK; ++j)
+            gt += k_real[j] > kBs / 2;
+        inv = gt > kK / 2;
+    }
+    uint64_t w[3] = {0, 0, 0};
+    uint32_t ones = 0, bits = 0, qo[4] = {0, 0, 0, 0}, qb[4] = {0, 0, 0, 0};
+    for (uint32_t j = 0; j < kK; ++j)
+    {
+        if ((j & 7) == 0)
+        {
+            qo[j >> 3] = ones;
+            qb[j >> 3] = bits;
+        }
+        if (j >= nblk_here)
+            continue;
+        uint64_t c = inv ? kBs - k_real[j] : k_real[j];
+        uint32_t bit = j * 6;
+        w[bit >> 6] |= c << (bit & 63);
+        if ((bit & 63) > 58)
+            w[(bit >> 6) + 1] |= c >> (64 - (bit & 63));
+        ones += k_real[j];
+        bits += space[k_real[j]];
+    }
+    rec[0] = ones_before;
+    rec[1] = bits_before | (inv ? kInvBit : 0);
+    rec[2] = w[0];
+    rec[3] = w[1];
+    rec[4] = w[2];
+    rec[5] = (uint64_t)qo[1] | ((uint64_t)qo[2] << 10) | ((uint64_t)qo[3] << 20) | ((uint64_t)qb[1] << 31) | ((uint64_t)qb[2] << 41) | ((uint64_t)qb[3] << 51);
+    rec[6] = ones;
+    rec[7] = bits;
+}
+
+// the 64-byte records of an rrr_vector<63> from the arrays the reference serialises (m_bt classes, m_rank, m_btnrp,
+// m_invert: ingest, sdsl_format.cu); `rec` receives nsuper + 1 records, the last one holds the totals
+inline void rrr_records_host(uint64_t const * bt_words /* packed 6-bit stored classes */, uint64_t nblocks, uint64_t nsuper, uint64_t ones,
+                             std::vector<uint64_t> const & rank, std::vector<uint64_t> const & btnrp, std::vector<uint8_t> const & invert,
+                             uint64_t total_bits_hint, std::vector<uint64_t> & rec)
+{
+    RrrTables const & t = host_tables();
+    rec.assign(kRecWords * (nsuper + 1), 0);
+    for (uint64_t g = 0; g < nsuper; ++g)
+    {
+        uint32_t k_real[kK];
+        uint32_t here = 0;
+        for (uint32_t j = 0; j < kK; ++j)
+        {
+            uint64_t b = g * kK + j;
+            uint32_t c = 0;
+            if (b < nblocks)
+            {
+                uint64_t pos = b * 6;
+                uint64_t lo = bt_words[pos >> 6] >> (pos & 63);
+                if ((pos & 63) > 58)
+                    lo |= bt_words[(pos >> 6) + 1] << (64 - (pos & 63));
+                c = (uint32_t)(lo & 63);
+                if (invert[g])
+                    c = kBs - c;
+                ++here;
+            }
+            k_real[j] = c;
+        }
+        uint64_t * out = rec.data() + g * kRecWords;
+        rrr_make_record(k_real, here, g * kK + kK <= nblocks, t.space, rank[g], btnrp[g], out);
+        // keep the reference's invert bit verbatim (it equals the recomputed one for every complete superblock)
+        out[1] = btnrp[g] | (invert[g] ? kInvBit : 0);
+    }
+    rec[kRecWords * nsuper] = ones;
+    rec[kRecWords * nsuper + 1] = total_bits_hint;
 }
 
 } // namespace sdslgpu

@@ -97,3 +97,68 @@ def test_device_select_logic(emu, oracle, log_s, interp):
             assert (out == ob.select(q, b)).all(), (cid, b, log_s, interp)
             checked += len(q)
     assert checked > 100000
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# rrr_vector<63>: rrr_device.cuh (rank, rank + bit, select<0/1>, enumerative decode) over an image built by the
+# product's own host code (rrr_records_host, host_tables) from the reference's / the oracle's serialised vector
+# ---------------------------------------------------------------------------------------------------------------
+RRR_SO = os.path.join(ROOT, "sdsl-lite_b200", "build", "librrrhost.so")
+
+
+@pytest.fixture(scope="module")
+def rrr_emu():
+    src = os.path.join(ROOT, "tests", "cpp", "rrr_on_host.cpp")
+    deps = [src] + [os.path.join(ROOT, "sdsl-lite_b200", "csrc", f) for f in ("rrr_device.cuh", "common.cuh")]
+    os.makedirs(os.path.dirname(RRR_SO), exist_ok=True)
+    if not os.path.exists(RRR_SO) or os.path.getmtime(RRR_SO) < max(os.path.getmtime(d) for d in deps):
+        r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Wno-unknown-pragmas", "-DSDSLGPU_HOST_EMU", "-shared", "-fPIC", src, "-o", RRR_SO],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+    L = ctypes.CDLL(RRR_SO)
+    vp, u64 = ctypes.c_void_p, ctypes.c_uint64
+    L.rrr_emu_load.restype = vp
+    L.rrr_emu_load.argtypes = [vp]
+    L.rrr_emu_free.argtypes = [vp]
+    L.rrr_emu_rank.argtypes = [vp, ctypes.c_int, vp, u64, vp]
+    L.rrr_emu_select.argtypes = [vp, ctypes.c_int, vp, u64, vp]
+    L.rrr_emu_access.argtypes = [vp, vp, u64, vp, vp]
+    return L
+
+
+def _rrr_shapes():
+    for cid, w, nbits in _shapes():
+        yield cid, w, nbits
+    for d in (0.01, 0.1, 0.5, 0.9, 0.99):  # the density sweep of BASELINE config 3 in miniature; > 0.5 exercises inverted superblocks
+        n = 300_000 + int(d * 1000)
+        yield f"bernoulli.{d}", cases.bernoulli_words(n, d, 600 + int(d * 100)), n
+
+
+def test_device_rrr_logic(rrr_emu, oracle):
+    checked = 0
+    for cid, w, nbits in _rrr_shapes():
+        o = oracle.rrr(w, nbits)
+        blob = np.frombuffer(o.serialize(), dtype=np.uint8).copy()
+        blob = np.concatenate([blob, np.zeros(64, np.uint8)])
+        h = rrr_emu.rrr_emu_load(blob.ctypes.data)
+        try:
+            idx = cases.rank_queries(nbits, 13, 8000)
+            out = np.zeros(len(idx), np.uint64)
+            for b in (1, 0):
+                rrr_emu.rrr_emu_rank(h, b, idx.ctypes.data, len(idx), out.ctypes.data)
+                assert (out == o.rank(idx, b)).all(), (cid, "rank", b)
+                m = int(o.rank([nbits], b)[0])
+                q = cases.select_queries(m, 14, 8000)
+                if len(q):
+                    so = np.zeros(len(q), np.uint64)
+                    rrr_emu.rrr_emu_select(h, b, q.ctypes.data, len(q), so.ctypes.data)
+                    assert (so == o.select(q, b)).all(), (cid, "select", b)
+                    checked += len(q)
+            pos = np.ascontiguousarray(idx[idx < nbits])
+            if len(pos):
+                bit, rk = np.zeros(len(pos), np.uint64), np.zeros(len(pos), np.uint64)
+                rrr_emu.rrr_emu_access(h, pos.ctypes.data, len(pos), bit.ctypes.data, rk.ctypes.data)
+                assert (bit == o.access(pos)).all() and (rk == o.rank(pos, 1)).all(), (cid, "rank_and_bit")
+        finally:
+            rrr_emu.rrr_emu_free(h)
+    assert checked > 100000
