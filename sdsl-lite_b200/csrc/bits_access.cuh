@@ -4,6 +4,8 @@
 //   RrrBits   : rrr_vector<63> + rank_support_rrr + select_support_rrr -> fused records (rrr_device.cuh),
 //               i.e. wt_huff<rrr_vector<63>> / csa_wt<wt_huff<rrr_vector<63>>>
 #pragma once
+#include <cstddef>
+
 #include "bv_device.cuh"
 #include "rrr_device.cuh"
 
@@ -38,9 +40,14 @@ struct RrrBits
     static constexpr size_t kSmem = sizeof(RrrTables);
     __device__ __forceinline__ void attach(unsigned char * smem)
     {
+#ifdef SDSLGPU_HOST_EMU
+        (void)smem;
+        t = v.tables;
+#else
         RrrTables * s = reinterpret_cast<RrrTables *>(smem);
         stage_rrr(v.tables, s);
         t = s;
+#endif
     }
     __device__ __forceinline__ uint64_t rank1(uint64_t pos) const
     {

@@ -2,11 +2,16 @@
 // (wt_huff queries) and fm.cu (backward search, LF walks).
 #pragma once
 #include "bits_access.cuh"
+#ifdef SDSLGPU_HOST_EMU
+#include "wt_tree.h" // tests/cpp/wt_on_host.cpp: the per-query functions below as plain C++
+#else
 #include "internal.h"
+#endif
 
 namespace sdslgpu
 {
 
+#ifndef SDSLGPU_HOST_EMU
 // cooperative 16-byte copy of the node table + paths (~16 KB) into shared memory, once per CTA
 __device__ __forceinline__ void stage_tree(WtTree const * __restrict__ g, WtTree * s)
 {
@@ -16,6 +21,7 @@ __device__ __forceinline__ void stage_tree(WtTree const * __restrict__ g, WtTree
         dst[k] = __ldg(src + k);
     __syncthreads();
 }
+#endif
 
 // rank(i, c) for one query (wt_pc.hpp:371-399): path_len dependent sector gathers on the concatenated m_bv
 template <class Bits>

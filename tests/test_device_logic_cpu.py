@@ -20,7 +20,7 @@ SO = os.path.join(ROOT, "sdsl-lite_b200", "build", "libdevhost.so")
 def emu():
     os.makedirs(os.path.dirname(SO), exist_ok=True)
     src = os.path.join(ROOT, "tests", "cpp", "device_on_host.cpp")
-    deps = [src] + [os.path.join(ROOT, "sdsl-lite_b200", "csrc", f) for f in ("bv_device.cuh", "common.cuh")]
+    deps = [src, os.path.join(ROOT, "tests", "cpp", "host_image.h")] + [os.path.join(ROOT, "sdsl-lite_b200", "csrc", f) for f in ("bv_device.cuh", "common.cuh")]
     if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
         r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Wno-unknown-pragmas", "-DSDSLGPU_HOST_EMU", "-shared", "-fPIC", src, "-o", SO],
                            capture_output=True, text=True)
@@ -162,3 +162,54 @@ def test_device_rrr_logic(rrr_emu, oracle):
         finally:
             rrr_emu.rrr_emu_free(h)
     assert checked > 100000
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# wt_huff<>: wt_device.cuh (wt_rank_one, wt_inverse_select_one) over the tree shape and bit planes of the product's
+# host code (wt_shape.h) and the sector-block rank of bv_device.cuh
+# ---------------------------------------------------------------------------------------------------------------
+WT_SO = os.path.join(ROOT, "sdsl-lite_b200", "build", "libwthost.so")
+
+
+@pytest.fixture(scope="module")
+def wt_emu():
+    src = os.path.join(ROOT, "tests", "cpp", "wt_on_host.cpp")
+    deps = [src, os.path.join(ROOT, "tests", "cpp", "host_image.h")] + [
+        os.path.join(ROOT, "sdsl-lite_b200", "csrc", f) for f in ("wt_device.cuh", "wt_shape.h", "wt_tree.h", "bits_access.cuh", "bv_device.cuh", "rrr_device.cuh", "common.cuh")]
+    os.makedirs(os.path.dirname(WT_SO), exist_ok=True)
+    if not os.path.exists(WT_SO) or os.path.getmtime(WT_SO) < max(os.path.getmtime(d) for d in deps):
+        r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Wno-unknown-pragmas", "-pthread", "-DSDSLGPU_HOST_EMU", "-shared", "-fPIC", src, "-o", WT_SO],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+    L = ctypes.CDLL(WT_SO)
+    vp, u64 = ctypes.c_void_p, ctypes.c_uint64
+    L.wt_emu_create.restype = vp
+    L.wt_emu_create.argtypes = [vp, u64]
+    L.wt_emu_free.argtypes = [vp]
+    L.wt_emu_rank.argtypes = [vp, vp, vp, u64, vp]
+    L.wt_emu_inverse_select.argtypes = [vp, vp, u64, vp, vp]
+    return L
+
+
+def test_device_wt_logic(wt_emu, oracle):
+    import texts
+
+    rng = np.random.default_rng(23)
+    deep = np.concatenate([np.full(1 << k, 65 + k, np.uint8) for k in range(14)])
+    rng.shuffle(deep)
+    for name, t in list(texts.text_catalogue(large=False)) + [("deep", deep.tobytes())]:
+        a = np.ascontiguousarray(np.frombuffer(t, dtype=np.uint8))
+        h = wt_emu.wt_emu_create(a.ctypes.data, len(a))
+        try:
+            o = oracle.wt_huff(t)
+            i, c = texts.wt_queries(t, rng, 6000)
+            out = np.zeros(len(i), np.uint64)
+            wt_emu.wt_emu_rank(h, i.ctypes.data, c.ctypes.data, len(i), out.ctypes.data)
+            assert (out == o.rank(i, c)).all(), (name, "rank")
+            j = rng.integers(0, len(t), 6000, dtype=np.uint64)
+            rk, sym = np.zeros(len(j), np.uint64), np.zeros(len(j), np.uint64)
+            wt_emu.wt_emu_inverse_select(h, j.ctypes.data, len(j), rk.ctypes.data, sym.ctypes.data)
+            orr, oss = o.inverse_select(j)
+            assert (rk == orr).all() and (sym == oss).all(), (name, "inverse_select")
+        finally:
+            wt_emu.wt_emu_free(h)
