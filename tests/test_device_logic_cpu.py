@@ -213,3 +213,55 @@ def test_device_wt_logic(wt_emu, oracle):
             assert (rk == orr).all() and (sym == oss).all(), (name, "inverse_select")
         finally:
             wt_emu.wt_emu_free(h)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# sd_vector<>: sd_device.cuh (rank via select_0 on `high` + the backwards scan, select_1) over an image built from the
+# serialised vector
+# ---------------------------------------------------------------------------------------------------------------
+SD_SO = os.path.join(ROOT, "sdsl-lite_b200", "build", "libsdhost.so")
+
+
+@pytest.fixture(scope="module")
+def sd_emu():
+    src = os.path.join(ROOT, "tests", "cpp", "sd_on_host.cpp")
+    deps = [src, os.path.join(ROOT, "tests", "cpp", "host_image.h")] + [os.path.join(ROOT, "sdsl-lite_b200", "csrc", f) for f in ("sd_device.cuh", "bv_device.cuh", "common.cuh")]
+    os.makedirs(os.path.dirname(SD_SO), exist_ok=True)
+    if not os.path.exists(SD_SO) or os.path.getmtime(SD_SO) < max(os.path.getmtime(d) for d in deps):
+        r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Wno-unknown-pragmas", "-DSDSLGPU_HOST_EMU", "-shared", "-fPIC", src, "-o", SD_SO],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+    L = ctypes.CDLL(SD_SO)
+    vp, u64 = ctypes.c_void_p, ctypes.c_uint64
+    L.sd_emu_load.restype = vp
+    L.sd_emu_load.argtypes = [vp]
+    L.sd_emu_free.argtypes = [vp]
+    L.sd_emu_rank.argtypes = [vp, ctypes.c_int, vp, u64, vp]
+    L.sd_emu_select1.argtypes = [vp, vp, u64, vp]
+    return L
+
+
+def test_device_sd_logic(sd_emu, oracle):
+    checked = 0
+    for cid, w, nbits in _rrr_shapes():
+        if nbits == 0:
+            continue
+        o = oracle.sd(w, nbits)
+        blob = np.concatenate([np.frombuffer(o.serialize(), dtype=np.uint8), np.zeros(64, np.uint8)])
+        h = sd_emu.sd_emu_load(blob.ctypes.data)
+        try:
+            idx = cases.rank_queries(nbits, 17, 8000)
+            out = np.zeros(len(idx), np.uint64)
+            for b in (1, 0):
+                sd_emu.sd_emu_rank(h, b, idx.ctypes.data, len(idx), out.ctypes.data)
+                assert (out == o.rank(idx, b)).all(), (cid, "rank", b)
+            m = int(o.rank([nbits], 1)[0])
+            q = cases.select_queries(m, 18, 8000)
+            if len(q):
+                so = np.zeros(len(q), np.uint64)
+                sd_emu.sd_emu_select1(h, q.ctypes.data, len(q), so.ctypes.data)
+                assert (so == o.select(q, 1)).all(), (cid, "select_1")
+                checked += len(q)
+        finally:
+            sd_emu.sd_emu_free(h)
+    assert checked > 100000
