@@ -25,6 +25,25 @@ int cuda_fail(cudaError_t e, char const * what, char const * file, int line)
     return e == cudaErrorMemoryAllocation ? SDSLGPU_ENOMEM : SDSLGPU_ECUDA;
 }
 
+int sm_count()
+{
+    static int cached[64] = {0}; // per device ordinal; a benign race writes the same value twice
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+        return 148;
+    if (cached[dev] == 0)
+    {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+        {
+            cudaGetLastError();
+            n = 148;
+        }
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
 int DevicePool::alloc(void ** p, uint64_t n)
 {
     *p = nullptr;

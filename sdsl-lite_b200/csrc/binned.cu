@@ -312,7 +312,8 @@ int bin_scratch_alloc(BinScratch & w, BinPlan const & p, cudaStream_t s)
 int bin_launch_tile_sort(BinPlan const & p, BinScratch const & w, uint64_t const * q, uint64_t n, uint64_t sub, uint64_t maxkey, bool clamp, cudaStream_t s)
 {
     // persistent CTAs, two per SM (96 KB of shared memory each with the TMA key buffer)
-    unsigned grid = (unsigned)(p.ntiles < 2ull * kSmCount ? p.ntiles : 2ull * kSmCount);
+    uint64_t const resident = 2ull * (uint64_t)sm_count();
+    unsigned grid = (unsigned)(p.ntiles < resident ? p.ntiles : resident);
     if ((reinterpret_cast<uintptr_t>(q) & 15u) == 0)
     {
         int smem = kTile * 4 + kTile * 8;
@@ -337,7 +338,7 @@ int bin_launch_unsort(BinPlan const & p, BinScratch const & w, uint64_t n, uint6
 unsigned bin_apply_grid(BinPlan const & p)
 {
     uint64_t runs = (uint64_t)p.nb * p.ntiles;
-    uint64_t want = (runs + kThreads / 32 - 1) / (kThreads / 32), cap = (uint64_t)kSmCount * 8;
+    uint64_t want = (runs + kThreads / 32 - 1) / (kThreads / 32), cap = (uint64_t)sm_count() * 8;
     return (unsigned)(want < cap ? (want ? want : 1) : cap);
 }
 

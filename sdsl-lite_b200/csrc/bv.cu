@@ -73,7 +73,9 @@ __global__ void __launch_bounds__(kThreads) bv_samples_kernel(uint64_t const * _
                                                               uint64_t nblocks,
                                                               uint32_t log_s,
                                                               uint32_t * __restrict__ samp,
-                                                              uint64_t nsamp)
+                                                              uint64_t nsamp,
+                                                              bvblock const * __restrict__ blocks,
+                                                              uint32_t pos_mode)
 {
     uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks)
@@ -86,8 +88,23 @@ __global__ void __launch_bounds__(kThreads) bv_samples_kernel(uint64_t const * _
     if (c == 0)
         return;
     uint64_t S = 1ull << log_s;
+    uint32_t cnt = 0, d[7] = {0, 0, 0, 0, 0, 0, 0};
+    bool loaded = false;
     for (uint64_t j = (a + S - 1) >> log_s; j < nsamp && (j << log_s) + 1 <= a + c; ++j)
-        samp[j] = (uint32_t)b;
+    {
+        if (!pos_mode)
+        {
+            samp[j] = (uint32_t)b;
+            continue;
+        }
+        if (!loaded)
+        {
+            ld_block(blocks + b, cnt, d);
+            loaded = true;
+        }
+        // the sampled bit's position in 32-bit chunks (its block is chunk / 7)
+        samp[j] = (uint32_t)((first + block_select<B>(d, (uint32_t)((j << log_s) + 1 - a))) >> 5);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -278,7 +295,7 @@ __global__ void __launch_bounds__(kThreads) sdsl_table_abs_kernel(uint64_t const
 unsigned grid_for(uint64_t n, int per_thread)
 {
     uint64_t want = (n + (uint64_t)kThreads * per_thread - 1) / ((uint64_t)kThreads * per_thread);
-    uint64_t cap = (uint64_t)kSmCount * 8; // 8 resident CTAs of 256 threads per SM = 64 warps
+    uint64_t cap = (uint64_t)sm_count() * 8; // 8 resident CTAs of 256 threads per SM = 64 warps
     if (want < 1)
         want = 1;
     return (unsigned)(want < cap ? want : cap);
@@ -348,15 +365,19 @@ int bv_build(DevicePool & pool, BvImage & v, uint32_t flags, uint64_t const * wo
                 v.interp[b] = std::atoi(e) != 0;
             v.nsamp[b] = m ? ((m - 1) >> ls) + 1 : 0;
             SG_TRY(pool.alloc_t(&v.samp[b], v.nsamp[b] + 2));
+            // position-valued samples (bv_device.cuh bv_select) while positions >> 5 fit 32 bits
+            v.samp_pos[b] = nbits <= (1ull << 36); // chunk indices (and the + 6 sentinel) stay below 2^32
+            if (char const * e = std::getenv("SDSLGPU_SELECT_POS_SAMPLES")) // A/B knob
+                v.samp_pos[b] = v.samp_pos[b] && std::atoi(e) != 0;
             // sentinel(s): the last block
-            std::vector<uint32_t> tail(2, (uint32_t)(v.nblocks - 1));
+            std::vector<uint32_t> tail(2, (uint32_t)(v.samp_pos[b] ? (v.nblocks - 1) * 7 + 6 : v.nblocks - 1));
             SG_CUDA(cudaMemcpyAsync(v.samp[b] + v.nsamp[b], tail.data(), 8, cudaMemcpyHostToDevice, s));
             if (m)
             {
                 if (b)
-                    bv_samples_kernel<1><<<blocks_for(v.nblocks), kThreads, 0, s>>>(abs_ones, blk_ones, nbits, v.nblocks, ls, v.samp[b], v.nsamp[b]);
+                    bv_samples_kernel<1><<<blocks_for(v.nblocks), kThreads, 0, s>>>(abs_ones, blk_ones, nbits, v.nblocks, ls, v.samp[b], v.nsamp[b], v.blocks, v.samp_pos[b]);
                 else
-                    bv_samples_kernel<0><<<blocks_for(v.nblocks), kThreads, 0, s>>>(abs_ones, blk_ones, nbits, v.nblocks, ls, v.samp[b], v.nsamp[b]);
+                    bv_samples_kernel<0><<<blocks_for(v.nblocks), kThreads, 0, s>>>(abs_ones, blk_ones, nbits, v.nblocks, ls, v.samp[b], v.nsamp[b], v.blocks, v.samp_pos[b]);
                 SG_CUDA(cudaGetLastError());
             }
             SG_CUDA(cudaStreamSynchronize(s)); // `tail` must outlive the copy

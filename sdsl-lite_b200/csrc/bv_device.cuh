@@ -18,6 +18,7 @@ struct BvView
     uint64_t nbits;
     uint64_t ones;
     uint32_t interp[2]; // 1: start the block search at the interpolated position between two samples
+    uint32_t samp_pos[2]; // 1: samp[] holds (position of the sampled bit) >> 5 instead of the index of its block
 };
 
 // number of 1-bits in [0, pos), 0 <= pos <= nbits: one 32-byte sector gather
@@ -66,12 +67,21 @@ __device__ __forceinline__ uint64_t abs_before(bvblock const * __restrict__ bloc
 // this lands in the right sector block 75-90 % of the time on random data; any miss is repaired by walking /
 // bisecting on the block counts, so the result never depends on the guess.
 template <int B>
+__device__ __forceinline__ uint64_t bv_select_from(BvView const & v, uint64_t i, uint64_t lo, uint64_t hi, uint64_t g);
+
+template <int B>
 __device__ __forceinline__ uint64_t bv_select_between(BvView const & v, uint64_t i, uint64_t lo, uint64_t hi, uint64_t r, uint32_t log_span, bool interp)
+{
+    return bv_select_from<B>(v, i, lo, hi, interp ? lo + (((hi - lo) * r + (1ull << log_span >> 1)) >> log_span) : lo);
+}
+
+// the search proper: first probe at block g in [lo, hi], then walk / bisect
+template <int B>
+__device__ __forceinline__ uint64_t bv_select_from(BvView const & v, uint64_t i, uint64_t lo, uint64_t hi, uint64_t g)
 {
     bvblock const * __restrict__ blocks = v.blocks;
     uint64_t const * __restrict__ top = v.top;
     uint32_t cnt, d[7];
-    uint64_t g = interp ? lo + (((hi - lo) * r + (1ull << log_span >> 1)) >> log_span) : lo;
     ld_block(blocks + g, cnt, d);
     uint64_t a1 = __ldg(top + (g >> kSuperShift)) + cnt;
     uint64_t before = B ? a1 : g * kBlockBits - a1;
@@ -156,7 +166,14 @@ __device__ __forceinline__ uint64_t bv_select(BvView const & v, uint64_t i)
         lo = __ldg(samp + j);
         hi = __ldg(samp + j + 1);
     }
-    return bv_select_between<B>(v, i, lo, hi, (i - 1) & ((1ull << log_s) - 1), log_s, v.interp[B] != 0);
+    uint64_t const r = (i - 1) & ((1ull << log_s) - 1);
+    if (v.samp_pos[B])
+    { // position-valued samples: lo / hi are 32-bit chunk indices (224 = 7 * 32: a chunk never straddles two blocks), so
+      // the interpolation is not quantised to whole blocks at either end — first-probe misses 18 % -> 5 % on random data
+        uint64_t p = lo + (((hi - lo) * r + (1ull << log_s >> 1)) >> log_s);
+        return bv_select_from<B>(v, i, lo / 7, hi / 7, p / 7);
+    }
+    return bv_select_between<B>(v, i, lo, hi, r, log_s, v.interp[B] != 0);
 }
 
 } // namespace sdslgpu

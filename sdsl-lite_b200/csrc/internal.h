@@ -37,9 +37,10 @@ int cuda_fail(cudaError_t e, char const * what, char const * file, int line);
             return s__;                                                                                                \
     } while (0)
 
-// grid sizing: B200 has 148 SMs; query kernels are latency-bound gathers, so run a grid-stride loop
-// over 148 x kCtasPerSm resident CTAs of 256 threads (full occupancy at <= 32 registers/thread).
-static constexpr int kSmCount = 148;
+// grid sizing: query kernels are latency-bound gathers, so run a grid-stride loop over sm_count() x 8 resident
+// CTAs of 256 threads (full occupancy at <= 32 registers/thread).  sm_count() = cudaDevAttrMultiProcessorCount of the
+// CURRENT device (148 on a B200), queried once per device and cached (api.cu).
+int sm_count();
 static constexpr int kThreads = 256;
 
 struct DeviceGuard
@@ -121,6 +122,7 @@ struct BvImage
     uint64_t nsamp[2] = {0, 0};
     uint32_t log_s[2] = {6, 6};
     uint32_t interp[2] = {0, 0}; // interpolate between samples (set when the stride exceeds 64)
+    uint32_t samp_pos[2] = {0, 0}; // samples hold (position >> 5) instead of block indices (vectors up to 2^36 bits)
     // optional SDSL layout (SDSLGPU_F_SDSL_LAYOUT): raw words (+ pad) and the m_basic_block tables
     uint64_t * words = nullptr;
     uint64_t nwords = 0;
@@ -139,6 +141,8 @@ inline BvView bv_view(BvImage const & v)
     w.log_s[1] = v.log_s[1];
     w.interp[0] = v.interp[0];
     w.interp[1] = v.interp[1];
+    w.samp_pos[0] = v.samp_pos[0];
+    w.samp_pos[1] = v.samp_pos[1];
     w.nbits = v.nbits;
     w.ones = v.ones;
     return w;

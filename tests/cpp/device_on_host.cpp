@@ -32,10 +32,10 @@ extern "C"
         }
     }
     // out[k] = select_b(i[k]), 1 <= i[k] <= #b-bits, with samples every 2^log_s b-bits
-    void emu_select(uint64_t const * words, uint64_t nbits, int b, uint32_t log_s, uint32_t interp, uint64_t const * i, uint64_t n, uint64_t * out)
+    void emu_select(uint64_t const * words, uint64_t nbits, int b, uint32_t log_s, uint32_t interp, uint32_t pos_mode, uint64_t const * i, uint64_t n, uint64_t * out)
     {
         HostImage im;
-        build(im, words, nbits, log_s, interp);
+        build(im, words, nbits, log_s, interp, pos_mode);
         for (uint64_t k = 0; k < n; ++k)
             out[k] = b ? bv_select<1>(im.view, i[k]) : bv_select<0>(im.view, i[k]);
     }

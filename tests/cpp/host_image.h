@@ -20,7 +20,7 @@ struct HostImage
 
 // the layout of DESIGN.md §3.2 / bv.cu: 224 payload bits per block, cnt = ones since the start of the superblock of
 // 2^24 blocks, top[] = absolute count per superblock; samp[b][j] = block of the (j * S + 1)-th b-bit, two sentinels
-inline void build(HostImage & im, uint64_t const * words, uint64_t nbits, uint32_t log_s, uint32_t interp)
+inline void build(HostImage & im, uint64_t const * words, uint64_t nbits, uint32_t log_s, uint32_t interp, uint32_t pos_mode = 0)
 {
     uint64_t nblocks = nbits / kBlockBits + 1, n32 = (nbits + 31) >> 5;
     uint32_t const * w32 = reinterpret_cast<uint32_t const *>(words);
@@ -51,15 +51,16 @@ inline void build(HostImage & im, uint64_t const * words, uint64_t nbits, uint32
         {
             int bit = (im.blocks[k].d[o >> 5] >> (o & 31)) & 1;
             if ((seen[bit] & ((1ull << log_s) - 1)) == 0)
-                im.samp[bit].push_back((uint32_t)k);
+                im.samp[bit].push_back(pos_mode ? (uint32_t)((first + o) >> 5) : (uint32_t)k);
             ++seen[bit];
             ones += bit;
         }
     }
     for (int b = 0; b < 2; ++b)
     {
-        im.samp[b].push_back((uint32_t)(nblocks - 1));
-        im.samp[b].push_back((uint32_t)(nblocks - 1));
+        im.samp[b].push_back((uint32_t)(pos_mode ? (nblocks - 1) * 7 + 6 : nblocks - 1));
+        im.samp[b].push_back((uint32_t)(pos_mode ? (nblocks - 1) * 7 + 6 : nblocks - 1));
+        im.view.samp_pos[b] = pos_mode;
         im.view.samp[b] = im.samp[b].data();
         im.view.log_s[b] = log_s;
         im.view.interp[b] = interp;

@@ -25,21 +25,6 @@ def test_shim_compiles_and_links(pkg):
     assert os.path.exists(BIN)
 
 
-def test_benchmark_driver_compiles(pkg):
-    """tools/run_queries_b200.cpp — the reference's count / locate benchmark driver (benchmark/indexing_count/src/
-    run_queries_sdsl.cpp) over this engine — builds against the shim and the C ABI and prints its usage"""
-    if not os.path.exists(pkg.LIB_PATH):
-        pkg.build()
-    exe = os.path.join(PKG, "build", "run_queries_b200")
-    os.makedirs(os.path.dirname(exe), exist_ok=True)
-    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", os.path.join(ROOT, "tools", "run_queries_b200.cpp"), "-o", exe, "-L" + PKG, "-lsdslgpu",
-           "-Wl,-rpath," + PKG]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-3000:]
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
-    assert r.returncode == 1 and "usage:" in r.stderr
-
-
 def test_shim_host_only_parts(pkg):
     """bit_vector storage and its serialised form need no device"""
     _build(pkg)

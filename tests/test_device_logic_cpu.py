@@ -28,7 +28,7 @@ def emu():
     L = ctypes.CDLL(SO)
     vp, u64, u32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32
     L.emu_rank1.argtypes = [vp, u64, vp, u64, vp, vp]
-    L.emu_select.argtypes = [vp, u64, ctypes.c_int, u32, u32, vp, u64, vp]
+    L.emu_select.argtypes = [vp, u64, ctypes.c_int, u32, u32, u32, vp, u64, vp]
     L.emu_sel64.argtypes = [u64, u32]
     L.emu_sel64.restype = u32
     return L
@@ -80,7 +80,7 @@ def test_device_rank_and_bit_logic(emu, oracle):
             assert (bit[inside] == bits[idx[inside].astype(np.int64)]).all(), (cid, "bit / rank_and_bit")
 
 
-@pytest.mark.parametrize("interp", [0, 1])
+@pytest.mark.parametrize("interp", [0, 1, 2])  # 2: position-valued samples
 @pytest.mark.parametrize("log_s", [0, 3, 6, 9, 12])
 def test_device_select_logic(emu, oracle, log_s, interp):
     checked = 0
@@ -93,7 +93,7 @@ def test_device_select_logic(emu, oracle, log_s, interp):
             if not len(q):
                 continue
             out = np.zeros(len(q), np.uint64)
-            emu.emu_select(ww.ctypes.data, nbits, b, log_s, interp, q.ctypes.data, len(q), out.ctypes.data)
+            emu.emu_select(ww.ctypes.data, nbits, b, log_s, interp & 1, interp >> 1, q.ctypes.data, len(q), out.ctypes.data)
             assert (out == ob.select(q, b)).all(), (cid, b, log_s, interp)
             checked += len(q)
     assert checked > 100000
