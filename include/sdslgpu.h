@@ -14,12 +14,16 @@
  *  - batch calls take n inputs and write n outputs in the same order;
  *  - input/output pointers may be HOST or DEVICE pointers (detected per pointer with
  *    cudaPointerGetAttributes).  Device pointers must live on the handle's device; the call is
- *    then asynchronous on `stream`.  Host pointers are staged through pinned buffers in chunks
- *    (H2D, kernel and D2H overlapped) and the call returns after the results are in `out`;
+ *    then asynchronous on `stream`.  Host pointers are streamed through per-handle device chunk
+ *    buffers (3 slots x 2^22 queries, allocated on first use; H2D, kernel and D2H overlapped —
+ *    pin the host arrays with cudaHostRegister / cudaHostAlloc to get full PCIe speed) and the
+ *    call returns after the results are in `out`;
  *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream);
  *  - the SDSL preconditions that are undefined behaviour in the reference (rank idx > size,
  *    select i == 0 or i > #args) are DEFINED here: the result for that query is
- *    SDSLGPU_NPOS (all ones) and the call still returns SDSLGPU_OK;
+ *    SDSLGPU_NPOS (all ones) and the call still returns SDSLGPU_OK.  One in-band result of the
+ *    reference is kept instead: select on a KIND_RRR63 handle with i > #args returns size(), as
+ *    select_support_rrr does (rrr_vector.hpp:641-642, 686-689); i == 0 is SDSLGPU_NPOS there too;
  *  - there is NO CPU fallback: without a CUDA device every create call fails with SDSLGPU_ECUDA.
  */
 #ifndef SDSLGPU_H
@@ -142,6 +146,9 @@ int sdslgpu_select(const sdslgpu_handle *h, int b, const uint64_t *i, uint64_t n
 #define SDSLGPU_ORDER_DIRECT 1
 #define SDSLGPU_ORDER_BINNED 2
 int sdslgpu_set_batch_order(sdslgpu_handle *h, int order);
+/* 1 if SDSLGPU_ORDER_AUTO runs a batch of n queries on an index of index_bytes through the binned pipeline, else 0
+ * (for callers that want to report or plan around the choice; no handle, no device needed) */
+int sdslgpu_auto_is_binned(uint64_t index_bytes, uint64_t n);
 
 /* out[k] = bit idx[k] (0/1), 0 <= idx[k] < size.  Replaces operator[] of bit_vector
  * (int_vector.hpp:1900-1904), rrr_vector (rrr_vector.hpp:276-298), sd_vector (sd_vector.hpp:328-349). */
@@ -244,6 +251,14 @@ int sdslgpu_bv_serialize(const sdslgpu_handle *h, int what, void *buf, uint64_t 
  * `blob` is a HOST buffer.  A truncated or inconsistent blob gives SDSLGPU_EINVAL. */
 int sdslgpu_load_sdsl(const void *blob, uint64_t nbytes, int kind, int device, uint32_t flags, uint32_t param,
                       sdslgpu_handle **out);
+/* The same with both sampling densities of a CSA given explicitly — they are template parameters of the reference
+ * (csa_wt.hpp:50-51) and are not stored in the blob: sa_dens = t_dens (0 -> 32), isa_dens = t_inv_dens (0 -> the
+ * default 64 if the ISA sample count matches it, else the power of two that does; a count that no candidate
+ * reproduces, e.g. an index built with t_inv_dens = 100, is SDSLGPU_EINVAL unless isa_dens is passed).  If
+ * consumed != NULL it receives the number of bytes of `blob` the structure occupied, so that a buffer / stream holding
+ * several serialised structures can be read one after the other like the reference's load(std::istream&) does. */
+int sdslgpu_load_sdsl_ex(const void *blob, uint64_t nbytes, int kind, int device, uint32_t flags, uint32_t sa_dens,
+                         uint32_t isa_dens, uint64_t *consumed, sdslgpu_handle **out);
 
 /* Egress: the bytes the reference's serialize() / store_to_file (io.hpp:877-896) writes for the same input, so that
  * an index built here can be stored and loaded by the reference (and by sdslgpu_load_sdsl).  Same buffer protocol as
@@ -269,6 +284,71 @@ int sdslgpu_load_sdsl(const void *blob, uint64_t nbytes, int kind, int device, u
  * Byte-identical to the reference for every non-empty input (tests/test_egress_gpu.py; an EMPTY wt_huff of the
  * reference serialises uninitialised tables, here they are written as "no symbol"). */
 int sdslgpu_serialize(const sdslgpu_handle *h, int what, void *buf, uint64_t cap, uint64_t *nbytes);
+
+/* ---- multi-GPU groups ------------------------------------------------------------------------- */
+
+/* One box, several B200s: the index is REPLICATED on every member of a group, a query batch is SHARDED over the
+ * members (member r answers queries [r*s, (r+1)*s), s = n / nranks; the n - s*nranks left-over queries are answered by
+ * everybody) and the results are ALL-GATHERED, so that after the call every member's `out` holds all n answers
+ * (BASELINE.json north_star; SURVEY.md §8(b) lines 486-489, §8(e)).  The reference has no counterpart: its queries are
+ * scalar const member calls (rank_support_v.hpp:129-139) that a host program spreads over threads itself.
+ *
+ * A group is created either
+ *   - in ONE process driving several devices: sdslgpu_group_create(devices, ndev) -> a group with ndev LOCAL members
+ *     (ncclCommInitAll underneath); or
+ *   - with one process per GPU (torchrun, MPI): rank 0 calls sdslgpu_group_unique_id, ships the 128 bytes to the other
+ *     ranks by any means, and every rank calls sdslgpu_group_create_rank (ncclCommInitRank) -> 1 local member each.
+ * Every group call takes ARRAYS with one entry per LOCAL member (length ndev resp. 1): handles, device pointers,
+ * streams.  Each member's idx array holds ALL n queries (the batch is identical on every member; only the member's
+ * shard is read), each member's out array has room for n results.  All pointers are DEVICE pointers on the member's
+ * device.  streams == NULL: the group's own streams are used and the call returns when the results are complete;
+ * otherwise the call is asynchronous on streams[k].
+ * Group calls are collective: every member (every rank) must make the same calls in the same order.
+ * NCCL is bound at run time (dlopen of the libnccl.so.2 already in the process, else from the loader path or
+ * $SDSLGPU_NCCL_LIB); a box without it gets SDSLGPU_ENOTSUP from the create calls.
+ * Devices listed twice in sdslgpu_group_create give a "loopback" group (several members on one GPU, no NCCL; only
+ * SDSLGPU_GATHER_FUSED / _NONE) — it exists so that the fused path can be tested on a single GPU. */
+typedef struct sdslgpu_group sdslgpu_group;
+#define SDSLGPU_UNIQUE_ID_BYTES 128
+#define SDSLGPU_MAX_GROUP 16
+
+#define SDSLGPU_GATHER_NONE 0  /* no gather: member r's out holds only its shard [r*s, (r+1)*s) and the left-over tail */
+#define SDSLGPU_GATHER_NCCL 1  /* kernels, then ncclAllGather in place on out */
+#define SDSLGPU_GATHER_FUSED 2 /* the shard's last kernel stores every result into ALL members' out arrays over NVLink
+                                  (peer memory); out must come from sdslgpu_group_alloc.  Plain bit vectors: the un-sort
+                                  stage of the binned pipeline does the stores; other ops: a peer-store copy kernel
+                                  behind theirs.  No NCCL call on the data path. */
+#define SDSLGPU_GATHER_AUTO 3  /* FUSED when out is group-allocated and peers can map each other's memory, else NCCL */
+
+int sdslgpu_group_unique_id(void *id128);
+int sdslgpu_group_create_rank(const void *id128, int nranks, int rank, int device, sdslgpu_group **out);
+int sdslgpu_group_create(const int *devices, int ndev, sdslgpu_group **out);
+int sdslgpu_group_free(sdslgpu_group *g);
+/* any of the out pointers may be NULL.  *fused_possible = 1 when the members can store into each other's memory */
+int sdslgpu_group_info(const sdslgpu_group *g, int *nranks, int *nlocal, int *first_rank, int *fused_possible);
+
+/* Symmetric device memory: `bytes` on every member (zero-filled), ptrs[k] = local member k's copy.  Memory from this
+ * call is what SDSLGPU_GATHER_FUSED needs for `out` (every member must pass the same offset into it).  Collective. */
+int sdslgpu_group_alloc(sdslgpu_group *g, uint64_t bytes, void **ptrs);
+int sdslgpu_group_release(sdslgpu_group *g, void *const *ptrs);
+
+/* Replicates the index behind `src` (given on the rank that owns global rank `root`, NULL elsewhere) onto every member:
+ * out[k] = a new handle on local member k's device (the root's member gets its own copy too); free each with
+ * sdslgpu_free.  The index travels in the reference's own serialised form (sdslgpu_serialize -> ncclBroadcast ->
+ * sdslgpu_load_sdsl_ex), so a replica answers exactly like its source.  Collective. */
+int sdslgpu_group_replicate(sdslgpu_group *g, const sdslgpu_handle *src, int root, sdslgpu_handle **out);
+
+/* Sharded forms of sdslgpu_rank / sdslgpu_select (KIND_BV handles, b = 0 / 1), sdslgpu_wt_rank (byte trees: KIND_WT_HUFF,
+ * KIND_CSA_WT) and sdslgpu_fm_count: same results, in the same order, on every member. */
+int sdslgpu_group_rank(sdslgpu_group *g, const sdslgpu_handle *const *h, int b, const uint64_t *const *idx, uint64_t n,
+                       uint64_t *const *out, int gather, void *const *streams);
+int sdslgpu_group_select(sdslgpu_group *g, const sdslgpu_handle *const *h, int b, const uint64_t *const *i, uint64_t n,
+                         uint64_t *const *out, int gather, void *const *streams);
+int sdslgpu_group_wt_rank(sdslgpu_group *g, const sdslgpu_handle *const *h, const uint64_t *const *i, const uint8_t *const *c,
+                          uint64_t n, uint64_t *const *out, int gather, void *const *streams);
+int sdslgpu_group_fm_count(sdslgpu_group *g, const sdslgpu_handle *const *h, const uint8_t *const *pats,
+                           const uint64_t *const *pat_off, uint64_t n, uint64_t *const *cnt_out, int gather,
+                           void *const *streams);
 
 #ifdef __cplusplus
 }

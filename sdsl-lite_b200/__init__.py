@@ -47,6 +47,7 @@ _SIGNATURES = [
     ("sdslgpu_select", C.c_int, [vp, C.c_int, vp, C.c_uint64, vp, vp]),
     ("sdslgpu_access", C.c_int, [vp, vp, C.c_uint64, vp, vp]),
     ("sdslgpu_set_batch_order", C.c_int, [vp, C.c_int]),
+    ("sdslgpu_auto_is_binned", C.c_int, [C.c_uint64, C.c_uint64]),
     ("sdslgpu_bv_serialize", C.c_int, [vp, C.c_int, vp, C.c_uint64, u64p]),
     ("sdslgpu_wt_huff_create", C.c_int, [vp, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(vp)]),
     ("sdslgpu_wt_sigma", C.c_int, [vp, u64p]),
@@ -213,6 +214,11 @@ class _Handle:
         po, o, _k = _out_like(idx, n, out)
         _check(lib().sdslgpu_access(self._h, p, n, po, _stream_ptr(stream, idx)))
         return o
+
+
+def binned_wanted(index_bytes, n):
+    """what SDSLGPU_ORDER_AUTO resolves to for a batch of n queries on an index of index_bytes (sdslgpu_auto_is_binned)"""
+    return bool(lib().sdslgpu_auto_is_binned(int(index_bytes), int(n)))
 
 
 class BitVector(_Handle):
@@ -413,19 +419,22 @@ _SIGNATURES += [
 
 _SIGNATURES += [
     ("sdslgpu_load_sdsl", C.c_int, [vp, C.c_uint64, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
+    ("sdslgpu_load_sdsl_ex", C.c_int, [vp, C.c_uint64, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, u64p, C.POINTER(vp)]),
 ]
 
 
-def load_sdsl(blob, kind, device=0, flags=F_DEFAULT, param=0):
-    """Ingest bytes written by the reference's serialize()/store_to_file -> a handle object of the right class."""
+def load_sdsl(blob, kind, device=0, flags=F_DEFAULT, param=0, isa_dens=0, want_consumed=False):
+    """Ingest bytes written by the reference's serialize()/store_to_file -> a handle object of the right class.
+    param = t_dens of a CSA, isa_dens = its t_inv_dens (0: inferred); want_consumed -> (object, bytes of the blob used)."""
     cls = {KIND_BV: BitVector, KIND_RRR63: RrrVector, KIND_SD: SdVector, KIND_WT_HUFF: WtHuff, KIND_WT_INT: WtInt, KIND_CSA_WT: CsaWt}[kind]
     obj = cls.__new__(cls)
     _Handle.__init__(obj)
     buf = np.frombuffer(blob, dtype=np.uint8)
-    _check(lib().sdslgpu_load_sdsl(buf.ctypes.data, len(buf), kind, device, flags, param, C.byref(obj._h)))
+    used = C.c_uint64(0)
+    _check(lib().sdslgpu_load_sdsl_ex(buf.ctypes.data, len(buf), kind, device, flags, param, isa_dens, C.byref(used), C.byref(obj._h)))
     obj.flags = flags
     obj.nbits = obj.size
-    return obj
+    return (obj, used.value) if want_consumed else obj
 
 
 class WtInt(_Handle, _WaveletTreeOps):
@@ -441,3 +450,171 @@ class WtInt(_Handle, _WaveletTreeOps):
     rank = _WaveletTreeOps.wt_rank
     select = _WaveletTreeOps.wt_select
     access = _WaveletTreeOps.wt_access
+
+
+# ------------------------------------------------------------------------------------------------------
+# multi-GPU groups (include/sdslgpu.h "multi-GPU groups"; csrc/group.cu)
+# ------------------------------------------------------------------------------------------------------
+GATHER_NONE, GATHER_NCCL, GATHER_FUSED, GATHER_AUTO = 0, 1, 2, 3
+UNIQUE_ID_BYTES = 128
+vpp = C.POINTER(vp)
+
+_SIGNATURES += [
+    ("sdslgpu_group_unique_id", C.c_int, [vp]),
+    ("sdslgpu_group_create_rank", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    ("sdslgpu_group_create", C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
+    ("sdslgpu_group_free", C.c_int, [vp]),
+    ("sdslgpu_group_info", C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("sdslgpu_group_alloc", C.c_int, [vp, C.c_uint64, vpp]),
+    ("sdslgpu_group_release", C.c_int, [vp, vpp]),
+    ("sdslgpu_group_replicate", C.c_int, [vp, vp, C.c_int, vpp]),
+    ("sdslgpu_group_rank", C.c_int, [vp, vpp, C.c_int, vpp, C.c_uint64, vpp, C.c_int, vpp]),
+    ("sdslgpu_group_select", C.c_int, [vp, vpp, C.c_int, vpp, C.c_uint64, vpp, C.c_int, vpp]),
+    ("sdslgpu_group_wt_rank", C.c_int, [vp, vpp, vpp, vpp, C.c_uint64, vpp, C.c_int, vpp]),
+    ("sdslgpu_group_fm_count", C.c_int, [vp, vpp, vpp, vpp, C.c_uint64, vpp, C.c_int, vpp]),
+]
+
+
+def group_unique_id():
+    """the 128 bytes rank 0 hands to every other rank before Group.create_rank (ncclGetUniqueId)"""
+    buf = (C.c_uint8 * UNIQUE_ID_BYTES)()
+    _check(lib().sdslgpu_group_unique_id(buf))
+    return bytes(buf)
+
+
+class SymmetricBuffer:
+    """`bytes` of device memory on every local member of a group, mapped by all other members (sdslgpu_group_alloc);
+    tensor(k, dtype) views local member k's copy as a torch tensor without copying"""
+
+    def __init__(self, group, nbytes):
+        self.group, self.nbytes = group, int(nbytes)
+        self.ptrs = (vp * group.nlocal)()
+        _check(lib().sdslgpu_group_alloc(group._g, self.nbytes, self.ptrs))
+
+    def tensor(self, k=0, dtype=None):
+        import torch
+
+        dtype = dtype or torch.int64
+        dev = self.group.devices[k]
+
+        class _Raw:  # the CUDA array interface torch.as_tensor understands
+            pass
+
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (int(self.ptrs[k]), False), "version": 2}
+        t = torch.as_tensor(raw, device=torch.device("cuda", dev))
+        self._keep = getattr(self, "_keep", []) + [raw]
+        return t.view(dtype)
+
+    def release(self):
+        if self.ptrs is not None and self.group._g:
+            _check(lib().sdslgpu_group_release(self.group._g, self.ptrs))
+        self.ptrs = None
+
+
+class Group:
+    """Replicated index, sharded batch, all-gathered results.
+
+    Group.create(devices)           one process, several devices: every call takes LISTS with one entry per device
+    Group.create_rank(id, n, r, d)  one process per GPU (torchrun): lists of length one
+
+    rank / select / wt_rank / fm_count take per-member handle objects and torch CUDA tensors; every member's input holds
+    the WHOLE batch, every member's output receives ALL results.  gather = GATHER_NONE / _NCCL / _FUSED / _AUTO."""
+
+    def __init__(self):
+        self._g = vp()
+        self.devices = []
+
+    @classmethod
+    def create(cls, devices):
+        g = cls()
+        arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+        _check(lib().sdslgpu_group_create(arr, len(devices), C.byref(g._g)))
+        g.devices = [int(d) for d in devices]
+        g._info()
+        return g
+
+    @classmethod
+    def create_rank(cls, unique_id, nranks, rank, device):
+        g = cls()
+        assert len(unique_id) == UNIQUE_ID_BYTES
+        buf = (C.c_uint8 * UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+        _check(lib().sdslgpu_group_create_rank(buf, int(nranks), int(rank), int(device), C.byref(g._g)))
+        g.devices = [int(device)]
+        g._info()
+        return g
+
+    def _info(self):
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _check(lib().sdslgpu_group_info(self._g, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        self.nranks, self.nlocal, self.first_rank, self.fused_possible = a.value, b.value, c.value, bool(d.value)
+
+    def close(self):
+        if self._g:
+            lib().sdslgpu_group_free(self._g)
+            self._g = vp()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def alloc(self, nbytes):
+        return SymmetricBuffer(self, nbytes)
+
+    def replicate(self, src, root=0):
+        """src: a handle object on the process that owns global rank `root` (None elsewhere) -> list of replicas"""
+        out = (vp * self.nlocal)()
+        _check(lib().sdslgpu_group_replicate(self._g, src._h if src is not None else None, int(root), out))
+        res = []
+        for k in range(self.nlocal):
+            kind = C.c_int()
+            h = vp(out[k])
+            _check(lib().sdslgpu_kind(h, C.byref(kind)))
+            cls = {KIND_BV: BitVector, KIND_RRR63: RrrVector, KIND_SD: SdVector, KIND_WT_HUFF: WtHuff, KIND_WT_INT: WtInt, KIND_CSA_WT: CsaWt}[kind.value]
+            obj = cls.__new__(cls)
+            _Handle.__init__(obj)
+            obj._h = h
+            obj.nbits = obj.size
+            res.append(obj)
+        return res
+
+    def _ptrs(self, xs, what):
+        assert len(xs) == self.nlocal, f"{what}: one entry per local member ({self.nlocal})"
+        return (vp * self.nlocal)(*[int(x.data_ptr()) if _is_torch(x) else int(x) for x in xs])
+
+    def _handles(self, hs):
+        assert len(hs) == self.nlocal
+        return (vp * self.nlocal)(*[h._h.value for h in hs])
+
+    def _streams(self, streams):
+        if streams is None:
+            return None
+        return (vp * self.nlocal)(*[int(getattr(s, "cuda_stream", s)) for s in streams])
+
+    def rank(self, hs, b, idx, out, gather=GATHER_AUTO, streams=None):
+        _check(lib().sdslgpu_group_rank(self._g, self._handles(hs), int(b), self._ptrs(idx, "idx"), int(idx[0].numel()), self._ptrs(out, "out"),
+                                        int(gather), self._streams(streams)))
+        return out
+
+    def select(self, hs, b, i, out, gather=GATHER_AUTO, streams=None):
+        _check(lib().sdslgpu_group_select(self._g, self._handles(hs), int(b), self._ptrs(i, "i"), int(i[0].numel()), self._ptrs(out, "out"),
+                                          int(gather), self._streams(streams)))
+        return out
+
+    def wt_rank(self, hs, i, c, out, gather=GATHER_AUTO, streams=None):
+        _check(lib().sdslgpu_group_wt_rank(self._g, self._handles(hs), self._ptrs(i, "i"), self._ptrs(c, "c"), int(i[0].numel()),
+                                           self._ptrs(out, "out"), int(gather), self._streams(streams)))
+        return out
+
+    def fm_count(self, hs, flat, off, out, gather=GATHER_AUTO, streams=None):
+        _check(lib().sdslgpu_group_fm_count(self._g, self._handles(hs), self._ptrs(flat, "pats"), self._ptrs(off, "pat_off"), int(off[0].numel()) - 1,
+                                            self._ptrs(out, "cnt_out"), int(gather), self._streams(streams)))
+        return out

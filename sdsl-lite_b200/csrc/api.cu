@@ -189,8 +189,9 @@ static int run_batch(sdslgpu_handle const * hc, Column const * ins, int nin, Col
     std::lock_guard<std::mutex> lock(h->staging.mu);
     SG_TRY(h->staging.ensure());
     Staging & st = h->staging;
-    if (user)
-        SG_CUDA(cudaStreamSynchronize(user)); // order after the caller's earlier work
+    // order after the caller's earlier work: the staging streams are non-blocking, so not even the legacy default
+    // stream (user == NULL) is implicitly ordered before them
+    SG_CUDA(cudaStreamSynchronize(user));
     uint64_t const chunk = Staging::kChunk;
     uint64_t nchunks = (n + chunk - 1) / chunk;
     int status = SDSLGPU_OK;
@@ -609,6 +610,11 @@ extern "C"
         return SDSLGPU_OK;
     }
 
+    int sdslgpu_auto_is_binned(uint64_t index_bytes, uint64_t n)
+    {
+        return bin_wanted(SDSLGPU_ORDER_AUTO, index_bytes, n) ? 1 : 0;
+    }
+
     int sdslgpu_rank(const sdslgpu_handle * h, int b, const uint64_t * idx, uint64_t n, uint64_t * out, void * stream)
     {
         SG_TRY(check_handle(h));
@@ -790,7 +796,8 @@ extern "C"
         return create_compressed(SDSLGPU_KIND_SD, words, nbits, device, flags, out);
     }
 
-    int sdslgpu_load_sdsl(const void * blob, uint64_t nbytes, int kind, int device, uint32_t flags, uint32_t param, sdslgpu_handle ** out)
+    int sdslgpu_load_sdsl_ex(const void * blob, uint64_t nbytes, int kind, int device, uint32_t flags, uint32_t sa_dens, uint32_t isa_dens,
+                             uint64_t * consumed, sdslgpu_handle ** out)
     {
         if (!out || !blob)
         {
@@ -806,7 +813,7 @@ extern "C"
         sdslgpu_handle * h = nullptr;
         SG_TRY(new_handle(kind, device, flags, &h));
         DeviceGuard g(device);
-        int st = load_sdsl_blob(h, static_cast<uint8_t const *>(blob), nbytes, param, nullptr);
+        int st = load_sdsl_blob(h, static_cast<uint8_t const *>(blob), nbytes, sa_dens, isa_dens, consumed, nullptr);
         if (st != SDSLGPU_OK)
         {
             h->pool.release_all();
@@ -815,6 +822,11 @@ extern "C"
         }
         *out = h;
         return SDSLGPU_OK;
+    }
+
+    int sdslgpu_load_sdsl(const void * blob, uint64_t nbytes, int kind, int device, uint32_t flags, uint32_t param, sdslgpu_handle ** out)
+    {
+        return sdslgpu_load_sdsl_ex(blob, nbytes, kind, device, flags, param, 0, nullptr, out);
     }
 
     int sdslgpu_serialize(const sdslgpu_handle * h, int what, void * buf, uint64_t cap, uint64_t * nbytes)
@@ -828,7 +840,13 @@ extern "C"
         sdslgpu_handle * hm = const_cast<sdslgpu_handle *>(h);
         std::lock_guard<std::mutex> lock(hm->ser_mu);
         std::vector<uint8_t> blob;
-        if (hm->ser_what == what && buf)
+        bool const fetch = hm->ser_what == what && buf;
+        if (!fetch && hm->ser_what != -1)
+        { // a size query whose blob was never fetched: dropped by the next call instead of living as long as the handle
+            std::vector<uint8_t>().swap(hm->ser_blob);
+            hm->ser_what = -1;
+        }
+        if (fetch)
         { // the size query before this call already built it
             blob.swap(hm->ser_blob);
             hm->ser_what = -1;

@@ -201,12 +201,16 @@ __global__ void __launch_bounds__(kTileThreads, 2) bin_tile_sort_kernel(uint64_t
 // ------------------------------------------------------------------------------------------------
 // 3. back to the caller's order
 // ------------------------------------------------------------------------------------------------
+// kFan: every result is also stored to the same index of the other group members' result arrays (peer memory over
+// NVLink): each warp's store is 256 contiguous bytes per destination.
+template <bool kFan>
 __global__ void __launch_bounds__(kTileThreads, 2) bin_unsort_kernel(uint64_t const * __restrict__ res,
                                                                      uint16_t const * __restrict__ lp,
                                                                      uint16_t const * __restrict__ loff,
                                                                      uint32_t nb,
                                                                      uint64_t n,
-                                                                     uint64_t * __restrict__ out)
+                                                                     uint64_t * __restrict__ out,
+                                                                     Fan const fan)
 {
     extern __shared__ __align__(16) uint8_t unsort_smem[];
     uint64_t * sres = reinterpret_cast<uint64_t *>(unsort_smem);
@@ -228,7 +232,13 @@ __global__ void __launch_bounds__(kTileThreads, 2) bin_unsort_kernel(uint64_t co
     {
         uint64_t p = first + (uint64_t)u * kTileThreads + tid;
         if (p < n)
-            st_stream_u64(out + p, l[u] < nvalid ? sres[l[u]] : SDSLGPU_NPOS);
+        {
+            uint64_t const v = l[u] < nvalid ? sres[l[u]] : SDSLGPU_NPOS;
+            st_stream_u64(out + p, v);
+            if (kFan)
+                for (uint32_t r = 0; r < fan.n; ++r)
+                    fan.dst[r][p] = v;
+        }
     }
 }
 
@@ -326,11 +336,18 @@ int bin_launch_tile_sort(BinPlan const & p, BinScratch const & w, uint64_t const
     return SDSLGPU_OK;
 }
 
-int bin_launch_unsort(BinPlan const & p, BinScratch const & w, uint64_t n, uint64_t * out, cudaStream_t s)
+int bin_launch_unsort(BinPlan const & p, BinScratch const & w, uint64_t n, uint64_t * out, cudaStream_t s, Fan const * fan)
 {
     // 64 KB of dynamic shared memory for the result tile (attribute is per device / context: set on every call)
-    SG_CUDA(cudaFuncSetAttribute(bin_unsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTile * 8)));
-    bin_unsort_kernel<<<(unsigned)p.ntiles, kTileThreads, kTile * 8, s>>>(w.res, w.lp, w.loff, p.nb, n, out);
+    if (fan && fan->n)
+    {
+        SG_CUDA(cudaFuncSetAttribute(bin_unsort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTile * 8)));
+        bin_unsort_kernel<true><<<(unsigned)p.ntiles, kTileThreads, kTile * 8, s>>>(w.res, w.lp, w.loff, p.nb, n, out, *fan);
+        SG_CUDA(cudaGetLastError());
+        return SDSLGPU_OK;
+    }
+    SG_CUDA(cudaFuncSetAttribute(bin_unsort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTile * 8)));
+    bin_unsort_kernel<false><<<(unsigned)p.ntiles, kTileThreads, kTile * 8, s>>>(w.res, w.lp, w.loff, p.nb, n, out, Fan{});
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
 }
@@ -395,23 +412,23 @@ bool bv_binned_wanted(BvImage const & v, uint64_t n)
     return bin_wanted(v.order, v.nblocks * sizeof(bvblock), n);
 }
 
-int bv_rank_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done)
+int bv_rank_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done, Fan const * fan)
 {
     uint64_t bytes = v.nblocks * sizeof(bvblock);
     if (b)
-        return bin_run(BvRankOp<1>{bv_view(v)}, bytes, 0, v.nbits, idx, n, out, s, done);
-    return bin_run(BvRankOp<0>{bv_view(v)}, bytes, 0, v.nbits, idx, n, out, s, done);
+        return bin_run(BvRankOp<1>{bv_view(v)}, bytes, 0, v.nbits, idx, n, out, s, done, false, fan);
+    return bin_run(BvRankOp<0>{bv_view(v)}, bytes, 0, v.nbits, idx, n, out, s, done, false, fan);
 }
 
-int bv_select_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done)
+int bv_select_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done, Fan const * fan)
 {
     *done = false;
     uint64_t args = b ? v.ones : v.nbits - v.ones, bytes = v.nblocks * sizeof(bvblock);
     if (args == 0)
         return SDSLGPU_OK; // every query is out of domain: the direct kernel answers NPOS
     if (b)
-        return bin_run(BvSelectOp<1>{bv_view(v)}, bytes, 1, args - 1, idx, n, out, s, done);
-    return bin_run(BvSelectOp<0>{bv_view(v)}, bytes, 1, args - 1, idx, n, out, s, done);
+        return bin_run(BvSelectOp<1>{bv_view(v)}, bytes, 1, args - 1, idx, n, out, s, done, false, fan);
+    return bin_run(BvSelectOp<0>{bv_view(v)}, bytes, 1, args - 1, idx, n, out, s, done, false, fan);
 }
 
 } // namespace sdslgpu

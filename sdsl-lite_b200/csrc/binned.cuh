@@ -13,7 +13,9 @@
 //   2. bin_apply_kernel<Op>   warps take (bin, tile) runs from a global ticket counter in BIN-MAJOR order, so at any
 //                             moment the whole GPU gathers from one or two chunks: L2 hits after the first touch, and
 //                             the index is read from DRAM once per batch.  Results go to the runs' own slots.
-//   3. bin_unsort_kernel      one CTA per tile: the tile's results (contiguous) -> shared memory -> caller's order.
+//   3. bin_unsort_kernel      one CTA per tile: the tile's results (contiguous) -> shared memory -> caller's order
+//                             (multi-GPU group calls: and, with the same coalesced stores, into the result arrays of
+//                             every other member of the group over NVLink — the all-gather fused into this stage).
 //
 // No global sort, no scan across tiles; deterministic results.  ~22 B per query of extra coalesced streams next to
 // the 16 B of query + result every path moves.  (Storing rank results as u32 differences to the bin's first rank
@@ -59,7 +61,7 @@ bool bin_make_plan(uint64_t index_bytes, uint64_t maxkey, uint64_t n, BinPlan & 
 bool bin_wanted(int order, uint64_t index_bytes, uint64_t n);
 int bin_scratch_alloc(BinScratch & w, BinPlan const & p, cudaStream_t s);
 int bin_launch_tile_sort(BinPlan const & p, BinScratch const & w, uint64_t const * q, uint64_t n, uint64_t sub, uint64_t maxkey, bool clamp, cudaStream_t s);
-int bin_launch_unsort(BinPlan const & p, BinScratch const & w, uint64_t n, uint64_t * out, cudaStream_t s);
+int bin_launch_unsort(BinPlan const & p, BinScratch const & w, uint64_t n, uint64_t * out, cudaStream_t s, Fan const * fan = nullptr);
 unsigned bin_apply_grid(BinPlan const & p);
 
 // Op: plain-old-data functor with
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(kThreads, Op::kMinCtas) bin_apply_kernel(Op op
 // *done = false (and nothing launched) when the plan does not fit (shift > 32, tile count overflow).
 template <class Op>
 int bin_run(Op const & op, uint64_t index_bytes, uint64_t sub, uint64_t maxkey, uint64_t const * q, uint64_t n, uint64_t * out, cudaStream_t s, bool * done,
-            bool clamp_high = false)
+            bool clamp_high = false, Fan const * fan = nullptr)
 {
     *done = false;
     BinPlan p;
@@ -140,7 +142,7 @@ int bin_run(Op const & op, uint64_t index_bytes, uint64_t sub, uint64_t maxkey, 
         SG_CUDA(cudaFuncSetAttribute(bin_apply_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Op::kSmem));
     bin_apply_kernel<Op><<<bin_apply_grid(p), kThreads, Op::kSmem, s>>>(op, w.recs, w.loff, p.shift, p.nb, p.ntiles, w.ticket, w.res);
     SG_CUDA(cudaGetLastError());
-    SG_TRY(bin_launch_unsort(p, w, n, out, s));
+    SG_TRY(bin_launch_unsort(p, w, n, out, s, fan));
     *done = true;
     return SDSLGPU_OK;
 }

@@ -493,16 +493,22 @@ int bv_build_sdsl_rank_table(DevicePool & pool, BvImage & v, int b, cudaStream_t
     return SDSLGPU_OK;
 }
 
-int bv_rank_device(BvImage const & v, uint32_t flags, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)
+int bv_rank_device(BvImage const & v, uint32_t flags, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, Fan const * fan, bool * fanned)
 {
+    if (fanned)
+        *fanned = false;
     if (n == 0)
         return SDSLGPU_OK;
     if (!(flags & SDSLGPU_F_SDSL_LAYOUT) && bv_binned_wanted(v, n))
     {
         bool done = false;
-        SG_TRY(bv_rank_binned_device(v, b, idx, n, out, s, &done));
+        SG_TRY(bv_rank_binned_device(v, b, idx, n, out, s, &done, fan));
         if (done)
+        {
+            if (fanned)
+                *fanned = fan && fan->n;
             return SDSLGPU_OK;
+        }
     }
     constexpr int ILP = 2;
     unsigned grid = grid_for(n, ILP);
@@ -524,8 +530,10 @@ int bv_rank_device(BvImage const & v, uint32_t flags, int b, uint64_t const * id
     return SDSLGPU_OK;
 }
 
-int bv_select_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)
+int bv_select_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, Fan const * fan, bool * fanned)
 {
+    if (fanned)
+        *fanned = false;
     if (n == 0)
         return SDSLGPU_OK;
     if (v.samp[b] == nullptr)
@@ -536,9 +544,13 @@ int bv_select_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n,
     if (bv_binned_wanted(v, n))
     {
         bool done = false;
-        SG_TRY(bv_select_binned_device(v, b, idx, n, out, s, &done));
+        SG_TRY(bv_select_binned_device(v, b, idx, n, out, s, &done, fan));
         if (done)
+        {
+            if (fanned)
+                *fanned = fan && fan->n;
             return SDSLGPU_OK;
+        }
     }
     unsigned grid = grid_for(n);
     uint64_t args = b ? v.ones : v.nbits - v.ones;

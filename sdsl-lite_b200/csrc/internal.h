@@ -92,6 +92,16 @@ struct Staging
     void destroy();
 };
 
+// Result fan-out of the multi-GPU group calls (group.cu): a kernel that writes out[p] also stores the same value to
+// dst[r][p] for r < n — the `out` arrays of the other members of the group, mapped through CUDA IPC / peer access, so
+// the all-gather of results rides on the kernel's own stores over NVLink instead of a separate collective.
+static constexpr int kMaxFan = 15;
+struct Fan
+{
+    uint64_t * dst[kMaxFan];
+    uint32_t n = 0;
+};
+
 enum class PtrSpace
 {
     Host,
@@ -304,13 +314,18 @@ inline RrrBits rrr_bits(WtHuffImage const & w)
 int bv_build(DevicePool & pool, BvImage & v, uint32_t flags, uint64_t const * words_host_or_dev, bool words_on_device, uint64_t nbits, cudaStream_t s);
 int bv_build_sdsl_rank_table(DevicePool & pool, BvImage & v, int b, cudaStream_t s, bool v5 = false);
 int bv_build_pattern(DevicePool & pool, BvImage const & src, int pat, BvImage & dst, cudaStream_t s);
-int bv_rank_device(BvImage const & v, uint32_t flags, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
-int bv_select_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
+// fan / fanned: optional result fan-out (see Fan); *fanned tells whether the kernels that ran did the remote stores
+// (the binned pipeline's un-sort does; after a direct kernel the caller copies the shard itself)
+int bv_rank_device(BvImage const & v, uint32_t flags, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, Fan const * fan = nullptr,
+                   bool * fanned = nullptr);
+int bv_select_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, Fan const * fan = nullptr,
+                     bool * fanned = nullptr);
 int bv_access_device(BvImage const & v, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 // binned.cu: locality-ordered execution of large batches; *done = false means "not applicable, use the direct kernel"
 bool bv_binned_wanted(BvImage const & v, uint64_t n);
-int bv_rank_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done);
-int bv_select_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done);
+bool bin_wanted(int order, uint64_t index_bytes, uint64_t n);
+int bv_rank_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done, Fan const * fan = nullptr);
+int bv_select_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done, Fan const * fan = nullptr);
 // wt.cu
 int wt_huff_upload(sdslgpu_handle * h, uint64_t size, uint64_t sigma, WtTree const & tree, uint64_t const * bv_words, uint64_t bv_bits, cudaStream_t s);
 int wt_huff_finish(sdslgpu_handle * h, uint64_t size, uint64_t sigma, WtTree const & tree, cudaStream_t s);
@@ -341,7 +356,7 @@ int rrr_rank_image(RrrImage const & r, int b, uint64_t const * idx, uint64_t n, 
 int rrr_records_from_sdsl(DevicePool & pool, RrrImage & r, uint64_t const * bt_words, uint64_t nblocks, std::vector<uint64_t> const & rank,
                           std::vector<uint64_t> const & btnrp, std::vector<uint8_t> const & invert, uint64_t total_bits_hint, cudaStream_t s);
 // sdsl_format.cu
-int load_sdsl_blob(sdslgpu_handle * h, uint8_t const * blob, uint64_t nbytes, uint32_t sa_dens, cudaStream_t s);
+int load_sdsl_blob(sdslgpu_handle * h, uint8_t const * blob, uint64_t nbytes, uint32_t sa_dens, uint32_t isa_dens, uint64_t * consumed, cudaStream_t s);
 // sd.cu
 int sd_build(sdslgpu_handle * h, uint64_t const * words_host_or_dev, bool on_device, uint64_t nbits, cudaStream_t s);
 int sd_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);

@@ -157,7 +157,8 @@ int load_rrr_image(DevicePool & pool, RrrImage & im, Reader & r, cudaStream_t s)
 {
     im.size = r.u64();
     IntVec bt, btnr, btnrp, rank, inv;
-    if (!read_iv(r, bt) || !read_iv(r, btnr) || !read_iv(r, btnrp) || !read_iv(r, rank) || !read_iv(r, inv) || bt.width != 6 || btnr.width != 1)
+    if (!read_iv(r, bt) || !read_iv(r, btnr) || !read_iv(r, btnrp) || !read_iv(r, rank) || !read_iv(r, inv) || bt.width != 6 || btnr.width != 1 ||
+        inv.width != 1 || rank.width == 0 || rank.width > 64 || btnrp.width == 0 || btnrp.width > 64 || rank.size() == 0)
         return malformed("rrr_vector<63>");
     im.nblocks = bt.size();
     im.nsuper = btnrp.size();
@@ -173,7 +174,12 @@ int load_rrr_image(DevicePool & pool, RrrImage & im, Reader & r, cudaStream_t s)
         rk[g] = rank.get(g);
         bp[g] = btnrp.get(g);
         iv[g] = (uint8_t)inv.get(g);
+        // offsets into m_btnr must be non-decreasing and inside it; the sampled ranks non-decreasing and <= size
+        if (bp[g] > btnr.bits || (g && bp[g] < bp[g - 1]) || rk[g] > im.size || (g && rk[g] < rk[g - 1]))
+            return malformed("rrr_vector<63> (superblock samples out of range)");
     }
+    if (im.ones > im.size || (im.nsuper && im.ones < rk[im.nsuper - 1]))
+        return malformed("rrr_vector<63> (rank samples)");
     // the blob does not store the exact number of offset bits (m_btnr is padded to >= 64 bits); only its top bit
     // matters (it fixes the width of m_btnrp when serialising back), and m_btnrp's width preserves that
     uint64_t total_bits_hint = btnrp.width ? (1ull << (btnrp.width - 1)) : 0;
@@ -203,6 +209,16 @@ int load_sd(sdslgpu_handle * h, Reader & r, cudaStream_t s)
         return malformed("sd_vector");
     d.m = low.size();
     d.high_bits = high.bits;
+    {
+        uint64_t ones = 0;
+        for (uint64_t k = 0; k < (high.bits >> 6); ++k)
+            ones += (uint64_t)__builtin_popcountll(high.words[k]);
+        if (high.bits & 63)
+            ones += (uint64_t)__builtin_popcountll(high.words[high.bits >> 6] & ((1ull << (high.bits & 63)) - 1));
+        // sd_vector.hpp:236-253: one 1 per element plus one 0 per bucket of 2^wl positions
+        if (d.wl > 63 || ones != d.m || high.bits < d.m || ((high.bits - d.m) << d.wl) < d.size)
+            return malformed("sd_vector (m_high does not match m_low / size)");
+    }
     d.low_words = low.words.size() + 1;
     std::vector<uint64_t> lw(d.low_words, 0);
     std::memcpy(lw.data(), low.words.data(), low.words.size() * 8);
@@ -247,6 +263,22 @@ int load_wt_huff(sdslgpu_handle * h, Reader & r, cudaStream_t s)
         tree.path[c] = r.u64();
     if (!r.ok)
         return malformed("wt_huff (byte_tree)");
+    {
+        uint64_t const bits = over_rrr ? h->wt.rrr.size : bv.bits;
+        for (uint64_t v = 0; v < nn; ++v)
+        {
+            bool const idx_ok = (tree.parent[v] == 0xFFFF || tree.parent[v] < nn) && (tree.child[v][0] == 0xFFFF || tree.child[v][0] < nn) &&
+                                (tree.child[v][1] == 0xFFFF || tree.child[v][1] < nn);
+            if (!idx_ok || tree.bv_pos[v] > bits || tree.bv_pos_rank[v] > tree.bv_pos[v] || (v && tree.bv_pos[v] < tree.bv_pos[v - 1]))
+                return malformed("wt_huff (byte_tree node out of range)");
+        }
+        for (int c = 0; c < 256 && size; ++c)
+            if (tree.c_to_leaf[c] != 0xFFFF && tree.c_to_leaf[c] >= nn)
+                return malformed("wt_huff (c_to_leaf out of range)");
+        for (int c = 0; c < 256 && size; ++c)
+            if ((tree.path[c] >> 56) > 56)
+                return malformed("wt_huff (code longer than 56 bits)");
+    }
     if (size == 0)
         for (int c = 0; c < 256; ++c)
             tree.c_to_leaf[c] = 0xFFFF; // an empty reference tree serialises uninitialised tables
@@ -264,20 +296,20 @@ int load_wt_int(sdslgpu_handle * h, Reader & r, cudaStream_t s)
     if (!read_iv(r, tree) || tree.width != 1 || !skip_iv(r) || !skip_select_mcl(r) || !skip_select_mcl(r))
         return malformed("wt_int");
     w.max_level = r.u32();
-    if (!r.ok || (uint64_t)w.max_level * w.size != tree.bits)
+    if (!r.ok || w.max_level > 64 || (uint64_t)w.max_level * w.size != tree.bits || (w.size && w.max_level == 0))
         return malformed("wt_int (level count)");
     return bv_build(h->pool, w.tree, h->flags & ~SDSLGPU_F_NO_SELECT, tree.words.data(), false, tree.bits, s);
 }
 
-int load_csa(sdslgpu_handle * h, Reader & r, uint32_t sa_dens, cudaStream_t s)
+int load_csa(sdslgpu_handle * h, Reader & r, uint32_t sa_dens, uint32_t isa_dens, cudaStream_t s)
 {
     SG_TRY(load_wt_huff(h, r, s));
     IntVec sa, isa, c2c, comp2char, C;
     if (!read_iv(r, sa) || !read_iv(r, isa) || !read_iv(r, c2c) || !read_iv(r, comp2char) || !read_iv(r, C) || c2c.width != 8 || c2c.size() != 256 ||
-        C.width != 64)
+        C.width != 64 || comp2char.width != 8 || sa.width == 0 || sa.width > 64 || (isa.bits && (isa.width == 0 || isa.width > 64)))
         return malformed("csa_wt");
     uint16_t sigma = r.u16();
-    if (!r.ok || C.size() != (uint64_t)sigma + 1 || sigma > 256)
+    if (!r.ok || C.size() != (uint64_t)sigma + 1 || sigma > 256 || comp2char.size() < sigma)
         return malformed("csa_wt (alphabet)");
     CsaImage & c = h->csa;
     c.n = h->wt.size;
@@ -306,17 +338,39 @@ int load_csa(sdslgpu_handle * h, Reader & r, uint32_t sa_dens, cudaStream_t s)
     SG_TRY(h->pool.alloc_t(&c.tab, 1));
     SG_CUDA(cudaMemcpyAsync(c.tab, &c.host_tab, sizeof(FmTables), cudaMemcpyHostToDevice, s));
     SG_CUDA(cudaStreamSynchronize(s));
-    // ISA samples (t_inv_dens is not stored: inferred from the sample count, csa_sampling_strategy.hpp:762-763)
+    // ISA samples: isa.size() == (n - 1) / t_inv_dens + 1 (csa_sampling_strategy.hpp:762-763).  t_inv_dens is a
+    // template parameter of the reference and is not stored: sdslgpu_load_sdsl_ex takes it; without it (0) the default
+    // 64, then the powers of two are tried, and a count no candidate reproduces is an error, never a guess.
     std::vector<uint64_t> isav(isa.size() + 1, 0);
     for (uint64_t k = 0; k < isa.size(); ++k)
         isav[k] = isa.get(k);
-    c.isa_dens = 64;
-    if (isa.size() && isa.size() != (c.n - 1) / 64 + 1)
+    if (c.n == 0 || isa.size() == 0)
+        return malformed("csa_wt (no ISA samples)");
+    auto isa_count = [&](uint64_t d) { return (c.n - 1) / d + 1; };
+    if (isa_dens)
     {
-        uint32_t d = 1;
-        while (d < (1u << 20) && (c.n - 1) / d + 1 != isa.size())
-            d <<= 1;
-        c.isa_dens = d;
+        if (isa_count(isa_dens) != isa.size())
+        {
+            set_error("sdslgpu_load_sdsl: %llu ISA samples do not match size %llu at t_inv_dens %u", (unsigned long long)isa.size(), (unsigned long long)c.n,
+                      isa_dens);
+            return SDSLGPU_EINVAL;
+        }
+        c.isa_dens = isa_dens;
+    }
+    else
+    {
+        uint64_t d = 64;
+        if (isa_count(d) != isa.size())
+            for (d = 1; d <= (1ull << 32) && isa_count(d) != isa.size(); d <<= 1)
+            {}
+        if (d > (1ull << 32))
+        {
+            set_error("sdslgpu_load_sdsl: cannot infer t_inv_dens from %llu ISA samples (size %llu): not a power of two — pass it to sdslgpu_load_sdsl_ex",
+                      (unsigned long long)isa.size(), (unsigned long long)c.n);
+            return SDSLGPU_EINVAL;
+        }
+        // several densities can give the same count when n is small; any of them indexes the samples that exist
+        c.isa_dens = (uint32_t)(d > 0xFFFFFFFFull ? 0x80000000u : d);
     }
     SG_TRY(csa_upload_isa(h, isav.data(), isa.size(), s));
     // the searches' one-hot occurrence bitmaps, decoded from the ingested tree (fm16.cu) unless a compact index was asked for
@@ -327,26 +381,47 @@ int load_csa(sdslgpu_handle * h, Reader & r, uint32_t sa_dens, cudaStream_t s)
 
 } // namespace
 
-int load_sdsl_blob(sdslgpu_handle * h, uint8_t const * blob, uint64_t nbytes, uint32_t sa_dens, cudaStream_t s)
+// the select supports behind sd_vector's m_high (sd_vector.hpp:434-435) and the end of the other structures
+static int finish_tail(sdslgpu_handle * h, Reader & r)
+{
+    if (h->kind == SDSLGPU_KIND_SD && (!skip_select_mcl(r) || !skip_select_mcl(r)))
+        r.ok = true, r.pos = r.n; // older callers pass only size, wl, low, high: the supports are optional on ingest
+    return SDSLGPU_OK;
+}
+
+int load_sdsl_blob(sdslgpu_handle * h, uint8_t const * blob, uint64_t nbytes, uint32_t sa_dens, uint32_t isa_dens, uint64_t * consumed, cudaStream_t s)
 {
     Reader r{blob, nbytes};
+    int st = SDSLGPU_EINVAL;
     switch (h->kind)
     {
     case SDSLGPU_KIND_BV:
-        return load_bv(h, r, s);
+        st = load_bv(h, r, s);
+        break;
     case SDSLGPU_KIND_RRR63:
-        return load_rrr(h, r, s);
+        st = load_rrr(h, r, s);
+        break;
     case SDSLGPU_KIND_SD:
-        return load_sd(h, r, s);
+        st = load_sd(h, r, s);
+        if (st == SDSLGPU_OK)
+            st = finish_tail(h, r);
+        break;
     case SDSLGPU_KIND_WT_HUFF:
-        return load_wt_huff(h, r, s);
+        st = load_wt_huff(h, r, s);
+        break;
     case SDSLGPU_KIND_WT_INT:
-        return load_wt_int(h, r, s);
+        st = load_wt_int(h, r, s);
+        break;
     case SDSLGPU_KIND_CSA_WT:
-        return load_csa(h, r, sa_dens ? sa_dens : 32, s);
+        st = load_csa(h, r, sa_dens ? sa_dens : 32, isa_dens, s);
+        break;
+    default:
+        set_error("sdslgpu_load_sdsl: unknown kind %d", h->kind);
+        return SDSLGPU_EINVAL;
     }
-    set_error("sdslgpu_load_sdsl: unknown kind %d", h->kind);
-    return SDSLGPU_EINVAL;
+    if (st == SDSLGPU_OK && consumed)
+        *consumed = r.pos; // bytes of the structure itself: a stream holding several structures continues here
+    return st;
 }
 
 } // namespace sdslgpu

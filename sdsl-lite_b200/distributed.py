@@ -18,6 +18,16 @@ def shard_sizes(n, world):
     return [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
 
 
+def _gather_device(group=None):
+    """where collective buffers must live: the current CUDA device under the NCCL backend, the host under gloo"""
+    import torch
+    import torch.distributed as dist
+
+    if dist.is_initialized() and dist.get_backend(group) == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
 def sharded_query(fn, columns, group=None, gather=True):
     """Answer a batch split across the ranks of `group`.
 
@@ -36,7 +46,10 @@ def sharded_query(fn, columns, group=None, gather=True):
     if not gather or world == 1:
         return local
     was_numpy = isinstance(local, np.ndarray)
-    t = torch.from_numpy(local.view(np.int64)) if was_numpy else local
+    t = torch.from_numpy(np.ascontiguousarray(local).view(np.int64)) if was_numpy else local
+    dev = _gather_device(group)
+    if t.device.type != dev.type:  # host results under NCCL (or device results under gloo): the collective decides
+        t = t.to(dev)
     sizes = shard_sizes(n, world)
     pad = max(sizes)
     buf = torch.zeros(pad, dtype=t.dtype, device=t.device)
@@ -44,7 +57,13 @@ def sharded_query(fn, columns, group=None, gather=True):
     parts = [torch.empty(pad, dtype=t.dtype, device=t.device) for _ in range(world)]
     dist.all_gather(parts, buf, group=group)
     full = torch.cat([p[:s] for p, s in zip(parts, sizes)])
-    return full.numpy().view(np.uint64) if was_numpy else full
+    return full.cpu().numpy().view(np.uint64) if was_numpy else full
+
+
+def _to_numpy_u64(x):
+    if isinstance(x, np.ndarray):
+        return x
+    return x.cpu().numpy().view(np.uint64)
 
 
 def sharded_locate(count_fn, locate_fn, flat, off, group=None):
@@ -63,22 +82,24 @@ def sharded_locate(count_fn, locate_fn, flat, off, group=None):
     occ_off, occ = locate_fn(local_flat, local_off)
     if world == 1:
         return occ_off, occ
-    cnt = np.diff(occ_off.astype(np.int64))
     sizes = shard_sizes(n, world)
     # 1) all-gather the per-pattern counts (padded), 2) all-gather the occurrences (padded to the largest shard)
+    dev = _gather_device(group)
+    occ_off, occ = _to_numpy_u64(occ_off), _to_numpy_u64(occ)
+    cnt = np.diff(occ_off.astype(np.int64))
     cpad = max(sizes)
-    cbuf = torch.zeros(cpad, dtype=torch.int64)
-    cbuf[: hi - lo] = torch.from_numpy(cnt)
-    cparts = [torch.empty(cpad, dtype=torch.int64) for _ in range(world)]
+    cbuf = torch.zeros(cpad, dtype=torch.int64, device=dev)
+    cbuf[: hi - lo] = torch.from_numpy(cnt).to(dev)
+    cparts = [torch.empty(cpad, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(cparts, cbuf, group=group)
-    all_cnt = torch.cat([p[:s] for p, s in zip(cparts, sizes)]).numpy()
+    all_cnt = torch.cat([p[:s] for p, s in zip(cparts, sizes)]).cpu().numpy()
     totals = [int(p[:s].sum()) for p, s in zip(cparts, sizes)]
     opad = max(max(totals), 1)
-    obuf = torch.zeros(opad, dtype=torch.int64)
-    obuf[: len(occ)] = torch.from_numpy(np.ascontiguousarray(occ).view(np.int64))
-    oparts = [torch.empty(opad, dtype=torch.int64) for _ in range(world)]
+    obuf = torch.zeros(opad, dtype=torch.int64, device=dev)
+    obuf[: len(occ)] = torch.from_numpy(np.ascontiguousarray(occ).view(np.int64)).to(dev)
+    oparts = [torch.empty(opad, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(oparts, obuf, group=group)
-    full_occ = torch.cat([p[:t] for p, t in zip(oparts, totals)]).numpy().view(np.uint64)
+    full_occ = torch.cat([p[:t] for p, t in zip(oparts, totals)]).cpu().numpy().view(np.uint64)
     full_off = np.zeros(n + 1, dtype=np.uint64)
     full_off[1:] = np.cumsum(all_cnt).astype(np.uint64)
     return full_off, full_occ

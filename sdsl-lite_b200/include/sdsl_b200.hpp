@@ -90,12 +90,23 @@ inline void skip_int_vector(std::istream & in)
     if (!in)
         throw std::runtime_error("load: truncated stream");
 }
-inline handle_ptr load_blob(std::istream & in, int kind, uint32_t flags, uint32_t param)
+// Like the reference's load(std::istream&): consumes exactly the structure's bytes.  The library parses from a
+// buffer, so the rest of the stream is read, sdslgpu_load_sdsl_ex reports how much of it the structure occupied, and
+// the stream is put back right behind it (a stream that cannot seek keeps the old behaviour: read to its end).
+inline handle_ptr load_blob(std::istream & in, int kind, uint32_t flags, uint32_t param, uint32_t isa_dens = 0)
 {
+    std::istream::pos_type const start = in.tellg();
     std::vector<char> blob((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>()); // the rest of the stream
     sdslgpu_handle * h = nullptr;
-    check(sdslgpu_load_sdsl(blob.data(), blob.size(), kind, default_device(), flags, param, &h), "load");
-    return adopt(h);
+    uint64_t used = 0;
+    check(sdslgpu_load_sdsl_ex(blob.data(), blob.size(), kind, default_device(), flags, param, isa_dens, &used, &h), "load");
+    handle_ptr p = adopt(h);
+    if (start != std::istream::pos_type(-1))
+    {
+        in.clear();
+        in.seekg(start + (std::streamoff)used);
+    }
+    return p;
 }
 } // namespace detail
 
