@@ -318,17 +318,21 @@ def main():
 
     variants = {}
     shard_q = nq // world
-    binned = args.order == "binned" or (args.order == "auto" and pkg.binned_wanted(index_bytes, shard_q if world > 1 else nq))
+    per_call = shard_q if world > 1 else nq
+    binned_r = args.order == "binned" or (args.order == "auto" and pkg.binned_wanted(index_bytes, per_call, select=False))
+    binned_s = args.order == "binned" or (args.order == "auto" and pkg.binned_wanted(index_bytes, per_call, select=True))
+    kernels_per_step = (3 if binned_r else 1) + (3 if binned_s else 1)
     if world == 1:
         main_t = timed(plain_step, args.steps, args.warmup, clocks=True)
         main_name = "single GPU"
-        launches_per_step = 6 if binned else 2
+        launches_per_step = kernels_per_step
     else:
         fused = group.fused_possible
         main_gather = pkg.GATHER_FUSED if fused else pkg.GATHER_NCCL
         main_name = "fused: peer stores over NVLink from the last kernel of each shard" if fused else "ncclAllGather after the shard kernels"
         main_t = timed(group_step(main_gather), args.steps, args.warmup, clocks=True)
-        launches_per_step = (6 if binned else 2) + (4 if fused else 0) + (2 if fused and not binned else 0)
+        # fused: 2 flag-exchange kernels per op; the shard kernels themselves do the peer stores
+        launches_per_step = kernels_per_step + (4 if fused else 0)
         k2 = max(5, args.steps // 2)
         if fused:
             variants["nccl_all_gather"] = timed(group_step(pkg.GATHER_NCCL), k2, 3)
@@ -471,10 +475,11 @@ def main():
             traffic = {}
         k_rank, k_sel = ("bv_rank_kernel", "bv_select_kernel")
         n_rank, n_sel = "bv_rank_kernel<1,2>", "bv_select_kernel<1>"
-        if binned:  # one op = three launches; the roofline entry is for the whole op (all three inside the event pair)
-            k_rank, k_sel = "binned_rank_pipeline", "binned_select_pipeline"
-            n_rank = "bin_tile_sort_kernel<1> + bin_apply_kernel<BvRankOp<1>> + bin_unsort_kernel"
-            n_sel = "bin_tile_sort_kernel<1> + bin_apply_kernel<BvSelectOp<1>> + bin_unsort_kernel"
+        # binned: one op = three launches; the roofline entry is for the whole op (all three inside the event pair)
+        if binned_r:
+            k_rank, n_rank = "binned_rank_pipeline", "bin_tile_sort_kernel<1> + bin_apply_kernel<BvRankOp<1>> + bin_unsort_kernel"
+        if binned_s:
+            k_sel, n_sel = "binned_select_pipeline", "bin_tile_sort_kernel<1> + bin_apply_kernel<BvSelectOp<1>> + bin_unsort_kernel"
         per_gpu_q = shard_q if world > 1 else nq
 
         def roof(bytes_per_q, ms, kernel=None):
@@ -483,8 +488,8 @@ def main():
             return {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "frac_read_only": ro / peak, "traffic": traffic.get(kernel),
                     "traffic_source": traffic_src if traffic.get(kernel) else None, "peak_source": peak_src, "algorithmic_bytes_per_query": bytes_per_q,
                     "read_bytes_per_query": bytes_per_q - RESULT_BYTES, "kernel_ms": ms, "queries_per_launch": per_gpu_q}
-        r_rank = dict(roof(RANK_BYTES, rank_ms, k_rank), kernel=n_rank, launches=3 if binned else 1, qps=per_gpu_q / (rank_ms * 1e-3))
-        r_sel = dict(roof(SELECT_BYTES, sel_ms, k_sel), kernel=n_sel, launches=3 if binned else 1, qps=per_gpu_q / (sel_ms * 1e-3))
+        r_rank = dict(roof(RANK_BYTES, rank_ms, k_rank), kernel=n_rank, launches=3 if binned_r else 1, qps=per_gpu_q / (rank_ms * 1e-3))
+        r_sel = dict(roof(SELECT_BYTES, sel_ms, k_sel), kernel=n_sel, launches=3 if binned_s else 1, qps=per_gpu_q / (sel_ms * 1e-3))
         dominant = r_sel if sel_ms >= rank_ms else r_rank
         cfg = workload_config(args, nbits, world)
         line = {
@@ -495,7 +500,7 @@ def main():
             "roofline": dominant, "roofline_by_kernel": {"rank": r_rank, "select": r_sel},
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
-            "gpu_launches": launches_per_step * args.steps, "batch_order": "binned" if binned else "direct",
+            "gpu_launches": launches_per_step * args.steps, "batch_order": {"rank": "binned" if binned_r else "direct", "select": "binned" if binned_s else "direct"},
             "clocks": clocks, "per_rank": per_rank, "parity": parity,
             "index_device_bytes": index_bytes,
             "extras": extras,

@@ -133,6 +133,20 @@ int sdslgpu_rank(const sdslgpu_handle *h, int b, const uint64_t *idx, uint64_t n
  *          on KIND_BV also select_support_mcl<10|01|00|11, 2>::select (select_support.hpp:204-405). */
 int sdslgpu_select(const sdslgpu_handle *h, int b, const uint64_t *i, uint64_t n, uint64_t *out, void *stream);
 
+/* The same two calls with queries and results in the reference's own compact container: int_vector<w>.  Field k of
+ * width w occupies bits [k*w, (k+1)*w) of the word array, LSB first (int_vector.hpp:1900-1904 for w = 1, get_int /
+ * bits::read_int bits.hpp:777-790 in general) — i.e. `words` is int_vector<>::data() of a vector the caller filled or
+ * bit-compressed (util::bit_compress, util.hpp:502-516).  Positions in a 2^33-bit vector need 34 bits, not 64: the
+ * batch crosses PCIe at 4.25 bytes per query and per result instead of 8.  idx_words holds ceil(n*idx_width/64)
+ * words, out_words receives ceil(n*out_width/64) words; a result is truncated to out_width bits (choose
+ * out_width >= bits::hi(size)+1; SDSLGPU_NPOS becomes the all-ones field).  Both arrays on the host (chunks of 2^23
+ * queries: H2D of the packed chunk, unpack / kernels / pack on the device, D2H of the packed results, overlapped) or
+ * both on the device (asynchronous on `stream`).  Values are identical to sdslgpu_rank / sdslgpu_select. */
+int sdslgpu_rank_iv(const sdslgpu_handle *h, int b, const uint64_t *idx_words, uint32_t idx_width, uint64_t n,
+                    uint64_t *out_words, uint32_t out_width, void *stream);
+int sdslgpu_select_iv(const sdslgpu_handle *h, int b, const uint64_t *i_words, uint32_t i_width, uint64_t n,
+                      uint64_t *out_words, uint32_t out_width, void *stream);
+
 /* Order of work inside one sdslgpu_rank / sdslgpu_select call on a KIND_BV handle; never changes a result.
  *   SDSLGPU_ORDER_DIRECT  one thread per query in the caller's order: one random DRAM gather per query
  *   SDSLGPU_ORDER_BINNED  the batch is counting-sorted tile by tile into ~24 MB chunks of the index, answered chunk
@@ -140,15 +154,15 @@ int sdslgpu_select(const sdslgpu_handle *h, int b, const uint64_t *i, uint64_t n
  *                         scratch per query (cudaMallocAsync on the call's stream)
  *   SDSLGPU_ORDER_AUTO    (default) BINNED when the index is larger than the L2 (>= 192 MB) and the batch is dense
  *                         enough for queries to share cache lines (>= 2^21 queries and >= 1 query per 64 bytes of
- *                         index), else DIRECT
+ *                         index for rank, per 192 bytes for select — the measured break-even points), else DIRECT
  * The reference has no counterpart (its queries are scalar calls, rank_support_v.hpp:129-139). */
 #define SDSLGPU_ORDER_AUTO 0
 #define SDSLGPU_ORDER_DIRECT 1
 #define SDSLGPU_ORDER_BINNED 2
 int sdslgpu_set_batch_order(sdslgpu_handle *h, int order);
-/* 1 if SDSLGPU_ORDER_AUTO runs a batch of n queries on an index of index_bytes through the binned pipeline, else 0
- * (for callers that want to report or plan around the choice; no handle, no device needed) */
-int sdslgpu_auto_is_binned(uint64_t index_bytes, uint64_t n);
+/* 1 if SDSLGPU_ORDER_AUTO runs a batch of n rank (select != 0: select) queries on an index of index_bytes through the
+ * binned pipeline, else 0 (for callers that want to report or plan around the choice; no handle, no device needed) */
+int sdslgpu_auto_is_binned(uint64_t index_bytes, uint64_t n, int select);
 
 /* out[k] = bit idx[k] (0/1), 0 <= idx[k] < size.  Replaces operator[] of bit_vector
  * (int_vector.hpp:1900-1904), rrr_vector (rrr_vector.hpp:276-298), sd_vector (sd_vector.hpp:328-349). */

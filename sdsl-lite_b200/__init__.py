@@ -47,7 +47,9 @@ _SIGNATURES = [
     ("sdslgpu_select", C.c_int, [vp, C.c_int, vp, C.c_uint64, vp, vp]),
     ("sdslgpu_access", C.c_int, [vp, vp, C.c_uint64, vp, vp]),
     ("sdslgpu_set_batch_order", C.c_int, [vp, C.c_int]),
-    ("sdslgpu_auto_is_binned", C.c_int, [C.c_uint64, C.c_uint64]),
+    ("sdslgpu_auto_is_binned", C.c_int, [C.c_uint64, C.c_uint64, C.c_int]),
+    ("sdslgpu_rank_iv", C.c_int, [vp, C.c_int, vp, C.c_uint32, C.c_uint64, vp, C.c_uint32, vp]),
+    ("sdslgpu_select_iv", C.c_int, [vp, C.c_int, vp, C.c_uint32, C.c_uint64, vp, C.c_uint32, vp]),
     ("sdslgpu_bv_serialize", C.c_int, [vp, C.c_int, vp, C.c_uint64, u64p]),
     ("sdslgpu_wt_huff_create", C.c_int, [vp, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(vp)]),
     ("sdslgpu_wt_sigma", C.c_int, [vp, u64p]),
@@ -215,10 +217,104 @@ class _Handle:
         _check(lib().sdslgpu_access(self._h, p, n, po, _stream_ptr(stream, idx)))
         return o
 
+    # ---- the same with queries / results as int_vector<w> fields (sdslgpu_rank_iv / _select_iv) ----
+    def _iv(self, fn, words, width, n, b, out_width, out, stream):
+        p, nw, keep, _ = _in_ptr(words)
+        assert nw >= iv_words(n, width), "packed query array too short"
+        po, o, _k = _out_like(words, iv_words(n, out_width), out)
+        _check(fn(self._h, b, p, int(width), int(n), po, int(out_width), _stream_ptr(stream, words)))
+        return o
 
-def binned_wanted(index_bytes, n):
+    def rank_iv(self, words, width, n, b=1, out_width=64, out=None, stream=None):
+        return self._iv(lib().sdslgpu_rank_iv, words, width, n, b, out_width, out, stream)
+
+    def select_iv(self, words, width, n, b=1, out_width=64, out=None, stream=None):
+        return self._iv(lib().sdslgpu_select_iv, words, width, n, b, out_width, out, stream)
+
+
+def iv_words(n, width):
+    return (int(n) * int(width) + 63) >> 6
+
+
+def iv_pack(values, width):
+    """u64 values -> the word array of an int_vector<width> (field k at bits [k*width, (k+1)*width), LSB first).
+    Host-side helper for tests / bench (numpy): 64 fields fill exactly `width` words, so the work is 64 vectorised passes."""
+    v = np.ascontiguousarray(values, dtype=np.uint64)
+    n = len(v)
+    mask = np.uint64((1 << width) - 1) if width < 64 else np.uint64(2**64 - 1)
+    groups = (n + 63) // 64
+    pad = np.zeros(groups * 64, dtype=np.uint64)
+    pad[:n] = v & mask
+    pad = pad.reshape(groups, 64)
+    out = np.zeros((groups, width + 1), dtype=np.uint64)
+    for j in range(64):
+        pos = j * width
+        w, off = pos >> 6, pos & 63
+        out[:, w] |= pad[:, j] << np.uint64(off)
+        if off + width > 64:
+            out[:, w + 1] |= pad[:, j] >> np.uint64(64 - off)
+    return out[:, :width].reshape(-1)[: iv_words(n, width)].copy()
+
+
+def iv_unpack(words, width, n):
+    w = np.ascontiguousarray(words, dtype=np.uint64)
+    groups = (n + 63) // 64
+    need = groups * width
+    buf = np.zeros(need + 1, dtype=np.uint64)
+    buf[: min(len(w), need)] = w[:need]
+    g = buf[:need].reshape(groups, width)
+    gx = np.concatenate([g, np.zeros((groups, 1), np.uint64)], axis=1)
+    out = np.zeros((groups, 64), dtype=np.uint64)
+    mask = np.uint64((1 << width) - 1) if width < 64 else np.uint64(2**64 - 1)
+    for j in range(64):
+        pos = j * width
+        wi, off = pos >> 6, pos & 63
+        x = gx[:, wi] >> np.uint64(off)
+        if off + width > 64:
+            x = x | (gx[:, wi + 1] << np.uint64(64 - off))
+        out[:, j] = x & mask
+    return out.reshape(-1)[:n].copy()
+
+
+class PackedBatch:
+    """bench.py's e2e leg over the int_vector<w> wire format: the rank and select queries of one step as packed,
+    pinned host arrays (w = bits needed for a position / an index), results into packed pinned host arrays"""
+
+    def __init__(self, bv, idx, sel, nbits):
+        import torch
+
+        self.bv, self.n = bv, len(idx)
+        self.w = max(int(nbits).bit_length(), 1)  # positions 0..nbits and ranks 0..nbits fit
+        self.h_idx = torch.from_numpy(iv_pack(idx, self.w).view(np.int64)).pin_memory()
+        self.h_sel = torch.from_numpy(iv_pack(sel, self.w).view(np.int64)).pin_memory()
+        self.h_out_r = torch.empty(iv_words(self.n, self.w), dtype=torch.int64).pin_memory()
+        self.h_out_s = torch.empty(iv_words(self.n, self.w), dtype=torch.int64).pin_memory()
+        self.h2d_bytes = 2 * iv_words(self.n, self.w) * 8
+        self.d2h_bytes = 2 * iv_words(self.n, self.w) * 8
+
+    def _np(self, t):
+        return t.numpy().view(np.uint64)
+
+    def step(self):
+        self.bv.rank_iv(self._np(self.h_idx), self.w, self.n, 1, self.w, out=self._np(self.h_out_r))
+        self.bv.select_iv(self._np(self.h_sel), self.w, self.n, 1, self.w, out=self._np(self.h_out_s))
+
+    def check(self, bv, idx_prefix, sel_prefix):
+        """values of the packed path == values of the u64 path on a prefix"""
+        k = len(idx_prefix)
+        mask = np.uint64((1 << self.w) - 1)
+        r = iv_unpack(self._np(self.h_out_r), self.w, k)
+        s_ = iv_unpack(self._np(self.h_out_s), self.w, k)
+        return bool((r == (bv.rank(idx_prefix, 1) & mask)).all() and (s_ == (bv.select(sel_prefix, 1) & mask)).all())
+
+    def describe(self):
+        return (f"sdslgpu_rank_iv / sdslgpu_select_iv: queries and results as int_vector<{self.w}> fields in pinned host arrays "
+                f"({self.w / 8:g} B per query and per result over PCIe instead of 8; chunks of 2^23 queries: H2D, unpack, kernels, pack, D2H overlapped)")
+
+
+def binned_wanted(index_bytes, n, select=False):
     """what SDSLGPU_ORDER_AUTO resolves to for a batch of n queries on an index of index_bytes (sdslgpu_auto_is_binned)"""
-    return bool(lib().sdslgpu_auto_is_binned(int(index_bytes), int(n)))
+    return bool(lib().sdslgpu_auto_is_binned(int(index_bytes), int(n), int(bool(select))))
 
 
 class BitVector(_Handle):

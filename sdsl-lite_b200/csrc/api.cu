@@ -111,6 +111,172 @@ void Staging::destroy()
     ready = false;
 }
 
+int StagingIv::ensure()
+{
+    if (ready)
+        return SDSLGPU_OK;
+    for (int k = 0; k < kSlots; ++k)
+    {
+        SG_CUDA(cudaMalloc(reinterpret_cast<void **>(&pin[k]), (kChunk + 2) * 8));
+        SG_CUDA(cudaMalloc(reinterpret_cast<void **>(&pout[k]), (kChunk + 2) * 8));
+        SG_CUDA(cudaMalloc(reinterpret_cast<void **>(&uin[k]), kChunk * 8));
+        SG_CUDA(cudaMalloc(reinterpret_cast<void **>(&uout[k]), kChunk * 8));
+        SG_CUDA(cudaStreamCreateWithFlags(&stream[k], cudaStreamNonBlocking));
+    }
+    ready = true;
+    return SDSLGPU_OK;
+}
+
+void StagingIv::destroy()
+{
+    for (int k = 0; k < kSlots; ++k)
+    {
+        for (uint64_t ** p : {&pin[k], &pout[k], &uin[k], &uout[k]})
+        {
+            if (*p)
+                cudaFree(*p);
+            *p = nullptr;
+        }
+        if (stream[k])
+            cudaStreamDestroy(stream[k]);
+        stream[k] = nullptr;
+    }
+    ready = false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// int_vector<w> wire format: field k occupies bits [k*w, (k+1)*w) of the word array, LSB first
+// (int_vector.hpp get_int / bits::read_int, bits.hpp:777-790; bits::write_int :737-760)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) iv_unpack_kernel(uint64_t const * __restrict__ words, uint64_t nwords, uint32_t width, uint64_t n, uint64_t * __restrict__ out)
+{
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t const mask = width >= 64 ? ~0ull : (1ull << width) - 1ull;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+    {
+        uint64_t const pos = k * width, w = pos >> 6;
+        uint32_t const off = (uint32_t)(pos & 63);
+        uint64_t v = words[w] >> off;
+        if (off + width > 64 && w + 1 < nwords)
+            v |= words[w + 1] << (64 - off);
+        st_stream_u64(out + k, v & mask);
+    }
+}
+
+// one thread per OUTPUT word: the (at most 64 / w + 2) fields overlapping it, each value truncated to w bits
+// (SDSLGPU_NPOS becomes the all-ones field)
+__global__ void __launch_bounds__(kThreads) iv_pack_kernel(uint64_t const * __restrict__ vals, uint64_t n, uint32_t width, uint64_t * __restrict__ words, uint64_t nwords)
+{
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t const mask = width >= 64 ? ~0ull : (1ull << width) - 1ull;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nwords; j += stride)
+    {
+        uint64_t const lo_bit = j * 64, hi_bit = lo_bit + 64;
+        uint64_t acc = 0;
+        for (uint64_t k = lo_bit / width; k < n && k * width < hi_bit; ++k)
+        {
+            uint64_t const v = ld_stream_u64(vals + k) & mask, pos = k * width;
+            acc |= pos >= lo_bit ? v << (pos - lo_bit) : v >> (lo_bit - pos);
+        }
+        words[j] = acc;
+    }
+}
+
+static uint64_t iv_words(uint64_t n, uint32_t width)
+{
+    return (n * width + 63) >> 6;
+}
+
+// launch(in_u64_on_device, n, out_u64_on_device, stream) over queries / results that travel as int_vector<w> fields.
+// Host arrays are streamed chunk by chunk (packed over PCIe, unpacked / packed on the device); device arrays are
+// unpacked into stream-ordered scratch, answered and packed back, asynchronously on the caller's stream.
+template <class Launch>
+static int run_batch_iv(sdslgpu_handle const * hc, uint64_t const * in_words, uint32_t in_width, uint64_t n, uint64_t * out_words, uint32_t out_width,
+                        cudaStream_t user, Launch launch)
+{
+    sdslgpu_handle * h = const_cast<sdslgpu_handle *>(hc);
+    if (n == 0)
+        return SDSLGPU_OK;
+    if (!in_words || !out_words || in_width == 0 || in_width > 64 || out_width == 0 || out_width > 64)
+    {
+        set_error("int_vector batch: null pointer or width outside 1..64");
+        return SDSLGPU_EINVAL;
+    }
+    DeviceGuard g(h->device);
+    if (!g.ok)
+    {
+        set_error("cannot select CUDA device %d", h->device);
+        return SDSLGPU_ECUDA;
+    }
+    PtrSpace isp, osp;
+    SG_TRY(classify(in_words, h->device, &isp));
+    SG_TRY(classify(out_words, h->device, &osp));
+    if (isp == PtrSpace::Device && osp == PtrSpace::Device)
+    {
+        uint64_t * tmp = nullptr;
+        SG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&tmp), 2 * n * 8, user));
+        iv_unpack_kernel<<<grid_for(n), kThreads, 0, user>>>(in_words, iv_words(n, in_width), in_width, n, tmp);
+        int st = launch(tmp, n, tmp + n, user);
+        if (st == SDSLGPU_OK)
+        {
+            uint64_t const ow = iv_words(n, out_width);
+            iv_pack_kernel<<<grid_for(ow), kThreads, 0, user>>>(tmp + n, n, out_width, out_words, ow);
+            if (cudaGetLastError() != cudaSuccess)
+                st = SDSLGPU_ECUDA;
+        }
+        cudaFreeAsync(tmp, user);
+        return st;
+    }
+    if (isp != osp)
+    {
+        set_error("int_vector batch: queries and results must both be host arrays or both device arrays");
+        return SDSLGPU_EINVAL;
+    }
+    std::lock_guard<std::mutex> lock(h->staging.mu);
+    SG_TRY(h->staging_iv.ensure());
+    StagingIv & st = h->staging_iv;
+    SG_CUDA(cudaStreamSynchronize(user));
+    uint64_t const chunk = StagingIv::kChunk, nchunks = (n + chunk - 1) / chunk;
+    uint64_t const in_total = iv_words(n, in_width), out_total = iv_words(n, out_width);
+    int status = SDSLGPU_OK;
+    for (uint64_t c = 0; c < nchunks && status == SDSLGPU_OK; ++c)
+    {
+        int const slot = (int)(c % StagingIv::kSlots);
+        cudaStream_t s = st.stream[slot];
+        uint64_t const lo = c * chunk, cnt = (n - lo < chunk) ? n - lo : chunk;
+        // chunk = 2^23 queries: lo * width is a multiple of 64, so every chunk starts on a word boundary on both sides
+        uint64_t const iw0 = lo * in_width / 64, ow0 = lo * out_width / 64;
+        uint64_t iw = iv_words(cnt, in_width), ow = iv_words(cnt, out_width);
+        if (iw0 + iw > in_total)
+            iw = in_total - iw0;
+        if (ow0 + ow > out_total)
+            ow = out_total - ow0;
+        cudaError_t e = cudaMemcpyAsync(st.pin[slot], in_words + iw0, iw * 8, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess)
+        {
+            status = cuda_fail(e, "H2D packed chunk", __FILE__, __LINE__);
+            break;
+        }
+        iv_unpack_kernel<<<grid_for(cnt), kThreads, 0, s>>>(st.pin[slot], iw, in_width, cnt, st.uin[slot]);
+        status = launch(st.uin[slot], cnt, st.uout[slot], s);
+        if (status != SDSLGPU_OK)
+            break;
+        iv_pack_kernel<<<grid_for(ow), kThreads, 0, s>>>(st.uout[slot], cnt, out_width, st.pout[slot], ow);
+        e = cudaGetLastError();
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(out_words + ow0, st.pout[slot], ow * 8, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess)
+            status = cuda_fail(e, "D2H packed chunk", __FILE__, __LINE__);
+    }
+    for (int k = 0; k < StagingIv::kSlots; ++k)
+    {
+        cudaError_t e = cudaStreamSynchronize(st.stream[k]);
+        if (e != cudaSuccess && status == SDSLGPU_OK)
+            status = cuda_fail(e, "staging sync", __FILE__, __LINE__);
+    }
+    return status;
+}
+
 int classify(void const * p, int device, PtrSpace * space)
 {
     cudaPointerAttributes a;
@@ -517,6 +683,7 @@ extern "C"
         DeviceGuard g(h->device);
         cudaDeviceSynchronize();
         h->staging.destroy();
+        h->staging_iv.destroy();
         h->pool.release_all();
         delete h;
         return SDSLGPU_OK;
@@ -610,9 +777,9 @@ extern "C"
         return SDSLGPU_OK;
     }
 
-    int sdslgpu_auto_is_binned(uint64_t index_bytes, uint64_t n)
+    int sdslgpu_auto_is_binned(uint64_t index_bytes, uint64_t n, int select)
     {
-        return bin_wanted(SDSLGPU_ORDER_AUTO, index_bytes, n) ? 1 : 0;
+        return bin_wanted(SDSLGPU_ORDER_AUTO, index_bytes, n, select ? kBinSelectDensity : kBinRankDensity) ? 1 : 0;
     }
 
     int sdslgpu_rank(const sdslgpu_handle * h, int b, const uint64_t * idx, uint64_t n, uint64_t * out, void * stream)
@@ -687,6 +854,49 @@ extern "C"
         }
         set_error("sdslgpu_select: unsupported handle kind %d", h->kind);
         return SDSLGPU_ENOTSUP;
+    }
+
+    // queries / results as int_vector<w> fields.  op: 0 = rank, 1 = select
+    static int rank_select_iv(const sdslgpu_handle * h, int op, int b, const uint64_t * in_words, uint32_t in_width, uint64_t n, uint64_t * out_words,
+                              uint32_t out_width, void * stream)
+    {
+        SG_TRY(check_handle(h));
+        char const * who = op ? "sdslgpu_select_iv" : "sdslgpu_rank_iv";
+        if (b != 0 && b != 1)
+        {
+            set_error("%s: b must be 0 or 1", who);
+            return SDSLGPU_EINVAL;
+        }
+        cudaStream_t user = static_cast<cudaStream_t>(stream);
+        switch (h->kind)
+        {
+        case SDSLGPU_KIND_BV:
+            return run_batch_iv(h, in_words, in_width, n, out_words, out_width, user, [=](uint64_t const * q, uint64_t cnt, uint64_t * o, cudaStream_t s) {
+                return op ? bv_select_device(h->bv, b, q, cnt, o, s) : bv_rank_device(h->bv, h->flags, b, q, cnt, o, s);
+            });
+        case SDSLGPU_KIND_RRR63:
+            return run_batch_iv(h, in_words, in_width, n, out_words, out_width, user, [=](uint64_t const * q, uint64_t cnt, uint64_t * o, cudaStream_t s) {
+                return op ? rrr_select_device(h, b, q, cnt, o, s) : rrr_rank_device(h, b, q, cnt, o, s);
+            });
+        case SDSLGPU_KIND_SD:
+            return run_batch_iv(h, in_words, in_width, n, out_words, out_width, user, [=](uint64_t const * q, uint64_t cnt, uint64_t * o, cudaStream_t s) {
+                return op ? sd_select_device(h, b, q, cnt, o, s) : sd_rank_device(h, b, q, cnt, o, s);
+            });
+        }
+        set_error("%s: unsupported handle kind %d", who, h->kind);
+        return SDSLGPU_ENOTSUP;
+    }
+
+    int sdslgpu_rank_iv(const sdslgpu_handle * h, int b, const uint64_t * idx_words, uint32_t idx_width, uint64_t n, uint64_t * out_words, uint32_t out_width,
+                        void * stream)
+    {
+        return rank_select_iv(h, 0, b, idx_words, idx_width, n, out_words, out_width, stream);
+    }
+
+    int sdslgpu_select_iv(const sdslgpu_handle * h, int b, const uint64_t * i_words, uint32_t i_width, uint64_t n, uint64_t * out_words, uint32_t out_width,
+                          void * stream)
+    {
+        return rank_select_iv(h, 1, b, i_words, i_width, n, out_words, out_width, stream);
     }
 
     int sdslgpu_access(const sdslgpu_handle * h, const uint64_t * idx, uint64_t n, uint64_t * out, void * stream)

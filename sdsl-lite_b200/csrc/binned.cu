@@ -276,15 +276,18 @@ bool bin_make_plan(uint64_t index_bytes, uint64_t maxkey, uint64_t n, BinPlan & 
     return p.ntiles < (1ull << 31);
 }
 
-bool bin_wanted(int order, uint64_t index_bytes, uint64_t n)
+bool bin_wanted(int order, uint64_t index_bytes, uint64_t n, uint32_t index_bytes_per_query)
 {
     if (order == SDSLGPU_ORDER_BINNED)
         return true;
     if (order == SDSLGPU_ORDER_DIRECT)
         return false;
-    // auto: only when the index cannot live in L2 and the batch is dense enough that the queries of a bin share
-    // cache lines (>= 2 queries per 128-byte line of the index on average); a sparser batch misses in DRAM anyway
-    return index_bytes >= (192ull << 20) && n >= (1ull << 21) && n >= index_bytes / 64;
+    // auto: only when the index cannot live in L2 and the batch is dense enough that the queries of a bin share cache
+    // lines; a sparser batch misses in DRAM anyway and the two extra passes are pure cost.  The break-even density is
+    // measured (tools/sweep_order.py, profiles/r02a_sweep_order.jsonl, 1.23 GB index): a one-gather op (rank) pays from
+    // 1 query per 64 bytes of index (1.9e7 queries: 0.96x at 1.7e7, 1.11x at 2.5e7), a multi-gather op (select: sample
+    // + blocks) from 1 per 192 bytes (6.4e6: 0.92x at 4.2e6, 1.11x at 8.4e6).
+    return index_bytes >= (192ull << 20) && n >= (1ull << 21) && n >= index_bytes / index_bytes_per_query;
 }
 
 static constexpr uint64_t kTicketBytes = kTicketLanes * kTicketStride * 8;
@@ -407,9 +410,9 @@ struct BvSelectOp
     }
 };
 
-bool bv_binned_wanted(BvImage const & v, uint64_t n)
+bool bv_binned_wanted(BvImage const & v, uint64_t n, bool select)
 {
-    return bin_wanted(v.order, v.nblocks * sizeof(bvblock), n);
+    return bin_wanted(v.order, v.nblocks * sizeof(bvblock), n, select ? kBinSelectDensity : kBinRankDensity);
 }
 
 int bv_rank_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done, Fan const * fan)

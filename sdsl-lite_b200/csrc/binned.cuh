@@ -58,7 +58,6 @@ struct BinScratch
 
 // binned.cu
 bool bin_make_plan(uint64_t index_bytes, uint64_t maxkey, uint64_t n, BinPlan & p);
-bool bin_wanted(int order, uint64_t index_bytes, uint64_t n);
 int bin_scratch_alloc(BinScratch & w, BinPlan const & p, cudaStream_t s);
 int bin_launch_tile_sort(BinPlan const & p, BinScratch const & w, uint64_t const * q, uint64_t n, uint64_t sub, uint64_t maxkey, bool clamp, cudaStream_t s);
 int bin_launch_unsort(BinPlan const & p, BinScratch const & w, uint64_t n, uint64_t * out, cudaStream_t s, Fan const * fan = nullptr);

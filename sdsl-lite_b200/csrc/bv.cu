@@ -110,13 +110,15 @@ __global__ void __launch_bounds__(kThreads) bv_samples_kernel(uint64_t const * _
 // ------------------------------------------------------------------------------------------------
 // rank: one 32-byte sector per query
 // ------------------------------------------------------------------------------------------------
-template <int B, int ILP>
+// kFan (multi-GPU group calls, group.cu): every result is also stored to the same index of the other members' arrays
+template <int B, int ILP, bool kFan>
 __global__ void __launch_bounds__(kThreads) bv_rank_kernel(bvblock const * __restrict__ blocks,
                                                            uint64_t const * __restrict__ top,
                                                            uint64_t nbits,
                                                            uint64_t const * __restrict__ idx,
                                                            uint64_t n,
-                                                           uint64_t * __restrict__ out)
+                                                           uint64_t * __restrict__ out,
+                                                           Fan const fan)
 {
     uint64_t const stride = (uint64_t)gridDim.x * blockDim.x * ILP;
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x * ILP + threadIdx.x; base < n; base += stride)
@@ -145,7 +147,11 @@ __global__ void __launch_bounds__(kThreads) bv_rank_kernel(bvblock const * __res
                 uint64_t r = __ldg(top + (blk[u] >> kSuperShift)) + cnt[u] + block_prefix_popc(d[u], rem);
                 if (!B)
                     r = i[u] - r;
-                st_stream_u64(out + q, ok[u] ? r : SDSLGPU_NPOS);
+                r = ok[u] ? r : SDSLGPU_NPOS;
+                st_stream_u64(out + q, r);
+                if (kFan)
+                    for (uint32_t p = 0; p < fan.n; ++p)
+                        fan.dst[p][q] = r;
             }
         }
     }
@@ -198,9 +204,9 @@ __global__ void __launch_bounds__(kThreads) bv_rank_sdsl_kernel(uint64_t const *
 // ------------------------------------------------------------------------------------------------
 // select
 // ------------------------------------------------------------------------------------------------
-template <int B>
+template <int B, bool kFan>
 __global__ void __launch_bounds__(kThreads)
-    bv_select_kernel(BvView const v, uint64_t args, uint64_t const * __restrict__ idx, uint64_t n, uint64_t * __restrict__ out)
+    bv_select_kernel(BvView const v, uint64_t args, uint64_t const * __restrict__ idx, uint64_t n, uint64_t * __restrict__ out, Fan const fan)
 {
     uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
@@ -210,6 +216,9 @@ __global__ void __launch_bounds__(kThreads)
         if (i >= 1 && i <= args)
             r = bv_select<B>(v, i);
         st_stream_u64(out + q, r);
+        if (kFan)
+            for (uint32_t p = 0; p < fan.n; ++p)
+                fan.dst[p][q] = r;
     }
 }
 
@@ -519,12 +528,21 @@ int bv_rank_device(BvImage const & v, uint32_t flags, int b, uint64_t const * id
         else
             bv_rank_sdsl_kernel<0, ILP><<<grid, kThreads, 0, s>>>(v.words, v.rank_table[0], v.nbits, idx, n, out);
     }
+    else if (fan && fan->n)
+    {
+        if (b)
+            bv_rank_kernel<1, ILP, true><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.nbits, idx, n, out, *fan);
+        else
+            bv_rank_kernel<0, ILP, true><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.nbits, idx, n, out, *fan);
+        if (fanned)
+            *fanned = true;
+    }
     else
     {
         if (b)
-            bv_rank_kernel<1, ILP><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.nbits, idx, n, out);
+            bv_rank_kernel<1, ILP, false><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.nbits, idx, n, out, Fan{});
         else
-            bv_rank_kernel<0, ILP><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.nbits, idx, n, out);
+            bv_rank_kernel<0, ILP, false><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.nbits, idx, n, out, Fan{});
     }
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
@@ -541,7 +559,7 @@ int bv_select_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n,
         set_error("select requested on a handle created with SDSLGPU_F_NO_SELECT");
         return SDSLGPU_ENOTSUP;
     }
-    if (bv_binned_wanted(v, n))
+    if (bv_binned_wanted(v, n, true))
     {
         bool done = false;
         SG_TRY(bv_select_binned_device(v, b, idx, n, out, s, &done, fan));
@@ -554,10 +572,19 @@ int bv_select_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n,
     }
     unsigned grid = grid_for(n);
     uint64_t args = b ? v.ones : v.nbits - v.ones;
-    if (b)
-        bv_select_kernel<1><<<grid, kThreads, 0, s>>>(bv_view(v), args, idx, n, out);
+    if (fan && fan->n)
+    {
+        if (b)
+            bv_select_kernel<1, true><<<grid, kThreads, 0, s>>>(bv_view(v), args, idx, n, out, *fan);
+        else
+            bv_select_kernel<0, true><<<grid, kThreads, 0, s>>>(bv_view(v), args, idx, n, out, *fan);
+        if (fanned)
+            *fanned = true;
+    }
+    else if (b)
+        bv_select_kernel<1, false><<<grid, kThreads, 0, s>>>(bv_view(v), args, idx, n, out, Fan{});
     else
-        bv_select_kernel<0><<<grid, kThreads, 0, s>>>(bv_view(v), args, idx, n, out);
+        bv_select_kernel<0, false><<<grid, kThreads, 0, s>>>(bv_view(v), args, idx, n, out, Fan{});
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
 }

@@ -169,9 +169,12 @@ __device__ __forceinline__ uint64_t bv_select(BvView const & v, uint64_t i)
     uint64_t const r = (i - 1) & ((1ull << log_s) - 1);
     if (v.samp_pos[B])
     { // position-valued samples: lo / hi are 32-bit chunk indices (224 = 7 * 32: a chunk never straddles two blocks), so
-      // the interpolation is not quantised to whole blocks at either end — first-probe misses 18 % -> 5 % on random data
-        uint64_t p = lo + (((hi - lo) * r + (1ull << log_s >> 1)) >> log_s);
-        return bv_select_from<B>(v, i, lo / 7, hi / 7, p / 7);
+      // the interpolation is not quantised to whole blocks at either end — first-probe misses 18 % -> 5 % on random data.
+      // Everything stays in 32-bit registers: chunk indices are < 2^32 and r < 2^log_s <= 2^16, so one 32 x 32 -> 64
+      // multiply, and the three divisions by 7 are 32-bit multiply-high sequences instead of 64-bit ones.
+        uint32_t const lo32 = (uint32_t)lo, hi32 = (uint32_t)hi;
+        uint32_t const p = lo32 + (uint32_t)(((uint64_t)(hi32 - lo32) * (uint32_t)r + (1ull << log_s >> 1)) >> log_s);
+        return bv_select_from<B>(v, i, lo32 / 7u, hi32 / 7u, p / 7u);
     }
     return bv_select_between<B>(v, i, lo, hi, r, log_s, v.interp[B] != 0);
 }

@@ -102,6 +102,22 @@ struct Fan
     uint32_t n = 0;
 };
 
+// Staging of the int_vector<w> wire format (sdslgpu_rank_iv / _select_iv): per slot the packed chunk as it crosses
+// PCIe, its unpacked u64 form for the kernels, and the same two for the results.
+struct StagingIv
+{
+    static constexpr int kSlots = 3;
+    static constexpr uint64_t kChunk = 1ull << 23; // queries per chunk (a multiple of 64: chunks start on word boundaries)
+    bool ready = false;
+    uint64_t * pin[kSlots] = {nullptr, nullptr, nullptr};  // packed queries  (kChunk words: width <= 64)
+    uint64_t * pout[kSlots] = {nullptr, nullptr, nullptr}; // packed results
+    uint64_t * uin[kSlots] = {nullptr, nullptr, nullptr};  // unpacked queries
+    uint64_t * uout[kSlots] = {nullptr, nullptr, nullptr}; // unpacked results
+    cudaStream_t stream[kSlots] = {nullptr, nullptr, nullptr};
+    int ensure();
+    void destroy();
+};
+
 enum class PtrSpace
 {
     Host,
@@ -251,6 +267,7 @@ struct sdslgpu_handle
     int order = SDSLGPU_ORDER_AUTO; // sdslgpu_set_batch_order (bit vectors keep their own copy in BvImage::order)
     sdslgpu::DevicePool pool;
     sdslgpu::Staging staging;
+    sdslgpu::StagingIv staging_iv;
     sdslgpu::BvImage bv;        // KIND_BV
     // KIND_BV: indicator vectors of the two-bit patterns 10 / 01 / 00 / 11, built on first use (bv.cu)
     sdslgpu::BvImage pat[4];
@@ -322,8 +339,9 @@ int bv_select_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n,
                      bool * fanned = nullptr);
 int bv_access_device(BvImage const & v, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 // binned.cu: locality-ordered execution of large batches; *done = false means "not applicable, use the direct kernel"
-bool bv_binned_wanted(BvImage const & v, uint64_t n);
-bool bin_wanted(int order, uint64_t index_bytes, uint64_t n);
+static constexpr uint32_t kBinRankDensity = 64, kBinSelectDensity = 192; // bytes of index per query at the break-even (binned.cu bin_wanted)
+bool bv_binned_wanted(BvImage const & v, uint64_t n, bool select = false);
+bool bin_wanted(int order, uint64_t index_bytes, uint64_t n, uint32_t index_bytes_per_query = kBinRankDensity);
 int bv_rank_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done, Fan const * fan = nullptr);
 int bv_select_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done, Fan const * fan = nullptr);
 // wt.cu

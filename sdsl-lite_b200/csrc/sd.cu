@@ -286,7 +286,7 @@ int sd_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint
 {
     if (n == 0)
         return SDSLGPU_OK;
-    if (b && h->sd.m && bin_wanted(h->order, sd_index_bytes(h->sd), n)) // select_0 is a binary search over select_1: no locality
+    if (b && h->sd.m && bin_wanted(h->order, sd_index_bytes(h->sd), n, kBinSelectDensity)) // select_0 is a binary search over select_1: no locality
     {
         bool done = false;
         SG_TRY(bin_run(SdSelect1Op{sd_view(h->sd)}, sd_index_bytes(h->sd), 1, h->sd.m - 1, idx, n, out, s, &done));

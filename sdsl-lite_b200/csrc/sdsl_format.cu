@@ -269,7 +269,8 @@ int load_wt_huff(sdslgpu_handle * h, Reader & r, cudaStream_t s)
         {
             bool const idx_ok = (tree.parent[v] == 0xFFFF || tree.parent[v] < nn) && (tree.child[v][0] == 0xFFFF || tree.child[v][0] < nn) &&
                                 (tree.child[v][1] == 0xFFFF || tree.child[v][1] < nn);
-            if (!idx_ok || tree.bv_pos[v] > bits || tree.bv_pos_rank[v] > tree.bv_pos[v] || (v && tree.bv_pos[v] < tree.bv_pos[v - 1]))
+            bool const inner = tree.child[v][0] != 0xFFFF; // a leaf keeps its symbol in bv_pos_rank (wt_helper.hpp:279-283)
+            if (!idx_ok || tree.bv_pos[v] > bits || (inner && tree.bv_pos_rank[v] > tree.bv_pos[v]) || (v && tree.bv_pos[v] < tree.bv_pos[v - 1]))
                 return malformed("wt_huff (byte_tree node out of range)");
         }
         for (int c = 0; c < 256 && size; ++c)
