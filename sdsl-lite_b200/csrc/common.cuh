@@ -26,6 +26,14 @@ static inline int __popcll(uint64_t x)
 {
     return __builtin_popcountll(x);
 }
+static inline int __clz(int x)
+{
+    return x ? __builtin_clz((unsigned)x) : 32;
+}
+static inline int __ffs(int x)
+{
+    return __builtin_ffs(x);
+}
 template <class T>
 static inline T __ldg(T const * p)
 {

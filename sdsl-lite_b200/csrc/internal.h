@@ -219,6 +219,11 @@ struct SdImage
     uint32_t wl = 0;
     uint64_t * low = nullptr; // m_low, packed wl-bit entries
     BvImage high;             // m_high with rank blocks + select<1>/<0> samples
+    // select_0 of the vector itself (the job of select_0_support_sd, sd_vector.hpp:752-921): block of `high` in which
+    // every 2^log_s0-th zero of the vector is crossed (sd_device.cuh sd_select0_one)
+    uint32_t * samp0 = nullptr;
+    uint64_t nsamp0 = 0;
+    uint32_t log_s0 = 0;
 };
 
 // one-hot occurrence bitmaps of the BWT (occ16_device.cuh), staged in shared memory by the fm16 kernels
@@ -376,6 +381,7 @@ int rrr_records_from_sdsl(DevicePool & pool, RrrImage & r, uint64_t const * bt_w
 // sdsl_format.cu
 int load_sdsl_blob(sdslgpu_handle * h, uint8_t const * blob, uint64_t nbytes, uint32_t sa_dens, uint32_t isa_dens, uint64_t * consumed, cudaStream_t s);
 // sd.cu
+int sd_build_select0_samples(sdslgpu_handle * h, cudaStream_t s);
 int sd_build(sdslgpu_handle * h, uint64_t const * words_host_or_dev, bool on_device, uint64_t nbits, cudaStream_t s);
 int sd_rank_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 int sd_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);

@@ -84,23 +84,10 @@ __global__ void __launch_bounds__(kThreads) sd_select_kernel(SdView const v, uin
             if (B)
                 r = sd_select1_one(v, i);
             else
-            { // binary search over select_1 for the last one with fewer than i zeros before it (sd_vector.hpp:637-663)
-                uint64_t lb = 1, rb = v.m + 1, r0 = 0, pos = ~0ull;
-                while (lb < rb)
-                {
-                    uint64_t mid = lb + (rb - lb) / 2;
-                    uint64_t x = sd_select1_one(v, mid);
-                    uint64_t rank0 = x + 1 - mid;
-                    if (rank0 >= i)
-                        rb = mid;
-                    else
-                    {
-                        r0 = rank0;
-                        pos = x;
-                        lb = mid + 1;
-                    }
-                }
-                r = pos + i - r0;
+            {
+                r = v.samp0 ? sd_select0_one(v, i) : ~0ull;
+                if (r == ~0ull)
+                    r = sd_select0_bsearch(v, i);
             }
         }
         st_stream_u64(out + q, r);
@@ -166,7 +153,48 @@ static SdView sd_view(SdImage const & d)
     v.wl = d.wl;
     v.high = bv_view(d.high);
     v.low = d.low;
+    v.samp0 = d.samp0;
+    v.log_s0 = d.log_s0;
     return v;
+}
+
+// one thread per sector block of `high`: the samples whose zero is crossed in this block (sd_device.cuh)
+__global__ void __launch_bounds__(kThreads) sd_samp0_kernel(SdView const v, uint64_t nblocks, uint32_t log_s, uint64_t nsamp, uint32_t * __restrict__ samp0)
+{
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nblocks)
+        return;
+    int64_t v_prev, v_last;
+    if (!sd_block_zero_span(v, g, v_prev, v_last))
+        return;
+    // sample q stands for zero number q * S + 1: owned iff v_prev < q * S + 1 <= v_last
+    uint64_t const S = 1ull << log_s;
+    for (uint64_t q = ((uint64_t)v_prev + S - 1) >> log_s; q < nsamp && (q << log_s) + 1 <= (uint64_t)v_last; ++q)
+        samp0[q] = (uint32_t)g;
+}
+
+int sd_build_select0_samples(sdslgpu_handle * h, cudaStream_t s)
+{
+    SdImage & d = h->sd;
+    uint64_t const zeros = d.size - d.m;
+    if (zeros == 0 || d.high.nblocks >= (1ull << 32) || (h->flags & SDSLGPU_F_NO_SELECT))
+        return SDSLGPU_OK;
+    // about one sample per sector block of `high`: the sample's block is then the crossing block or its neighbour
+    uint32_t ls = 0;
+    while ((zeros >> ls) > d.high.nblocks)
+        ++ls;
+    if (char const * e = std::getenv("SDSLGPU_SD_SELECT0_LOG_S")) // tuning / test knob
+        ls = (uint32_t)std::atoi(e) > 40 ? 40u : (uint32_t)std::atoi(e);
+    d.log_s0 = ls;
+    d.nsamp0 = ((zeros - 1) >> ls) + 1;
+    SG_TRY(h->pool.alloc_t(&d.samp0, d.nsamp0 + 1));
+    SG_CUDA(cudaMemsetAsync(d.samp0, 0, (d.nsamp0 + 1) * 4, s));
+    SdView v = sd_view(d);
+    v.samp0 = nullptr;
+    sd_samp0_kernel<<<blocks_for(d.high.nblocks), kThreads, 0, s>>>(v, d.high.nblocks, ls, d.nsamp0, d.samp0);
+    SG_CUDA(cudaGetLastError());
+    SG_CUDA(cudaStreamSynchronize(s));
+    return SDSLGPU_OK;
 }
 
 static uint32_t hi_bit(uint64_t x)
@@ -227,7 +255,7 @@ int sd_build(sdslgpu_handle * h, uint64_t const * words_in, bool on_device, uint
     // rank blocks + select samples over `high`; SDSLGPU_F_SDSL_LAYOUT keeps the raw words for serialisation
     SG_TRY(bv_build(h->pool, d.high, h->flags & SDSLGPU_F_SDSL_LAYOUT, high, true, d.high_bits, s));
     h->pool.release(high);
-    return SDSLGPU_OK;
+    return sd_build_select0_samples(h, s);
 }
 
 // ops of the locality-ordered batch pipeline (binned.cuh): rank(i) looks at bucket i >> wl of `high` and the low
@@ -261,6 +289,22 @@ struct SdSelect1Op
     }
 };
 
+// select_0(i): the crossing block of `high` and the low parts of its bucket both move forward with i
+struct SdSelect0Op
+{
+    static constexpr int kIlp = 1;
+    static constexpr int kMinCtas = 6;
+    static constexpr uint32_t kSmem = 0;
+    SdView v;
+    __device__ __forceinline__ void stage(uint8_t *) const
+    {}
+    __device__ __forceinline__ uint64_t operator()(uint64_t key) const
+    {
+        uint64_t r = sd_select0_one(v, key + 1);
+        return r != ~0ull ? r : sd_select0_bsearch(v, key + 1);
+    }
+};
+
 static uint64_t sd_index_bytes(SdImage const & d)
 {
     return d.high.nblocks * sizeof(bvblock) + d.low_words * 8;
@@ -286,10 +330,17 @@ int sd_select_device(sdslgpu_handle const * h, int b, uint64_t const * idx, uint
 {
     if (n == 0)
         return SDSLGPU_OK;
-    if (b && h->sd.m && bin_wanted(h->order, sd_index_bytes(h->sd), n, kBinSelectDensity)) // select_0 is a binary search over select_1: no locality
+    if (b && h->sd.m && bin_wanted(h->order, sd_index_bytes(h->sd), n, kBinSelectDensity))
     {
         bool done = false;
         SG_TRY(bin_run(SdSelect1Op{sd_view(h->sd)}, sd_index_bytes(h->sd), 1, h->sd.m - 1, idx, n, out, s, &done));
+        if (done)
+            return SDSLGPU_OK;
+    }
+    if (!b && h->sd.samp0 && h->sd.size > h->sd.m && bin_wanted(h->order, sd_index_bytes(h->sd), n, kBinSelectDensity))
+    { // (without samples select_0 is a binary search over select_1: no locality to order the batch by)
+        bool done = false;
+        SG_TRY(bin_run(SdSelect0Op{sd_view(h->sd)}, sd_index_bytes(h->sd), 1, h->sd.size - h->sd.m - 1, idx, n, out, s, &done));
         if (done)
             return SDSLGPU_OK;
     }

@@ -226,7 +226,8 @@ int load_sd(sdslgpu_handle * h, Reader & r, cudaStream_t s)
     SG_CUDA(cudaMemcpyAsync(d.low, lw.data(), d.low_words * 8, cudaMemcpyHostToDevice, s));
     SG_CUDA(cudaStreamSynchronize(s));
     // the two select_support_mcl blobs that follow are not needed
-    return bv_build(h->pool, d.high, h->flags & SDSLGPU_F_SDSL_LAYOUT, high.words.data(), false, high.bits, s);
+    SG_TRY(bv_build(h->pool, d.high, h->flags & SDSLGPU_F_SDSL_LAYOUT, high.words.data(), false, high.bits, s));
+    return sd_build_select0_samples(h, s);
 }
 
 int load_wt_huff(sdslgpu_handle * h, Reader & r, cudaStream_t s)

@@ -17,6 +17,7 @@ struct Sd
 {
     std::vector<uint64_t> low, high;
     hostimg::HostImage img;
+    std::vector<uint32_t> samp0;
     SdView v;
 };
 } // namespace
@@ -45,6 +46,8 @@ extern "C"
         s->v.wl = wl;
         s->v.high = s->img.view;
         s->v.low = s->low.data();
+        s->v.samp0 = nullptr;
+        s->v.log_s0 = 0;
         return s;
     }
     void sd_emu_free(void * h)
@@ -65,5 +68,44 @@ extern "C"
         Sd * s = static_cast<Sd *>(h);
         for (uint64_t k = 0; k < n; ++k)
             out[k] = sd_select1_one(s->v, i[k]);
+    }
+    // select_0 through the sample table, built here exactly as sd.cu's sd_samp0_kernel does (one "thread" per block);
+    // log_s < 0: the library's choice (about one sample per block).  *fallbacks = queries the samples gave up on.
+    void sd_emu_select0(void * h, int log_s, uint64_t const * i, uint64_t n, uint64_t * out, uint64_t * fallbacks)
+    {
+        Sd * s = static_cast<Sd *>(h);
+        uint64_t const zeros = s->v.size - s->v.m, nblocks = s->v.high.nbits / kBlockBits + 1;
+        *fallbacks = 0;
+        if (zeros == 0)
+            return;
+        uint32_t ls = 0;
+        if (log_s < 0)
+            while ((zeros >> ls) > nblocks)
+                ++ls;
+        else
+            ls = (uint32_t)log_s;
+        uint64_t const nsamp = ((zeros - 1) >> ls) + 1, S = 1ull << ls;
+        s->samp0.assign(nsamp + 1, 0);
+        s->v.samp0 = nullptr;
+        for (uint64_t g = 0; g < nblocks; ++g)
+        {
+            int64_t v_prev, v_last;
+            if (!sd_block_zero_span(s->v, g, v_prev, v_last))
+                continue;
+            for (uint64_t q = ((uint64_t)v_prev + S - 1) >> ls; q < nsamp && (q << ls) + 1 <= (uint64_t)v_last; ++q)
+                s->samp0[q] = (uint32_t)g;
+        }
+        s->v.samp0 = s->samp0.data();
+        s->v.log_s0 = ls;
+        for (uint64_t k = 0; k < n; ++k)
+        {
+            uint64_t r = sd_select0_one(s->v, i[k]);
+            if (r == ~0ull)
+            {
+                ++*fallbacks;
+                r = sd_select0_bsearch(s->v, i[k]);
+            }
+            out[k] = r;
+        }
     }
 }

@@ -38,7 +38,7 @@ def test_compressed_catalogue(pkg, oracle, orc, kind):
             assert v.size == nbits
             idx = cases.rank_queries(nbits, 11, 40000)
             got_rank = {b: v.rank(idx, b) for b in (0, 1)}
-            sel_q = {b: cases.select_queries(v.arg_count(b), 12, 2000 if (kind == "sd" and b == 0) else 40000) for b in (0, 1)}
+            sel_q = {b: cases.select_queries(v.arg_count(b), 12, 40000) for b in (0, 1)}
             got_sel = {b: v.select(sel_q[b], b) for b in (0, 1)}
             pos = idx[idx < nbits]
             got_acc = v.access(pos)
@@ -74,7 +74,7 @@ def test_compressed_density_sweep_properties(pkg, oracle, kind):
             k = cases.select_queries(v.arg_count(1), 9, 300000)
             p = v.select(k, 1)
             assert (p == plain.select(k, 1)).all() and (v.access(p) == 1).all()
-            k0 = cases.select_queries(v.arg_count(0), 10, 300000 if kind == "rrr" else 3000)
+            k0 = cases.select_queries(v.arg_count(0), 10, 300000)
             assert (v.select(k0, 0) == plain.select(k0, 0)).all()
             o = getattr(oracle, kind)(w, nbits)
             assert (v.rank(idx[:5000], 1) == o.rank(idx[:5000], 1)).all()
@@ -85,7 +85,7 @@ def test_compressed_density_sweep_properties(pkg, oracle, kind):
 def test_compressed_binned_order(pkg, oracle, monkeypatch, kind, chunk_bytes):
     """ORDER_BINNED (binned.cuh pipeline with the sd / rrr ops) forced onto the catalogue with tiny bins: rank (both
     patterns), select_1 and rrr select_0 agree with the oracle, out-of-domain queries included (rrr: the reference's
-    in-band size() past the last b-bit); sd select_0 has no binned form and still answers through the direct kernel"""
+    in-band size() past the last b-bit); sd select_0 runs its own binned op over the sampled crossing blocks (sd_device.cuh)"""
     monkeypatch.setenv("SDSLGPU_BIN_CHUNK_BYTES", chunk_bytes)
     for cid, w, nbits in _vectors():
         if kind == "sd" and nbits == 0:
@@ -113,8 +113,14 @@ def test_compressed_binned_order(pkg, oracle, monkeypatch, kind, chunk_bytes):
                     got = v.select(qb, 1)
                     assert (got[::5] == pkg.NPOS).all() and (got[1::5] == o.select(q[1::5], 1)).all(), (kind, cid, "select1 mixed", nq)
                     assert (got[2::5] == (nbits if kind == "rrr" else pkg.NPOS)).all(), (kind, cid, "select1 past the end", nq)
-            q0 = cases.select_queries(v.arg_count(0), 6, 500 if kind == "sd" else 20000)
+            q0 = cases.select_queries(v.arg_count(0), 6, 20000)
             if len(q0):
                 assert (v.select(q0, 0) == o.select(q0, 0)).all(), (kind, cid, "select0")
+                qb = q0.copy()
+                qb[::7] = 0
+                qb[3::7] = np.uint64(v.arg_count(0) + 1)
+                got = v.select(qb, 0)
+                assert (got[::7] == pkg.NPOS).all() and (got[1::7] == o.select(q0[1::7], 0)).all(), (kind, cid, "select0 mixed")
+                assert (got[3::7] == (nbits if kind == "rrr" else pkg.NPOS)).all(), (kind, cid, "select0 past the end")
             if kind == "rrr":
                 assert (v.select(np.array([0, v.arg_count(0) + 1, 2**63], np.uint64), 0) == np.array([pkg.NPOS, nbits, nbits], np.uint64)).all()

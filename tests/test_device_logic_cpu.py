@@ -238,6 +238,7 @@ def sd_emu():
     L.sd_emu_free.argtypes = [vp]
     L.sd_emu_rank.argtypes = [vp, ctypes.c_int, vp, u64, vp]
     L.sd_emu_select1.argtypes = [vp, vp, u64, vp]
+    L.sd_emu_select0.argtypes = [vp, ctypes.c_int, vp, u64, vp, vp]
     return L
 
 
@@ -265,3 +266,34 @@ def test_device_sd_logic(sd_emu, oracle):
         finally:
             sd_emu.sd_emu_free(h)
     assert checked > 100000
+
+
+@pytest.mark.parametrize("log_s", [-1, 0, 5, 12])
+def test_device_sd_select0_samples(sd_emu, oracle, log_s):
+    """sd_select0_one (sample table over the zeros of the vector -> crossing block of `high` -> bucket) against the
+    oracle's select_support_sd<0>; every zero of the small shapes, random ones of the large; the walk limit may only
+    be hit on clustered data, and then the binary-search fallback answers"""
+    checked = fell = 0
+    for cid, w, nbits in _rrr_shapes():
+        if nbits == 0:
+            continue
+        o = oracle.sd(w, nbits)
+        z = nbits - int(o.rank([nbits], 1)[0])
+        if z == 0:
+            continue
+        blob = np.concatenate([np.frombuffer(o.serialize(), dtype=np.uint8), np.zeros(64, np.uint8)])
+        h = sd_emu.sd_emu_load(blob.ctypes.data)
+        try:
+            q = np.arange(1, z + 1, dtype=np.uint64) if z <= 20000 else np.unique(np.concatenate(
+                [cases.select_queries(z, 19, 20000), np.array([1, 2, z - 1, z], dtype=np.uint64)]))
+            out = np.zeros(len(q), np.uint64)
+            fb = ctypes.c_uint64(0)
+            sd_emu.sd_emu_select0(h, log_s, q.ctypes.data, len(q), out.ctypes.data, ctypes.byref(fb))
+            assert (out == o.select(q, 0)).all(), (cid, "select_0", log_s)
+            checked += len(q)
+            fell += fb.value
+            if log_s == -1 and cid.startswith("rand"):
+                assert fb.value == 0, (cid, "uniformly random data never needs the fallback")
+        finally:
+            sd_emu.sd_emu_free(h)
+    assert checked > 100000 and fell < checked // 2
