@@ -220,6 +220,11 @@ int sdslgpu_csa_create_ex(const uint8_t *text, uint64_t n, int device, uint32_t 
                           sdslgpu_handle **out);
 int sdslgpu_csa_create(const uint8_t *text, uint64_t n, int device, uint32_t flags, sdslgpu_handle **out);
 
+/* The byte_alphabet of a CSA (csa_alphabet_strategy.hpp:136-212), i.e. the public members csa.C, csa.char2comp,
+ * csa.comp2char, csa.sigma (csa_wt.hpp:117-120) that backward_search is written against: C[0..256] (entries past sigma
+ * are 0), char2comp[256], comp2char[256] (entries past sigma are 0), *sigma.  Any pointer may be NULL. */
+int sdslgpu_csa_alphabet(const sdslgpu_handle *h, uint64_t *C257, uint8_t *char2comp256, uint8_t *comp2char256, uint32_t *sigma);
+
 /* Patterns in CSR form: pattern k = pats[pat_off[k] .. pat_off[k+1]).
  * cnt_out[k] = number of occurrences; if l_out != NULL, l_out[k] = left end of the suffix-array interval
  * (meaningful when cnt_out[k] > 0).  The empty pattern matches size() times; a pattern longer than size()

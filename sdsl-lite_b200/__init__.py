@@ -398,6 +398,7 @@ _SIGNATURES += [
     ("sdslgpu_csa_create", C.c_int, [vp, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(vp)]),
     ("sdslgpu_csa_create_ex", C.c_int, [vp, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
     ("sdslgpu_fm_count", C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, vp]),
+    ("sdslgpu_csa_alphabet", C.c_int, [vp, vp, vp, vp, C.POINTER(C.c_uint32)]),
     ("sdslgpu_fm_sa", C.c_int, [vp, vp, C.c_uint64, vp, vp]),
     ("sdslgpu_fm_locate", C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, C.c_uint64, u64p, vp]),
     ("sdslgpu_fm_extract", C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, vp]),
@@ -427,6 +428,13 @@ class CsaWt(_Handle, _WaveletTreeOps):
 
     # csa.bwt.rank(i, c) etc.
     bwt_rank = _WaveletTreeOps.wt_rank
+
+    def alphabet(self):
+        """-> (C uint64[257], char2comp uint8[256], comp2char uint8[256], sigma): csa.C / .char2comp / .comp2char / .sigma"""
+        Cs, c2c, cc2 = np.zeros(257, np.uint64), np.zeros(256, np.uint8), np.zeros(256, np.uint8)
+        sg = C.c_uint32()
+        _check(lib().sdslgpu_csa_alphabet(self._h, Cs.ctypes.data, c2c.ctypes.data, cc2.ctypes.data, C.byref(sg)))
+        return Cs, c2c, cc2, sg.value
 
     def count(self, flat, off, want_l=False, stream=None):
         """flat: uint8 pattern bytes, off: uint64[n+1] (numpy or torch CUDA tensors)"""

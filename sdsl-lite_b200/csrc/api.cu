@@ -1264,6 +1264,26 @@ extern "C"
         return sdslgpu_csa_create_ex(text, n, device, flags, 0, 0, out);
     }
 
+    int sdslgpu_csa_alphabet(const sdslgpu_handle * h, uint64_t * C, uint8_t * char2comp, uint8_t * comp2char, uint32_t * sigma)
+    {
+        SG_TRY(check_handle(h));
+        if (h->kind != SDSLGPU_KIND_CSA_WT)
+        {
+            set_error("sdslgpu_csa_alphabet: handle is not a CSA");
+            return SDSLGPU_ENOTSUP;
+        }
+        FmTables const & t = h->csa.host_tab;
+        if (C)
+            std::memcpy(C, t.C, sizeof(t.C));
+        if (char2comp)
+            std::memcpy(char2comp, t.char2comp, 256);
+        if (comp2char)
+            std::memcpy(comp2char, t.comp2char, 256);
+        if (sigma)
+            *sigma = t.sigma;
+        return SDSLGPU_OK;
+    }
+
     int sdslgpu_fm_count(const sdslgpu_handle * h, const uint8_t * pats, const uint64_t * pat_off, uint64_t n, uint64_t * cnt_out, uint64_t * l_out, void * stream)
     {
         SG_TRY(check_handle(h));

@@ -331,6 +331,9 @@ int finish_create(sdslgpu_group * g)
     for (int k = 0; k < g->nlocal; ++k)
     {
         SG_CUDA(cudaSetDevice(g->m[k].device));
+        cudaFuncAttributes fa; // loads the modules of the exchange / copy kernels now, not behind a spinning kernel
+        SG_CUDA(cudaFuncGetAttributes(&fa, group_barrier_kernel));
+        SG_CUDA(cudaFuncGetAttributes(&fa, fan_copy_kernel));
         SG_CUDA(cudaStreamCreateWithFlags(&g->m[k].stream, cudaStreamNonBlocking));
         SG_CUDA(cudaMalloc(reinterpret_cast<void **>(&g->m[k].status), 256));
         SG_CUDA(cudaMemset(g->m[k].status, 0, 256));
@@ -450,19 +453,26 @@ int group_run(sdslgpu_group * g, uint64_t n, uint64_t * const * out, int gather,
     for (int k = 0; k < g->nlocal; ++k)
         st[k] = (streams && streams[k]) ? static_cast<cudaStream_t>(streams[k]) : g->m[k].stream;
     bool const own_streams = streams == nullptr;
+    // Three passes over the local members, never a kernel launch of member k behind a flag exchange that waits for a
+    // member this same host thread has not launched yet: the first launch of a kernel loads its module, which can
+    // synchronise the context, and a spinning exchange kernel would then wait for a launch that cannot be issued.
+    std::vector<Fan> fans(g->nlocal);
+    if (mode == SDSLGPU_GATHER_FUSED)
+        for (int k = 0; k < g->nlocal; ++k)
+        {
+            GroupMember & me = g->m[k];
+            SG_CUDA(cudaSetDevice(me.device));
+            for (int r = 0; r < g->nranks; ++r)
+                if (r != me.rank)
+                    fans[k].dst[fans[k].n++] = reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(sb->peer[k][r]) + off0) + (uint64_t)me.rank * s;
+            SG_TRY(launch_barrier(g, k, ep_in, st[k])); // every member has reached this call: its result array may be written
+        }
     for (int k = 0; k < g->nlocal; ++k)
     {
         GroupMember & me = g->m[k];
         SG_CUDA(cudaSetDevice(me.device));
         uint64_t const first = (uint64_t)me.rank * s;
-        Fan fan;
-        if (mode == SDSLGPU_GATHER_FUSED)
-        {
-            for (int r = 0; r < g->nranks; ++r)
-                if (r != me.rank)
-                    fan.dst[fan.n++] = reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(sb->peer[k][r]) + off0) + first;
-            SG_TRY(launch_barrier(g, k, ep_in, st[k])); // every member has reached this call: its result array may be written
-        }
+        Fan const & fan = fans[k];
         if (s)
         {
             bool fanned = false;
@@ -478,9 +488,13 @@ int group_run(sdslgpu_group * g, uint64_t n, uint64_t * const * out, int gather,
             bool fanned = false;
             SG_TRY(shard(k, covered, n - covered, out[k] + covered, st[k], nullptr, &fanned));
         }
-        if (mode == SDSLGPU_GATHER_FUSED)
-            SG_TRY(launch_barrier(g, k, ep_out, st[k])); // everybody's stores into my array have landed
     }
+    if (mode == SDSLGPU_GATHER_FUSED)
+        for (int k = 0; k < g->nlocal; ++k)
+        {
+            SG_CUDA(cudaSetDevice(g->m[k].device));
+            SG_TRY(launch_barrier(g, k, ep_out, st[k])); // everybody's stores into my array have landed
+        }
     if (mode == SDSLGPU_GATHER_NCCL && s)
     {
         NcclApi * nc = nccl_api();
