@@ -234,6 +234,11 @@ static int wt_huff_build_on_device(sdslgpu_handle * h, uint8_t const * text, uin
     WtTree tree;
     uint64_t sigma = 0;
     uint64_t bits = build_huff_tree(C, tree, sigma);
+    if (bits == kWtTooDeep)
+    {
+        set_error("wt_huff: Huffman code deeper than 56 levels (the reference throws \"Code depth greater than 56!!!\", wt_helper.hpp:304-307)");
+        return SDSLGPU_EINVAL;
+    }
     uint64_t * d_words = nullptr;
     if (cudaMalloc(reinterpret_cast<void **>(&d_words), (((bits + 63) >> 6) + 2) * 8) != cudaSuccess)
     {
@@ -288,6 +293,11 @@ int wt_huff_build_from_text(sdslgpu_handle * h, uint8_t const * text, uint64_t n
     if (n)
     {
         bits = build_huff_tree(C, tree, sigma);
+        if (bits == kWtTooDeep)
+        {
+            set_error("wt_huff: Huffman code deeper than 56 levels (the reference throws \"Code depth greater than 56!!!\", wt_helper.hpp:304-307)");
+            return SDSLGPU_EINVAL;
+        }
         bv.assign(((bits + 63) >> 6) + 1, 0);
         fill_bit_planes(text, n, tree, bv);
     }

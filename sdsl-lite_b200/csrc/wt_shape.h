@@ -7,7 +7,6 @@
 #include <atomic>
 #include <cstdint>
 #include <cstring>
-#include <queue>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -20,98 +19,102 @@ namespace sdslgpu
 // ------------------------------------------------------------------------------------------------
 // host: Huffman shape + BFS layout (tiny), then the bit planes in parallel over text chunks
 // ------------------------------------------------------------------------------------------------
-namespace
-{
-struct PcNode
-{
-    uint64_t freq, sym, parent, child[2];
-};
-} // namespace
+static constexpr uint64_t kWtTooDeep = ~0ull; // build_huff_tree: a code longer than 56 bits (the reference throws)
 
-// Fills tree (bv_pos, children, parents, c_to_leaf, path) and returns the number of bits of m_bv.
-// Tie-breaking follows the reference exactly: min-heap ordered by (frequency, node number); the first
-// node popped becomes child 0 (wt_huff.hpp:102-114); nodes are renumbered in BFS order with the two
-// children of a node adjacent (wt_helper.hpp:236-271).
+// Fills tree (bv_pos, children, parents, c_to_leaf, path) and returns the number of bits of m_bv, or kWtTooDeep when
+// some symbol's code would be longer than the 56 bits a path word holds — the reference refuses such an input with
+// std::logic_error("Code depth greater than 56!!!") (wt_helper.hpp:304-307).
+//
+// The shape must be THE tree of the reference, because m_bv and the serialised node table are compared byte for byte:
+//  * merge order (wt_huff.hpp:82-115): always the two lightest subtrees, ties broken by node number; the lighter one
+//    becomes child 0.  Leaves are numbered by symbol, merged nodes in order of creation, so the classic two-queue form
+//    applies: leaves sorted by (weight, symbol) in one queue, merged nodes — created with non-decreasing weight — in a
+//    second; the next lightest subtree is at the head of one of them, and on equal weight the leaf wins (smaller number).
+//  * numbering (wt_helper.hpp:236-271): breadth first from the root, the two children of a node adjacent.
+// The code word of a symbol falls out of the same breadth-first pass: a child's word is its parent's with the branch
+// bit appended at position depth(parent) (bit j of a path = the branch taken at depth j, wt_pc.hpp:384-395).
 inline uint64_t build_huff_tree(uint64_t const (&C)[256], WtTree & tree, uint64_t & sigma)
 {
-    std::vector<PcNode> t;
-    typedef std::pair<uint64_t, uint64_t> P;
-    std::priority_queue<P, std::vector<P>, std::greater<P>> pq;
-    sigma = 0;
-    for (uint64_t c = 0; c < 256; ++c)
-        if (C[c] > 0)
-        {
-            pq.push(P(C[c], t.size()));
-            t.push_back(PcNode{C[c], c, ~0ull, {~0ull, ~0ull}});
-            ++sigma;
-        }
-    while (pq.size() > 1)
+    struct Sub // a subtree during the merge
     {
-        P a = pq.top();
-        pq.pop();
-        P b = pq.top();
-        pq.pop();
-        t[a.second].parent = t.size();
-        t[b.second].parent = t.size();
-        pq.push(P(a.first + b.first, t.size()));
-        t.push_back(PcNode{a.first + b.first, 0, ~0ull, {a.second, b.second}});
+        uint64_t weight;
+        uint32_t kid[2]; // kUndef32 for a leaf
+        uint32_t symbol;
+    };
+    constexpr uint32_t kUndef32 = 0xFFFFFFFFu;
+    std::vector<Sub> sub;
+    for (uint32_t c = 0; c < 256; ++c)
+        if (C[c])
+            sub.push_back(Sub{C[c], {kUndef32, kUndef32}, c});
+    sigma = sub.size();
+    std::vector<uint32_t> leaves(sub.size());
+    for (uint32_t k = 0; k < leaves.size(); ++k)
+        leaves[k] = k;
+    std::stable_sort(leaves.begin(), leaves.end(), [&](uint32_t a, uint32_t b) { return sub[a].weight < sub[b].weight; });
+    size_t lh = 0, mh = sigma; // heads of the leaf queue (`leaves`) and of the merged queue (sub[mh ...])
+    auto lightest = [&]() -> uint32_t {
+        bool const leaf_left = lh < leaves.size(), merged_left = mh < sub.size();
+        if (leaf_left && (!merged_left || sub[leaves[lh]].weight <= sub[mh].weight))
+            return leaves[lh++];
+        return (uint32_t)mh++;
+    };
+    for (uint64_t merges = sigma > 1 ? sigma - 1 : 0; merges > 0; --merges)
+    {
+        uint32_t const a = lightest(), b = lightest();
+        sub.push_back(Sub{sub[a].weight + sub[b].weight, {a, b}, 0});
     }
     std::memset(&tree, 0, sizeof(tree));
-    tree.nnodes = (uint32_t)t.size();
-    // BFS relabel
-    std::vector<uint64_t> src(t.size()); // BFS id -> index in t
-    std::vector<uint64_t> freq(t.size());
-    uint64_t bv_size = 0, node_cnt = 1, head = 0;
-    src[0] = t.size() - 1;
-    tree.parent[0] = kWtUndef;
-    while (head < node_cnt)
+    for (int c = 0; c < 256; ++c)
     {
-        uint64_t idx = head++;
-        PcNode const & p = t[src[idx]];
-        tree.bv_pos[idx] = bv_size;
-        if (p.child[0] != ~0ull)
-        {
-            bv_size += p.freq;
-            for (int k = 0; k < 2; ++k)
-            {
-                src[node_cnt] = p.child[k];
-                tree.parent[node_cnt] = (uint16_t)idx;
-                tree.child[idx][k] = (uint16_t)node_cnt++;
-            }
+        tree.c_to_leaf[c] = kWtUndef;
+        tree.path[c] = 0;
+    }
+    tree.nnodes = (uint32_t)sub.size();
+    if (sub.empty())
+        return 0;
+    // breadth-first numbering; origin[v] = which subtree became node v, word / depth = its code so far
+    std::vector<uint32_t> origin(sub.size());
+    std::vector<uint64_t> word(sub.size(), 0);
+    std::vector<uint32_t> depth(sub.size(), 0);
+    uint64_t bits = 0;
+    uint32_t placed = 1;
+    bool too_deep = false;
+    origin[0] = (uint32_t)sub.size() - 1; // the last merge is the root
+    tree.parent[0] = kWtUndef;
+    for (uint32_t v = 0; v < placed; ++v)
+    {
+        Sub const & me = sub[origin[v]];
+        tree.bv_pos[v] = bits;
+        if (me.kid[0] == kUndef32)
+        { // a leaf keeps its symbol in the rank field (wt_helper.hpp:119-137) and ends a code word
+            tree.child[v][0] = tree.child[v][1] = kWtUndef;
+            tree.bv_pos_rank[v] = me.symbol;
+            tree.c_to_leaf[me.symbol] = (uint16_t)v;
+            too_deep |= depth[v] > 56;
+            tree.path[me.symbol] = word[v] | ((uint64_t)depth[v] << 56);
+            continue;
         }
-        else
+        bits += me.weight; // an inner node owns one bit per symbol below it
+        for (uint32_t k = 0; k < 2; ++k, ++placed)
         {
-            tree.child[idx][0] = tree.child[idx][1] = kWtUndef;
-            tree.bv_pos_rank[idx] = p.sym; // leaves keep the symbol here (wt_helper.hpp:119-137)
+            origin[placed] = me.kid[k];
+            tree.parent[placed] = (uint16_t)v;
+            tree.child[v][k] = (uint16_t)placed;
+            depth[placed] = depth[v] + 1;
+            word[placed] = depth[v] < 64 ? (word[v] | ((uint64_t)k << depth[v])) : word[v];
         }
     }
-    for (int c = 0; c < 256; ++c)
-        tree.c_to_leaf[c] = kWtUndef;
-    for (uint64_t v = 0; v < t.size(); ++v)
-        if (tree.child[v][0] == kWtUndef)
-            tree.c_to_leaf[(uint8_t)tree.bv_pos_rank[v]] = (uint16_t)v;
-    uint64_t prev_c = 0;
+    // a symbol that does not occur has an empty code; its path word names the last occurring symbol before it
+    // (wt_helper.hpp:311-315) — part of the serialised tree
+    uint64_t last_present = 0;
     for (uint64_t c = 0; c < 256; ++c)
     {
         if (tree.c_to_leaf[c] != kWtUndef)
-        {
-            uint16_t v = tree.c_to_leaf[c];
-            uint64_t pw = 0, pl = 0;
-            while (v != 0)
-            {
-                pw <<= 1;
-                if (tree.child[tree.parent[v]][1] == v)
-                    pw |= 1;
-                ++pl;
-                v = tree.parent[v];
-            }
-            tree.path[c] = pw | (pl << 56);
-            prev_c = c;
-        }
+            last_present = c;
         else
-            tree.path[c] = prev_c; // length 0 (wt_helper.hpp:311-315 stores the previous symbol here)
+            tree.path[c] = last_present;
     }
-    return bv_size;
+    return too_deep ? kWtTooDeep : bits;
 }
 
 // The bit planes: chunk the text over T threads.  Per chunk and node the start offset is the node's

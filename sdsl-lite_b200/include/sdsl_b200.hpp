@@ -13,6 +13,7 @@
 // with set_vector (rank_support.hpp:33, util.hpp:414-432).  Errors from the C ABI become std::runtime_error
 // (the reference throws std::logic_error / std::runtime_error from constructors too).
 #pragma once
+#include <array>
 #include <cstdint>
 #include <fstream>
 #include <istream>
@@ -120,10 +121,21 @@ inline void set_device(int d)
 // bit_vector = int_vector<1> (int_vector.hpp:210-257): host words + a lazily built device image that
 // carries rank_support_v<0/1> and select_support_mcl<0/1>.
 // ------------------------------------------------------------------------------------------------------
+struct bv_tag;
+template <uint8_t t_b, class t_vec, uint8_t t_pat_len = 1>
+class rank_support;
+template <uint8_t t_b, class t_vec, uint8_t t_pat_len = 1>
+class select_support;
 class bit_vector
 {
 public:
     typedef sdsl_b200::size_type size_type;
+    typedef bv_tag index_category; // sdsl_concepts.hpp
+    typedef bool value_type;
+    typedef rank_support<1, bit_vector, 1> rank_1_type; // int_vector.hpp:227-231
+    typedef rank_support<0, bit_vector, 1> rank_0_type;
+    typedef select_support<1, bit_vector, 1> select_1_type;
+    typedef select_support<0, bit_vector, 1> select_0_type;
     bit_vector() = default;
     explicit bit_vector(size_type n, bool value = false) : m_size(n), m_words((n + 63) / 64 + 1, value ? ~0ull : 0ull)
     {
@@ -157,6 +169,34 @@ public:
     bool operator[](size_type i) const // int_vector.hpp:1900-1904
     {
         return (m_words[i >> 6] >> (i & 63)) & 1;
+    }
+    //! bv[i] = b (int_vector_reference<bit_vector>, int_vector.hpp:1006-1070)
+    class reference
+    {
+    public:
+        reference(bit_vector * v, size_type i) : m_v(v), m_i(i)
+        {}
+        reference & operator=(bool b)
+        {
+            m_v->set(m_i, b);
+            return *this;
+        }
+        reference & operator=(reference const & o)
+        {
+            return *this = (bool)o;
+        }
+        operator bool() const
+        {
+            return (m_v->m_words[m_i >> 6] >> (m_i & 63)) & 1;
+        }
+
+    private:
+        bit_vector * m_v;
+        size_type m_i;
+    };
+    reference operator[](size_type i)
+    {
+        return reference(this, i);
     }
     void set(size_type i, bool v)
     {
@@ -280,7 +320,7 @@ constexpr int pattern_code(uint8_t t_b, uint8_t t_pat_len)
 } // namespace detail
 
 //! rank_support_v<t_b,1> concept (rank_support_v.hpp:47-192) for any bit-vector type of this header.
-template <uint8_t t_b, class t_vec, uint8_t t_pat_len = 1>
+template <uint8_t t_b, class t_vec, uint8_t t_pat_len>
 class rank_support : public detail::support_base<t_vec>
 {
     using base = detail::support_base<t_vec>;
@@ -333,7 +373,7 @@ public:
     }
 };
 
-template <uint8_t t_b, class t_vec, uint8_t t_pat_len = 1>
+template <uint8_t t_b, class t_vec, uint8_t t_pat_len>
 class select_support : public detail::support_base<t_vec>
 {
     using base = detail::support_base<t_vec>;
@@ -425,6 +465,8 @@ public:
     typedef rank_support<0, compressed_vector> rank_0_type;
     typedef select_support<1, compressed_vector> select_1_type;
     typedef select_support<0, compressed_vector> select_0_type;
+    typedef bv_tag index_category;
+    typedef bool value_type;
     compressed_vector() = default;
     explicit compressed_vector(bit_vector const & bv) : m_size(bv.size())
     {
@@ -469,10 +511,123 @@ private:
 };
 } // namespace detail
 
-template <uint16_t t_bs = 63>
-using rrr_vector = detail::compressed_vector<SDSLGPU_KIND_RRR63>; // only t_bs = 63 is on the hot path
-template <int dummy = 0>
-using sd_vector = detail::compressed_vector<SDSLGPU_KIND_SD>;
+//! rrr_vector<t_bs, t_rac, t_k> (rrr_vector.hpp:67-76): only t_bs = 63, t_k = 32 is on the hot path
+template <uint16_t t_bs = 63, class t_rac = void, uint16_t t_k = 32>
+class rrr_vector : public detail::compressed_vector<SDSLGPU_KIND_RRR63>
+{
+    static_assert(t_bs == 63 && t_k == 32, "this engine implements rrr_vector<63, int_vector<>, 32> (the benchmarked block size)");
+
+public:
+    using detail::compressed_vector<SDSLGPU_KIND_RRR63>::compressed_vector;
+};
+//! sd_vector<t_hi_bit_vector, t_select_1, t_select_0> (sd_vector.hpp:131-136): the template arguments choose host-side
+//! component types in the reference; on the device `high` always is a sector-block image
+template <class t_hi_bit_vector = bit_vector, class t_select_1 = void, class t_select_0 = void>
+class sd_vector : public detail::compressed_vector<SDSLGPU_KIND_SD>
+{
+public:
+    using detail::compressed_vector<SDSLGPU_KIND_SD>::compressed_vector;
+};
+//! select_0_support_sd (sd_vector.hpp:752-978): select_0 straight from sampled pointers into `high`; here every
+//! select_support<0, sd_vector> already answers that way (csrc/sd_device.cuh sd_select0_one)
+template <class t_sd_vector = sd_vector<>>
+using select_0_support_sd = select_support<0, detail::compressed_vector<SDSLGPU_KIND_SD>>;
+
+// ------------------------------------------------------------------------------------------------------
+// category tags (sdsl_concepts.hpp:16-44) and the random-access iterator the containers hand out (iterators.hpp:21-140)
+// ------------------------------------------------------------------------------------------------------
+struct bv_tag {};
+struct iv_tag {};
+struct csa_tag {};
+struct cst_tag {};
+struct wt_tag {};
+struct psi_tag {};
+struct lf_tag {};
+struct csa_member_tag {};
+struct byte_alphabet_tag
+{
+    static constexpr uint8_t WIDTH = 8;
+};
+struct int_alphabet_tag
+{
+    static constexpr uint8_t WIDTH = 0;
+};
+
+template <class t_container>
+class random_access_const_iterator
+{
+public:
+    typedef std::random_access_iterator_tag iterator_category;
+    typedef decltype(std::declval<t_container const &>()[0]) value_type;
+    typedef std::ptrdiff_t difference_type;
+    typedef void pointer;
+    typedef value_type reference;
+    random_access_const_iterator() = default;
+    random_access_const_iterator(t_container const * c, size_type i = 0) : m_c(c), m_i(i)
+    {}
+    value_type operator*() const
+    {
+        return (*m_c)[m_i];
+    }
+    value_type operator[](difference_type d) const
+    {
+        return (*m_c)[m_i + d];
+    }
+    random_access_const_iterator & operator++()
+    {
+        ++m_i;
+        return *this;
+    }
+    random_access_const_iterator operator++(int)
+    {
+        random_access_const_iterator t = *this;
+        ++m_i;
+        return t;
+    }
+    random_access_const_iterator & operator--()
+    {
+        --m_i;
+        return *this;
+    }
+    random_access_const_iterator & operator+=(difference_type d)
+    {
+        m_i += d;
+        return *this;
+    }
+    random_access_const_iterator & operator-=(difference_type d)
+    {
+        m_i -= d;
+        return *this;
+    }
+    random_access_const_iterator operator+(difference_type d) const
+    {
+        return random_access_const_iterator(m_c, m_i + d);
+    }
+    random_access_const_iterator operator-(difference_type d) const
+    {
+        return random_access_const_iterator(m_c, m_i - d);
+    }
+    difference_type operator-(random_access_const_iterator const & o) const
+    {
+        return (difference_type)m_i - (difference_type)o.m_i;
+    }
+    bool operator==(random_access_const_iterator const & o) const
+    {
+        return m_i == o.m_i;
+    }
+    bool operator!=(random_access_const_iterator const & o) const
+    {
+        return m_i != o.m_i;
+    }
+    bool operator<(random_access_const_iterator const & o) const
+    {
+        return m_i < o.m_i;
+    }
+
+private:
+    t_container const * m_c = nullptr;
+    size_type m_i = 0;
+};
 
 // ------------------------------------------------------------------------------------------------------
 // wavelet trees (wt_pc.hpp:61-78, 314-474; wt_int.hpp:57-61, 340-507)
@@ -485,6 +640,9 @@ class wavelet_tree_base
 public:
     typedef sdsl_b200::size_type size_type;
     typedef t_sym value_type;
+    typedef wt_tag index_category;
+    typedef random_access_const_iterator<wavelet_tree_base> const_iterator;
+    typedef const_iterator iterator;
     size_type size() const
     {
         return m_size;
@@ -499,6 +657,14 @@ public:
         uint64_t s;
         check(sdslgpu_wt_access(image(), &i, 1, &s, nullptr, nullptr), "wt[i]");
         return (value_type)s;
+    }
+    const_iterator begin() const // wt_pc.hpp:694-701: the symbols in order (one scalar call each: for compatibility)
+    {
+        return const_iterator(this, 0);
+    }
+    const_iterator end() const
+    {
+        return const_iterator(this, m_size);
     }
     size_type rank(size_type i, value_type c) const
     {
@@ -543,6 +709,11 @@ public:
             throw std::runtime_error("empty wavelet tree");
         return m_image.get();
     }
+    //! a view of an image somebody else owns (csa.wavelet_tree / csa.bwt share the index's handle)
+    void share_image(handle_ptr p)
+    {
+        adopt_ptr(p);
+    }
 
 protected:
     void adopt_image(sdslgpu_handle * h)
@@ -560,41 +731,73 @@ protected:
     size_type m_size = 0;
     handle_ptr m_image;
 };
+
+template <class t_bitvector>
+struct wt_flags
+{
+    static constexpr uint32_t value = SDSLGPU_F_DEFAULT;
+};
+template <uint16_t t_bs, class t_rac, uint16_t t_k>
+struct wt_flags<rrr_vector<t_bs, t_rac, t_k>>
+{
+    static constexpr uint32_t value = SDSLGPU_F_RRR_BV; // wt_huff<rrr_vector<63>>: the H0-compressed tree
+};
 } // namespace detail
 
+//! wt_huff<t_bitvector, t_rank, t_select, t_select_zero, t_tree_strat> (wt_huff.hpp:56-67).  t_bitvector = bit_vector
+//! (default) or rrr_vector<63>; the support types are host-side choices of the reference — the device image carries
+//! its own rank blocks and select samples whatever they are.
+template <class t_bitvector = bit_vector, class t_rank = void, class t_select = void, class t_select_zero = void, class t_tree_strat = void>
 class wt_huff : public detail::wavelet_tree_base<uint8_t>
 {
 public:
-    wt_huff() = default;
-    //! wt_pc(t_it begin, t_it end) (wt_pc.hpp:194): any contiguous range of bytes
-    wt_huff(uint8_t const * begin, uint8_t const * end)
+    typedef byte_alphabet_tag alphabet_category;
+    typedef t_bitvector bit_vector_type;
+    enum
     {
+        lex_ordered = 0 // Huffman shape: not lexicographically ordered (wt_huff.hpp:49-53)
+    };
+    static constexpr uint32_t image_flags = detail::wt_flags<t_bitvector>::value;
+    wt_huff() = default;
+    //! wt_pc(t_it begin, t_it end, tmp_dir) (wt_pc.hpp:194): any range of bytes
+    template <class t_it>
+    wt_huff(t_it begin, t_it end, std::string const & = std::string())
+    {
+        std::vector<uint8_t> text(begin, end);
         sdslgpu_handle * h = nullptr;
-        check(sdslgpu_wt_huff_create(begin, (uint64_t)(end - begin), detail::default_device(), SDSLGPU_F_DEFAULT, &h), "wt_huff");
+        check(sdslgpu_wt_huff_create(text.data(), (uint64_t)text.size(), detail::default_device(), image_flags, &h), "wt_huff");
         adopt_image(h);
     }
-    explicit wt_huff(std::string const & text) : wt_huff(reinterpret_cast<uint8_t const *>(text.data()), reinterpret_cast<uint8_t const *>(text.data()) + text.size())
+    explicit wt_huff(std::string const & text) : wt_huff(text.begin(), text.end())
     {}
-    //! load (wt_pc.hpp:729-741): reads the rest of the stream
+    //! load (wt_pc.hpp:729-741): consumes exactly the tree's bytes
     void load(std::istream & in)
     {
-        adopt_ptr(detail::load_blob(in, SDSLGPU_KIND_WT_HUFF, SDSLGPU_F_DEFAULT, 0));
+        adopt_ptr(detail::load_blob(in, SDSLGPU_KIND_WT_HUFF, image_flags, 0));
     }
 };
 
+template <class t_bitvector = bit_vector, class t_rank = void, class t_select = void, class t_select_zero = void>
 class wt_int : public detail::wavelet_tree_base<uint64_t>
 {
 public:
-    wt_int() = default;
-    wt_int(uint64_t const * begin, uint64_t const * end)
+    typedef int_alphabet_tag alphabet_category;
+    enum
     {
+        lex_ordered = 1
+    };
+    wt_int() = default;
+    template <class t_it>
+    wt_int(t_it begin, t_it end, std::string const & = std::string())
+    {
+        std::vector<uint64_t> seq(begin, end);
         sdslgpu_handle * h = nullptr;
-        check(sdslgpu_wt_int_create(begin, (uint64_t)(end - begin), detail::default_device(), SDSLGPU_F_DEFAULT, &h), "wt_int");
+        check(sdslgpu_wt_int_create(seq.data(), (uint64_t)seq.size(), detail::default_device(), SDSLGPU_F_DEFAULT, &h), "wt_int");
         adopt_image(h);
     }
-    explicit wt_int(std::vector<uint64_t> const & seq) : wt_int(seq.data(), seq.data() + seq.size())
+    explicit wt_int(std::vector<uint64_t> const & seq) : wt_int(seq.begin(), seq.end())
     {}
-    //! load (wt_int.hpp:808-821): reads the rest of the stream
+    //! load (wt_int.hpp:808-821): consumes exactly the tree's bytes
     void load(std::istream & in)
     {
         adopt_ptr(detail::load_blob(in, SDSLGPU_KIND_WT_INT, SDSLGPU_F_DEFAULT, 0));
@@ -604,54 +807,207 @@ public:
 // ------------------------------------------------------------------------------------------------------
 // csa_wt<wt_huff<>> and the search algorithms (csa_wt.hpp:49-130; suffix_array_algorithm.hpp:166-248,463-570)
 // ------------------------------------------------------------------------------------------------------
-class csa_wt
+namespace detail
+{
+//! csa.bwt (suffix_array_helper.hpp:424-470): bwt[i], bwt.rank(i, c), bwt.select(i, c), size()
+class bwt_view
 {
 public:
     typedef sdsl_b200::size_type size_type;
+    typedef uint8_t value_type;
+    typedef csa_member_tag category;
+    typedef random_access_const_iterator<bwt_view> const_iterator;
+    bwt_view() = default;
+    explicit bwt_view(handle_ptr p, size_type n) : m_image(p), m_size(n)
+    {}
+    size_type size() const
+    {
+        return m_size;
+    }
+    bool empty() const
+    {
+        return m_size == 0;
+    }
+    value_type operator[](size_type i) const
+    {
+        uint64_t s;
+        check(sdslgpu_wt_access(m_image.get(), &i, 1, &s, nullptr, nullptr), "bwt[i]");
+        return (value_type)s;
+    }
+    size_type rank(size_type i, value_type c) const
+    {
+        uint64_t r;
+        check(sdslgpu_wt_rank(m_image.get(), &i, &c, 1, &r, nullptr), "bwt.rank");
+        return r;
+    }
+    size_type select(size_type i, value_type c) const
+    {
+        uint64_t r;
+        check(sdslgpu_wt_select(m_image.get(), &i, &c, 1, &r, nullptr), "bwt.select");
+        return r;
+    }
+    const_iterator begin() const
+    {
+        return const_iterator(this, 0);
+    }
+    const_iterator end() const
+    {
+        return const_iterator(this, m_size);
+    }
+
+private:
+    handle_ptr m_image;
+    size_type m_size = 0;
+};
+
+//! csa.lf (suffix_array_helper.hpp:346-360): lf[i] = C[char2comp[bwt[i]]] + bwt.rank(i, bwt[i])
+class lf_view
+{
+public:
+    typedef sdsl_b200::size_type size_type;
+    typedef size_type value_type;
+    typedef csa_member_tag category;
+    lf_view() = default;
+    lf_view(handle_ptr p, size_type n, std::vector<uint64_t> const * C, std::vector<uint8_t> const * c2c) : m_image(p), m_size(n), m_C(C), m_c2c(c2c)
+    {}
+    size_type size() const
+    {
+        return m_size;
+    }
+    value_type operator[](size_type i) const
+    {
+        uint64_t s, r;
+        check(sdslgpu_wt_access(m_image.get(), &i, 1, &s, &r, nullptr), "lf[i]"); // inverse_select: (rank(i, bwt[i]), bwt[i])
+        return (*m_C)[(*m_c2c)[s]] + r;
+    }
+
+private:
+    handle_ptr m_image;
+    size_type m_size = 0;
+    std::vector<uint64_t> const * m_C = nullptr;
+    std::vector<uint8_t> const * m_c2c = nullptr;
+};
+} // namespace detail
+
+//! csa_wt<t_wt, t_dens, t_inv_dens, t_sa_sample_strat, t_isa_sample_strat, t_alphabet_strat> (csa_wt.hpp:49-56) over a
+//! byte alphabet.  t_wt = wt_huff<> or wt_huff<rrr_vector<63>>; the sampling strategies are the reference's defaults
+//! (sa_order_sa_sampling, isa_sampling).  The public members backward_search / count / locate are written against in
+//! the reference — char2comp, comp2char, C, sigma, bwt, lf, wavelet_tree (csa_wt.hpp:117-130) — are here with the same
+//! names and meaning.
+template <class t_wt = wt_huff<>, uint32_t t_dens = 32, uint32_t t_inv_dens = 64, class t_sa_sample_strat = void, class t_isa_sample_strat = void,
+          class t_alphabet_strat = void>
+class csa_wt
+{
+public:
+    enum
+    {
+        sa_sample_dens = t_dens,
+        isa_sample_dens = t_inv_dens
+    };
+    typedef sdsl_b200::size_type size_type;
+    typedef uint64_t value_type;
+    typedef std::ptrdiff_t difference_type;
     typedef uint8_t char_type;
+    typedef uint8_t comp_char_type;
     typedef std::string string_type;
+    typedef t_wt wavelet_tree_type;
+    typedef detail::bwt_view bwt_type;
+    typedef detail::lf_view lf_type;
+    typedef csa_tag index_category;
+    typedef lf_tag extract_category;
+    typedef byte_alphabet_tag alphabet_category;
+    typedef random_access_const_iterator<csa_wt> const_iterator;
+    typedef const_iterator iterator;
+
+    std::vector<uint8_t> char2comp; // csa_wt.hpp:117-120: 256 / sigma / sigma + 1 entries
+    std::vector<uint8_t> comp2char;
+    std::vector<uint64_t> C;
+    uint16_t sigma = 0;
+    bwt_type bwt; // csa_wt.hpp:122-127
+    bwt_type L;
+    lf_type lf;
+    wavelet_tree_type wavelet_tree;
+
     csa_wt() = default;
-    //! construct(csa, text, 1) / construct_im(csa, text, 1): the text must not contain a 0 byte (construct.hpp:34-46)
-    //! t_dens / t_inv_dens (csa_wt.hpp:50-51) are run-time arguments here; 0 = the reference's defaults 32 / 64
-    explicit csa_wt(std::string const & text, uint32_t t_dens = 0, uint32_t t_inv_dens = 0)
+    //! the text must not contain a 0 byte (construct.hpp:34-46); what construct_im(csa, text, 1) does
+    explicit csa_wt(std::string const & text)
     {
         sdslgpu_handle * h = nullptr;
-        check(sdslgpu_csa_create_ex(reinterpret_cast<uint8_t const *>(text.data()), text.size(), detail::default_device(), SDSLGPU_F_DEFAULT, t_dens, t_inv_dens, &h),
+        uint32_t const flags = t_wt::image_flags;
+        check(sdslgpu_csa_create_ex(reinterpret_cast<uint8_t const *>(text.data()), text.size(), detail::default_device(), flags, t_dens, t_inv_dens, &h),
               "csa_wt");
-        m_image = detail::adopt(h);
-        check(sdslgpu_size(h, &m_size), "size");
+        bind(detail::adopt(h));
+    }
+    csa_wt(csa_wt const & o)
+    {
+        *this = o;
+    }
+    csa_wt & operator=(csa_wt const & o)
+    {
+        if (this != &o)
+        {
+            if (o.m_image)
+                bind(o.m_image); // views are re-pointed at this object's own tables (util::init_support in the reference)
+            else
+                clear();
+        }
+        return *this;
+    }
+    csa_wt(csa_wt && o) noexcept
+    {
+        if (o.m_image)
+            bind(o.m_image);
+    }
+    csa_wt & operator=(csa_wt && o) noexcept
+    {
+        if (this != &o && o.m_image)
+            bind(o.m_image);
+        return *this;
     }
     size_type size() const
     {
         return m_size;
     }
+    bool empty() const
+    {
+        return m_size == 0;
+    }
+    static size_type max_size()
+    {
+        return ~(size_type)0 >> 8;
+    }
     //! csa[i]: the i-th suffix array entry (csa_wt.hpp:363-381)
-    size_type operator[](size_type i) const
+    value_type operator[](size_type i) const
     {
         uint64_t r;
         check(sdslgpu_fm_sa(image(), &i, 1, &r, nullptr), "csa[i]");
         return r;
     }
-    //! csa.bwt.rank(i, c) (suffix_array_helper.hpp:461-464)
+    const_iterator begin() const
+    {
+        return const_iterator(this, 0);
+    }
+    const_iterator end() const
+    {
+        return const_iterator(this, m_size);
+    }
+    //! csa.bwt.rank(i, c) (suffix_array_helper.hpp:461-464); kept from the first version of this header
     size_type rank_bwt(size_type i, char_type c) const
     {
-        uint64_t r;
-        check(sdslgpu_wt_rank(image(), &i, &c, 1, &r, nullptr), "rank_bwt");
-        return r;
+        return bwt.rank(i, c);
     }
     //! serialize (csa_wt.hpp:389-402): wavelet tree, SA samples, ISA samples, alphabet — the reference's bytes
     size_type serialize(std::ostream & out) const
     {
         return detail::write_blob(image(), 0, out);
     }
-    //! load (csa_wt.hpp:410-416): reads the rest of the stream; t_dens is a template argument in the reference and is
-    //! not stored in the file, so an index sampled at another density needs it named here (0 = 32)
+    //! load (csa_wt.hpp:410-416): consumes exactly the index's bytes.  The densities are template arguments, as in the
+    //! reference, and are checked against the sample counts in the file.
     //! flags: SDSLGPU_F_V5_SCAN for the reference's wt_huff<bit_vector, rank_support_v5<>, select_support_scan<>, ...>
-    //! form (its count benchmark's FM_HUFF), SDSLGPU_F_RRR_BV for wt_huff<rrr_vector<63>>, SDSLGPU_F_COMPACT
-    void load(std::istream & in, uint32_t t_dens = 0, uint32_t flags = SDSLGPU_F_DEFAULT)
+    //! form (its count benchmark's FM_HUFF), SDSLGPU_F_COMPACT to keep the tree as the only occurrence structure
+    void load(std::istream & in, uint32_t flags = SDSLGPU_F_DEFAULT)
     {
-        m_image = detail::load_blob(in, SDSLGPU_KIND_CSA_WT, flags, t_dens);
-        check(sdslgpu_size(m_image.get(), &m_size), "size");
+        bind(detail::load_blob(in, SDSLGPU_KIND_CSA_WT, flags | t_wt::image_flags, t_dens, t_inv_dens));
     }
     sdslgpu_handle const * image() const
     {
@@ -661,27 +1017,142 @@ public:
     }
 
 private:
+    void clear()
+    {
+        m_image.reset();
+        m_size = 0;
+        sigma = 0;
+        char2comp.clear();
+        comp2char.clear();
+        C.clear();
+        bwt = L = bwt_type();
+        lf = lf_type();
+        wavelet_tree = wavelet_tree_type();
+    }
+    void bind(detail::handle_ptr p)
+    {
+        m_image = p;
+        check(sdslgpu_size(p.get(), &m_size), "size");
+        uint64_t c[257];
+        uint8_t c2c[256], cc2[256];
+        uint32_t sg = 0;
+        check(sdslgpu_csa_alphabet(p.get(), c, c2c, cc2, &sg), "alphabet");
+        sigma = (uint16_t)sg;
+        char2comp.assign(c2c, c2c + 256);
+        comp2char.assign(cc2, cc2 + sg);
+        C.assign(c, c + sg + 1);
+        bwt = bwt_type(p, m_size);
+        L = bwt;
+        lf = lf_type(p, m_size, &C, &char2comp);
+        wavelet_tree.share_image(p);
+    }
     size_type m_size = 0;
     detail::handle_ptr m_image;
 };
 
+//! construct_im(idx, data, num_bytes) (construct.hpp:69-92) and construct(idx, file, num_bytes) (construct.hpp:127-193)
+//! for the index types of this header: num_bytes must be 1 (a byte sequence).  Construction itself runs on the
+//! device (suffix array by prefix doubling, BWT, samples, wavelet tree).
+template <class t_wt, uint32_t t_dens, uint32_t t_inv_dens, class A, class B, class Cc>
+void construct_im(csa_wt<t_wt, t_dens, t_inv_dens, A, B, Cc> & idx, std::string const & data, uint8_t num_bytes = 1)
+{
+    if (num_bytes != 1)
+        throw std::runtime_error("construct_im: byte alphabets only (num_bytes = 1)");
+    idx = csa_wt<t_wt, t_dens, t_inv_dens, A, B, Cc>(data);
+}
+template <class t_bv, class A, class B, class Cc, class D>
+void construct_im(wt_huff<t_bv, A, B, Cc, D> & idx, std::string const & data, uint8_t num_bytes = 1)
+{
+    if (num_bytes != 1)
+        throw std::runtime_error("construct_im: byte alphabets only (num_bytes = 1)");
+    idx = wt_huff<t_bv, A, B, Cc, D>(data.begin(), data.end());
+}
+template <class t_index>
+void construct(t_index & idx, std::string const & file, uint8_t num_bytes = 1)
+{
+    std::ifstream in(file, std::ios::binary);
+    if (!in)
+        throw std::runtime_error("construct: cannot open " + file);
+    std::string data((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    construct_im(idx, data, num_bytes);
+}
+
 //! sdsl::count(csa, begin, end) (suffix_array_algorithm.hpp:463-471)
-template <class t_pat_iter>
-size_type count(csa_wt const & csa, t_pat_iter begin, t_pat_iter end)
+template <class t_csa, class t_pat_iter, class = typename std::enable_if<std::is_same<typename t_csa::index_category, csa_tag>::value>::type>
+typename t_csa::size_type count(t_csa const & csa, t_pat_iter begin, t_pat_iter end)
 {
     std::string p(begin, end);
     uint64_t off[2] = {0, p.size()}, cnt = 0;
     check(sdslgpu_fm_count(csa.image(), reinterpret_cast<uint8_t const *>(p.data()), off, 1, &cnt, nullptr, nullptr), "count");
     return cnt;
 }
-inline size_type count(csa_wt const & csa, std::string const & pat)
+template <class t_csa, class = typename std::enable_if<std::is_same<typename t_csa::index_category, csa_tag>::value>::type>
+typename t_csa::size_type count(t_csa const & csa, typename t_csa::string_type const & pat)
 {
     return count(csa, pat.begin(), pat.end());
 }
 
+//! backward_search(csa, l, r, c, l_res, r_res) (suffix_array_algorithm.hpp:166-201): one step, the two bwt.rank calls of
+//! the reference in one launch.  Returns the size of the new interval.
+template <class t_csa, class = typename std::enable_if<std::is_same<typename t_csa::index_category, csa_tag>::value>::type>
+typename t_csa::size_type backward_search(t_csa const & csa, typename t_csa::size_type l, typename t_csa::size_type r, typename t_csa::char_type c,
+                                          typename t_csa::size_type & l_res, typename t_csa::size_type & r_res)
+{
+    typename t_csa::size_type const cc = csa.char2comp[c];
+    if (cc == 0 && c > 0)
+    { // character is not in the text: the empty interval [1, 0]
+        l_res = 1;
+        r_res = 0;
+        return 0;
+    }
+    typename t_csa::size_type const c_begin = csa.C[cc];
+    if (l == 0 && r + 1 == csa.size())
+    { // the whole suffix array: the table alone answers
+        l_res = c_begin;
+        r_res = csa.C[cc + 1] - 1;
+    }
+    else
+    {
+        uint64_t pos[2] = {l, r + 1}, rk[2];
+        uint8_t sym[2] = {c, c};
+        check(sdslgpu_wt_rank(csa.image(), pos, sym, 2, rk, nullptr), "backward_search");
+        l_res = c_begin + rk[0];
+        r_res = c_begin + rk[1] - 1;
+    }
+    return r_res + 1 - l_res;
+}
+
+//! backward_search(csa, l, r, begin, end, l_res, r_res) (suffix_array_algorithm.hpp:227-248): a whole pattern from an
+//! arbitrary interval; from the full interval it is one call of the count kernel, otherwise step by step
+template <class t_csa, class t_pat_iter, class = typename std::enable_if<std::is_same<typename t_csa::index_category, csa_tag>::value>::type>
+typename t_csa::size_type backward_search(t_csa const & csa, typename t_csa::size_type l, typename t_csa::size_type r, t_pat_iter begin, t_pat_iter end,
+                                          typename t_csa::size_type & l_res, typename t_csa::size_type & r_res)
+{
+    t_pat_iter it = end;
+    while (begin < it && r + 1 - l > 0)
+    {
+        --it;
+        backward_search(csa, l, r, (typename t_csa::char_type) * it, l_res, r_res);
+        l = l_res;
+        r = r_res;
+    }
+    l_res = l;
+    r_res = r;
+    return r + 1 - l;
+}
+
+//! lex_interval(csa, begin, end) (suffix_array_algorithm.hpp:512-517): {l, r} of the pattern, r < l if it does not occur
+template <class t_csa, class t_pat_iter, class = typename std::enable_if<std::is_same<typename t_csa::index_category, csa_tag>::value>::type>
+std::array<typename t_csa::size_type, 2> lex_interval(t_csa const & csa, t_pat_iter begin, t_pat_iter end)
+{
+    std::array<typename t_csa::size_type, 2> res;
+    backward_search(csa, 0, csa.size() - 1, begin, end, res[0], res[1]);
+    return res;
+}
+
 //! sdsl::locate(csa, begin, end): all occurrences, in suffix-array order (suffix_array_algorithm.hpp:534-550)
-template <class t_pat_iter>
-std::vector<uint64_t> locate(csa_wt const & csa, t_pat_iter begin, t_pat_iter end)
+template <class t_csa, class t_pat_iter, class = typename std::enable_if<std::is_same<typename t_csa::index_category, csa_tag>::value>::type>
+std::vector<uint64_t> locate(t_csa const & csa, t_pat_iter begin, t_pat_iter end)
 {
     std::string p(begin, end);
     uint64_t off[2] = {0, p.size()}, occ_off[2], total = 0;
@@ -692,13 +1163,15 @@ std::vector<uint64_t> locate(csa_wt const & csa, t_pat_iter begin, t_pat_iter en
         check(sdslgpu_fm_locate(csa.image(), bytes, off, 1, occ_off, occ.data(), total, &total, nullptr), "locate");
     return occ;
 }
-inline std::vector<uint64_t> locate(csa_wt const & csa, std::string const & pat)
+template <class t_csa, class = typename std::enable_if<std::is_same<typename t_csa::index_category, csa_tag>::value>::type>
+std::vector<uint64_t> locate(t_csa const & csa, typename t_csa::string_type const & pat)
 {
     return locate(csa, pat.begin(), pat.end());
 }
 
 //! sdsl::extract(csa, begin, end): text[begin..end], end inclusive (suffix_array_algorithm.hpp:645-665)
-inline std::string extract(csa_wt const & csa, size_type begin, size_type end)
+template <class t_csa, class = typename std::enable_if<std::is_same<typename t_csa::index_category, csa_tag>::value>::type>
+typename t_csa::string_type extract(t_csa const & csa, typename t_csa::size_type begin, typename t_csa::size_type end)
 {
     std::string out(end - begin + 1, '\0');
     uint64_t off[2] = {0, end - begin + 1};
@@ -707,7 +1180,8 @@ inline std::string extract(csa_wt const & csa, size_type begin, size_type end)
 }
 
 //! batch count: one launch for the whole pattern set
-inline std::vector<uint64_t> count(csa_wt const & csa, std::vector<std::string> const & pats)
+template <class t_csa, class = typename std::enable_if<std::is_same<typename t_csa::index_category, csa_tag>::value>::type>
+std::vector<uint64_t> count(t_csa const & csa, std::vector<std::string> const & pats)
 {
     std::string flat;
     std::vector<uint64_t> off(pats.size() + 1, 0), cnt(pats.size());
@@ -722,7 +1196,8 @@ inline std::vector<uint64_t> count(csa_wt const & csa, std::vector<std::string> 
 }
 
 //! batch locate: occurrences of pattern k are occ[occ_off[k] .. occ_off[k+1]) in suffix-array order
-inline void locate(csa_wt const & csa, std::vector<std::string> const & pats, std::vector<uint64_t> & occ_off, std::vector<uint64_t> & occ)
+template <class t_csa, class = typename std::enable_if<std::is_same<typename t_csa::index_category, csa_tag>::value>::type>
+void locate(t_csa const & csa, std::vector<std::string> const & pats, std::vector<uint64_t> & occ_off, std::vector<uint64_t> & occ)
 {
     std::string flat;
     std::vector<uint64_t> off(pats.size() + 1, 0);
@@ -769,6 +1244,12 @@ size_type size_in_bytes(T const & v)
 {
     std::ostringstream os;
     return v.serialize(os);
+}
+//! sdsl::size_in_mega_bytes(v) (io.hpp:788-794)
+template <class T>
+double size_in_mega_bytes(T const & v)
+{
+    return (double)size_in_bytes(v) / (1024.0 * 1024.0);
 }
 
 } // namespace sdsl_b200

@@ -137,7 +137,7 @@ int main(int argc, char ** argv)
     std::string text;
     for (int j = 0; j < 20000; ++j)
         text += (char)("abracadabra_$%&XYZ"[rng() % 18]);
-    wt_huff wt(text);
+    wt_huff<> wt(text);
     {
         std::string u(text);
         std::sort(u.begin(), u.end());
@@ -164,7 +164,7 @@ int main(int argc, char ** argv)
     std::vector<uint64_t> seq(5000);
     for (auto & x : seq)
         x = rng() % 1000;
-    wt_int wi(seq);
+    wt_int<> wi(seq);
     EXPECT(wi.size() == seq.size());
     for (uint64_t j = 0; j < seq.size(); j += 97)
     {
@@ -173,7 +173,7 @@ int main(int argc, char ** argv)
     }
     // ---- csa_wt + count / locate (examples/fm-index.cpp:64-69)
     std::string t2 = "abracadabra abracadabra simsalabim abracadabra";
-    csa_wt csa(t2);
+    csa_wt<> csa(t2);
     EXPECT(csa.size() == t2.size() + 1);
     EXPECT(count(csa, std::string("abra")) == 6);
     EXPECT(count(csa, std::string("")) == t2.size() + 1 && count(csa, std::string("xyz")) == 0);
@@ -201,21 +201,21 @@ int main(int argc, char ** argv)
         std::stringstream ss;
         uint64_t written = wt.serialize(ss);
         EXPECT(written == ss.str().size() && written == size_in_bytes(wt));
-        wt_huff wt2;
+        wt_huff<> wt2;
         wt2.load(ss);
         EXPECT(wt2.size() == wt.size() && wt2.sigma == wt.sigma);
         for (uint64_t j = 0; j < text.size(); j += 131)
             EXPECT(wt2[j] == wt[j] && wt2.rank(j, (uint8_t)text[j]) == wt.rank(j, (uint8_t)text[j]));
         std::string file = "/tmp/sdsl_b200_shim_test.csa";
         EXPECT(store_to_file(csa, file));
-        csa_wt csa2;
+        csa_wt<> csa2;
         EXPECT(load_from_file(csa2, file) && csa2.size() == csa.size());
         EXPECT(count(csa2, std::string("abra")) == 6 && extract(csa2, 12, 22) == "abracadabra");
         EXPECT(!load_from_file(csa2, "/nonexistent/dir/x.csa"));
         std::remove(file.c_str());
         std::stringstream s2, s3;
         wi.serialize(s2);
-        wt_int wi2;
+        wt_int<> wi2;
         wi2.load(s2);
         EXPECT(wi2.size() == wi.size() && wi2[5] == wi[5]);
         bit_vector bv(5000);

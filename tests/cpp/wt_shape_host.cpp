@@ -45,3 +45,20 @@ extern "C" uint64_t wt_shape_host(uint8_t const * text, uint64_t n, uint64_t * b
         std::memcpy(bv_out, bv.data(), nw * 8);
     return bits;
 }
+
+// the shape alone from a histogram: number of bits of m_bv, or ~0 when a code would be deeper than 56 levels
+// (the reference throws there, wt_helper.hpp:304-307); max_depth_out = longest code length
+extern "C" uint64_t wt_shape_from_histogram(uint64_t const * C256, uint32_t * max_depth_out)
+{
+    uint64_t C[256];
+    std::memcpy(C, C256, sizeof(C));
+    WtTree tree;
+    uint64_t sigma = 0;
+    uint64_t bits = build_huff_tree(C, tree, sigma);
+    uint32_t d = 0;
+    for (int c = 0; c < 256; ++c)
+        if (tree.c_to_leaf[c] != kWtUndef && (uint32_t)(tree.path[c] >> 56) > d)
+            d = (uint32_t)(tree.path[c] >> 56);
+    *max_depth_out = d;
+    return bits;
+}

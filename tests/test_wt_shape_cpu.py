@@ -27,6 +27,8 @@ def shape():
     vp, u64 = ctypes.c_void_p, ctypes.c_uint64
     L.wt_shape_host.restype = u64
     L.wt_shape_host.argtypes = [vp, u64, vp, u64, vp, u64, vp, vp]
+    L.wt_shape_from_histogram.restype = u64
+    L.wt_shape_from_histogram.argtypes = [vp, vp]
 
     def run(t):
         a = np.ascontiguousarray(np.frombuffer(t, dtype=np.uint8))
@@ -38,6 +40,7 @@ def shape():
         assert (bits + 63) // 64 <= cap_words
         return int(bits), bv[: (bits + 63) // 64].tobytes(), tree[: tb.value].tobytes(), int(sg.value)
 
+    run.lib = L
     return run
 
 
@@ -61,3 +64,24 @@ def test_shape_bits_and_tree_equal_the_reference(shape, ref):
         assert hdr == (1 << 56) | bits, (name, "m_bv size")
         assert blob[24 : 24 + len(bv)] == bv, (name, "m_bv words")
         assert blob[-len(tree) :] == tree, (name, "byte_tree")
+
+
+def test_code_depth_guard(shape):
+    """Fibonacci weights give the deepest Huffman tree: k symbols -> depth k - 1.  57 symbols (depth 56) are the deepest
+    the path words can hold; 58 must be refused, as the reference does (wt_helper.hpp:304-307)"""
+    def depth_of(k):
+        C = np.zeros(256, np.uint64)
+        a, b = 1, 1
+        for j in range(k):
+            C[j] = a
+            a, b = b, a + b
+        d = ctypes.c_uint32(0)
+        bits = shape.lib.wt_shape_from_histogram(C.ctypes.data, ctypes.byref(d))
+        return bits, d.value
+
+    bits, d = depth_of(57)
+    assert bits != 2**64 - 1 and d == 56
+    bits, d = depth_of(58)
+    assert bits == 2**64 - 1
+    bits, d = depth_of(20)
+    assert d == 19
