@@ -2,20 +2,26 @@
 //
 // Replaces the sequential fill of the reference's constructors (wt_pc.hpp:194-248 insert_char per symbol,
 // wt_int.hpp:168-260 one stable partition per level) — 13.6 s on one core for the 2^28-byte tree of BASELINE
-// config 4 — by one stable radix pass per tree depth:
+// config 4 — by one stable regrouping pass per tree depth:
 //   wt_huff: nodes are numbered in BFS order and m_bv concatenates them in that order, so the bits of depth l are the
 //            contiguous range [bv_pos(first node of depth l), bv_pos(first node of depth l+1)), and inside it the
-//            symbols appear grouped by node, in text order.  Sorting the sequence stably by "inner node at depth l"
-//            (symbols whose code is already finished sort behind everything and drop out) therefore yields the bits
-//            of depth l in order; the sorted sequence is the input of depth l+1.
+//            symbols appear grouped by node, in text order.  The sequence grouped by "inner node at depth l" (symbols
+//            whose code is already finished drop out) therefore yields the bits of depth l in order, and regrouped by
+//            the nodes one depth further down it is the input of depth l+1.
 //   wt_int:  level k of m_tree is the sequence stably sorted by its top k bits; bit = the next lower bit.
-// The Huffman shape itself (<= 511 nodes) stays on the host (wt.cu build_huff_tree).  Sorting primitive:
-// cub::DeviceRadixSort (CCCL, shipped with the toolkit) as in gpu_sa.cu — builder only, no query kernel uses it.
+// The Huffman shape itself (<= 511 nodes) stays on the host (wt_shape.h build_huff_tree).
+// wt_huff needs no sort at all: going one depth down, the elements of every node are split STABLY by their code bit —
+// zeros to child 0, ones to child 1, elements whose code ends drop out — and where a child's elements start is known
+// from the tree (bv_pos).  So an element's destination is "start of its child + number of elements of its node with the
+// same bit before it", and that number is a rank query on the bits just written: one popcount pass + scan.cuh's prefix
+// sum + one scatter pass per depth (wt_split_kernel), all hand-written.  wt_int keeps cub::DeviceRadixSort (its nodes
+// are not known in advance) — builder only, no query kernel uses it.
 // The result is checked bit for bit against the host builders and the reference (tests/test_wt_gpu.py,
 // tests/test_egress_gpu.py compare complete serialised trees).
 #include <cub/device/device_radix_sort.cuh>
 
 #include "internal.h"
+#include "scan.cuh"
 #include "wt_device.cuh"
 
 namespace sdslgpu
@@ -43,8 +49,8 @@ struct Buf
     }
 };
 
-// per tree depth: sort key of every symbol (inner node at that depth, relative to the depth's first node; kDrop
-// position = "code finished") and the bit its code has there
+// per tree depth: the inner node every symbol sits in at that depth (relative to the depth's first node) and the bit
+// its code has there
 struct LevelLut
 {
     uint16_t key[256];
@@ -62,16 +68,6 @@ __global__ void __launch_bounds__(kThreads) wt_hist_kernel(uint8_t const * __res
     __syncthreads();
     if (h[threadIdx.x])
         atomicAdd(&hist[threadIdx.x], (unsigned long long)h[threadIdx.x]);
-}
-
-__global__ void __launch_bounds__(kThreads) wt_level_keys_kernel(uint8_t const * __restrict__ vals, uint64_t cnt, LevelLut const * __restrict__ lut, uint16_t * __restrict__ keys)
-{
-    __shared__ uint16_t key[256];
-    key[threadIdx.x] = lut->key[threadIdx.x];
-    __syncthreads();
-    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += stride)
-        keys[k] = key[vals[k]];
 }
 
 // bits [start, start + m) of the output vector = bit of the m first elements of the sorted sequence.  One warp
@@ -99,6 +95,69 @@ __global__ void __launch_bounds__(kThreads)
         uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
         if (lane == 0 && word)
             atomicOr(out32 + u, word);
+    }
+}
+
+// ones per 32-bit word of the bit range just written: the input of the prefix sum behind wt_split_kernel
+__global__ void __launch_bounds__(kThreads) wt_word_popc_kernel(uint32_t const * __restrict__ words32, uint64_t u0, uint64_t nwords, uint32_t * __restrict__ cnt)
+{
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nwords; k += stride)
+        cnt[k] = (uint32_t)__popc(words32[u0 + k]);
+}
+
+// the inner nodes of one tree depth, as the split needs them (indexed like LevelLut::key: relative to the depth's first node)
+struct LevelNodes
+{
+    uint64_t seg_start[256]; // first element of the node in the depth's sequence
+    uint64_t dst[2][256];    // where the elements going to child 0 / 1 start in the NEXT depth's sequence; kDropDst: a leaf
+};
+static constexpr uint64_t kDropDst = ~0ull;
+
+// One depth down: element i of the current sequence (symbol c, inner node v = key[c], code bit b) moves to
+// dst[b][v] + (number of elements of v with bit b before i).  The bits of the current depth already sit in the output
+// vector at [start, start + cnt); `prefix` holds, per 32-bit word from word start / 32 on, the ones before that word.
+__global__ void __launch_bounds__(kThreads) wt_split_kernel(uint8_t const * __restrict__ cur,
+                                                            uint64_t cnt,
+                                                            LevelLut const * __restrict__ lut,
+                                                            LevelNodes const * __restrict__ nodes,
+                                                            uint32_t nnodes,
+                                                            uint32_t const * __restrict__ words32,
+                                                            uint64_t const * __restrict__ prefix,
+                                                            uint64_t start,
+                                                            uint8_t * __restrict__ nxt)
+{
+    __shared__ uint16_t key[256];
+    __shared__ uint32_t mask[8];
+    __shared__ uint64_t seg_start[256], seg_ones[256], dst0[256], dst1[256];
+    uint64_t const u0 = start >> 5;
+    // ones in bits [u0 * 32, x) of the output vector
+    auto ones_before = [&](uint64_t x) -> uint64_t {
+        uint64_t const u = x >> 5;
+        uint32_t const o = (uint32_t)(x & 31u);
+        return prefix[u - u0] + (o ? (uint64_t)__popc(words32[u] & ((1u << o) - 1u)) : 0ull);
+    };
+    uint32_t const t = threadIdx.x; // kThreads == 256
+    key[t] = lut->key[t];
+    if (t < 8)
+        mask[t] = lut->bit[t];
+    uint64_t const base_ones = ones_before(start);
+    if (t < nnodes)
+    {
+        seg_start[t] = nodes->seg_start[t];
+        dst0[t] = nodes->dst[0][t];
+        dst1[t] = nodes->dst[1][t];
+        seg_ones[t] = ones_before(start + nodes->seg_start[t]) - base_ones;
+    }
+    __syncthreads();
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + t; i < cnt; i += stride)
+    {
+        uint32_t const c = cur[i], v = key[c], b = (mask[c >> 5] >> (c & 31u)) & 1u;
+        uint64_t const r1 = ones_before(start + i) - base_ones - seg_ones[v]; // ones of node v before element i
+        uint64_t const d = b ? dst1[v] : dst0[v];
+        if (d != kDropDst)
+            nxt[d + (b ? r1 : (i - seg_start[v]) - r1)] = (uint8_t)c;
     }
 }
 
@@ -196,24 +255,47 @@ int wt_huff_planes_device(uint8_t const * d_text, uint64_t n, WtTree const & tre
     first[maxd + 1] = nn;
     auto bv_start = [&](uint32_t v) { return v < nn ? tree.bv_pos[v] : bits; };
 
-    Buf bufa, bufb, k0, k1, luts, cubtmp;
-    size_t cub_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint16_t const *)nullptr, (uint16_t *)nullptr, (uint8_t const *)nullptr, (uint8_t *)nullptr, n, 0, 16, s);
-    if (bufa.alloc(n) != cudaSuccess || bufb.alloc(n) != cudaSuccess || k0.alloc(n * 2) != cudaSuccess || k1.alloc(n * 2) != cudaSuccess ||
-        luts.alloc((maxd + 1) * sizeof(LevelLut)) != cudaSuccess || cubtmp.alloc(cub_bytes) != cudaSuccess)
+    Buf bufa, bufb, luts, lnodes, wcnt, wpre, stmp;
+    uint64_t const max_words32 = (n + 31) / 32 + 2; // a depth never has more than n bits
+    if (bufa.alloc(n) != cudaSuccess || bufb.alloc(n) != cudaSuccess || luts.alloc((maxd + 1) * sizeof(LevelLut)) != cudaSuccess ||
+        lnodes.alloc((maxd + 1) * sizeof(LevelNodes)) != cudaSuccess || wcnt.alloc(max_words32 * 4) != cudaSuccess ||
+        wpre.alloc((max_words32 + 1) * 8) != cudaSuccess || stmp.alloc(scan_tmp_words(max_words32) * 8) != cudaSuccess)
     {
         cudaGetLastError();
         return SDSLGPU_ENOTSUP;
     }
-    // sort keys / code bits of every symbol at every depth
+    // per depth: the node (relative to the depth's first) and the code bit of every symbol; per inner node of the depth:
+    // where its elements start and where those of its two children start one depth further down
     std::vector<LevelLut> lut(maxd + 1);
-    std::vector<uint32_t> drop(maxd + 1);
+    std::vector<LevelNodes> nodes(maxd + 1);
     for (uint32_t l = 0; l <= maxd; ++l)
     {
-        drop[l] = first[l + 1] - first[l];
+        uint32_t const at_depth = first[l + 1] - first[l];
+        if (at_depth > 256)
+        {
+            set_error("wt_huff device build: %u nodes at one depth", at_depth);
+            return SDSLGPU_ECUDA;
+        }
         for (int c = 0; c < 256; ++c)
-            lut[l].key[c] = (uint16_t)drop[l];
+            lut[l].key[c] = 0;
         std::memset(lut[l].bit, 0, sizeof(lut[l].bit));
+        for (uint32_t j = 0; j < 256; ++j)
+        {
+            nodes[l].seg_start[j] = 0;
+            nodes[l].dst[0][j] = nodes[l].dst[1][j] = kDropDst;
+        }
+        for (uint32_t v = first[l]; v < first[l + 1]; ++v)
+            if (tree.child[v][0] != kWtUndef)
+            {
+                uint32_t const j = v - first[l];
+                nodes[l].seg_start[j] = tree.bv_pos[v] - bv_start(first[l]);
+                for (int b = 0; b < 2; ++b)
+                {
+                    uint32_t const w = tree.child[v][b];
+                    if (tree.child[w][0] != kWtUndef) // the child is an inner node: its elements live on at depth l + 1
+                        nodes[l].dst[b][j] = tree.bv_pos[w] - bv_start(first[l + 1]);
+                }
+            }
     }
     for (int c = 0; c < 256; ++c)
     {
@@ -230,37 +312,32 @@ int wt_huff_planes_device(uint8_t const * d_text, uint64_t n, WtTree const & tre
         }
     }
     SG_CUDA(cudaMemcpyAsync(luts.p, lut.data(), lut.size() * sizeof(LevelLut), cudaMemcpyHostToDevice, s));
+    SG_CUDA(cudaMemcpyAsync(lnodes.p, nodes.data(), nodes.size() * sizeof(LevelNodes), cudaMemcpyHostToDevice, s));
 
     uint8_t const * cur = d_text;
     uint8_t * spare[2] = {bufa.as<uint8_t>(), bufb.as<uint8_t>()};
-    uint64_t cnt = n;
+    uint32_t * const words32 = reinterpret_cast<uint32_t *>(d_words);
     for (uint32_t l = 0; l < maxd; ++l)
     {
-        uint64_t start = bv_start(first[l]), m = bv_start(first[l + 1]) - start;
+        uint64_t const start = bv_start(first[l]), m = bv_start(first[l + 1]) - start; // elements = bits of this depth
         if (m == 0)
             break;
         LevelLut const * dl = luts.as<LevelLut>() + l;
-        if (l > 0)
-        { // regroup by inner node of this depth; finished codes drop behind the first m elements
-            int key_bits = 1;
-            while ((1u << key_bits) <= drop[l])
-                ++key_bits;
-            wt_level_keys_kernel<<<grid_for(cnt, 4), kThreads, 0, s>>>(cur, cnt, dl, k0.as<uint16_t>());
-            SG_CUDA(cudaGetLastError());
-            uint8_t * nxt = spare[l & 1];
-            size_t need = 0;
-            cub::DeviceRadixSort::SortPairs(nullptr, need, k0.as<uint16_t>(), k1.as<uint16_t>(), cur, nxt, cnt, 0, key_bits, s);
-            if (need > cub_bytes)
-            {
-                set_error("wt_huff device build: radix-sort scratch grew from %llu to %llu bytes", (unsigned long long)cub_bytes, (unsigned long long)need);
-                return SDSLGPU_ECUDA;
-            }
-            SG_CUDA(cub::DeviceRadixSort::SortPairs(cubtmp.p, need, k0.as<uint16_t>(), k1.as<uint16_t>(), cur, nxt, cnt, 0, key_bits, s));
-            cur = nxt;
-        }
-        wt_pack_huff_kernel<<<pack_grid(m), kThreads, 0, s>>>(cur, dl, m, start, reinterpret_cast<uint32_t *>(d_words));
+        wt_pack_huff_kernel<<<pack_grid(m), kThreads, 0, s>>>(cur, dl, m, start, words32);
         SG_CUDA(cudaGetLastError());
-        cnt = m;
+        uint64_t const next_m = bv_start(first[l + 2 <= maxd + 1 ? l + 2 : maxd + 1]) - bv_start(first[l + 1]);
+        if (l + 1 >= maxd || next_m == 0)
+            break; // the deepest inner nodes: nothing lives on below them
+        // regroup for depth l + 1: stable split of every node by the bit just written
+        uint64_t const u0 = start >> 5, nw = ((start + m + 31) >> 5) - u0;
+        wt_word_popc_kernel<<<grid_for(nw), kThreads, 0, s>>>(words32, u0, nw, wcnt.as<uint32_t>());
+        SG_CUDA(cudaGetLastError());
+        SG_CUDA(exclusive_scan(wcnt.as<uint32_t>(), nw, wpre.as<uint64_t>(), stmp.as<uint64_t>(), s));
+        uint8_t * nxt = spare[l & 1];
+        wt_split_kernel<<<grid_for(m, 4), kThreads, 0, s>>>(cur, m, dl, lnodes.as<LevelNodes>() + l, first[l + 1] - first[l], words32, wpre.as<uint64_t>(), start,
+                                                            nxt);
+        SG_CUDA(cudaGetLastError());
+        cur = nxt;
     }
     SG_CUDA(cudaStreamSynchronize(s));
     return SDSLGPU_OK;

@@ -49,7 +49,15 @@ all1) run_tests; run_bench; run_sweep; run_launches; run_ncu ;;
 quick1) run_bench; run_sweep; run_launches; run_ncu ;;
 multi)
     N=${NGPU:-2}
-    timeout 900 python -m pytest tests -m gpu -x -q -k "group or multi" > $OUT/${TAG}_pytest_multi.txt 2>&1; tail -5 $OUT/${TAG}_pytest_multi.txt
+    timeout 900 python -m pytest tests/test_group_gpu.py -m gpu -x -q > $OUT/${TAG}_pytest_multi.txt 2>&1; tail -15 $OUT/${TAG}_pytest_multi.txt
+    nvidia-smi topo -m > $OUT/${TAG}_topo.txt 2>&1
+    : > $OUT/${TAG}_probe_pcie.jsonl
+    for n in 1 2 4 8; do
+        [ $n -gt $N ] && break
+        if [ $n -eq 1 ]; then timeout 300 python tools/probe_pcie.py >> $OUT/${TAG}_probe_pcie.jsonl 2>/dev/null
+        else timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29700 + n)) tools/probe_pcie.py >> $OUT/${TAG}_probe_pcie.jsonl 2>/dev/null; fi
+    done
+    cat $OUT/${TAG}_probe_pcie.jsonl
     for n in 1 2 4 8; do
         [ $n -gt $N ] && break
         if [ $n -eq 1 ]; then
