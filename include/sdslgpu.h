@@ -321,7 +321,7 @@ int sdslgpu_serialize(const sdslgpu_handle *h, int what, void *buf, uint64_t cap
  * streams.  Each member's idx array holds ALL n queries (the batch is identical on every member; only the member's
  * shard is read), each member's out array has room for n results.  All pointers are DEVICE pointers on the member's
  * device.  streams == NULL: the group's own streams are used and the call returns when the results are complete;
- * otherwise the call is asynchronous on streams[k].
+ * otherwise the call is asynchronous on streams[k] (an entry that is NULL means the legacy default stream).
  * Group calls are collective: every member (every rank) must make the same calls in the same order.
  * NCCL is bound at run time (dlopen of the libnccl.so.2 already in the process, else from the loader path or
  * $SDSLGPU_NCCL_LIB); a box without it gets SDSLGPU_ENOTSUP from the create calls.

@@ -451,7 +451,7 @@ int group_run(sdslgpu_group * g, uint64_t n, uint64_t * const * out, int gather,
         g->epoch += 2;
     std::vector<cudaStream_t> st(g->nlocal);
     for (int k = 0; k < g->nlocal; ++k)
-        st[k] = (streams && streams[k]) ? static_cast<cudaStream_t>(streams[k]) : g->m[k].stream;
+        st[k] = streams ? static_cast<cudaStream_t>(streams[k]) : g->m[k].stream; // a NULL entry is the legacy default stream
     bool const own_streams = streams == nullptr;
     // Three passes over the local members, never a kernel launch of member k behind a flag exchange that waits for a
     // member this same host thread has not launched yet: the first launch of a kernel loads its module, which can
