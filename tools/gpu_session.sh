@@ -61,7 +61,7 @@ multi)
     for n in 1 2 4 8; do
         [ $n -gt $N ] && break
         if [ $n -eq 1 ]; then
-            timeout 900 python bench.py --gpus 1 ${BENCH_ARGS:-} > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err
+            timeout 900 python bench.py --gpus 1 ${BENCH_ARGS:-} ${BENCH_ARGS_N1:-} > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err
         else
             timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) \
                 bench.py --gpus $n ${BENCH_ARGS:-} > $OUT/${TAG}_bench_n$n.json 2> $OUT/${TAG}_bench_n$n.err
