@@ -181,7 +181,8 @@ struct RrrImage
     uint64_t * btnr = nullptr;    // m_btnr
     uint64_t * records = nullptr; // 64-byte record per superblock (rank, btnrp|invert, 32 classes, quarter sums) + closing record
     void * tables = nullptr;      // RrrTables (binomials + code lengths), device copy
-    uint32_t * hint[2] = {nullptr, nullptr}; // select hints: superblock of every 8192nd b-bit
+    uint32_t * hint[2] = {nullptr, nullptr}; // select hints: superblock of every 2^hint_shift[b]-th b-bit
+    uint32_t hint_shift[2] = {13, 13};
 };
 
 struct WtHuffImage
@@ -303,6 +304,8 @@ inline RrrView rrr_view(RrrImage const & r)
     v.tables = reinterpret_cast<RrrTables const *>(r.tables);
     v.hint[0] = r.hint[0];
     v.hint[1] = r.hint[1];
+    v.hint_shift[0] = r.hint_shift[0];
+    v.hint_shift[1] = r.hint_shift[1];
     return v;
 }
 inline PlainBits plain_bits(WtHuffImage const & w)

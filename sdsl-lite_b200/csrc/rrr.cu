@@ -17,7 +17,7 @@
 //     w5      prefix sums after 8 / 16 / 24 blocks: ones (10+10+11 bits) and offset bits (10+10+11 bits)
 //     w6      ones in the superblock, w7 offset bits of the superblock
 // so rank = record + one read of the offset stream (m_btnr, unchanged), and the class scan is at most 7 steps.
-// C(n,k) for n,k <= 63 (32 KB) and the code lengths live in shared memory.
+// C(n,k) for n <= 62 (23.6 KB: 64-bit rows for n >= 34, 32-bit rows below) and the code lengths live in shared memory.
 #include "binned.cuh"
 #include "internal.h"
 #include "rrr_device.cuh"
@@ -72,8 +72,9 @@ __global__ void __launch_bounds__(kThreads) rrr_access_kernel(RrrView const v, u
             {
                 uint64_t p = r.w[1] & ~kInvBit, ones = 0;
                 rec_prefix(r, t, nblk, inv, ones, p);
-                uint64_t bin = rrr_decode(t, k, read_int(v.btnr, p, t->space[k]), off + 1);
-                res = (bin >> off) & 1;
+                uint32_t bit;
+                rrr_prefix_ones(t, k, read_int(v.btnr, p, t->space[k]), off, true, bit);
+                res = bit;
             }
         }
         st_stream_u64(out + q, res);
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(kThreads) rrr_encode_kernel(uint64_t const * _
         uint32_t z = __ffsll((long long)bin) - 1; // skip zeros: they only shorten the block
         bin >>= z;
         nn -= z;
-        nr += t->binom[nn - 1][k];
+        nr += rrr_binom(t, nn - 1, k);
         --k;
         bin >>= 1;
         --nn;
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(kThreads) rrr_encode_kernel(uint64_t const * _
 
 // select hints: one thread per superblock writes the hints whose sampled b-bit falls inside it
 template <int B>
-__global__ void __launch_bounds__(kThreads) rrr_hint_kernel(uint64_t const * __restrict__ records, uint64_t nsuper, uint32_t * __restrict__ hint, uint64_t nhint)
+__global__ void __launch_bounds__(kThreads) rrr_hint_kernel(uint64_t const * __restrict__ records, uint64_t nsuper, uint32_t * __restrict__ hint, uint64_t nhint, uint32_t shift)
 {
     uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nsuper)
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(kThreads) rrr_hint_kernel(uint64_t const * __r
     uint64_t a = B ? r0 : g * kBs * kK - r0, e = B ? r1 : (g + 1) * kBs * kK - r1; // b-bits before / through g
     if (e <= a)
         return;
-    for (uint64_t j = (a + (1ull << kHintShift) - 1) >> kHintShift; j < nhint && (j << kHintShift) + 1 <= e; ++j)
+    for (uint64_t j = (a + (1ull << shift) - 1) >> shift; j < nhint && (j << shift) + 1 <= e; ++j)
         hint[j] = (uint32_t)g;
 }
 
@@ -226,7 +227,9 @@ int rrr_build_hints(DevicePool & pool, RrrImage & r, cudaStream_t s)
     {
         // zeros are counted over whole 2016-bit superblocks (the zero-extended tail included), like select0 does
         uint64_t args = b ? r.ones : r.nsuper * kBs * kK - r.ones;
-        uint64_t nhint = args ? ((args - 1) >> kHintShift) + 1 : 0;
+        uint32_t const shift = rrr_hint_shift(args, r.nsuper);
+        r.hint_shift[b] = shift;
+        uint64_t nhint = args ? ((args - 1) >> shift) + 1 : 0;
         SG_TRY(pool.alloc_t(&r.hint[b], nhint + 2));
         std::vector<uint32_t> fill(nhint + 2, (uint32_t)(r.nsuper ? r.nsuper - 1 : 0));
         SG_CUDA(cudaMemcpyAsync(r.hint[b], fill.data(), (nhint + 2) * 4, cudaMemcpyHostToDevice, s));
@@ -234,9 +237,9 @@ int rrr_build_hints(DevicePool & pool, RrrImage & r, cudaStream_t s)
         if (nhint)
         {
             if (b)
-                rrr_hint_kernel<1><<<blocks_for(r.nsuper), kThreads, 0, s>>>(r.records, r.nsuper, r.hint[b], nhint);
+                rrr_hint_kernel<1><<<blocks_for(r.nsuper), kThreads, 0, s>>>(r.records, r.nsuper, r.hint[b], nhint, shift);
             else
-                rrr_hint_kernel<0><<<blocks_for(r.nsuper), kThreads, 0, s>>>(r.records, r.nsuper, r.hint[b], nhint);
+                rrr_hint_kernel<0><<<blocks_for(r.nsuper), kThreads, 0, s>>>(r.records, r.nsuper, r.hint[b], nhint, shift);
             SG_CUDA(cudaGetLastError());
         }
     }

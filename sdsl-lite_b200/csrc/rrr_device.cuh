@@ -14,13 +14,33 @@ static constexpr uint32_t kBs = 63; // t_bs
 static constexpr uint32_t kK = 32;  // t_k
 static constexpr uint64_t kInvBit = 1ull << 63;
 static constexpr uint32_t kRecWords = 8;
-static constexpr uint32_t kHintShift = 13;
+// select hints: one per 2^hint_shift b-bits, the stride chosen per vector and bit value so that two neighbouring hints
+// bracket about four superblocks whatever the density (rrr_hint_shift; a fixed stride of 2^13 made a 1 %-dense vector
+// bisect over ~400 records, nine dependent gathers)
+__host__ __device__ __forceinline__ uint32_t rrr_hint_shift(uint64_t args, uint64_t nsuper)
+{
+    uint32_t s = 0;
+    while (s < 20 && (args >> s) > nsuper / 4 + 1)
+        ++s;
+    return s;
+}
 
+// C(n, k) for n <= 62, 0 for k > n (rrr_helper.hpp:193-237), split by magnitude: every C(n, k) with n <= 33 is below
+// 2^32, so the last 34 steps of a block's enumerative decode run in 32-bit registers on a table of half the size.
+// 23.6 KB of shared memory per CTA (the full 64 x 64 x u64 table was 32 KB).
+static constexpr uint32_t kBinomSplit = 34;
 struct RrrTables
 {
-    uint64_t binom[64][64]; // binom[n][k] = C(n, k), 0 for k > n   (rrr_helper.hpp:193-237)
-    uint8_t space[64];      // bits of an offset of class k: 0 if C(63,k) == 1 else hi(C(63,k)) + 1 (:286-293)
+    uint64_t hi[63 - kBinomSplit][64]; // C(n, k), n = 34 .. 62
+    uint32_t lo[kBinomSplit][64];      // C(n, k), n = 0 .. 33
+    uint8_t space[64];                 // bits of an offset of class k: 0 if C(63,k) == 1 else hi(C(63,k)) + 1 (:286-293)
 };
+static_assert(sizeof(RrrTables) % 16 == 0, "staged with 16-byte copies");
+
+__host__ __device__ __forceinline__ uint64_t rrr_binom(RrrTables const * t, uint32_t n, uint32_t k)
+{
+    return n >= kBinomSplit ? t->hi[n - kBinomSplit][k] : (uint64_t)t->lo[n][k];
+}
 
 #ifndef SDSLGPU_HOST_EMU
 __device__ __forceinline__ void stage_rrr(RrrTables const * __restrict__ g, RrrTables * s)
@@ -33,26 +53,85 @@ __device__ __forceinline__ void stage_rrr(RrrTables const * __restrict__ g, RrrT
 }
 #endif
 
-// the block with k ones and offset nr, decoded up to `upto` positions (inverse of bin_to_nr, rrr_helper.hpp:346-366;
-// what decode_bit / decode_popcount / decode_select of rrr_helper.hpp:369-649 all compute from)
-__device__ __forceinline__ uint64_t rrr_decode(RrrTables const * t, uint32_t k, uint64_t nr, uint32_t upto)
+// Enumerative decode of one block (k ones among 63 positions, offset nr), the inverse of bin_to_nr
+// (rrr_helper.hpp:346-366): position p holds a one iff nr >= C(62 - p, k) for the k ones still to place; then
+// nr -= C(62 - p, k), --k.  Before step p, nr < C(63 - p, k) — so from p = 29 on nr < C(34, k) < 2^32 and the walk
+// continues in 32-bit arithmetic.  The reference's decode_popcount / decode_bit / decode_select (rrr_helper.hpp:369-649)
+// are all functions of this walk; nothing here materialises the 63-bit word.
+static constexpr uint32_t kWide = 63 - kBinomSplit; // steps p = 0 .. 28 compare 64-bit binomials
+
+// ones among positions [0, off) and, if want_bit, the bit at position off (off < 63 then)
+__device__ __forceinline__ uint32_t rrr_prefix_ones(RrrTables const * t, uint32_t k, uint64_t nr, uint32_t off, bool want_bit, uint32_t & bit)
 {
-    if (k == 0)
-        return 0;
-    if (k == kBs)
-        return (1ull << kBs) - 1;
-    uint64_t bin = 0;
-    for (uint32_t p = 0; p < upto && k; ++p)
+    uint32_t const k0 = k, upto = off + (want_bit ? 1u : 0u);
+    uint32_t p = 0, k_at_off = k;
+    uint32_t const wide = upto < kWide ? upto : kWide;
+    for (; p < wide && k; ++p)
     {
-        uint64_t c = t->binom[kBs - 1 - p][k];
+        if (p == off)
+            k_at_off = k;
+        uint64_t const c = t->hi[kWide - 1 - p][k];
         if (nr >= c)
         {
             nr -= c;
-            bin |= 1ull << p;
             --k;
         }
     }
-    return bin;
+    if (p < upto && k)
+    {
+        uint32_t r = (uint32_t)nr;
+        for (; p < upto && k; ++p)
+        {
+            if (p == off)
+                k_at_off = k;
+            uint32_t const c = t->lo[62 - p][k];
+            if (r >= c)
+            {
+                r -= c;
+                --k;
+            }
+        }
+    }
+    if (p <= off)
+        k_at_off = k; // the walk ended (no ones left) before reaching off
+    bit = want_bit ? k_at_off - ((p > off) ? k : k_at_off) : 0u;
+    return k0 - k_at_off;
+}
+
+// position (0..62) of the target-th (1-based) B-bit of the block; requires target <= number of B-bits
+template <int B>
+__device__ __forceinline__ uint32_t rrr_select_in_block(RrrTables const * t, uint32_t k, uint64_t nr, uint32_t target)
+{
+    uint32_t p = 0;
+    for (; p < kWide && k; ++p)
+    {
+        uint64_t const c = t->hi[kWide - 1 - p][k];
+        bool const one = nr >= c;
+        if (one)
+        {
+            nr -= c;
+            --k;
+        }
+        if (one == (B != 0) && --target == 0)
+            return p;
+    }
+    if (k)
+    {
+        uint32_t r = (uint32_t)nr;
+        for (; k; ++p)
+        {
+            uint32_t const c = t->lo[62 - p][k];
+            bool const one = r >= c;
+            if (one)
+            {
+                r -= c;
+                --k;
+            }
+            if (one == (B != 0) && --target == 0)
+                return p;
+        }
+    }
+    return p + target - 1; // no ones left: the rest of the block is zeros (only reachable for B == 0)
 }
 
 struct RrrView
@@ -64,7 +143,8 @@ struct RrrView
     uint64_t const * btnr;    // packed offsets (m_btnr)
     uint64_t const * records; // 8 words per superblock, see the file header
     RrrTables const * tables;
-    uint32_t const * hint[2]; // hint[b][j] = superblock holding the (j * 2^kHintShift + 1)-th b-bit (+ sentinels)
+    uint32_t const * hint[2]; // hint[b][j] = superblock holding the (j * 2^hint_shift[b] + 1)-th b-bit (+ sentinels)
+    uint32_t hint_shift[2];
 };
 
 struct RrrRecord
@@ -111,18 +191,35 @@ __host__ __device__ __forceinline__ uint32_t rec_qbits(uint64_t w5, uint32_t q)
     return q == 0 ? 0u : q == 1 ? (uint32_t)((w5 >> 31) & 1023) : q == 2 ? (uint32_t)((w5 >> 41) & 1023) : (uint32_t)((w5 >> 51) & 2047);
 }
 
-// ones and offset bits of the first nblk (0..31) blocks of a superblock
-__device__ __forceinline__ void rec_prefix(RrrRecord const & r, RrrTables const * t, uint32_t nblk, bool inv, uint64_t & ones, uint64_t & p)
+// the eight stored classes of quarter q (blocks 8q .. 8q+7): 48 bits starting at bit 48 q of w2..w4
+__host__ __device__ __forceinline__ uint64_t rec_quarter(uint64_t w2, uint64_t w3, uint64_t w4, uint32_t q)
 {
-    uint32_t q = nblk >> 3;
+    uint64_t const x = q == 0 ? w2 : q == 1 ? ((w2 >> 48) | (w3 << 16)) : q == 2 ? ((w3 >> 32) | (w4 << 32)) : (w4 >> 16);
+    return x & 0xFFFFFFFFFFFFull;
+}
+
+// ones and offset bits of the first nblk (0..31) blocks of a superblock; also returns the class of block nblk itself
+// (real, i.e. inversion undone).  Quarter prefixes come from w5; inside the quarter the stored classes are summed in
+// one SWAR step (six-bit fields -> four 12-bit lanes -> one multiply) and the code lengths by at most 7 table reads,
+// without a branch per class.
+__device__ __forceinline__ uint32_t rec_prefix(RrrRecord const & r, RrrTables const * t, uint32_t nblk, bool inv, uint64_t & ones, uint64_t & p)
+{
+    uint32_t const q = nblk >> 3, rem = nblk & 7u;
     ones += rec_qones(r.w[5], q);
     p += rec_qbits(r.w[5], q);
-    for (uint32_t j = q << 3; j < nblk; ++j)
-    {
-        uint32_t c = rec_class(r.w[2], r.w[3], r.w[4], j);
-        ones += inv ? kBs - c : c;
-        p += t->space[c]; // space is symmetric: stored or real class give the same width (rrr_vector.hpp:528-541)
-    }
+    uint64_t const x = rec_quarter(r.w[2], r.w[3], r.w[4], q);
+    uint64_t const low = x & ((1ull << (6u * rem)) - 1ull); // the classes of the rem blocks before block nblk
+    uint64_t const kLanes = 0x03F03F03F03Full;               // fields 0, 2, 4, 6
+    uint64_t const pair = (low & kLanes) + ((low >> 6) & kLanes);
+    uint32_t const stored = (uint32_t)((pair * 0x001001001001ull) >> 36) & 0xFFFu;
+    ones += inv ? (uint64_t)kBs * rem - stored : stored;
+    uint32_t bits = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 7; ++j)
+        bits += j < rem ? t->space[(uint32_t)(x >> (6u * j)) & 63u] : 0u; // space is symmetric: stored or real class (rrr_vector.hpp:528-541)
+    p += bits;
+    uint32_t const c = (uint32_t)(x >> (6u * rem)) & 63u;
+    return inv ? kBs - c : c;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -142,16 +239,13 @@ __device__ __forceinline__ uint64_t rrr_rank1_one(RrrView const & v, RrrTables c
     bool inv = (r.w[1] & kInvBit) != 0;
     uint64_t p = r.w[1] & ~kInvBit, ones = r.w[0];
     uint32_t nblk = (uint32_t)(blk - g * kK);
-    rec_prefix(r, t, nblk, inv, ones, p);
-    if (off == 0)
+    uint32_t const k = rec_prefix(r, t, nblk, inv, ones, p);
+    if (off == 0 || k == 0)
         return ones;
-    uint32_t k = rec_class(r.w[2], r.w[3], r.w[4], nblk);
-    if (inv)
-        k = kBs - k;
-    uint32_t sp = t->space[k];
-    uint64_t nr = sp ? read_int(v.btnr, p, sp) : 0;
-    uint64_t bin = rrr_decode(t, k, nr, off);
-    return ones + __popcll(bin & ((1ull << off) - 1));
+    if (k == kBs)
+        return ones + off;
+    uint32_t sp = t->space[k], bit;
+    return ones + rrr_prefix_ones(t, k, sp ? read_int(v.btnr, p, sp) : 0, off, false, bit);
 }
 
 // rank1(pos) and the bit at pos (pos < size) from one record + one offset read
@@ -164,14 +258,14 @@ __device__ __forceinline__ uint64_t rrr_rank1_and_bit(RrrView const & v, RrrTabl
     bool inv = (r.w[1] & kInvBit) != 0;
     uint64_t p = r.w[1] & ~kInvBit, ones = r.w[0];
     uint32_t nblk = (uint32_t)(blk - g * kK);
-    rec_prefix(r, t, nblk, inv, ones, p);
-    uint32_t k = rec_class(r.w[2], r.w[3], r.w[4], nblk);
-    if (inv)
-        k = kBs - k;
+    uint32_t const k = rec_prefix(r, t, nblk, inv, ones, p);
+    if (k == 0 || k == kBs)
+    {
+        bit = k != 0;
+        return ones + (k ? off : 0u);
+    }
     uint32_t sp = t->space[k];
-    uint64_t bin = rrr_decode(t, k, sp ? read_int(v.btnr, p, sp) : 0, off + 1);
-    bit = (uint32_t)(bin >> off) & 1u;
-    return ones + __popcll(bin & ((1ull << off) - 1));
+    return ones + rrr_prefix_ones(t, k, sp ? read_int(v.btnr, p, sp) : 0, off, true, bit);
 }
 
 // position of the i-th (1-based) B-bit, 1 <= i <= #B-bits (rrr_vector.hpp:639-726)
@@ -179,7 +273,7 @@ template <int B>
 __device__ __forceinline__ uint64_t rrr_select_one(RrrView const & v, RrrTables const * t, uint64_t i)
 {
     // superblock g with count_before(g) < i <= count_before(g + 1)   (:643-655), bracketed by the hints
-    uint64_t hj = (i - 1) >> kHintShift;
+    uint64_t hj = (i - 1) >> v.hint_shift[B];
     uint64_t begin = __ldg(v.hint[B] + hj), end = (uint64_t)__ldg(v.hint[B] + hj + 1) + 1;
     while (end - begin > 1)
     {
@@ -214,22 +308,28 @@ __device__ __forceinline__ uint64_t rrr_select_one(RrrView const & v, RrrTables 
         cnt += B ? o : quarter * 8 * kBs - o;
         p += rec_qbits(r.w[5], quarter);
     }
-    uint32_t j = quarter << 3, k = 0, sp = 0;
+    uint64_t const x = rec_quarter(r.w[2], r.w[3], r.w[4], quarter); // the quarter's eight classes, six bits each
+    uint32_t j = 0, k = 0, sp = 0;
     for (;; ++j)
     {
-        k = rec_class(r.w[2], r.w[3], r.w[4], j);
+        k = (uint32_t)(x >> (6u * j)) & 63u;
         if (inv)
             k = kBs - k;
         sp = t->space[k];
         uint32_t c = B ? k : kBs - k;
-        if (cnt + c >= i)
+        if (cnt + c >= i || j == 7)
             break;
         cnt += c;
         p += sp;
     }
-    uint64_t bin = rrr_decode(t, k, sp ? read_int(v.btnr, p, sp) : 0, kBs);
-    uint64_t x = B ? bin : (~bin & ((1ull << kBs) - 1));
-    return (begin * kK + j) * kBs + sel64(x, (uint32_t)(i - cnt));
+    j += quarter << 3;
+    uint32_t const target = (uint32_t)(i - cnt);
+    uint32_t pos;
+    if (k == 0 || k == kBs)
+        pos = target - 1; // a uniform block: its target-th bit (of the only value it has)
+    else
+        pos = rrr_select_in_block<B>(t, k, sp ? read_int(v.btnr, p, sp) : 0, target);
+    return (begin * kK + j) * kBs + pos;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -250,9 +350,14 @@ inline RrrTables const & host_tables()
         for (int n = 1; n <= 64; ++n)
             for (int k = 1; k <= n; ++k)
                 full[n][k] = full[n - 1][k - 1] + full[n - 1][k];
-        for (int n = 0; n < 64; ++n)
+        for (int n = 0; n < 63; ++n)
             for (int k = 0; k < 64; ++k)
-                t.binom[n][k] = full[n][k];
+            {
+                if (n >= (int)kBinomSplit)
+                    t.hi[n - kBinomSplit][k] = full[n][k];
+                else
+                    t.lo[n][k] = (uint32_t)full[n][k]; // C(33, 16) = 1.17e9 < 2^32
+            }
         for (int k = 0; k < 64; ++k)
         {
             uint64_t c = full[63][k];

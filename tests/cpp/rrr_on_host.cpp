@@ -78,8 +78,11 @@ extern "C"
         rrr_records_host(bt.w.data(), nblocks, nsuper, ones, rk, bp, iv, 0, e->rec);
         e->btnr = btnr.w;
         for (int b = 0; b < 2; ++b)
-        { // rrr.cu rrr_hint_kernel: superblock holding the (j * 2^kHintShift + 1)-th b-bit, two sentinels
-            uint64_t args = b ? ones : nsuper * kBs * kK - ones, nhint = args ? ((args - 1) >> kHintShift) + 1 : 0;
+        { // rrr.cu rrr_hint_kernel: superblock holding the (j * 2^shift + 1)-th b-bit, two sentinels
+            uint64_t args = b ? ones : nsuper * kBs * kK - ones;
+            uint32_t const kHintShift = rrr_hint_shift(args, nsuper);
+            e->v.hint_shift[b] = kHintShift;
+            uint64_t nhint = args ? ((args - 1) >> kHintShift) + 1 : 0;
             e->hint[b].assign(nhint + 2, (uint32_t)(nsuper ? nsuper - 1 : 0));
             for (uint64_t g = 0; g < nsuper; ++g)
             {
