@@ -335,6 +335,15 @@ struct RrrRankOp
     static constexpr int kIlp = 1;
     static constexpr int kMinCtas = 6;
     static constexpr uint32_t kSmem = sizeof(RrrTables);
+#ifndef BIN_RRR_BUCKETS
+#define BIN_RRR_BUCKETS 4
+#endif
+    // the decode walk of rank(i) covers i % 63 positions of a block: lanes of one trip get queries of the same quarter
+    static constexpr uint32_t kBuckets = BIN_RRR_BUCKETS;
+    __device__ __forceinline__ uint32_t bucket(uint64_t i) const
+    {
+        return ((uint32_t)(i % kBs) * kBuckets) / kBs;
+    }
     RrrView v;
     int b;
     RrrTables const * t;

@@ -63,6 +63,12 @@ static constexpr uint32_t kWide = 63 - kBinomSplit; // steps p = 0 .. 28 compare
 // ones among positions [0, off) and, if want_bit, the bit at position off (off < 63 then)
 __device__ __forceinline__ uint32_t rrr_prefix_ones(RrrTables const * t, uint32_t k, uint64_t nr, uint32_t off, bool want_bit, uint32_t & bit)
 {
+    if (k == 1)
+    { // one one: it sits at position 62 - nr (nr = C(62 - p, 1)); a third of all blocks at 1 % density
+        uint32_t const one_at = 62u - (uint32_t)nr;
+        bit = want_bit && one_at == off;
+        return one_at < off;
+    }
     uint32_t const k0 = k, upto = off + (want_bit ? 1u : 0u);
     uint32_t p = 0, k_at_off = k;
     uint32_t const wide = upto < kWide ? upto : kWide;
@@ -102,6 +108,11 @@ __device__ __forceinline__ uint32_t rrr_prefix_ones(RrrTables const * t, uint32_
 template <int B>
 __device__ __forceinline__ uint32_t rrr_select_in_block(RrrTables const * t, uint32_t k, uint64_t nr, uint32_t target)
 {
+    if (k == 1)
+    {
+        uint32_t const one_at = 62u - (uint32_t)nr;
+        return B ? one_at : (target - 1 < one_at ? target - 1 : target);
+    }
     uint32_t p = 0;
     for (; p < kWide && k; ++p)
     {
