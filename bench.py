@@ -183,7 +183,7 @@ def measured_traffic():
     if not files:
         return {}, None
     tj = json.load(open(files[-1]))
-    return {k: v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in tj.items() if isinstance(v, dict)}, os.path.basename(files[-1])
+    return {k: v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in tj.items() if isinstance(v, dict) and "dram_bytes_read" in v}, os.path.basename(files[-1])
 
 
 def main():

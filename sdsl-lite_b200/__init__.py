@@ -20,7 +20,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsdslgpu.so")
+LIB_PATH = os.environ.get("SDSLGPU_LIB") or os.path.join(HERE, "libsdslgpu.so")  # SDSLGPU_LIB: a variant build (tools/variants.sh)
 
 OK, EINVAL, ENOMEM, ECUDA, ENOTSUP = 0, -1, -2, -3, -4
 NPOS = np.uint64(0xFFFFFFFFFFFFFFFF)

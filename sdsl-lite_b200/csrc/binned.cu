@@ -401,20 +401,12 @@ struct BvSelectOp
     static constexpr int kIlp = BIN_SEL_ILP;
     static constexpr int kMinCtas = BIN_SEL_CTAS;
     static constexpr uint32_t kSmem = 0;
-#ifndef BIN_SEL_TWO_PASS
-#define BIN_SEL_TWO_PASS 1
-#endif
-    static constexpr bool kTwoPass = BIN_SEL_TWO_PASS != 0;
     BvView v;
     __device__ __forceinline__ void stage(uint8_t *) const
     {}
     __device__ __forceinline__ uint64_t operator()(uint64_t key) const
     {
         return bv_select<B>(v, key + 1);
-    }
-    __device__ __forceinline__ bool try_fast(uint64_t key, uint64_t & a) const
-    {
-        return bv_select_try<B>(v, key + 1, a);
     }
 };
 

@@ -22,8 +22,6 @@
 // halves two of those streams but the un-sort then needs the bin of every slot; measured, it gains nothing:
 // profiles/r01d_binned_v4_relative_*.)
 #pragma once
-#include <type_traits>
-
 #include "internal.h"
 
 namespace sdslgpu
@@ -71,38 +69,6 @@ unsigned bin_apply_grid(BinPlan const & p);
 //   static constexpr uint32_t kSmem    bytes of dynamic shared memory its tables need (0: none)
 //   __device__ void stage(uint8_t *)   copy tables into shared memory (called by every thread; must __syncthreads if kSmem)
 //   __device__ uint64_t operator()(uint64_t key) const
-//   static constexpr bool kTwoPass     (optional) the op also has  __device__ bool try_fast(uint64_t key, uint64_t & a) const:
-//                                      the common case without its divergent repair path.  A warp then answers a run
-//                                      in two passes: try_fast for every query (all lanes busy), the slots it declined
-//                                      collected in a per-warp shared-memory queue, then operator() for the queue with
-//                                      the lanes packed — instead of 31 lanes idling whenever one lane repairs.
-template <class Op, class = void>
-struct bin_two_pass
-{
-    static constexpr bool value = false;
-};
-template <class Op>
-struct bin_two_pass<Op, typename std::enable_if<Op::kTwoPass>::type>
-{
-    static constexpr bool value = true;
-};
-static constexpr uint32_t kDeferSlots = 96; // per warp; drained when fewer than 32 are free
-//   static constexpr uint32_t kBuckets (optional, > 1) with  __device__ uint32_t bucket(uint64_t key) const  in [0, kBuckets):
-//                                      a cheap predictor of how long operator() will run for this key (rrr: how far into
-//                                      its block the enumerative decode has to walk).  A warp then takes the queries of a
-//                                      run bucket by bucket, so the 32 lanes of one trip loop about equally long.
-template <class Op, class = void>
-struct bin_buckets
-{
-    static constexpr uint32_t value = 1;
-};
-template <class Op>
-struct bin_buckets<Op, typename std::enable_if<(Op::kBuckets > 1)>::type>
-{
-    static constexpr uint32_t value = Op::kBuckets;
-};
-static constexpr uint32_t kBucketChunk = 128; // queries of a run sorted into buckets at a time (per warp)
-
 template <class Op>
 __global__ void __launch_bounds__(kThreads, Op::kMinCtas) bin_apply_kernel(Op op,
                                                              uint32_t const * __restrict__ recs,
@@ -138,81 +104,6 @@ __global__ void __launch_bounds__(kThreads, Op::kMinCtas) bin_apply_kernel(Op op
             uint64_t const hi = (uint64_t)b << shift;
             uint32_t const * r_in = recs + t * kTile;
             uint64_t * r_out = res + t * kTile;
-            if constexpr (bin_buckets<Op>::value > 1)
-            {
-                constexpr uint32_t NB = bin_buckets<Op>::value;
-                __shared__ uint16_t bucketed[kThreads / 32][NB][kBucketChunk];
-                uint16_t(*const bq)[kBucketChunk] = bucketed[threadIdx.x >> 5];
-                for (uint32_t c0 = o0; c0 < o1; c0 += kBucketChunk)
-                {
-                    uint32_t const c1 = c0 + kBucketChunk < o1 ? c0 + kBucketChunk : o1;
-                    uint32_t cnt[NB];
-#pragma unroll
-                    for (uint32_t j = 0; j < NB; ++j)
-                        cnt[j] = 0;
-                    for (uint32_t k0 = c0; k0 < c1; k0 += 32)
-                    {
-                        uint32_t const k = k0 + lane;
-                        uint32_t const b = k < c1 ? op.bucket(hi + ld_stream_u32(r_in + k)) : NB;
-#pragma unroll
-                        for (uint32_t j = 0; j < NB; ++j)
-                        {
-                            uint32_t const m = __ballot_sync(0xFFFFFFFFu, b == j);
-                            if (b == j)
-                                bq[j][cnt[j] + __popc(m & ((1u << lane) - 1u))] = (uint16_t)k;
-                            cnt[j] += __popc(m);
-                        }
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (uint32_t j = 0; j < NB; ++j)
-                        for (uint32_t e = lane; e < cnt[j]; e += 32)
-                        {
-                            uint32_t const k = bq[j][e];
-                            st_stream_u64(r_out + k, op(hi + ld_stream_u32(r_in + k)));
-                        }
-                    __syncwarp();
-                }
-                continue;
-            }
-            if constexpr (bin_two_pass<Op>::value)
-            {
-                __shared__ uint16_t defer[kThreads / 32][kDeferSlots];
-                uint16_t * const dq = defer[threadIdx.x >> 5];
-                uint32_t queued = 0;
-                auto drain = [&]() {
-                    __syncwarp();
-                    for (uint32_t e = lane; e < queued; e += 32)
-                    {
-                        uint32_t const k = dq[e];
-                        st_stream_u64(r_out + k, op(hi + ld_stream_u32(r_in + k)));
-                    }
-                    __syncwarp();
-                    queued = 0;
-                };
-                for (uint32_t k0 = o0; k0 < o1; k0 += 32)
-                {
-                    uint32_t const k = k0 + lane;
-                    bool miss = false;
-                    if (k < o1)
-                    {
-                        uint64_t a;
-                        if (op.try_fast(hi + ld_stream_u32(r_in + k), a))
-                            st_stream_u64(r_out + k, a);
-                        else
-                            miss = true;
-                    }
-                    uint32_t const m = __ballot_sync(0xFFFFFFFFu, miss);
-                    if (miss)
-                        dq[queued + __popc(m & ((1u << lane) - 1u))] = (uint16_t)k; // k < kTile = 8192
-                    queued += __popc(m);
-                    if (queued > kDeferSlots - 32)
-                        drain();
-                }
-                if (queued)
-                    drain();
-                continue;
-            }
             constexpr int I = Op::kIlp;
             for (uint32_t k = o0 + lane; k < o1; k += 32 * I)
             { // I independent gathers per lane and trip

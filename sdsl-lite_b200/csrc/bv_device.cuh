@@ -143,47 +143,6 @@ __device__ __forceinline__ uint64_t bv_select_from(BvView const & v, uint64_t i,
 }
 
 
-// The first probe of bv_select alone: sample pair -> interpolated block -> is the i-th B-bit in it?  true: `pos` is the
-// answer (95 % of the queries on random data).  false: nothing is decided — the caller runs bv_select, whose walk /
-// bisection repairs the guess.  Splitting the two lets a warp answer the hits of a whole run with all lanes busy and
-// then the misses together, instead of every warp-query idling 31 lanes while one of them walks (binned.cuh).
-template <int B>
-__device__ __forceinline__ bool bv_select_try(BvView const & v, uint64_t i, uint64_t & pos)
-{
-    uint32_t const * __restrict__ samp = v.samp[B];
-    uint32_t const log_s = v.log_s[B];
-    uint64_t const j = (i - 1) >> log_s;
-    uint32_t lo32, hi32;
-    if ((j & 1) == 0)
-    {
-        uint2 const s2 = __ldg(reinterpret_cast<uint2 const *>(samp + j));
-        lo32 = s2.x;
-        hi32 = s2.y;
-    }
-    else
-    {
-        lo32 = __ldg(samp + j);
-        hi32 = __ldg(samp + j + 1);
-    }
-    uint32_t const r = (uint32_t)((i - 1) & ((1ull << log_s) - 1));
-    uint64_t g;
-    if (v.samp_pos[B])
-        g = (lo32 + (uint32_t)(((uint64_t)(hi32 - lo32) * r + (1ull << log_s >> 1)) >> log_s)) / 7u;
-    else
-        g = v.interp[B] ? lo32 + (((uint64_t)(hi32 - lo32) * r + (1ull << log_s >> 1)) >> log_s) : lo32;
-    uint32_t cnt, d[7];
-    ld_block(v.blocks + g, cnt, d);
-    uint64_t const a1 = __ldg(v.top + (g >> kSuperShift)) + cnt;
-    uint64_t const before = B ? a1 : g * kBlockBits - a1;
-    if (before >= i)
-        return false;
-    uint64_t const need = i - before;
-    if (need > block_popc<B>(d))
-        return false;
-    pos = g * kBlockBits + block_select<B>(d, (uint32_t)need);
-    return true;
-}
-
 // position of the i-th (1-based) B-bit, given 1 <= i <= #B-bits
 // (device form of select_support_mcl<B>::select, select_support_mcl.hpp:384-439: sampled hint, then a
 //  scan over block counts instead of the reference's word scan)

@@ -330,20 +330,14 @@ int rrr_records_from_sdsl(DevicePool & pool, RrrImage & r,
 
 // op of the locality-ordered batch pipeline (binned.cuh): rank(i) reads the 64-byte record of superblock i / 2016
 // and the offset bits right behind btnrp — both grow with i
+#ifndef BIN_RRR_CTAS
+#define BIN_RRR_CTAS 6 // resident CTAs per SM the rrr ops are compiled for (tools/variants.sh measures 4 / 6 / 8)
+#endif
 struct RrrRankOp
 {
     static constexpr int kIlp = 1;
-    static constexpr int kMinCtas = 6;
+    static constexpr int kMinCtas = BIN_RRR_CTAS;
     static constexpr uint32_t kSmem = sizeof(RrrTables);
-#ifndef BIN_RRR_BUCKETS
-#define BIN_RRR_BUCKETS 4
-#endif
-    // the decode walk of rank(i) covers i % 63 positions of a block: lanes of one trip get queries of the same quarter
-    static constexpr uint32_t kBuckets = BIN_RRR_BUCKETS;
-    __device__ __forceinline__ uint32_t bucket(uint64_t i) const
-    {
-        return ((uint32_t)(i % kBs) * kBuckets) / kBs;
-    }
     RrrView v;
     int b;
     RrrTables const * t;
@@ -366,7 +360,7 @@ template <int B>
 struct RrrSelectOp
 {
     static constexpr int kIlp = 1;
-    static constexpr int kMinCtas = 6;
+    static constexpr int kMinCtas = BIN_RRR_CTAS;
     static constexpr uint32_t kSmem = sizeof(RrrTables);
     RrrView v;
     uint64_t args;

@@ -60,6 +60,15 @@ __device__ __forceinline__ void stage_rrr(RrrTables const * __restrict__ g, RrrT
 // are all functions of this walk; nothing here materialises the 63-bit word.
 static constexpr uint32_t kWide = 63 - kBinomSplit; // steps p = 0 .. 28 compare 64-bit binomials
 
+// One step of the walk at position p, k ones left: is there a one?  (k == 0 needs no special case: C(n, 0) = 1 > nr = 0.)
+// Written on byte offsets into the two tables so that the unrolled loops below keep only `nr` and the column offset
+// live: LDS, compare, conditional subtract, conditional column step — 7 instructions per 64-bit step, 5 per 32-bit step.
+#ifdef SDSLGPU_HOST_EMU
+#define SG_UNROLL4
+#else
+#define SG_UNROLL4 _Pragma("unroll 4")
+#endif
+
 // ones among positions [0, off) and, if want_bit, the bit at position off (off < 63 then)
 __device__ __forceinline__ uint32_t rrr_prefix_ones(RrrTables const * t, uint32_t k, uint64_t nr, uint32_t off, bool want_bit, uint32_t & bit)
 {
@@ -69,39 +78,36 @@ __device__ __forceinline__ uint32_t rrr_prefix_ones(RrrTables const * t, uint32_
         bit = want_bit && one_at == off;
         return one_at < off;
     }
-    uint32_t const k0 = k, upto = off + (want_bit ? 1u : 0u);
-    uint32_t p = 0, k_at_off = k;
-    uint32_t const wide = upto < kWide ? upto : kWide;
-    for (; p < wide && k; ++p)
+    uint32_t const k0 = k;
+    uint32_t const wide = off < kWide ? off : kWide; // steps [0, wide) on 64-bit binomials, [wide, off) on 32-bit ones
     {
-        if (p == off)
-            k_at_off = k;
-        uint64_t const c = t->hi[kWide - 1 - p][k];
-        if (nr >= c)
+        uint64_t const * row = &t->hi[kWide - 1][0]; // C(62 - p, .) for p = 0; one row back per step
+        SG_UNROLL4
+        for (uint32_t p = 0; p < wide; ++p, row -= 64)
         {
-            nr -= c;
-            --k;
+            uint64_t const c = row[k];
+            bool const one = nr >= c;
+            nr -= one ? c : 0ull;
+            k -= one ? 1u : 0u;
         }
     }
-    if (p < upto && k)
+    uint32_t r = (uint32_t)nr; // from step 29 on nr < C(34, k) < 2^32
+    if (off > kWide)
     {
-        uint32_t r = (uint32_t)nr;
-        for (; p < upto && k; ++p)
+        uint32_t const * row = &t->lo[62 - kWide][0];
+        SG_UNROLL4
+        for (uint32_t p = kWide; p < off; ++p, row -= 64)
         {
-            if (p == off)
-                k_at_off = k;
-            uint32_t const c = t->lo[62 - p][k];
-            if (r >= c)
-            {
-                r -= c;
-                --k;
-            }
+            uint32_t const c = row[k];
+            bool const one = r >= c;
+            r -= one ? c : 0u;
+            k -= one ? 1u : 0u;
         }
     }
-    if (p <= off)
-        k_at_off = k; // the walk ended (no ones left) before reaching off
-    bit = want_bit ? k_at_off - ((p > off) ? k : k_at_off) : 0u;
-    return k0 - k_at_off;
+    bit = 0;
+    if (want_bit)
+        bit = off < kWide ? (nr >= t->hi[kWide - 1 - off][k]) : (r >= t->lo[62 - off][k]);
+    return k0 - k;
 }
 
 // position (0..62) of the target-th (1-based) B-bit of the block; requires target <= number of B-bits
@@ -113,36 +119,34 @@ __device__ __forceinline__ uint32_t rrr_select_in_block(RrrTables const * t, uin
         uint32_t const one_at = 62u - (uint32_t)nr;
         return B ? one_at : (target - 1 < one_at ? target - 1 : target);
     }
-    uint32_t p = 0;
-    for (; p < kWide && k; ++p)
     {
-        uint64_t const c = t->hi[kWide - 1 - p][k];
-        bool const one = nr >= c;
-        if (one)
+        uint64_t const * row = &t->hi[kWide - 1][0];
+        SG_UNROLL4
+        for (uint32_t p = 0; p < kWide; ++p, row -= 64)
         {
-            nr -= c;
-            --k;
-        }
-        if (one == (B != 0) && --target == 0)
-            return p;
-    }
-    if (k)
-    {
-        uint32_t r = (uint32_t)nr;
-        for (; k; ++p)
-        {
-            uint32_t const c = t->lo[62 - p][k];
-            bool const one = r >= c;
-            if (one)
-            {
-                r -= c;
-                --k;
-            }
-            if (one == (B != 0) && --target == 0)
+            uint64_t const c = row[k];
+            bool const one = nr >= c;
+            nr -= one ? c : 0ull;
+            k -= one ? 1u : 0u;
+            target -= (one == (B != 0)) ? 1u : 0u;
+            if (target == 0)
                 return p;
         }
     }
-    return p + target - 1; // no ones left: the rest of the block is zeros (only reachable for B == 0)
+    uint32_t r = (uint32_t)nr;
+    uint32_t const * row = &t->lo[62 - kWide][0];
+    SG_UNROLL4
+    for (uint32_t p = kWide; p < kBs; ++p, row -= 64)
+    {
+        uint32_t const c = row[k];
+        bool const one = r >= c;
+        r -= one ? c : 0u;
+        k -= one ? 1u : 0u;
+        target -= (one == (B != 0)) ? 1u : 0u;
+        if (target == 0)
+            return p;
+    }
+    return kBs - 1; // not reached for a valid target
 }
 
 struct RrrView

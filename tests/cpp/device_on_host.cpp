@@ -31,22 +31,6 @@ extern "C"
             }
         }
     }
-    // the two-pass form of the binned select op: bv_select_try where it decides, bv_select otherwise; returns the hits
-    uint64_t emu_select_two_pass(uint64_t const * words, uint64_t nbits, int b, uint32_t log_s, uint32_t interp, uint32_t pos_mode, uint64_t const * i, uint64_t n,
-                                 uint64_t * out)
-    {
-        HostImage im;
-        build(im, words, nbits, log_s, interp, pos_mode);
-        uint64_t hits = 0;
-        for (uint64_t k = 0; k < n; ++k)
-        {
-            uint64_t a = 0;
-            bool const hit = b ? bv_select_try<1>(im.view, i[k], a) : bv_select_try<0>(im.view, i[k], a);
-            hits += hit;
-            out[k] = hit ? a : (b ? bv_select<1>(im.view, i[k]) : bv_select<0>(im.view, i[k]));
-        }
-        return hits;
-    }
     // out[k] = select_b(i[k]), 1 <= i[k] <= #b-bits, with samples every 2^log_s b-bits
     void emu_select(uint64_t const * words, uint64_t nbits, int b, uint32_t log_s, uint32_t interp, uint32_t pos_mode, uint64_t const * i, uint64_t n, uint64_t * out)
     {

@@ -29,8 +29,6 @@ def emu():
     vp, u64, u32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32
     L.emu_rank1.argtypes = [vp, u64, vp, u64, vp, vp]
     L.emu_select.argtypes = [vp, u64, ctypes.c_int, u32, u32, u32, vp, u64, vp]
-    L.emu_select_two_pass.argtypes = [vp, u64, ctypes.c_int, u32, u32, u32, vp, u64, vp]
-    L.emu_select_two_pass.restype = u64
     L.emu_sel64.argtypes = [u64, u32]
     L.emu_sel64.restype = u32
     return L
@@ -97,10 +95,6 @@ def test_device_select_logic(emu, oracle, log_s, interp):
             out = np.zeros(len(q), np.uint64)
             emu.emu_select(ww.ctypes.data, nbits, b, log_s, interp & 1, interp >> 1, q.ctypes.data, len(q), out.ctypes.data)
             assert (out == ob.select(q, b)).all(), (cid, b, log_s, interp)
-            # the binned pipeline's two-pass form: first probe alone where it decides, the full search otherwise
-            out2 = np.zeros(len(q), np.uint64)
-            hits = emu.emu_select_two_pass(ww.ctypes.data, nbits, b, log_s, interp & 1, interp >> 1, q.ctypes.data, len(q), out2.ctypes.data)
-            assert (out2 == out).all() and hits <= len(q), (cid, b, log_s, interp, "two-pass")
             checked += len(q)
     assert checked > 100000
 
