@@ -65,8 +65,41 @@ static constexpr uint32_t kWide = 63 - kBinomSplit; // steps p = 0 .. 28 compare
 // live: LDS, compare, conditional subtract, conditional column step — 7 instructions per 64-bit step, 5 per 32-bit step.
 #ifdef SDSLGPU_HOST_EMU
 #define SG_UNROLL4
+// if nr >= c: nr -= c, --k; returns whether a one was placed
+inline bool rrr_step64(uint64_t & nr, uint32_t & k, uint64_t c)
+{
+    bool const one = nr >= c;
+    nr -= one ? c : 0ull;
+    k -= one ? 1u : 0u;
+    return one;
+}
+inline bool rrr_step32(uint32_t & r, uint32_t & k, uint32_t c)
+{
+    bool const one = r >= c;
+    r -= one ? c : 0u;
+    k -= one ? 1u : 0u;
+    return one;
+}
 #else
 #define SG_UNROLL4 _Pragma("unroll 4")
+// predicated forms: one compare, then the subtraction and the decrement under its predicate (the compiler's own
+// translation of the ternaries selects zero-or-c into temporaries first: 4 more instructions per 64-bit step)
+__device__ __forceinline__ bool rrr_step64(uint64_t & nr, uint32_t & k, uint64_t c)
+{
+    uint32_t one;
+    asm("{\n .reg .pred p;\n setp.ge.u64 p, %0, %3;\n @p sub.u64 %0, %0, %3;\n @p sub.u32 %1, %1, 1;\n selp.u32 %2, 1, 0, p;\n}"
+        : "+l"(nr), "+r"(k), "=r"(one)
+        : "l"(c));
+    return one != 0;
+}
+__device__ __forceinline__ bool rrr_step32(uint32_t & r, uint32_t & k, uint32_t c)
+{
+    uint32_t one;
+    asm("{\n .reg .pred p;\n setp.ge.u32 p, %0, %3;\n @p sub.u32 %0, %0, %3;\n @p sub.u32 %1, %1, 1;\n selp.u32 %2, 1, 0, p;\n}"
+        : "+r"(r), "+r"(k), "=r"(one)
+        : "r"(c));
+    return one != 0;
+}
 #endif
 
 // ones among positions [0, off) and, if want_bit, the bit at position off (off < 63 then)
@@ -84,12 +117,7 @@ __device__ __forceinline__ uint32_t rrr_prefix_ones(RrrTables const * t, uint32_
         uint64_t const * row = &t->hi[kWide - 1][0]; // C(62 - p, .) for p = 0; one row back per step
         SG_UNROLL4
         for (uint32_t p = 0; p < wide; ++p, row -= 64)
-        {
-            uint64_t const c = row[k];
-            bool const one = nr >= c;
-            nr -= one ? c : 0ull;
-            k -= one ? 1u : 0u;
-        }
+            rrr_step64(nr, k, row[k]);
     }
     uint32_t r = (uint32_t)nr; // from step 29 on nr < C(34, k) < 2^32
     if (off > kWide)
@@ -97,12 +125,7 @@ __device__ __forceinline__ uint32_t rrr_prefix_ones(RrrTables const * t, uint32_
         uint32_t const * row = &t->lo[62 - kWide][0];
         SG_UNROLL4
         for (uint32_t p = kWide; p < off; ++p, row -= 64)
-        {
-            uint32_t const c = row[k];
-            bool const one = r >= c;
-            r -= one ? c : 0u;
-            k -= one ? 1u : 0u;
-        }
+            rrr_step32(r, k, row[k]);
     }
     bit = 0;
     if (want_bit)
@@ -124,10 +147,7 @@ __device__ __forceinline__ uint32_t rrr_select_in_block(RrrTables const * t, uin
         SG_UNROLL4
         for (uint32_t p = 0; p < kWide; ++p, row -= 64)
         {
-            uint64_t const c = row[k];
-            bool const one = nr >= c;
-            nr -= one ? c : 0ull;
-            k -= one ? 1u : 0u;
+            bool const one = rrr_step64(nr, k, row[k]);
             target -= (one == (B != 0)) ? 1u : 0u;
             if (target == 0)
                 return p;
@@ -138,10 +158,7 @@ __device__ __forceinline__ uint32_t rrr_select_in_block(RrrTables const * t, uin
     SG_UNROLL4
     for (uint32_t p = kWide; p < kBs; ++p, row -= 64)
     {
-        uint32_t const c = row[k];
-        bool const one = r >= c;
-        r -= one ? c : 0u;
-        k -= one ? 1u : 0u;
+        bool const one = rrr_step32(r, k, row[k]);
         target -= (one == (B != 0)) ? 1u : 0u;
         if (target == 0)
             return p;
