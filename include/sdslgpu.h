@@ -357,8 +357,9 @@ int sdslgpu_group_release(sdslgpu_group *g, void *const *ptrs);
  * sdslgpu_load_sdsl_ex), so a replica answers exactly like its source.  Collective. */
 int sdslgpu_group_replicate(sdslgpu_group *g, const sdslgpu_handle *src, int root, sdslgpu_handle **out);
 
-/* Sharded forms of sdslgpu_rank / sdslgpu_select (KIND_BV handles, b = 0 / 1), sdslgpu_wt_rank (byte trees: KIND_WT_HUFF,
- * KIND_CSA_WT) and sdslgpu_fm_count: same results, in the same order, on every member. */
+/* Sharded forms of sdslgpu_rank / sdslgpu_select (KIND_BV, KIND_RRR63, KIND_SD handles, b = 0 / 1; plain bit vectors
+ * have the peer stores fused into their kernels, the compressed ones use the copy kernel), sdslgpu_wt_rank (byte
+ * trees: KIND_WT_HUFF, KIND_CSA_WT) and sdslgpu_fm_count: same results, in the same order, on every member. */
 int sdslgpu_group_rank(sdslgpu_group *g, const sdslgpu_handle *const *h, int b, const uint64_t *const *idx, uint64_t n,
                        uint64_t *const *out, int gather, void *const *streams);
 int sdslgpu_group_select(sdslgpu_group *g, const sdslgpu_handle *const *h, int b, const uint64_t *const *i, uint64_t n,

@@ -901,16 +901,45 @@ extern "C"
     }
 
     // ---------------------------------------------------------------------------------------- sharded queries
+    // bit-vector handles of any kind: plain (fan-out fused into its kernels), rrr_vector<63>, sd_vector<>
+    static int check_bitvector_members(sdslgpu_group const * g, sdslgpu_handle const * const * h, int b, char const * who)
+    {
+        if (!g || !h)
+        {
+            set_error("%s: null argument", who);
+            return SDSLGPU_EINVAL;
+        }
+        if (b != 0 && b != 1)
+        {
+            set_error("%s: b must be 0 or 1", who);
+            return SDSLGPU_EINVAL;
+        }
+        for (int k = 0; k < g->nlocal; ++k)
+        {
+            if (!h[k] || (h[k]->kind != SDSLGPU_KIND_BV && h[k]->kind != SDSLGPU_KIND_RRR63 && h[k]->kind != SDSLGPU_KIND_SD) || h[k]->kind != h[0]->kind)
+            {
+                set_error("%s: member %d has no bit-vector handle (plain, rrr, sd; the same kind on every member)", who, k);
+                return SDSLGPU_EINVAL;
+            }
+            if (h[k]->device != g->m[k].device)
+            {
+                set_error("%s: handle %d lives on device %d, the group member on device %d", who, k, h[k]->device, g->m[k].device);
+                return SDSLGPU_EINVAL;
+            }
+        }
+        return SDSLGPU_OK;
+    }
+
     int sdslgpu_group_rank(sdslgpu_group * g, const sdslgpu_handle * const * h, int b, const uint64_t * const * idx, uint64_t n, uint64_t * const * out,
                            int gather, void * const * streams)
     {
-        SG_TRY(check_members(g, h, SDSLGPU_KIND_BV, SDSLGPU_KIND_BV, "sdslgpu_group_rank"));
-        if (b != 0 && b != 1)
-        {
-            set_error("sdslgpu_group_rank: b must be 0 or 1");
-            return SDSLGPU_EINVAL;
-        }
+        SG_TRY(check_bitvector_members(g, h, b, "sdslgpu_group_rank"));
         return group_run(g, n, out, gather, streams, [&](int k, uint64_t first, uint64_t cnt, uint64_t * o, cudaStream_t s, Fan const * fan, bool * fanned) {
+            *fanned = false;
+            if (h[k]->kind == SDSLGPU_KIND_RRR63)
+                return rrr_rank_device(h[k], b, idx[k] + first, cnt, o, s);
+            if (h[k]->kind == SDSLGPU_KIND_SD)
+                return sd_rank_device(h[k], b, idx[k] + first, cnt, o, s);
             return bv_rank_device(h[k]->bv, h[k]->flags, b, idx[k] + first, cnt, o, s, fan, fanned);
         });
     }
@@ -918,13 +947,13 @@ extern "C"
     int sdslgpu_group_select(sdslgpu_group * g, const sdslgpu_handle * const * h, int b, const uint64_t * const * i, uint64_t n, uint64_t * const * out,
                              int gather, void * const * streams)
     {
-        SG_TRY(check_members(g, h, SDSLGPU_KIND_BV, SDSLGPU_KIND_BV, "sdslgpu_group_select"));
-        if (b != 0 && b != 1)
-        {
-            set_error("sdslgpu_group_select: b must be 0 or 1");
-            return SDSLGPU_EINVAL;
-        }
+        SG_TRY(check_bitvector_members(g, h, b, "sdslgpu_group_select"));
         return group_run(g, n, out, gather, streams, [&](int k, uint64_t first, uint64_t cnt, uint64_t * o, cudaStream_t s, Fan const * fan, bool * fanned) {
+            *fanned = false;
+            if (h[k]->kind == SDSLGPU_KIND_RRR63)
+                return rrr_select_device(h[k], b, i[k] + first, cnt, o, s);
+            if (h[k]->kind == SDSLGPU_KIND_SD)
+                return sd_select_device(h[k], b, i[k] + first, cnt, o, s);
             return bv_select_device(h[k]->bv, b, i[k] + first, cnt, o, s, fan, fanned);
         });
     }

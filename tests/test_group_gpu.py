@@ -102,6 +102,36 @@ def _run_bv(pkg, oracle, g, devices, gathers, nbits=3_000_001, nq=100_003, order
             h.close()
 
 
+def _run_compressed(pkg, oracle, g, devices, gathers):
+    """rrr_vector<63> / sd_vector<> through the same group calls (copy-kernel gather)"""
+    nbits, nq = 1_000_003, 40_001
+    w = cases.bernoulli_words(nbits, 0.2, 21)
+    rng = np.random.default_rng(6)
+    idx = rng.integers(0, nbits + 1, nq, dtype=np.uint64)
+    for kind, cls in (("rrr", pkg.RrrVector), ("sd", pkg.SdVector)):
+        o = getattr(oracle, kind)(w, nbits)
+        hs = [cls(w, nbits, device=d) for d in devices]
+        try:
+            sym = g.alloc(nq * 8)
+            outs = [sym.tensor(k) for k in range(len(devices))]
+            d_idx = [_dev(idx, d) for d in devices]
+            for gather in gathers:
+                for b in (1, 0):
+                    for t in outs:
+                        t.fill_(-7)
+                    g.rank(hs, b, d_idx, outs, gather=gather)
+                    for t in outs:
+                        assert (_host(t) == o.rank(idx, b)).all(), (kind, "rank", b, gather)
+                    sel = rng.integers(1, hs[0].arg_count(b) + 1, nq, dtype=np.uint64)
+                    g.select(hs, b, [_dev(sel, d) for d in devices], outs, gather=gather)
+                    for t in outs:
+                        assert (_host(t) == o.select(sel, b)).all(), (kind, "select", b, gather)
+            sym.release()
+        finally:
+            for h in hs:
+                h.close()
+
+
 def _run_wt_fm(pkg, oracle, g, devices, gathers):
     rng = np.random.default_rng(9)
     t = dict(texts.text_catalogue(zero_free=True, large=False))["dna"]
@@ -145,6 +175,7 @@ def test_group_loopback_fused_on_one_gpu(pkg, oracle, members):
     with pkg.Group.create(devices) as g:
         assert g.nranks == members and g.nlocal == members and g.fused_possible
         _run_bv(pkg, oracle, g, devices, [pkg.GATHER_FUSED, pkg.GATHER_AUTO])
+        _run_compressed(pkg, oracle, g, devices, [pkg.GATHER_FUSED])
         _run_wt_fm(pkg, oracle, g, devices, [pkg.GATHER_FUSED])
         import torch
 
@@ -173,6 +204,7 @@ def test_group_multi_device_nccl_and_fused(pkg, oracle):
         assert g.nranks == len(devices)
         gathers = [pkg.GATHER_NCCL] + ([pkg.GATHER_FUSED, pkg.GATHER_AUTO] if g.fused_possible else [])
         _run_bv(pkg, oracle, g, devices, gathers)
+        _run_compressed(pkg, oracle, g, devices, gathers)
         _run_wt_fm(pkg, oracle, g, devices, gathers)
         # replicate: an index built on device 0 arrives on every member and answers identically
         nbits = 1_000_003
