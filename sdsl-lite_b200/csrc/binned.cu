@@ -203,22 +203,17 @@ __global__ void __launch_bounds__(kTileThreads, 2) bin_tile_sort_kernel(uint64_t
 // ------------------------------------------------------------------------------------------------
 // kFan: every result is also stored to the same index of the other group members' result arrays (peer memory over
 // NVLink): each warp's store is 256 contiguous bytes per destination.
-// kRes32: the scratch holds answers mod 2^32; slot k lies in the bin b with loff[b] <= k < loff[b+1], and the answer is
-// base[b] + ((res32 - base[b]) mod 2^32) (every bin spans less than 2^32, checked when the bases were computed).
-template <bool kFan, bool kRes32>
+template <bool kFan>
 __global__ void __launch_bounds__(kTileThreads, 2) bin_unsort_kernel(uint64_t const * __restrict__ res,
                                                                      uint16_t const * __restrict__ lp,
                                                                      uint16_t const * __restrict__ loff,
                                                                      uint32_t nb,
                                                                      uint64_t n,
                                                                      uint64_t * __restrict__ out,
-                                                                     Fan const fan,
-                                                                     uint64_t const * __restrict__ bases)
+                                                                     Fan const fan)
 {
     extern __shared__ __align__(16) uint8_t unsort_smem[];
     uint64_t * sres = reinterpret_cast<uint64_t *>(unsort_smem);
-    __shared__ uint16_t sloff[kRes32 ? kMaxBins + 2 : 1];
-    __shared__ uint64_t sbase[kRes32 ? kMaxBins + 2 : 1];
     uint32_t const tid = threadIdx.x;
     uint64_t const tile = blockIdx.x, first = tile * kTile;
     uint32_t const nvalid = loff[tile * (nb + 2) + nb]; // slots >= nvalid hold the out-of-domain queries
@@ -229,51 +224,8 @@ __global__ void __launch_bounds__(kTileThreads, 2) bin_unsort_kernel(uint64_t co
         uint64_t p = first + (uint64_t)u * kTileThreads + tid;
         l[u] = (p < n) ? ld_stream_u16(lp + p) : 0xFFFFu;
     }
-    if (kRes32)
-    {
-        for (uint32_t k = tid; k < nb + 2; k += kTileThreads)
-        {
-            sloff[k] = loff[tile * (nb + 2) + k];
-            sbase[k] = k <= nb ? bases[k] : 0;
-        }
-        __syncthreads();
-        // eight consecutive slots per thread: one search for the bin of the first, then the bins only move forward
-        uint32_t const k0 = tid * kPer;
-        if (k0 < nvalid)
-        {
-            uint32_t const * r32 = reinterpret_cast<uint32_t const *>(res) + first + k0;
-            uint32_t v[kPer];
-            uint4 const a = *reinterpret_cast<uint4 const *>(r32), c = *reinterpret_cast<uint4 const *>(r32 + 4);
-            v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = c.x, v[5] = c.y, v[6] = c.z, v[7] = c.w;
-            uint32_t lo = 0, hi = nb; // largest b in [0, nb) with sloff[b] <= k0 (sloff[0] = 0)
-            while (hi - lo > 1)
-            {
-                uint32_t const mid = (lo + hi) >> 1;
-                if (sloff[mid] <= k0)
-                    lo = mid;
-                else
-                    hi = mid;
-            }
-            uint32_t b = lo;
-#pragma unroll
-            for (int u = 0; u < kPer; ++u)
-            {
-                uint32_t const k = k0 + u;
-                if (k < nvalid)
-                {
-                    while (k >= sloff[b + 1]) // also steps over empty bins
-                        ++b;
-                    uint64_t const base = sbase[b];
-                    sres[k] = base + (uint32_t)(v[u] - (uint32_t)base);
-                }
-            }
-        }
-    }
-    else
-    {
-        for (uint32_t k = tid; k < nvalid; k += kTileThreads)
-            sres[k] = ld_stream_u64(res + first + k);
-    }
+    for (uint32_t k = tid; k < nvalid; k += kTileThreads)
+        sres[k] = ld_stream_u64(res + first + k);
     __syncthreads();
 #pragma unroll
     for (int u = 0; u < kPer; ++u)
@@ -345,18 +297,11 @@ static uint64_t up256(uint64_t x)
     return (x + 255) & ~255ull;
 }
 
-std::mutex & bin_bases_mutex()
-{
-    static std::mutex m;
-    return m;
-}
-
-int bin_scratch_alloc(BinScratch & w, BinPlan const & p, cudaStream_t s, bool res32)
+int bin_scratch_alloc(BinScratch & w, BinPlan const & p, cudaStream_t s)
 {
     uint64_t slots = p.ntiles * kTile;
-    uint64_t b_recs = up256(slots * 4), b_lp = up256(slots * 2), b_loff = up256(p.ntiles * (p.nb + 2) * 2), b_res = up256(slots * (res32 ? 4 : 8));
+    uint64_t b_recs = up256(slots * 4), b_lp = up256(slots * 2), b_loff = up256(p.ntiles * (p.nb + 2) * 2), b_res = up256(slots * 8);
     w.s = s;
-    w.res32 = res32;
     cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&w.mem), kTicketBytes + b_recs + b_lp + b_loff + b_res, s);
     if (e != cudaSuccess)
     {
@@ -394,22 +339,20 @@ int bin_launch_tile_sort(BinPlan const & p, BinScratch const & w, uint64_t const
     return SDSLGPU_OK;
 }
 
-template <bool kFan, bool kRes32>
-static int launch_unsort(BinPlan const & p, BinScratch const & w, uint64_t n, uint64_t * out, cudaStream_t s, Fan const & fan, uint64_t const * bases)
+int bin_launch_unsort(BinPlan const & p, BinScratch const & w, uint64_t n, uint64_t * out, cudaStream_t s, Fan const * fan)
 {
     // 64 KB of dynamic shared memory for the result tile (attribute is per device / context: set on every call)
-    SG_CUDA(cudaFuncSetAttribute(bin_unsort_kernel<kFan, kRes32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTile * 8)));
-    bin_unsort_kernel<kFan, kRes32><<<(unsigned)p.ntiles, kTileThreads, kTile * 8, s>>>(w.res, w.lp, w.loff, p.nb, n, out, fan, bases);
+    if (fan && fan->n)
+    {
+        SG_CUDA(cudaFuncSetAttribute(bin_unsort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTile * 8)));
+        bin_unsort_kernel<true><<<(unsigned)p.ntiles, kTileThreads, kTile * 8, s>>>(w.res, w.lp, w.loff, p.nb, n, out, *fan);
+        SG_CUDA(cudaGetLastError());
+        return SDSLGPU_OK;
+    }
+    SG_CUDA(cudaFuncSetAttribute(bin_unsort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTile * 8)));
+    bin_unsort_kernel<false><<<(unsigned)p.ntiles, kTileThreads, kTile * 8, s>>>(w.res, w.lp, w.loff, p.nb, n, out, Fan{});
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
-}
-
-int bin_launch_unsort(BinPlan const & p, BinScratch const & w, uint64_t n, uint64_t * out, cudaStream_t s, Fan const * fan, uint64_t const * bases)
-{
-    bool const f = fan && fan->n;
-    if (bases)
-        return f ? launch_unsort<true, true>(p, w, n, out, s, *fan, bases) : launch_unsort<false, true>(p, w, n, out, s, Fan{}, bases);
-    return f ? launch_unsort<true, false>(p, w, n, out, s, *fan, nullptr) : launch_unsort<false, false>(p, w, n, out, s, Fan{}, nullptr);
 }
 
 unsigned bin_apply_grid(BinPlan const & p)
@@ -467,13 +410,6 @@ struct BvSelectOp
     }
 };
 
-// 32-bit result scratch (BinBases) for the plain bit vector's ops; SDSLGPU_BIN_RES32=0 keeps the 64-bit scratch (A/B knob)
-static bool res32_wanted()
-{
-    char const * e = std::getenv("SDSLGPU_BIN_RES32");
-    return !e || std::atoi(e) != 0;
-}
-
 bool bv_binned_wanted(BvImage const & v, uint64_t n, bool select)
 {
     return bin_wanted(v.order, v.nblocks * sizeof(bvblock), n, select ? kBinSelectDensity : kBinRankDensity);
@@ -483,8 +419,8 @@ int bv_rank_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64
 {
     uint64_t bytes = v.nblocks * sizeof(bvblock);
     if (b)
-        return bin_run(BvRankOp<1>{bv_view(v)}, bytes, 0, v.nbits, idx, n, out, s, done, false, fan, res32_wanted() ? &v.bases[1] : nullptr, v.owner);
-    return bin_run(BvRankOp<0>{bv_view(v)}, bytes, 0, v.nbits, idx, n, out, s, done, false, fan, res32_wanted() ? &v.bases[0] : nullptr, v.owner);
+        return bin_run(BvRankOp<1>{bv_view(v)}, bytes, 0, v.nbits, idx, n, out, s, done, false, fan);
+    return bin_run(BvRankOp<0>{bv_view(v)}, bytes, 0, v.nbits, idx, n, out, s, done, false, fan);
 }
 
 int bv_select_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done, Fan const * fan)
@@ -494,8 +430,8 @@ int bv_select_binned_device(BvImage const & v, int b, uint64_t const * idx, uint
     if (args == 0)
         return SDSLGPU_OK; // every query is out of domain: the direct kernel answers NPOS
     if (b)
-        return bin_run(BvSelectOp<1>{bv_view(v)}, bytes, 1, args - 1, idx, n, out, s, done, false, fan, res32_wanted() ? &v.bases[3] : nullptr, v.owner);
-    return bin_run(BvSelectOp<0>{bv_view(v)}, bytes, 1, args - 1, idx, n, out, s, done, false, fan, res32_wanted() ? &v.bases[2] : nullptr, v.owner);
+        return bin_run(BvSelectOp<1>{bv_view(v)}, bytes, 1, args - 1, idx, n, out, s, done, false, fan);
+    return bin_run(BvSelectOp<0>{bv_view(v)}, bytes, 1, args - 1, idx, n, out, s, done, false, fan);
 }
 
 } // namespace sdslgpu

@@ -22,8 +22,6 @@
 // halves two of those streams but the un-sort then needs the bin of every slot; measured, it gains nothing:
 // profiles/r01d_binned_v4_relative_*.)
 #pragma once
-#include <mutex>
-
 #include "internal.h"
 
 namespace sdslgpu
@@ -49,8 +47,7 @@ struct BinScratch
     uint32_t * recs = nullptr;
     uint16_t * lp = nullptr;
     uint16_t * loff = nullptr;
-    uint64_t * res = nullptr; // one answer per slot: u64, or u32 (answer mod 2^32) when the op's bin bases are cached
-    bool res32 = false;
+    uint64_t * res = nullptr;
     unsigned long long * ticket = nullptr;
     ~BinScratch()
     {
@@ -61,12 +58,9 @@ struct BinScratch
 
 // binned.cu
 bool bin_make_plan(uint64_t index_bytes, uint64_t maxkey, uint64_t n, BinPlan & p);
-int bin_scratch_alloc(BinScratch & w, BinPlan const & p, cudaStream_t s, bool res32 = false);
-// looks up / computes the cached bin bases of an op (host part; the kernel is launched by bin_run)
-std::mutex & bin_bases_mutex();
+int bin_scratch_alloc(BinScratch & w, BinPlan const & p, cudaStream_t s);
 int bin_launch_tile_sort(BinPlan const & p, BinScratch const & w, uint64_t const * q, uint64_t n, uint64_t sub, uint64_t maxkey, bool clamp, cudaStream_t s);
-int bin_launch_unsort(BinPlan const & p, BinScratch const & w, uint64_t n, uint64_t * out, cudaStream_t s, Fan const * fan = nullptr,
-                      uint64_t const * bases = nullptr);
+int bin_launch_unsort(BinPlan const & p, BinScratch const & w, uint64_t n, uint64_t * out, cudaStream_t s, Fan const * fan = nullptr);
 unsigned bin_apply_grid(BinPlan const & p);
 
 // Op: plain-old-data functor with
@@ -75,7 +69,7 @@ unsigned bin_apply_grid(BinPlan const & p);
 //   static constexpr uint32_t kSmem    bytes of dynamic shared memory its tables need (0: none)
 //   __device__ void stage(uint8_t *)   copy tables into shared memory (called by every thread; must __syncthreads if kSmem)
 //   __device__ uint64_t operator()(uint64_t key) const
-template <class Op, bool kRes32>
+template <class Op>
 __global__ void __launch_bounds__(kThreads, Op::kMinCtas) bin_apply_kernel(Op op,
                                                              uint32_t const * __restrict__ recs,
                                                              uint16_t const * __restrict__ loff,
@@ -110,7 +104,6 @@ __global__ void __launch_bounds__(kThreads, Op::kMinCtas) bin_apply_kernel(Op op
             uint64_t const hi = (uint64_t)b << shift;
             uint32_t const * r_in = recs + t * kTile;
             uint64_t * r_out = res + t * kTile;
-            uint32_t * r_out32 = reinterpret_cast<uint32_t *>(res) + t * kTile;
             constexpr int I = Op::kIlp;
             for (uint32_t k = o0 + lane; k < o1; k += 32 * I)
             { // I independent gathers per lane and trip
@@ -124,32 +117,10 @@ __global__ void __launch_bounds__(kThreads, Op::kMinCtas) bin_apply_kernel(Op op
 #pragma unroll
                 for (int u = 0; u < I; ++u)
                     if (k + 32 * u < o1)
-                    {
-                        if (kRes32)
-                            st_stream_u32(r_out32 + k + 32 * u, (uint32_t)a[u]);
-                        else
-                            st_stream_u64(r_out + k + 32 * u, a[u]);
-                    }
+                        st_stream_u64(r_out + k + 32 * u, a[u]);
             }
         }
     }
-}
-
-// smallest answer of every bin (answers are monotone in the key for rank and select): base[b] = op(b << shift),
-// base[nb] = op(maxkey); *too_wide is set when a bin spans 2^32 or more
-template <class Op>
-__global__ void bin_bases_kernel(Op op, uint32_t shift, uint32_t nb, uint64_t maxkey, uint64_t * __restrict__ base, uint32_t * __restrict__ too_wide)
-{
-    extern __shared__ __align__(16) uint8_t bin_smem[];
-    op.stage(bin_smem);
-    uint32_t const b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > nb)
-        return;
-    uint64_t const key = b < nb ? (uint64_t)b << shift : maxkey;
-    uint64_t const a = op(key), next = op(b + 1 < nb ? (uint64_t)(b + 1) << shift : maxkey);
-    base[b] = a;
-    if (b < nb && next - a >= (1ull << 32))
-        atomicExch(too_wide, 1u);
 }
 
 // the whole pipeline.  key = q - sub, in domain iff key <= maxkey; out-of-domain queries get SDSLGPU_NPOS
@@ -157,53 +128,20 @@ __global__ void bin_bases_kernel(Op op, uint32_t shift, uint32_t nb, uint64_t ma
 // *done = false (and nothing launched) when the plan does not fit (shift > 32, tile count overflow).
 template <class Op>
 int bin_run(Op const & op, uint64_t index_bytes, uint64_t sub, uint64_t maxkey, uint64_t const * q, uint64_t n, uint64_t * out, cudaStream_t s, bool * done,
-            bool clamp_high = false, Fan const * fan = nullptr, BinBases * cache = nullptr, DevicePool * pool = nullptr)
+            bool clamp_high = false, Fan const * fan = nullptr)
 {
     *done = false;
     BinPlan p;
     if (n == 0 || !bin_make_plan(index_bytes, maxkey, n, p))
         return SDSLGPU_OK;
-    // 32-bit result scratch when the op's bin bases are (or can be) cached with the structure
-    uint64_t const * bases = nullptr;
-    if (cache && pool && !clamp_high)
-    {
-        std::lock_guard<std::mutex> lock(bin_bases_mutex());
-        if (cache->state == 0 || cache->shift != p.shift || cache->maxkey != maxkey || cache->nb != p.nb)
-        { // first batch of this op on this structure (or another bin size): one tiny kernel and one 4-byte read-back
-            if (!cache->d)
-                SG_TRY(pool->alloc_t(&cache->d, kMaxBins + 4));
-            uint32_t * flag = reinterpret_cast<uint32_t *>(cache->d + kMaxBins + 2);
-            SG_CUDA(cudaMemsetAsync(flag, 0, 4, s));
-            bin_bases_kernel<Op><<<(p.nb + 1 + 127) / 128, 128, Op::kSmem, s>>>(op, p.shift, p.nb, maxkey, cache->d, flag);
-            SG_CUDA(cudaGetLastError());
-            uint32_t too_wide = 0;
-            SG_CUDA(cudaMemcpyAsync(&too_wide, flag, 4, cudaMemcpyDeviceToHost, s));
-            SG_CUDA(cudaStreamSynchronize(s));
-            cache->shift = p.shift;
-            cache->nb = p.nb;
-            cache->maxkey = maxkey;
-            cache->state = too_wide ? 2 : 1;
-        }
-        if (cache->state == 1)
-            bases = cache->d;
-    }
     BinScratch w;
-    SG_TRY(bin_scratch_alloc(w, p, s, bases != nullptr));
+    SG_TRY(bin_scratch_alloc(w, p, s));
     SG_TRY(bin_launch_tile_sort(p, w, q, n, sub, maxkey, clamp_high, s));
-    if (bases)
-    {
-        if (Op::kSmem > 48 * 1024)
-            SG_CUDA(cudaFuncSetAttribute(bin_apply_kernel<Op, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Op::kSmem));
-        bin_apply_kernel<Op, true><<<bin_apply_grid(p), kThreads, Op::kSmem, s>>>(op, w.recs, w.loff, p.shift, p.nb, p.ntiles, w.ticket, w.res);
-    }
-    else
-    {
-        if (Op::kSmem > 48 * 1024)
-            SG_CUDA(cudaFuncSetAttribute(bin_apply_kernel<Op, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Op::kSmem));
-        bin_apply_kernel<Op, false><<<bin_apply_grid(p), kThreads, Op::kSmem, s>>>(op, w.recs, w.loff, p.shift, p.nb, p.ntiles, w.ticket, w.res);
-    }
+    if (Op::kSmem > 48 * 1024)
+        SG_CUDA(cudaFuncSetAttribute(bin_apply_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Op::kSmem));
+    bin_apply_kernel<Op><<<bin_apply_grid(p), kThreads, Op::kSmem, s>>>(op, w.recs, w.loff, p.shift, p.nb, p.ntiles, w.ticket, w.res);
     SG_CUDA(cudaGetLastError());
-    SG_TRY(bin_launch_unsort(p, w, n, out, s, fan, bases));
+    SG_TRY(bin_launch_unsort(p, w, n, out, s, fan));
     *done = true;
     return SDSLGPU_OK;
 }

@@ -316,7 +316,6 @@ unsigned blocks_for(uint64_t n)
 
 int bv_build(DevicePool & pool, BvImage & v, uint32_t flags, uint64_t const * words_in, bool on_device, uint64_t nbits, cudaStream_t s)
 {
-    v.owner = &pool;
     v.nbits = nbits;
     v.nwords = (nbits + 63) >> 6;
     v.nblocks = nbits / kBlockBits + 1;

@@ -134,21 +134,8 @@ int classify(void const * p, int device, PtrSpace * space);
 namespace sdslgpu
 {
 
-// Per (structure, op): the smallest answer of every bin of the binned pipeline (binned.cuh), cached with the handle.
-// With it the pipeline's result scratch holds 32-bit answers (answer mod 2^32; the un-sort adds the bin's base back):
-// 8 bytes per query less in the two streams around the apply stage.  Usable when every bin spans less than 2^32.
-struct BinBases
-{
-    int state = 0; // 0: not computed for (shift, maxkey); 1: usable; 2: some bin spans >= 2^32 (64-bit scratch)
-    uint32_t shift = 0, nb = 0;
-    uint64_t maxkey = 0;
-    uint64_t * d = nullptr; // nb + 1 entries on the device (the last one: the answer of maxkey)
-};
-
 struct BvImage
 {
-    DevicePool * owner = nullptr; // the handle's pool (caches built after construction allocate from it)
-    mutable BinBases bases[4];    // [0/1]: rank_0 / rank_1, [2/3]: select_0 / select_1
     uint64_t nbits = 0;
     uint64_t nblocks = 0;      // nbits/224 + 1 (one past the end so rank(size) stays in range)
     bvblock * blocks = nullptr; // sector-interleaved payload + counts
