@@ -821,21 +821,28 @@ extern "C"
         // header: kind, flags, sa_dens, isa_dens, order, nbytes — then the reference-format blob (sdslgpu_serialize)
         uint64_t hdr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         std::vector<uint8_t> blob;
+        int root_status = SDSLGPU_OK;
         if (root_here)
-        {
+        { // a failure here must still reach the other ranks (hdr[6] stays 0): they are about to wait in ncclBroadcast
             uint64_t nb = 0;
             int what = replicate_what(src);
-            SG_TRY(sdslgpu_serialize(src, what, nullptr, 0, &nb));
-            blob.resize(nb ? nb : 1);
-            SG_TRY(sdslgpu_serialize(src, what, blob.data(), nb, &nb));
-            blob.resize(nb);
-            hdr[0] = (uint64_t)src->kind;
-            hdr[1] = src->flags & ~(uint32_t)SDSLGPU_F_V5_SCAN;
-            hdr[2] = src->kind == SDSLGPU_KIND_CSA_WT ? src->csa.sa_dens : 0;
-            hdr[3] = src->kind == SDSLGPU_KIND_CSA_WT ? src->csa.isa_dens : 0;
-            hdr[4] = (uint64_t)src->order;
-            hdr[5] = nb;
-            hdr[6] = 1; // valid
+            root_status = sdslgpu_serialize(src, what, nullptr, 0, &nb);
+            if (root_status == SDSLGPU_OK)
+            {
+                blob.resize(nb ? nb : 1);
+                root_status = sdslgpu_serialize(src, what, blob.data(), nb, &nb);
+                blob.resize(nb);
+            }
+            if (root_status == SDSLGPU_OK)
+            {
+                hdr[0] = (uint64_t)src->kind;
+                hdr[1] = src->flags & ~(uint32_t)SDSLGPU_F_V5_SCAN;
+                hdr[2] = src->kind == SDSLGPU_KIND_CSA_WT ? src->csa.sa_dens : 0;
+                hdr[3] = src->kind == SDSLGPU_KIND_CSA_WT ? src->csa.isa_dens : 0;
+                hdr[4] = (uint64_t)src->order;
+                hdr[5] = nb;
+                hdr[6] = 1; // valid
+            }
         }
         int prev = -1;
         cudaGetDevice(&prev);
@@ -867,8 +874,9 @@ extern "C"
                 return cuda_fail(e, "replicate header", __FILE__, __LINE__);
             if (hdr[6] != 1)
             {
-                set_error("sdslgpu_group_replicate: the root rank failed to serialise its handle");
-                return SDSLGPU_EINVAL;
+                if (!root_here)
+                    set_error("sdslgpu_group_replicate: the root rank failed to serialise its handle");
+                return root_here ? root_status : SDSLGPU_EINVAL;
             }
             uint64_t const nb = hdr[5];
             uint8_t * d_blob = nullptr;
@@ -888,6 +896,8 @@ extern "C"
             if (e != cudaSuccess)
                 return cuda_fail(e, "replicate blob", __FILE__, __LINE__);
         }
+        if (root_status != SDSLGPU_OK)
+            return root_status; // one process driving all devices: nobody is waiting
         for (int k = 0; k < g->nlocal; ++k)
         {
             out[k] = nullptr;
