@@ -376,6 +376,10 @@ struct BvRankOp
 #endif
     static constexpr int kIlp = BIN_RANK_ILP;
     static constexpr int kMinCtas = BIN_RANK_CTAS;
+#ifndef BIN_RANK_LOOKAHEAD
+#define BIN_RANK_LOOKAHEAD 2
+#endif
+    static constexpr int kLookAhead = BIN_RANK_LOOKAHEAD;
     static constexpr uint32_t kSmem = 0;
     BvView v;
     __device__ __forceinline__ void stage(uint8_t *) const
@@ -400,6 +404,10 @@ struct BvSelectOp
 #endif
     static constexpr int kIlp = BIN_SEL_ILP;
     static constexpr int kMinCtas = BIN_SEL_CTAS;
+#ifndef BIN_SEL_LOOKAHEAD
+#define BIN_SEL_LOOKAHEAD 1 // the record look-ahead spills (32 registers at 8 CTAs / SM)
+#endif
+    static constexpr int kLookAhead = BIN_SEL_LOOKAHEAD;
     static constexpr uint32_t kSmem = 0;
     BvView v;
     __device__ __forceinline__ void stage(uint8_t *) const

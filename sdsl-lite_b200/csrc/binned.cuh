@@ -69,6 +69,20 @@ unsigned bin_apply_grid(BinPlan const & p);
 //   static constexpr uint32_t kSmem    bytes of dynamic shared memory its tables need (0: none)
 //   __device__ void stage(uint8_t *)   copy tables into shared memory (called by every thread; must __syncthreads if kSmem)
 //   __device__ uint64_t operator()(uint64_t key) const
+//   static constexpr int kLookAhead    (optional; default 2) how far bin_apply_kernel issues memory operations ahead of
+//                                      their use: 0 nothing, 1 the next run's ticket, 2 also the next trip's record —
+//                                      each costs registers, so ops at the edge of their register budget opt out
+template <class Op, class = void>
+struct bin_look_ahead
+{
+    static constexpr int value = 2;
+};
+template <class Op>
+struct bin_look_ahead<Op, decltype((void)Op::kLookAhead)>
+{
+    static constexpr int value = Op::kLookAhead;
+};
+
 template <class Op>
 __global__ void __launch_bounds__(kThreads, Op::kMinCtas) bin_apply_kernel(Op op,
                                                              uint32_t const * __restrict__ recs,
@@ -87,14 +101,26 @@ __global__ void __launch_bounds__(kThreads, Op::kMinCtas) bin_apply_kernel(Op op
     // window of the bin-major sequence (about one run per resident warp: less than one bin) whatever the residency
     // or the speed of individual warps.  32 counters, each owning the runs w = 32 k + c, keep the atomics off one address.
     uint32_t const c = (blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) % kTicketLanes;
+    // A warp's work is a chain of dependent memory operations: ticket -> bin boundaries -> query record -> the op's own
+    // gathers.  Two of the links are taken off the critical path by issuing them one step ahead: the NEXT run's ticket
+    // is drawn while the current run is answered, and the NEXT trip's record is loaded before the current trip's gathers.
+    auto draw = [&]() -> unsigned long long {
+        unsigned long long w = 0;
+        if (lane == 0)
+            w = atomicAdd(ticket + c * kTicketStride, 1ull);
+        return w;
+    };
+    constexpr int kAhead = bin_look_ahead<Op>::value;
+    unsigned long long drawn = kAhead >= 1 ? draw() : 0ull;
     for (;;)
     {
-        unsigned long long w0 = 0;
-        if (lane == 0)
-            w0 = atomicAdd(ticket + c * kTicketStride, 1ull);
-        w0 = __shfl_sync(0xFFFFFFFFu, w0, 0) * kTicketLanes + c;
+        if (kAhead < 1)
+            drawn = draw();
+        unsigned long long const w0 = __shfl_sync(0xFFFFFFFFu, drawn, 0) * kTicketLanes + c;
         if (w0 >= runs)
             break;
+        if (kAhead >= 1)
+            drawn = draw(); // in flight until the next round of this loop
         {
             uint64_t const w = w0;
             uint32_t const b = (uint32_t)(w / ntiles);
@@ -105,6 +131,20 @@ __global__ void __launch_bounds__(kThreads, Op::kMinCtas) bin_apply_kernel(Op op
             uint32_t const * r_in = recs + t * kTile;
             uint64_t * r_out = res + t * kTile;
             constexpr int I = Op::kIlp;
+            if (I == 1 && kAhead >= 2)
+            {
+                uint32_t k = o0 + lane;
+                uint32_t rec = k < o1 ? ld_stream_u32(r_in + k) : 0u;
+                while (k < o1)
+                {
+                    uint32_t const kn = k + 32;
+                    uint32_t const recn = kn < o1 ? ld_stream_u32(r_in + kn) : 0u; // next trip's record: no consumer yet
+                    st_stream_u64(r_out + k, op(hi + rec));
+                    k = kn;
+                    rec = recn;
+                }
+                continue;
+            }
             for (uint32_t k = o0 + lane; k < o1; k += 32 * I)
             { // I independent gathers per lane and trip
                 uint64_t key[I], a[I];
