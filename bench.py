@@ -13,9 +13,10 @@ N = 1  `value` = queries/s with the query and result arrays already in HBM (CUDA
 N > 1  STRONG scaling of the same batch (north_star: "replicated index, NCCL all-gather of results only"): the 1e8 + 1e8
        queries are sharded over the N ranks through the C ABI's group calls (sdslgpu_group_rank / _select) and the
        results are all-gathered INSIDE the timed region, so every rank ends the step holding all 2e8 answers.
-       `value` = 2e8 / step time (max over ranks) with the fused gather (peer stores over NVLink from the un-sort
-       kernel) when peers can map each other's memory, else with ncclAllGather; `variants` carries the same step with
-       ncclAllGather, without any gather, and the weak line (every rank answers a whole batch of its own).
+       `value` = 2e8 / step time (max over ranks) with the best gather this box supports, each one first checked to
+       reproduce the single-GPU answers on every rank: packed peer stores (answers cross NVLink as 34-bit fields from the
+       shards' last kernels), u64 peer stores, ncclAllGather; `variants` carries the others, the step without any
+       gather, and the weak line (every rank answers a whole batch of its own).
 """
 import argparse
 import json
@@ -328,14 +329,42 @@ def main():
         launches_per_step = kernels_per_step
     else:
         fused = group.fused_possible
-        main_gather = pkg.GATHER_FUSED if fused else pkg.GATHER_NCCL
-        main_name = "fused: peer stores over NVLink from the last kernel of each shard" if fused else "ncclAllGather after the shard kernels"
+        # this rank's own single-GPU answers for the whole batch: what every gathered array must equal
+        ref_r, ref_s = torch.empty(nq, dtype=torch.int64, device="cuda"), torch.empty(nq, dtype=torch.int64, device="cuda")
+        bv.rank(d_idx, 1, out=ref_r)
+        bv.select(d_sel, 1, out=ref_s)
+
+        def gathered_ok(gather):
+            """one step with this gather on every rank; True iff every rank's arrays equal its single-GPU answers"""
+            good = 1
+            try:
+                d_out_r.fill_(-3)
+                d_out_s.fill_(-3)
+                group_step(gather)()
+                torch.cuda.synchronize()
+                good = int(torch.equal(d_out_r, ref_r) and torch.equal(d_out_s, ref_s))
+            except Exception as ex:  # an unsupported mode on this box
+                print("bench.py: gather mode", gather, "failed:", repr(ex)[:200], file=sys.stderr)
+                good = 0
+            f = torch.tensor([good], device="cuda")
+            dist.all_reduce(f, op=dist.ReduceOp.MIN)
+            return bool(f.item())
+
+        names = {pkg.GATHER_PACKED: "packed: the shards' last kernels store the answers as 34-bit fields into every peer's staging buffer over NVLink, each GPU widens what it received",
+                 pkg.GATHER_FUSED: "fused: peer stores of u64 answers over NVLink from the last kernel of each shard",
+                 pkg.GATHER_NCCL: "ncclAllGather after the shard kernels"}
+        candidates = ([pkg.GATHER_PACKED, pkg.GATHER_FUSED] if fused else []) + [pkg.GATHER_NCCL]
+        main_gather = next((gm for gm in candidates if gathered_ok(gm)), None)
+        if main_gather is None:
+            raise SystemExit("bench.py: no gather mode reproduces the single-GPU answers — refusing to report a number")
+        main_name = names[main_gather]
         main_t = timed(group_step(main_gather), args.steps, args.warmup, clocks=True)
-        # fused: 2 flag-exchange kernels per op; the shard kernels themselves do the peer stores
-        launches_per_step = kernels_per_step + (4 if fused else 0)
+        # peer-store modes: 2 flag-exchange kernels per op (+ 1 widening kernel per op when packed)
+        launches_per_step = kernels_per_step + (4 if main_gather != pkg.GATHER_NCCL else 0) + (2 if main_gather == pkg.GATHER_PACKED else 0)
         k2 = max(5, args.steps // 2)
-        if fused:
-            variants["nccl_all_gather"] = timed(group_step(pkg.GATHER_NCCL), k2, 3)
+        for gm, key in ((pkg.GATHER_FUSED, "fused_u64"), (pkg.GATHER_NCCL, "nccl_all_gather")):
+            if gm != main_gather and gm in candidates and gathered_ok(gm):
+                variants[key] = timed(group_step(gm), k2, 3)
         variants["no_gather"] = timed(group_step(pkg.GATHER_NONE), k2, 3)
         variants["weak_whole_batch_per_rank"] = timed(plain_step, k2, 3)
         for k, v in variants.items():
@@ -343,8 +372,11 @@ def main():
             v["value"] = per / (v["ms_per_step"] * 1e-3)
             v.pop("clocks", None)
         # leave the gathered results of the main variant in the arrays for the parity check below
+        d_out_r.fill_(-3)
+        d_out_s.fill_(-3)
         group_step(main_gather)()
         torch.cuda.synchronize()
+        del ref_r, ref_s
     ms_per_step = main_t["ms_per_step"]
     rank_ms, sel_ms, clocks, per_rank = main_t["rank_ms"], main_t["select_ms"], main_t["clocks"], main_t["per_rank"]
     value = 2 * nq / (ms_per_step * 1e-3)
@@ -506,10 +538,11 @@ def main():
             "extras": extras,
         }
         if world > 1:
-            nv = (world - 1) * shard_q * 8 * 2
+            bytes_per_answer = 34 / 8 if main_gather == pkg.GATHER_PACKED and nbits == 1 << 33 else 8
+            nv = int((world - 1) * shard_q * bytes_per_answer * 2)
             line["gather"] = {"how": main_name, "nvlink_bytes_sent_per_rank_per_step": nv, "nvlink_bytes_received_per_rank_per_step": nv,
                               "received_gbs_per_rank": nv / (ms_per_step * 1e-3) / 1e9,
-                              "limit": "each rank must RECEIVE (N-1)/N of 2e8 x 8 B per step over NVLink (900 GB/s per direction nominal): the results, not the kernels, bound the gathered line"}
+                              "limit": "each rank must RECEIVE (N-1)/N of the 2e8 answers per step over NVLink (900 GB/s per direction nominal; 8 B each as u64, 4.25 B packed): the answers, not the kernels, bound the gathered line"}
             line["value_no_gather"] = variants["no_gather"]["value"]
             line["variants"] = variants
         emit(line)

@@ -559,7 +559,7 @@ class WtInt(_Handle, _WaveletTreeOps):
 # ------------------------------------------------------------------------------------------------------
 # multi-GPU groups (include/sdslgpu.h "multi-GPU groups"; csrc/group.cu)
 # ------------------------------------------------------------------------------------------------------
-GATHER_NONE, GATHER_NCCL, GATHER_FUSED, GATHER_AUTO = 0, 1, 2, 3
+GATHER_NONE, GATHER_NCCL, GATHER_FUSED, GATHER_AUTO, GATHER_PACKED = 0, 1, 2, 3, 4
 UNIQUE_ID_BYTES = 128
 vpp = C.POINTER(vp)
 

@@ -5,6 +5,7 @@
 
 #include "binned.cuh"
 #include "bv_device.cuh"
+#include "fan.cuh"
 
 namespace sdslgpu
 {
@@ -201,9 +202,10 @@ __global__ void __launch_bounds__(kTileThreads, 2) bin_tile_sort_kernel(uint64_t
 // ------------------------------------------------------------------------------------------------
 // 3. back to the caller's order
 // ------------------------------------------------------------------------------------------------
-// kFan: every result is also stored to the same index of the other group members' result arrays (peer memory over
-// NVLink): each warp's store is 256 contiguous bytes per destination.
-template <bool kFan>
+// kFan = 1: every result is also stored to the same index of the other group members' result arrays (peer memory
+// over NVLink): each warp's store is 256 contiguous bytes per destination.  kFan = 2: the same results as w-bit fields
+// into the peers' staging regions (fan.cuh): w/2 words per warp and destination instead of 32.
+template <int kFan>
 __global__ void __launch_bounds__(kTileThreads, 2) bin_unsort_kernel(uint64_t const * __restrict__ res,
                                                                      uint16_t const * __restrict__ lp,
                                                                      uint16_t const * __restrict__ loff,
@@ -231,13 +233,18 @@ __global__ void __launch_bounds__(kTileThreads, 2) bin_unsort_kernel(uint64_t co
     for (int u = 0; u < kPer; ++u)
     {
         uint64_t p = first + (uint64_t)u * kTileThreads + tid;
+        uint64_t const v = l[u] < nvalid ? sres[l[u]] : SDSLGPU_NPOS;
         if (p < n)
         {
-            uint64_t const v = l[u] < nvalid ? sres[l[u]] : SDSLGPU_NPOS;
             st_stream_u64(out + p, v);
-            if (kFan)
-                for (uint32_t r = 0; r < fan.n; ++r)
-                    fan.dst[r][p] = v;
+            if (kFan == 1)
+                fan_store(fan, p, v);
+        }
+        if (kFan == 2)
+        { // warp-collective: 32 consecutive p per warp and u
+            uint64_t const p0 = p - (tid & 31u);
+            if (p0 < n)
+                fan_store_packed(fan, p0, tid & 31u, n - p0 < 32 ? (uint32_t)(n - p0) : 32u, v);
         }
     }
 }
@@ -339,20 +346,21 @@ int bin_launch_tile_sort(BinPlan const & p, BinScratch const & w, uint64_t const
     return SDSLGPU_OK;
 }
 
-int bin_launch_unsort(BinPlan const & p, BinScratch const & w, uint64_t n, uint64_t * out, cudaStream_t s, Fan const * fan)
+template <int kFan>
+static int launch_unsort(BinPlan const & p, BinScratch const & w, uint64_t n, uint64_t * out, cudaStream_t s, Fan const & fan)
 {
     // 64 KB of dynamic shared memory for the result tile (attribute is per device / context: set on every call)
-    if (fan && fan->n)
-    {
-        SG_CUDA(cudaFuncSetAttribute(bin_unsort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTile * 8)));
-        bin_unsort_kernel<true><<<(unsigned)p.ntiles, kTileThreads, kTile * 8, s>>>(w.res, w.lp, w.loff, p.nb, n, out, *fan);
-        SG_CUDA(cudaGetLastError());
-        return SDSLGPU_OK;
-    }
-    SG_CUDA(cudaFuncSetAttribute(bin_unsort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTile * 8)));
-    bin_unsort_kernel<false><<<(unsigned)p.ntiles, kTileThreads, kTile * 8, s>>>(w.res, w.lp, w.loff, p.nb, n, out, Fan{});
+    SG_CUDA(cudaFuncSetAttribute(bin_unsort_kernel<kFan>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTile * 8)));
+    bin_unsort_kernel<kFan><<<(unsigned)p.ntiles, kTileThreads, kTile * 8, s>>>(w.res, w.lp, w.loff, p.nb, n, out, fan);
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
+}
+
+int bin_launch_unsort(BinPlan const & p, BinScratch const & w, uint64_t n, uint64_t * out, cudaStream_t s, Fan const * fan)
+{
+    if (fan && fan->n)
+        return fan->width ? launch_unsort<2>(p, w, n, out, s, *fan) : launch_unsort<1>(p, w, n, out, s, *fan);
+    return launch_unsort<0>(p, w, n, out, s, Fan{});
 }
 
 unsigned bin_apply_grid(BinPlan const & p)

@@ -10,6 +10,7 @@
 // byte-identical to the reference's, and a rank kernel that reads it exactly as the reference does.
 #include <cstdlib>
 
+#include "fan.cuh"
 #include "internal.h"
 #include "bv_device.cuh"
 #include "scan.cuh"
@@ -110,8 +111,10 @@ __global__ void __launch_bounds__(kThreads) bv_samples_kernel(uint64_t const * _
 // ------------------------------------------------------------------------------------------------
 // rank: one 32-byte sector per query
 // ------------------------------------------------------------------------------------------------
-// kFan (multi-GPU group calls, group.cu): every result is also stored to the same index of the other members' arrays
-template <int B, int ILP, bool kFan>
+// kFan (multi-GPU group calls, group.cu; fan.cuh): 1 = every result is also stored to the same index of the other
+// members' arrays, 2 = as packed fields into their staging regions.  The loop bound is warp-uniform (all lanes of a warp
+// leave together) so that the packed form can shuffle.
+template <int B, int ILP, int kFan>
 __global__ void __launch_bounds__(kThreads) bv_rank_kernel(bvblock const * __restrict__ blocks,
                                                            uint64_t const * __restrict__ top,
                                                            uint64_t nbits,
@@ -121,8 +124,10 @@ __global__ void __launch_bounds__(kThreads) bv_rank_kernel(bvblock const * __res
                                                            Fan const fan)
 {
     uint64_t const stride = (uint64_t)gridDim.x * blockDim.x * ILP;
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x * ILP + threadIdx.x; base < n; base += stride)
+    uint32_t const lane = threadIdx.x & 31u;
+    for (uint64_t wbase = (uint64_t)blockIdx.x * blockDim.x * ILP + (threadIdx.x - lane); wbase < n; wbase += stride)
     {
+        uint64_t const base = wbase + lane;
         uint64_t i[ILP], blk[ILP];
         uint32_t cnt[ILP], d[ILP][7];
         bool ok[ILP];
@@ -141,17 +146,22 @@ __global__ void __launch_bounds__(kThreads) bv_rank_kernel(bvblock const * __res
         for (int u = 0; u < ILP; ++u)
         {
             uint64_t q = base + (uint64_t)u * blockDim.x;
+            uint32_t rem = (uint32_t)(i[u] - blk[u] * kBlockBits);
+            uint64_t r = __ldg(top + (blk[u] >> kSuperShift)) + cnt[u] + block_prefix_popc(d[u], rem);
+            if (!B)
+                r = i[u] - r;
+            r = ok[u] ? r : SDSLGPU_NPOS;
             if (q < n)
             {
-                uint32_t rem = (uint32_t)(i[u] - blk[u] * kBlockBits);
-                uint64_t r = __ldg(top + (blk[u] >> kSuperShift)) + cnt[u] + block_prefix_popc(d[u], rem);
-                if (!B)
-                    r = i[u] - r;
-                r = ok[u] ? r : SDSLGPU_NPOS;
                 st_stream_u64(out + q, r);
-                if (kFan)
-                    for (uint32_t p = 0; p < fan.n; ++p)
-                        fan.dst[p][q] = r;
+                if (kFan == 1)
+                    fan_store(fan, q, r);
+            }
+            if (kFan == 2)
+            {
+                uint64_t const q0 = q - lane;
+                if (q0 < n)
+                    fan_store_packed(fan, q0, lane, n - q0 < 32 ? (uint32_t)(n - q0) : 32u, r);
             }
         }
     }
@@ -204,21 +214,27 @@ __global__ void __launch_bounds__(kThreads) bv_rank_sdsl_kernel(uint64_t const *
 // ------------------------------------------------------------------------------------------------
 // select
 // ------------------------------------------------------------------------------------------------
-template <int B, bool kFan>
+template <int B, int kFan>
 __global__ void __launch_bounds__(kThreads)
     bv_select_kernel(BvView const v, uint64_t args, uint64_t const * __restrict__ idx, uint64_t n, uint64_t * __restrict__ out, Fan const fan)
 {
     uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
-    {
-        uint64_t i = ld_stream_u64(idx + q);
+    uint32_t const lane = threadIdx.x & 31u;
+    for (uint64_t q0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); q0 < n; q0 += stride)
+    { // warp-uniform bound: the packed fan-out shuffles
+        uint64_t const q = q0 + lane;
         uint64_t r = SDSLGPU_NPOS;
-        if (i >= 1 && i <= args)
-            r = bv_select<B>(v, i);
-        st_stream_u64(out + q, r);
-        if (kFan)
-            for (uint32_t p = 0; p < fan.n; ++p)
-                fan.dst[p][q] = r;
+        if (q < n)
+        {
+            uint64_t i = ld_stream_u64(idx + q);
+            if (i >= 1 && i <= args)
+                r = bv_select<B>(v, i);
+            st_stream_u64(out + q, r);
+            if (kFan == 1)
+                fan_store(fan, q, r);
+        }
+        if (kFan == 2)
+            fan_store_packed(fan, q0, lane, n - q0 < 32 ? (uint32_t)(n - q0) : 32u, r);
     }
 }
 
@@ -530,19 +546,26 @@ int bv_rank_device(BvImage const & v, uint32_t flags, int b, uint64_t const * id
     }
     else if (fan && fan->n)
     {
-        if (b)
-            bv_rank_kernel<1, ILP, true><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.nbits, idx, n, out, *fan);
+        if (fan->width)
+        {
+            if (b)
+                bv_rank_kernel<1, ILP, 2><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.nbits, idx, n, out, *fan);
+            else
+                bv_rank_kernel<0, ILP, 2><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.nbits, idx, n, out, *fan);
+        }
+        else if (b)
+            bv_rank_kernel<1, ILP, 1><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.nbits, idx, n, out, *fan);
         else
-            bv_rank_kernel<0, ILP, true><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.nbits, idx, n, out, *fan);
+            bv_rank_kernel<0, ILP, 1><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.nbits, idx, n, out, *fan);
         if (fanned)
             *fanned = true;
     }
     else
     {
         if (b)
-            bv_rank_kernel<1, ILP, false><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.nbits, idx, n, out, Fan{});
+            bv_rank_kernel<1, ILP, 0><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.nbits, idx, n, out, Fan{});
         else
-            bv_rank_kernel<0, ILP, false><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.nbits, idx, n, out, Fan{});
+            bv_rank_kernel<0, ILP, 0><<<grid, kThreads, 0, s>>>(v.blocks, v.top, v.nbits, idx, n, out, Fan{});
     }
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
@@ -574,17 +597,24 @@ int bv_select_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n,
     uint64_t args = b ? v.ones : v.nbits - v.ones;
     if (fan && fan->n)
     {
-        if (b)
-            bv_select_kernel<1, true><<<grid, kThreads, 0, s>>>(bv_view(v), args, idx, n, out, *fan);
+        if (fan->width)
+        {
+            if (b)
+                bv_select_kernel<1, 2><<<grid, kThreads, 0, s>>>(bv_view(v), args, idx, n, out, *fan);
+            else
+                bv_select_kernel<0, 2><<<grid, kThreads, 0, s>>>(bv_view(v), args, idx, n, out, *fan);
+        }
+        else if (b)
+            bv_select_kernel<1, 1><<<grid, kThreads, 0, s>>>(bv_view(v), args, idx, n, out, *fan);
         else
-            bv_select_kernel<0, true><<<grid, kThreads, 0, s>>>(bv_view(v), args, idx, n, out, *fan);
+            bv_select_kernel<0, 1><<<grid, kThreads, 0, s>>>(bv_view(v), args, idx, n, out, *fan);
         if (fanned)
             *fanned = true;
     }
     else if (b)
-        bv_select_kernel<1, false><<<grid, kThreads, 0, s>>>(bv_view(v), args, idx, n, out, Fan{});
+        bv_select_kernel<1, 0><<<grid, kThreads, 0, s>>>(bv_view(v), args, idx, n, out, Fan{});
     else
-        bv_select_kernel<0, false><<<grid, kThreads, 0, s>>>(bv_view(v), args, idx, n, out, Fan{});
+        bv_select_kernel<0, 0><<<grid, kThreads, 0, s>>>(bv_view(v), args, idx, n, out, Fan{});
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
 }

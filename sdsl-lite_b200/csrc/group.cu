@@ -22,6 +22,7 @@
 
 #include <nccl.h> // types and prototypes only; no link-time dependency
 
+#include "fan.cuh"
 #include "internal.h"
 
 namespace sdslgpu
@@ -140,6 +141,7 @@ struct sdslgpu_group
     bool p2p = false;      // symmetric memory works (IPC handles could be opened / peer access enabled)
     sdslgpu::GroupMember m[sdslgpu::kMaxRanks];
     std::vector<sdslgpu::SymBuf> syms;
+    sdslgpu::SymBuf stage; // SDSLGPU_GATHER_PACKED: per member one region per source rank, grown on demand
     uint64_t epoch = 0;
     std::mutex mu;
 };
@@ -200,6 +202,41 @@ __global__ void __launch_bounds__(kThreads) fan_copy_kernel(uint64_t const * __r
         uint64_t const v = ld_stream_u64(src + k);
         for (uint32_t r = 0; r < fan.n; ++r)
             fan.dst[r][k] = v;
+    }
+}
+
+// SDSLGPU_GATHER_PACKED for ops whose kernels do not fan out themselves: the shard's answers, packed, to every peer
+__global__ void __launch_bounds__(kThreads) fan_pack_kernel(uint64_t const * __restrict__ src, Fan const fan, uint64_t n)
+{
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t const lane = threadIdx.x & 31u;
+    for (uint64_t p0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); p0 < n; p0 += stride)
+    {
+        uint64_t const p = p0 + lane;
+        fan_store_packed(fan, p0, lane, n - p0 < 32 ? (uint32_t)(n - p0) : 32u, p < n ? ld_stream_u64(src + p) : 0ull);
+    }
+}
+
+// the receiving side: widen the fields the other members stored into my staging regions into my result array.
+// region r (source rank r != me) holds answers [r*s, (r+1)*s) as w-bit fields; all ones = SDSLGPU_NPOS
+__global__ void __launch_bounds__(kThreads)
+    fan_unpack_kernel(uint64_t const * __restrict__ stage, uint64_t region_words, uint32_t w, uint64_t s, int me, int nranks, uint64_t * __restrict__ out)
+{
+    uint64_t const total = (uint64_t)(nranks - 1) * s, stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t const mask = (1ull << w) - 1ull;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride)
+    {
+        uint64_t r = e / s;
+        uint64_t const i = e - r * s;
+        r += r >= (uint64_t)me ? 1u : 0u;
+        uint64_t const * reg = stage + r * region_words;
+        uint64_t const pos = i * w, word = pos >> 6;
+        uint32_t const off = (uint32_t)(pos & 63u);
+        uint64_t v = reg[word] >> off;
+        if (off + w > 64)
+            v |= reg[word + 1] << (64 - off);
+        v &= mask;
+        st_stream_u64(out + r * s + i, v == mask ? SDSLGPU_NPOS : v);
     }
 }
 
@@ -334,6 +371,8 @@ int finish_create(sdslgpu_group * g)
         cudaFuncAttributes fa; // loads the modules of the exchange / copy kernels now, not behind a spinning kernel
         SG_CUDA(cudaFuncGetAttributes(&fa, group_barrier_kernel));
         SG_CUDA(cudaFuncGetAttributes(&fa, fan_copy_kernel));
+        SG_CUDA(cudaFuncGetAttributes(&fa, fan_pack_kernel));
+        SG_CUDA(cudaFuncGetAttributes(&fa, fan_unpack_kernel));
         SG_CUDA(cudaStreamCreateWithFlags(&g->m[k].stream, cudaStreamNonBlocking));
         SG_CUDA(cudaMalloc(reinterpret_cast<void **>(&g->m[k].status), 256));
         SG_CUDA(cudaMemset(g->m[k].status, 0, 256));
@@ -393,8 +432,21 @@ int launch_barrier(sdslgpu_group * g, int k, uint64_t epoch, cudaStream_t s)
 
 // The sharded call.  shard(k, first, count, out, stream, fan, &fanned) launches member k's kernels for queries
 // [first, first + count) writing out[0 .. count) (a pointer already offset to `first`).
+// bits that hold every possible answer of an op (answers <= max_answer) with the all-ones pattern left free for
+// SDSLGPU_NPOS, rounded up to what fan_store_packed handles (even, 22 .. 62); 0: the op cannot travel packed
+uint32_t pack_width_for(uint64_t max_answer)
+{
+    uint32_t w = 1;
+    while (w < 64 && ((1ull << w) - 1ull) <= max_answer)
+        ++w;
+    w += w & 1u;
+    if (w < kPackMinWidth)
+        w = kPackMinWidth;
+    return w <= kPackMaxWidth ? w : 0u;
+}
+
 template <class Shard>
-int group_run(sdslgpu_group * g, uint64_t n, uint64_t * const * out, int gather, void * const * streams, Shard shard)
+int group_run(sdslgpu_group * g, uint64_t n, uint64_t * const * out, int gather, void * const * streams, uint32_t pack_width, Shard shard)
 {
     if (!g || !out)
     {
@@ -431,11 +483,17 @@ int group_run(sdslgpu_group * g, uint64_t n, uint64_t * const * out, int gather,
             sb = f;
             off0 = off;
         }
+    bool const packed_ok = g->p2p && g->nranks > 1 && pack_width != 0 && std::getenv("SDSLGPU_GROUP_NO_PACKED") == nullptr;
     int mode = gather;
     if (g->nranks == 1)
         mode = SDSLGPU_GATHER_NONE;
     else if (gather == SDSLGPU_GATHER_AUTO)
-        mode = fused_ok ? SDSLGPU_GATHER_FUSED : SDSLGPU_GATHER_NCCL;
+        mode = packed_ok ? SDSLGPU_GATHER_PACKED : fused_ok ? SDSLGPU_GATHER_FUSED : SDSLGPU_GATHER_NCCL;
+    if (mode == SDSLGPU_GATHER_PACKED && !packed_ok)
+    {
+        set_error("SDSLGPU_GATHER_PACKED needs peer-mapped memory between the members (and answers of at most 62 bits)");
+        return SDSLGPU_EINVAL;
+    }
     if (mode == SDSLGPU_GATHER_FUSED && !fused_ok)
     {
         set_error("SDSLGPU_GATHER_FUSED needs result arrays from sdslgpu_group_alloc (same offset on every member) and peer-mapped memory");
@@ -446,8 +504,16 @@ int group_run(sdslgpu_group * g, uint64_t n, uint64_t * const * out, int gather,
         set_error("SDSLGPU_GATHER_NCCL: no NCCL communicator in this group (%s)", g->loopback ? "loopback group on one device" : "libnccl.so.2 not found");
         return SDSLGPU_ENOTSUP;
     }
+    bool const peer_stores = mode == SDSLGPU_GATHER_FUSED || mode == SDSLGPU_GATHER_PACKED;
+    uint64_t const region_words = fan_region_words(s, pack_width) + 1; // + 1: the receiver reads two words per field
+    if (mode == SDSLGPU_GATHER_PACKED && g->stage.bytes < (uint64_t)g->nranks * region_words * 8)
+    { // first packed call (or a larger batch): everybody re-allocates its staging regions — collective, like the call itself
+        SG_TRY(nccl_barrier(g));
+        sym_free(g, g->stage);
+        SG_TRY(sym_alloc(g, (uint64_t)g->nranks * region_words * 8 + ((uint64_t)g->nranks * region_words * 8) / 4, g->stage));
+    }
     uint64_t const ep_in = g->epoch + 1, ep_out = g->epoch + 2;
-    if (mode == SDSLGPU_GATHER_FUSED)
+    if (peer_stores)
         g->epoch += 2;
     std::vector<cudaStream_t> st(g->nlocal);
     for (int k = 0; k < g->nlocal; ++k)
@@ -457,15 +523,22 @@ int group_run(sdslgpu_group * g, uint64_t n, uint64_t * const * out, int gather,
     // member this same host thread has not launched yet: the first launch of a kernel loads its module, which can
     // synchronise the context, and a spinning exchange kernel would then wait for a launch that cannot be issued.
     std::vector<Fan> fans(g->nlocal);
-    if (mode == SDSLGPU_GATHER_FUSED)
+    if (peer_stores)
         for (int k = 0; k < g->nlocal; ++k)
         {
             GroupMember & me = g->m[k];
             SG_CUDA(cudaSetDevice(me.device));
             for (int r = 0; r < g->nranks; ++r)
-                if (r != me.rank)
+            {
+                if (r == me.rank)
+                    continue;
+                if (mode == SDSLGPU_GATHER_PACKED) // my region of member r's staging buffer
+                    fans[k].dst[fans[k].n++] = static_cast<uint64_t *>(g->stage.peer[k][r]) + (uint64_t)me.rank * region_words;
+                else
                     fans[k].dst[fans[k].n++] = reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(sb->peer[k][r]) + off0) + (uint64_t)me.rank * s;
-            SG_TRY(launch_barrier(g, k, ep_in, st[k])); // every member has reached this call: its result array may be written
+            }
+            fans[k].width = mode == SDSLGPU_GATHER_PACKED ? pack_width : 0u;
+            SG_TRY(launch_barrier(g, k, ep_in, st[k])); // every member has reached this call: its arrays may be written
         }
     for (int k = 0; k < g->nlocal; ++k)
     {
@@ -479,7 +552,10 @@ int group_run(sdslgpu_group * g, uint64_t n, uint64_t * const * out, int gather,
             SG_TRY(shard(k, first, s, out[k] + first, st[k], fan.n ? &fan : nullptr, &fanned));
             if (fan.n && !fanned)
             {
-                fan_copy_kernel<<<grid_for(s), kThreads, 0, st[k]>>>(out[k] + first, fan, s);
+                if (fan.width)
+                    fan_pack_kernel<<<grid_for(s), kThreads, 0, st[k]>>>(out[k] + first, fan, s);
+                else
+                    fan_copy_kernel<<<grid_for(s), kThreads, 0, st[k]>>>(out[k] + first, fan, s);
                 SG_CUDA(cudaGetLastError());
             }
         }
@@ -489,11 +565,17 @@ int group_run(sdslgpu_group * g, uint64_t n, uint64_t * const * out, int gather,
             SG_TRY(shard(k, covered, n - covered, out[k] + covered, st[k], nullptr, &fanned));
         }
     }
-    if (mode == SDSLGPU_GATHER_FUSED)
+    if (peer_stores)
         for (int k = 0; k < g->nlocal; ++k)
         {
             SG_CUDA(cudaSetDevice(g->m[k].device));
-            SG_TRY(launch_barrier(g, k, ep_out, st[k])); // everybody's stores into my array have landed
+            SG_TRY(launch_barrier(g, k, ep_out, st[k])); // everybody's stores into my arrays have landed
+            if (mode == SDSLGPU_GATHER_PACKED && s)
+            {
+                fan_unpack_kernel<<<grid_for((uint64_t)(g->nranks - 1) * s), kThreads, 0, st[k]>>>(static_cast<uint64_t const *>(g->stage.local[k]), region_words,
+                                                                                                 pack_width, s, g->m[k].rank, g->nranks, out[k]);
+                SG_CUDA(cudaGetLastError());
+            }
         }
     if (mode == SDSLGPU_GATHER_NCCL && s)
     {
@@ -515,7 +597,7 @@ int group_run(sdslgpu_group * g, uint64_t n, uint64_t * const * out, int gather,
         {
             SG_CUDA(cudaSetDevice(g->m[k].device));
             SG_CUDA(cudaStreamSynchronize(st[k]));
-            if (mode == SDSLGPU_GATHER_FUSED)
+            if (peer_stores)
             {
                 uint32_t bad = 0;
                 SG_CUDA(cudaMemcpy(&bad, g->m[k].status, 4, cudaMemcpyDeviceToHost));
@@ -700,6 +782,7 @@ extern "C"
         for (SymBuf & sb : g->syms)
             sym_free(g, sb);
         g->syms.clear();
+        sym_free(g, g->stage);
         NcclApi * nc = nccl_api();
         for (int k = 0; k < g->nlocal; ++k)
         {
@@ -944,7 +1027,9 @@ extern "C"
                            int gather, void * const * streams)
     {
         SG_TRY(check_bitvector_members(g, h, b, "sdslgpu_group_rank"));
-        return group_run(g, n, out, gather, streams, [&](int k, uint64_t first, uint64_t cnt, uint64_t * o, cudaStream_t s, Fan const * fan, bool * fanned) {
+        uint64_t size = 0;
+        SG_TRY(sdslgpu_size(h[0], &size));
+        return group_run(g, n, out, gather, streams, pack_width_for(size), [&](int k, uint64_t first, uint64_t cnt, uint64_t * o, cudaStream_t s, Fan const * fan, bool * fanned) {
             *fanned = false;
             if (h[k]->kind == SDSLGPU_KIND_RRR63)
                 return rrr_rank_device(h[k], b, idx[k] + first, cnt, o, s);
@@ -958,7 +1043,9 @@ extern "C"
                              int gather, void * const * streams)
     {
         SG_TRY(check_bitvector_members(g, h, b, "sdslgpu_group_select"));
-        return group_run(g, n, out, gather, streams, [&](int k, uint64_t first, uint64_t cnt, uint64_t * o, cudaStream_t s, Fan const * fan, bool * fanned) {
+        uint64_t size = 0;
+        SG_TRY(sdslgpu_size(h[0], &size));
+        return group_run(g, n, out, gather, streams, pack_width_for(size), [&](int k, uint64_t first, uint64_t cnt, uint64_t * o, cudaStream_t s, Fan const * fan, bool * fanned) {
             *fanned = false;
             if (h[k]->kind == SDSLGPU_KIND_RRR63)
                 return rrr_select_device(h[k], b, i[k] + first, cnt, o, s);
@@ -972,7 +1059,9 @@ extern "C"
                               uint64_t * const * out, int gather, void * const * streams)
     {
         SG_TRY(check_members(g, h, SDSLGPU_KIND_WT_HUFF, SDSLGPU_KIND_CSA_WT, "sdslgpu_group_wt_rank"));
-        return group_run(g, n, out, gather, streams, [&](int k, uint64_t first, uint64_t cnt, uint64_t * o, cudaStream_t s, Fan const *, bool * fanned) {
+        uint64_t size = 0;
+        SG_TRY(sdslgpu_size(h[0], &size));
+        return group_run(g, n, out, gather, streams, pack_width_for(size), [&](int k, uint64_t first, uint64_t cnt, uint64_t * o, cudaStream_t s, Fan const *, bool * fanned) {
             *fanned = false;
             return wt_rank_device(h[k], i[k] + first, c[k] + first, cnt, o, s);
         });
@@ -982,7 +1071,9 @@ extern "C"
                                uint64_t * const * cnt_out, int gather, void * const * streams)
     {
         SG_TRY(check_members(g, h, SDSLGPU_KIND_CSA_WT, SDSLGPU_KIND_CSA_WT, "sdslgpu_group_fm_count"));
-        return group_run(g, n, cnt_out, gather, streams, [&](int k, uint64_t first, uint64_t cnt, uint64_t * o, cudaStream_t s, Fan const *, bool * fanned) {
+        uint64_t size = 0;
+        SG_TRY(sdslgpu_size(h[0], &size));
+        return group_run(g, n, cnt_out, gather, streams, pack_width_for(size), [&](int k, uint64_t first, uint64_t cnt, uint64_t * o, cudaStream_t s, Fan const *, bool * fanned) {
             *fanned = false;
             return fm_count_device(h[k], pats[k], pat_off[k] + first, cnt, o, nullptr, s);
         });

@@ -100,6 +100,7 @@ struct Fan
 {
     uint64_t * dst[kMaxFan];
     uint32_t n = 0;
+    uint32_t width = 0; // 0: dst[r] are the peers' u64 result arrays; w: their staging regions for w-bit fields (fan.cuh)
 };
 
 // Staging of the int_vector<w> wire format (sdslgpu_rank_iv / _select_iv): per slot the packed chunk as it crosses

@@ -53,7 +53,7 @@ def main():
     d_idx, d_sel = to_dev(idx), to_dev(sel)
     sym = g.alloc(nq * 8)
     out = sym.tensor(0)
-    gathers = [pkg.GATHER_NCCL] + ([pkg.GATHER_FUSED, pkg.GATHER_AUTO] if g.fused_possible else [])
+    gathers = [pkg.GATHER_NCCL] + ([pkg.GATHER_FUSED, pkg.GATHER_PACKED, pkg.GATHER_AUTO] if g.fused_possible else [])
     for order in (pkg.ORDER_BINNED, pkg.ORDER_DIRECT):
         bv.set_batch_order(order)
         for gather in gathers:

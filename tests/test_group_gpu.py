@@ -75,10 +75,14 @@ def _run_bv(pkg, oracle, g, devices, gathers, nbits=3_000_001, nq=100_003, order
                 for k, o in enumerate(outs2):
                     got = _host(o)
                     assert (got[:-1] == want_s[:-1]).all() and got[-1] == pkg.NPOS, ("select", order, gather, k)
-            if pkg.GATHER_NCCL in gathers:  # NCCL works on any device memory, not only group-allocated
-                g.rank(hs, 1, d_idx, plain, gather=pkg.GATHER_NCCL)
-                for o in plain:
-                    assert (_host(o)[3:] == want_r[1][3:]).all()
+            for gm in (pkg.GATHER_NCCL, pkg.GATHER_PACKED):  # both work on any device memory, not only group-allocated
+                if gm in gathers:
+                    for o in plain:
+                        o.fill_(-7)
+                    g.rank(hs, 1, d_idx, plain, gather=gm)
+                    for o in plain:
+                        got = _host(o)
+                        assert (got[3:] == want_r[1][3:]).all() and got[2] == pkg.NPOS, gm
         # GATHER_NONE: every member holds its own shard (and the left-over tail)
         for o in outs:
             o.fill_(-7)
@@ -174,9 +178,10 @@ def test_group_loopback_fused_on_one_gpu(pkg, oracle, members):
     devices = [0] * members
     with pkg.Group.create(devices) as g:
         assert g.nranks == members and g.nlocal == members and g.fused_possible
-        _run_bv(pkg, oracle, g, devices, [pkg.GATHER_FUSED, pkg.GATHER_AUTO])
-        _run_compressed(pkg, oracle, g, devices, [pkg.GATHER_FUSED])
-        _run_wt_fm(pkg, oracle, g, devices, [pkg.GATHER_FUSED])
+        _run_bv(pkg, oracle, g, devices, [pkg.GATHER_FUSED, pkg.GATHER_PACKED, pkg.GATHER_AUTO])
+        _run_bv(pkg, oracle, g, devices, [pkg.GATHER_PACKED], nbits=1 << 24, nq=70_001)  # 26-bit fields
+        _run_compressed(pkg, oracle, g, devices, [pkg.GATHER_FUSED, pkg.GATHER_PACKED])
+        _run_wt_fm(pkg, oracle, g, devices, [pkg.GATHER_FUSED, pkg.GATHER_PACKED])
         import torch
 
         with pytest.raises(pkg.SdslGpuError):  # FUSED needs group-allocated result arrays
@@ -202,7 +207,7 @@ def test_group_multi_device_nccl_and_fused(pkg, oracle):
     devices = list(range(min(n, 8)))
     with pkg.Group.create(devices) as g:
         assert g.nranks == len(devices)
-        gathers = [pkg.GATHER_NCCL] + ([pkg.GATHER_FUSED, pkg.GATHER_AUTO] if g.fused_possible else [])
+        gathers = [pkg.GATHER_NCCL] + ([pkg.GATHER_FUSED, pkg.GATHER_PACKED, pkg.GATHER_AUTO] if g.fused_possible else [])
         _run_bv(pkg, oracle, g, devices, gathers)
         _run_compressed(pkg, oracle, g, devices, gathers)
         _run_wt_fm(pkg, oracle, g, devices, gathers)

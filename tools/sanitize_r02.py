@@ -76,18 +76,20 @@ with pkg.Group.create([0, 0, 0]) as g:
     for order in (pkg.ORDER_BINNED, pkg.ORDER_DIRECT):
         for h in hs:
             h.set_batch_order(order)
-        g.rank(hs, 1, d_idx, outs, gather=pkg.GATHER_FUSED)
-        for o in outs:
-            assert (host(o) == ob.rank(idx, 1)).all()
-        g.select(hs, 1, d_sel, outs, gather=pkg.GATHER_FUSED)
-        for o in outs:
-            assert (host(o) == ob.select(sel, 1)).all()
+        for gm in (pkg.GATHER_FUSED, pkg.GATHER_PACKED):
+            g.rank(hs, 1, d_idx, outs, gather=gm)
+            for o in outs:
+                assert (host(o) == ob.rank(idx, 1)).all()
+            g.select(hs, 1, d_sel, outs, gather=gm)
+            for o in outs:
+                assert (host(o) == ob.select(sel, 1)).all()
     t = dict(texts.text_catalogue(zero_free=True, large=False))["dna"]
     qi, qc = texts.wt_queries(t, rng, nq)
     wts = [pkg.WtHuff(t) for _ in range(3)]
-    g.wt_rank(wts, [dev(qi)] * 3, [dev(qc)] * 3, outs, gather=pkg.GATHER_FUSED)
-    for o in outs:
-        assert (host(o) == orc.wt_huff(t).rank(qi, qc)).all()
+    for gm in (pkg.GATHER_FUSED, pkg.GATHER_PACKED):
+        g.wt_rank(wts, [dev(qi)] * 3, [dev(qc)] * 3, outs, gather=gm)
+        for o in outs:
+            assert (host(o) == orc.wt_huff(t).rank(qi, qc)).all()
     sym.release()
     for h in hs + wts:
         h.close()
