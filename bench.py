@@ -354,16 +354,20 @@ def main():
                  pkg.GATHER_FUSED: "fused: peer stores of u64 answers over NVLink from the last kernel of each shard",
                  pkg.GATHER_NCCL: "ncclAllGather after the shard kernels"}
         candidates = ([pkg.GATHER_PACKED, pkg.GATHER_FUSED] if fused else []) + [pkg.GATHER_NCCL]
-        main_gather = next((gm for gm in candidates if gathered_ok(gm)), None)
-        if main_gather is None:
+        verified = [gm for gm in candidates if gathered_ok(gm)]
+        if not verified:
             raise SystemExit("bench.py: no gather mode reproduces the single-GPU answers — refusing to report a number")
+        # which of them is the fastest depends on N (packed pays an extra widening kernel, u64 pays NVLink bytes):
+        # three untimed trial steps each, outside the timed region, decide
+        trial = {gm: timed(group_step(gm), 3, 2)["ms_per_step"] for gm in verified}
+        main_gather = min(trial, key=trial.get)
         main_name = names[main_gather]
         main_t = timed(group_step(main_gather), args.steps, args.warmup, clocks=True)
         # peer-store modes: 2 flag-exchange kernels per op (+ 1 widening kernel per op when packed)
         launches_per_step = kernels_per_step + (4 if main_gather != pkg.GATHER_NCCL else 0) + (2 if main_gather == pkg.GATHER_PACKED else 0)
         k2 = max(5, args.steps // 2)
-        for gm, key in ((pkg.GATHER_FUSED, "fused_u64"), (pkg.GATHER_NCCL, "nccl_all_gather")):
-            if gm != main_gather and gm in candidates and gathered_ok(gm):
+        for gm, key in ((pkg.GATHER_PACKED, "packed_34bit"), (pkg.GATHER_FUSED, "fused_u64"), (pkg.GATHER_NCCL, "nccl_all_gather")):
+            if gm != main_gather and gm in verified:
                 variants[key] = timed(group_step(gm), k2, 3)
         variants["no_gather"] = timed(group_step(pkg.GATHER_NONE), k2, 3)
         variants["weak_whole_batch_per_rank"] = timed(plain_step, k2, 3)
