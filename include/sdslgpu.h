@@ -337,12 +337,15 @@ typedef struct sdslgpu_group sdslgpu_group;
                                   (peer memory); out must come from sdslgpu_group_alloc.  Plain bit vectors: the un-sort
                                   stage of the binned pipeline does the stores; other ops: a peer-store copy kernel
                                   behind theirs.  No NCCL call on the data path. */
-#define SDSLGPU_GATHER_AUTO 3  /* PACKED when peers can map each other's memory, else FUSED / NCCL as available */
+#define SDSLGPU_GATHER_AUTO 3  /* the fastest available: FUSED when out is group-allocated, else PACKED when peers can map
+                                  each other's memory, else NCCL */
 #define SDSLGPU_GATHER_PACKED 4 /* like FUSED, but the answers cross NVLink as w-bit fields (w = bits of the largest
                                   possible answer, e.g. 34 instead of 64 for a 2^33-bit vector: the int_vector<w>
                                   layout) into a staging buffer the group owns on every member, and a kernel on the
-                                  receiving side widens them into out — which may be ANY device memory here.  The
-                                  collective is bound by the bytes every GPU has to receive; this halves them. */
+                                  receiving side widens them into out — which may be ANY device memory here.  Half the
+                                  NVLink bytes of FUSED, but measured 10-17 % slower than FUSED (the 136-byte stores
+                                  per warp and peer are not line-aligned, and the widening is one more kernel) and
+                                  3-17 % faster than NCCL: the mode for result arrays the group did not allocate. */
 
 int sdslgpu_group_unique_id(void *id128);
 int sdslgpu_group_create_rank(const void *id128, int nranks, int rank, int device, sdslgpu_group **out);

@@ -488,7 +488,7 @@ int group_run(sdslgpu_group * g, uint64_t n, uint64_t * const * out, int gather,
     if (g->nranks == 1)
         mode = SDSLGPU_GATHER_NONE;
     else if (gather == SDSLGPU_GATHER_AUTO)
-        mode = packed_ok ? SDSLGPU_GATHER_PACKED : fused_ok ? SDSLGPU_GATHER_FUSED : SDSLGPU_GATHER_NCCL;
+        mode = fused_ok ? SDSLGPU_GATHER_FUSED : packed_ok ? SDSLGPU_GATHER_PACKED : SDSLGPU_GATHER_NCCL; // measured order
     if (mode == SDSLGPU_GATHER_PACKED && !packed_ok)
     {
         set_error("SDSLGPU_GATHER_PACKED needs peer-mapped memory between the members (and answers of at most 62 bits)");
