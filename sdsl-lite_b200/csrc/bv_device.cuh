@@ -68,6 +68,10 @@ __device__ __forceinline__ uint64_t abs_before(bvblock const * __restrict__ bloc
 // bisecting on the block counts, so the result never depends on the guess.
 template <int B>
 __device__ __forceinline__ uint64_t bv_select_from(BvView const & v, uint64_t i, uint64_t lo, uint64_t hi, uint64_t g);
+// the same search, additionally handing out the block it ended in: g_out = its index, d_out = its 224 payload bits
+// (callers that look at the neighbourhood of the answer — sd_vector rank — read them from registers, not from memory)
+template <int B>
+__device__ __forceinline__ uint64_t bv_select_from(BvView const & v, uint64_t i, uint64_t lo, uint64_t hi, uint64_t g, uint32_t (&d_out)[7], uint64_t & g_out);
 
 template <int B>
 __device__ __forceinline__ uint64_t bv_select_between(BvView const & v, uint64_t i, uint64_t lo, uint64_t hi, uint64_t r, uint32_t log_span, bool interp)
@@ -75,13 +79,21 @@ __device__ __forceinline__ uint64_t bv_select_between(BvView const & v, uint64_t
     return bv_select_from<B>(v, i, lo, hi, interp ? lo + (((hi - lo) * r + (1ull << log_span >> 1)) >> log_span) : lo);
 }
 
-// the search proper: first probe at block g in [lo, hi], then walk / bisect
 template <int B>
 __device__ __forceinline__ uint64_t bv_select_from(BvView const & v, uint64_t i, uint64_t lo, uint64_t hi, uint64_t g)
 {
+    uint32_t d[7];
+    uint64_t g_out;
+    return bv_select_from<B>(v, i, lo, hi, g, d, g_out);
+}
+
+// the search proper: first probe at block g in [lo, hi], then walk / bisect
+template <int B>
+__device__ __forceinline__ uint64_t bv_select_from(BvView const & v, uint64_t i, uint64_t lo, uint64_t hi, uint64_t g, uint32_t (&d)[7], uint64_t & g_out)
+{
     bvblock const * __restrict__ blocks = v.blocks;
     uint64_t const * __restrict__ top = v.top;
-    uint32_t cnt, d[7];
+    uint32_t cnt;
     ld_block(blocks + g, cnt, d);
     uint64_t a1 = __ldg(top + (g >> kSuperShift)) + cnt;
     uint64_t before = B ? a1 : g * kBlockBits - a1;
@@ -139,15 +151,27 @@ __device__ __forceinline__ uint64_t bv_select_from(BvView const & v, uint64_t i,
             ld_block(blocks + g, cnt, d);
         c = block_popc<B>(d);
     }
+    g_out = g;
     return g * kBlockBits + block_select<B>(d, (uint32_t)need);
 }
 
+
+template <int B>
+__device__ __forceinline__ uint64_t bv_select(BvView const & v, uint64_t i, uint32_t (&d_out)[7], uint64_t & g_out);
 
 // position of the i-th (1-based) B-bit, given 1 <= i <= #B-bits
 // (device form of select_support_mcl<B>::select, select_support_mcl.hpp:384-439: sampled hint, then a
 //  scan over block counts instead of the reference's word scan)
 template <int B>
 __device__ __forceinline__ uint64_t bv_select(BvView const & v, uint64_t i)
+{
+    uint32_t d[7];
+    uint64_t g;
+    return bv_select<B>(v, i, d, g);
+}
+
+template <int B>
+__device__ __forceinline__ uint64_t bv_select(BvView const & v, uint64_t i, uint32_t (&d_out)[7], uint64_t & g_out)
 {
     uint32_t const * __restrict__ samp = v.samp[B];
     uint32_t const log_s = v.log_s[B];
@@ -174,9 +198,9 @@ __device__ __forceinline__ uint64_t bv_select(BvView const & v, uint64_t i)
       // multiply, and the three divisions by 7 are 32-bit multiply-high sequences instead of 64-bit ones.
         uint32_t const lo32 = (uint32_t)lo, hi32 = (uint32_t)hi;
         uint32_t const p = lo32 + (uint32_t)(((uint64_t)(hi32 - lo32) * (uint32_t)r + (1ull << log_s >> 1)) >> log_s);
-        return bv_select_from<B>(v, i, lo32 / 7u, hi32 / 7u, p / 7u);
+        return bv_select_from<B>(v, i, lo32 / 7u, hi32 / 7u, p / 7u, d_out, g_out);
     }
-    return bv_select_between<B>(v, i, lo, hi, r, log_s, v.interp[B] != 0);
+    return bv_select_from<B>(v, i, lo, hi, v.interp[B] ? lo + (((hi - lo) * r + (1ull << log_s >> 1)) >> log_s) : lo, d_out, g_out);
 }
 
 } // namespace sdslgpu

@@ -24,22 +24,37 @@ __device__ __forceinline__ uint64_t sd_low(SdView const & v, uint64_t j)
     return read_int(v.low, j * v.wl, v.wl);
 }
 
-// number of ones in [0, i)   (sd_vector.hpp:553-575)
+// bit `o` (0..223) of a block's payload held in registers, without dynamic register indexing
+__device__ __forceinline__ uint32_t sd_reg_bit(uint32_t const (&d)[7], uint32_t o)
+{
+    uint32_t w = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 7; ++j)
+        w = (j == (o >> 5)) ? d[j] : w;
+    return (w >> (o & 31u)) & 1u;
+}
+
+// number of ones in [0, i)   (sd_vector.hpp:553-575): the zero that closes bucket i >> wl in `high`, then backwards over
+// the bucket's elements while their low part is >= i's.  The select hands out the sector block it ended in, so the
+// bits below the zero are tested in registers; only a bucket that continues into the previous block costs a gather
+// per element (the reference reads `high` bit by bit, :566-573).
 __device__ __forceinline__ uint64_t sd_rank1_one(SdView const & v, uint64_t i)
 {
     uint64_t hv = i >> v.wl;
-    uint64_t sh = bv_select<0>(v.high, hv + 1); // end of bucket hv in `high`
-    uint64_t rl = sh - hv;                      // elements with high part <= hv
+    uint32_t d[7];
+    uint64_t g;
+    uint64_t sh = bv_select<0>(v.high, hv + 1, d, g); // end of bucket hv in `high`
+    uint64_t rl = sh - hv;                          // elements with high part <= hv
     if (rl == 0)
         return 0;
-    uint64_t vl = i & ((1ull << v.wl) - 1);
+    uint64_t const vl = i & ((1ull << v.wl) - 1), start = g * kBlockBits;
     do
     {
         if (!sh)
             return 0;
         --sh;
         --rl;
-    } while (bv_bit(v.high, sh) && sd_low(v, rl) >= vl);
+    } while ((sh >= start ? sd_reg_bit(d, (uint32_t)(sh - start)) : bv_bit(v.high, sh)) && sd_low(v, rl) >= vl);
     return rl + 1;
 }
 
