@@ -841,6 +841,7 @@ extern "C"
                 });
             }
             return run_batch(h, &in, 1, &o, 1, n, static_cast<cudaStream_t>(stream), [=](void const * const * ip, uint64_t cnt, void * const * op, cudaStream_t s) {
+                SG_TRY(bv_ensure_select_sectors(h, b, cnt)); // first large batch: one-gather select (bv_device.cuh)
                 return bv_select_device(h->bv, b, static_cast<uint64_t const *>(ip[0]), cnt, static_cast<uint64_t *>(op[0]), s);
             });
         case SDSLGPU_KIND_RRR63:
@@ -872,6 +873,8 @@ extern "C"
         {
         case SDSLGPU_KIND_BV:
             return run_batch_iv(h, in_words, in_width, n, out_words, out_width, user, [=](uint64_t const * q, uint64_t cnt, uint64_t * o, cudaStream_t s) {
+                if (op)
+                    SG_TRY(bv_ensure_select_sectors(h, b, cnt));
                 return op ? bv_select_device(h->bv, b, q, cnt, o, s) : bv_rank_device(h->bv, h->flags, b, q, cnt, o, s);
             });
         case SDSLGPU_KIND_RRR63:

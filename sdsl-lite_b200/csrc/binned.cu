@@ -49,27 +49,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 // key j of the tile: from the TMA buffer (complete tiles) or straight from global memory
 // (clamp: keys beyond maxkey — but not a wrapped-around 0 - sub — count as maxkey: for ops whose answer is the same
 //  for every query past the end, like select_support_rrr's in-band size())
-template <bool kFull>
-__device__ __forceinline__ bool tile_key(uint64_t const * __restrict__ src, uint32_t limit, uint32_t j, uint64_t sub, uint64_t maxkey, uint32_t clamp, uint64_t & key)
+template <bool kFull, bool kClamp>
+__device__ __forceinline__ bool tile_key(uint64_t const * __restrict__ src, uint32_t limit, uint32_t j, uint64_t sub, uint64_t maxkey, uint64_t & key)
 {
     if (!kFull && j >= limit)
         return false;
     key = (kFull ? src[j] : ld_stream_u64(src + j)) - sub;
-    if (clamp && key > maxkey && key != ~0ull)
+    if (kClamp && key > maxkey && key != ~0ull)
         key = maxkey;
     return true;
 }
 
 // pass A: histogram of the tile over the bins (bin nb = out of domain)
-template <bool kFull>
-__device__ __forceinline__ void tile_count(uint64_t const * __restrict__ src, uint32_t limit, uint64_t sub, uint64_t maxkey, uint32_t clamp, uint32_t shift,
+template <bool kFull, bool kClamp>
+__device__ __forceinline__ void tile_count(uint64_t const * __restrict__ src, uint32_t limit, uint64_t sub, uint64_t maxkey, uint32_t shift,
                                            uint32_t nb, uint32_t * __restrict__ cnt, uint32_t tid)
 {
 #pragma unroll
     for (int u = 0; u < kPer; ++u)
     {
         uint64_t key;
-        if (tile_key<kFull>(src, limit, (uint32_t)u * kTileThreads + tid, sub, maxkey, clamp, key))
+        if (tile_key<kFull, kClamp>(src, limit, (uint32_t)u * kTileThreads + tid, sub, maxkey, key))
             atomicAdd(&cnt[(key <= maxkey) ? (uint32_t)(key >> shift) : nb], 1u);
     }
 }
@@ -77,15 +77,15 @@ __device__ __forceinline__ void tile_count(uint64_t const * __restrict__ src, ui
 // pass B: every key takes the next free slot of its bin (cur[] starts at the bins' exclusive offsets): in-bin offsets
 // to shared memory in slot order, slots to `lp`.  Keeping nothing in registers between the passes (the keys are
 // re-read from shared memory) is what lets two 1024-thread CTAs share an SM without spills.
-template <bool kFull>
-__device__ __forceinline__ void tile_scatter(uint64_t const * __restrict__ src, uint32_t limit, uint64_t sub, uint64_t maxkey, uint32_t clamp, uint32_t shift,
+template <bool kFull, bool kClamp>
+__device__ __forceinline__ void tile_scatter(uint64_t const * __restrict__ src, uint32_t limit, uint64_t sub, uint64_t maxkey, uint32_t shift,
                                              uint32_t mask32, uint32_t nb, uint32_t * __restrict__ cur, uint32_t * __restrict__ srec, uint16_t * __restrict__ lp_t, uint32_t tid)
 {
 #pragma unroll
     for (int u = 0; u < kPer; ++u)
     {
         uint64_t key;
-        if (tile_key<kFull>(src, limit, (uint32_t)u * kTileThreads + tid, sub, maxkey, clamp, key))
+        if (tile_key<kFull, kClamp>(src, limit, (uint32_t)u * kTileThreads + tid, sub, maxkey, key))
         {
             uint32_t l = atomicAdd(&cur[(key <= maxkey) ? (uint32_t)(key >> shift) : nb], 1u);
             srec[l] = (uint32_t)key & mask32;
@@ -94,12 +94,11 @@ __device__ __forceinline__ void tile_scatter(uint64_t const * __restrict__ src, 
     }
 }
 
-template <bool kTma>
+template <bool kTma, bool kClamp>
 __global__ void __launch_bounds__(kTileThreads, 2) bin_tile_sort_kernel(uint64_t const * __restrict__ q,
                                                                         uint64_t n,
                                                                         uint64_t sub,
                                                                         uint64_t maxkey,
-                                                                        uint32_t clamp,
                                                                         uint32_t shift,
                                                                         uint32_t nb,
                                                                         uint64_t ntiles,
@@ -142,10 +141,10 @@ __global__ void __launch_bounds__(kTileThreads, 2) bin_tile_sort_kernel(uint64_t
         {
             mbar_wait(bar, parity);
             parity ^= 1u;
-            tile_count<true>(skey, limit, sub, maxkey, clamp, shift, nb, cnt, tid);
+            tile_count<true, kClamp>(skey, limit, sub, maxkey, shift, nb, cnt, tid);
         }
         else
-            tile_count<false>(q + base, limit, sub, maxkey, clamp, shift, nb, cnt, tid);
+            tile_count<false, kClamp>(q + base, limit, sub, maxkey, shift, nb, cnt, tid);
         __syncthreads();
         if (tid < 32)
         { // exclusive scan of the nb+1 counters; entry nb+1 receives the total
@@ -173,9 +172,9 @@ __global__ void __launch_bounds__(kTileThreads, 2) bin_tile_sort_kernel(uint64_t
         for (uint32_t k = tid; k < nb + 2; k += kTileThreads)
             loff[tile * (nb + 2) + k] = (uint16_t)cnt[k];
         if (full)
-            tile_scatter<true>(skey, limit, sub, maxkey, clamp, shift, mask32, nb, cur, srec, lp + base + tid, tid);
+            tile_scatter<true, kClamp>(skey, limit, sub, maxkey, shift, mask32, nb, cur, srec, lp + base + tid, tid);
         else
-            tile_scatter<false>(q + base, limit, sub, maxkey, clamp, shift, mask32, nb, cur, srec, lp + base + tid, tid);
+            tile_scatter<false, kClamp>(q + base, limit, sub, maxkey, shift, mask32, nb, cur, srec, lp + base + tid, tid);
         __syncthreads(); // srec complete; every key has been read out of skey for the last time
         if (kTma && tid == 0)
         {
@@ -252,7 +251,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) bin_unsort_kernel(uint64_t co
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static uint64_t chunk_target_bytes()
+static uint64_t chunk_target_bytes(uint32_t chunk_mib)
 {
     if (char const * e = std::getenv("SDSLGPU_BIN_CHUNK_BYTES")) // test / tuning knob
     {
@@ -260,13 +259,15 @@ static uint64_t chunk_target_bytes()
         if (v > 0)
             return (uint64_t)v;
     }
-    return 24ull << 20;
+    return (uint64_t)chunk_mib << 20;
 }
 
-// bins are equal ranges of the key space sized so that one bin's share of the index is ~24 MB
-bool bin_make_plan(uint64_t index_bytes, uint64_t maxkey, uint64_t n, BinPlan & p)
+// bins are equal ranges of the key space sized so that one bin's share of the index is ~chunk_mib MiB (24 unless the op
+// says otherwise: what is in flight at any moment — one bin's lines and the streams passing by — has to stay in the L2;
+// measured on the 2^33-bit vector, profiles/r02s_*, r02t_*: rank 16 MiB 1.177 ms, 24: 1.196, 32: 1.198, 48: 1.60)
+bool bin_make_plan(uint64_t index_bytes, uint64_t maxkey, uint64_t n, BinPlan & p, uint32_t chunk_mib)
 {
-    uint64_t target = chunk_target_bytes();
+    uint64_t target = chunk_target_bytes(chunk_mib);
     uint64_t want = (index_bytes + target - 1) / target;
     if (want < 1)
         want = 1;
@@ -329,7 +330,8 @@ int bin_scratch_alloc(BinScratch & w, BinPlan const & p, cudaStream_t s)
     return SDSLGPU_OK;
 }
 
-int bin_launch_tile_sort(BinPlan const & p, BinScratch const & w, uint64_t const * q, uint64_t n, uint64_t sub, uint64_t maxkey, bool clamp, cudaStream_t s)
+template <bool kClamp>
+static int launch_tile_sort(BinPlan const & p, BinScratch const & w, uint64_t const * q, uint64_t n, uint64_t sub, uint64_t maxkey, cudaStream_t s)
 {
     // persistent CTAs, two per SM (96 KB of shared memory each with the TMA key buffer)
     uint64_t const resident = 2ull * (uint64_t)sm_count();
@@ -337,13 +339,20 @@ int bin_launch_tile_sort(BinPlan const & p, BinScratch const & w, uint64_t const
     if ((reinterpret_cast<uintptr_t>(q) & 15u) == 0)
     {
         int smem = kTile * 4 + kTile * 8;
-        SG_CUDA(cudaFuncSetAttribute(bin_tile_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        bin_tile_sort_kernel<true><<<grid, kTileThreads, smem, s>>>(q, n, sub, maxkey, clamp ? 1u : 0u, p.shift, p.nb, p.ntiles, w.recs, w.lp, w.loff);
+        SG_CUDA(cudaFuncSetAttribute(bin_tile_sort_kernel<true, kClamp>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        bin_tile_sort_kernel<true, kClamp><<<grid, kTileThreads, smem, s>>>(q, n, sub, maxkey, p.shift, p.nb, p.ntiles, w.recs, w.lp, w.loff);
     }
     else
-        bin_tile_sort_kernel<false><<<grid, kTileThreads, kTile * 4, s>>>(q, n, sub, maxkey, clamp ? 1u : 0u, p.shift, p.nb, p.ntiles, w.recs, w.lp, w.loff);
+        bin_tile_sort_kernel<false, kClamp><<<grid, kTileThreads, kTile * 4, s>>>(q, n, sub, maxkey, p.shift, p.nb, p.ntiles, w.recs, w.lp, w.loff);
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
+}
+
+// clamp (select_support_rrr's in-band size() past the last bit) is a template parameter: the plain ops' sort carries no
+// trace of it
+int bin_launch_tile_sort(BinPlan const & p, BinScratch const & w, uint64_t const * q, uint64_t n, uint64_t sub, uint64_t maxkey, bool clamp, cudaStream_t s)
+{
+    return clamp ? launch_tile_sort<true>(p, w, q, n, sub, maxkey, s) : launch_tile_sort<false>(p, w, q, n, sub, maxkey, s);
 }
 
 template <int kFan>
@@ -388,6 +397,7 @@ struct BvRankOp
 #define BIN_RANK_LOOKAHEAD 2
 #endif
     static constexpr int kLookAhead = BIN_RANK_LOOKAHEAD;
+    static constexpr uint32_t kChunkMiB = 16; // a one-gather op turns its bins over fastest: smaller bins, -1.6 %
     static constexpr uint32_t kSmem = 0;
     BvView v;
     __device__ __forceinline__ void stage(uint8_t *) const
@@ -426,6 +436,27 @@ struct BvSelectOp
     }
 };
 
+// select through the select sectors (bv_device.cuh): one gather per query, like rank; the few queries whose sector is
+// marked "does not fit" take the sampled select
+template <int B>
+struct BvSelectSectOp
+{
+    static constexpr int kIlp = 1;
+    static constexpr int kMinCtas = 8;
+#ifndef BIN_SECT_LOOKAHEAD
+#define BIN_SECT_LOOKAHEAD 2
+#endif
+    static constexpr int kLookAhead = BIN_SECT_LOOKAHEAD;
+    static constexpr uint32_t kSmem = 0;
+    BvView v;
+    __device__ __forceinline__ void stage(uint8_t *) const
+    {}
+    __device__ __forceinline__ uint64_t operator()(uint64_t key) const
+    {
+        return bv_select_any<B>(v, key + 1);
+    }
+};
+
 bool bv_binned_wanted(BvImage const & v, uint64_t n, bool select)
 {
     return bin_wanted(v.order, v.nblocks * sizeof(bvblock), n, select ? kBinSelectDensity : kBinRankDensity);
@@ -445,6 +476,13 @@ int bv_select_binned_device(BvImage const & v, int b, uint64_t const * idx, uint
     uint64_t args = b ? v.ones : v.nbits - v.ones, bytes = v.nblocks * sizeof(bvblock);
     if (args == 0)
         return SDSLGPU_OK; // every query is out of domain: the direct kernel answers NPOS
+    if (v.sect[b])
+    { // the bins are ranges of the sector array
+        uint64_t const sect_bytes = v.nsect[b] * sizeof(bvblock);
+        if (b)
+            return bin_run(BvSelectSectOp<1>{bv_view(v)}, sect_bytes, 1, args - 1, idx, n, out, s, done, false, fan);
+        return bin_run(BvSelectSectOp<0>{bv_view(v)}, sect_bytes, 1, args - 1, idx, n, out, s, done, false, fan);
+    }
     if (b)
         return bin_run(BvSelectOp<1>{bv_view(v)}, bytes, 1, args - 1, idx, n, out, s, done, false, fan);
     return bin_run(BvSelectOp<0>{bv_view(v)}, bytes, 1, args - 1, idx, n, out, s, done, false, fan);

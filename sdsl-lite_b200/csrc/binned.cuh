@@ -57,7 +57,7 @@ struct BinScratch
 };
 
 // binned.cu
-bool bin_make_plan(uint64_t index_bytes, uint64_t maxkey, uint64_t n, BinPlan & p);
+bool bin_make_plan(uint64_t index_bytes, uint64_t maxkey, uint64_t n, BinPlan & p, uint32_t chunk_mib = 24);
 int bin_scratch_alloc(BinScratch & w, BinPlan const & p, cudaStream_t s);
 int bin_launch_tile_sort(BinPlan const & p, BinScratch const & w, uint64_t const * q, uint64_t n, uint64_t sub, uint64_t maxkey, bool clamp, cudaStream_t s);
 int bin_launch_unsort(BinPlan const & p, BinScratch const & w, uint64_t n, uint64_t * out, cudaStream_t s, Fan const * fan = nullptr);
@@ -72,6 +72,17 @@ unsigned bin_apply_grid(BinPlan const & p);
 //   static constexpr int kLookAhead    (optional; default 2) how far bin_apply_kernel issues memory operations ahead of
 //                                      their use: 0 nothing, 1 the next run's ticket, 2 also the next trip's record —
 //                                      each costs registers, so ops at the edge of their register budget opt out
+//   static constexpr uint32_t kChunkMiB (optional; default 24) the share of the index one bin covers
+template <class Op, class = void>
+struct bin_chunk_mib
+{
+    static constexpr uint32_t value = 24;
+};
+template <class Op>
+struct bin_chunk_mib<Op, decltype((void)Op::kChunkMiB)>
+{
+    static constexpr uint32_t value = Op::kChunkMiB;
+};
 template <class Op, class = void>
 struct bin_look_ahead
 {
@@ -172,7 +183,7 @@ int bin_run(Op const & op, uint64_t index_bytes, uint64_t sub, uint64_t maxkey, 
 {
     *done = false;
     BinPlan p;
-    if (n == 0 || !bin_make_plan(index_bytes, maxkey, n, p))
+    if (n == 0 || !bin_make_plan(index_bytes, maxkey, n, p, bin_chunk_mib<Op>::value))
         return SDSLGPU_OK;
     BinScratch w;
     SG_TRY(bin_scratch_alloc(w, p, s));

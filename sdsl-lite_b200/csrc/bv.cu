@@ -108,6 +108,20 @@ __global__ void __launch_bounds__(kThreads) bv_samples_kernel(uint64_t const * _
     }
 }
 
+// select sectors (bv_device.cuh): one thread per sector
+template <int B>
+__global__ void __launch_bounds__(kThreads) bv_select_sectors_kernel(BvView const v, uint64_t nblocks, uint64_t args, uint32_t ls, uint64_t nsect, bvblock * __restrict__ sect)
+{
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nsect)
+        return;
+    uint32_t c0, d[7];
+    bv_make_sector<B>(v, nblocks, args, ls, j, c0, d);
+    uint4 * o = reinterpret_cast<uint4 *>(sect + j);
+    o[0] = make_uint4(c0, d[0], d[1], d[2]);
+    o[1] = make_uint4(d[3], d[4], d[5], d[6]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // rank: one 32-byte sector per query
 // ------------------------------------------------------------------------------------------------
@@ -228,7 +242,9 @@ __global__ void __launch_bounds__(kThreads)
         {
             uint64_t i = ld_stream_u64(idx + q);
             if (i >= 1 && i <= args)
-                r = bv_select<B>(v, i);
+            {
+                r = bv_select_any<B>(v, i); // select sectors, once a large batch has had them built
+            }
             st_stream_u64(out + q, r);
             if (kFan == 1)
                 fan_store(fan, q, r);
@@ -617,6 +633,58 @@ int bv_select_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n,
         bv_select_kernel<0, 0><<<grid, kThreads, 0, s>>>(bv_view(v), args, idx, n, out, Fan{});
     SG_CUDA(cudaGetLastError());
     return SDSLGPU_OK;
+}
+
+// Builds the select sectors of pattern b of one of a handle's bit-vector images the first time a select batch large
+// enough for the locality-ordered pipeline arrives (the handle is logically const; same pattern as the two-bit pattern
+// images in api.cu).  Not built — and the sampled select keeps serving — for handles created with SDSLGPU_F_COMPACT,
+// vectors beyond 2^36 bits, densities below ~5 %, or when the memory is not there.
+int bv_ensure_select_sectors_image(sdslgpu_handle const * ch, BvImage const & cv, int b)
+{
+    if ((b != 0 && b != 1) || cv.sect_tried[b] || cv.samp[b] == nullptr)
+        return SDSLGPU_OK;
+    sdslgpu_handle * h = const_cast<sdslgpu_handle *>(ch);
+    std::lock_guard<std::mutex> lock(h->pat_mu);
+    BvImage & v = const_cast<BvImage &>(cv); // one of h's own images
+    if (v.sect_tried[b])
+        return SDSLGPU_OK;
+    v.sect_tried[b] = true;
+    uint64_t const args = b ? v.ones : v.nbits - v.ones;
+    uint32_t const ls = args ? bv_sect_log_s(args, v.nbits) : 0u;
+    bool off = (h->flags & SDSLGPU_F_COMPACT) != 0 || v.nbits > (1ull << 36) || ls == 0;
+    if (char const * e = std::getenv("SDSLGPU_SELECT_SECTORS")) // A/B knob
+        off = off || std::atoi(e) == 0;
+    if (off)
+        return SDSLGPU_OK;
+    uint64_t const nsect = ((args - 1) >> ls) + 1;
+    size_t free_b = 0, total_b = 0;
+    DeviceGuard g(h->device);
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || (nsect + 1) * sizeof(bvblock) + (1ull << 30) > free_b)
+    {
+        cudaGetLastError();
+        return SDSLGPU_OK; // not enough room next to what the caller still needs: keep the sampled select
+    }
+    bvblock * sect = nullptr;
+    if (h->pool.alloc_t(&sect, nsect + 1) != SDSLGPU_OK)
+        return SDSLGPU_OK;
+    if (b)
+        bv_select_sectors_kernel<1><<<blocks_for(nsect), kThreads, 0, nullptr>>>(bv_view(v), v.nblocks, args, ls, nsect, sect);
+    else
+        bv_select_sectors_kernel<0><<<blocks_for(nsect), kThreads, 0, nullptr>>>(bv_view(v), v.nblocks, args, ls, nsect, sect);
+    SG_CUDA(cudaGetLastError());
+    SG_CUDA(cudaStreamSynchronize(nullptr));
+    v.sect_log_s[b] = ls;
+    v.nsect[b] = nsect;
+    v.sect[b] = sect; // last: a concurrent reader either sees no sectors or complete ones
+    return SDSLGPU_OK;
+}
+
+// KIND_BV handles: a no-op unless a select batch of n queries would run through the pipeline
+int bv_ensure_select_sectors(sdslgpu_handle const * h, int b, uint64_t n)
+{
+    if ((b != 0 && b != 1) || h->bv.sect_tried[b] || !bv_binned_wanted(h->bv, n, true))
+        return SDSLGPU_OK;
+    return bv_ensure_select_sectors_image(h, h->bv, b);
 }
 
 int bv_access_device(BvImage const & v, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)

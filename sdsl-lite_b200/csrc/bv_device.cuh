@@ -19,7 +19,32 @@ struct BvView
     uint64_t ones;
     uint32_t interp[2]; // 1: start the block search at the interpolated position between two samples
     uint32_t samp_pos[2]; // 1: samp[] holds (position of the sampled bit) >> 5 instead of the index of its block
+    bvblock const * sect[2]; // select sectors (below) or nullptr
+    uint32_t sect_log_s[2];
 };
+
+// ------------------------------------------------------------------------------------------------
+// Select sectors: select in ONE 32-byte gather (large, dense vectors; built on the first large select batch).
+// Sector j of pattern B serves the B-bits number j*S + 1 .. (j+1)*S, S = 2^sect_log_s:
+//   cnt  : c0 = (position of B-bit number j*S + 1) >> 5, the 32-bit chunk it lies in; bit 31 = "does not fit"
+//   d[7] : the 224 bits of the vector from chunk c0 on — complemented for B = 0, so the B-bits are the set bits —
+//          with the bits before B-bit j*S + 1 cleared: the (r + 1)-th set bit of d is B-bit number j*S + r + 1.
+// S is chosen so that S B-bits span ~150 positions on average; where a sector's S B-bits need more than the 193 - 224
+// positions it holds (sparse stretches) bit 31 is set and the query goes the sampled way (bv_select).  The sampled
+// select needs two dependent gathers per query (sample pair, block) and a third one for 5 % of them; the request port
+// between an SM's L1 and the crossbar, not HBM, bounds it.  This structure trades memory for that:
+// 32 bytes per S B-bits = 2 bits per bit of a half-dense vector (the reference's select_support_mcl: 0.2).
+// ------------------------------------------------------------------------------------------------
+static constexpr uint32_t kSectOverflow = 0x80000000u;
+
+// S = 2^ls with S / density <= ~150 positions; ls < 3 (density below ~5 %): no sectors, 0 is returned
+__host__ __device__ __forceinline__ uint32_t bv_sect_log_s(uint64_t args, uint64_t nbits)
+{
+    uint32_t ls = 0;
+    while (ls < 7 && ((2ull << ls) * nbits <= 150ull * args))
+        ++ls;
+    return ls >= 3 ? ls : 0u;
+}
 
 // number of 1-bits in [0, pos), 0 <= pos <= nbits: one 32-byte sector gather
 // (device form of rank_support_v<1>::rank, rank_support_v.hpp:129-139)
@@ -201,6 +226,62 @@ __device__ __forceinline__ uint64_t bv_select(BvView const & v, uint64_t i, uint
         return bv_select_from<B>(v, i, lo32 / 7u, hi32 / 7u, p / 7u, d_out, g_out);
     }
     return bv_select_from<B>(v, i, lo, hi, v.interp[B] ? lo + (((hi - lo) * r + (1ull << log_s >> 1)) >> log_s) : lo, d_out, g_out);
+}
+
+// B-bit number key + 1 from its select sector; *fits = false (and nothing else done) when the sector is marked
+template <int B>
+__device__ __forceinline__ uint64_t bv_select_sector(BvView const & v, uint64_t key, bool & fits)
+{
+    uint32_t const ls = v.sect_log_s[B];
+    uint32_t c0, d[7];
+    ld_block(v.sect[B] + (key >> ls), c0, d);
+    fits = (c0 & kSectOverflow) == 0;
+    if (!fits)
+        return 0;
+    return ((uint64_t)c0 << 5) + block_select<1>(d, ((uint32_t)key & ((1u << ls) - 1u)) + 1u);
+}
+
+// select by whichever structure the image has: its select sector if there is one and the query fits it, else samples
+template <int B>
+__device__ __forceinline__ uint64_t bv_select_any(BvView const & v, uint64_t i)
+{
+    if (v.sect[B])
+    {
+        bool fits;
+        uint64_t const r = bv_select_sector<B>(v, i - 1, fits);
+        if (fits)
+            return r;
+    }
+    return bv_select<B>(v, i);
+}
+
+// what the build kernel stores for sector j (bv.cu bv_select_sectors_kernel; the CPU tests build their images with it)
+template <int B>
+__device__ __forceinline__ void bv_make_sector(BvView const & v, uint64_t nblocks, uint64_t args, uint32_t ls, uint64_t j, uint32_t & c0_out, uint32_t (&d)[7])
+{
+    uint64_t const pos0 = bv_select<B>(v, (j << ls) + 1);
+    uint64_t const c0 = pos0 >> 5;
+#pragma unroll
+    for (uint32_t t = 0; t < 7; ++t)
+    {
+        uint64_t const c = c0 + t, blk = c / 7;
+        uint32_t x = 0;
+        if (blk < nblocks && c * 32 < v.nbits)
+        {
+            x = ld_nc_u32(&v.blocks[blk].d[c - blk * 7]);
+            if (!B)
+            {
+                x = ~x;
+                if (c * 32 + 32 > v.nbits) // the vector ends inside this chunk: what lies behind it is not a 0-bit
+                    x &= (1u << (uint32_t)(v.nbits - c * 32)) - 1u;
+            }
+        }
+        d[t] = x;
+    }
+    d[0] &= ~((1u << ((uint32_t)pos0 & 31u)) - 1u);
+    uint64_t const left = args - (j << ls), S = 1ull << ls;
+    uint32_t const need = (uint32_t)(left < S ? left : S);
+    c0_out = (uint32_t)c0 | (block_popc<1>(d) < need ? kSectOverflow : 0u);
 }
 
 } // namespace sdslgpu

@@ -1051,6 +1051,7 @@ extern "C"
                 return rrr_select_device(h[k], b, i[k] + first, cnt, o, s);
             if (h[k]->kind == SDSLGPU_KIND_SD)
                 return sd_select_device(h[k], b, i[k] + first, cnt, o, s);
+            SG_TRY(bv_ensure_select_sectors(h[k], b, cnt));
             return bv_select_device(h[k]->bv, b, i[k] + first, cnt, o, s, fan, fanned);
         });
     }

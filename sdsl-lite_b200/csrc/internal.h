@@ -150,6 +150,11 @@ struct BvImage
     uint32_t log_s[2] = {6, 6};
     uint32_t interp[2] = {0, 0}; // interpolate between samples (set when the stride exceeds 64)
     uint32_t samp_pos[2] = {0, 0}; // samples hold (position >> 5) instead of block indices (vectors up to 2^36 bits)
+    // select sectors (bv_device.cuh): built by bv_ensure_select_sectors on the first large select batch of a KIND_BV handle
+    bvblock * sect[2] = {nullptr, nullptr};
+    uint64_t nsect[2] = {0, 0};
+    uint32_t sect_log_s[2] = {0, 0};
+    bool sect_tried[2] = {false, false}; // built, or found not to apply (density, size, memory): do not try again
     // optional SDSL layout (SDSLGPU_F_SDSL_LAYOUT): raw words (+ pad) and the m_basic_block tables
     uint64_t * words = nullptr;
     uint64_t nwords = 0;
@@ -170,6 +175,10 @@ inline BvView bv_view(BvImage const & v)
     w.interp[1] = v.interp[1];
     w.samp_pos[0] = v.samp_pos[0];
     w.samp_pos[1] = v.samp_pos[1];
+    w.sect[0] = v.sect[0];
+    w.sect[1] = v.sect[1];
+    w.sect_log_s[0] = v.sect_log_s[0];
+    w.sect_log_s[1] = v.sect_log_s[1];
     w.nbits = v.nbits;
     w.ones = v.ones;
     return w;
@@ -352,6 +361,8 @@ static constexpr uint32_t kBinRankDensity = 64, kBinSelectDensity = 192; // byte
 bool bv_binned_wanted(BvImage const & v, uint64_t n, bool select = false);
 bool bin_wanted(int order, uint64_t index_bytes, uint64_t n, uint32_t index_bytes_per_query = kBinRankDensity);
 int bv_rank_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done, Fan const * fan = nullptr);
+int bv_ensure_select_sectors(sdslgpu_handle const * h, int b, uint64_t n); // bv.cu; a no-op unless a binned select of n queries would use them
+int bv_ensure_select_sectors_image(sdslgpu_handle const * h, BvImage const & v, int b); // any bit-vector image the handle owns
 int bv_select_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done, Fan const * fan = nullptr);
 // wt.cu
 int wt_huff_upload(sdslgpu_handle * h, uint64_t size, uint64_t sigma, WtTree const & tree, uint64_t const * bv_words, uint64_t bv_bits, cudaStream_t s);

@@ -29,6 +29,8 @@ def emu():
     vp, u64, u32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32
     L.emu_rank1.argtypes = [vp, u64, vp, u64, vp, vp]
     L.emu_select.argtypes = [vp, u64, ctypes.c_int, u32, u32, u32, vp, u64, vp]
+    L.emu_select_sectors.argtypes = [vp, u64, ctypes.c_int, u32, vp, u64, vp]
+    L.emu_select_sectors.restype = ctypes.c_int64
     L.emu_sel64.argtypes = [u64, u32]
     L.emu_sel64.restype = u32
     return L
@@ -55,6 +57,13 @@ def _shapes():
     b = (rng.random(n) < 0.5).astype(np.uint8)
     b[100_000:600_000] = 0  # a desert inside random data (and an oasis for the zeros)
     yield "desert", cases.pack_bits(b), n
+    # gaps of 2 - 15 Mbit between neighbouring ones: hint ranges of tens of thousands of blocks around a handful of ones
+    n = 36_000_000
+    b = np.zeros(n, np.uint8)
+    b[[0, 5, 2_200_000, 2_200_001, 4_500_000, 19_500_000, 19_500_003, 35_999_999]] = 1
+    b[7_000_000:7_000_300] = rng.random(300) < 0.5
+    yield "wide_gaps", cases.pack_bits(b), n
+    yield "wide_gaps_inverted", cases.pack_bits(1 - b), n
 
 
 def test_word_select(emu):
@@ -97,6 +106,34 @@ def test_device_select_logic(emu, oracle, log_s, interp):
             assert (out == ob.select(q, b)).all(), (cid, b, log_s, interp)
             checked += len(q)
     assert checked > 100000
+
+
+@pytest.mark.parametrize("log_s", [0, 3, 6, 7])  # 0: the stride the library picks from the density
+def test_device_select_sectors(emu, oracle, log_s):
+    """Select sectors (bv_device.cuh: bv_make_sector / bv_select_sector): one 32-byte record answers a query, sectors
+    whose B-bits do not fit are marked and answered by the sampled select.  Forced strides put dense sectors on sparse
+    data (everything marked) and sparse sectors on dense data (nothing marked)."""
+    checked = marked_total = built = 0
+    for cid, w, nbits in _shapes():
+        ww = _words(w)
+        ob = oracle.bv(w, nbits)
+        for b in (1, 0):
+            m = int(ob.rank([nbits], b)[0])
+            q = cases.select_queries(m, 23 + log_s, 6000)
+            if not len(q):
+                continue
+            out = np.zeros(len(q), np.uint64)
+            marked = emu.emu_select_sectors(ww.ctypes.data, nbits, b, log_s, q.ctypes.data, len(q), out.ctypes.data)
+            if marked < 0:
+                assert log_s == 0, (cid, b)  # only the library's own choice may decline (density below ~5 %)
+                continue
+            built += 1
+            assert (out == ob.select(q, b)).all(), (cid, b, log_s)
+            checked += len(q) - marked
+            marked_total += marked
+    assert built >= 10 and checked > 50000
+    if log_s:
+        assert marked_total > 0  # the fallback was exercised
 
 
 # ---------------------------------------------------------------------------------------------------------------
