@@ -110,13 +110,13 @@ __global__ void __launch_bounds__(kThreads) bv_samples_kernel(uint64_t const * _
 
 // select sectors (bv_device.cuh): one thread per sector
 template <int B>
-__global__ void __launch_bounds__(kThreads) bv_select_sectors_kernel(BvView const v, uint64_t nblocks, uint64_t args, uint32_t ls, uint64_t nsect, bvblock * __restrict__ sect)
+__global__ void __launch_bounds__(kThreads) bv_select_sectors_kernel(BvView const v, uint64_t nblocks, uint64_t args, uint32_t stride, uint64_t nsect, bvblock * __restrict__ sect)
 {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nsect)
         return;
     uint32_t c0, d[7];
-    bv_make_sector<B>(v, nblocks, args, ls, j, c0, d);
+    bv_make_sector<B>(v, nblocks, args, stride, j, c0, d);
     uint4 * o = reinterpret_cast<uint4 *>(sect + j);
     o[0] = make_uint4(c0, d[0], d[1], d[2]);
     o[1] = make_uint4(d[3], d[4], d[5], d[6]);
@@ -650,13 +650,15 @@ int bv_ensure_select_sectors_image(sdslgpu_handle const * ch, BvImage const & cv
         return SDSLGPU_OK;
     v.sect_tried[b] = true;
     uint64_t const args = b ? v.ones : v.nbits - v.ones;
-    uint32_t const ls = args ? bv_sect_log_s(args, v.nbits) : 0u;
-    bool off = (h->flags & SDSLGPU_F_COMPACT) != 0 || v.nbits > (1ull << 36) || ls == 0;
+    uint32_t stride = bv_sect_stride(args, v.nbits);
+    if (char const * e = std::getenv("SDSLGPU_SELECT_SECTOR_STRIDE")) // tuning knob
+        stride = (uint32_t)std::atoi(e);
+    bool off = (h->flags & SDSLGPU_F_COMPACT) != 0 || v.nbits > (1ull << 36) || stride == 0 || args == 0;
     if (char const * e = std::getenv("SDSLGPU_SELECT_SECTORS")) // A/B knob
         off = off || std::atoi(e) == 0;
     if (off)
         return SDSLGPU_OK;
-    uint64_t const nsect = ((args - 1) >> ls) + 1;
+    uint64_t const nsect = (args - 1) / stride + 1;
     size_t free_b = 0, total_b = 0;
     DeviceGuard g(h->device);
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || (nsect + 1) * sizeof(bvblock) + (1ull << 30) > free_b)
@@ -668,12 +670,13 @@ int bv_ensure_select_sectors_image(sdslgpu_handle const * ch, BvImage const & cv
     if (h->pool.alloc_t(&sect, nsect + 1) != SDSLGPU_OK)
         return SDSLGPU_OK;
     if (b)
-        bv_select_sectors_kernel<1><<<blocks_for(nsect), kThreads, 0, nullptr>>>(bv_view(v), v.nblocks, args, ls, nsect, sect);
+        bv_select_sectors_kernel<1><<<blocks_for(nsect), kThreads, 0, nullptr>>>(bv_view(v), v.nblocks, args, stride, nsect, sect);
     else
-        bv_select_sectors_kernel<0><<<blocks_for(nsect), kThreads, 0, nullptr>>>(bv_view(v), v.nblocks, args, ls, nsect, sect);
+        bv_select_sectors_kernel<0><<<blocks_for(nsect), kThreads, 0, nullptr>>>(bv_view(v), v.nblocks, args, stride, nsect, sect);
     SG_CUDA(cudaGetLastError());
     SG_CUDA(cudaStreamSynchronize(nullptr));
-    v.sect_log_s[b] = ls;
+    v.sect_stride[b] = stride;
+    v.sect_magic[b] = bv_sect_magic(stride);
     v.nsect[b] = nsect;
     v.sect[b] = sect; // last: a concurrent reader either sees no sectors or complete ones
     return SDSLGPU_OK;

@@ -3,6 +3,8 @@
 // Used by bv.cu (plain rank/select), wt.cu (wavelet-tree levels), fm.cu (backward search, LF walks),
 // sd.cu (Elias-Fano high part).
 #pragma once
+#include <cmath>
+
 #include "common.cuh"
 
 namespace sdslgpu
@@ -20,30 +22,41 @@ struct BvView
     uint32_t interp[2]; // 1: start the block search at the interpolated position between two samples
     uint32_t samp_pos[2]; // 1: samp[] holds (position of the sampled bit) >> 5 instead of the index of its block
     bvblock const * sect[2]; // select sectors (below) or nullptr
-    uint32_t sect_log_s[2];
+    uint32_t sect_stride[2]; // S: B-bits per sector
+    uint64_t sect_magic[2];  // floor(2^64 / S) + 1: key / S = umul64hi(key, magic) for key < 2^64 / S
 };
 
 // ------------------------------------------------------------------------------------------------
 // Select sectors: select in ONE 32-byte gather (large, dense vectors; built on the first large select batch).
-// Sector j of pattern B serves the B-bits number j*S + 1 .. (j+1)*S, S = 2^sect_log_s:
+// Sector j of pattern B serves the B-bits number j*S + 1 .. (j+1)*S, S = sect_stride:
 //   cnt  : c0 = (position of B-bit number j*S + 1) >> 5, the 32-bit chunk it lies in; bit 31 = "does not fit"
 //   d[7] : the 224 bits of the vector from chunk c0 on — complemented for B = 0, so the B-bits are the set bits —
 //          with the bits before B-bit j*S + 1 cleared: the (r + 1)-th set bit of d is B-bit number j*S + r + 1.
-// S is chosen so that S B-bits span ~150 positions on average; where a sector's S B-bits need more than the 193 - 224
-// positions it holds (sparse stretches) bit 31 is set and the query goes the sampled way (bv_select).  The sampled
-// select needs two dependent gathers per query (sample pair, block) and a third one for 5 % of them; the request port
-// between an SM's L1 and the crossbar, not HBM, bounds it.  This structure trades memory for that:
-// 32 bytes per S B-bits = 2 bits per bit of a half-dense vector (the reference's select_support_mcl: 0.2).
+// S is the largest stride whose S B-bits still fit the record at the vector's density with 3.5 standard deviations to
+// spare (81 at density 1/2); where a sector's S B-bits need more than the 193 - 224 positions it holds (sparse
+// stretches) bit 31 is set and the query goes the sampled way (bv_select).  The sampled select needs two dependent
+// gathers per query (sample pair, block) and a third one for 5 % of them; the request port between an SM's L1 and the
+// crossbar, not HBM, bounds it.  This structure trades memory for that: 32 bytes per S B-bits = 1.6 bits
+// per bit of a half-dense vector (the reference's select_support_mcl: 0.2).
 // ------------------------------------------------------------------------------------------------
 static constexpr uint32_t kSectOverflow = 0x80000000u;
 
-// S = 2^ls with S / density <= ~150 positions; ls < 3 (density below ~5 %): no sectors, 0 is returned
-__host__ __device__ __forceinline__ uint32_t bv_sect_log_s(uint64_t args, uint64_t nbits)
+// B-bits per sector for a vector of `args` B-bits among `nbits`: the span of S B-bits at density d has mean S / d and
+// variance S (1 - d) / d^2; the largest S with mean + 3.5 sigma <= 208 (the record holds 193 - 224 positions, depending
+// on where in its first chunk the first B-bit lies).  Below 8 (density under ~8 %) a sector is no better than a
+// position list: 0 is returned and no sectors are built.
+inline uint32_t bv_sect_stride(uint64_t args, uint64_t nbits)
 {
-    uint32_t ls = 0;
-    while (ls < 7 && ((2ull << ls) * nbits <= 150ull * args))
-        ++ls;
-    return ls >= 3 ? ls : 0u;
+    if (args == 0 || nbits == 0)
+        return 0;
+    double const d = (double)args / (double)nbits, a = 3.5 * std::sqrt(1.0 - (d < 1.0 ? d : 1.0));
+    double const x = (-a + std::sqrt(a * a + 4.0 * 208.0 * d)) / 2.0;
+    uint32_t const S = (uint32_t)(x * x);
+    return S >= 8 ? (S > 208 ? 208u : S) : 0u;
+}
+inline uint64_t bv_sect_magic(uint32_t stride)
+{
+    return ~0ull / stride + 1; // floor(2^64 / S) + 1 (also when S divides 2^64)
 }
 
 // number of 1-bits in [0, pos), 0 <= pos <= nbits: one 32-byte sector gather
@@ -232,13 +245,13 @@ __device__ __forceinline__ uint64_t bv_select(BvView const & v, uint64_t i, uint
 template <int B>
 __device__ __forceinline__ uint64_t bv_select_sector(BvView const & v, uint64_t key, bool & fits)
 {
-    uint32_t const ls = v.sect_log_s[B];
+    uint64_t const j = __umul64hi(key, v.sect_magic[B]); // key / S
     uint32_t c0, d[7];
-    ld_block(v.sect[B] + (key >> ls), c0, d);
+    ld_block(v.sect[B] + j, c0, d);
     fits = (c0 & kSectOverflow) == 0;
     if (!fits)
         return 0;
-    return ((uint64_t)c0 << 5) + block_select<1>(d, ((uint32_t)key & ((1u << ls) - 1u)) + 1u);
+    return ((uint64_t)c0 << 5) + block_select<1>(d, (uint32_t)(key - j * v.sect_stride[B]) + 1u);
 }
 
 // select by whichever structure the image has: its select sector if there is one and the query fits it, else samples
@@ -257,9 +270,9 @@ __device__ __forceinline__ uint64_t bv_select_any(BvView const & v, uint64_t i)
 
 // what the build kernel stores for sector j (bv.cu bv_select_sectors_kernel; the CPU tests build their images with it)
 template <int B>
-__device__ __forceinline__ void bv_make_sector(BvView const & v, uint64_t nblocks, uint64_t args, uint32_t ls, uint64_t j, uint32_t & c0_out, uint32_t (&d)[7])
+__device__ __forceinline__ void bv_make_sector(BvView const & v, uint64_t nblocks, uint64_t args, uint32_t stride, uint64_t j, uint32_t & c0_out, uint32_t (&d)[7])
 {
-    uint64_t const pos0 = bv_select<B>(v, (j << ls) + 1);
+    uint64_t const pos0 = bv_select<B>(v, j * stride + 1);
     uint64_t const c0 = pos0 >> 5;
 #pragma unroll
     for (uint32_t t = 0; t < 7; ++t)
@@ -279,8 +292,8 @@ __device__ __forceinline__ void bv_make_sector(BvView const & v, uint64_t nblock
         d[t] = x;
     }
     d[0] &= ~((1u << ((uint32_t)pos0 & 31u)) - 1u);
-    uint64_t const left = args - (j << ls), S = 1ull << ls;
-    uint32_t const need = (uint32_t)(left < S ? left : S);
+    uint64_t const left = args - j * stride;
+    uint32_t const need = (uint32_t)(left < stride ? left : stride);
     c0_out = (uint32_t)c0 | (block_popc<1>(d) < need ? kSectOverflow : 0u);
 }
 

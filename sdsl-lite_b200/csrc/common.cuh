@@ -34,6 +34,10 @@ static inline int __ffs(int x)
 {
     return __builtin_ffs(x);
 }
+static inline uint64_t __umul64hi(uint64_t a, uint64_t b)
+{
+    return (uint64_t)(((unsigned __int128)a * b) >> 64);
+}
 template <class T>
 static inline T __ldg(T const * p)
 {

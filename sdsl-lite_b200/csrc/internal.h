@@ -153,7 +153,8 @@ struct BvImage
     // select sectors (bv_device.cuh): built by bv_ensure_select_sectors on the first large select batch of a KIND_BV handle
     bvblock * sect[2] = {nullptr, nullptr};
     uint64_t nsect[2] = {0, 0};
-    uint32_t sect_log_s[2] = {0, 0};
+    uint32_t sect_stride[2] = {0, 0};
+    uint64_t sect_magic[2] = {0, 0};
     bool sect_tried[2] = {false, false}; // built, or found not to apply (density, size, memory): do not try again
     // optional SDSL layout (SDSLGPU_F_SDSL_LAYOUT): raw words (+ pad) and the m_basic_block tables
     uint64_t * words = nullptr;
@@ -177,8 +178,10 @@ inline BvView bv_view(BvImage const & v)
     w.samp_pos[1] = v.samp_pos[1];
     w.sect[0] = v.sect[0];
     w.sect[1] = v.sect[1];
-    w.sect_log_s[0] = v.sect_log_s[0];
-    w.sect_log_s[1] = v.sect_log_s[1];
+    w.sect_stride[0] = v.sect_stride[0];
+    w.sect_stride[1] = v.sect_stride[1];
+    w.sect_magic[0] = v.sect_magic[0];
+    w.sect_magic[1] = v.sect_magic[1];
     w.nbits = v.nbits;
     w.ones = v.ones;
     return w;

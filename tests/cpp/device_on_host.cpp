@@ -40,19 +40,19 @@ extern "C"
             out[k] = b ? bv_select<1>(im.view, i[k]) : bv_select<0>(im.view, i[k]);
     }
     // the same through select sectors (bv_device.cuh): built with bv_make_sector as bv.cu's kernel does, answered with
-    // bv_select_sector, marked sectors by the sampled select.  log_s = 0: the library's choice (bv_sect_log_s).
+    // bv_select_sector, marked sectors by the sampled select.  stride = 0: the library's choice (bv_sect_stride).
     // Returns the number of queries that met a marked sector, or -1 if the density rules sectors out.
-    int64_t emu_select_sectors(uint64_t const * words, uint64_t nbits, int b, uint32_t log_s, uint64_t const * i, uint64_t n, uint64_t * out)
+    int64_t emu_select_sectors(uint64_t const * words, uint64_t nbits, int b, uint32_t stride, uint64_t const * i, uint64_t n, uint64_t * out)
     {
         HostImage im;
         build(im, words, nbits, 9, 1, 1);
         uint64_t const args = b ? im.view.ones : nbits - im.view.ones;
         if (args == 0)
             return -1;
-        uint32_t const ls = log_s ? log_s : bv_sect_log_s(args, nbits);
+        uint32_t const ls = stride ? stride : bv_sect_stride(args, nbits);
         if (ls == 0)
             return -1;
-        uint64_t const nsect = ((args - 1) >> ls) + 1, nblocks = nbits / kBlockBits + 1;
+        uint64_t const nsect = (args - 1) / ls + 1, nblocks = nbits / kBlockBits + 1;
         std::vector<bvblock> sect(nsect + 1);
         for (uint64_t j = 0; j < nsect; ++j)
         {
@@ -62,7 +62,8 @@ extern "C"
                 bv_make_sector<0>(im.view, nblocks, args, ls, j, sect[j].cnt, sect[j].d);
         }
         im.view.sect[b] = sect.data();
-        im.view.sect_log_s[b] = ls;
+        im.view.sect_stride[b] = ls;
+        im.view.sect_magic[b] = bv_sect_magic(ls);
         int64_t marked = 0;
         for (uint64_t k = 0; k < n; ++k)
         {

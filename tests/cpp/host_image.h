@@ -61,7 +61,8 @@ inline void build(HostImage & im, uint64_t const * words, uint64_t nbits, uint32
         im.samp[b].push_back((uint32_t)(pos_mode ? (nblocks - 1) * 7 + 6 : nblocks - 1));
         im.samp[b].push_back((uint32_t)(pos_mode ? (nblocks - 1) * 7 + 6 : nblocks - 1));
         im.view.sect[b] = nullptr; // select sectors: built by the harnesses that test them
-        im.view.sect_log_s[b] = 0;
+        im.view.sect_stride[b] = 0;
+        im.view.sect_magic[b] = 0;
         im.view.samp_pos[b] = pos_mode;
         im.view.samp[b] = im.samp[b].data();
         im.view.log_s[b] = log_s;

@@ -64,4 +64,14 @@ for name, cls in kinds:
         v.close()
         del sel
 os.environ.pop("SDSLGPU_SELECT_SECTORS", None)
+if "bv" not in skip:
+    for stride in [int(x) for x in os.environ.get("VARIANT_STRIDES", "").split(",") if x]:  # B-bits per select sector
+        os.environ["SDSLGPU_SELECT_SECTOR_STRIDE"] = str(stride)
+        v = pkg.BitVector(words, nbits)
+        sel = torch.randint(1, v.arg_count(1) + 1, (nq,), dtype=torch.int64, device="cuda", generator=g.manual_seed(7))
+        timed(f"bv_select_stride{stride}", lambda: v.select(sel, 1, out=out))
+        res[f"bv_stride{stride}_bytes"] = v.device_bytes
+        v.close()
+        del sel
+    os.environ.pop("SDSLGPU_SELECT_SECTOR_STRIDE", None)
 print(json.dumps(res), flush=True)
