@@ -68,7 +68,8 @@ extern "C" {
                                     (1.14 bytes/symbol; a backward-search step is one sector gather per Huffman
                                     level).  By default a CSA additionally holds 32 one-hot sector-block bitmaps
                                     and the BWT (5.6 bytes/symbol) so that a step is 2 gathers and
-                                    an LF step 3; results are identical.  Implied by SDSLGPU_F_RRR_BV. */
+                                    an LF step 3; results are identical.  Implied by SDSLGPU_F_RRR_BV.
+                                    Bit vectors (KIND_BV): never build select sectors (see sdslgpu_select). */
 
 /* bit patterns of sdslgpu_rank / sdslgpu_select / sdslgpu_arg_count on KIND_BV handles: the reference's
  * <t_b, t_pat_len> template arguments (rank_support_v.hpp:46, select_support_mcl.hpp:54).  An occurrence of a
@@ -132,6 +133,15 @@ int sdslgpu_rank(const sdslgpu_handle *h, int b, const uint64_t *idx, uint64_t n
  *          select_support_sd<b>::select (sd_vector.hpp:621-664);
  *          on KIND_BV also select_support_mcl<10|01|00|11, 2>::select (select_support.hpp:204-405). */
 int sdslgpu_select(const sdslgpu_handle *h, int b, const uint64_t *i, uint64_t n, uint64_t *out, void *stream);
+/* Memory note (KIND_BV, b in {0,1}).  The first select batch that SDSLGPU_ORDER_AUTO / _BINNED runs through the binned
+ * pipeline builds "select sectors" for that b (csrc/bv_device.cuh): one 32-byte record per S b-bits holding the position
+ * of the first of them and the 193 - 224 bits of the vector that follow it, so that a query is ONE gather (the sampled
+ * select it replaces: a sample pair, a block, and a neighbouring block for 5 % of the queries).  S follows from the
+ * density (81 at 1/2); the records cost 32/S bytes per b-bit — 1.7 GB for the ones of a 2^33-bit vector of density 1/2
+ * whose rank/select image is 1.3 GB — and are counted by sdslgpu_device_bytes once built.  They are NOT built for
+ * handles created with SDSLGPU_F_COMPACT, densities under ~8 %, vectors beyond 2^36 bits, or when less than the records
+ * + 1 GiB of device memory is free; the sampled select then keeps serving.  Results are identical either way.  The
+ * build (a few ms) synchronises the device once: do not make that first call inside a stream capture. */
 
 /* The same two calls with queries and results in the reference's own compact container: int_vector<w>.  Field k of
  * width w occupies bits [k*w, (k+1)*w) of the word array, LSB first (int_vector.hpp:1900-1904 for w = 1, get_int /
@@ -149,7 +159,7 @@ int sdslgpu_select_iv(const sdslgpu_handle *h, int b, const uint64_t *i_words, u
 
 /* Order of work inside one sdslgpu_rank / sdslgpu_select call on a KIND_BV handle; never changes a result.
  *   SDSLGPU_ORDER_DIRECT  one thread per query in the caller's order: one random DRAM gather per query
- *   SDSLGPU_ORDER_BINNED  the batch is counting-sorted tile by tile into ~24 MB chunks of the index, answered chunk
+ *   SDSLGPU_ORDER_BINNED  the batch is counting-sorted tile by tile into 16 - 24 MB chunks of the index, answered chunk
  *                         by chunk (L2-resident gathers) and un-sorted again; needs ~14 bytes of stream-ordered
  *                         scratch per query (cudaMallocAsync on the call's stream)
  *   SDSLGPU_ORDER_AUTO    (default) BINNED when the index is larger than the L2 (>= 192 MB) and the batch is dense
