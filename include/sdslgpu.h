@@ -140,7 +140,7 @@ int sdslgpu_select(const sdslgpu_handle *h, int b, const uint64_t *i, uint64_t n
  * density (81 at 1/2); the records cost 32/S bytes per b-bit — 1.7 GB for the ones of a 2^33-bit vector of density 1/2
  * whose rank/select image is 1.3 GB — and are counted by sdslgpu_device_bytes once built.  They are NOT built for
  * handles created with SDSLGPU_F_COMPACT, densities under ~8 %, vectors beyond 2^36 bits, or when less than the records
- * + 1 GiB of device memory is free; the sampled select then keeps serving.  Results are identical either way.  The
+ * + the batch's scratch + 1 GiB of device memory is free; the sampled select then keeps serving.  Results are identical either way.  The
  * build (a few ms) synchronises the device once: do not make that first call inside a stream capture. */
 
 /* The same two calls with queries and results in the reference's own compact container: int_vector<w>.  Field k of

@@ -639,7 +639,7 @@ int bv_select_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n,
 // enough for the locality-ordered pipeline arrives (the handle is logically const; same pattern as the two-bit pattern
 // images in api.cu).  Not built — and the sampled select keeps serving — for handles created with SDSLGPU_F_COMPACT,
 // vectors beyond 2^36 bits, densities below ~5 %, or when the memory is not there.
-int bv_ensure_select_sectors_image(sdslgpu_handle const * ch, BvImage const & cv, int b)
+int bv_ensure_select_sectors_image(sdslgpu_handle const * ch, BvImage const & cv, int b, uint64_t reserve_bytes)
 {
     if ((b != 0 && b != 1) || cv.sect_tried[b] || cv.samp[b] == nullptr)
         return SDSLGPU_OK;
@@ -661,10 +661,10 @@ int bv_ensure_select_sectors_image(sdslgpu_handle const * ch, BvImage const & cv
     uint64_t const nsect = (args - 1) / stride + 1;
     size_t free_b = 0, total_b = 0;
     DeviceGuard g(h->device);
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || (nsect + 1) * sizeof(bvblock) + (1ull << 30) > free_b)
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || (nsect + 1) * sizeof(bvblock) + reserve_bytes + (1ull << 30) > free_b)
     {
         cudaGetLastError();
-        return SDSLGPU_OK; // not enough room next to what the caller still needs: keep the sampled select
+        return SDSLGPU_OK; // not enough room next to the batch's own scratch and 1 GiB for the caller: keep the sampled select
     }
     bvblock * sect = nullptr;
     if (h->pool.alloc_t(&sect, nsect + 1) != SDSLGPU_OK)
@@ -687,7 +687,7 @@ int bv_ensure_select_sectors(sdslgpu_handle const * h, int b, uint64_t n)
 {
     if ((b != 0 && b != 1) || h->bv.sect_tried[b] || !bv_binned_wanted(h->bv, n, true))
         return SDSLGPU_OK;
-    return bv_ensure_select_sectors_image(h, h->bv, b);
+    return bv_ensure_select_sectors_image(h, h->bv, b, 16 * n); // 14 bytes of pipeline scratch per query (binned.cuh)
 }
 
 int bv_access_device(BvImage const & v, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s)

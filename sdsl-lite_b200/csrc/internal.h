@@ -365,7 +365,7 @@ bool bv_binned_wanted(BvImage const & v, uint64_t n, bool select = false);
 bool bin_wanted(int order, uint64_t index_bytes, uint64_t n, uint32_t index_bytes_per_query = kBinRankDensity);
 int bv_rank_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done, Fan const * fan = nullptr);
 int bv_ensure_select_sectors(sdslgpu_handle const * h, int b, uint64_t n); // bv.cu; a no-op unless a binned select of n queries would use them
-int bv_ensure_select_sectors_image(sdslgpu_handle const * h, BvImage const & v, int b); // any bit-vector image the handle owns
+int bv_ensure_select_sectors_image(sdslgpu_handle const * h, BvImage const & v, int b, uint64_t reserve_bytes); // any bit-vector image the handle owns
 int bv_select_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done, Fan const * fan = nullptr);
 // wt.cu
 int wt_huff_upload(sdslgpu_handle * h, uint64_t size, uint64_t sigma, WtTree const & tree, uint64_t const * bv_words, uint64_t bv_bits, cudaStream_t s);

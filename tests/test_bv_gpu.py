@@ -192,12 +192,14 @@ def test_two_bit_patterns_large_properties(pkg):
         assert total == nbits - 1
 
 
-@pytest.mark.parametrize("chunk_bytes", ["64", "4096", "1048576"])
-def test_binned_order_matches_direct_and_oracle(pkg, oracle, monkeypatch, chunk_bytes):
+@pytest.mark.parametrize("chunk_bytes,sectors", [("64", "1"), ("4096", "1"), ("1048576", "1"), ("4096", "0")])
+def test_binned_order_matches_direct_and_oracle(pkg, oracle, monkeypatch, chunk_bytes, sectors):
     """ORDER_BINNED (binned.cu: tile counting sort -> bin-major gathers -> un-sort) forced onto the catalogue with
     tiny bins (many bins, empty bins, bins of one block): same answers as the oracle for both patterns, for batches
-    shorter than a tile, of exactly one tile, ragged, and with out-of-domain queries mixed in"""
+    shorter than a tile, of exactly one tile, ragged, and with out-of-domain queries mixed in.  sectors = 1: select runs
+    through the select sectors wherever the density allows them (bv_device.cuh), 0: through the samples everywhere"""
     monkeypatch.setenv("SDSLGPU_BIN_CHUNK_BYTES", chunk_bytes)
+    monkeypatch.setenv("SDSLGPU_SELECT_SECTORS", sectors)
     for cid, w, nbits in cases.bitvector_catalogue(large=True):
         o = oracle.bv(w, nbits)
         with pkg.BitVector(w, nbits) as bv:
@@ -264,3 +266,41 @@ def test_binned_order_large_device_batches(pkg):
             p = res[pkg.ORDER_BINNED][3]
             bv.set_batch_order(pkg.ORDER_DIRECT)
             assert bool((bv.rank(p, b) == sel - 1).all())
+
+
+def test_select_sectors_are_built_once_and_only_where_they_apply(pkg, oracle):
+    """Select sectors (include/sdslgpu.h, memory note of sdslgpu_select): built by the first select batch that runs
+    through the pipeline, per bit value, counted by device_bytes; not for SDSLGPU_F_COMPACT handles, not for sparse
+    vectors, not by direct-order batches; answers are the same with and without them, in both batch orders."""
+    rng = np.random.default_rng(41)
+    nbits = 3_000_017
+    dense = cases.pack_bits((rng.random(nbits) < 0.5).astype(np.uint8))
+    sparse = cases.pack_bits((rng.random(nbits) < 0.02).astype(np.uint8))
+    o = oracle.bv(dense, nbits)
+    with pkg.BitVector(dense, nbits) as bv, pkg.BitVector(dense, nbits, flags=pkg.F_COMPACT) as compact, pkg.BitVector(sparse, nbits) as sp:
+        b0 = bv.device_bytes
+        q1 = cases.select_queries(bv.arg_count(1), 3, 40000)
+        q0 = cases.select_queries(bv.arg_count(0), 4, 40000)
+        want1, want0 = o.select(q1, 1), o.select(q0, 0)
+        bv.set_batch_order(pkg.ORDER_DIRECT)
+        assert (bv.select(q1, 1) == want1).all() and bv.device_bytes == b0  # a direct batch builds nothing
+        bv.set_batch_order(pkg.ORDER_BINNED)
+        assert (bv.select(q1, 1) == want1).all()
+        b1 = bv.device_bytes
+        assert b1 > b0 + bv.arg_count(1) // 81 * 32 * 9 // 10  # ~32 bytes per 81 ones
+        assert (bv.select(q1, 1) == want1).all() and bv.device_bytes == b1  # built once
+        assert (bv.select(q0, 0) == want0).all() and bv.device_bytes > b1  # the zeros get their own
+        bv.set_batch_order(pkg.ORDER_DIRECT)  # the direct kernel uses them too once they exist
+        assert (bv.select(q1, 1) == want1).all() and (bv.select(q0, 0) == want0).all()
+        every = np.arange(1, bv.arg_count(1) + 1, dtype=np.uint64)  # every one of the vector, sector boundaries included
+        assert (bv.select(every, 1) == o.select(every, 1)).all()
+        for other in (compact, sp):
+            other.set_batch_order(pkg.ORDER_BINNED)
+            before = other.device_bytes
+            q = cases.select_queries(other.arg_count(1), 5, 20000)
+            got = other.select(q, 1)
+            assert other.device_bytes == before
+            if other is compact:
+                assert (got == o.select(q, 1)).all()
+            else:
+                assert (got == oracle.bv(sparse, nbits).select(q, 1)).all()
