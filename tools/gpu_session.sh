@@ -4,7 +4,7 @@
 # Every stage writes into gpurun_out/<tag>_*; copy what should be judged into profiles/ afterwards.
 #   tests      pytest -m gpu (whole suite)                         [TAG, PYTEST_ARGS]
 #   bench      python bench.py (N = 1)                             [TAG, BENCH_ARGS]
-#   sweep      tools/sweep_order.py, both select sample formats    [TAG]
+#   sweep      tools/sweep_order.py, select with and without sectors [TAG]
 #   launches   ncu launch list of a short bench.py run             [TAG]
 #   ncu        ncu --set full of the binned pipelines' kernels     [TAG]
 #   all1       tests + bench + sweep + launches + ncu
@@ -26,7 +26,7 @@ run_bench() {
 run_sweep() {
     rm -f $OUT/${TAG}_sweep_order.jsonl
     timeout 600 python tools/sweep_order.py --tag pos --out $OUT/${TAG}_sweep_order.jsonl > $OUT/${TAG}_sweep.log 2>&1
-    SDSLGPU_SELECT_POS_SAMPLES=0 timeout 600 python tools/sweep_order.py --tag block --ops select1 --out $OUT/${TAG}_sweep_order.jsonl >> $OUT/${TAG}_sweep.log 2>&1
+    SDSLGPU_SELECT_SECTORS=0 timeout 600 python tools/sweep_order.py --tag sampled_select --ops select1 --out $OUT/${TAG}_sweep_order.jsonl >> $OUT/${TAG}_sweep.log 2>&1
     tail -30 $OUT/${TAG}_sweep.log
 }
 run_launches() {

@@ -4,7 +4,7 @@ bit vector in both batch orders (sdslgpu_set_batch_order), CUDA-event times, res
 orders.  One JSON line per (op, n, order).  The AUTO threshold of csrc/binned.cu (bin_wanted) is set from this table.
 
     python tools/sweep_order.py --nbits-log2 33 --log2n 21,22,23,24,25,26 --out gpurun_out/sweep.jsonl
-    SDSLGPU_SELECT_POS_SAMPLES=0 python tools/sweep_order.py ...     (A/B of the select sample format)
+    SDSLGPU_SELECT_SECTORS=0 python tools/sweep_order.py ...         (select through the samples only)
 """
 import argparse
 import json
@@ -66,7 +66,8 @@ for op in args.ops.split(","):
     b = 0 if op.endswith("0") else 1
     for n in ns:
         q = q_all[:n]
-        row = {"op": op, "n": n, "nbits_log2": args.nbits_log2, "tag": args.tag, "pos_samples": os.environ.get("SDSLGPU_SELECT_POS_SAMPLES", "default")}
+        row = {"op": op, "n": n, "nbits_log2": args.nbits_log2, "tag": args.tag, "pos_samples": os.environ.get("SDSLGPU_SELECT_POS_SAMPLES", "default"),
+               "select_sectors": os.environ.get("SDSLGPU_SELECT_SECTORS", "default")}
         for order, name in ((pkg.ORDER_DIRECT, "direct"), (pkg.ORDER_BINNED, "binned")):
             bv.set_batch_order(order)
             o = ref if name == "direct" else out

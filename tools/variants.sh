@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 V=sdsl-lite_b200/build/variants
 declare -A FLAGS=(
   [product]=""
-  [sort_reread_keys]="-DBIN_SORT_KEEP_RECS=0"
+  [sect_lookahead1]="-DBIN_SECT_LOOKAHEAD=1"
 )
 case ${1:-build} in
 build)
