@@ -163,8 +163,9 @@ int sdslgpu_select_iv(const sdslgpu_handle *h, int b, const uint64_t *i_words, u
  *                         by chunk (L2-resident gathers) and un-sorted again; needs ~14 bytes of stream-ordered
  *                         scratch per query (cudaMallocAsync on the call's stream)
  *   SDSLGPU_ORDER_AUTO    (default) BINNED when the index is larger than the L2 (>= 192 MB) and the batch is dense
- *                         enough for queries to share cache lines (>= 2^21 queries and >= 1 query per 64 bytes of
- *                         index for rank, per 192 bytes for select — the measured break-even points), else DIRECT
+ *                         enough for queries to share cache lines (>= 2^21 queries and >= 1 query per 128 bytes of
+ *                         index for rank and for select through select sectors, per 192 bytes for the sampled
+ *                         select — the measured break-even points), else DIRECT
  * The reference has no counterpart (its queries are scalar calls, rank_support_v.hpp:129-139). */
 #define SDSLGPU_ORDER_AUTO 0
 #define SDSLGPU_ORDER_DIRECT 1

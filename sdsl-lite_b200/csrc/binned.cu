@@ -307,9 +307,9 @@ bool bin_wanted(int order, uint64_t index_bytes, uint64_t n, uint32_t index_byte
         return false;
     // auto: only when the index cannot live in L2 and the batch is dense enough that the queries of a bin share cache
     // lines; a sparser batch misses in DRAM anyway and the two extra passes are pure cost.  The break-even density is
-    // measured (tools/sweep_order.py, profiles/r02a_sweep_order.jsonl, 1.23 GB index): a one-gather op (rank) pays from
-    // 1 query per 64 bytes of index (1.9e7 queries: 0.96x at 1.7e7, 1.11x at 2.5e7), a multi-gather op (select: sample
-    // + blocks) from 1 per 192 bytes (6.4e6: 0.92x at 4.2e6, 1.11x at 8.4e6).
+    // measured (tools/sweep_order.py, profiles/r02z_sweep_order.jsonl, 1.23 GB index): a one-gather op (rank, select
+    // through select sectors) pays from 1 query per 128 bytes of index (9.6e6 queries: 0.98x at 8.4e6, 1.08 - 1.15x at
+    // 1.25e7), the sampled select (sample + blocks) from 1 per 192 bytes (6.4e6: 0.85x at 4.2e6, 1.06x at 8.4e6).
     return index_bytes >= (192ull << 20) && n >= (1ull << 21) && n >= index_bytes / index_bytes_per_query;
 }
 
@@ -472,9 +472,10 @@ struct BvSelectSectOp
     }
 };
 
-bool bv_binned_wanted(BvImage const & v, uint64_t n, bool select)
+bool bv_binned_wanted(BvImage const & v, uint64_t n, bool select, int b)
 {
-    return bin_wanted(v.order, v.nblocks * sizeof(bvblock), n, select ? kBinSelectDensity : kBinRankDensity);
+    bool const one_gather = !select || ((b == 0 || b == 1) && v.sect[b] != nullptr);
+    return bin_wanted(v.order, v.nblocks * sizeof(bvblock), n, one_gather ? kBinRankDensity : kBinSelectDensity);
 }
 
 int bv_rank_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done, Fan const * fan)

@@ -598,7 +598,7 @@ int bv_select_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n,
         set_error("select requested on a handle created with SDSLGPU_F_NO_SELECT");
         return SDSLGPU_ENOTSUP;
     }
-    if (bv_binned_wanted(v, n, true))
+    if (bv_binned_wanted(v, n, true, b))
     {
         bool done = false;
         SG_TRY(bv_select_binned_device(v, b, idx, n, out, s, &done, fan));
@@ -685,7 +685,8 @@ int bv_ensure_select_sectors_image(sdslgpu_handle const * ch, BvImage const & cv
 // KIND_BV handles: a no-op unless a select batch of n queries would run through the pipeline
 int bv_ensure_select_sectors(sdslgpu_handle const * h, int b, uint64_t n)
 {
-    if ((b != 0 && b != 1) || h->bv.sect_tried[b] || !bv_binned_wanted(h->bv, n, true))
+    // (the batch sizes from which a one-gather select pays in the pipeline: what the sectors will make of this select)
+    if ((b != 0 && b != 1) || h->bv.sect_tried[b] || !bin_wanted(h->bv.order, h->bv.nblocks * sizeof(bvblock), n, kBinRankDensity))
         return SDSLGPU_OK;
     return bv_ensure_select_sectors_image(h, h->bv, b, 16 * n); // 14 bytes of pipeline scratch per query (binned.cuh)
 }

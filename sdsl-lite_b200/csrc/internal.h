@@ -360,8 +360,10 @@ int bv_select_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n,
                      bool * fanned = nullptr);
 int bv_access_device(BvImage const & v, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s);
 // binned.cu: locality-ordered execution of large batches; *done = false means "not applicable, use the direct kernel"
-static constexpr uint32_t kBinRankDensity = 64, kBinSelectDensity = 192; // bytes of index per query at the break-even (binned.cu bin_wanted)
-bool bv_binned_wanted(BvImage const & v, uint64_t n, bool select = false);
+// bytes of index per query at the break-even between the two batch orders (binned.cu bin_wanted): one-gather ops (rank,
+// select through select sectors) / ops with two or more dependent gathers (sampled select, sd and rrr selects)
+static constexpr uint32_t kBinRankDensity = 128, kBinSelectDensity = 192;
+bool bv_binned_wanted(BvImage const & v, uint64_t n, bool select = false, int b = 1);
 bool bin_wanted(int order, uint64_t index_bytes, uint64_t n, uint32_t index_bytes_per_query = kBinRankDensity);
 int bv_rank_binned_device(BvImage const & v, int b, uint64_t const * idx, uint64_t n, uint64_t * out, cudaStream_t s, bool * done, Fan const * fan = nullptr);
 int bv_ensure_select_sectors(sdslgpu_handle const * h, int b, uint64_t n); // bv.cu; a no-op unless a binned select of n queries would use them
