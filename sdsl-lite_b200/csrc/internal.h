@@ -319,6 +319,7 @@ inline RrrView rrr_view(RrrImage const & r)
     v.hint[1] = r.hint[1];
     v.hint_shift[0] = r.hint_shift[0];
     v.hint_shift[1] = r.hint_shift[1];
+    v.try_sparse = (r.ones * 32 <= r.size || (r.size - r.ones) * 32 <= r.size) ? 1u : 0u;
     return v;
 }
 inline PlainBits plain_bits(WtHuffImage const & w)

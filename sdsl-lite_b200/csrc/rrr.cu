@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kThreads) rrr_access_kernel(RrrView const v, u
                 uint64_t p = r.w[1] & ~kInvBit, ones = 0;
                 rec_prefix(r, t, nblk, inv, ones, p);
                 uint32_t bit;
-                rrr_prefix_ones(t, k, read_int(v.btnr, p, t->space[k]), off, true, bit);
+                rrr_prefix_ones(t, k, read_int(v.btnr, p, t->space[k]), off, true, bit, v.try_sparse != 0);
                 res = bit;
             }
         }

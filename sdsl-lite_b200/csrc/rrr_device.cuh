@@ -28,6 +28,9 @@ __host__ __device__ __forceinline__ uint32_t rrr_hint_shift(uint64_t args, uint6
 // C(n, k) for n <= 62, 0 for k > n (rrr_helper.hpp:193-237), split by magnitude: every C(n, k) with n <= 33 is below
 // 2^32, so the last 34 steps of a block's enumerative decode run in 32-bit registers on a table of half the size.
 // 23.6 KB of shared memory per CTA (the full 64 x 64 x u64 table was 32 KB).
+#ifndef RRR_SPARSE_PATH
+#define RRR_SPARSE_PATH 1 // 0: every block is decoded position by position (A/B partner, tools/variants.sh)
+#endif
 static constexpr uint32_t kBinomSplit = 34;
 struct RrrTables
 {
@@ -102,8 +105,110 @@ __device__ __forceinline__ bool rrr_step32(uint32_t & r, uint32_t & k, uint32_t 
 }
 #endif
 
+// ------------------------------------------------------------------------------------------------
+// Blocks with few ones (or few zeros): the ones are found one at a time instead of position by position.  With k ones
+// left and every position p < p0 decided, the next one sits at the first p >= p0 with nr >= C(62 - p, k): C(n, k) grows
+// with n, so that is n* = the largest n <= 62 - p0 with C(n, k) <= nr — a bisection over a column of the table (six
+// probes at most) per ONE, where the walk pays one step per POSITION (31 on average, and a warp waits for its longest).
+// At 1 - 5 % density (0.6 - 3 ones per block) that is the difference between ~100 and ~450 instructions per warp trip.
+// A block with few zeros is its complement's mirror image: the complement of a block of class k and offset nr has
+// class 63 - k and offset C(63, k) - 1 - nr (the enumeration is lexicographic, complementing reverses it).
+// The search costs ~50 instructions per one, so it only wins for a handful of ones — and a warp that holds one lane on
+// the walk pays for the walk anyway: the search is taken only when EVERY lane of the warp that arrives here together has
+// such a block (measured, profiles/r02z_rrr_sparse_variants.jsonl: a per-lane switch at k <= 10 made 5 - 25 % density up
+// to 60 % slower; with the warp-wide switch 1 % density gains 19 % in rank, 10 - 14 % in select, the rest is unchanged).
+// Either path is correct for any class, so the answer never depends on the choice.  Vectors between 1/32 and 31/32 dense do
+// not even ask (RrrView::try_sparse): the vote alone cost them 1 - 2 %.
+// ------------------------------------------------------------------------------------------------
+static constexpr uint32_t kSparseK = 5;
+#ifdef SDSLGPU_HOST_EMU
+inline bool rrr_warp_all(bool x)
+{
+    return x;
+}
+#else
+__device__ __forceinline__ bool rrr_warp_all(bool x)
+{
+    return __all_sync(__activemask(), x) != 0;
+}
+#endif
+
+// largest n in [lo, hi] with C(n, k) <= nr; requires C(lo, k) <= nr
+__device__ __forceinline__ uint32_t rrr_largest_n(RrrTables const * t, uint32_t k, uint64_t nr, uint32_t lo, uint32_t hi)
+{
+    while (lo < hi)
+    {
+        uint32_t const mid = (lo + hi + 1) >> 1;
+        if (rrr_binom(t, mid, k) <= nr)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    return lo;
+}
+
+// class and offset of the complemented block
+__device__ __forceinline__ void rrr_complement(RrrTables const * t, uint32_t & k, uint64_t & nr)
+{
+    uint64_t const c63 = rrr_binom(t, 62, k) + rrr_binom(t, 62, k - 1); // C(63, k), 1 <= k <= 62
+    nr = c63 - 1 - nr;
+    k = kBs - k;
+}
+
+// ones among positions [0, off) of a block with 1 <= k <= kSparseK ones (and the bit at `off`, off <= 62)
+__device__ __forceinline__ uint32_t rrr_prefix_ones_sparse(RrrTables const * t, uint32_t k, uint64_t nr, uint32_t off, bool want_bit, uint32_t & bit)
+{
+    uint32_t cnt = 0, n_hi = 62;
+    uint32_t const lim = 63 - off; // a one at position p < off has n = 62 - p >= lim
+    while (k)
+    {
+        if (lim > n_hi || rrr_binom(t, lim, k) > nr)
+            break; // the next one lies at or behind `off`
+        uint32_t const n = rrr_largest_n(t, k, nr, lim, n_hi);
+        nr -= rrr_binom(t, n, k);
+        --k;
+        ++cnt;
+        if (n == 0)
+            break;
+        n_hi = n - 1;
+    }
+    bit = 0;
+    if (want_bit && k) // the next one sits exactly at `off` iff C(62 - off, k) <= nr (62 - off <= n_hi holds here)
+        bit = rrr_binom(t, 62 - off, k) <= nr;
+    return cnt;
+}
+
+// position of the target-th (1-based) B-bit of a block with 1 <= k <= kSparseK ONES; requires that it exists
+template <int B>
+__device__ __forceinline__ uint32_t rrr_select_sparse(RrrTables const * t, uint32_t k, uint64_t nr, uint32_t target)
+{
+    uint32_t j = 0, n_hi = 62; // j = ones found so far
+    while (k)
+    {
+        uint32_t const n = rrr_largest_n(t, k, nr, k - 1, n_hi); // C(k - 1, k) = 0 <= nr
+        uint32_t const p = 62 - n;
+        if (B)
+        {
+            if (++j == target)
+                return p;
+        }
+        else
+        {
+            if (p - j >= target) // zeros before this one
+                return target - 1 + j;
+            ++j;
+        }
+        nr -= rrr_binom(t, n, k);
+        --k;
+        if (n == 0)
+            break;
+        n_hi = n - 1;
+    }
+    return target - 1 + j; // B = 0: behind the last one
+}
+
 // ones among positions [0, off) and, if want_bit, the bit at position off (off < 63 then)
-__device__ __forceinline__ uint32_t rrr_prefix_ones(RrrTables const * t, uint32_t k, uint64_t nr, uint32_t off, bool want_bit, uint32_t & bit)
+__device__ __forceinline__ uint32_t rrr_prefix_ones(RrrTables const * t, uint32_t k, uint64_t nr, uint32_t off, bool want_bit, uint32_t & bit, bool try_sparse = true)
 {
     if (k == 1)
     { // one one: it sits at position 62 - nr (nr = C(62 - p, 1)); a third of all blocks at 1 % density
@@ -111,6 +216,18 @@ __device__ __forceinline__ uint32_t rrr_prefix_ones(RrrTables const * t, uint32_
         bit = want_bit && one_at == off;
         return one_at < off;
     }
+#if RRR_SPARSE_PATH
+    if (try_sparse && rrr_warp_all(k <= kSparseK || k >= kBs - kSparseK))
+    {
+        if (k <= kSparseK)
+            return rrr_prefix_ones_sparse(t, k, nr, off, want_bit, bit);
+        // few zeros: count them in the complement
+        rrr_complement(t, k, nr);
+        uint32_t const zeros = rrr_prefix_ones_sparse(t, k, nr, off, want_bit, bit);
+        bit = want_bit ? 1u - bit : 0u;
+        return off - zeros;
+    }
+#endif
     uint32_t const k0 = k;
     uint32_t const wide = off < kWide ? off : kWide; // steps [0, wide) on 64-bit binomials, [wide, off) on 32-bit ones
     {
@@ -135,13 +252,23 @@ __device__ __forceinline__ uint32_t rrr_prefix_ones(RrrTables const * t, uint32_
 
 // position (0..62) of the target-th (1-based) B-bit of the block; requires target <= number of B-bits
 template <int B>
-__device__ __forceinline__ uint32_t rrr_select_in_block(RrrTables const * t, uint32_t k, uint64_t nr, uint32_t target)
+__device__ __forceinline__ uint32_t rrr_select_in_block(RrrTables const * t, uint32_t k, uint64_t nr, uint32_t target, bool try_sparse = true)
 {
     if (k == 1)
     {
         uint32_t const one_at = 62u - (uint32_t)nr;
         return B ? one_at : (target - 1 < one_at ? target - 1 : target);
     }
+#if RRR_SPARSE_PATH
+    if (try_sparse && rrr_warp_all(k <= kSparseK || k >= kBs - kSparseK))
+    {
+        if (k <= kSparseK)
+            return rrr_select_sparse<B>(t, k, nr, target);
+        // few zeros: the B-bits of the block are the (1 - B)-bits of its complement
+        rrr_complement(t, k, nr);
+        return rrr_select_sparse<1 - B>(t, k, nr, target);
+    }
+#endif
     {
         uint64_t const * row = &t->hi[kWide - 1][0];
         SG_UNROLL4
@@ -177,6 +304,7 @@ struct RrrView
     RrrTables const * tables;
     uint32_t const * hint[2]; // hint[b][j] = superblock holding the (j * 2^hint_shift[b] + 1)-th b-bit (+ sentinels)
     uint32_t hint_shift[2];
+    uint32_t try_sparse; // the vector is sparse or dense enough (<= 1/32 ones or zeros) for whole warps to meet few-one blocks
 };
 
 struct RrrRecord
@@ -277,7 +405,7 @@ __device__ __forceinline__ uint64_t rrr_rank1_one(RrrView const & v, RrrTables c
     if (k == kBs)
         return ones + off;
     uint32_t sp = t->space[k], bit;
-    return ones + rrr_prefix_ones(t, k, sp ? read_int(v.btnr, p, sp) : 0, off, false, bit);
+    return ones + rrr_prefix_ones(t, k, sp ? read_int(v.btnr, p, sp) : 0, off, false, bit, v.try_sparse != 0);
 }
 
 // rank1(pos) and the bit at pos (pos < size) from one record + one offset read
@@ -297,7 +425,7 @@ __device__ __forceinline__ uint64_t rrr_rank1_and_bit(RrrView const & v, RrrTabl
         return ones + (k ? off : 0u);
     }
     uint32_t sp = t->space[k];
-    return ones + rrr_prefix_ones(t, k, sp ? read_int(v.btnr, p, sp) : 0, off, true, bit);
+    return ones + rrr_prefix_ones(t, k, sp ? read_int(v.btnr, p, sp) : 0, off, true, bit, v.try_sparse != 0);
 }
 
 // position of the i-th (1-based) B-bit, 1 <= i <= #B-bits (rrr_vector.hpp:639-726)
@@ -360,7 +488,7 @@ __device__ __forceinline__ uint64_t rrr_select_one(RrrView const & v, RrrTables 
     if (k == 0 || k == kBs)
         pos = target - 1; // a uniform block: its target-th bit (of the only value it has)
     else
-        pos = rrr_select_in_block<B>(t, k, sp ? read_int(v.btnr, p, sp) : 0, target);
+        pos = rrr_select_in_block<B>(t, k, sp ? read_int(v.btnr, p, sp) : 0, target, v.try_sparse != 0);
     return (begin * kK + j) * kBs + pos;
 }
 

@@ -97,6 +97,7 @@ extern "C"
         e->v.nblocks = nblocks;
         e->v.nsuper = nsuper;
         e->v.ones = ones;
+        e->v.try_sparse = 1; // the one-at-a-time search wherever a block qualifies, whatever the density of the vector
         e->v.btnr = e->btnr.data();
         e->v.records = e->rec.data();
         e->v.tables = &host_tables();

@@ -166,7 +166,9 @@ def rrr_emu():
 def _rrr_shapes():
     for cid, w, nbits in _shapes():
         yield cid, w, nbits
-    for d in (0.01, 0.1, 0.5, 0.9, 0.99):  # the density sweep of BASELINE config 3 in miniature; > 0.5 exercises inverted superblocks
+    # the density sweep of BASELINE config 3 in miniature; > 0.5 exercises inverted superblocks; 0.16 / 0.84 put the classes
+    # on both sides of the switch between the one-at-a-time search (few ones / few zeros) and the position walk
+    for d in (0.01, 0.05, 0.1, 0.16, 0.5, 0.84, 0.9, 0.95, 0.99):
         n = 300_000 + int(d * 1000)
         yield f"bernoulli.{d}", cases.bernoulli_words(n, d, 600 + int(d * 100)), n
 

@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 V=sdsl-lite_b200/build/variants
 declare -A FLAGS=(
   [product]=""
-  [sect_lookahead1]="-DBIN_SECT_LOOKAHEAD=1"
+  [rrr_walk_only]="-DRRR_SPARSE_PATH=0"
 )
 case ${1:-build} in
 build)
@@ -16,6 +16,6 @@ build)
   done ;;
 run)
   for lib in $V/lib_*.so; do
-    SDSLGPU_LIB=$PWD/$lib timeout 300 python tools/variant_probe.py $(basename $lib) || echo "{\"variant\": \"$lib\", \"error\": true}"
+    SDSLGPU_LIB=$PWD/$lib timeout 300 python ${PROBE:-tools/variant_probe.py} $(basename $lib) || echo "{\"variant\": \"$lib\", \"error\": true}"
   done ;;
 esac
