@@ -5,12 +5,18 @@
 // (SURVEY.md §7.3-5).  Here: prefix doubling.  Round 0 sorts the suffixes by their first 8 bytes (one 64-bit radix
 // sort); every later round sorts by (rank of the h-prefix, rank of the h-prefix h positions later) and doubles h,
 // until all ranks are distinct.  Random text finishes after round 0; natural-language text in a handful of rounds;
-// the worst case (a^n) needs log2(n) rounds.  The sort itself is cub::DeviceRadixSort (CCCL, shipped with the CUDA
-// toolkit) — a library primitive used ONLY here, in the builder; no query kernel depends on it.  Any correct
-// suffix sorter yields the same array, and the resulting index is checked byte for byte against the reference's.
+// the worst case (a^n) needs log2(n) rounds.  The sort itself is the engine's own stable LSD radix sort (radix.cuh; round 1
+// and most of round 2 called cub::DeviceRadixSort here — build with -DSDSLGPU_CUB_SORT=1 for that A/B partner).  Any
+// correct suffix sorter yields the same array, and the resulting index is checked byte for byte against the reference's.
+#ifndef SDSLGPU_CUB_SORT
+#define SDSLGPU_CUB_SORT 0
+#endif
+#if SDSLGPU_CUB_SORT
 #include <cub/device/device_radix_sort.cuh>
+#endif
 
 #include "internal.h"
+#include "radix.cuh"
 #include "scan.cuh"
 
 namespace sdslgpu
@@ -118,10 +124,12 @@ int gpu_suffix_array_bwt(uint8_t const * text_host,
         return SDSLGPU_ENOTSUP;
     Buf t, k0, k1, v0, v1, rk, fl, hb, tmp, cubtmp, dbwt, dsamp;
     uint64_t nsamp = (n + dens - 1) / dens, nisa = (n - 1) / isa_dens + 1;
-    size_t cub_bytes = 0;
+    size_t cub_bytes = radix_temp_bytes(n);
+#if SDSLGPU_CUB_SORT
     cub::DoubleBuffer<uint64_t> dk(nullptr, nullptr);
     cub::DoubleBuffer<uint32_t> dv(nullptr, nullptr);
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, dk, dv, n, 0, 64, s);
+#endif
     if (t.alloc(n + 16) != cudaSuccess || k0.alloc(n * 8) != cudaSuccess || k1.alloc(n * 8) != cudaSuccess || v0.alloc(n * 4) != cudaSuccess ||
         v1.alloc(n * 4) != cudaSuccess || rk.alloc(n * 4) != cudaSuccess || fl.alloc(n * 4) != cudaSuccess || hb.alloc((n + 1) * 8) != cudaSuccess ||
         tmp.alloc(scan_tmp_words(n) * 8) != cudaSuccess || cubtmp.alloc(cub_bytes) != cudaSuccess || dsamp.alloc(nisa * 8) != cudaSuccess)
@@ -132,9 +140,10 @@ int gpu_suffix_array_bwt(uint8_t const * text_host,
     SG_CUDA(cudaMemsetAsync(t.p, 0, n + 16, s));
     if (len)
         SG_CUDA(cudaMemcpyAsync(t.p, text_host, len, cudaMemcpyHostToDevice, s));
-    dk = cub::DoubleBuffer<uint64_t>(k0.as<uint64_t>(), k1.as<uint64_t>());
-    dv = cub::DoubleBuffer<uint32_t>(v0.as<uint32_t>(), v1.as<uint32_t>());
-    sa_init_keys_kernel<<<blocks_for(n), kThreads, 0, s>>>(t.as<uint8_t>(), n, dk.Current(), dv.Current());
+    // two key and two value buffers; k_cur / v_cur hold the current order, the others are the sort's scratch
+    uint64_t *k_cur = k0.as<uint64_t>(), *k_alt = k1.as<uint64_t>();
+    uint32_t *v_cur = v0.as<uint32_t>(), *v_alt = v1.as<uint32_t>();
+    sa_init_keys_kernel<<<blocks_for(n), kThreads, 0, s>>>(t.as<uint8_t>(), n, k_cur, v_cur);
     SG_CUDA(cudaGetLastError());
     uint32_t rounds = 0;
     int rank_bits = 1;
@@ -144,9 +153,21 @@ int gpu_suffix_array_bwt(uint8_t const * text_host,
     {
         // round 0 sorts by the 8-byte prefix; later rounds only need the bits the two ranks occupy
         int hi_bit = rounds == 0 ? 64 : 32 + rank_bits;
-        SG_CUDA(cub::DeviceRadixSort::SortPairs(cubtmp.p, cub_bytes, dk, dv, n, 0, hi_bit, s));
+#if SDSLGPU_CUB_SORT
+        {
+            cub::DoubleBuffer<uint64_t> dk(k_cur, k_alt);
+            cub::DoubleBuffer<uint32_t> dv(v_cur, v_alt);
+            SG_CUDA(cub::DeviceRadixSort::SortPairs(cubtmp.p, cub_bytes, dk, dv, n, 0, hi_bit, s));
+            k_cur = dk.Current();
+            k_alt = dk.Alternate();
+            v_cur = dv.Current();
+            v_alt = dv.Alternate();
+        }
+#else
+        SG_CUDA(radix_sort<true>(k_cur, k_alt, v_cur, v_alt, n, 0, hi_bit, cubtmp.p, s));
+#endif
         ++rounds;
-        sa_flag_heads_kernel<<<blocks_for(n), kThreads, 0, s>>>(dk.Current(), n, fl.as<uint32_t>());
+        sa_flag_heads_kernel<<<blocks_for(n), kThreads, 0, s>>>(k_cur, n, fl.as<uint32_t>());
         SG_CUDA(cudaGetLastError());
         SG_CUDA(exclusive_scan(fl.as<uint32_t>(), n, hb.as<uint64_t>(), tmp.as<uint64_t>(), s));
         uint64_t groups = 0;
@@ -154,17 +175,17 @@ int gpu_suffix_array_bwt(uint8_t const * text_host,
         SG_CUDA(cudaStreamSynchronize(s));
         if (groups == n || h >= n)
             break;
-        sa_scatter_rank_kernel<<<blocks_for(n), kThreads, 0, s>>>(hb.as<uint64_t>(), fl.as<uint32_t>(), dv.Current(), n, rk.as<uint32_t>());
+        sa_scatter_rank_kernel<<<blocks_for(n), kThreads, 0, s>>>(hb.as<uint64_t>(), fl.as<uint32_t>(), v_cur, n, rk.as<uint32_t>());
         SG_CUDA(cudaGetLastError());
-        sa_next_keys_kernel<<<blocks_for(n), kThreads, 0, s>>>(rk.as<uint32_t>(), dv.Current(), n, h, dk.Current());
+        sa_next_keys_kernel<<<blocks_for(n), kThreads, 0, s>>>(rk.as<uint32_t>(), v_cur, n, h, k_cur);
         SG_CUDA(cudaGetLastError());
     }
     if (rounds_out)
         *rounds_out = rounds;
     // BWT + samples; the key buffers are free again: reuse one for the BWT bytes and the scan output for the samples
-    uint8_t * d_bwt = reinterpret_cast<uint8_t *>(dk.Alternate());
+    uint8_t * d_bwt = reinterpret_cast<uint8_t *>(k_alt);
     uint64_t * d_samp = hb.as<uint64_t>();
-    sa_bwt_kernel<<<blocks_for(n), kThreads, 0, s>>>(t.as<uint8_t>(), dv.Current(), n, dens, isa_dens, d_bwt, d_samp, dsamp.as<uint64_t>());
+    sa_bwt_kernel<<<blocks_for(n), kThreads, 0, s>>>(t.as<uint8_t>(), v_cur, n, dens, isa_dens, d_bwt, d_samp, dsamp.as<uint64_t>());
     SG_CUDA(cudaGetLastError());
     bwt.resize(n);
     samples.resize(nsamp);

@@ -14,13 +14,19 @@
 // zeros to child 0, ones to child 1, elements whose code ends drop out — and where a child's elements start is known
 // from the tree (bv_pos).  So an element's destination is "start of its child + number of elements of its node with the
 // same bit before it", and that number is a rank query on the bits just written: one popcount pass + scan.cuh's prefix
-// sum + one scatter pass per depth (wt_split_kernel), all hand-written.  wt_int keeps cub::DeviceRadixSort (its nodes
-// are not known in advance) — builder only, no query kernel uses it.
+// sum + one scatter pass per depth (wt_split_kernel), all hand-written.  wt_int (its nodes are not known in advance)
+// sorts with the engine's own radix sort (radix.cuh; -DSDSLGPU_CUB_SORT=1 puts cub::DeviceRadixSort back for an A/B).
 // The result is checked bit for bit against the host builders and the reference (tests/test_wt_gpu.py,
 // tests/test_egress_gpu.py compare complete serialised trees).
+#ifndef SDSLGPU_CUB_SORT
+#define SDSLGPU_CUB_SORT 0
+#endif
+#if SDSLGPU_CUB_SORT
 #include <cub/device/device_radix_sort.cuh>
+#endif
 
 #include "internal.h"
+#include "radix.cuh"
 #include "scan.cuh"
 #include "wt_device.cuh"
 
@@ -365,8 +371,10 @@ int wt_int_planes_device(uint64_t * d_seq, uint64_t n, uint32_t * max_level_out,
         ++hi;
     uint32_t const levels = hi + 1; // wt_int.hpp:182 (an all-zero sequence still gets one level)
     uint64_t const bits = n * levels, nwords = ((bits + 63) >> 6) + 2;
-    size_t cub_bytes = 0;
+    size_t cub_bytes = radix_temp_bytes(n);
+#if SDSLGPU_CUB_SORT
     cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (uint64_t const *)nullptr, (uint64_t *)nullptr, n, 0, 64, s);
+#endif
     uint64_t * d_words = nullptr;
     if (cubtmp.alloc(cub_bytes) != cudaSuccess || cudaMalloc(reinterpret_cast<void **>(&d_words), nwords * 8) != cudaSuccess)
     {
@@ -384,6 +392,7 @@ int wt_int_planes_device(uint64_t * d_seq, uint64_t n, uint32_t * max_level_out,
         wt_pack_int_kernel<<<pack_grid(n), kThreads, 0, s>>>(cur, shift, n, (uint64_t)k * n, reinterpret_cast<uint32_t *>(d_words));
         SG_CUDA(cudaGetLastError());
         // next level's order: stable by the top k+1 bits
+#if SDSLGPU_CUB_SORT
         size_t need = 0;
         cub::DeviceRadixSort::SortKeys(nullptr, need, cur, nxt, n, (int)shift, (int)levels, s);
         if (need > cub_bytes)
@@ -395,6 +404,10 @@ int wt_int_planes_device(uint64_t * d_seq, uint64_t n, uint32_t * max_level_out,
         uint64_t * t = cur;
         cur = nxt;
         nxt = t;
+#else
+        uint32_t *no_vals = nullptr, *no_vals_alt = nullptr;
+        SG_CUDA(radix_sort<false>(cur, nxt, no_vals, no_vals_alt, n, (int)shift, (int)levels, cubtmp.p, s)); // `cur` = the result
+#endif
     }
     wt_distinct_kernel<<<grid_for(n, 8), kThreads, 0, s>>>(cur, n, scal.as<unsigned long long>() + 1);
     SG_CUDA(cudaGetLastError());
