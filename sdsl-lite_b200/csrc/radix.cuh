@@ -1,6 +1,8 @@
 // radix.cuh — stable least-significant-digit radix sort of u64 keys (optionally carrying u32 values), 8 bits per pass.
 // CONSTRUCTION only (the suffix sorter of gpu_sa.cu, the level orders of wt_int in wt_build.cu); hand-written so that
-// no library kernel runs anywhere in the engine (round 1 and most of round 2 used cub::DeviceRadixSort here).
+// no library kernel runs anywhere in the engine (round 1 and most of round 2 used cub::DeviceRadixSort here; measured
+// against it on the same builds, profiles/r02zz_bench_build.jsonl: csa_wt of a 2^28-byte text 0.60 - 0.98 -> 0.45 s,
+// wt_int of 2^26 20-bit values 0.084 - 0.17 -> 0.080 s).
 //
 // One pass over a digit = three launches:
 //   rs_hist_kernel      digit histogram of every tile of 4096 keys              hist[digit][tile]

@@ -15,16 +15,10 @@
 // from the tree (bv_pos).  So an element's destination is "start of its child + number of elements of its node with the
 // same bit before it", and that number is a rank query on the bits just written: one popcount pass + scan.cuh's prefix
 // sum + one scatter pass per depth (wt_split_kernel), all hand-written.  wt_int (its nodes are not known in advance)
-// sorts with the engine's own radix sort (radix.cuh; -DSDSLGPU_CUB_SORT=1 puts cub::DeviceRadixSort back for an A/B).
+// sorts with the engine's own radix sort (radix.cuh; a library sort until the end of round 2: 0.084 - 0.17 s for 2^26
+// values of 20 bits, now 0.080 s).
 // The result is checked bit for bit against the host builders and the reference (tests/test_wt_gpu.py,
 // tests/test_egress_gpu.py compare complete serialised trees).
-#ifndef SDSLGPU_CUB_SORT
-#define SDSLGPU_CUB_SORT 0
-#endif
-#if SDSLGPU_CUB_SORT
-#include <cub/device/device_radix_sort.cuh>
-#endif
-
 #include "internal.h"
 #include "radix.cuh"
 #include "scan.cuh"
@@ -354,7 +348,7 @@ int wt_huff_planes_device(uint8_t const * d_text, uint64_t n, WtTree const & tre
 int wt_int_planes_device(uint64_t * d_seq, uint64_t n, uint32_t * max_level_out, uint64_t * sigma_out, uint64_t ** d_words_out, cudaStream_t s)
 {
     *d_words_out = nullptr;
-    Buf scal, alt, cubtmp;
+    Buf scal, alt, sort_tmp;
     if (scal.alloc(16) != cudaSuccess || alt.alloc(n * 8) != cudaSuccess)
     {
         cudaGetLastError();
@@ -371,12 +365,9 @@ int wt_int_planes_device(uint64_t * d_seq, uint64_t n, uint32_t * max_level_out,
         ++hi;
     uint32_t const levels = hi + 1; // wt_int.hpp:182 (an all-zero sequence still gets one level)
     uint64_t const bits = n * levels, nwords = ((bits + 63) >> 6) + 2;
-    size_t cub_bytes = radix_temp_bytes(n);
-#if SDSLGPU_CUB_SORT
-    cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (uint64_t const *)nullptr, (uint64_t *)nullptr, n, 0, 64, s);
-#endif
+    uint64_t const sort_bytes = radix_temp_bytes(n);
     uint64_t * d_words = nullptr;
-    if (cubtmp.alloc(cub_bytes) != cudaSuccess || cudaMalloc(reinterpret_cast<void **>(&d_words), nwords * 8) != cudaSuccess)
+    if (sort_tmp.alloc(sort_bytes) != cudaSuccess || cudaMalloc(reinterpret_cast<void **>(&d_words), nwords * 8) != cudaSuccess)
     {
         cudaGetLastError();
         return SDSLGPU_ENOTSUP;
@@ -392,22 +383,8 @@ int wt_int_planes_device(uint64_t * d_seq, uint64_t n, uint32_t * max_level_out,
         wt_pack_int_kernel<<<pack_grid(n), kThreads, 0, s>>>(cur, shift, n, (uint64_t)k * n, reinterpret_cast<uint32_t *>(d_words));
         SG_CUDA(cudaGetLastError());
         // next level's order: stable by the top k+1 bits
-#if SDSLGPU_CUB_SORT
-        size_t need = 0;
-        cub::DeviceRadixSort::SortKeys(nullptr, need, cur, nxt, n, (int)shift, (int)levels, s);
-        if (need > cub_bytes)
-        {
-            set_error("wt_int device build: radix-sort scratch grew from %llu to %llu bytes", (unsigned long long)cub_bytes, (unsigned long long)need);
-            return SDSLGPU_ECUDA;
-        }
-        SG_CUDA(cub::DeviceRadixSort::SortKeys(cubtmp.p, need, cur, nxt, n, (int)shift, (int)levels, s));
-        uint64_t * t = cur;
-        cur = nxt;
-        nxt = t;
-#else
         uint32_t *no_vals = nullptr, *no_vals_alt = nullptr;
-        SG_CUDA(radix_sort<false>(cur, nxt, no_vals, no_vals_alt, n, (int)shift, (int)levels, cubtmp.p, s)); // `cur` = the result
-#endif
+        SG_CUDA(radix_sort<false>(cur, nxt, no_vals, no_vals_alt, n, (int)shift, (int)levels, sort_tmp.p, s)); // `cur` = the result
     }
     wt_distinct_kernel<<<grid_for(n, 8), kThreads, 0, s>>>(cur, n, scal.as<unsigned long long>() + 1);
     SG_CUDA(cudaGetLastError());
