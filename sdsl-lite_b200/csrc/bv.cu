@@ -653,7 +653,7 @@ int bv_ensure_select_sectors_image(sdslgpu_handle const * ch, BvImage const & cv
     uint32_t stride = bv_sect_stride(args, v.nbits);
     if (char const * e = std::getenv("SDSLGPU_SELECT_SECTOR_STRIDE")) // tuning knob
         stride = (uint32_t)std::atoi(e);
-    bool off = (h->flags & SDSLGPU_F_COMPACT) != 0 || v.nbits > (1ull << 36) || stride == 0 || args == 0;
+    bool off = (h->flags & SDSLGPU_F_COMPACT) != 0 || v.nbits > (1ull << 36) || stride < 2 || args == 0; // (the magic of 1 is 2^64)
     if (char const * e = std::getenv("SDSLGPU_SELECT_SECTORS")) // A/B knob
         off = off || std::atoi(e) == 0;
     if (off)

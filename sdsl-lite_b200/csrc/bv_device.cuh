@@ -56,7 +56,7 @@ inline uint32_t bv_sect_stride(uint64_t args, uint64_t nbits)
 }
 inline uint64_t bv_sect_magic(uint32_t stride)
 {
-    return ~0ull / stride + 1; // floor(2^64 / S) + 1 (also when S divides 2^64)
+    return ~0ull / stride + 1; // floor(2^64 / S) + 1 (also when S divides 2^64); S >= 2
 }
 
 // number of 1-bits in [0, pos), 0 <= pos <= nbits: one 32-byte sector gather

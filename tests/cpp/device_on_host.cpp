@@ -78,6 +78,15 @@ extern "C"
         }
         return marked;
     }
+    // key / stride the way bv_select_sector does it: multiply-high by bv_sect_magic(stride)
+    uint64_t emu_sect_div(uint32_t stride, uint64_t key)
+    {
+        return __umul64hi(key, bv_sect_magic(stride));
+    }
+    uint32_t emu_sect_stride(uint64_t args, uint64_t nbits)
+    {
+        return bv_sect_stride(args, nbits);
+    }
     uint32_t emu_sel64(uint64_t x, uint32_t k)
     {
         return sel64(x, k);

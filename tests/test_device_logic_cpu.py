@@ -31,6 +31,10 @@ def emu():
     L.emu_select.argtypes = [vp, u64, ctypes.c_int, u32, u32, u32, vp, u64, vp]
     L.emu_select_sectors.argtypes = [vp, u64, ctypes.c_int, u32, vp, u64, vp]
     L.emu_select_sectors.restype = ctypes.c_int64
+    L.emu_sect_div.argtypes = [u32, u64]
+    L.emu_sect_div.restype = u64
+    L.emu_sect_stride.argtypes = [u64, u64]
+    L.emu_sect_stride.restype = u32
     L.emu_sel64.argtypes = [u64, u32]
     L.emu_sel64.restype = u32
     return L
@@ -106,6 +110,23 @@ def test_device_select_logic(emu, oracle, log_s, interp):
             assert (out == ob.select(q, b)).all(), (cid, b, log_s, interp)
             checked += len(q)
     assert checked > 100000
+
+
+def test_select_sector_stride_and_division(emu):
+    """The sector index of a query is key / stride by one multiply-high (bv_sect_magic): exact for every stride the
+    library can pick and every key a 2^36-bit vector can produce; the stride itself follows the density."""
+    rng = np.random.default_rng(8)
+    keys = [0, 1, 2**32 - 1, 2**32, 2**36 - 1, 2**40] + [int(x) for x in rng.integers(0, 2**36, 300, dtype=np.uint64)]
+    for stride in list(range(8, 209)) + [2, 3, 7, 255, 256, 1000]:
+        edge = [stride * k + d for k in (1, 12345, 2**30 // stride) for d in (-1, 0, 1)]
+        for key in keys + edge:
+            assert emu.emu_sect_div(stride, key) == key // stride, (stride, key)
+    n = 1 << 33
+    assert emu.emu_sect_stride(n // 2, n) == 81 and emu.emu_sect_stride(n // 4, n) == 34  # the measured optimum at density 1/2
+    assert emu.emu_sect_stride(n // 50, n) == 0 and emu.emu_sect_stride(0, n) == 0        # too sparse for sectors
+    assert 150 <= emu.emu_sect_stride(n, n) <= 208                                         # all ones: as many as a sector holds
+    strides = [emu.emu_sect_stride(int(n * d), n) for d in (0.09, 0.1, 0.2, 0.3, 0.5, 0.7, 0.9)]
+    assert strides == sorted(strides) and strides[0] >= 8
 
 
 @pytest.mark.parametrize("stride", [0, 8, 64, 81, 208])  # 0: the stride the library picks from the density
