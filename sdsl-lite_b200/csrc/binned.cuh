@@ -7,7 +7,7 @@
 // touch one L2-sized chunk of the index:
 //
 //   1. bin_tile_sort_kernel   one CTA per tile of 8192 queries: counting sort of the tile by bin = key >> shift
-//                             (a bin = a contiguous ~24 MB chunk of the index).  Writes, per tile, the 32-bit in-bin
+//                             (a bin = a contiguous 16 - 24 MB chunk of the index, per op: bin_chunk_mib).  Writes, per tile, the 32-bit in-bin
 //                             offsets in bin order (`recs`), every query's slot (`lp`, u16) and the tile's bin
 //                             boundaries (`loff`, u16).  Streaming: 8 B read + 6 B written per query.
 //   2. bin_apply_kernel<Op>   warps take (bin, tile) runs from a global ticket counter in BIN-MAJOR order, so at any
@@ -20,7 +20,9 @@
 // No global sort, no scan across tiles; deterministic results.  ~22 B per query of extra coalesced streams next to
 // the 16 B of query + result every path moves.  (Storing rank results as u32 differences to the bin's first rank
 // halves two of those streams but the un-sort then needs the bin of every slot; measured, it gains nothing:
-// profiles/r01d_binned_v4_relative_*.)
+// profiles/r01d_binned_v4_relative_*; so do u32 answers with bit planes for the high bits, profiles/r02s_*.)
+// The speed of the scheme comes from the number of queries per index line IN ONE BATCH: a batch cut into pieces —
+// sub-batches on two streams to hide a fused NVLink gather, profiles/r02z_fan_sub_batches_n2.jsonl — loses it.
 #pragma once
 #include "internal.h"
 
