@@ -113,7 +113,9 @@ int sdslgpu_kind(const sdslgpu_handle *h, int *kind);
 int sdslgpu_size(const sdslgpu_handle *h, uint64_t *size);
 /* number of b-bits (occurrences of pattern b) in a bit-vector handle (= rank_b(size)); select domain is 1..arg_count */
 int sdslgpu_arg_count(const sdslgpu_handle *h, int b, uint64_t *count);
-/* bytes of device memory held by the handle */
+/* bytes of device memory held by the handle's index structures, including what queries derive on first use (pattern
+ * images, select sectors); NOT counted: the chunk buffers of the host-pointer path (3 slots x 2^22 queries x 32 bytes =
+ * 0.4 GB, allocated by the handle's first call with host pointers; the int_vector<w> path has its own of the same order) */
 int sdslgpu_device_bytes(const sdslgpu_handle *h, uint64_t *bytes);
 
 /* ---- batched queries on bit vectors --------------------------------------------------------- */
