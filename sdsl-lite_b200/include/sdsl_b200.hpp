@@ -212,7 +212,7 @@ public:
         if (!m_image)
         {
             sdslgpu_handle * h = nullptr;
-            check(sdslgpu_bv_create(m_words.data(), m_size, detail::default_device(), SDSLGPU_F_DEFAULT, &h), "bit_vector");
+            check(sdslgpu_bv_create(m_words.data(), m_size, detail::default_device(), m_flags, &h), "bit_vector");
             m_image = detail::adopt(h);
         }
         return m_image.get();
@@ -251,6 +251,18 @@ public:
     {
         return !(*this == o);
     }
+    //! Keep select on its samples instead of letting the first large select batch build select sectors (32 bytes per ~81
+    //! ones of a half-dense vector; select in one gather, 1.25x faster): SDSLGPU_F_COMPACT, see sdslgpu_select in sdslgpu.h.
+    //! Takes effect when the device image is (re)built; never changes a result.
+    void compact_select(bool on = true)
+    {
+        uint32_t const f = on ? SDSLGPU_F_COMPACT : SDSLGPU_F_DEFAULT;
+        if (f != m_flags)
+        {
+            m_flags = f;
+            m_image.reset();
+        }
+    }
     //! how large batches are executed: SDSLGPU_ORDER_AUTO (default) / _DIRECT / _BINNED; never changes a result
     void batch_order(int order) const
     {
@@ -268,6 +280,7 @@ private:
     }
     size_type m_size = 0;
     std::vector<uint64_t> m_words;
+    uint32_t m_flags = SDSLGPU_F_DEFAULT;
     mutable detail::handle_ptr m_image;
 };
 
